@@ -1,0 +1,749 @@
+// api.cu -- the C ABI of libbnkgpu.so (include/bnkgpu.h): workspace, rate categories, column
+// tiling, and the orchestration of the device kernels.  No CPU fallback: every compute entry
+// point returns BNK_ERR_CUDA if the device cannot run it.
+#include "device_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+namespace bnk {
+
+static thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? BNK_ERR_NOMEM : BNK_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    int64_t *acct = nullptr;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); if (acct) *acct -= (int64_t)(cap * sizeof(T)); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = n;
+        if (acct) *acct += (int64_t)(n * sizeof(T));
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p) { cudaFree(p); if (acct) *acct -= (int64_t)(cap * sizeof(T)); }
+        p = nullptr; cap = 0;
+    }
+};
+
+struct Chunk {
+    int cat_lo, cat_hi;    // global category range
+    int tile_lo, tile_hi;  // tiles of this chunk
+    int ncat_max;          // largest category span of one of its tiles
+};
+
+}  // namespace bnk
+
+using namespace bnk;
+
+struct bnk_ws {
+    bnk_model model;
+    const bnk_tree *tree = nullptr;
+    int K = 0, n = 0, n_int = 0, max_cols = 0, device = 0, sm_count = 148, smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0, dev_bytes = 0;
+    int cfg_tile_cols = 0, cfg_cpt = 0;
+    size_t table_budget = (size_t)12 << 30;
+    // static device data
+    DevBuf<double> d_model;  // evec | ievec | eval | prior | logprior
+    DevBuf<UpStep> d_up;
+    DevBuf<DownStep> d_down;
+    DevBuf<ChildRef> d_up_child, d_down_child;
+    DevBuf<int32_t> d_parent, d_node_of_ent, d_leaf_nodes, d_leaf_parent;
+    DevBuf<double> d_dist;
+    std::vector<double> dist;
+    int n_leaves = 0;
+    // rates / categories / tiles
+    int ncols = -1;  // columns of the current rate assignment
+    bool identity_perm = true;
+    std::vector<double> cat_rate;
+    std::vector<int32_t> orig_col, col_cat_global, cat_of_col;
+    std::vector<TileDesc> tiles;
+    std::vector<Chunk> chunks;
+    int tile_cols = 0, cpt = 1, ncg = 0, threads = 0;
+    DevBuf<double> d_cat_rate;
+    DevBuf<int32_t> d_orig_col, d_col_cat, d_cat_of_col, d_qrow, d_flag;
+    DevBuf<TileDesc> d_tiles;
+    bool tables_log_valid = false, tables_lin_valid = false;  // only meaningful with a single chunk
+    // buffers
+    DevBuf<double> d_P, d_PT, d_L, d_LT, d_spill, d_msg, d_logl, d_post, d_sum;
+    DevBuf<uint8_t> d_obs_in, d_present_in, d_obs_s, d_present_s, d_ptr, d_kind, d_kindm, d_state;
+    cudaEvent_t ev[5][2] = {};
+    bool ev_valid[5] = {false, false, false, false, false};
+    ModelDev md() const
+    {
+        const double *b = d_model.p;
+        return ModelDev{b, b + K * K, b + 2 * K * K, b + 2 * K * K + K, b + 2 * K * K + 2 * K, K};
+    }
+};
+
+// --------------------------------------------------------------------------------------
+extern "C" const char *bnk_last_error(void) { return g_err.c_str(); }
+extern "C" const char *bnk_version(void) { return "bnkgpu 0.1 (sm_100a)"; }
+
+extern "C" int bnk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(BNK_ERR_CUDA, "no CUDA runtime / device"); }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
+        if (major == 10) ok++;
+    }
+    return ok;
+}
+
+extern "C" int bnk_model_create(const char *name, const double *F, bnk_model **out) { return model_by_name(name, F, out); }
+extern "C" int bnk_model_create_custom(int K, const double *F, const double *IRM, int symmetric, int normalise, bnk_model **out)
+{
+    return model_from_rates(K, F, IRM, symmetric != 0, normalise != 0, out);
+}
+extern "C" int bnk_model_create_from_eigen(int K, const double *F, const double *evec, const double *ievec,
+                                           const double *eval, bnk_model **out)
+{
+    return model_from_eigen(K, F, evec, ievec, eval, out);
+}
+extern "C" void bnk_model_destroy(bnk_model *m) { delete m; }
+extern "C" int bnk_model_nstates(const bnk_model *m) { return m ? m->K : fail(BNK_ERR_ARG, "model: null"); }
+extern "C" int bnk_model_get(const bnk_model *m, double *R, double *evec, double *ievec, double *eval, double *F, double *prior)
+{
+    if (!m) return fail(BNK_ERR_ARG, "model: null");
+    const int K = m->K;
+    if (R) {
+        if (!m->has_R) return fail(BNK_ERR_STATE, "model: created from an eigensystem, no rate matrix kept");
+        std::memcpy(R, m->R, sizeof(double) * K * K);
+    }
+    if (evec) std::memcpy(evec, m->evec, sizeof(double) * K * K);
+    if (ievec) std::memcpy(ievec, m->ievec, sizeof(double) * K * K);
+    if (eval) std::memcpy(eval, m->eval, sizeof(double) * K);
+    if (F) std::memcpy(F, m->F, sizeof(double) * K);
+    if (prior) std::memcpy(prior, m->prior, sizeof(double) * K);
+    return BNK_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// workspace
+// --------------------------------------------------------------------------------------
+template <typename T>
+static int upload(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st)
+{
+    CUDA_TRY(b.ensure(v.size() ? v.size() : 1));
+    if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return BNK_OK;
+}
+
+#define TRY(expr)                       \
+    do {                                \
+        int rc_ = (expr);               \
+        if (rc_ != BNK_OK) return rc_;  \
+    } while (0)
+
+static void ws_free(bnk_ws *ws)
+{
+    if (!ws) return;
+    cudaSetDevice(ws->device);
+    if (ws->stream) cudaStreamSynchronize(ws->stream);
+    DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
+                            &ws->d_spill, &ws->d_msg, &ws->d_logl, &ws->d_post, &ws->d_sum};
+    for (auto *b : dd) b->release();
+    DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
+                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state};
+    for (auto *b : db) b->release();
+    DevBuf<int32_t> *di[] = {&ws->d_parent, &ws->d_node_of_ent, &ws->d_leaf_nodes, &ws->d_leaf_parent,
+                             &ws->d_orig_col, &ws->d_col_cat, &ws->d_cat_of_col, &ws->d_qrow, &ws->d_flag};
+    for (auto *b : di) b->release();
+    ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
+    for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
+    if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
+    delete ws;
+}
+
+extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_cols, int device, void *stream, bnk_ws **out)
+{
+    if (!m || !t || !out || max_cols < 1) return fail(BNK_ERR_ARG, "ws: bad argument");
+    if (m->K != 20 && m->K != 4) return fail(BNK_ERR_MODEL, "ws: device kernels exist for 20- and 4-state models, got %d", m->K);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BNK_ERR_CUDA, "ws: no CUDA device visible (libbnkgpu has no CPU fallback)");
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    int major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(BNK_ERR_CUDA, "ws: device %d is sm_%dx; libbnkgpu is built for sm_100a only", device, major);
+    bnk_ws *ws = new (std::nothrow) bnk_ws();
+    if (!ws) return fail(BNK_ERR_NOMEM, "ws: out of host memory");
+    ws->model = *m;
+    ws->tree = t;
+    ws->K = m->K; ws->n = t->n; ws->n_int = t->n_int; ws->max_cols = max_cols; ws->device = device;
+    cudaDeviceGetAttribute(&ws->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ws->smem_optin = walk_max_smem_optin(device);
+    if (stream) ws->stream = (cudaStream_t)stream;
+    else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ws; return fail(BNK_ERR_CUDA, "ws: cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        ws->own_stream = true;
+    }
+    for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
+    // accounting hooks
+    DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
+                            &ws->d_spill, &ws->d_msg, &ws->d_logl, &ws->d_post, &ws->d_sum};
+    for (auto *b : dd) b->acct = &ws->dev_bytes;
+    DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
+                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state};
+    for (auto *b : db) b->acct = &ws->dev_bytes;
+
+    const int K = ws->K;
+    std::vector<double> mh(2 * K * K + 3 * K, 0.0);
+    std::memcpy(&mh[0], m->evec, sizeof(double) * K * K);
+    std::memcpy(&mh[K * K], m->ievec, sizeof(double) * K * K);
+    std::memcpy(&mh[2 * K * K], m->eval, sizeof(double) * K);
+    std::memcpy(&mh[2 * K * K + K], m->prior, sizeof(double) * K);
+    std::vector<int32_t> leaf_nodes, leaf_parent;
+    for (int32_t v = 0; v < t->n; v++)
+        if (t->ent_of_node[v] < 0) { leaf_nodes.push_back(v); leaf_parent.push_back(t->parent[v]); }
+    ws->n_leaves = (int)leaf_nodes.size();
+    ws->dist = t->dist;
+    int rc = BNK_OK;
+    auto step = [&](int r) { if (rc == BNK_OK) rc = r; };
+    step(upload(ws->d_model, mh, ws->stream));
+    step(upload(ws->d_up, t->up, ws->stream));
+    step(upload(ws->d_down, t->down, ws->stream));
+    step(upload(ws->d_up_child, t->up_child, ws->stream));
+    step(upload(ws->d_down_child, t->down_child, ws->stream));
+    step(upload(ws->d_parent, t->parent, ws->stream));
+    step(upload(ws->d_node_of_ent, t->node_of_ent, ws->stream));
+    step(upload(ws->d_leaf_nodes, leaf_nodes, ws->stream));
+    step(upload(ws->d_leaf_parent, leaf_parent, ws->stream));
+    step(upload(ws->d_dist, ws->dist, ws->stream));
+    if (rc == BNK_OK && ws->d_flag.ensure(1) != cudaSuccess) rc = fail(BNK_ERR_NOMEM, "ws: device allocation failed");
+    if (rc == BNK_OK && ws->d_sum.ensure(1) != cudaSuccess) rc = fail(BNK_ERR_NOMEM, "ws: device allocation failed");
+    if (rc == BNK_OK) {
+        launch_log_prior(ws->md().prior, const_cast<double *>(ws->md().logprior), K, ws->stream);
+        ws->launches++;
+        cudaError_t e = cudaStreamSynchronize(ws->stream);
+        if (e != cudaSuccess) rc = fail(BNK_ERR_CUDA, "ws: initialisation failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != BNK_OK) { ws_free(ws); return rc; }
+    *out = ws;
+    return BNK_OK;
+}
+
+extern "C" void bnk_ws_destroy(bnk_ws *ws) { ws_free(ws); }
+
+extern "C" int bnk_ws_sync(bnk_ws *ws)
+{
+    if (!ws) return fail(BNK_ERR_ARG, "ws: null");
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    return BNK_OK;
+}
+
+extern "C" int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread)
+{
+    if (!ws) return fail(BNK_ERR_ARG, "ws: null");
+    if (cols_per_thread != 0 && cols_per_thread != 1 && cols_per_thread != 2 && cols_per_thread != 4)
+        return fail(BNK_ERR_ARG, "ws: cols_per_thread must be 0 (auto), 1, 2 or 4");
+    if (ws->K == 4 && cols_per_thread > 1) return fail(BNK_ERR_ARG, "ws: 4-state kernels are built with 1 column per thread");
+    if (tile_cols < 0) return fail(BNK_ERR_ARG, "ws: tile_cols < 0");
+    ws->cfg_tile_cols = tile_cols;
+    ws->cfg_cpt = cols_per_thread;
+    ws->ncols = -1;  // tiles are rebuilt by the next bnk_set_rates
+    return BNK_OK;
+}
+
+extern "C" int64_t bnk_ws_launch_count(const bnk_ws *ws) { return ws ? ws->launches : 0; }
+extern "C" int64_t bnk_ws_device_bytes(const bnk_ws *ws) { return ws ? ws->dev_bytes : 0; }
+
+extern "C" int bnk_ws_phase_ms(bnk_ws *ws, int phase, float *ms)
+{
+    if (!ws || !ms || phase < 0 || phase > 4) return fail(BNK_ERR_ARG, "phase_ms: bad argument");
+    if (!ws->ev_valid[phase]) { *ms = 0.f; return BNK_OK; }
+    CUDA_TRY(cudaEventElapsedTime(ms, ws->ev[phase][0], ws->ev[phase][1]));
+    return BNK_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// rates -> categories -> sorted columns -> tiles -> chunks
+// --------------------------------------------------------------------------------------
+static const int MAXCAT_TILE = 4;
+
+extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
+{
+    if (!ws || n_cols < 0) return fail(BNK_ERR_ARG, "set_rates: bad argument");
+    if (n_cols > ws->max_cols) return fail(BNK_ERR_ARG, "set_rates: n_cols %d exceeds the workspace's max_cols %d", n_cols, ws->max_cols);
+    if (rates)
+        for (int32_t c = 0; c < n_cols; c++)
+            if (!(rates[c] >= 0.0) || std::isinf(rates[c])) return fail(BNK_ERR_ARG, "set_rates: rate[%d] is negative or not finite", c);
+    CUDA_TRY(cudaSetDevice(ws->device));
+    const int K = ws->K;
+    // distinct rates, ascending; columns sorted by (rate, index)
+    ws->orig_col.resize(n_cols);
+    for (int32_t c = 0; c < n_cols; c++) ws->orig_col[c] = c;
+    ws->cat_rate.clear();
+    ws->col_cat_global.assign(n_cols, 0);
+    ws->cat_of_col.assign(n_cols, 0);
+    ws->identity_perm = true;
+    if (rates && n_cols > 0) {
+        std::stable_sort(ws->orig_col.begin(), ws->orig_col.end(), [&](int32_t a, int32_t b) { return rates[a] < rates[b]; });
+        for (int32_t c = 0; c < n_cols; c++) {
+            const double r = rates[ws->orig_col[c]];
+            if (ws->cat_rate.empty() || r != ws->cat_rate.back()) ws->cat_rate.push_back(r);
+            ws->col_cat_global[c] = (int32_t)ws->cat_rate.size() - 1;
+            ws->cat_of_col[ws->orig_col[c]] = ws->col_cat_global[c];
+            if (ws->orig_col[c] != c) ws->identity_perm = false;
+        }
+    } else {
+        ws->cat_rate.push_back(1.0);  // PhyloBN.DEFAULT_RATE (Prediction.java:615-618)
+    }
+    const int ncat = (int)ws->cat_rate.size();
+    // thread / tile geometry
+    int cpt = ws->cfg_cpt ? ws->cfg_cpt : 1;
+    int tc = ws->cfg_tile_cols;
+    const int max_threads = 768;
+    const int tc_cap = (max_threads / K) * cpt;
+    if (tc <= 0) {
+        const int target_tiles = ws->sm_count * 2;
+        tc = (n_cols + target_tiles - 1) / target_tiles;
+        if (tc < 4) tc = 4;
+    }
+    if (tc > tc_cap) tc = tc_cap;
+    if (tc < 1) tc = 1;
+    ws->tile_cols = tc; ws->cpt = cpt;
+    ws->ncg = (tc + cpt - 1) / cpt;
+    ws->threads = ((ws->ncg * K + 31) / 32) * 32;
+    // tiles: big categories are split evenly; small ones are packed together (<= MAXCAT_TILE per tile)
+    ws->tiles.clear();
+    std::vector<int> cat_begin(ncat + 1, 0);
+    for (int32_t c = 0; c < n_cols; c++) cat_begin[ws->col_cat_global[c] + 1]++;
+    for (int k = 0; k < ncat; k++) cat_begin[k + 1] += cat_begin[k];
+    // chunks of categories bounded by the table budget
+    const size_t per_cat = (size_t)ws->n * K * K * sizeof(double) * 2;
+    int cats_per_chunk = (int)std::max<size_t>(1, ws->table_budget / std::max<size_t>(per_cat, 1));
+    if (cats_per_chunk > 60000) cats_per_chunk = 60000;
+    ws->chunks.clear();
+    for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
+        const int hi = std::min(ncat, lo + cats_per_chunk);
+        Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
+        TileDesc cur{0, 0, 0, 0};
+        auto close = [&]() { if (cur.ncols > 0) { ws->tiles.push_back(cur); ck.ncat_max = std::max(ck.ncat_max, cur.ncat); } cur = TileDesc{0, 0, 0, 0}; };
+        for (int k = lo; k < hi; k++) {
+            const int nc = cat_begin[k + 1] - cat_begin[k];
+            if (nc == 0) continue;
+            if (nc * 2 >= tc) {
+                close();
+                const int nt = (nc + tc - 1) / tc;
+                for (int q = 0; q < nt; q++) {
+                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                    ws->tiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+                }
+            } else {
+                if (cur.ncols > 0 && (cur.ncols + nc > tc || cur.ncat >= MAXCAT_TILE || cur.col0 + cur.ncols != cat_begin[k])) close();
+                if (cur.ncols == 0) { cur.col0 = cat_begin[k]; cur.cat0 = k - lo; }
+                cur.ncols += nc;
+                cur.ncat = (k - lo) - cur.cat0 + 1;
+            }
+        }
+        close();
+        ck.tile_hi = (int)ws->tiles.size();
+        if (ck.tile_hi > ck.tile_lo) ws->chunks.push_back(ck);
+    }
+    // chunk-local category per sorted column
+    std::vector<int32_t> col_cat_local(n_cols);
+    for (const Chunk &ck : ws->chunks)
+        for (int tI = ck.tile_lo; tI < ck.tile_hi; tI++) {
+            const TileDesc &td = ws->tiles[tI];
+            for (int c = td.col0; c < td.col0 + td.ncols; c++) col_cat_local[c] = ws->col_cat_global[c] - ck.cat_lo;
+        }
+    TRY(upload(ws->d_cat_rate, ws->cat_rate, ws->stream));
+    TRY(upload(ws->d_orig_col, ws->orig_col, ws->stream));
+    TRY(upload(ws->d_col_cat, col_cat_local, ws->stream));
+    TRY(upload(ws->d_cat_of_col, ws->cat_of_col, ws->stream));
+    TRY(upload(ws->d_tiles, ws->tiles, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
+    ws->ncols = n_cols;
+    ws->tables_log_valid = ws->tables_lin_valid = false;
+    return BNK_OK;
+}
+
+extern "C" int bnk_set_distances(bnk_ws *ws, const double *dist)
+{
+    if (!ws || !dist) return fail(BNK_ERR_ARG, "set_distances: bad argument");
+    for (int32_t i = 0; i < ws->n; i++)
+        if (ws->tree->parent[i] >= 0 && !(dist[i] >= 0.0)) return fail(BNK_ERR_TREE, "set_distances: distance[%d] is negative or NaN", i);
+    CUDA_TRY(cudaSetDevice(ws->device));
+    ws->dist.assign(dist, dist + ws->n);
+    CUDA_TRY(cudaMemcpyAsync(ws->d_dist.p, ws->dist.data(), sizeof(double) * ws->n, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    ws->tables_log_valid = ws->tables_lin_valid = false;
+    return BNK_OK;
+}
+
+extern "C" int bnk_probs(bnk_ws *ws, int32_t n_t, const double *t, double *P, double *logP)
+{
+    if (!ws || !t || n_t < 1) return fail(BNK_ERR_ARG, "probs: bad argument");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    const int KK = ws->K * ws->K;
+    DevBuf<double> dt, dP, dL, dr;
+    int rc = BNK_OK;
+    auto body = [&]() -> int {
+        CUDA_TRY(dt.ensure(n_t));
+        CUDA_TRY(dr.ensure(1));
+        if (P) CUDA_TRY(dP.ensure((size_t)n_t * KK));
+        if (logP) CUDA_TRY(dL.ensure((size_t)n_t * KK));
+        const double one = 1.0;
+        CUDA_TRY(cudaMemcpyAsync(dt.p, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, ws->stream));
+        CUDA_TRY(cudaMemcpyAsync(dr.p, &one, sizeof(double), cudaMemcpyHostToDevice, ws->stream));
+        TableSet ts{dP.p, nullptr, dL.p, nullptr};
+        launch_build_tables(ws->K, ws->md(), dt.p, nullptr, dr.p, n_t, 1, ts, ws->stream);
+        ws->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (P) CUDA_TRY(cudaMemcpyAsync(P, dP.p, sizeof(double) * n_t * KK, cudaMemcpyDeviceToHost, ws->stream));
+        if (logP) CUDA_TRY(cudaMemcpyAsync(logP, dL.p, sizeof(double) * n_t * KK, cudaMemcpyDeviceToHost, ws->stream));
+        CUDA_TRY(cudaStreamSynchronize(ws->stream));
+        return BNK_OK;
+    };
+    rc = body();
+    dt.release(); dP.release(); dL.release(); dr.release();
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------
+// run helpers
+// --------------------------------------------------------------------------------------
+static int ensure_rates(bnk_ws *ws, int32_t n_cols)
+{
+    if (n_cols < 1) return fail(BNK_ERR_ARG, "n_cols must be >= 1");
+    if (ws->ncols < 0) return bnk_set_rates(ws, n_cols, nullptr);
+    if (ws->ncols != n_cols)
+        return fail(BNK_ERR_STATE, "n_cols = %d but rates were set for %d columns (call bnk_set_rates first)", n_cols, ws->ncols);
+    return BNK_OK;
+}
+
+// decides FAST vs GENERAL kernels and produces the category-sorted copies of the inputs
+static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_present, bool &general,
+                          const uint8_t *&obs_s, const uint8_t *&present_s)
+{
+    const int n = ws->n, nc = ws->ncols;
+    general = d_present != nullptr;
+    if (!general && ws->n_int > 0) {
+        int32_t flag = 0;
+        CUDA_TRY(cudaMemsetAsync(ws->d_flag.p, 0, sizeof(int32_t), ws->stream));
+        CUDA_TRY(launch_scan_internal_obs(d_obs, ws->d_node_of_ent.p, ws->n_int, nc, ws->d_flag.p, ws->stream));
+        ws->launches++;
+        CUDA_TRY(cudaMemcpyAsync(&flag, ws->d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->stream));
+        CUDA_TRY(cudaStreamSynchronize(ws->stream));
+        general = flag != 0;
+    }
+    obs_s = d_obs; present_s = d_present;
+    if (!ws->identity_perm) {
+        CUDA_TRY(ws->d_obs_s.ensure((size_t)n * nc));
+        CUDA_TRY(launch_gather_cols(d_obs, ws->d_obs_s.p, ws->d_orig_col.p, n, nc, ws->stream));
+        ws->launches++;
+        obs_s = ws->d_obs_s.p;
+        if (d_present) {
+            CUDA_TRY(ws->d_present_s.ensure((size_t)n * nc));
+            CUDA_TRY(launch_gather_cols(d_present, ws->d_present_s.p, ws->d_orig_col.p, n, nc, ws->stream));
+            ws->launches++;
+            present_s = ws->d_present_s.p;
+        }
+    }
+    return BNK_OK;
+}
+
+static int build_tables(bnk_ws *ws, const Chunk &ck, bool log_space)
+{
+    const int K = ws->K, KK = K * K, ncat = ck.cat_hi - ck.cat_lo;
+    const size_t elems = (size_t)ncat * ws->n * KK;
+    const bool single = ws->chunks.size() == 1;
+    bool &valid = log_space ? ws->tables_log_valid : ws->tables_lin_valid;
+    if (single && valid) return BNK_OK;
+    TableSet ts{nullptr, nullptr, nullptr, nullptr};
+    if (log_space) {
+        CUDA_TRY(ws->d_L.ensure(elems));
+        CUDA_TRY(ws->d_LT.ensure(elems));
+        ts.L = ws->d_L.p; ts.LT = ws->d_LT.p;
+    } else {
+        CUDA_TRY(ws->d_P.ensure(elems));
+        CUDA_TRY(ws->d_PT.ensure(elems));
+        ts.P = ws->d_P.p; ts.PT = ws->d_PT.p;
+    }
+    CUDA_TRY(cudaEventRecord(ws->ev[0][0], ws->stream));
+    launch_build_tables(K, ws->md(), ws->d_dist.p, ws->d_parent.p, ws->d_cat_rate.p + ck.cat_lo, ws->n, ncat, ts, ws->stream);
+    ws->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ws->ev[0][1], ws->stream));
+    ws->ev_valid[0] = true;
+    valid = single;
+    return BNK_OK;
+}
+
+struct WalkSetup {
+    WalkArgs a;
+    WalkLaunch wl;
+};
+
+static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_needed, const uint8_t *obs_s,
+                      const uint8_t *present_s, WalkSetup &s)
+{
+    const int K = ws->K;
+    std::memset(&s.a, 0, sizeof(s.a));
+    const bnk_tree *t = ws->tree;
+    s.a.up = ws->d_up.p; s.a.down = ws->d_down.p;
+    s.a.up_child = ws->d_up_child.p; s.a.down_child = ws->d_down_child.p;
+    s.a.n_steps = t->n_int;
+    s.a.tiles = ws->d_tiles.p + ck.tile_lo;
+    s.a.ncg = ws->ncg;
+    s.a.ncat_max = ck.ncat_max;
+    s.a.obs = obs_s; s.a.present = present_s;
+    s.a.ncols = ws->ncols; s.a.n_nodes = ws->n;
+    s.a.orig_col = ws->d_orig_col.p; s.a.col_cat = ws->d_col_cat.p;
+    // stack slots: as many as fit in shared memory, the rest spill to global memory
+    const size_t base = walk_smem_bytes(K, ws->cpt, ws->ncg, ck.ncat_max, 0);
+    const size_t per_slot = sizeof(double) * (size_t)ws->ncg * ws->cpt * K;
+    const size_t budget = (size_t)ws->smem_optin;
+    if (base > budget) return fail(BNK_ERR_ARG, "tile of %d columns x %d categories does not fit shared memory", ws->tile_cols, ck.ncat_max);
+    int smem_slots = (int)std::min<size_t>((size_t)slots_needed, (budget - base) / per_slot);
+    s.a.smem_slots = smem_slots;
+    if (slots_needed > smem_slots) {
+        CUDA_TRY(ws->d_spill.ensure((size_t)(slots_needed - smem_slots) * ws->ncols * K));
+        s.a.spill = ws->d_spill.p;
+    }
+    s.wl.K = K; s.wl.cpt = ws->cpt; s.wl.threads = ws->threads; s.wl.n_tiles = ck.tile_hi - ck.tile_lo;
+    s.wl.general = general; s.wl.stream = ws->stream;
+    s.wl.smem_bytes = base + per_slot * smem_slots;
+    return BNK_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// joint
+// --------------------------------------------------------------------------------------
+extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present, uint8_t *d_out_state)
+{
+    if (!ws || !d_obs || !d_out_state) return fail(BNK_ERR_ARG, "joint: null argument");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    TRY(ensure_rates(ws, n_cols));
+    const int K = ws->K, nc = ws->ncols;
+    bool general;
+    const uint8_t *obs_s, *present_s;
+    TRY(prepare_inputs(ws, d_obs, d_present, general, obs_s, present_s));
+    if (ws->n_int > 0) {
+        CUDA_TRY(ws->d_ptr.ensure((size_t)ws->n_int * nc * K));
+        CUDA_TRY(ws->d_kind.ensure((size_t)ws->n_int * nc));
+    }
+    for (size_t ci = 0; ci < ws->chunks.size(); ci++) {
+        const Chunk &ck = ws->chunks[ci];
+        TRY(build_tables(ws, ck, true));
+        if (ws->n_int > 0) {
+            WalkSetup s;
+            TRY(setup_walk(ws, ck, general, ws->tree->up_slots, obs_s, present_s, s));
+            s.a.T_row = ws->d_L.p; s.a.T_col = ws->d_LT.p; s.a.prior = ws->md().logprior;
+            s.a.ptr = ws->d_ptr.p; s.a.kind = ws->d_kind.p;
+            CUDA_TRY(cudaEventRecord(ws->ev[1][0], ws->stream));
+            CUDA_TRY(launch_joint_up(s.wl, s.a));
+            ws->launches++;
+            CUDA_TRY(cudaEventRecord(ws->ev[1][1], ws->stream));
+            ws->ev_valid[1] = true;
+        }
+        TracebackArgs ta;
+        std::memset(&ta, 0, sizeof(ta));
+        ta.down = ws->d_down.p; ta.n_steps = ws->n_int; ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
+        ta.ptr = ws->d_ptr.p; ta.kind = ws->d_kind.p; ta.obs = d_obs; ta.present = d_present;
+        ta.out_state = d_out_state; ta.tb_slots = ws->tree->tb_slots;
+        ta.leaf_nodes = ws->d_leaf_nodes.p; ta.leaf_parent = ws->d_leaf_parent.p; ta.n_leaves = ws->n_leaves;
+        ta.L = ws->d_L.p;
+        ta.cat_of_col = ws->d_cat_of_col.p; ta.cat_lo = ck.cat_lo; ta.cat_hi = ck.cat_hi;
+        CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
+        if (ws->n_int > 0) { CUDA_TRY(launch_traceback(ta, ws->stream)); ws->launches++; }
+        CUDA_TRY(launch_leaf_states(ta, ws->stream));
+        ws->launches++;
+        CUDA_TRY(cudaEventRecord(ws->ev[2][1], ws->stream));
+        ws->ev_valid[2] = true;
+    }
+    return BNK_OK;
+}
+
+extern "C" int bnk_joint(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present, uint8_t *out_state)
+{
+    if (!ws || !obs || !out_state) return fail(BNK_ERR_ARG, "joint: null argument");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    TRY(ensure_rates(ws, n_cols));
+    const size_t bytes = (size_t)ws->n * n_cols;
+    CUDA_TRY(ws->d_obs_in.ensure(bytes));
+    CUDA_TRY(ws->d_state.ensure(bytes));
+    CUDA_TRY(cudaMemcpyAsync(ws->d_obs_in.p, obs, bytes, cudaMemcpyHostToDevice, ws->stream));
+    if (present) {
+        CUDA_TRY(ws->d_present_in.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(ws->d_present_in.p, present, bytes, cudaMemcpyHostToDevice, ws->stream));
+    }
+    TRY(bnk_joint_dev(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, ws->d_state.p));
+    CUDA_TRY(cudaMemcpyAsync(out_state, ws->d_state.p, bytes, cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    return BNK_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// marginal / log-likelihood
+// --------------------------------------------------------------------------------------
+static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present, const int32_t *query_nodes,
+                   int32_t n_query, double *d_out_post, double *d_out_logl, double *d_out_sum)
+{
+    CUDA_TRY(cudaSetDevice(ws->device));
+    TRY(ensure_rates(ws, n_cols));
+    const bnk_tree *t = ws->tree;
+    const int K = ws->K, nc = ws->ncols;
+    const bool want_post = d_out_post != nullptr;
+    for (int32_t v = 0; v < t->n; v++)
+        if (t->first[v + 1] - t->first[v] > 16)
+            return fail(BNK_ERR_TREE, "sum-product kernels handle at most 16 children per node (node %d has %d)", v, t->first[v + 1] - t->first[v]);
+    // query rows
+    std::vector<int32_t> qrow(std::max(ws->n_int, 1), -1);
+    if (want_post) {
+        if (n_query < 0) {
+            for (int32_t e = 0; e < ws->n_int; e++) qrow[e] = e;
+        } else {
+            if (!query_nodes && n_query > 0) return fail(BNK_ERR_ARG, "marginal: query_nodes is null");
+            for (int32_t q = 0; q < n_query; q++) {
+                const int32_t v = query_nodes[q];
+                if (v < 0 || v >= t->n) return fail(BNK_ERR_QUERY, "marginal: query node %d is not a node of the tree", v);
+                if (t->ent_of_node[v] >= 0) {
+                    if (qrow[t->ent_of_node[v]] >= 0) return fail(BNK_ERR_QUERY, "marginal: node %d queried twice", v);
+                    qrow[t->ent_of_node[v]] = q;
+                } else {  // childless node: no posterior is produced (NaN row)
+                    CUDA_TRY(launch_fill_f64(d_out_post + (size_t)q * nc * K, (size_t)nc * K, NAN, ws->stream));
+                    ws->launches++;
+                }
+            }
+        }
+        TRY(upload(ws->d_qrow, qrow, ws->stream));
+    }
+    bool general;
+    const uint8_t *obs_s, *present_s;
+    TRY(prepare_inputs(ws, d_obs, d_present, general, obs_s, present_s));
+    double *logl = d_out_logl;
+    if (!logl && d_out_sum) { CUDA_TRY(ws->d_logl.ensure(nc)); logl = ws->d_logl.p; }
+    if (want_post && ws->n_int > 0) {
+        CUDA_TRY(ws->d_msg.ensure((size_t)ws->n_int * nc * K));
+        if (general) CUDA_TRY(ws->d_kindm.ensure((size_t)ws->n_int * nc));
+    }
+    if (logl && ws->n_int == 0) { CUDA_TRY(launch_fill_f64(logl, nc, 0.0, ws->stream)); ws->launches++; }
+    for (size_t ci = 0; ci < ws->chunks.size() && ws->n_int > 0; ci++) {
+        const Chunk &ck = ws->chunks[ci];
+        TRY(build_tables(ws, ck, false));
+        WalkSetup s;
+        TRY(setup_walk(ws, ck, general, std::max(t->up_slots, want_post ? t->down_slots : 0), obs_s, present_s, s));
+        s.a.T_row = ws->d_P.p; s.a.T_col = ws->d_PT.p; s.a.prior = ws->md().prior;
+        s.a.msg = want_post ? ws->d_msg.p : nullptr;
+        s.a.kindm = (want_post && general) ? ws->d_kindm.p : nullptr;
+        s.a.out_logl = logl;
+        CUDA_TRY(cudaEventRecord(ws->ev[3][0], ws->stream));
+        CUDA_TRY(launch_sum_up(s.wl, s.a));
+        ws->launches++;
+        CUDA_TRY(cudaEventRecord(ws->ev[3][1], ws->stream));
+        ws->ev_valid[3] = true;
+        if (want_post) {
+            s.a.T_row = ws->d_PT.p;
+            s.a.out_post = d_out_post;
+            s.a.qrow = ws->d_qrow.p;
+            CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
+            CUDA_TRY(launch_sum_down(s.wl, s.a));
+            ws->launches++;
+            CUDA_TRY(cudaEventRecord(ws->ev[4][1], ws->stream));
+            ws->ev_valid[4] = true;
+        }
+    }
+    if (d_out_sum) { CUDA_TRY(launch_sum_f64(logl, nc, d_out_sum, ws->stream)); ws->launches++; }
+    if (want_post) CUDA_TRY(cudaStreamSynchronize(ws->stream));  // qrow (host vector) was uploaded asynchronously
+    return BNK_OK;
+}
+
+extern "C" int bnk_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present,
+                                const int32_t *query_nodes_host, int32_t n_query, double *d_out_post, double *d_out_logl)
+{
+    if (!ws || !d_obs) return fail(BNK_ERR_ARG, "marginal: null argument");
+    return run_sum(ws, n_cols, d_obs, d_present, query_nodes_host, n_query, d_out_post, d_out_logl, nullptr);
+}
+
+extern "C" int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present,
+                              double *d_out_logl, double *d_out_sum)
+{
+    if (!ws || !d_obs) return fail(BNK_ERR_ARG, "loglik: null argument");
+    return run_sum(ws, n_cols, d_obs, d_present, nullptr, 0, nullptr, d_out_logl, d_out_sum);
+}
+
+static int stage_inputs(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present)
+{
+    const size_t bytes = (size_t)ws->n * n_cols;
+    CUDA_TRY(ws->d_obs_in.ensure(bytes));
+    CUDA_TRY(cudaMemcpyAsync(ws->d_obs_in.p, obs, bytes, cudaMemcpyHostToDevice, ws->stream));
+    if (present) {
+        CUDA_TRY(ws->d_present_in.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(ws->d_present_in.p, present, bytes, cudaMemcpyHostToDevice, ws->stream));
+    }
+    return BNK_OK;
+}
+
+extern "C" int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present,
+                            const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl)
+{
+    if (!ws || !obs) return fail(BNK_ERR_ARG, "marginal: null argument");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    TRY(ensure_rates(ws, n_cols));
+    TRY(stage_inputs(ws, n_cols, obs, present));
+    const int nq = n_query < 0 ? ws->n_int : n_query;
+    const size_t post_elems = (size_t)nq * n_cols * ws->K;
+    if (out_post && post_elems) CUDA_TRY(ws->d_post.ensure(post_elems));
+    if (out_logl) CUDA_TRY(ws->d_logl.ensure(n_cols));
+    TRY(run_sum(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, query_nodes, n_query,
+                (out_post && post_elems) ? ws->d_post.p : nullptr, out_logl ? ws->d_logl.p : nullptr, nullptr));
+    if (out_post && post_elems)
+        CUDA_TRY(cudaMemcpyAsync(out_post, ws->d_post.p, post_elems * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    if (out_logl) CUDA_TRY(cudaMemcpyAsync(out_logl, ws->d_logl.p, sizeof(double) * n_cols, cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    return BNK_OK;
+}
+
+extern "C" int bnk_loglik(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present, double *out_logl, double *out_sum)
+{
+    if (!ws || !obs) return fail(BNK_ERR_ARG, "loglik: null argument");
+    CUDA_TRY(cudaSetDevice(ws->device));
+    TRY(ensure_rates(ws, n_cols));
+    TRY(stage_inputs(ws, n_cols, obs, present));
+    CUDA_TRY(ws->d_logl.ensure(n_cols));
+    TRY(run_sum(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, nullptr, 0, nullptr, ws->d_logl.p,
+                out_sum ? ws->d_sum.p : nullptr));
+    if (out_logl) CUDA_TRY(cudaMemcpyAsync(out_logl, ws->d_logl.p, sizeof(double) * n_cols, cudaMemcpyDeviceToHost, ws->stream));
+    if (out_sum) CUDA_TRY(cudaMemcpyAsync(out_sum, ws->d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    return BNK_OK;
+}

@@ -1,0 +1,105 @@
+// device_common.cuh -- types shared by the CUDA translation units of libbnkgpu.
+#pragma once
+#include "internal.h"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace bnk {
+
+struct ModelDev {  // device pointers
+    const double *evec, *ievec, *eval;  // K*K, K*K, K
+    const double *prior, *logprior;     // K each
+    int K;
+};
+
+// Per (category, node) tables, index ((cat * n_nodes + node) * K + a) * K + b.
+//   P [a][b] = P(child = b | parent = a)      PT[a][b] = P [b][a]
+//   L = log P (fdlibm log, log 0 = -inf)      LT likewise
+struct TableSet {
+    double *P, *PT, *L, *LT;
+};
+
+// A tile = a run of consecutive columns (in category-sorted order) owned by one CTA.
+struct TileDesc {
+    int32_t col0, ncols;  // sorted-space column range
+    int32_t cat0, ncat;   // chunk-local category range covered by those columns
+};
+
+enum : uint8_t { KIND_NONE = 0, KIND_MSG = 1, KIND_ROOT = 2, KIND_OBS = 3 };
+
+struct WalkArgs {
+    // static program
+    const UpStep *up;
+    const DownStep *down;
+    const ChildRef *up_child, *down_child;
+    int32_t n_steps;
+    const TileDesc *tiles;
+    int32_t ncg;       // column groups per CTA (threads = ncg * K, rounded up to a warp)
+    int32_t ncat_max;  // largest TileDesc::ncat
+    // inputs, category-sorted column space, [node][ncols]
+    const uint8_t *obs, *present;  // present == nullptr: everything present
+    int32_t ncols, n_nodes;
+    const int32_t *orig_col;  // sorted -> original column index
+    const int32_t *col_cat;   // sorted column -> chunk-local category
+    // tables of the current category chunk
+    const double *T_row;  // matvec rows: L (joint up), P (sum up), PT (down)
+    const double *T_col;  // lookups [obs][x]: LT (joint), PT (sum up / down)
+    const double *prior;  // log prior (joint) or prior (sum)
+    // message stack: slots < smem_slots live in shared memory, the rest in spill[(slot - smem_slots)][ncols][K]
+    int32_t smem_slots;
+    double *spill;
+    // joint outputs, original column space
+    uint8_t *ptr;   // [n_int][ncols][K] traceback pointers
+    uint8_t *kind;  // [n_int][ncols]
+    // sum-product intermediates, sorted column space
+    double *msg;     // [n_int][ncols][K] scaled up-messages (nullptr: not stored)
+    uint8_t *kindm;  // [n_int][ncols] (GENERAL only)
+    // sum-product outputs, original column space
+    double *out_logl;       // [ncols]
+    double *out_post;       // [n_query][ncols][K]
+    const int32_t *qrow;    // [n_int] -> row of out_post or -1
+};
+
+void launch_build_tables(int K, const ModelDev &md, const double *times, const int32_t *skip,
+                         const double *rates, int n_nodes, int n_cat, const TableSet &ts, cudaStream_t st);
+void launch_log_prior(const double *prior, double *logprior, int K, cudaStream_t st);
+
+struct WalkLaunch {
+    int K, cpt, threads, n_tiles;
+    bool general;
+    size_t smem_bytes;
+    cudaStream_t stream;
+};
+size_t walk_smem_bytes(int K, int cpt, int ncg, int ncat_max, int slots);
+int walk_max_smem_optin(int device);
+cudaError_t launch_joint_up(const WalkLaunch &wl, const WalkArgs &a);
+cudaError_t launch_sum_up(const WalkLaunch &wl, const WalkArgs &a);
+cudaError_t launch_sum_down(const WalkLaunch &wl, const WalkArgs &a);
+
+struct TracebackArgs {
+    const DownStep *down;
+    int32_t n_steps, ncols, n_nodes, K;
+    const uint8_t *ptr, *kind;      // original column space
+    const uint8_t *obs, *present;   // original column space, [node][ncols]
+    uint8_t *out_state;             // [node][ncols]
+    int32_t tb_slots;
+    // childless nodes
+    const int32_t *leaf_nodes, *leaf_parent;
+    int32_t n_leaves;
+    const double *L;                // [cat][node][K*K] for the rare unobserved-leaf case
+    const int32_t *cat_of_col;      // original column -> global category
+    int32_t cat_lo, cat_hi;         // categories of the chunk being processed; other columns are skipped
+};
+cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t st);
+cudaError_t launch_leaf_states(const TracebackArgs &a, cudaStream_t st);
+
+cudaError_t launch_gather_cols(const uint8_t *in, uint8_t *out, const int32_t *orig_col, int n_rows,
+                               int ncols, cudaStream_t st);
+// flag[0] |= 1 if any internal-node row of obs holds an observation
+cudaError_t launch_scan_internal_obs(const uint8_t *obs, const int32_t *node_of_ent, int n_int, int ncols,
+                                     int32_t *flag, cudaStream_t st);
+cudaError_t launch_fill_f64(double *p, size_t n, double v, cudaStream_t st);
+cudaError_t launch_sum_f64(const double *in, int n, double *out, cudaStream_t st);
+
+}  // namespace bnk

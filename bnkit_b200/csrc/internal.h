@@ -1,0 +1,70 @@
+// internal.h -- shared declarations of libbnkgpu (not part of the ABI).
+#pragma once
+#include "../../include/bnkgpu.h"
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#define BNK_MAXK BNK_MAX_STATES
+
+struct bnk_model {
+    int K = 0;
+    bool has_R = true;
+    char name[16] = "custom";
+    double F[BNK_MAXK] = {0}, prior[BNK_MAXK] = {0};
+    double R[BNK_MAXK * BNK_MAXK] = {0};
+    double evec[BNK_MAXK * BNK_MAXK] = {0}, ievec[BNK_MAXK * BNK_MAXK] = {0};
+    double eval[BNK_MAXK] = {0};
+};
+
+namespace bnk {
+
+int fail(int code, const char *fmt, ...);  // records the thread's last error, returns code
+
+int model_from_rates(int K, const double *F, const double *M, bool symmetric, bool normalise, bnk_model **out);
+int model_by_name(const char *name, const double *F_override, bnk_model **out);
+int model_from_eigen(int K, const double *F, const double *evec, const double *ievec,
+                     const double *eval, bnk_model **out);
+
+// One step of the column-tile walk = one internal node (a node with >= 1 child in the
+// static tree).  Childless nodes never get a step: their message is a table lookup made
+// while folding the parent's children.
+struct UpStep {
+    int32_t node;         // tree index
+    int32_t parent;       // tree index or -1
+    int32_t slot;         // message-stack slot receiving this node's message, -1 for the static root
+    int32_t child_begin;  // into the child arrays
+    int32_t n_child;
+    int32_t ent;          // row of this node among internal nodes (index order)
+};
+struct DownStep {
+    int32_t node, parent;
+    int32_t tslot;        // slot holding the from-above vector for this node, -1 for the static root
+    int32_t child_begin, n_child;
+    int32_t ent;
+    int32_t pslot;        // traceback: slot holding the parent's state (-1: none)
+    int32_t oslot;        // traceback: slot receiving this node's state (-1: not needed)
+};
+struct ChildRef {
+    int32_t node;
+    int32_t slot;  // up: stack slot of the child's message; down: slot receiving the child's from-above vector; -1 childless
+    int32_t ent;   // row among internal nodes, -1 if childless
+};
+
+}  // namespace bnk
+
+struct bnk_tree {
+    int32_t n = 0, n_int = 0, root_count = 0;
+    std::vector<int32_t> parent;
+    std::vector<double> dist;
+    std::vector<int32_t> first, kids;  // children CSR in index order (IdxTree.children[])
+    std::vector<int32_t> ent_of_node;  // -1 for childless nodes
+    std::vector<int32_t> node_of_ent;
+    std::vector<bnk::UpStep> up;       // post-order, heavy child first
+    std::vector<bnk::ChildRef> up_child;
+    std::vector<bnk::DownStep> down;   // pre-order, heavy child last
+    std::vector<bnk::ChildRef> down_child;
+    int32_t up_slots = 0, down_slots = 0, tb_slots = 0;
+};

@@ -1,0 +1,288 @@
+"""ctypes binding of libbnkgpu.so (include/bnkgpu.h).
+
+The library is the product; this module only marshals numpy / torch buffers into the C ABI.
+There is no fallback: if the shared library is missing or no B200 is visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libbnkgpu.so")
+_LIB = None
+NONE = 255
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+
+
+class BnkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbnkgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/bnkgpu.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "bnk_last_error", "bnk_version", "bnk_device_count",
+    "bnk_model_create", "bnk_model_create_custom", "bnk_model_create_from_eigen", "bnk_model_destroy",
+    "bnk_model_nstates", "bnk_model_get",
+    "bnk_tree_create", "bnk_tree_destroy", "bnk_tree_size", "bnk_tree_n_internal", "bnk_tree_prune_orphans",
+    "bnk_ws_create", "bnk_ws_destroy", "bnk_ws_sync", "bnk_ws_configure", "bnk_ws_launch_count",
+    "bnk_ws_device_bytes", "bnk_set_rates", "bnk_set_distances", "bnk_probs",
+    "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
+    "bnk_ws_phase_ms",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise ImportError(
+            "bnkit_b200: %s is missing -- build it with `python -m bnkit_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % _SO)
+    L = C.CDLL(_SO)
+    L.bnk_last_error.restype = C.c_char_p
+    L.bnk_version.restype = C.c_char_p
+    L.bnk_model_create.argtypes = [C.c_char_p, _dp, C.POINTER(_vp)]
+    L.bnk_model_create_custom.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.bnk_model_create_from_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.POINTER(_vp)]
+    L.bnk_model_destroy.argtypes = [_vp]
+    L.bnk_model_destroy.restype = None
+    L.bnk_model_nstates.argtypes = [_vp]
+    L.bnk_model_get.argtypes = [_vp] + [_dp] * 6
+    L.bnk_tree_create.argtypes = [C.c_int32, _ip, _dp, C.POINTER(_vp)]
+    L.bnk_tree_destroy.argtypes = [_vp]
+    L.bnk_tree_destroy.restype = None
+    L.bnk_tree_size.argtypes = [_vp]
+    L.bnk_tree_n_internal.argtypes = [_vp]
+    L.bnk_tree_prune_orphans.argtypes = [_vp, C.c_int32, _bp, _bp]
+    L.bnk_ws_create.argtypes = [_vp, _vp, C.c_int32, C.c_int, _vp, C.POINTER(_vp)]
+    L.bnk_ws_destroy.argtypes = [_vp]
+    L.bnk_ws_destroy.restype = None
+    L.bnk_ws_sync.argtypes = [_vp]
+    L.bnk_ws_configure.argtypes = [_vp, C.c_int, C.c_int]
+    L.bnk_ws_launch_count.argtypes = [_vp]
+    L.bnk_ws_launch_count.restype = C.c_int64
+    L.bnk_ws_device_bytes.argtypes = [_vp]
+    L.bnk_ws_device_bytes.restype = C.c_int64
+    L.bnk_set_rates.argtypes = [_vp, C.c_int32, _dp]
+    L.bnk_set_distances.argtypes = [_vp, _dp]
+    L.bnk_probs.argtypes = [_vp, C.c_int32, _dp, _dp, _dp]
+    L.bnk_joint.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
+    L.bnk_marginal.argtypes = [_vp, C.c_int32, _vp, _vp, _ip, C.c_int32, _vp, _vp]
+    L.bnk_loglik.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
+    L.bnk_joint_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
+    L.bnk_marginal_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _ip, C.c_int32, _vp, _vp]
+    L.bnk_loglik_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
+    L.bnk_ws_phase_ms.argtypes = [_vp, C.c_int, C.POINTER(C.c_float)]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise BnkError(rc, lib().bnk_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _ptr(x):
+    """address of a numpy array, a torch tensor (host or device), an int, or None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+class Model:
+    """bnk_model handle <-> bn.ctmc.SubstModel."""
+
+    def __init__(self, name=None, F=None, custom=None, eigen=None):
+        L = lib()
+        h = _vp()
+        self._keep = []
+        if eigen is not None:
+            K, Fe, evec, ievec, ev = eigen
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Fe, evec, ievec, ev)]
+            check(L.bnk_model_create_from_eigen(int(K), *[_d(a) for a in arrs], C.byref(h)))
+        elif custom is not None:
+            K, Fc, M, symmetric, normalise = custom
+            Fc = np.ascontiguousarray(Fc, dtype=np.float64)
+            M = np.ascontiguousarray(M, dtype=np.float64)
+            check(L.bnk_model_create_custom(int(K), _d(Fc), _d(M), int(symmetric), int(normalise), C.byref(h)))
+        else:
+            Fa = None if F is None else np.ascontiguousarray(F, dtype=np.float64)
+            check(L.bnk_model_create(name.encode(), _d(Fa), C.byref(h)))
+        self.h = h
+        self.name = name
+        self.K = L.bnk_model_nstates(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().bnk_model_destroy(self.h)
+            self.h = None
+
+    def parts(self, want_R=True):
+        K = self.K
+        R, ev, iev = (np.zeros((K, K)) for _ in range(3))
+        lam, F, prior = (np.zeros(K) for _ in range(3))
+        check(lib().bnk_model_get(self.h, _d(R) if want_R else None, _d(ev), _d(iev), _d(lam), _d(F), _d(prior)))
+        return dict(R=R if want_R else None, evec=ev, ievec=iev, eval=lam, F=F, prior=prior)
+
+
+class Tree:
+    """bnk_tree handle <-> dat.phylo.IdxTree (parent[] / distance[] arrays)."""
+
+    def __init__(self, parent, dist=None):
+        self.parent = np.ascontiguousarray(parent, dtype=np.int32)
+        self.dist = None if dist is None else np.ascontiguousarray(dist, dtype=np.float64)
+        h = _vp()
+        check(lib().bnk_tree_create(len(self.parent), _i(self.parent), _d(self.dist), C.byref(h)))
+        self.h = h
+        self.n = len(self.parent)
+        self.n_internal = lib().bnk_tree_n_internal(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().bnk_tree_destroy(self.h)
+            self.h = None
+
+    def internal_nodes(self):
+        has_child = np.zeros(self.n, dtype=bool)
+        has_child[self.parent[self.parent >= 0]] = True
+        return np.nonzero(has_child)[0].astype(np.int32)
+
+    def prune_orphans(self, present):
+        present = np.ascontiguousarray(present, dtype=np.uint8)
+        out = np.empty_like(present)
+        check(lib().bnk_tree_prune_orphans(self.h, present.shape[1], present.ctypes.data_as(_bp), out.ctypes.data_as(_bp)))
+        return out
+
+
+class Workspace:
+    """bnk_ws handle: device buffers + stream for one (model, tree)."""
+
+    def __init__(self, model, tree, max_cols, device=-1, stream=None):
+        self.model, self.tree = model, tree  # keep alive
+        h = _vp()
+        check(lib().bnk_ws_create(model.h, tree.h, int(max_cols), int(device), stream, C.byref(h)))
+        self.h = h
+        self.K = model.K
+        self.n = tree.n
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bnk_ws_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def sync(self):
+        check(lib().bnk_ws_sync(self.h))
+
+    def configure(self, tile_cols=0, cols_per_thread=0):
+        check(lib().bnk_ws_configure(self.h, int(tile_cols), int(cols_per_thread)))
+
+    def launch_count(self):
+        return lib().bnk_ws_launch_count(self.h)
+
+    def device_bytes(self):
+        return lib().bnk_ws_device_bytes(self.h)
+
+    def set_rates(self, n_cols, rates=None):
+        r = None if rates is None else np.ascontiguousarray(rates, dtype=np.float64)
+        check(lib().bnk_set_rates(self.h, int(n_cols), _d(r)))
+
+    def set_distances(self, dist):
+        d = np.ascontiguousarray(dist, dtype=np.float64)
+        check(lib().bnk_set_distances(self.h, _d(d)))
+
+    def probs(self, times, want_log=True):
+        t = np.ascontiguousarray(np.atleast_1d(times), dtype=np.float64)
+        P = np.zeros((len(t), self.K, self.K))
+        Lg = np.zeros_like(P) if want_log else None
+        check(lib().bnk_probs(self.h, len(t), _d(t), _d(P), _d(Lg)))
+        return (P, Lg) if want_log else P
+
+    def phase_ms(self, phase):
+        ms = C.c_float(0)
+        check(lib().bnk_ws_phase_ms(self.h, phase, C.byref(ms)))
+        return ms.value
+
+    # ---- host-buffer entry points (numpy or pinned torch tensors) ----
+    def joint(self, obs, present=None, out=None):
+        obs = _as_u8(obs)
+        n_cols = obs.shape[1]
+        present = None if present is None else _as_u8(present)
+        if out is None:
+            out = np.empty((self.n, n_cols), dtype=np.uint8)
+        check(lib().bnk_joint(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(out)))
+        return out
+
+    def marginal(self, obs, present=None, query=None, want_logl=True, out=None):
+        obs = _as_u8(obs)
+        n_cols = obs.shape[1]
+        present = None if present is None else _as_u8(present)
+        if query is None:
+            nq, q = -1, None
+            rows = self.tree.n_internal
+        else:
+            q = np.ascontiguousarray(query, dtype=np.int32)
+            nq = rows = len(q)
+        if out is None:
+            out = np.empty((rows, n_cols, self.K))
+        logl = np.empty(n_cols) if want_logl else None
+        check(lib().bnk_marginal(self.h, n_cols, _ptr(obs), _ptr(present), _i(q), nq, _ptr(out), _ptr(logl)))
+        return out, logl
+
+    def loglik(self, obs, present=None):
+        obs = _as_u8(obs)
+        n_cols = obs.shape[1]
+        present = None if present is None else _as_u8(present)
+        logl = np.empty(n_cols)
+        total = np.zeros(1)
+        check(lib().bnk_loglik(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(logl), _ptr(total)))
+        return logl, float(total[0])
+
+    # ---- device-resident entry points (torch CUDA tensors or raw device addresses) ----
+    def joint_dev(self, n_cols, d_obs, d_present, d_out_state):
+        check(lib().bnk_joint_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _ptr(d_out_state)))
+
+    def marginal_dev(self, n_cols, d_obs, d_present, d_out_post, d_out_logl=None, query=None):
+        if query is None:
+            nq, q = -1, None
+        else:
+            q = np.ascontiguousarray(query, dtype=np.int32)
+            nq = len(q)
+        check(lib().bnk_marginal_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _i(q), nq,
+                                     _ptr(d_out_post), _ptr(d_out_logl)))
+
+    def loglik_dev(self, n_cols, d_obs, d_present, d_out_logl, d_out_sum):
+        check(lib().bnk_loglik_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _ptr(d_out_logl), _ptr(d_out_sum)))
+
+
+def _as_u8(a):
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.uint8)
+    return a  # torch tensor: caller guarantees uint8, contiguous
+
+
+def device_count():
+    return lib().bnk_device_count()

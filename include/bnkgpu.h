@@ -1,0 +1,155 @@
+/*
+ * bnkgpu.h -- C ABI of libbnkgpu.so: B200 (sm_100a) per-alignment-column inference on the
+ * phylogenetic Bayesian network behind GRASP ancestral sequence reconstruction.
+ *
+ * This is the drop-in boundary for ONE path of bodenlab/bnkit: what
+ *   asr.Prediction.getJoint    (src/asr/Prediction.java:614-649)
+ *   asr.Prediction.getMarginal (src/asr/Prediction.java:555-597)
+ * run today, one column at a time, through asr.MaxLhoodJoint / asr.MaxLhoodMarginal
+ * (TreeDecor<E>, src/dat/phylo/TreeDecor.java:8-11), dat.phylo.PhyloBN.create
+ * (src/dat/phylo/PhyloBN.java:143-164), bn.ctmc.SubstNode / SubstModel.getProbs and
+ * bn.alg.VarElim (src/bn/alg/VarElim.java:187-334, :363-476).  The reference has no FFI of
+ * its own (pure Java); INTEGRATION.md shows the JNI stub a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns BNK_OK (0) or a negative bnk_status; bnk_last_error() gives
+ *     the message for the calling thread.  Nothing throws across the boundary.
+ *   - state indices follow the model alphabet order (ARNDCQEGHILKMFPSTWYV for the protein
+ *     models, ACGT for JC/Yang): index i <-> model.getDomain().get(i).  BNK_NONE (255)
+ *     means "not instantiated" on input and "no state" on output (Java null).
+ *   - trees are given as dat.phylo.IdxTree stores them (src/dat/phylo/IdxTree.java:27-32):
+ *     parent[i] < i, parent[root] = -1, distance[i] = branch length above node i.
+ *   - per-column arrays are [node][column] with the column index fastest, i.e. one
+ *     alignment row per node (dat.EnumSeq order), n_cols bytes per row.
+ *   - a workspace owns its device buffers and a CUDA stream; calls on one workspace are
+ *     serialised by the caller, different workspaces are independent.
+ *   - there is no CPU fallback: every entry point that computes fails with
+ *     BNK_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef BNKGPU_H
+#define BNKGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNK_NONE 255
+#define BNK_MAX_STATES 20
+
+typedef enum {
+    BNK_OK = 0,
+    BNK_ERR_ARG = -1,      /* invalid argument (IllegalArgumentException in the reference) */
+    BNK_ERR_MODEL = -2,    /* unknown model name / eigen-decomposition failed (ArithmeticException) */
+    BNK_ERR_TREE = -3,     /* malformed tree arrays */
+    BNK_ERR_CUDA = -4,     /* no usable device, launch or runtime failure */
+    BNK_ERR_NOMEM = -5,    /* host or device allocation failed */
+    BNK_ERR_STATE = -6,    /* call order: nothing uploaded / result not computed */
+    BNK_ERR_QUERY = -7     /* invalid ancestor id (ASRRuntimeException, Prediction.java:561-562) */
+} bnk_status;
+
+typedef struct bnk_model bnk_model; /* <-> bn.ctmc.SubstModel */
+typedef struct bnk_tree bnk_tree;   /* <-> dat.phylo.IdxTree  */
+typedef struct bnk_ws bnk_ws;       /* device workspace for one (model, tree) pair */
+
+const char *bnk_last_error(void);
+const char *bnk_version(void);
+/* number of visible CUDA devices of compute capability 10.x; < 0 on runtime failure */
+int bnk_device_count(void);
+
+/* ---- substitution models ------------------------------------------------------------ */
+/* SubstModel.createModel(name) / createModel(name, empiricalFreqs)  (SubstModel.java:334-385).
+ * name in {"LG","JTT","WAG","Dayhoff","JC","Yang"}; F_or_null = 20 (or 4) frequencies. */
+int bnk_model_create(const char *name, const double *F_or_null, bnk_model **out);
+/* new SubstModel(F, IRM, alphabet, symmetric, normalise)  (SubstModel.java:80-110) */
+int bnk_model_create_custom(int n_states, const double *F, const double *IRM, int symmetric,
+                            int normalise, bnk_model **out);
+/* Adopt an eigensystem computed elsewhere -- what the JNI stub passes from the JVM's own
+ * SubstModel.getRexp() (getEigvec / getInvEigvec / getEigval, Matrix.java:63-77) so the
+ * device tables start from exactly the reference's bits. */
+int bnk_model_create_from_eigen(int n_states, const double *F, const double *evec,
+                                const double *ievec, const double *eval, bnk_model **out);
+void bnk_model_destroy(bnk_model *m);
+int bnk_model_nstates(const bnk_model *m);
+/* any output may be NULL. R, evec, ievec: K*K row-major; eval, F, prior: K. */
+int bnk_model_get(const bnk_model *m, double *R, double *evec, double *ievec, double *eval,
+                  double *F, double *prior);
+
+/* ---- trees -------------------------------------------------------------------------- */
+/* IdxTree arrays (IdxTree.toJSON "Parents"/"Distances", IdxTree.java:277-351).
+ * dist[root] is ignored.  Distances are used as given (Newick.java:54-56 already mapped 0 -> 1e-5). */
+int bnk_tree_create(int32_t n_nodes, const int32_t *parent, const double *dist, bnk_tree **out);
+void bnk_tree_destroy(bnk_tree *t);
+int bnk_tree_size(const bnk_tree *t);
+int bnk_tree_n_internal(const bnk_tree *t); /* nodes with at least one child = ancestors */
+/* IdxTree.getPrunedIndex(pruneMe, removeOrphans=true) (IdxTree.java:411-464) as a mask
+ * transform: present_in/out [n_nodes][n_cols]; out may alias in.  Host-side integer work. */
+int bnk_tree_prune_orphans(const bnk_tree *t, int32_t n_cols, const uint8_t *present_in,
+                           uint8_t *present_out);
+
+/* ---- workspace ---------------------------------------------------------------------- */
+/* device < 0: current device.  stream: a cudaStream_t to launch on (e.g. torch's current
+ * stream) or NULL for a private one.  max_cols bounds n_cols of later calls. */
+int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_cols, int device,
+                  void *stream, bnk_ws **out);
+void bnk_ws_destroy(bnk_ws *ws);
+int bnk_ws_sync(bnk_ws *ws);
+/* tuning knobs (0 = automatic): columns per CTA tile, columns per thread */
+int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread);
+/* kernels launched by this workspace since creation (bench.py's gpu_launches) */
+int64_t bnk_ws_launch_count(const bnk_ws *ws);
+/* bytes of device memory currently held */
+int64_t bnk_ws_device_bytes(const bnk_ws *ws);
+
+/* Per-column evolutionary rates (Prediction.java:615-618: null => 1.0 for every column;
+ * PhyloBN.java:158: t = distance * rate).  Distinct values become rate categories; the
+ * P(t) / log P(t) tables of every (branch, category) are built on the device. */
+int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates_or_null);
+/* Replace branch lengths (optimisation loops); tables are rebuilt at the next run. */
+int bnk_set_distances(bnk_ws *ws, const double *dist);
+
+/* Device-side SubstModel.getProbs (SubstModel.java:303-327) for n_t times:
+ * P [n_t][K][K] (P[i][j] = P(child=j | parent=i)), logP likewise; either may be NULL. */
+int bnk_probs(bnk_ws *ws, int32_t n_t, const double *t, double *P, double *logP);
+
+/* ---- the hot path, host buffers (what the JNI stub calls) ----------------------------- */
+/* obs      [n_nodes][n_cols]  TreeInstance per column (TreeInstance.java:21-57), BNK_NONE = null
+ * present  [n_nodes][n_cols]  1 = node kept in this column's pruned tree (Prediction.getTree,
+ *                             Prediction.java:329-402); NULL = every node in every column
+ * out_state[n_nodes][n_cols]  MaxLhoodJoint.getDecoration per node (MaxLhoodJoint.java:157-167):
+ *                             inferred state, the observed state passed through, or BNK_NONE */
+int bnk_joint(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
+              uint8_t *out_state);
+/* query_nodes: n_query node indices, or NULL with n_query = -1 for every internal node in
+ * index order.  out_post [n_query][n_cols][K] (NaN where the node has no posterior in that
+ * column); out_logl [n_cols] = VarElim.logLikelihood() of the column; either may be NULL. */
+int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
+                 const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl);
+/* out_logl [n_cols] (may be NULL), *out_sum = sum over columns (may be NULL) */
+int bnk_loglik(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
+               double *out_logl, double *out_sum);
+
+/* ---- the hot path, device-resident buffers (bench "value", multi-GPU shards) ---------- */
+/* Same semantics; every pointer is a device pointer valid on the workspace's device.
+ * Launches are asynchronous on the workspace stream. */
+int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,
+                  uint8_t *d_out_state);
+int bnk_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,
+                     const int32_t *query_nodes_host, int32_t n_query, double *d_out_post,
+                     double *d_out_logl);
+/* d_out_sum: one double on the device, = sum of the column log-likelihoods (input to the
+ * NCCL all-reduce of an optimisation loop) */
+int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,
+                   double *d_out_logl, double *d_out_sum);
+
+/* ---- instrumentation ------------------------------------------------------------------ */
+/* CUDA-event time (ms) of the kernels of the most recent *_dev / host call, by phase:
+ * 0 tables, 1 joint up-sweep, 2 traceback, 3 marginal up-sweep, 4 marginal down-sweep.
+ * Requires bnk_ws_sync first. */
+int bnk_ws_phase_ms(bnk_ws *ws, int phase, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,135 @@
+"""GPU parity: libbnkgpu (through its C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): joint states bit-exact, ties in the reference's order;
+posteriors and log-likelihoods within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import NONE, leaves_of, random_obs, random_present, random_tree
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _post_close(got, want, tol=TOL):
+    """posteriors: same NaN pattern, |got - want| <= tol * max(want, tiny) with an absolute floor of tol * 1e-3"""
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    err = np.abs(got[ok] - want[ok])
+    bound = tol * np.maximum(np.abs(want[ok]), 1e-3)
+    assert (err <= bound).all(), "max excess %g" % (err - bound).max()
+
+
+@pytest.mark.parametrize("name", ["LG", "JTT", "WAG", "Dayhoff", "JC", "Yang"])
+def test_tables_bit_exact(bnk, oracle, name):
+    """Device P(t) and log P(t) equal the oracle's bit for bit (same eigensystem, same fdlibm exp/log)."""
+    m = bnk.Model(name)
+    om = oracle.Model(name)
+    tree = bnk.Tree([-1, 0, 0], [0.0, 0.1, 0.2])
+    ws = bnk.Workspace(m, tree, 4)
+    rng = np.random.default_rng(7)
+    times = np.concatenate([[0.0, 1e-7, 1e-5, 0.01, 0.07, 0.1, 1.0, 5.0, 50.0], rng.gamma(1.1, 0.2, 40)])
+    P, L = ws.probs(times)
+    for i, t in enumerate(times):
+        Po = om.probs(t)
+        assert np.array_equal(P[i], Po), (name, t)
+        Lo = np.array([[oracle.lib().om_log(x) for x in row] for row in Po])
+        assert np.array_equal(L[i], Lo), (name, t)
+
+
+def _run_case(bnk, oracle, name, rng, n_leaves, n_cols, max_children=2, gap=0.0, internal=0.0, mask=False,
+              rates=None, few_states=None, tile_cols=0, cpt=0):
+    m = bnk.Model(name)
+    om = oracle.Model(name)
+    parent, dist = random_tree(rng, n_leaves, max_children=max_children, zero_branch_prob=0.05)
+    obs = random_obs(rng, parent, n_cols, m.K, gap_prob=gap, internal_obs_prob=internal, few_states=few_states)
+    present = random_present(rng, parent, obs) if mask else None
+    tree = bnk.Tree(parent, dist)
+    ws = bnk.Workspace(m, tree, n_cols)
+    if tile_cols or cpt:
+        ws.configure(tile_cols, cpt)
+    ws.set_rates(n_cols, rates)
+    got = ws.joint(obs, present)
+    want = oracle.fast_joint(om, parent, dist, obs, present, rates, nthreads=4)
+    assert np.array_equal(got, want), "joint states differ at %d of %d" % ((got != want).sum(), got.size)
+    post, logl = ws.marginal(obs, present)
+    wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, present, rates, nthreads=4)
+    internal_nodes = tree.internal_nodes()
+    _post_close(post, wpost[internal_nodes])
+    assert np.allclose(logl, wlogl, rtol=TOL, atol=1e-12)
+    logl2, total = ws.loglik(obs, present)
+    assert np.allclose(logl2, wlogl, rtol=TOL, atol=1e-12)
+    assert np.isclose(total, wlogl.sum(), rtol=TOL)
+    ws.close()
+
+
+@pytest.mark.parametrize("name", ["LG", "JTT", "WAG", "Dayhoff"])
+def test_fast_path_random_trees(bnk, oracle, name):
+    rng = np.random.default_rng(11)
+    for n_leaves in (2, 3, 7, 40, 200):
+        _run_case(bnk, oracle, name, rng, n_leaves, 67)
+
+
+def test_four_state_models(bnk, oracle):
+    rng = np.random.default_rng(12)
+    for name in ("JC", "Yang"):
+        for n_leaves in (3, 8, 50):
+            _run_case(bnk, oracle, name, rng, n_leaves, 33)
+
+
+def test_multifurcations_and_rates(bnk, oracle):
+    rng = np.random.default_rng(13)
+    rates = rng.choice([0.2, 0.7, 1.0, 3.1], size=301)
+    _run_case(bnk, oracle, "LG", rng, 60, 301, max_children=5, rates=rates)
+    rates = rng.gamma(0.5, 2.0, size=45) + 1e-3  # every column its own rate
+    _run_case(bnk, oracle, "WAG", rng, 25, 45, max_children=3, rates=rates)
+
+
+def test_general_path_masks_and_internal_evidence(bnk, oracle):
+    rng = np.random.default_rng(14)
+    _run_case(bnk, oracle, "JTT", rng, 39, 130, max_children=3, gap=0.6, mask=True)
+    _run_case(bnk, oracle, "LG", rng, 30, 90, gap=0.3, internal=0.2, mask=True, rates=rng.choice([0.5, 2.0], size=90))
+    _run_case(bnk, oracle, "LG", rng, 12, 64, internal=0.3)             # evidence on internal nodes, no mask
+    _run_case(bnk, oracle, "LG", rng, 20, 64, gap=0.4)                  # uninstantiated leaves, everything present
+
+
+def test_ties_go_to_lowest_state(bnk, oracle):
+    """JC with equal branch lengths and few distinct leaf states produces exact ties."""
+    rng = np.random.default_rng(15)
+    m, om = bnk.Model("JC"), oracle.Model("JC")
+    for n_leaves in (4, 9, 33):
+        parent, dist = random_tree(rng, n_leaves)
+        dist[:] = 0.25
+        obs = random_obs(rng, parent, 128, 4)
+        ws = bnk.Workspace(m, bnk.Tree(parent, dist), 128)
+        got = ws.joint(obs)
+        want = oracle.fast_joint(om, parent, dist, obs)
+        assert np.array_equal(got, want)
+        ws.close()
+
+
+@pytest.mark.parametrize("tile_cols,cpt", [(4, 1), (7, 1), (16, 2), (38, 1), (30, 4), (64, 2)])
+def test_tile_geometries(bnk, oracle, tile_cols, cpt):
+    rng = np.random.default_rng(16)
+    rates = rng.choice([0.3, 1.0, 2.5], size=257)
+    _run_case(bnk, oracle, "LG", rng, 50, 257, rates=rates, tile_cols=tile_cols, cpt=cpt)
+    _run_case(bnk, oracle, "LG", rng, 21, 100, gap=0.5, mask=True, tile_cols=tile_cols, cpt=cpt)
+
+
+def test_deep_caterpillar_and_spill(bnk, oracle):
+    """A 600-level caterpillar (one launch, no per-level cost) and a wide tree."""
+    from bnkit_b200 import synth
+    rng = np.random.default_rng(17)
+    m, om = bnk.Model("LG"), oracle.Model("LG")
+    for parent, dist in (synth.caterpillar_tree(600, seed=3), synth.balanced_tree(512, seed=4)):
+        obs = random_obs(rng, parent, 96, 20, few_states=6)
+        ws = bnk.Workspace(m, bnk.Tree(parent, dist), 96)
+        got = ws.joint(obs)
+        assert np.array_equal(got, oracle.fast_joint(om, parent, dist, obs, nthreads=4))
+        post, logl = ws.marginal(obs)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, nthreads=4)
+        _post_close(post, wpost[leaves_of(parent) == False])
+        assert np.allclose(logl, wlogl, rtol=TOL)
+        ws.close()
