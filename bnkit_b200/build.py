@@ -12,6 +12,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("tables.cu", ["-fmad=false"]),
     ("sweeps.cu", []),
+    ("sweeps_fast.cu", []),
     ("traceback.cu", []),
     ("api.cu", []),
     ("subst_model.cpp", ["-fmad=false"]),

@@ -72,11 +72,12 @@ struct bnk_ws {
     bool own_stream = false;
     int64_t launches = 0, dev_bytes = 0;
     int cfg_tile_cols = 0, cfg_cpt = 0;
+    bool force_generic = false;
     size_t table_budget = (size_t)12 << 30;
     // static device data
     DevBuf<double> d_model;  // evec | ievec | eval | prior | logprior
-    DevBuf<UpStep> d_up;
-    DevBuf<DownStep> d_down;
+    DevBuf<Step> d_up;
+    DevBuf<Step> d_down;
     DevBuf<ChildRef> d_up_child, d_down_child;
     DevBuf<int32_t> d_parent, d_node_of_ent, d_leaf_nodes, d_leaf_parent;
     DevBuf<double> d_dist;
@@ -272,6 +273,8 @@ extern "C" int bnk_ws_sync(bnk_ws *ws)
 extern "C" int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread)
 {
     if (!ws) return fail(BNK_ERR_ARG, "ws: null");
+    ws->force_generic = cols_per_thread < 0;  // negative: same geometry, generic kernels only (tests)
+    if (cols_per_thread < 0) cols_per_thread = -cols_per_thread;
     if (cols_per_thread != 0 && cols_per_thread != 1 && cols_per_thread != 2 && cols_per_thread != 4)
         return fail(BNK_ERR_ARG, "ws: cols_per_thread must be 0 (auto), 1, 2 or 4");
     if (ws->K == 4 && cols_per_thread > 1) return fail(BNK_ERR_ARG, "ws: 4-state kernels are built with 1 column per thread");
@@ -511,6 +514,7 @@ static int build_tables(bnk_ws *ws, const Chunk &ck, bool log_space)
 struct WalkSetup {
     WalkArgs a;
     WalkLaunch wl;
+    bool fast = false;  // lean kernels of sweeps_fast.cu apply
 };
 
 static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_needed, const uint8_t *obs_s,
@@ -528,6 +532,20 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_neede
     s.a.obs = obs_s; s.a.present = present_s;
     s.a.ncols = ws->ncols; s.a.n_nodes = ws->n;
     s.a.orig_col = ws->d_orig_col.p; s.a.col_cat = ws->d_col_cat.p;
+    s.wl.K = K; s.wl.cpt = ws->cpt; s.wl.threads = ws->threads; s.wl.n_tiles = ck.tile_hi - ck.tile_lo;
+    s.wl.general = general; s.wl.stream = ws->stream;
+    // lean kernels: nothing masked, evidence on childless nodes only, binary (or unary) nodes,
+    // one category per tile, whole stack in shared memory
+    s.fast = false;
+    if (!general && !ws->force_generic && t->max_children <= 2 && ck.ncat_max == 1) {
+        const size_t need = fast_smem_bytes(K, ws->cpt, ws->ncg, slots_needed);
+        if (need <= (size_t)ws->smem_optin) {
+            s.fast = true;
+            s.a.smem_slots = slots_needed;
+            s.wl.smem_bytes = need;
+            return BNK_OK;
+        }
+    }
     // stack slots: as many as fit in shared memory, the rest spill to global memory
     const size_t base = walk_smem_bytes(K, ws->cpt, ws->ncg, ck.ncat_max, 0);
     const size_t per_slot = sizeof(double) * (size_t)ws->ncg * ws->cpt * K;
@@ -539,8 +557,6 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_neede
         CUDA_TRY(ws->d_spill.ensure((size_t)(slots_needed - smem_slots) * ws->ncols * K));
         s.a.spill = ws->d_spill.p;
     }
-    s.wl.K = K; s.wl.cpt = ws->cpt; s.wl.threads = ws->threads; s.wl.n_tiles = ck.tile_hi - ck.tile_lo;
-    s.wl.general = general; s.wl.stream = ws->stream;
     s.wl.smem_bytes = base + per_slot * smem_slots;
     return BNK_OK;
 }
@@ -564,13 +580,15 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
     for (size_t ci = 0; ci < ws->chunks.size(); ci++) {
         const Chunk &ck = ws->chunks[ci];
         TRY(build_tables(ws, ck, true));
+        bool fast_joint = false;
         if (ws->n_int > 0) {
             WalkSetup s;
             TRY(setup_walk(ws, ck, general, ws->tree->up_slots, obs_s, present_s, s));
             s.a.T_row = ws->d_L.p; s.a.T_col = ws->d_LT.p; s.a.prior = ws->md().logprior;
             s.a.ptr = ws->d_ptr.p; s.a.kind = ws->d_kind.p;
+            fast_joint = s.fast;
             CUDA_TRY(cudaEventRecord(ws->ev[1][0], ws->stream));
-            CUDA_TRY(launch_joint_up(s.wl, s.a));
+            CUDA_TRY(s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;
             CUDA_TRY(cudaEventRecord(ws->ev[1][1], ws->stream));
             ws->ev_valid[1] = true;
@@ -578,7 +596,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
         TracebackArgs ta;
         std::memset(&ta, 0, sizeof(ta));
         ta.down = ws->d_down.p; ta.n_steps = ws->n_int; ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
-        ta.ptr = ws->d_ptr.p; ta.kind = ws->d_kind.p; ta.obs = d_obs; ta.present = d_present;
+        ta.ptr = ws->d_ptr.p; ta.kind = fast_joint ? nullptr : ws->d_kind.p; ta.obs = d_obs; ta.present = d_present;
         ta.out_state = d_out_state; ta.tb_slots = ws->tree->tb_slots;
         ta.leaf_nodes = ws->d_leaf_nodes.p; ta.leaf_parent = ws->d_leaf_parent.p; ta.n_leaves = ws->n_leaves;
         ta.L = ws->d_L.p;
@@ -667,16 +685,16 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
         s.a.kindm = (want_post && general) ? ws->d_kindm.p : nullptr;
         s.a.out_logl = logl;
         CUDA_TRY(cudaEventRecord(ws->ev[3][0], ws->stream));
-        CUDA_TRY(launch_sum_up(s.wl, s.a));
+        CUDA_TRY(s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
         ws->launches++;
         CUDA_TRY(cudaEventRecord(ws->ev[3][1], ws->stream));
         ws->ev_valid[3] = true;
         if (want_post) {
             s.a.T_row = ws->d_PT.p;
             s.a.out_post = d_out_post;
-            s.a.qrow = ws->d_qrow.p;
+            s.a.qrow = (n_query < 0) ? nullptr : ws->d_qrow.p;
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
-            CUDA_TRY(launch_sum_down(s.wl, s.a));
+            CUDA_TRY(s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;
             CUDA_TRY(cudaEventRecord(ws->ev[4][1], ws->stream));
             ws->ev_valid[4] = true;

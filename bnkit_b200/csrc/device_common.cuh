@@ -30,8 +30,8 @@ enum : uint8_t { KIND_NONE = 0, KIND_MSG = 1, KIND_ROOT = 2, KIND_OBS = 3 };
 
 struct WalkArgs {
     // static program
-    const UpStep *up;
-    const DownStep *down;
+    const Step *up;
+    const Step *down;
     const ChildRef *up_child, *down_child;
     int32_t n_steps;
     const TileDesc *tiles;
@@ -76,11 +76,17 @@ int walk_max_smem_optin(int device);
 cudaError_t launch_joint_up(const WalkLaunch &wl, const WalkArgs &a);
 cudaError_t launch_sum_up(const WalkLaunch &wl, const WalkArgs &a);
 cudaError_t launch_sum_down(const WalkLaunch &wl, const WalkArgs &a);
+// lean variants (sweeps_fast.cu): no mask, evidence on childless nodes only, <= 2 children per
+// node, one rate category per tile, whole message stack in shared memory
+size_t fast_smem_bytes(int K, int cpt, int ncg, int slots);
+cudaError_t launch_joint_up_fast(const WalkLaunch &wl, const WalkArgs &a);
+cudaError_t launch_sum_up_fast(const WalkLaunch &wl, const WalkArgs &a);
+cudaError_t launch_sum_down_fast(const WalkLaunch &wl, const WalkArgs &a);
 
 struct TracebackArgs {
-    const DownStep *down;
+    const Step *down;
     int32_t n_steps, ncols, n_nodes, K;
-    const uint8_t *ptr, *kind;      // original column space
+    const uint8_t *ptr, *kind;      // original column space; kind == nullptr: root steps are KIND_ROOT, all others KIND_MSG
     const uint8_t *obs, *present;   // original column space, [node][ncols]
     uint8_t *out_state;             // [node][ncols]
     int32_t tb_slots;

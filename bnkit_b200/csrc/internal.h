@@ -30,27 +30,27 @@ int model_from_eigen(int K, const double *F, const double *evec, const double *i
 
 // One step of the column-tile walk = one internal node (a node with >= 1 child in the
 // static tree).  Childless nodes never get a step: their message is a table lookup made
-// while folding the parent's children.
-struct UpStep {
+// while folding the parent's children.  64 bytes, streamed into shared memory in chunks;
+// the first two children are inline so binary trees never touch the overflow array.
+struct Step {
     int32_t node;         // tree index
     int32_t parent;       // tree index or -1
-    int32_t slot;         // message-stack slot receiving this node's message, -1 for the static root
-    int32_t child_begin;  // into the child arrays
-    int32_t n_child;
     int32_t ent;          // row of this node among internal nodes (index order)
-};
-struct DownStep {
-    int32_t node, parent;
-    int32_t tslot;        // slot holding the from-above vector for this node, -1 for the static root
-    int32_t child_begin, n_child;
-    int32_t ent;
+    int32_t n_child;
+    int32_t slot;         // up: stack slot receiving this node's message; down: slot holding its from-above vector; -1 static root
+    int32_t child_begin;  // into the ChildRef array (all children, used for index >= 2)
+    int32_t c_node[2];    // first two children: tree index,
+    int32_t c_slot[2];    //   up: slot of the child's message / down: slot receiving its from-above vector; -1 childless
+    int32_t c_ent[2];     //   internal row or -1
     int32_t pslot;        // traceback: slot holding the parent's state (-1: none)
     int32_t oslot;        // traceback: slot receiving this node's state (-1: not needed)
+    int32_t pad[2];
 };
+static_assert(sizeof(Step) == 64, "Step must be 64 bytes");
 struct ChildRef {
     int32_t node;
-    int32_t slot;  // up: stack slot of the child's message; down: slot receiving the child's from-above vector; -1 childless
-    int32_t ent;   // row among internal nodes, -1 if childless
+    int32_t slot;
+    int32_t ent;
 };
 
 }  // namespace bnk
@@ -62,9 +62,9 @@ struct bnk_tree {
     std::vector<int32_t> first, kids;  // children CSR in index order (IdxTree.children[])
     std::vector<int32_t> ent_of_node;  // -1 for childless nodes
     std::vector<int32_t> node_of_ent;
-    std::vector<bnk::UpStep> up;       // post-order, heavy child first
+    std::vector<bnk::Step> up;         // post-order, heavy child first
     std::vector<bnk::ChildRef> up_child;
-    std::vector<bnk::DownStep> down;   // pre-order, heavy child last
+    std::vector<bnk::Step> down;   // pre-order, heavy child last
     std::vector<bnk::ChildRef> down_child;
-    int32_t up_slots = 0, down_slots = 0, tb_slots = 0;
+    int32_t up_slots = 0, down_slots = 0, tb_slots = 0, max_children = 0;
 };

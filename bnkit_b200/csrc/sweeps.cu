@@ -8,9 +8,12 @@
 // whole tree for them (program built in tree_plan.cpp): thread (c, p) owns entry p of the
 // 20-state vectors of column c.  Live messages sit in a shared-memory stack; the node's
 // 20x20 table (log P for max-product, P for sum-product, P^T for the down-sweep) is streamed
-// into shared memory with cp.async three nodes deep; children that are alignment leaves
-// never materialise a message -- their contribution is one table lookup by the observed
-// state.  No launch per tree level, no message round trip through HBM for the joint pass.
+// into shared memory with cp.async three nodes deep, the walk program itself in 32-step
+// chunks; children that are alignment leaves never materialise a message -- their
+// contribution is one table lookup by the observed state, software-pipelined two steps
+// ahead (state bytes at distance 2, table entries at distance 1) so that no global-memory
+// latency sits on the per-node critical path.  No launch per tree level, no message round
+// trip through HBM for the joint pass.
 //
 // Arithmetic contracts
 //   joint:  log space, adds only, in the reference's association order
@@ -26,7 +29,8 @@
 
 namespace bnk {
 
-constexpr int NSTAGE = 3;  // table ring depth (prefetch distance 2 nodes)
+constexpr int NSTAGE = 3;   // table ring depth
+constexpr int PCHUNK = 32;  // walk-program steps per shared-memory chunk (double buffered)
 constexpr int MAXDEG_LOCAL = 16;
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
@@ -41,13 +45,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int K>
 struct Smem {
     static constexpr int LROW = K + 2;  // padded row: conflict-free 128-bit row reads, 16 B aligned
+    Step *prog;     // [2][PCHUNK]
     double *tab;    // [NSTAGE][ncat_max][K][LROW]
     double *gs;     // [2][tcpad][LROW]
     double *unit;   // [LROW]  zeros (log space) or ones (linear space)
     double *stack;  // [smem_slots][tcpad][K]
     __device__ Smem(unsigned char *raw, int ncat_max, int tcpad)
     {
-        tab = reinterpret_cast<double *>(raw);
+        prog = reinterpret_cast<Step *>(raw);
+        tab = reinterpret_cast<double *>(raw + 2 * PCHUNK * sizeof(Step));
         gs = tab + (size_t)NSTAGE * ncat_max * K * LROW;
         unit = gs + (size_t)2 * tcpad * LROW;
         stack = unit + LROW;
@@ -57,7 +63,8 @@ struct Smem {
 size_t walk_smem_bytes(int K, int cpt, int ncg, int ncat_max, int slots)
 {
     const size_t lrow = K + 2, tcpad = (size_t)ncg * cpt;
-    return sizeof(double) * ((size_t)NSTAGE * ncat_max * K * lrow + 2 * tcpad * lrow + lrow + (size_t)slots * tcpad * K);
+    return 2 * PCHUNK * sizeof(Step) +
+           sizeof(double) * ((size_t)NSTAGE * ncat_max * K * lrow + 2 * tcpad * lrow + lrow + (size_t)slots * tcpad * K);
 }
 
 int walk_max_smem_optin(int device)
@@ -69,15 +76,26 @@ int walk_max_smem_optin(int device)
 
 // stream one node's row table (all categories of this tile) into a ring stage
 template <int K>
-__device__ __forceinline__ void prefetch_table(const WalkArgs &a, const TileDesc &tile, int node, double *stage_base)
+__device__ __forceinline__ void prefetch_table(const double *T_row, int n_nodes, const TileDesc &tile, int node,
+                                               double *stage_base)
 {
     constexpr int LROW = K + 2, CH = K / 2;  // 16-byte chunks per row
     const int total = tile.ncat * K * CH;
     for (int q = threadIdx.x; q < total; q += blockDim.x) {
         const int ct = q / (K * CH), r = q - ct * (K * CH);
         const int row = r / CH, ch = r - row * CH;
-        const double *src = a.T_row + ((size_t)(tile.cat0 + ct) * a.n_nodes + node) * (K * K) + row * K + ch * 2;
+        const double *src = T_row + ((size_t)(tile.cat0 + ct) * n_nodes + node) * (K * K) + row * K + ch * 2;
         cp_async_16(stage_base + ((size_t)ct * K + row) * LROW + ch * 2, src);
+    }
+}
+
+__device__ __forceinline__ void prefetch_prog(const Step *prog_g, int n_steps, int chunk, Step *dst)
+{
+    const int q = threadIdx.x;  // one 16-byte piece per thread; blockDim.x >= 32, so loop
+    for (int k = q; k < PCHUNK * 4; k += blockDim.x) {
+        const int s = chunk * PCHUNK + (k >> 2);
+        if (s < n_steps)
+            cp_async_16(reinterpret_cast<char *>(dst) + k * 16, reinterpret_cast<const char *>(prog_g + s) + (k & 3) * 16);
     }
 }
 
@@ -90,6 +108,45 @@ __device__ __forceinline__ double pow2_scale_from_hi(int mhi, int &e)
     return __hiloint2double((2046 - be) << 20, 0);
 }
 
+// state bytes one step needs for one column (loaded two steps ahead)
+struct Bytes {
+    uint8_t ov, op;    // observation at the node / at its parent (BNK_NONE = none)
+    uint8_t pv, pp;    // node present / parent present
+    uint8_t ou[2];     // observations at the first two children
+    uint8_t pu[2];     // their presence
+};
+// table entries one step needs for one column (loaded one step ahead)
+struct Looks {
+    double base;       // root-like start value: prior[p] or T[v][obs_parent -> p]
+    double g[2];       // messages of observed first-two children: T[child][p -> obs_child]
+};
+
+template <bool GENERAL>
+__device__ __forceinline__ Bytes load_bytes(const WalkArgs &a, const Step &s, int col, bool down)
+{
+    Bytes b;
+    b.ov = BNK_NONE; b.op = BNK_NONE; b.pv = 1; b.pp = s.parent >= 0;
+    b.ou[0] = b.ou[1] = BNK_NONE; b.pu[0] = b.pu[1] = 1;
+    if (GENERAL) {
+        if (a.present) {
+            b.pv = a.present[(size_t)s.node * a.ncols + col];
+            if (s.parent >= 0) b.pp = a.present[(size_t)s.parent * a.ncols + col];
+        }
+        b.ov = a.obs[(size_t)s.node * a.ncols + col];
+        if (s.parent >= 0) b.op = a.obs[(size_t)s.parent * a.ncols + col];
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        if (e < s.n_child) {
+            const bool childless = down ? (s.c_ent[e] < 0) : (s.c_slot[e] < 0);
+            if (GENERAL && a.present) b.pu[e] = a.present[(size_t)s.c_node[e] * a.ncols + col];
+            if (GENERAL || childless) b.ou[e] = a.obs[(size_t)s.c_node[e] * a.ncols + col];
+        }
+    }
+    if (GENERAL && !b.pp) b.op = BNK_NONE;
+    return b;
+}
+
 // ------------------------------------------------------------------------------------
 // up-sweeps.  MODE 0: max-product in log space (joint).  MODE 1: sum-product, linear space.
 // ------------------------------------------------------------------------------------
@@ -97,14 +154,17 @@ template <int K, int CPT, bool GENERAL, int MODE>
 __global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int LROW = K + 2;
+    constexpr int LROW = K + 2, KK = K * K;
     const TileDesc tile = a.tiles[blockIdx.x];
     const int tcpad = a.ncg * CPT;
     Smem<K> sm(smem_raw, a.ncat_max, tcpad);
     const int tid = threadIdx.x, p = tid % K, cg = tid / K;
     const size_t stage_elems = (size_t)a.ncat_max * K * LROW;
+    const int n_steps = a.n_steps;
+    const double ident = (MODE == 0) ? 0.0 : 1.0;
 
     int lc[CPT], col[CPT], tcat[CPT], ocol[CPT];
+    size_t tb[CPT];
     bool act[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; j++) {
@@ -113,8 +173,10 @@ __global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
         col[j] = tile.col0 + (act[j] ? lc[j] : 0);
         tcat[j] = a.col_cat[col[j]] - tile.cat0;
         ocol[j] = a.orig_col[col[j]];
+        tb[j] = (size_t)(tile.cat0 + tcat[j]) * a.n_nodes;
     }
-    for (int q = tid; q < LROW; q += blockDim.x) sm.unit[q] = (MODE == 0) ? 0.0 : 1.0;
+    const double prior_p = a.prior[p];
+    for (int q = tid; q < LROW; q += blockDim.x) sm.unit[q] = ident;
 
     // per-column accumulators of the sum-product (identical in the K threads of a column)
     int esum[CPT];
@@ -122,71 +184,96 @@ __global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
 #pragma unroll
     for (int j = 0; j < CPT; j++) { esum[j] = 0; logacc[j] = 0.0; }
 
-    // prologue: tables of the first two steps
+    // prologue: program chunk 0, then the tables of the first two steps
+    prefetch_prog(a.up, n_steps, 0, sm.prog);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     for (int s = 0; s < NSTAGE - 1; s++) {
-        if (s < a.n_steps) prefetch_table<K>(a, tile, a.up[s].node, sm.tab + s * stage_elems);
+        if (s < n_steps) prefetch_table<K>(a.T_row, a.n_nodes, tile, sm.prog[s].node, sm.tab + s * stage_elems);
         cp_async_commit();
     }
+    auto step_ref = [&](int i) -> const Step & { return sm.prog[((i / PCHUNK) & 1) * PCHUNK + (i % PCHUNK)]; };
+    auto load_looks = [&](const Step &s, const Bytes &b, int j) -> Looks {
+        Looks l;
+        l.base = ident; l.g[0] = l.g[1] = ident;
+        const bool rootlike = !b.pp || b.op != BNK_NONE;
+        if (rootlike) l.base = (b.op != BNK_NONE) ? a.T_col[(tb[j] + s.node) * KK + p * K + b.op] : prior_p;
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+            if (e < s.n_child && b.pu[e] && b.ou[e] != BNK_NONE)
+                l.g[e] = a.T_col[(tb[j] + s.c_node[e]) * KK + b.ou[e] * K + p];
+        return l;
+    };
 
-    for (int i = 0; i < a.n_steps; i++) {
-        const UpStep st = a.up[i];
+    Bytes B0[CPT], B1[CPT];
+    Looks L0[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) {
+        if (act[j] && n_steps > 0) B0[j] = load_bytes<GENERAL>(a, step_ref(0), col[j], false);
+        if (act[j] && n_steps > 1) B1[j] = load_bytes<GENERAL>(a, step_ref(1), col[j], false);
+        if (act[j] && n_steps > 0) L0[j] = load_looks(step_ref(0), B0[j], j);
+    }
+
+    for (int i = 0; i < n_steps; i++) {
+        const Step st = step_ref(i);
         const int v = st.node;
         double *gs = sm.gs + (size_t)(i & 1) * tcpad * LROW;
         uint8_t kind[CPT];
+        Bytes B2[CPT];
+        Looks L1[CPT];
+        // ---------------- software pipeline: bytes of step i+2, table entries of step i+1 ----------------
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            if (!act[j]) continue;
+            if (i + 2 < n_steps) B2[j] = load_bytes<GENERAL>(a, step_ref(i + 2), col[j], false);
+            if (i + 1 < n_steps) L1[j] = load_looks(step_ref(i + 1), B1[j], j);
+        }
         // ---------------- fold the children ----------------
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             kind[j] = KIND_NONE;
             if (!act[j]) continue;
-            const size_t tb = (size_t)(tile.cat0 + tcat[j]) * a.n_nodes;  // table row base of this column's category
-            bool pv = true, pp = st.parent >= 0;
-            uint8_t ov = BNK_NONE, op = BNK_NONE;
-            if (GENERAL) {
-                if (a.present) {
-                    pv = a.present[(size_t)v * a.ncols + col[j]] != 0;
-                    pp = pp && a.present[(size_t)st.parent * a.ncols + col[j]] != 0;
-                }
-                ov = a.obs[(size_t)v * a.ncols + col[j]];
-                if (pp) op = a.obs[(size_t)st.parent * a.ncols + col[j]];
-            }
+            const Bytes b = B0[j];
+            const bool pv = b.pv != 0, pp = b.pp != 0;
+            const uint8_t ov = b.ov, op = b.op;
             const bool rootlike = !pp || op != BNK_NONE;
-            double G;
-            if (MODE == 0) G = 0.0; else G = 1.0;
-            bool first = true;
-            if (rootlike) {
-                G = (op != BNK_NONE) ? a.T_col[(tb + v) * (K * K) + p * K + op] : a.prior[p];
-                first = false;
-            }
+            double G = rootlike ? L0[j].base : ident;
+            bool first = !rootlike;
             int nk = 0;
             const bool need = pv && ov == BNK_NONE;  // only unobserved present nodes combine messages
-            for (int e = 0; e < st.n_child; e++) {
-                const ChildRef ch = a.up_child[st.child_begin + e];
-                if (GENERAL && a.present && a.present[(size_t)ch.node * a.ncols + col[j]] == 0) continue;
+            // one child's contribution; the first two children use the values prefetched a step ago
+            auto take = [&](int cnode, int cslot, bool pu, uint8_t ou, bool pref, double gpref) {
+                if (!pu) return;
                 nk++;
                 if (!need) {
-                    if (MODE == 1 && GENERAL && pv && ch.slot < 0) {  // observed v: scalar factors of its observed childless children
-                        const uint8_t ou = a.obs[(size_t)ch.node * a.ncols + col[j]];
-                        if (ou != BNK_NONE) logacc[j] += log(a.T_col[(tb + ch.node) * (K * K) + ou * K + ov]);
-                    }
-                    continue;
+                    if (MODE == 1 && GENERAL && pv && cslot < 0 && ou != BNK_NONE)  // observed v: scalar factor of an observed childless child
+                        logacc[j] += log(a.T_col[(tb[j] + cnode) * KK + ou * K + ov]);
+                    return;
                 }
                 double g;
-                uint8_t ou = BNK_NONE;
-                if (ch.slot < 0 || GENERAL) ou = a.obs[(size_t)ch.node * a.ncols + col[j]];
                 if (ou != BNK_NONE) {
-                    g = a.T_col[(tb + ch.node) * (K * K) + ou * K + p];
-                } else if (ch.slot < 0) {  // unobserved childless node: marginalise / maximise its own row
-                    const double *row = a.T_row + (tb + ch.node) * (K * K) + p * K;
+                    g = pref ? gpref : a.T_col[(tb[j] + cnode) * KK + ou * K + p];
+                } else if (cslot < 0) {  // unobserved childless node: maximise / marginalise its own row
+                    const double *row = a.T_row + (tb[j] + cnode) * KK + p * K;
                     g = row[0];
                     for (int x = 1; x < K; x++) g = (MODE == 0) ? (row[x] > g ? row[x] : g) : g + row[x];
-                } else if (ch.slot < a.smem_slots) {
-                    g = sm.stack[((size_t)ch.slot * tcpad + lc[j]) * K + p];
+                } else if (cslot < a.smem_slots) {
+                    g = sm.stack[((size_t)cslot * tcpad + lc[j]) * K + p];
                 } else {
-                    g = a.spill[((size_t)(ch.slot - a.smem_slots) * a.ncols + col[j]) * K + p];
+                    g = a.spill[((size_t)(cslot - a.smem_slots) * a.ncols + col[j]) * K + p];
                 }
                 if (MODE == 0) G = first ? g : G + g;
                 else G = first ? g : G * g;
                 first = false;
+            };
+            if (st.n_child > 0) take(st.c_node[0], st.c_slot[0], b.pu[0] != 0, b.ou[0], true, L0[j].g[0]);
+            if (st.n_child > 1) take(st.c_node[1], st.c_slot[1], b.pu[1] != 0, b.ou[1], true, L0[j].g[1]);
+            for (int e = 2; e < st.n_child; e++) {
+                const ChildRef ch = a.up_child[st.child_begin + e];
+                const bool pu = !(GENERAL && a.present) || a.present[(size_t)ch.node * a.ncols + col[j]] != 0;
+                const uint8_t ou = (GENERAL || ch.slot < 0) ? a.obs[(size_t)ch.node * a.ncols + col[j]] : (uint8_t)BNK_NONE;
+                take(ch.node, ch.slot, pu, ou, false, 0.0);
             }
             if (!pv) kind[j] = KIND_NONE;
             else if (ov != BNK_NONE) kind[j] = KIND_OBS;
@@ -194,14 +281,16 @@ __global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
             else kind[j] = rootlike ? KIND_ROOT : KIND_MSG;
             if (MODE == 1 && GENERAL && kind[j] == KIND_OBS) {  // scalar factor of an observed node
                 if (!pp) { if (nk > 0) logacc[j] += log(a.prior[ov]); }
-                else if (op != BNK_NONE) logacc[j] += log(a.T_col[(tb + v) * (K * K) + ov * K + op]);
+                else if (op != BNK_NONE) logacc[j] += log(a.T_col[(tb[j] + v) * KK + ov * K + op]);
             }
             gs[(size_t)lc[j] * LROW + p] = G;
         }
         cp_async_wait<NSTAGE - 2>();
         __syncthreads();
-        if (i + NSTAGE - 1 < a.n_steps)
-            prefetch_table<K>(a, tile, a.up[i + NSTAGE - 1].node, sm.tab + ((i + NSTAGE - 1) % NSTAGE) * stage_elems);
+        if (i + NSTAGE - 1 < n_steps)
+            prefetch_table<K>(a.T_row, a.n_nodes, tile, step_ref(i + NSTAGE - 1).node,
+                              sm.tab + ((i + NSTAGE - 1) % NSTAGE) * stage_elems);
+        if (i % PCHUNK == 0) prefetch_prog(a.up, n_steps, i / PCHUNK + 1, sm.prog + (((i / PCHUNK) + 1) & 1) * PCHUNK);
         cp_async_commit();
         // ---------------- contract with the node's table ----------------
         const double *stage = sm.tab + (i % NSTAGE) * stage_elems;
@@ -254,6 +343,8 @@ __global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < CPT; j++) { B0[j] = B1[j]; B1[j] = B2[j]; L0[j] = L1[j]; }
     }
     if (MODE == 1 && a.out_logl && p == 0) {
 #pragma unroll
@@ -268,18 +359,36 @@ __global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
 //   post_v   = normalise(D_v * prod_children g_c)    (CGTable.query + EnumDistrib.normalise)
 //   T_c[x]   = D_v[x] * prod_{w != c} g_w[x]         pushed for every internal child c
 // ------------------------------------------------------------------------------------
+// value of one of the first two children in the down-sweep: prefetched (observed child: table
+// entry; internal child: stored up-message) or, for an uninstantiated childless node, the row sum
+__device__ __forceinline__ double child_value(const WalkArgs &a, const Step &st, const Bytes &b, const Looks &l, int e,
+                                              size_t tb, int col, int p, int K)
+{
+    if (b.ou[e] != BNK_NONE || st.c_ent[e] >= 0) return l.g[e];
+    double s = 0.0;
+    for (int x = 0; x < K; x++) s += a.T_col[(tb + st.c_node[e]) * (K * K) + x * K + p];
+    return s;
+}
+
+struct DownBytes {
+    Bytes b;
+    uint8_t kind;
+};
+
 template <int K, int CPT, bool GENERAL>
 __global__ void __launch_bounds__(768) down_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int LROW = K + 2;
+    constexpr int LROW = K + 2, KK = K * K;
     const TileDesc tile = a.tiles[blockIdx.x];
     const int tcpad = a.ncg * CPT;
     Smem<K> sm(smem_raw, a.ncat_max, tcpad);
     const int tid = threadIdx.x, p = tid % K, cg = tid / K;
     const size_t stage_elems = (size_t)a.ncat_max * K * LROW;
+    const int n_steps = a.n_steps;
 
     int lc[CPT], col[CPT], tcat[CPT], ocol[CPT];
+    size_t tb[CPT];
     bool act[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; j++) {
@@ -288,116 +397,166 @@ __global__ void __launch_bounds__(768) down_kernel(const WalkArgs a)
         col[j] = tile.col0 + (act[j] ? lc[j] : 0);
         tcat[j] = a.col_cat[col[j]] - tile.cat0;
         ocol[j] = a.orig_col[col[j]];
+        tb[j] = (size_t)(tile.cat0 + tcat[j]) * a.n_nodes;
     }
+    const double prior_p = a.prior[p];
+
+    prefetch_prog(a.down, n_steps, 0, sm.prog);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     // ring: step i uses stage i % NSTAGE; the table of step i + NSTAGE is requested right after
     // the barrier of step i, when nobody reads stage i % NSTAGE any more.
     for (int s = 0; s < NSTAGE; s++) {
-        if (s < a.n_steps) prefetch_table<K>(a, tile, a.down[s].node, sm.tab + s * stage_elems);
+        if (s < n_steps) prefetch_table<K>(a.T_row, a.n_nodes, tile, sm.prog[s].node, sm.tab + s * stage_elems);
         cp_async_commit();
+    }
+    auto step_ref = [&](int i) -> const Step & { return sm.prog[((i / PCHUNK) & 1) * PCHUNK + (i % PCHUNK)]; };
+    auto load_dbytes = [&](const Step &s, int j) -> DownBytes {
+        DownBytes d;
+        d.b = load_bytes<GENERAL>(a, s, col[j], true);
+        d.kind = GENERAL ? a.kindm[(size_t)s.ent * a.ncols + col[j]] : (s.parent < 0 ? KIND_ROOT : KIND_MSG);
+        return d;
+    };
+    // values of the first two children (observed: table entry; internal: stored up-message) and the root-like base
+    auto load_looks = [&](const Step &s, const DownBytes &d, int j) -> Looks {
+        Looks l;
+        l.base = prior_p; l.g[0] = l.g[1] = 1.0;
+        if (d.kind == KIND_ROOT && d.b.op != BNK_NONE) l.base = a.T_col[(tb[j] + s.node) * KK + p * K + d.b.op];
+        if (d.kind == KIND_MSG || d.kind == KIND_ROOT) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (e >= s.n_child || !d.b.pu[e]) continue;
+                if (d.b.ou[e] != BNK_NONE) l.g[e] = a.T_col[(tb[j] + s.c_node[e]) * KK + d.b.ou[e] * K + p];
+                else if (s.c_ent[e] >= 0) l.g[e] = a.msg[((size_t)s.c_ent[e] * a.ncols + col[j]) * K + p];
+            }
+        }
+        return l;
+    };
+    DownBytes B0[CPT], B1[CPT];
+    Looks L0[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) {
+        if (act[j] && n_steps > 0) B0[j] = load_dbytes(step_ref(0), j);
+        if (act[j] && n_steps > 1) B1[j] = load_dbytes(step_ref(1), j);
+        if (act[j] && n_steps > 0) L0[j] = load_looks(step_ref(0), B0[j], j);
     }
     cp_async_wait<NSTAGE - 1>();
     __syncthreads();
-    for (int i = 0; i < a.n_steps; i++) {
-        const DownStep st = a.down[i];
-        const int v = st.node;
+
+    for (int i = 0; i < n_steps; i++) {
+        const Step st = step_ref(i);
         double *gs = sm.gs + (size_t)(i & 1) * tcpad * LROW;
         const double *stage = sm.tab + (i % NSTAGE) * stage_elems;
-        uint8_t kind[CPT];
-        double D[CPT], U[CPT];
+        DownBytes B2[CPT];
+        Looks L1[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
-            kind[j] = KIND_NONE; D[j] = 0.0; U[j] = 0.0;
             if (!act[j]) continue;
-            const size_t tb = (size_t)(tile.cat0 + tcat[j]) * a.n_nodes;
-            kind[j] = GENERAL ? a.kindm[(size_t)st.ent * a.ncols + col[j]] : (st.parent < 0 ? KIND_ROOT : KIND_MSG);
+            if (i + 2 < n_steps) B2[j] = load_dbytes(step_ref(i + 2), j);
+            if (i + 1 < n_steps) L1[j] = load_looks(step_ref(i + 1), B1[j], j);
+        }
+        uint8_t kind[CPT];
+        double U[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            kind[j] = KIND_NONE; U[j] = 0.0;
+            if (!act[j]) continue;
+            kind[j] = B0[j].kind;
             if (kind[j] != KIND_MSG && kind[j] != KIND_ROOT) continue;
+            const Bytes b = B0[j].b;
             // ---- from-above vector ----
+            double D;
             if (kind[j] == KIND_ROOT) {
-                uint8_t op = BNK_NONE;
-                if (GENERAL && st.parent >= 0 && (!a.present || a.present[(size_t)st.parent * a.ncols + col[j]]))
-                    op = a.obs[(size_t)st.parent * a.ncols + col[j]];
-                D[j] = (op != BNK_NONE) ? a.T_col[(tb + v) * (K * K) + p * K + op] : a.prior[p];
+                D = L0[j].base;
             } else {
                 const double2 *row2 = reinterpret_cast<const double2 *>(stage + ((size_t)tcat[j] * K + p) * LROW);
+                const double2 *t2 = (st.slot < a.smem_slots)
+                    ? reinterpret_cast<const double2 *>(sm.stack + ((size_t)st.slot * tcpad + lc[j]) * K)
+                    : reinterpret_cast<const double2 *>(a.spill + ((size_t)(st.slot - a.smem_slots) * a.ncols + col[j]) * K);
                 double acc0 = 0.0, acc1 = 0.0;
                 int mhi = 0;
-                if (st.tslot < a.smem_slots) {
-                    const double2 *t2 = reinterpret_cast<const double2 *>(sm.stack + ((size_t)st.tslot * tcpad + lc[j]) * K);
 #pragma unroll
-                    for (int x2 = 0; x2 < K / 2; x2++) {
-                        const double2 l = row2[x2], t = t2[x2];
-                        acc0 = fma(l.x, t.x, acc0);
-                        acc1 = fma(l.y, t.y, acc1);
-                        mhi = max(mhi, max(__double2hiint(t.x), __double2hiint(t.y)));
-                    }
-                } else {
-                    const double2 *t2 = reinterpret_cast<const double2 *>(
-                        a.spill + ((size_t)(st.tslot - a.smem_slots) * a.ncols + col[j]) * K);
-#pragma unroll
-                    for (int x2 = 0; x2 < K / 2; x2++) {
-                        const double2 l = row2[x2], t = t2[x2];
-                        acc0 = fma(l.x, t.x, acc0);
-                        acc1 = fma(l.y, t.y, acc1);
-                        mhi = max(mhi, max(__double2hiint(t.x), __double2hiint(t.y)));
-                    }
+                for (int x2 = 0; x2 < K / 2; x2++) {
+                    const double2 l = row2[x2], t = t2[x2];
+                    acc0 = fma(l.x, t.x, acc0);
+                    acc1 = fma(l.y, t.y, acc1);
+                    mhi = max(mhi, max(__double2hiint(t.x), __double2hiint(t.y)));
                 }
                 int e;
                 const double scale = pow2_scale_from_hi(mhi, e);
-                D[j] = (acc0 + acc1) * scale;
+                D = (acc0 + acc1) * scale;
             }
-        }
-        // child slots never alias this step's own slot (tree_plan.cpp allocates them before
-        // releasing it), so they can be written without waiting for the other threads' reads
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            if (!act[j] || (kind[j] != KIND_MSG && kind[j] != KIND_ROOT)) continue;
-            const size_t tb = (size_t)(tile.cat0 + tcat[j]) * a.n_nodes;
-            // ---- children: messages, product, and the from-above vectors they receive ----
-            double gv[MAXDEG_LOCAL];
-            uint8_t push[MAXDEG_LOCAL];
-            double G = 1.0;
-            const int nch = st.n_child < MAXDEG_LOCAL ? st.n_child : MAXDEG_LOCAL;
-            for (int e = 0; e < nch; e++) {
-                const ChildRef ch = a.down_child[st.child_begin + e];
-                gv[e] = 1.0; push[e] = 0;
-                if (GENERAL && a.present && a.present[(size_t)ch.node * a.ncols + col[j]] == 0) continue;
-                uint8_t ou = BNK_NONE;
-                if (ch.ent < 0 || GENERAL) ou = a.obs[(size_t)ch.node * a.ncols + col[j]];
-                if (ou != BNK_NONE) {
-                    gv[e] = a.T_col[(tb + ch.node) * (K * K) + ou * K + p];
-                } else if (ch.ent < 0) {
-                    double s = 0.0;  // unobserved childless node: sum_x' P_u[p][x'] = sum_x' PT_u[x'][p]
-                    for (int x = 0; x < K; x++) s += a.T_col[(tb + ch.node) * (K * K) + x * K + p];
-                    gv[e] = s;
-                } else {
-                    gv[e] = a.msg[((size_t)ch.ent * a.ncols + col[j]) * K + p];
-                    push[e] = 1;
+            // ---- children: messages, product, and the from-above vectors they receive.  Child slots
+            // never alias this step's own slot (tree_plan.cpp), so they are written without a barrier.
+            if (st.n_child <= 2) {
+                const double g0 = (st.n_child > 0 && b.pu[0]) ? child_value(a, st, b, L0[j], 0, tb[j], col[j], p, K) : 1.0;
+                const double g1 = (st.n_child > 1 && b.pu[1]) ? child_value(a, st, b, L0[j], 1, tb[j], col[j], p, K) : 1.0;
+                U[j] = D * (g0 * g1);
+                if (st.n_child > 0 && b.pu[0] && b.ou[0] == BNK_NONE && st.c_ent[0] >= 0) {
+                    const double t = D * g1;
+                    const int sl = st.c_slot[0];
+                    if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                    else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
                 }
-                G *= gv[e];
-            }
-            U[j] = D[j] * G;
-            gs[(size_t)lc[j] * LROW + p] = U[j];
-            // prefix / suffix products give prod_{w != c} without dividing
-            double pre = D[j];
-            double suf[MAXDEG_LOCAL];
-            {
-                double s = 1.0;
-                for (int e = nch - 1; e >= 0; e--) { suf[e] = s; s *= gv[e]; }
-            }
-            for (int e = 0; e < nch; e++) {
-                if (push[e]) {
+                if (st.n_child > 1 && b.pu[1] && b.ou[1] == BNK_NONE && st.c_ent[1] >= 0) {
+                    const double t = D * g0;
+                    const int sl = st.c_slot[1];
+                    if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                    else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
+                }
+            } else {
+                double gv[MAXDEG_LOCAL], suf[MAXDEG_LOCAL];
+                uint8_t push[MAXDEG_LOCAL];
+                const int nch = st.n_child < MAXDEG_LOCAL ? st.n_child : MAXDEG_LOCAL;
+                double G = 1.0;
+                for (int e = 0; e < nch; e++) {
                     const ChildRef ch = a.down_child[st.child_begin + e];
-                    const double t = pre * suf[e];
-                    if (ch.slot < a.smem_slots) sm.stack[((size_t)ch.slot * tcpad + lc[j]) * K + p] = t;
-                    else a.spill[((size_t)(ch.slot - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
+                    gv[e] = 1.0; push[e] = 0;
+                    const bool pu = (e == 0) ? (b.pu[0] != 0) : (e == 1) ? (b.pu[1] != 0)
+                                  : (!(GENERAL && a.present) || a.present[(size_t)ch.node * a.ncols + col[j]] != 0);
+                    if (!pu) continue;
+                    const uint8_t ou = (e == 0) ? b.ou[0] : (e == 1) ? b.ou[1]
+                                     : ((GENERAL || ch.ent < 0) ? a.obs[(size_t)ch.node * a.ncols + col[j]] : (uint8_t)BNK_NONE);
+                    if (e == 0) {
+                        gv[e] = child_value(a, st, b, L0[j], 0, tb[j], col[j], p, K);
+                    } else if (e == 1) {
+                        gv[e] = child_value(a, st, b, L0[j], 1, tb[j], col[j], p, K);
+                    } else if (ou != BNK_NONE) {
+                        gv[e] = a.T_col[(tb[j] + ch.node) * KK + ou * K + p];
+                    } else if (ch.ent < 0) {
+                        double s = 0.0;
+                        for (int x = 0; x < K; x++) s += a.T_col[(tb[j] + ch.node) * KK + x * K + p];
+                        gv[e] = s;
+                    } else {
+                        gv[e] = a.msg[((size_t)ch.ent * a.ncols + col[j]) * K + p];
+                    }
+                    push[e] = (ou == BNK_NONE && ch.ent >= 0);
+                    G *= gv[e];
                 }
-                pre *= gv[e];
+                U[j] = D * G;
+                {
+                    double s = 1.0;
+                    for (int e = nch - 1; e >= 0; e--) { suf[e] = s; s *= gv[e]; }
+                }
+                double pre = D;
+                for (int e = 0; e < nch; e++) {
+                    if (push[e]) {
+                        const int sl = a.down_child[st.child_begin + e].slot;
+                        const double t = pre * suf[e];
+                        if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                        else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
+                    }
+                    pre *= gv[e];
+                }
             }
+            gs[(size_t)lc[j] * LROW + p] = U[j];
         }
         cp_async_wait<NSTAGE - 2>();  // table of step i + 1 has landed (this thread's copies)
         __syncthreads();              // ... and everybody's; gs and the child slots are visible
-        if (i + NSTAGE < a.n_steps)
-            prefetch_table<K>(a, tile, a.down[i + NSTAGE].node, sm.tab + (i % NSTAGE) * stage_elems);
+        if (i + NSTAGE < n_steps)
+            prefetch_table<K>(a.T_row, a.n_nodes, tile, step_ref(i + NSTAGE).node, sm.tab + (i % NSTAGE) * stage_elems);
+        if (i % PCHUNK == 0) prefetch_prog(a.down, n_steps, i / PCHUNK + 1, sm.prog + (((i / PCHUNK) + 1) & 1) * PCHUNK);
         cp_async_commit();
         // ---- normalise and emit the posterior ----
         const int q = a.qrow ? a.qrow[st.ent] : st.ent;
@@ -416,6 +575,8 @@ __global__ void __launch_bounds__(768) down_kernel(const WalkArgs a)
                 a.out_post[((size_t)q * a.ncols + ocol[j]) * K + p] = out;
             }
         }
+#pragma unroll
+        for (int j = 0; j < CPT; j++) { B0[j] = B1[j]; B1[j] = B2[j]; L0[j] = L1[j]; }
     }
 }
 

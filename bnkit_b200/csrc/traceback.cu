@@ -3,48 +3,97 @@
 //
 // The reference follows per-factor pointer chains recursively; on a tree that is
 //   state[v] = ptr_v[ state[parent(v)] ]     (ptr rows written by the joint up-sweep)
-// walked root-to-leaves.  One thread owns one column and walks the static pre-order
-// program; ancestors' states needed later sit in a per-thread shared-memory stack whose
-// depth is bounded by tree_plan.cpp (heavy child last).
+// walked root-to-leaves over the static pre-order program.
 #include "device_common.cuh"
 
 namespace bnk {
 
-__global__ void __launch_bounds__(128) traceback_kernel(const TracebackArgs a)
+// One warp owns one column: lane p holds "its" pointer byte ptr_v[p] of each step of a batch
+// (the layout the up-sweep wrote; TB_U independent loads in flight per lane), and the chain
+//   state[v] = ptr_v[state[parent]]
+// is resolved with warp shuffles only: the stack of ancestors' states that are needed later
+// (depth bounded by tree_plan.cpp, heavy child last) lives in a register distributed over
+// the lanes -- lane k holds slot k -- so one step costs two dependent shuffles and nothing
+// else sits on the critical path.  REGSTACK = false keeps the stack in shared memory for
+// trees that need more than 32 slots.
+constexpr int TB_U = 16;
+constexpr int TB_WARPS = 8;
+
+template <bool REGSTACK>
+__global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const TracebackArgs a)
 {
-    extern __shared__ uint8_t sstack[];  // [tb_slots][blockDim.x]
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ uint8_t tb_smem[];  // [TB_WARPS][tb_slots] when !REGSTACK
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int col = blockIdx.x * TB_WARPS + wid;
     if (col >= a.ncols) return;
     const int gcat = a.cat_of_col[col];
     if (gcat < a.cat_lo || gcat >= a.cat_hi) return;
-    const int K = a.K, nt = blockDim.x, tid = threadIdx.x;
-    for (int i = 0; i < a.n_steps; i++) {
-        const DownStep st = a.down[i];
-        const size_t ec = (size_t)st.ent * a.ncols + col;
-        const uint8_t kind = a.kind[ec];
-        uint8_t s = BNK_NONE;
-        if (kind == KIND_MSG) {
-            const uint8_t ps = sstack[st.pslot * nt + tid];
-            s = a.ptr[ec * K + ps];
-        } else if (kind == KIND_ROOT) {
-            s = a.ptr[ec * K];
-        } else if (kind == KIND_OBS) {
-            s = a.obs[(size_t)st.node * a.ncols + col];
+    const int K = a.K;
+    uint8_t *st = tb_smem + wid * (a.tb_slots > 0 ? a.tb_slots : 1);
+    const uint8_t *pcol = a.ptr + (size_t)col * K + (lane < K ? lane : 0);
+    const uint8_t *kcol = a.kind ? a.kind + col : nullptr;
+    const unsigned row_stride = (unsigned)(a.ncols * K), ncols_u = (unsigned)a.ncols;
+    const unsigned FULL = 0xffffffffu;
+    int stack_reg = BNK_NONE;  // REGSTACK: slot `lane`
+
+    // lane u of the warp carries the program fields of step b0 + u
+    int n_ent = 0, n_node = 0, n_meta = 0;
+    auto fetch = [&](int b0) {
+        const int si = b0 + lane;
+        if (lane < TB_U && si < a.n_steps) {
+            const Step &sp = a.down[si];
+            n_ent = sp.ent; n_node = sp.node;
+            n_meta = (sp.pslot + 1) | ((sp.oslot + 1) << 12) | ((sp.parent < 0 ? 1 : 0) << 24);
         }
-        if (st.oslot >= 0) sstack[st.oslot * nt + tid] = s;
-        a.out_state[(size_t)st.node * a.ncols + col] = s;
+    };
+    fetch(0);
+    for (int b0 = 0; b0 < a.n_steps; b0 += TB_U) {
+        const int c_ent = n_ent, c_node = n_node, c_meta = n_meta;
+        fetch(b0 + TB_U);
+        int byte[TB_U];
+#pragma unroll
+        for (int u = 0; u < TB_U; u++) {
+            const unsigned ent = (unsigned)__shfl_sync(FULL, c_ent, u);
+            byte[u] = (b0 + u < a.n_steps) ? pcol[(size_t)ent * row_stride] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < TB_U; u++) {
+            if (b0 + u >= a.n_steps) break;
+            const int node = __shfl_sync(FULL, c_node, u), meta = __shfl_sync(FULL, c_meta, u);
+            const int pslot = (meta & 0xfff) - 1, oslot = ((meta >> 12) & 0xfff) - 1;
+            int kind = (meta >> 24) ? KIND_ROOT : KIND_MSG;
+            if (kcol) kind = kcol[(size_t)(unsigned)__shfl_sync(FULL, c_ent, u) * ncols_u];
+            int src = 0;
+            if (REGSTACK) {
+                const int ps = __shfl_sync(FULL, stack_reg, pslot & 31);
+                if (kind == KIND_MSG) src = ps;
+            } else if (kind == KIND_MSG) {
+                src = st[pslot];
+            }
+            int s = __shfl_sync(FULL, byte[u], src & 31);
+            if (kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + col];
+            else if (kind != KIND_MSG && kind != KIND_ROOT) s = BNK_NONE;
+            if (REGSTACK) {
+                if (lane == oslot) stack_reg = s;
+            } else {
+                if (lane == 0 && oslot >= 0) st[oslot] = (uint8_t)s;
+                __syncwarp();
+            }
+            if (lane == 0) a.out_state[(size_t)(unsigned)node * ncols_u + col] = (uint8_t)s;
+        }
     }
 }
 
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t st)
 {
-    const int threads = 128;
-    const size_t smem = (size_t)(a.tb_slots > 0 ? a.tb_slots : 1) * threads;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    if (a.tb_slots >= 4095) return cudaErrorInvalidValue;
+    const unsigned grid = (a.ncols + TB_WARPS - 1) / TB_WARPS;
+    if (a.tb_slots <= 32) {
+        traceback_kernel<true><<<grid, TB_WARPS * 32, 0, st>>>(a);
+    } else {
+        const size_t smem = (size_t)TB_WARPS * a.tb_slots;
+        traceback_kernel<false><<<grid, TB_WARPS * 32, smem, st>>>(a);
     }
-    traceback_kernel<<<(a.ncols + threads - 1) / threads, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

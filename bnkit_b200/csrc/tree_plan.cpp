@@ -58,6 +58,8 @@ static void build_plan(bnk_tree *t)
         }
     }
     t->n_int = (int32_t)t->node_of_ent.size();
+    t->max_children = 0;
+    for (int32_t i = 0; i < n; i++) t->max_children = std::max(t->max_children, t->first[i + 1] - t->first[i]);
 
     // weight = number of internal nodes in the subtree (children have larger indices)
     std::vector<int32_t> weight(n, 0);
@@ -113,12 +115,17 @@ static void build_plan(bnk_tree *t)
         SlotPool pool;
         std::vector<int32_t> slot_of(n, -1);
         for (int32_t v : up_order) {
-            UpStep s;
+            Step s;
+            std::memset(&s, 0, sizeof(s));
             s.node = v; s.parent = t->parent[v]; s.ent = t->ent_of_node[v];
             s.child_begin = (int32_t)t->up_child.size();
             s.n_child = t->first[v + 1] - t->first[v];
+            s.pslot = s.oslot = -1;
+            for (int k = 0; k < 2; k++) { s.c_node[k] = -1; s.c_slot[k] = -1; s.c_ent[k] = -1; }
             for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) {
                 const int32_t u = t->kids[e];
+                const int k = e - t->first[v];
+                if (k < 2) { s.c_node[k] = u; s.c_slot[k] = slot_of[u]; s.c_ent[k] = t->ent_of_node[u]; }
                 t->up_child.push_back(ChildRef{u, slot_of[u], t->ent_of_node[u]});
             }
             for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) pool.release(slot_of[t->kids[e]]);
@@ -134,16 +141,20 @@ static void build_plan(bnk_tree *t)
         SlotPool tpool, spool;
         std::vector<int32_t> tslot(n, -1), sslot(n, -1), remaining(n, 0);
         for (int32_t v : down_order) {
-            DownStep s;
+            Step s;
+            std::memset(&s, 0, sizeof(s));
             s.node = v; s.parent = t->parent[v]; s.ent = t->ent_of_node[v];
-            s.tslot = tslot[v];
+            s.slot = tslot[v];
             s.child_begin = (int32_t)t->down_child.size();
             s.n_child = t->first[v + 1] - t->first[v];
+            for (int k = 0; k < 2; k++) { s.c_node[k] = -1; s.c_slot[k] = -1; s.c_ent[k] = -1; }
             int32_t n_int_child = 0;
             for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) {
                 const int32_t u = t->kids[e];
+                const int k = e - t->first[v];
                 int32_t sl = -1;
                 if (t->ent_of_node[u] >= 0) { sl = tpool.alloc(); tslot[u] = sl; n_int_child++; }
+                if (k < 2) { s.c_node[k] = u; s.c_slot[k] = sl; s.c_ent[k] = t->ent_of_node[u]; }
                 t->down_child.push_back(ChildRef{u, sl, t->ent_of_node[u]});
             }
             tpool.release(tslot[v]);  // after the children's slots: a child never reuses its parent's slot in the same step
