@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's interface for the hot path, over libbnkgpu.
+
+The reference is Java; this image has no JDK, so (as the task allows) the host side above
+the C ABI is written in Python with the reference's names, argument meaning and error
+behaviour for exactly this path:
+
+    bn.ctmc.SubstModel.createModel / getDomain / getProbs   src/bn/ctmc/SubstModel.java:303-385
+    dat.phylo.IdxTree (parents / distances / labels, JSON)   src/dat/phylo/IdxTree.java:27-32, :277-351, :411-503
+    dat.file.Newick.parse (0.0 -> 1e-5)                      src/dat/file/Newick.java:47-131, :170-257
+    dat.phylo.TreeInstance                                   src/dat/phylo/TreeInstance.java:21-57
+    asr.MaxLhoodJoint / asr.MaxLhoodMarginal (TreeDecor<E>)  src/asr/MaxLhoodJoint.java:39-170, src/asr/MaxLhoodMarginal.java:39-108
+    asr.Prediction.getJoint / getMarginal                    src/asr/Prediction.java:555-649
+
+The per-column decorators exist for API parity (and are what the parity tests drive, like the
+reference's own MaxLhoodJointTest / MaxLhoodMarginalTest); the batch entry points of
+Prediction are the drop-in that matters: one call, every column, on the GPU.
+Everything numeric happens in libbnkgpu.so; nothing here falls back to the CPU.
+"""
+import json
+
+import numpy as np
+
+from . import lib
+
+ALPHABETS = {
+    "LG": "ARNDCQEGHILKMFPSTWYV", "JTT": "ARNDCQEGHILKMFPSTWYV", "WAG": "ARNDCQEGHILKMFPSTWYV",
+    "Dayhoff": "ARNDCQEGHILKMFPSTWYV", "JC": "ACGT", "Yang": "ACGT",
+}
+NONE = lib.NONE
+
+
+class ASRRuntimeException(RuntimeError):
+    """asr.ASRRuntimeException (unchecked)"""
+
+
+class EnumDistrib:
+    """bn.prob.EnumDistrib: a normalised distribution over the model's domain (index order = model alphabet)."""
+
+    def __init__(self, domain, probs):
+        self.domain = domain
+        self.distrib = np.asarray(probs, dtype=np.float64)
+
+    def get(self, key):
+        return float(self.distrib[key if isinstance(key, (int, np.integer)) else self.domain.index(key)])
+
+    def getMaxIndex(self):  # EnumDistrib.java:274-281: first strict maximum, ascending
+        mi = 0
+        for i in range(1, len(self.distrib)):
+            if self.distrib[mi] < self.distrib[i]:
+                mi = i
+        return mi
+
+    def getMax(self):
+        return self.domain[self.getMaxIndex()]
+
+    def __repr__(self):
+        return "<" + " ".join("%s:%.3f" % (s, p) for s, p in zip(self.domain, self.distrib)) + ">"
+
+
+class SubstModel:
+    """bn.ctmc.SubstModel facade; the 20x20 arithmetic lives in libbnkgpu (host eigensystem, device P(t))."""
+
+    def __init__(self, handle, name, domain):
+        self.handle, self.name, self.domain = handle, name, list(domain)
+
+    @staticmethod
+    def createModel(name, empiricalFreqs=None):
+        if name not in ALPHABETS:
+            return None  # SubstModel.createModel returns null for unknown names (SubstModel.java:334-338)
+        return SubstModel(lib.Model(name, F=empiricalFreqs), name, ALPHABETS[name])
+
+    @staticmethod
+    def fromEigen(F, evec, ievec, evals, domain, name="custom"):
+        """What the JNI stub does with the JVM's own SubstModel.getRexp()."""
+        return SubstModel(lib.Model(eigen=(len(F), F, evec, ievec, evals)), name, domain)
+
+    def getName(self):
+        return self.name
+
+    def getDomain(self):
+        return self.domain
+
+    def getProbs(self, t):
+        """P[i][j] = P(child = j | parent = i, t), computed on the device (SubstModel.java:303-327)."""
+        ws = lib.Workspace(self.handle, lib.Tree([-1], [0.0]), 1)
+        try:
+            return ws.probs([t], want_log=False)[0]
+        finally:
+            ws.close()
+
+
+class IdxTree:
+    """dat.phylo.IdxTree: nodes indexed depth-first, parent index < child index."""
+
+    def __init__(self, parents, distances=None, labels=None):
+        self.parent = np.asarray(parents, dtype=np.int32)
+        n = len(self.parent)
+        self.distance = np.zeros(n) if distances is None else np.asarray(distances, dtype=np.float64).copy()
+        self.labels = list(labels) if labels is not None else [str(i) for i in range(n)]
+        self.children = [[] for _ in range(n)]
+        for i, p in enumerate(self.parent):
+            if p >= 0:
+                self.children[p].append(i)
+        self._handle = None
+
+    # ---- construction ----
+    @staticmethod
+    def fromJSON(obj):
+        """{"Parents": [...], "Labels": [...], "Distances": [...], "Branchpoints": n} (IdxTree.java:277-351)"""
+        if isinstance(obj, str):
+            obj = json.loads(obj)
+        return IdxTree(obj["Parents"], obj.get("Distances"), obj.get("Labels"))
+
+    def toJSON(self):
+        return {"Parents": [int(p) for p in self.parent], "Labels": list(self.labels),
+                "Distances": [float(d) for d in self.distance], "Branchpoints": self.getSize()}
+
+    @staticmethod
+    def fromNewick(text):
+        """Newick -> IdxTree.  Ancestors are named N0, N1, ... in depth-first order unless labelled;
+        a distance of exactly 0.0 becomes 1e-5 (Newick.java:54-56, :103-105)."""
+        s = "".join(text.split())
+        if s.endswith(";"):
+            s = s[:-1]
+        parents, dists, labels = [], [], []
+        pos = 0
+        anc = [0]
+
+        def node(par):
+            nonlocal pos
+            idx = len(parents)
+            parents.append(par)
+            dists.append(0.0)
+            labels.append(None)
+            internal = False
+            if pos < len(s) and s[pos] == "(":
+                internal = True
+                my_anc = anc[0]
+                anc[0] += 1
+                pos += 1
+                while True:
+                    node(idx)
+                    if s[pos] == ",":
+                        pos += 1
+                        continue
+                    if s[pos] == ")":
+                        pos += 1
+                        break
+                    raise ValueError("Newick: expected ',' or ')' at %d" % pos)
+            start = pos
+            while pos < len(s) and s[pos] not in ",():":
+                pos += 1
+            name = s[start:pos]
+            if pos < len(s) and s[pos] == ":":
+                pos += 1
+                start = pos
+                while pos < len(s) and s[pos] not in ",()":
+                    pos += 1
+                try:
+                    d = float(s[start:pos])
+                except ValueError:
+                    raise RuntimeError("A distance value couldn't be parsed as a number. The value is \"%s\"" % s[start:pos])
+                dists[idx] = 0.00001 if d == 0.0 else d
+            labels[idx] = name if name else ("N%d" % my_anc if internal else "")
+            return idx
+
+        import sys
+        old = sys.getrecursionlimit()
+        sys.setrecursionlimit(max(old, 100000))
+        try:
+            node(-1)
+        finally:
+            sys.setrecursionlimit(old)
+        return IdxTree(parents, dists, labels)
+
+    # ---- accessors (IdxTree.java) ----
+    def getSize(self):
+        return len(self.parent)
+
+    def getParent(self, idx):
+        return int(self.parent[idx])
+
+    def getChildren(self, idx):
+        return list(self.children[idx])
+
+    def isLeaf(self, idx):
+        return len(self.children[idx]) == 0
+
+    def getDistance(self, idx):
+        return float(self.distance[idx])
+
+    def getLabel(self, idx):
+        return self.labels[idx]
+
+    def getIndex(self, label):
+        for i, l in enumerate(self.labels):
+            if l == label:
+                return i
+        return -1
+
+    def getLeaves(self):
+        return [i for i in range(self.getSize()) if self.isLeaf(i)]
+
+    def getAncestors(self):
+        return [i for i in range(self.getSize()) if not self.isLeaf(i)]
+
+    def isConnected(self, idx):  # IdxTree.java:746-751
+        return len(self.children[idx]) > 0 or self.parent[idx] != -1
+
+    def handle(self):
+        if self._handle is None:
+            self._handle = lib.Tree(self.parent, self.distance)
+        return self._handle
+
+    def getPrunedMask(self, pruneMe, removeOrphans=True):
+        """getPrunedIndex + createPrunedTree (IdxTree.java:411-503) as a presence mask over the
+        ORIGINAL indices: mask[i] = 1 iff node i survives (the GPU path keeps one shared topology)."""
+        present = np.ones((self.getSize(), 1), dtype=np.uint8)
+        for i in pruneMe:
+            present[i, 0] = 0
+        if removeOrphans:
+            present = self.handle().prune_orphans(present)
+        return present[:, 0]
+
+    def getPrunedIndex(self, pruneMe, removeOrphans=True):
+        mask = self.getPrunedMask(pruneMe, removeOrphans)
+        match, k = [], 0
+        for i in range(self.getSize()):
+            if mask[i]:
+                match.append(k)
+                k += 1
+            else:
+                match.append(-1)
+        return match
+
+    @staticmethod
+    def createPrunedTree(source, prunedIndex):
+        keep = [i for i, m in enumerate(prunedIndex) if m >= 0]
+        parents = []
+        for i in keep:
+            p = source.parent[i]
+            parents.append(prunedIndex[p] if p >= 0 else -1)
+        return IdxTree(parents, [source.distance[i] for i in keep], [source.labels[i] for i in keep])
+
+    def getNRoots(self):
+        return int((self.parent < 0).sum())
+
+
+class TreeInstance:
+    """dat.phylo.TreeInstance: one value (or None) per branch point of a tree."""
+
+    def __init__(self, tree, assign):
+        self.tree = tree
+        if isinstance(assign, dict):
+            arr = [None] * tree.getSize()
+            for k, v in assign.items():
+                arr[k] = v
+            assign = arr
+        self.instance = list(assign)
+
+    def getInstance(self, idx):
+        return self.instance[idx]
+
+    def getSize(self):
+        return len(self.instance)
+
+
+def _encode(values, domain):
+    out = np.full(len(values), NONE, dtype=np.uint8)
+    for i, v in enumerate(values):
+        if v is not None:
+            try:
+                out[i] = domain.index(v)
+            except ValueError:
+                raise ASRRuntimeException("Value %r is not in the model's domain" % (v,))
+    return out
+
+
+class MaxLhoodJoint:
+    """asr.MaxLhoodJoint: joint ML reconstruction of every uninstantiated, connected branch point."""
+
+    def __init__(self, tree, model, rate=1.0):
+        self.tree, self.model, self.rate = tree, model, float(rate)
+        self.values = None
+
+    def decorate(self, ti):
+        obs = _encode(ti.instance, self.model.domain)[:, None]
+        ws = lib.Workspace(self.model.handle, self.tree.handle(), 1)
+        try:
+            ws.set_rates(1, [self.rate])
+            st = ws.joint(obs)[:, 0]
+        finally:
+            ws.close()
+        self.values = [None if s == NONE else self.model.domain[s] for s in st]
+
+    def getDecoration(self, idx):
+        return self.values[idx]
+
+
+class MaxLhoodMarginal:
+    """asr.MaxLhoodMarginal: posterior distribution at one branch point."""
+
+    def __init__(self, bpidx, tree, model, rate=1.0):
+        self.bpidx, self.tree, self.model, self.rate = int(bpidx), tree, model, float(rate)
+        self.value = None
+
+    def decorate(self, ti):
+        obs = _encode(ti.instance, self.model.domain)[:, None]
+        ws = lib.Workspace(self.model.handle, self.tree.handle(), 1)
+        try:
+            ws.set_rates(1, [self.rate])
+            post, _ = ws.marginal(obs, query=[self.bpidx], want_logl=False)
+        finally:
+            ws.close()
+        p = post[0, 0]
+        self.value = None if np.isnan(p).any() else EnumDistrib(self.model.domain, p)
+
+    def getDecoration(self, idx):
+        if idx == self.bpidx:
+            return self.value
+        raise ASRRuntimeException("Invalid ancestor index, not defined for marginal inference: %d" % idx)
+
+
+class Prediction:
+    """The character-inference half of asr.Prediction: getJoint / getMarginal over all columns.
+
+    states:  [n_nodes][n_cols] characters (or None) at the extant leaves, as POGTree.getNodeInstance
+             (src/dat/pog/POGTree.java:419-436) yields per column;
+    present: [n_nodes][n_cols] 0/1, the per-column pruned trees of Prediction.getTree
+             (src/asr/Prediction.java:329-402) as a mask, or None when every node is present.
+    """
+
+    def __init__(self, tree, states, present=None, device=-1):
+        self.tree = tree
+        self.states = states
+        self.present = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+        self.device = device
+        self.n_cols = len(states[0]) if len(states) else 0
+        self._ws = None
+        self._ws_model = None
+
+    def _obs(self, model):
+        n = self.tree.getSize()
+        obs = np.full((n, self.n_cols), NONE, dtype=np.uint8)
+        lut = {c: i for i, c in enumerate(model.domain)}
+        for v in range(n):
+            row = self.states[v]
+            for c in range(self.n_cols):
+                ch = row[c]
+                if ch is not None:
+                    if ch not in lut:
+                        raise ASRRuntimeException("Invalid character %r for model %s" % (ch, model.getName()))
+                    obs[v, c] = lut[ch]
+        return obs
+
+    def _workspace(self, model, rates):
+        if self._ws is None or self._ws_model is not model:
+            if self._ws is not None:
+                self._ws.close()
+            self._ws = lib.Workspace(model.handle, self.tree.handle(), max(self.n_cols, 1), device=self.device)
+            self._ws_model = model
+        self._ws.set_rates(self.n_cols, rates)  # None => 1.0 per column (Prediction.java:615-618)
+        return self._ws
+
+    def getJoint(self, model, rates=None):
+        """Object[][] states[bpidx][pos]: Character from model.getDomain() or None (Prediction.java:614-649)."""
+        ws = self._workspace(model, rates)
+        st = ws.joint(self._obs(model), self.present)
+        dom = model.domain
+        return [[None if s == NONE else dom[s] for s in row] for row in st]
+
+    def getMarginal(self, ancestor, model, rates=None):
+        """EnumDistrib[] over positions for one ancestor (index or label), None where it is absent
+        (Prediction.java:555-597); an unknown ancestor raises ASRRuntimeException (:561-562)."""
+        idx = ancestor if isinstance(ancestor, (int, np.integer)) else self.tree.getIndex(ancestor)
+        if isinstance(ancestor, str) and idx < 0 and ancestor.startswith("N"):
+            idx = self.tree.getIndex(ancestor[1:])
+        if idx < 0 or idx >= self.tree.getSize():
+            raise ASRRuntimeException("Invalid ancestor ID " + str(ancestor))
+        ws = self._workspace(model, rates)
+        try:
+            post, _ = ws.marginal(self._obs(model), self.present, query=[idx], want_logl=False)
+        except lib.BnkError as e:
+            if e.code == -7:
+                raise ASRRuntimeException("Invalid ancestor ID " + str(ancestor))
+            raise
+        return [None if np.isnan(post[0, c]).any() else EnumDistrib(model.domain, post[0, c]) for c in range(self.n_cols)]
+
+    def getMarginalAll(self, model, rates=None):
+        """All ancestors at once (what `-m` looped over every N<k> costs the reference 37 full passes)."""
+        ws = self._workspace(model, rates)
+        return ws.marginal(self._obs(model), self.present)
+
+    def close(self):
+        if self._ws is not None:
+            self._ws.close()
+            self._ws = None
+
+
+def load_alignment(path):
+    """FASTA or CLUSTAL -> (names, rows of characters with '-' -> None)   (dat/file/Utils.java:103-138)."""
+    names, seqs = [], {}
+    with open(path) as fh:
+        first = fh.readline()
+        fh.seek(0)
+        if first.startswith(">"):
+            cur = None
+            for line in fh:
+                line = line.strip()
+                if not line:
+                    continue
+                if line.startswith(">"):
+                    cur = line[1:].split()[0]
+                    names.append(cur)
+                    seqs[cur] = []
+                else:
+                    seqs[cur].append(line)
+        else:  # CLUSTAL
+            for line in fh:
+                if not line.strip() or line.startswith("CLUSTAL") or line[0] in " \t":
+                    continue
+                parts = line.split()
+                if len(parts) < 2:
+                    continue
+                if parts[0] not in seqs:
+                    names.append(parts[0])
+                    seqs[parts[0]] = []
+                seqs[parts[0]].append(parts[1])
+    rows = []
+    for nm in names:
+        s = "".join(seqs[nm])
+        rows.append([None if ch == "-" else ch for ch in s])
+    return names, rows

@@ -1,0 +1,164 @@
+"""GPU parity on the reference's own data files (committed fixtures), through the Java-API mirror,
+and size-independent properties at the full BASELINE.json size."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import NONE, leaves_of, random_obs, random_tree
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def _dataset(name):
+    from bnkit_b200 import synth
+    d = json.load(open(os.path.join(GOLD, name)))
+    parent = np.array(d["tree"]["Parents"], dtype=np.int32)
+    dist = np.array(d["tree"]["Distances"])
+    labels = d["tree"]["Labels"]
+    n, C = len(parent), len(d["seqs"][0])
+    obs = np.full((n, C), NONE, np.uint8)
+    for name_, seq in zip(d["names"], d["seqs"]):
+        v = labels.index(name_)
+        obs[v] = [NONE if ch == "-" else AA.index(ch) for ch in seq]
+    leaf = leaves_of(parent)
+    present = synth.path_presence_mask(parent, (obs != NONE) & leaf[:, None])
+    return d, parent, dist, obs, present
+
+
+def test_c1_documented_result_and_oracle_parity(bnk, oracle):
+    """BASELINE configs[0]: data/66.*; docs/json-api.md:113-122 pins N0..N2 = A, H at columns 2, 4 (JTT)."""
+    d, parent, dist, obs, present = _dataset("c1_66.json")
+    for name in ("JTT", "LG"):
+        m, om = bnk.Model(name), oracle.Model(name)
+        ws = bnk.Workspace(m, bnk.Tree(parent, dist), obs.shape[1])
+        st = ws.joint(obs, present)
+        assert np.array_equal(st, oracle.fast_joint(om, parent, dist, obs, present))
+        if name == "JTT":
+            for anc in (0, 1, 2):
+                cols = [c for c in range(obs.shape[1]) if present[anc, c]]
+                assert cols == d["doc_result"]["indices"]
+                assert [AA[st[anc, c]] for c in cols] == d["doc_result"]["values"]
+        ws.close()
+
+
+def test_c2_marginal_all_ancestors(bnk, oracle):
+    """BASELINE configs[1]: data/3_2_1_1_filt.*, JTT, marginal at all 37 ancestors x 1307 columns."""
+    d, parent, dist, obs, present = _dataset("c2_3_2_1_1_filt.json")
+    m, om = bnk.Model("JTT"), oracle.Model("JTT")
+    tree = bnk.Tree(parent, dist)
+    assert tree.n == 76 and tree.n_internal == 37 and obs.shape[1] == 1307
+    ws = bnk.Workspace(m, tree, obs.shape[1])
+    post, logl = ws.marginal(obs, present)
+    wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, present, nthreads=8)
+    wp = wpost[tree.internal_nodes()]
+    assert np.array_equal(np.isnan(post), np.isnan(wp))
+    ok = ~np.isnan(wp)
+    assert (np.abs(post[ok] - wp[ok]) <= 1e-9 * np.maximum(wp[ok], 1e-3)).all()
+    assert np.allclose(logl, wlogl, rtol=1e-9, atol=1e-12)
+    assert np.array_equal(ws.joint(obs, present), oracle.fast_joint(om, parent, dist, obs, present, nthreads=8))
+    # gap-free variant (no mask): gaps replaced by drawn residues
+    rng = np.random.default_rng(6)
+    leaf = leaves_of(parent)
+    obs2 = obs.copy()
+    fill = (obs2 == NONE) & leaf[:, None]
+    obs2[fill] = rng.integers(0, 20, fill.sum())
+    post2, logl2 = ws.marginal(obs2)
+    wpost2, wlogl2 = oracle.fast_marginal(om, parent, dist, obs2, nthreads=8)
+    assert np.allclose(post2, wpost2[tree.internal_nodes()], rtol=1e-9, atol=1e-12)
+    assert np.allclose(logl2, wlogl2, rtol=1e-9)
+    ws.close()
+
+
+def test_java_api_mirror_against_bruteforce(bnk, oracle):
+    """The reference's own test method (MaxLhoodJointTest.joint1, MaxLhoodMarginalTest.marginal1) driven
+    through the mirrored classes: TreeInstance -> MaxLhoodJoint / MaxLhoodMarginal.decorate -> getDecoration."""
+    from bnkit_b200.phylo import ASRRuntimeException, IdxTree, MaxLhoodJoint, MaxLhoodMarginal, SubstModel, TreeInstance
+    model = SubstModel.createModel("JC")
+    om = oracle.Model("JC")
+    dom = model.getDomain()
+    for seed in range(12):
+        rng = np.random.default_rng(300 + seed)
+        parent, dist = random_tree(rng, int(rng.integers(3, 8)))
+        tree = IdxTree(parent, dist)
+        assign = [dom[int(rng.integers(0, 4))] if tree.isLeaf(i) else None for i in range(tree.getSize())]
+        ti = TreeInstance(tree, assign)
+        obs = np.array([NONE if a is None else dom.index(a) for a in assign], np.uint8)
+        b = oracle.brute(om, parent, dist, obs)
+        mlj = MaxLhoodJoint(tree, model)
+        mlj.decorate(ti)
+        got = [mlj.getDecoration(i) for i in range(tree.getSize())]
+        want = [dom[s] for s in oracle.fast_joint(om, parent, dist, obs[:, None])[:, 0]]
+        assert got == want
+        mlm = MaxLhoodMarginal(0, tree, model)
+        mlm.decorate(ti)
+        assert np.allclose(mlm.getDecoration(0).distrib, b["post"][0], atol=1e-9)
+        with pytest.raises(ASRRuntimeException):
+            mlm.getDecoration(1)
+
+
+def test_prediction_batch_entry_points(bnk, oracle):
+    from bnkit_b200.phylo import ASRRuntimeException, IdxTree, Prediction, SubstModel
+    d, parent, dist, obs, present = _dataset("c1_66.json")
+    tree = IdxTree.fromJSON(d["tree"])
+    states = [[None] * obs.shape[1] for _ in range(tree.getSize())]
+    for name_, seq in zip(d["names"], d["seqs"]):
+        states[tree.getIndex(name_)] = [None if ch == "-" else ch for ch in seq]
+    model = SubstModel.createModel("LG")
+    pred = Prediction(tree, states, present)
+    joint = pred.getJoint(model)
+    want = oracle.fast_joint(oracle.Model("LG"), parent, dist, obs, present)
+    assert [[None if s == NONE else AA[s] for s in row] for row in want] == joint
+    marg = pred.getMarginal("N0", model)
+    assert [x is None for x in marg] == [not present[0, c] for c in range(obs.shape[1])]
+    with pytest.raises(ASRRuntimeException):
+        pred.getMarginal("N999", model)
+    rates = [0.5, 1.0, 2.0, 1.0, 0.25]
+    j2 = pred.getJoint(model, rates)
+    w2 = oracle.fast_joint(oracle.Model("LG"), parent, dist, obs, present, rates)
+    assert [[None if s == NONE else AA[s] for s in row] for row in w2] == j2
+    pred.close()
+
+
+def test_full_size_properties_c3(bnk):
+    """BASELINE configs[2] at full size (10,000 leaves x 5,000 columns, LG + Gamma4): properties that
+    need no oracle -- tile-geometry invariance (bit-identical states), column-permutation
+    equivariance, posteriors sum to 1, sum of column log-likelihoods == the reduced sum."""
+    from bnkit_b200 import synth
+    n_cols = 5000
+    parent, dist = synth.balanced_tree(10000, seed=1)
+    m = bnk.Model("LG")
+    r4 = synth.gamma_category_rates(0.5, 4)
+    rng = np.random.default_rng(4)
+    rates = r4[rng.integers(0, 4, n_cols)]
+    leaf = leaves_of(parent)
+    obs = np.full((len(parent), n_cols), NONE, np.uint8)
+    obs[leaf] = rng.integers(0, 20, (leaf.sum(), 1)) ^ (rng.random((leaf.sum(), n_cols)) < 0.15).astype(np.uint8)
+    tree = bnk.Tree(parent, dist)
+    ws = bnk.Workspace(m, tree, n_cols)
+    ws.set_rates(n_cols, rates)
+    st = ws.joint(obs)
+    logl, total = ws.loglik(obs)
+    assert np.isfinite(logl).all() and np.isclose(total, logl.sum(), rtol=1e-12)
+    assert (st[~leaf] < 20).all() and np.array_equal(st[leaf], obs[leaf])
+    # other tile geometry and the general kernels give bit-identical states
+    for tile, cpt in ((34, 2), (11, -1)):
+        ws2 = bnk.Workspace(m, tree, n_cols)
+        ws2.configure(tile, cpt)
+        ws2.set_rates(n_cols, rates)
+        assert np.array_equal(ws2.joint(obs), st)
+        l2, _ = ws2.loglik(obs)
+        assert np.allclose(l2, logl, rtol=1e-12)
+        ws2.close()
+    # permuting columns permutes results
+    perm = rng.permutation(n_cols)
+    ws.set_rates(n_cols, rates[perm])
+    assert np.array_equal(ws.joint(np.ascontiguousarray(obs[:, perm])), st[:, perm])
+    # posteriors of a subset of ancestors are distributions
+    q = tree.internal_nodes()[::997]
+    post, _ = ws.marginal(np.ascontiguousarray(obs[:, perm]), query=q)
+    assert np.allclose(post.sum(-1), 1.0, atol=1e-12) and (post >= 0).all()
+    ws.close()

@@ -1,0 +1,92 @@
+"""Host-side logic that needs no GPU: the Java-API mirror's parsers and tree bookkeeping, the
+synthetic workload generators, and the column sharding used by the multi-GPU path."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_newick_matches_documented_idxtree(bnk):
+    from bnkit_b200.phylo import IdxTree
+    c1 = json.load(open(os.path.join(ROOT, "tests", "golden", "c1_66.json")))
+    t = IdxTree.fromJSON(c1["tree"])
+    assert t.getSize() == 131 and len(t.getLeaves()) == 66 and t.getNRoots() == 1
+    assert [int(p) for p in t.parent] == c1["doc_parents"]         # docs/json-api.md:103-107
+    # ancestor labels N<k> in depth-first order <-> the doc's "0", "1", ...
+    anc = [l for l in c1["doc_labels"] if l.isdigit()]
+    mine = [t.getLabel(i) for i in t.getAncestors()]
+    assert mine[: len(anc)] == ["N" + a for a in anc]
+    assert IdxTree.fromJSON(t.toJSON()).toJSON() == t.toJSON()
+
+
+def test_newick_zero_distance_and_labels(bnk):
+    from bnkit_b200.phylo import IdxTree
+    t = IdxTree.fromNewick("((a:0.0,b:0.5)x:0.25,(c:1e-3,d:2):0.0,e:3);")
+    assert t.getSize() == 8 and [int(p) for p in t.parent] == [-1, 0, 1, 1, 0, 4, 4, 0]
+    assert t.getLabel(1) == "x" and t.getLabel(0) == "N0" and t.getLabel(4) == "N2"
+    assert t.getDistance(2) == 0.00001 and t.getDistance(4) == 0.00001   # Newick.java:54-56, :103-105
+    assert t.getChildren(0) == [1, 4, 7] and t.isLeaf(7) and t.isConnected(0)
+    with pytest.raises(RuntimeError):
+        IdxTree.fromNewick("(a:xyz,b:1);")
+
+
+def test_pruned_tree_fixture_through_the_mirror(bnk):
+    from bnkit_b200.phylo import IdxTree
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "idxtree_prune.json")))
+    t = IdxTree(fx["parents"])
+    for case in fx["cases"]:
+        idx = t.getPrunedIndex(set(case["prune"]), removeOrphans=False)
+        pruned = IdxTree.createPrunedTree(t, idx)
+        assert pruned.getSize() == t.getSize() - case["removed"] and pruned.getNRoots() == case["roots"]
+        if case["same_size_with_orphan_removal"]:
+            idx2 = t.getPrunedIndex(set(case["prune"]), removeOrphans=True)
+            assert IdxTree.createPrunedTree(t, idx2).getSize() == pruned.getSize()
+
+
+def test_substmodel_registry(bnk):
+    from bnkit_b200.phylo import SubstModel
+    assert SubstModel.createModel("nope") is None
+    m = SubstModel.createModel("JTT")
+    assert "".join(m.getDomain()) == "ARNDCQEGHILKMFPSTWYV" and m.getName() == "JTT"
+    assert "".join(SubstModel.createModel("JC").getDomain()) == "ACGT"
+
+
+def test_synthetic_generators(bnk):
+    from bnkit_b200 import lib, synth
+    for maker, n_leaves in ((synth.balanced_tree, 37), (synth.caterpillar_tree, 37), (synth.random_tree, 37)):
+        parent, dist = maker(n_leaves)
+        assert len(parent) == 2 * n_leaves - 1 and (parent[1:] < np.arange(1, len(parent))).all() and parent[0] == -1
+        assert (dist[1:] >= 1e-7).all()
+    parent, _ = synth.balanced_tree(1024)
+    depth = np.zeros(len(parent), int)
+    for v in range(1, len(parent)):
+        depth[v] = depth[parent[v]] + 1
+    assert depth.max() == 10
+    parent, _ = synth.caterpillar_tree(100)
+    depth = np.zeros(len(parent), int)
+    for v in range(1, len(parent)):
+        depth[v] = depth[parent[v]] + 1
+    assert depth.max() == 99
+    r = synth.gamma_category_rates(0.5, 4)
+    assert np.isclose(r.mean(), 1.0) and (np.diff(r) > 0).all()
+    parts = lib.Model("LG").parts()
+    parent, dist = synth.balanced_tree(16)
+    obs = synth.simulate_alignment(parent, dist, parts, 50, r[np.arange(50) % 4], seed=1)
+    leaf = np.ones(len(parent), bool); leaf[parent[parent >= 0]] = False
+    assert (obs[leaf] < 20).all() and (obs[~leaf] == 255).all()
+    mask = synth.path_presence_mask(parent, (obs != 255) & leaf[:, None])
+    assert mask.all()     # no gaps: every ancestor lies on a path between present leaves
+
+
+def test_shard_columns(bnk):
+    from bnkit_b200.dist import shard_columns
+    for n_cols in (1, 7, 5000, 2001):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_columns(n_cols, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n_cols
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,195 @@
+"""The CPU oracle against everything the reference itself pins for this path:
+tutorial known answers, the brute-force method of MaxLhoodJointTest / MaxLhoodMarginalTest,
+the IdxTreeTest prune fixture, and the documented Recon output on data/66.*."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import NONE, leaves_of, random_obs, random_present, random_tree
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def gold(name):
+    with open(os.path.join(GOLD, name)) as fh:
+        return json.load(fh)
+
+
+def test_elementary_functions_within_one_ulp(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.uniform(-745, 709, 20000), rng.uniform(-1, 1, 20000), [0.0, -0.0, 1e-300, -1e-300]])
+    e = np.array([L.om_exp(float(x)) for x in xs])
+    assert (np.abs(e - np.exp(xs)) <= np.spacing(np.exp(xs))).all()
+    ys = np.concatenate([rng.uniform(1e-12, 3, 20000), np.exp(rng.uniform(-700, 700, 20000)), [5e-324, 1.0]])
+    l = np.array([L.om_log(float(y)) for y in ys])
+    assert (np.abs(l - np.log(ys)) <= np.spacing(np.abs(np.log(ys)))).all()
+    assert L.om_log(0.0) == -np.inf and np.isnan(L.om_log(-1.0))
+    assert L.om_exp(-np.inf) == 0.0 and L.om_exp(np.inf) == np.inf
+    # Factorize.logSumOfLogs (Factorize.java:1199-1210)
+    assert L.om_logsum(-np.inf, -3.0) == -3.0 and L.om_logsum(-2.0, -np.inf) == -2.0
+    assert L.om_logsum(-np.inf, -np.inf) == -np.inf
+    assert np.isclose(L.om_logsum(np.log(0.25), np.log(0.5)), np.log(0.75), rtol=1e-15)
+
+
+def test_tutorial_rate_matrix_and_transition_probabilities(oracle):
+    fx = gold("tutorial_lg.json")
+    m = oracle.Model("LG")
+    p = m.parts()
+    # the tutorial prints S as 0.062 where LG.java has 0.061197: allow one unit in the last printed place
+    assert np.abs(p["F"] - np.array(fx["F_3dp"])).max() < 1.0e-3
+    assert np.abs(np.round(p["R"], 2) - np.array(fx["R_2dp"])).max() < 1e-12
+    for t, P in fx["P_3dp"].items():
+        assert np.abs(m.probs(float(t)) - np.array(P)).max() <= 0.0005 + 1e-12
+    assert np.abs(p["evec"] @ p["ievec"] - np.eye(20)).max() < 1e-13
+    assert np.abs(p["R"].sum(1)).max() < 1e-14                       # makeValid
+    assert np.isclose(-(np.diag(p["R"]) * p["F"]).sum(), 1.0)        # normalize: one substitution per unit time
+    assert np.isclose(p["prior"].sum(), 1.0) and np.allclose(p["prior"] * p["F"].sum(), p["F"])
+
+
+def test_tutorial_joint_example(oracle):
+    """tutorial_ML.html:205-238 == SubstNode.main (SubstNode.java:891-957): N0 = E, N1 = E."""
+    fx = gold("tutorial_lg.json")["example"]
+    m = oracle.Model("LG")
+    par, dist = fx["tree"]["parent"], fx["tree"]["dist"]
+    obs = np.full(4, NONE, np.uint8)
+    obs[1], obs[3] = AA.index("E"), AA.index("D")
+    b = oracle.brute(m, par, dist, obs)
+    st = oracle.fast_joint(m, par, dist, obs[:, None])[:, 0]
+    assert [AA[s] for s in st] == ["E", "E", "E", "D"] and list(b["state"]) == list(st)
+    prior = m.parts()["prior"]
+    P007, P001, P01 = m.probs(0.07), m.probs(0.01), m.probs(0.1)
+    def prod(a, c, Pmid):
+        a, c = AA.index(a), AA.index(c)
+        return prior[a] * P007[a, AA.index("E")] * Pmid[a, c] * P007[c, AA.index("D")]
+    for k, v in fx["joint_products_8dp"].items():
+        assert abs(prod(k[0], k[1], P001) - v) < 5.1e-9
+    tot = sum(prod(a, c, P001) for a in AA for c in AA)
+    for k, v in fx["joint_normalised_3dp"].items():
+        assert abs(prod(k[0], k[1], P001) / tot - v) < 5.1e-4
+    tot = sum(prod(a, c, P01) for a in AA for c in AA)
+    for k, v in fx["joint_normalised_t01_3dp"].items():
+        assert abs(prod(k[0], k[1], P01) / tot - v) < 5.1e-4
+    assert np.isclose(b["total_p"], sum(prod(a, c, P001) for a in AA for c in AA), rtol=1e-12)
+
+
+def test_joint_equals_bruteforce_jc(oracle):
+    """MaxLhoodJointTest.joint1 (test/asr/MaxLhoodJointTest.java:281-365): JC, 3..7 leaves, random leaf states."""
+    m = oracle.Model("JC")
+    for n_leaves in range(3, 8):
+        for seed in range(40):
+            rng = np.random.default_rng(1000 * n_leaves + seed)
+            parent, dist = random_tree(rng, n_leaves)
+            obs = random_obs(rng, parent, 1, 4)
+            b = oracle.brute(m, parent, dist, obs[:, 0], want_post=False)
+            st = oracle.fast_joint(m, parent, dist, obs)[:, 0]
+            # the brute-force maximum is unique up to ties; compare likelihood of the two assignments
+            if not np.array_equal(st, b["state"]):
+                bb = oracle.brute(m, parent, dist, st, want_post=False)  # everything observed: P(assignment)
+                assert np.isclose(bb["total_p"], b["best_p"], rtol=1e-12)
+
+
+def test_joint_with_internal_evidence_wag(oracle):
+    """MaxLhoodJointTest.infer0 (:55-147): 7-node tree, 3 randomly instantiated nodes incl. internal ones."""
+    m = oracle.Model("WAG")
+    parent = np.array([-1, 0, 1, 1, 0, 4, 4], dtype=np.int32)
+    for seed in range(60):
+        rng = np.random.default_rng(seed)
+        dist = np.maximum(rng.gamma(1.1, 0.2, 7), 1e-7)
+        obs = np.full(7, NONE, np.uint8)
+        for v in rng.choice(7, 3, replace=False):
+            obs[v] = rng.integers(0, 20)
+        b = oracle.brute(m, parent, dist, obs, want_post=False)
+        st = oracle.fast_joint(m, parent, dist, obs[:, None])[:, 0]
+        if not np.array_equal(st, b["state"]):
+            bb = oracle.brute(m, parent, dist, st, want_post=False)
+            assert np.isclose(bb["total_p"], b["best_p"], rtol=1e-12)
+
+
+def test_marginal_equals_bruteforce(oracle):
+    """MaxLhoodMarginalTest.marginal0 / marginal1 (:205-310, :330-399) with 1e-9 instead of 0.01."""
+    for name, K, sizes in (("LG", 20, (3, 4)), ("JC", 4, (3, 5, 8))):
+        m = oracle.Model(name)
+        for n_leaves in sizes:
+            for seed in range(25):
+                rng = np.random.default_rng(7000 + 100 * n_leaves + seed)
+                parent, dist = random_tree(rng, n_leaves, max_children=3 if K == 4 else 2)
+                obs = random_obs(rng, parent, 1, K, internal_obs_prob=0.2 if K == 4 else 0.0)
+                b = oracle.brute(m, parent, dist, obs[:, 0])
+                post, logl = oracle.fast_marginal(m, parent, dist, obs)
+                free = obs[:, 0] == NONE
+                assert np.allclose(post[free, 0, :], b["post"][free], rtol=1e-9, atol=1e-15)
+                assert np.isclose(logl[0], np.log(b["total_p"]), rtol=1e-10)
+
+
+def test_masks_and_forests_against_bruteforce(oracle):
+    m = oracle.Model("JC")
+    for seed in range(60):
+        rng = np.random.default_rng(9000 + seed)
+        parent, dist = random_tree(rng, int(rng.integers(3, 7)), max_children=3)
+        obs = random_obs(rng, parent, 1, 4, gap_prob=0.3)
+        present = random_present(rng, parent, obs, absent_prob=0.3)
+        b = oracle.brute(m, parent, dist, obs[:, 0], present[:, 0])
+        st = oracle.fast_joint(m, parent, dist, obs, present)[:, 0]
+        post, logl = oracle.fast_marginal(m, parent, dist, obs, present)
+        ok = ~np.isnan(post[:, 0, 0])
+        assert np.allclose(post[ok, 0, :], b["post"][ok], rtol=1e-9, atol=1e-15)
+        assert np.isclose(logl[0], np.log(b["total_p"]), rtol=1e-10)
+        if not np.array_equal(st, b["state"]):
+            o2 = st.copy()
+            bb = oracle.brute(m, parent, dist, o2, present[:, 0], want_post=False)
+            assert np.isclose(bb["total_p"], b["best_p"], rtol=1e-12)
+        assert (st[present[:, 0] == 0] == NONE).all()
+
+
+def test_prune_fixture(oracle):
+    """IdxTreeTest.createPrunedTree (test/dat/phylo/IdxTreeTest.java:15-56)."""
+    fx = gold("idxtree_prune.json")
+    parent = np.array(fx["parents"], dtype=np.int32)
+    n = len(parent)
+    for case in fx["cases"]:
+        present = np.ones(n, np.uint8)
+        present[case["prune"]] = 0
+        out, cnt, roots = oracle.prune(parent, present, remove_orphans=False)
+        assert cnt == n - case["removed"] and roots == case["roots"]
+        if case["same_size_with_orphan_removal"]:
+            out2, cnt2, _ = oracle.prune(parent, present, remove_orphans=True)
+            assert cnt2 == cnt
+
+
+def test_orphan_removal_semantics(oracle):
+    # chain 0 - 1 - 2(leaf), 1 - 3(leaf): pruning both leaves orphans the ancestors
+    parent = np.array([-1, 0, 1, 1], dtype=np.int32)
+    out, cnt, roots = oracle.prune(parent, np.array([1, 1, 0, 0], np.uint8), True)
+    assert cnt == 0
+    out, cnt, roots = oracle.prune(parent, np.array([1, 0, 1, 1], np.uint8), True)
+    assert list(out) == [0, 0, 1, 1] and roots == 2   # root has no extant descendant through present nodes
+
+
+def test_documented_recon_output_c1(oracle):
+    """docs/json-api.md:97-122: data/66.*, JTT, joint => N0, N1, N2 present at columns {2, 4} with states A, H."""
+    from bnkit_b200 import synth
+    c1 = gold("c1_66.json")
+    parent = np.array(c1["tree"]["Parents"], dtype=np.int32)
+    assert c1["tree"]["Parents"] == c1["doc_parents"]          # our Newick indexing == IdxTree's
+    dist = np.array(c1["tree"]["Distances"])
+    labels = c1["tree"]["Labels"]
+    n, C = len(parent), len(c1["seqs"][0])
+    obs = np.full((n, C), NONE, np.uint8)
+    for name, seq in zip(c1["names"], c1["seqs"]):
+        v = labels.index(name)
+        for c, ch in enumerate(seq):
+            if ch != "-":
+                obs[v, c] = AA.index(ch)
+    leaf = leaves_of(parent)
+    present = synth.path_presence_mask(parent, (obs != NONE) & leaf[:, None])
+    m = oracle.Model("JTT")
+    st = oracle.fast_joint(m, parent, dist, obs, present)
+    doc = c1["doc_result"]
+    for anc in (0, 1, 2):
+        cols = [c for c in range(C) if present[anc, c]]
+        assert cols == doc["indices"]
+        assert [AA[st[anc, c]] for c in cols] == doc["values"]
