@@ -331,12 +331,13 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     }
     const int ncat = (int)ws->cat_rate.size();
     // thread / tile geometry
-    int cpt = ws->cfg_cpt ? ws->cfg_cpt : 1;
+    // defaults from the r1 sweep on C3 (profiles/): 2 columns per thread, ~2.8 CTAs per SM
+    int cpt = ws->cfg_cpt ? ws->cfg_cpt : (K == 20 ? 2 : 1);
     int tc = ws->cfg_tile_cols;
-    const int max_threads = 768;
+    const int max_threads = cpt == 1 ? 768 : (cpt == 2 ? 512 : 256);  // the kernels' __launch_bounds__
     const int tc_cap = (max_threads / K) * cpt;
     if (tc <= 0) {
-        const int target_tiles = ws->sm_count * 2;
+        const int target_tiles = ws->sm_count * 3 - ws->sm_count / 6;
         tc = (n_cols + target_tiles - 1) / target_tiles;
         if (tc < 4) tc = 4;
     }

@@ -151,7 +151,7 @@ __device__ __forceinline__ Bytes load_bytes(const WalkArgs &a, const Step &s, in
 // up-sweeps.  MODE 0: max-product in log space (joint).  MODE 1: sum-product, linear space.
 // ------------------------------------------------------------------------------------
 template <int K, int CPT, bool GENERAL, int MODE>
-__global__ void __launch_bounds__(768) up_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LROW = K + 2, KK = K * K;
@@ -376,7 +376,7 @@ struct DownBytes {
 };
 
 template <int K, int CPT, bool GENERAL>
-__global__ void __launch_bounds__(768) down_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LROW = K + 2, KK = K * K;

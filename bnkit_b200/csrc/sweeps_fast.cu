@@ -130,7 +130,7 @@ __device__ __forceinline__ double f_rcp(double s)
 // active" branch at all.
 // ------------------------------------------------------------------------------------
 template <int K, int CPT, int MODE>
-__global__ void __launch_bounds__(768) up_fast_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fast_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using LY = FLayout<K>;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(768) up_fast_kernel(const WalkArgs a)
 // down-sweep (see sweeps.cu for the recurrences)
 // ------------------------------------------------------------------------------------
 template <int K, int CPT>
-__global__ void __launch_bounds__(768) down_fast_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_fast_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using LY = FLayout<K>;

@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Summarise gpurun_out ncu artefacts into profiles/ (tracked).
+
+    python tools/summarize_profiles.py <tag> <launches.csv> <report.ncu-rep> [bench.json]
+"""
+import csv, json, shutil, subprocess, sys
+from collections import defaultdict
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+tag, launches, rep = sys.argv[1], Path(sys.argv[2]), Path(sys.argv[3])
+bench = Path(sys.argv[4]) if len(sys.argv) > 4 else None
+out = ROOT / "profiles"
+out.mkdir(exist_ok=True)
+
+lines = ["# ncu summary %s" % tag, ""]
+if bench and bench.exists():
+    b = json.loads(bench.read_text().strip().splitlines()[-1])
+    shutil.copy(bench, out / ("%s_bench.json" % tag))
+    lines += ["Bench line (CUDA events, no profiler): %.3f ms/step, %.4g updates/s, phases %s, e2e %s" % (
+        b["ms_per_step"], b["value"], json.dumps(b["phase_ms"]), json.dumps(b.get("e2e"))), ""]
+
+rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
+hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+keep = [hdr] + rows[1:]
+with open(out / ("%s_launches.csv" % tag), "w", newline="") as fh:
+    csv.writer(fh).writerows(keep)
+agg = defaultdict(lambda: [0, 0.0])
+for r in rows[1:]:
+    k = r[idx["Kernel Name"]].split("(")[0]
+    v = float(r[idx["Metric Value"]].replace(",", "")) / 1e6
+    agg[k][0] += 1; agg[k][1] += v
+tot = sum(v[1] for v in agg.values())
+lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; serialised, cold cache: compare shares)", "",
+          "| kernel | launches | total ms | ms / launch | share |", "|---|---|---|---|---|"]
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    lines.append("| `%s` | %d | %.3f | %.3f | %.3f |" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
+
+raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+h = rr[0]; ix = {x: i for i, x in enumerate(h)}
+want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
+        ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe active %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active % (occupancy)"),
+        ("launch__registers_per_thread", "registers / thread"), ("launch__block_size", "block"), ("launch__grid_size", "grid"),
+        ("smsp__inst_executed.sum", "warp instructions"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"), ("lts__t_bytes.sum", "L2 bytes")]
+stalls = [x for x in h if "issue_stalled" in x and x.endswith("_per_issue_active.ratio")]
+lines += ["", "## `ncu --set full --clock-control none --import-source on` (one launch each)", ""]
+for r in rr[2:]:
+    lines.append("### `%s`" % r[ix["Kernel Name"]])
+    lines.append("")
+    for key, name in want:
+        if key in ix:
+            lines.append("- %s: %s %s" % (name, r[ix[key]], rr[1][ix[key]]))
+    top = sorted([(float(r[ix[s]]), s.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""))
+                  for s in stalls if r[ix[s]]], reverse=True)[:6]
+    lines.append("- warp stalls per issued instruction: " + ", ".join("%s %.2f" % (n, v) for v, n in top))
+    if "dram__bytes_read.sum" in ix:
+        def gb(key):
+            v = float(r[ix[key]]); u = rr[1][ix[key]]
+            return v * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}.get(u, 1.0)
+        lines.append("- DRAM traffic per launch: %.3f GB" % (gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")))
+    lines.append("")
+(out / ("%s_ncu_summary.md" % tag)).write_text("\n".join(lines) + "\n")
+print("wrote", out / ("%s_ncu_summary.md" % tag))
