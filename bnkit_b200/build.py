@@ -13,6 +13,7 @@ UNITS = [
     ("tables.cu", ["-fmad=false"]),
     ("sweeps.cu", []),
     ("sweeps_fast.cu", []),
+    ("wide.cu", []),
     ("traceback.cu", []),
     ("api.cu", []),
     ("subst_model.cpp", ["-fmad=false"]),

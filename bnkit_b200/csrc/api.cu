@@ -76,9 +76,11 @@ struct bnk_ws {
     size_t table_budget = (size_t)12 << 30;
     // static device data
     DevBuf<double> d_model;  // evec | ievec | eval | prior | logprior
-    DevBuf<Step> d_up;
-    DevBuf<Step> d_down;
-    DevBuf<ChildRef> d_up_child, d_down_child;
+    DevBuf<Step> d_up, d_down, d_up_n, d_down_n;             // full / narrow walk programs
+    DevBuf<ChildRef> d_up_child, d_down_child, d_up_child_n, d_down_child_n;
+    DevBuf<WideNode> d_wide;                                  // wide levels, concatenated (height 1 first)
+    std::vector<int32_t> level_off;                           // [wide_h + 1] into d_wide
+    bool no_wide = false;                                     // bnk_ws_configure: walker only (tests, profiling)
     DevBuf<int32_t> d_parent, d_node_of_ent, d_leaf_nodes, d_leaf_parent;
     DevBuf<double> d_dist;
     std::vector<double> dist;
@@ -88,16 +90,19 @@ struct bnk_ws {
     bool identity_perm = true;
     std::vector<double> cat_rate;
     std::vector<int32_t> orig_col, col_cat_global, cat_of_col;
-    std::vector<TileDesc> tiles;
+    std::vector<TileDesc> tiles, wtiles;   // walker tiles; wide tiles (one category, <= 128 columns)
     std::vector<Chunk> chunks;
+    std::vector<std::pair<int, int>> chunk_wtiles, chunk_cols;  // per chunk: wide tile range, sorted column range
     int tile_cols = 0, cpt = 1, ncg = 0, threads = 0;
     DevBuf<double> d_cat_rate;
     DevBuf<int32_t> d_orig_col, d_col_cat, d_cat_of_col, d_qrow, d_flag;
-    DevBuf<TileDesc> d_tiles;
+    DevBuf<TileDesc> d_tiles, d_wtiles;
+    DevBuf<int16_t> d_escale;
+    DevBuf<int32_t> d_esum_wide;
     bool tables_log_valid = false, tables_lin_valid = false;  // only meaningful with a single chunk
     // buffers
-    DevBuf<double> d_P, d_PT, d_L, d_LT, d_spill, d_msg, d_logl, d_post, d_sum;
-    DevBuf<uint8_t> d_obs_in, d_present_in, d_obs_s, d_present_s, d_ptr, d_kind, d_kindm, d_state;
+    DevBuf<double> d_P, d_PT, d_L, d_LT, d_spill, d_msg, d_tmsg, d_logl, d_post, d_sum;
+    DevBuf<uint8_t> d_obs_in, d_present_in, d_obs_s, d_present_s, d_ptr, d_kind, d_kindm, d_state, d_state_s;
     cudaEvent_t ev[5][2] = {};
     bool ev_valid[5] = {false, false, false, false, false};
     ModelDev md() const
@@ -175,15 +180,17 @@ static void ws_free(bnk_ws *ws)
     cudaSetDevice(ws->device);
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
-                            &ws->d_spill, &ws->d_msg, &ws->d_logl, &ws->d_post, &ws->d_sum};
+                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_post, &ws->d_sum};
     for (auto *b : dd) b->release();
     DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
-                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state};
+                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state, &ws->d_state_s};
     for (auto *b : db) b->release();
     DevBuf<int32_t> *di[] = {&ws->d_parent, &ws->d_node_of_ent, &ws->d_leaf_nodes, &ws->d_leaf_parent,
                              &ws->d_orig_col, &ws->d_col_cat, &ws->d_cat_of_col, &ws->d_qrow, &ws->d_flag};
     for (auto *b : di) b->release();
     ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
+    ws->d_up_n.release(); ws->d_down_n.release(); ws->d_up_child_n.release(); ws->d_down_child_n.release();
+    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
     if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
@@ -219,10 +226,10 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     // accounting hooks
     DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
-                            &ws->d_spill, &ws->d_msg, &ws->d_logl, &ws->d_post, &ws->d_sum};
+                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_post, &ws->d_sum};
     for (auto *b : dd) b->acct = &ws->dev_bytes;
     DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
-                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state};
+                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state, &ws->d_state_s};
     for (auto *b : db) b->acct = &ws->dev_bytes;
 
     const int K = ws->K;
@@ -239,10 +246,21 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     int rc = BNK_OK;
     auto step = [&](int r) { if (rc == BNK_OK) rc = r; };
     step(upload(ws->d_model, mh, ws->stream));
-    step(upload(ws->d_up, t->up, ws->stream));
-    step(upload(ws->d_down, t->down, ws->stream));
-    step(upload(ws->d_up_child, t->up_child, ws->stream));
-    step(upload(ws->d_down_child, t->down_child, ws->stream));
+    step(upload(ws->d_up, t->full.up, ws->stream));
+    step(upload(ws->d_down, t->full.down, ws->stream));
+    step(upload(ws->d_up_child, t->full.up_child, ws->stream));
+    step(upload(ws->d_down_child, t->full.down_child, ws->stream));
+    step(upload(ws->d_up_n, t->narrow.up, ws->stream));
+    step(upload(ws->d_down_n, t->narrow.down, ws->stream));
+    step(upload(ws->d_up_child_n, t->narrow.up_child, ws->stream));
+    step(upload(ws->d_down_child_n, t->narrow.down_child, ws->stream));
+    std::vector<WideNode> wide_all;
+    ws->level_off.assign(1, 0);
+    for (const auto &lv : t->levels) {
+        wide_all.insert(wide_all.end(), lv.begin(), lv.end());
+        ws->level_off.push_back((int32_t)wide_all.size());
+    }
+    step(upload(ws->d_wide, wide_all, ws->stream));
     step(upload(ws->d_parent, t->parent, ws->stream));
     step(upload(ws->d_node_of_ent, t->node_of_ent, ws->stream));
     step(upload(ws->d_leaf_nodes, leaf_nodes, ws->stream));
@@ -278,7 +296,8 @@ extern "C" int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread)
     if (cols_per_thread != 0 && cols_per_thread != 1 && cols_per_thread != 2 && cols_per_thread != 4)
         return fail(BNK_ERR_ARG, "ws: cols_per_thread must be 0 (auto), 1, 2 or 4");
     if (ws->K == 4 && cols_per_thread > 1) return fail(BNK_ERR_ARG, "ws: 4-state kernels are built with 1 column per thread");
-    if (tile_cols < 0) return fail(BNK_ERR_ARG, "ws: tile_cols < 0");
+    ws->no_wide = tile_cols < 0;  // negative: same geometry, walker kernels only (tests, profiling)
+    if (tile_cols < 0) tile_cols = -tile_cols;
     ws->cfg_tile_cols = tile_cols;
     ws->cfg_cpt = cols_per_thread;
     ws->ncols = -1;  // tiles are rebuilt by the next bnk_set_rates
@@ -355,10 +374,20 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     const size_t per_cat = (size_t)ws->n * K * K * sizeof(double) * 2;
     int cats_per_chunk = (int)std::max<size_t>(1, ws->table_budget / std::max<size_t>(per_cat, 1));
     if (cats_per_chunk > 60000) cats_per_chunk = 60000;
-    ws->chunks.clear();
+    ws->chunks.clear(); ws->wtiles.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
+    const int wt = wide_tile_cols();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
         const int hi = std::min(ncat, lo + cats_per_chunk);
         Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
+        const int w0 = (int)ws->wtiles.size();
+        for (int k = lo; k < hi; k++) {
+            const int nc = cat_begin[k + 1] - cat_begin[k];
+            const int nt = (nc + wt - 1) / wt;
+            for (int q = 0; q < nt; q++) {
+                const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                ws->wtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+            }
+        }
         TileDesc cur{0, 0, 0, 0};
         auto close = [&]() { if (cur.ncols > 0) { ws->tiles.push_back(cur); ck.ncat_max = std::max(ck.ncat_max, cur.ncat); } cur = TileDesc{0, 0, 0, 0}; };
         for (int k = lo; k < hi; k++) {
@@ -380,7 +409,11 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         }
         close();
         ck.tile_hi = (int)ws->tiles.size();
-        if (ck.tile_hi > ck.tile_lo) ws->chunks.push_back(ck);
+        if (ck.tile_hi > ck.tile_lo) {
+            ws->chunks.push_back(ck);
+            ws->chunk_wtiles.push_back({w0, (int)ws->wtiles.size()});
+            ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
+        }
     }
     // chunk-local category per sorted column
     std::vector<int32_t> col_cat_local(n_cols);
@@ -394,6 +427,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_col_cat, col_cat_local, ws->stream));
     TRY(upload(ws->d_cat_of_col, ws->cat_of_col, ws->stream));
     TRY(upload(ws->d_tiles, ws->tiles, ws->stream));
+    TRY(upload(ws->d_wtiles, ws->wtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
     ws->tables_log_valid = ws->tables_lin_valid = false;
@@ -515,18 +549,19 @@ static int build_tables(bnk_ws *ws, const Chunk &ck, bool log_space)
 struct WalkSetup {
     WalkArgs a;
     WalkLaunch wl;
-    bool fast = false;  // lean kernels of sweeps_fast.cu apply
+    bool fast = false;    // lean kernels of sweeps_fast.cu apply
+    bool hybrid = false;  // wide height levels run as level launches (wide.cu); the walker takes the narrow top
+    int tb_slots = 0;
 };
 
-static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_needed, const uint8_t *obs_s,
+// Decides the schedule for one chunk: lean or general walker kernels, and whether the wide
+// height levels run as level launches (hybrid) with the walker restricted to the narrow top.
+static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down, const uint8_t *obs_s,
                       const uint8_t *present_s, WalkSetup &s)
 {
     const int K = ws->K;
     std::memset(&s.a, 0, sizeof(s.a));
     const bnk_tree *t = ws->tree;
-    s.a.up = ws->d_up.p; s.a.down = ws->d_down.p;
-    s.a.up_child = ws->d_up_child.p; s.a.down_child = ws->d_down_child.p;
-    s.a.n_steps = t->n_int;
     s.a.tiles = ws->d_tiles.p + ck.tile_lo;
     s.a.ncg = ws->ncg;
     s.a.ncat_max = ck.ncat_max;
@@ -535,18 +570,31 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_neede
     s.a.orig_col = ws->d_orig_col.p; s.a.col_cat = ws->d_col_cat.p;
     s.wl.K = K; s.wl.cpt = ws->cpt; s.wl.threads = ws->threads; s.wl.n_tiles = ck.tile_hi - ck.tile_lo;
     s.wl.general = general; s.wl.stream = ws->stream;
+    auto use_program = [&](bool narrow) {
+        const Program &pg = narrow ? t->narrow : t->full;
+        s.a.up = narrow ? ws->d_up_n.p : ws->d_up.p;
+        s.a.down = narrow ? ws->d_down_n.p : ws->d_down.p;
+        s.a.up_child = narrow ? ws->d_up_child_n.p : ws->d_up_child.p;
+        s.a.down_child = narrow ? ws->d_down_child_n.p : ws->d_down_child.p;
+        s.a.n_steps = (int32_t)pg.up.size();
+        s.tb_slots = pg.tb_slots;
+        return std::max(pg.up_slots, want_down ? pg.down_slots : 0);
+    };
     // lean kernels: nothing masked, evidence on childless nodes only, binary (or unary) nodes,
     // one category per tile, whole stack in shared memory
-    s.fast = false;
+    s.fast = false; s.hybrid = false;
     if (!general && !ws->force_generic && t->max_children <= 2 && ck.ncat_max == 1) {
-        const size_t need = fast_smem_bytes(K, ws->cpt, ws->ncg, slots_needed);
+        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
+        const int slots = use_program(hybrid);
+        const size_t need = fast_smem_bytes(K, ws->cpt, ws->ncg, slots);
         if (need <= (size_t)ws->smem_optin) {
-            s.fast = true;
-            s.a.smem_slots = slots_needed;
+            s.fast = true; s.hybrid = hybrid;
+            s.a.smem_slots = slots;
             s.wl.smem_bytes = need;
             return BNK_OK;
         }
     }
+    const int slots_needed = use_program(false);
     // stack slots: as many as fit in shared memory, the rest spill to global memory
     const size_t base = walk_smem_bytes(K, ws->cpt, ws->ncg, ck.ncat_max, 0);
     const size_t per_slot = sizeof(double) * (size_t)ws->ncg * ws->cpt * K;
@@ -559,6 +607,37 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, int slots_neede
         s.a.spill = ws->d_spill.p;
     }
     s.wl.smem_bytes = base + per_slot * smem_slots;
+    return BNK_OK;
+}
+
+// arguments common to the level kernels of one chunk
+static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
+{
+    WideArgs w;
+    std::memset(&w, 0, sizeof(w));
+    w.tiles = ws->d_wtiles.p + ws->chunk_wtiles[ci].first;
+    w.obs = obs_s;
+    w.ncols = ws->ncols; w.n_nodes = ws->n;
+    w.orig_col = ws->d_orig_col.p;
+    w.col_lo = ws->chunk_cols[ci].first; w.col_hi = ws->chunk_cols[ci].second;
+    return w;
+}
+
+// one launch per wide height level (sliced when a level exceeds the grid's y limit)
+template <typename F>
+static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch)
+{
+    const int H = ws->tree->wide_h;
+    for (int k = 0; k < H; k++) {
+        const int h = ascending ? k : H - 1 - k;
+        for (int off = ws->level_off[h]; off < ws->level_off[h + 1]; off += 65535) {
+            const int cnt = std::min(65535, ws->level_off[h + 1] - off);
+            w.nodes = ws->d_wide.p + off;
+            w.wide_row0 = off;
+            CUDA_TRY(launch(w, cnt));
+            ws->launches++;
+        }
+    }
     return BNK_OK;
 }
 
@@ -578,36 +657,67 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
         CUDA_TRY(ws->d_ptr.ensure((size_t)ws->n_int * nc * K));
         CUDA_TRY(ws->d_kind.ensure((size_t)ws->n_int * nc));
     }
+    // states of internal nodes are produced in sorted column space, then scattered (identity: in place)
+    uint8_t *state_s = d_out_state;
+    if (!ws->identity_perm) { CUDA_TRY(ws->d_state_s.ensure((size_t)ws->n * nc)); state_s = ws->d_state_s.p; }
     for (size_t ci = 0; ci < ws->chunks.size(); ci++) {
         const Chunk &ck = ws->chunks[ci];
         TRY(build_tables(ws, ck, true));
-        bool fast_joint = false;
         if (ws->n_int > 0) {
             WalkSetup s;
-            TRY(setup_walk(ws, ck, general, ws->tree->up_slots, obs_s, present_s, s));
+            TRY(setup_walk(ws, ck, general, false, obs_s, present_s, s));
             s.a.T_row = ws->d_L.p; s.a.T_col = ws->d_LT.p; s.a.prior = ws->md().logprior;
             s.a.ptr = ws->d_ptr.p; s.a.kind = ws->d_kind.p;
-            fast_joint = s.fast;
+            WideArgs w = wide_args(ws, ci, obs_s);
+            w.T_row = ws->d_L.p; w.T_col = ws->d_LT.p; w.ptr = ws->d_ptr.p; w.state_s = state_s;
+            const int n_wt = ws->chunk_wtiles[ci].second - ws->chunk_wtiles[ci].first;
             CUDA_TRY(cudaEventRecord(ws->ev[1][0], ws->stream));
+            if (s.hybrid) {
+                CUDA_TRY(ws->d_msg.ensure((size_t)ws->n_int * nc * K));
+                w.msg = ws->d_msg.p; s.a.msg = ws->d_msg.p;
+                TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) { return launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
+            }
             CUDA_TRY(s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;
             CUDA_TRY(cudaEventRecord(ws->ev[1][1], ws->stream));
             ws->ev_valid[1] = true;
+            // traceback: the walked part first (it holds the roots), then the wide levels top-down
+            TracebackArgs ta;
+            std::memset(&ta, 0, sizeof(ta));
+            ta.down = s.a.down; ta.n_steps = s.a.n_steps; ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
+            ta.ptr = ws->d_ptr.p; ta.kind = s.fast ? nullptr : ws->d_kind.p;
+            ta.obs_s = obs_s; ta.state_s = state_s; ta.tb_slots = s.tb_slots;
+            ta.col_lo = w.col_lo; ta.col_hi = w.col_hi;
+            CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
+            CUDA_TRY(launch_traceback(ta, ws->stream));
+            ws->launches++;
+            if (s.hybrid)
+                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) { return launch_traceback_wide(K, wa, cnt, ws->stream); }));
+        } else {
+            CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
         }
+        if (ci + 1 == ws->chunks.size()) {  // all chunks done: back to the caller's column order, then the leaves
+            if (!ws->identity_perm && ws->n_int > 0) {
+                CUDA_TRY(launch_scatter_rows(state_s, d_out_state, ws->d_node_of_ent.p, ws->n_int, ws->d_orig_col.p, nc, ws->stream));
+                ws->launches++;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(ws->ev[2][1], ws->stream));
+        ws->ev_valid[2] = true;
+    }
+    // childless nodes (original column space; may read their parents' states)
+    for (size_t ci = 0; ci < ws->chunks.size(); ci++) {
+        const Chunk &ck = ws->chunks[ci];
+        if (ws->chunks.size() > 1) TRY(build_tables(ws, ck, true));  // the rare uninstantiated-leaf case reads L
         TracebackArgs ta;
         std::memset(&ta, 0, sizeof(ta));
-        ta.down = ws->d_down.p; ta.n_steps = ws->n_int; ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
-        ta.ptr = ws->d_ptr.p; ta.kind = fast_joint ? nullptr : ws->d_kind.p; ta.obs = d_obs; ta.present = d_present;
-        ta.out_state = d_out_state; ta.tb_slots = ws->tree->tb_slots;
+        ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
+        ta.obs = d_obs; ta.present = d_present; ta.out_state = d_out_state;
         ta.leaf_nodes = ws->d_leaf_nodes.p; ta.leaf_parent = ws->d_leaf_parent.p; ta.n_leaves = ws->n_leaves;
         ta.L = ws->d_L.p;
         ta.cat_of_col = ws->d_cat_of_col.p; ta.cat_lo = ck.cat_lo; ta.cat_hi = ck.cat_hi;
-        CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
-        if (ws->n_int > 0) { CUDA_TRY(launch_traceback(ta, ws->stream)); ws->launches++; }
         CUDA_TRY(launch_leaf_states(ta, ws->stream));
         ws->launches++;
-        CUDA_TRY(cudaEventRecord(ws->ev[2][1], ws->stream));
-        ws->ev_valid[2] = true;
     }
     return BNK_OK;
 }
@@ -680,12 +790,30 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
         const Chunk &ck = ws->chunks[ci];
         TRY(build_tables(ws, ck, false));
         WalkSetup s;
-        TRY(setup_walk(ws, ck, general, std::max(t->up_slots, want_post ? t->down_slots : 0), obs_s, present_s, s));
+        TRY(setup_walk(ws, ck, general, want_post, obs_s, present_s, s));
         s.a.T_row = ws->d_P.p; s.a.T_col = ws->d_PT.p; s.a.prior = ws->md().prior;
         s.a.msg = want_post ? ws->d_msg.p : nullptr;
         s.a.kindm = (want_post && general) ? ws->d_kindm.p : nullptr;
         s.a.out_logl = logl;
+        WideArgs w = wide_args(ws, ci, obs_s);
+        w.T_row = ws->d_P.p; w.T_col = ws->d_PT.p;
+        const int n_wt = ws->chunk_wtiles[ci].second - ws->chunk_wtiles[ci].first;
         CUDA_TRY(cudaEventRecord(ws->ev[3][0], ws->stream));
+        if (s.hybrid) {
+            CUDA_TRY(ws->d_msg.ensure((size_t)ws->n_int * nc * K));  // the walker reads the wide messages even for logL only
+            w.msg = ws->d_msg.p; s.a.msg = ws->d_msg.p;
+            if (logl) {
+                CUDA_TRY(ws->d_escale.ensure((size_t)std::max(t->n_wide, 1) * nc));
+                CUDA_TRY(ws->d_esum_wide.ensure(nc));
+                w.escale = ws->d_escale.p;
+            }
+            TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) { return launch_up_wide(K, 1, wa, n_wt, cnt, ws->stream); }));
+            if (logl) {
+                CUDA_TRY(launch_sum_escale(ws->d_escale.p, t->n_wide, nc, ws->d_esum_wide.p, ws->stream));
+                ws->launches++;
+                s.a.esum_wide = ws->d_esum_wide.p;
+            }
+        }
         CUDA_TRY(s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
         ws->launches++;
         CUDA_TRY(cudaEventRecord(ws->ev[3][1], ws->stream));
@@ -694,9 +822,17 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
             s.a.T_row = ws->d_PT.p;
             s.a.out_post = d_out_post;
             s.a.qrow = (n_query < 0) ? nullptr : ws->d_qrow.p;
+            if (s.hybrid) {
+                CUDA_TRY(ws->d_tmsg.ensure((size_t)ws->n_int * nc * K));
+                s.a.tmsg = ws->d_tmsg.p;
+            }
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
             CUDA_TRY(s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;
+            if (s.hybrid) {
+                w.tmsg = ws->d_tmsg.p; w.out_post = d_out_post; w.qrow = s.a.qrow;
+                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) { return launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
+            }
             CUDA_TRY(cudaEventRecord(ws->ev[4][1], ws->stream));
             ws->ev_valid[4] = true;
         }

@@ -49,7 +49,7 @@ struct WalkArgs {
     // message stack: slots < smem_slots live in shared memory, the rest in spill[(slot - smem_slots)][ncols][K]
     int32_t smem_slots;
     double *spill;
-    // joint outputs, original column space
+    // joint intermediates, sorted column space
     uint8_t *ptr;   // [n_int][ncols][K] traceback pointers
     uint8_t *kind;  // [n_int][ncols]
     // sum-product intermediates, sorted column space
@@ -59,7 +59,36 @@ struct WalkArgs {
     double *out_logl;       // [ncols]
     double *out_post;       // [n_query][ncols][K]
     const int32_t *qrow;    // [n_int] -> row of out_post or -1
+    // hybrid schedule (lean kernels only): children handled by the wide level kernels
+    double *tmsg;               // from-above vectors handed to wide children, [ent][K][ncols]
+    const int32_t *esum_wide;   // [ncols] rescale exponents accumulated by the wide sum up-sweep (or nullptr)
 };
+
+// arguments of the level kernels (wide.cu); all column indices are in sorted space
+struct WideArgs {
+    const WideNode *nodes;   // the level (or a slice of it): gridDim.y entries
+    const TileDesc *tiles;   // wide column tiles: one category each, <= 128 columns
+    const uint8_t *obs;
+    int32_t ncols, n_nodes;
+    const int32_t *orig_col;
+    const double *T_row, *T_col;
+    double *msg;             // wide nodes: [ent][K][ncols]
+    uint8_t *ptr;            // wide nodes: [ent][K][ncols]
+    int16_t *escale;         // [wide row][ncols] rescale exponent of each (node, column)
+    int32_t wide_row0;       // wide row of nodes[0]
+    double *tmsg;
+    double *out_post;
+    const int32_t *qrow;
+    uint8_t *state_s;        // [node][ncols]
+    int32_t col_lo, col_hi;  // traceback: columns of the chunk being processed
+};
+cudaError_t launch_up_wide(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
+cudaError_t launch_down_wide(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
+cudaError_t launch_traceback_wide(int K, const WideArgs &a, int n_nodes, cudaStream_t st);
+cudaError_t launch_sum_escale(const int16_t *escale, int n_rows, int ncols, int32_t *esum, cudaStream_t st);
+cudaError_t launch_scatter_rows(const uint8_t *in, uint8_t *out, const int32_t *nodes, int n_rows,
+                                const int32_t *orig_col, int ncols, cudaStream_t st);
+int wide_tile_cols();
 
 void launch_build_tables(int K, const ModelDev &md, const double *times, const int32_t *skip,
                          const double *rates, int n_nodes, int n_cat, const TableSet &ts, cudaStream_t st);
@@ -86,10 +115,15 @@ cudaError_t launch_sum_down_fast(const WalkLaunch &wl, const WalkArgs &a);
 struct TracebackArgs {
     const Step *down;
     int32_t n_steps, ncols, n_nodes, K;
-    const uint8_t *ptr, *kind;      // original column space; kind == nullptr: root steps are KIND_ROOT, all others KIND_MSG
-    const uint8_t *obs, *present;   // original column space, [node][ncols]
-    uint8_t *out_state;             // [node][ncols]
+    // walk traceback: everything in SORTED column space
+    const uint8_t *ptr, *kind;      // kind == nullptr: root steps are KIND_ROOT, all others KIND_MSG
+    const uint8_t *obs_s;           // sorted-space observations (KIND_OBS pass-through)
+    uint8_t *state_s;               // [node][ncols] sorted space
+    int32_t col_lo, col_hi;         // sorted columns of the chunk being processed
     int32_t tb_slots;
+    // leaf pass: ORIGINAL column space
+    const uint8_t *obs, *present;   // [node][ncols]
+    uint8_t *out_state;             // [node][ncols]
     // childless nodes
     const int32_t *leaf_nodes, *leaf_parent;
     int32_t n_leaves;

@@ -55,6 +55,26 @@ struct ChildRef {
 
 }  // namespace bnk
 
+namespace bnk {
+// A walk program over a set of internal nodes (all of them, or the "narrow" top of the tree).
+struct Program {
+    std::vector<Step> up;          // post-order, heavy child first
+    std::vector<ChildRef> up_child;
+    std::vector<Step> down;        // pre-order, heavy child last
+    std::vector<ChildRef> down_child;
+    int32_t up_slots = 0, down_slots = 0, tb_slots = 0;
+};
+// One node of a wide height level (processed by the level kernels of wide.cu): binary or unary.
+struct WideNode {
+    int32_t node, parent, ent, n_child;
+    int32_t c_node[2];  // tree index or -1
+    int32_t c_ent[2];   // internal row of the child or -1 (childless)
+};
+static_assert(sizeof(WideNode) == 32, "WideNode must be 32 bytes");
+constexpr int32_t SLOT_CHILDLESS = -1;  // Step::c_slot: the child is childless (message = table lookup)
+constexpr int32_t SLOT_WIDE = -2;       // Step::c_slot: the child was handled by a wide level kernel (message in HBM)
+}  // namespace bnk
+
 struct bnk_tree {
     int32_t n = 0, n_int = 0, root_count = 0;
     std::vector<int32_t> parent;
@@ -62,9 +82,13 @@ struct bnk_tree {
     std::vector<int32_t> first, kids;  // children CSR in index order (IdxTree.children[])
     std::vector<int32_t> ent_of_node;  // -1 for childless nodes
     std::vector<int32_t> node_of_ent;
-    std::vector<bnk::Step> up;         // post-order, heavy child first
-    std::vector<bnk::ChildRef> up_child;
-    std::vector<bnk::Step> down;   // pre-order, heavy child last
-    std::vector<bnk::ChildRef> down_child;
-    int32_t up_slots = 0, down_slots = 0, tb_slots = 0, max_children = 0;
+    std::vector<int32_t> height;       // 0 childless, else 1 + max over children
+    bnk::Program full;                 // every internal node (general kernels; deep trees)
+    // hybrid schedule: height levels 1..wide_h are wide enough to run as one launch each; the rest
+    // of the tree (an upward-closed set) is walked by column-owning CTAs
+    int32_t wide_h = 0;
+    std::vector<std::vector<bnk::WideNode>> levels;  // levels[h - 1], h = 1..wide_h
+    bnk::Program narrow;
+    int32_t n_wide = 0;
+    int32_t max_children = 0;
 };

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             if (!act[j]) continue;
-            if (MODE == 0 && p == 0) a.kind[(size_t)st.ent * a.ncols + ocol[j]] = kind[j];
+            if (MODE == 0 && p == 0) a.kind[(size_t)st.ent * a.ncols + col[j]] = kind[j];
             if (MODE == 1 && GENERAL && p == 0 && a.kindm) a.kindm[(size_t)st.ent * a.ncols + col[j]] = kind[j];
             if (kind[j] != KIND_MSG && kind[j] != KIND_ROOT) continue;
             const double2 *row2 = reinterpret_cast<const double2 *>(
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
                     if (v0 > best) { best = v0; bi = 2 * x2; }
                     if (v1 > best) { best = v1; bi = 2 * x2 + 1; }
                 }
-                a.ptr[((size_t)st.ent * a.ncols + ocol[j]) * K + p] = (uint8_t)bi;
+                a.ptr[((size_t)st.ent * a.ncols + col[j]) * K + p] = (uint8_t)bi;
                 if (st.slot >= 0) {
                     if (st.slot < a.smem_slots) sm.stack[((size_t)st.slot * tcpad + lc[j]) * K + p] = best;
                     else a.spill[((size_t)(st.slot - a.smem_slots) * a.ncols + col[j]) * K + p] = best;

@@ -148,10 +148,11 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
     const double *tcol_cat_p = a.T_col + (size_t)tile.cat0 * a.n_nodes * KK + p;
     const TableCopy<K> tcopy;
 
-    int sidx[CPT], gsw[CPT], ocol[CPT];
+    int sidx[CPT], gsw[CPT], ocol[CPT], scol[CPT];
     const uint8_t *obs_c[CPT];
     uint8_t *ptr_o[CPT];
     double *msg_o[CPT];
+    const double *wmsg_p[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; j++) {
         int lc = cg * CPT + j;
@@ -162,8 +163,10 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
         sidx[j] = (lc * K + p) * 8;
         gsw[j] = lc * LROW * 8;
         obs_c[j] = a.obs + col;
-        ptr_o[j] = (MODE == 0) ? a.ptr + (size_t)ocol[j] * K + p : nullptr;
+        scol[j] = col;
+        ptr_o[j] = (MODE == 0) ? a.ptr + (size_t)col * K + p : nullptr;
         msg_o[j] = (MODE == 1 && a.msg) ? a.msg + (size_t)col * K + p : nullptr;
+        wmsg_p[j] = a.msg ? a.msg + (size_t)p * ncols + col : nullptr;  // wide layout [ent][K][ncols]
     }
     const unsigned row_stride = (unsigned)(ncols * K);  // ptr / msg rows (host guarantees ncols * K < 2^31)
     const double prior_p = a.prior[p];
@@ -195,11 +198,16 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
     auto load_look = [&](int po, int k, int ob, int j, int e) -> double {
         const int cn = (e == 0) ? STEP_AT(po, k, c_node[0]) : STEP_AT(po, k, c_node[1]);
         const int cs = (e == 0) ? STEP_AT(po, k, c_slot[0]) : STEP_AT(po, k, c_slot[1]);
-        const bool childless = cn >= 0 && cs < 0;
+        const int ce = (e == 0) ? STEP_AT(po, k, c_ent[0]) : STEP_AT(po, k, c_ent[1]);
+        const bool childless = cn >= 0 && cs == SLOT_CHILDLESS, wide = cs == SLOT_WIDE;
         const int node = cn < 0 ? 0 : cn;
-        double g = tcol_cat_p[(unsigned)(node * KK + (ob == BNK_NONE ? 0 : ob) * K)];
-        if (!childless) g = ident;
-        else if (ob == BNK_NONE) {  // uninstantiated childless node: maximise / marginalise its own row
+        // one load either way: the table entry of an observed childless child, or the message a
+        // wide level kernel left in HBM ([ent][K][ncols])
+        const double *src = wide ? wmsg_p[j] + (size_t)(unsigned)ce * row_stride
+                                 : tcol_cat_p + (unsigned)(node * KK + (ob == BNK_NONE ? 0 : ob) * K);
+        double g = *src;
+        if (!childless && !wide) g = ident;
+        else if (childless && ob == BNK_NONE) {  // uninstantiated childless node: maximise / marginalise its own row
             const double *row = a.T_row + ((size_t)tile.cat0 * a.n_nodes + node) * KK + p * K;
             g = row[0];
             for (int x = 1; x < K; x++) g = (MODE == 0) ? (row[x] > g ? row[x] : g) : g + row[x];
@@ -317,7 +325,10 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
     }
     if (MODE == 1 && a.out_logl && p == 0) {
 #pragma unroll
-        for (int j = 0; j < CPT; j++) a.out_logl[ocol[j]] = logacc[j] + (double)esum[j] * 0.693147180559945309417232121458;
+        for (int j = 0; j < CPT; j++) {
+            const int ew = a.esum_wide ? a.esum_wide[scol[j]] : 0;
+            a.out_logl[ocol[j]] = logacc[j] + (double)(esum[j] + ew) * 0.693147180559945309417232121458;
+        }
     }
 }
 
@@ -345,6 +356,8 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
     int sidx[CPT], gsw[CPT], srd[CPT];
     const uint8_t *obs_c[CPT];
     const double *msg_i[CPT];
+    const double *wmsg_p[CPT];
+    double *tmsg_p[CPT];
     double *post_o[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; j++) {
@@ -357,6 +370,8 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
         gsw[j] = lc * LROW * 8;
         obs_c[j] = a.obs + col;
         msg_i[j] = a.msg + (size_t)col * K + p;
+        wmsg_p[j] = a.msg + (size_t)p * ncols + col;                      // wide layout [ent][K][ncols]
+        tmsg_p[j] = a.tmsg ? a.tmsg + (size_t)p * ncols + col : nullptr;  // likewise
         post_o[j] = a.out_post ? a.out_post + (size_t)a.orig_col[col] * K + p : nullptr;
     }
     const unsigned row_stride = (unsigned)(ncols * K);
@@ -385,9 +400,11 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
     auto load_val = [&](int po, int k, int ob, int j, int e) -> double {
         const int cn = (e == 0) ? STEP_AT(po, k, c_node[0]) : STEP_AT(po, k, c_node[1]);
         const int ce = (e == 0) ? STEP_AT(po, k, c_ent[0]) : STEP_AT(po, k, c_ent[1]);
-        const bool exists = cn >= 0, internal = ce >= 0;
+        const int cs = (e == 0) ? STEP_AT(po, k, c_slot[0]) : STEP_AT(po, k, c_slot[1]);
+        const bool exists = cn >= 0, internal = ce >= 0, wide = cs == SLOT_WIDE;
         const int node = cn < 0 ? 0 : cn;
-        const double *src = internal ? msg_i[j] + (size_t)(unsigned)ce * row_stride
+        const double *src = wide ? wmsg_p[j] + (size_t)(unsigned)ce * row_stride
+                          : internal ? msg_i[j] + (size_t)(unsigned)ce * row_stride
                                      : tcol_cat_p + (unsigned)(node * KK + (ob == BNK_NONE ? 0 : ob) * K);
         double g = *src;
         if (!exists) g = 1.0;
@@ -414,9 +431,12 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
         const int po = (i & (FRING - 1)) * (int)sizeof(Step);
         const int slot = STEP_AT(po, 0, slot);
         const bool rootstep = STEP_AT(po, 0, parent) < 0;
-        const bool in0 = STEP_AT(po, 0, c_ent[0]) >= 0, in1 = STEP_AT(po, 0, c_ent[1]) >= 0;
-        const int so0 = in0 ? ly.stack + STEP_AT(po, 0, c_slot[0]) * ly.slot_bytes : dummy_off;
-        const int so1 = in1 ? ly.stack + STEP_AT(po, 0, c_slot[1]) * ly.slot_bytes : dummy_off;
+        const int dcs0 = STEP_AT(po, 0, c_slot[0]), dcs1 = STEP_AT(po, 0, c_slot[1]);
+        const bool in0 = dcs0 >= 0, in1 = dcs1 >= 0;
+        const bool wd0 = dcs0 == SLOT_WIDE, wd1 = dcs1 == SLOT_WIDE;
+        const unsigned we0 = (unsigned)STEP_AT(po, 0, c_ent[0]), we1 = (unsigned)STEP_AT(po, 0, c_ent[1]);
+        const int so0 = in0 ? ly.stack + dcs0 * ly.slot_bytes : dummy_off;
+        const int so1 = in1 ? ly.stack + dcs1 * ly.slot_bytes : dummy_off;
         const int gs_off = LY::GS + (i & 1) * ly.gs_bytes;
         {
             const bool h2 = i + 2 < n_steps, h1 = i + 1 < n_steps;
@@ -459,6 +479,9 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
             // child slots never alias this step's own slot (tree_plan.cpp)
             SM_D(so0 + sidx[j]) = D * c1;
             SM_D(so1 + sidx[j]) = D * c0;
+            // children handled by the wide level kernels receive their from-above vector through HBM
+            if (wd0) tmsg_p[j][(size_t)we0 * row_stride] = D * c1;
+            if (wd1) tmsg_p[j][(size_t)we1 * row_stride] = D * c0;
         }
         f_cp_async_wait<FSTAGE - 2>();
         __syncthreads();

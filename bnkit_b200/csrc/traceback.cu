@@ -25,9 +25,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
     extern __shared__ uint8_t tb_smem[];  // [TB_WARPS][tb_slots] when !REGSTACK
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int col = blockIdx.x * TB_WARPS + wid;
-    if (col >= a.ncols) return;
-    const int gcat = a.cat_of_col[col];
-    if (gcat < a.cat_lo || gcat >= a.cat_hi) return;
+    if (col < a.col_lo || col >= a.col_hi) return;
     const int K = a.K;
     uint8_t *st = tb_smem + wid * (a.tb_slots > 0 ? a.tb_slots : 1);
     const uint8_t *pcol = a.ptr + (size_t)col * K + (lane < K ? lane : 0);
@@ -71,7 +69,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
                 src = st[pslot];
             }
             int s = __shfl_sync(FULL, byte[u], src & 31);
-            if (kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + col];
+            if (kind == KIND_OBS) s = a.obs_s[(size_t)(unsigned)node * ncols_u + col];
             else if (kind != KIND_MSG && kind != KIND_ROOT) s = BNK_NONE;
             if (REGSTACK) {
                 if (lane == oslot) stack_reg = s;
@@ -79,7 +77,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
                 if (lane == 0 && oslot >= 0) st[oslot] = (uint8_t)s;
                 __syncwarp();
             }
-            if (lane == 0) a.out_state[(size_t)(unsigned)node * ncols_u + col] = (uint8_t)s;
+            if (lane == 0) a.state_s[(size_t)(unsigned)node * ncols_u + col] = (uint8_t)s;
         }
     }
 }

@@ -34,6 +34,119 @@ struct SlotPool {  // lowest-free-index allocator
 };
 }  // namespace
 
+// Build the up / down walk programs over the internal nodes with member[v] != 0 (an upward-closed
+// set: the whole tree, or its narrow top).  Internal children outside the set are marked SLOT_WIDE.
+static void build_program(const bnk_tree *t, const std::vector<uint8_t> &member, Program &pg)
+{
+    const int32_t n = t->n;
+    auto internal = [&](int32_t v) { return t->ent_of_node[v] >= 0; };
+    // weight = number of member nodes in the subtree (children have larger indices)
+    std::vector<int32_t> weight(n, 0);
+    for (int32_t i = n - 1; i >= 0; i--) {
+        if (internal(i) && member[i]) weight[i] += 1;
+        if (t->parent[i] >= 0) weight[t->parent[i]] += weight[i];
+    }
+    // member children of each node, heaviest first (ties: index order)
+    auto member_children = [&](int32_t v, std::vector<int32_t> &out) {
+        out.clear();
+        for (int32_t e = t->first[v]; e < t->first[v + 1]; e++)
+            if (internal(t->kids[e]) && member[t->kids[e]]) out.push_back(t->kids[e]);
+        std::stable_sort(out.begin(), out.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
+    };
+    std::vector<int32_t> up_order, down_order;
+    {
+        std::vector<int32_t> stack, tmp;
+        std::vector<uint8_t> expanded(n, 0);
+        for (int32_t r = 0; r < n; r++) {
+            if (t->parent[r] >= 0 || !internal(r) || !member[r]) continue;
+            stack.push_back(r);
+            while (!stack.empty()) {
+                const int32_t v = stack.back();
+                if (expanded[v]) { stack.pop_back(); up_order.push_back(v); continue; }
+                expanded[v] = 1;
+                member_children(v, tmp);
+                for (auto it = tmp.rbegin(); it != tmp.rend(); ++it) stack.push_back(*it);  // heaviest on top
+            }
+        }
+    }
+    {
+        std::vector<int32_t> stack, tmp;
+        for (int32_t r = n - 1; r >= 0; r--)
+            if (t->parent[r] < 0 && internal(r) && member[r]) stack.push_back(r);
+        while (!stack.empty()) {
+            const int32_t v = stack.back();
+            stack.pop_back();
+            down_order.push_back(v);
+            member_children(v, tmp);  // heaviest first -> pushed first -> popped last
+            for (int32_t c : tmp) stack.push_back(c);
+        }
+    }
+    auto child_kind = [&](int32_t u) { return !internal(u) ? SLOT_CHILDLESS : (member[u] ? 0 : SLOT_WIDE); };
+
+    pg.up.clear(); pg.up_child.clear(); pg.down.clear(); pg.down_child.clear();
+    {
+        SlotPool pool;
+        std::vector<int32_t> slot_of(n, -1);
+        for (int32_t v : up_order) {
+            Step s;
+            std::memset(&s, 0, sizeof(s));
+            s.node = v; s.parent = t->parent[v]; s.ent = t->ent_of_node[v];
+            s.child_begin = (int32_t)pg.up_child.size();
+            s.n_child = t->first[v + 1] - t->first[v];
+            s.pslot = s.oslot = -1;
+            for (int k = 0; k < 2; k++) { s.c_node[k] = -1; s.c_slot[k] = -1; s.c_ent[k] = -1; }
+            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) {
+                const int32_t u = t->kids[e];
+                const int k = e - t->first[v];
+                const int32_t kind = child_kind(u);
+                const int32_t sl = kind == 0 ? slot_of[u] : kind;
+                if (k < 2) { s.c_node[k] = u; s.c_slot[k] = sl; s.c_ent[k] = t->ent_of_node[u]; }
+                pg.up_child.push_back(ChildRef{u, sl, t->ent_of_node[u]});
+            }
+            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) pool.release(slot_of[t->kids[e]]);
+            s.slot = (t->parent[v] >= 0) ? pool.alloc() : -1;
+            slot_of[v] = s.slot;
+            pg.up.push_back(s);
+        }
+        pg.up_slots = pool.next;
+    }
+    {
+        SlotPool tpool, spool;
+        std::vector<int32_t> tslot(n, -1), sslot(n, -1), remaining(n, 0);
+        for (int32_t v : down_order) {
+            Step s;
+            std::memset(&s, 0, sizeof(s));
+            s.node = v; s.parent = t->parent[v]; s.ent = t->ent_of_node[v];
+            s.slot = tslot[v];
+            s.child_begin = (int32_t)pg.down_child.size();
+            s.n_child = t->first[v + 1] - t->first[v];
+            for (int k = 0; k < 2; k++) { s.c_node[k] = -1; s.c_slot[k] = -1; s.c_ent[k] = -1; }
+            int32_t n_member_child = 0;
+            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) {
+                const int32_t u = t->kids[e];
+                const int k = e - t->first[v];
+                const int32_t kind = child_kind(u);
+                int32_t sl = kind;
+                if (kind == 0) { sl = tpool.alloc(); tslot[u] = sl; n_member_child++; }
+                if (k < 2) { s.c_node[k] = u; s.c_slot[k] = sl; s.c_ent[k] = t->ent_of_node[u]; }
+                pg.down_child.push_back(ChildRef{u, sl, t->ent_of_node[u]});
+            }
+            tpool.release(tslot[v]);  // after the children's slots: a child never reuses its parent's slot in the same step
+            // traceback slots
+            const int32_t p = t->parent[v];
+            s.pslot = (p >= 0) ? sslot[p] : -1;
+            if (p >= 0 && --remaining[p] == 0) spool.release(sslot[p]);
+            if (n_member_child > 0) { sslot[v] = spool.alloc(); remaining[v] = n_member_child; }
+            s.oslot = sslot[v];
+            pg.down.push_back(s);
+        }
+        pg.down_slots = tpool.next;
+        pg.tb_slots = spool.next;
+    }
+}
+
+static const int32_t WIDE_MIN_NODES = 16;  // a height level with at least this many nodes runs as one launch
+
 static void build_plan(bnk_tree *t)
 {
     const int32_t n = t->n;
@@ -61,114 +174,46 @@ static void build_plan(bnk_tree *t)
     t->max_children = 0;
     for (int32_t i = 0; i < n; i++) t->max_children = std::max(t->max_children, t->first[i + 1] - t->first[i]);
 
-    // weight = number of internal nodes in the subtree (children have larger indices)
-    std::vector<int32_t> weight(n, 0);
+    std::vector<uint8_t> all(n, 1);
+    build_program(t, all, t->full);
+
+    // heights and the hybrid split
+    t->height.assign(n, 0);
+    int32_t hmax = 0;
     for (int32_t i = n - 1; i >= 0; i--) {
-        if (t->ent_of_node[i] >= 0) weight[i] += 1;
-        if (t->parent[i] >= 0) weight[t->parent[i]] += weight[i];
+        if (t->ent_of_node[i] >= 0 && t->height[i] == 0) t->height[i] = 1;  // internal with childless children only
+        if (t->parent[i] >= 0) t->height[t->parent[i]] = std::max(t->height[t->parent[i]], t->height[i] + 1);
+        hmax = std::max(hmax, t->height[i]);
     }
-    // internal children of each node, heaviest first (ties: index order)
-    auto internal_children = [&](int32_t v, std::vector<int32_t> &out) {
-        out.clear();
-        for (int32_t e = t->first[v]; e < t->first[v + 1]; e++)
-            if (t->ent_of_node[t->kids[e]] >= 0) out.push_back(t->kids[e]);
-        std::stable_sort(out.begin(), out.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
-    };
-
-    // ---- up order: iterative post-order, heavy first ----
-    std::vector<int32_t> up_order;
-    up_order.reserve(t->n_int);
-    {
-        std::vector<int32_t> stack, tmp;
-        std::vector<uint8_t> expanded(n, 0);
-        for (int32_t r = 0; r < n; r++) {
-            if (t->parent[r] >= 0 || t->ent_of_node[r] < 0) continue;
-            stack.push_back(r);
-            while (!stack.empty()) {
-                const int32_t v = stack.back();
-                if (expanded[v]) { stack.pop_back(); up_order.push_back(v); continue; }
-                expanded[v] = 1;
-                internal_children(v, tmp);
-                for (auto it = tmp.rbegin(); it != tmp.rend(); ++it) stack.push_back(*it);  // heaviest on top
-            }
+    std::vector<int32_t> width(hmax + 2, 0);
+    for (int32_t i = 0; i < n; i++)
+        if (t->ent_of_node[i] >= 0) width[t->height[i]]++;
+    t->wide_h = 0;
+    if (t->max_children <= 2)
+        while (t->wide_h + 1 <= hmax && width[t->wide_h + 1] >= WIDE_MIN_NODES) t->wide_h++;
+    // the root of a tree is never wide (its level has one node), so the narrow set is never empty
+    std::vector<uint8_t> narrow(n, 0);
+    t->levels.assign(t->wide_h, {});
+    t->n_wide = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (t->ent_of_node[i] < 0) continue;
+        if (t->height[i] > t->wide_h || t->parent[i] < 0) { narrow[i] = 1; continue; }
+        WideNode w;
+        w.node = i; w.parent = t->parent[i]; w.ent = t->ent_of_node[i];
+        w.n_child = t->first[i + 1] - t->first[i];
+        for (int k = 0; k < 2; k++) {
+            const bool has = k < w.n_child;
+            const int32_t u = has ? t->kids[t->first[i] + k] : -1;
+            w.c_node[k] = u;
+            w.c_ent[k] = has ? t->ent_of_node[u] : -1;
         }
+        t->levels[t->height[i] - 1].push_back(w);
+        t->n_wide++;
     }
-    // ---- down order: iterative pre-order, heavy last ----
-    std::vector<int32_t> down_order;
-    down_order.reserve(t->n_int);
-    {
-        std::vector<int32_t> stack, tmp;
-        for (int32_t r = n - 1; r >= 0; r--)
-            if (t->parent[r] < 0 && t->ent_of_node[r] >= 0) stack.push_back(r);
-        while (!stack.empty()) {
-            const int32_t v = stack.back();
-            stack.pop_back();
-            down_order.push_back(v);
-            internal_children(v, tmp);  // heaviest first -> push in this order so the lightest is on top
-            for (int32_t c : tmp) stack.push_back(c);
-        }
-    }
-
-    // ---- up program + message-stack slots ----
-    t->up.clear(); t->up_child.clear();
-    {
-        SlotPool pool;
-        std::vector<int32_t> slot_of(n, -1);
-        for (int32_t v : up_order) {
-            Step s;
-            std::memset(&s, 0, sizeof(s));
-            s.node = v; s.parent = t->parent[v]; s.ent = t->ent_of_node[v];
-            s.child_begin = (int32_t)t->up_child.size();
-            s.n_child = t->first[v + 1] - t->first[v];
-            s.pslot = s.oslot = -1;
-            for (int k = 0; k < 2; k++) { s.c_node[k] = -1; s.c_slot[k] = -1; s.c_ent[k] = -1; }
-            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) {
-                const int32_t u = t->kids[e];
-                const int k = e - t->first[v];
-                if (k < 2) { s.c_node[k] = u; s.c_slot[k] = slot_of[u]; s.c_ent[k] = t->ent_of_node[u]; }
-                t->up_child.push_back(ChildRef{u, slot_of[u], t->ent_of_node[u]});
-            }
-            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) pool.release(slot_of[t->kids[e]]);
-            s.slot = (t->parent[v] >= 0) ? pool.alloc() : -1;
-            slot_of[v] = s.slot;
-            t->up.push_back(s);
-        }
-        t->up_slots = pool.next;
-    }
-    // ---- down program: from-above vector slots and traceback state slots ----
-    t->down.clear(); t->down_child.clear();
-    {
-        SlotPool tpool, spool;
-        std::vector<int32_t> tslot(n, -1), sslot(n, -1), remaining(n, 0);
-        for (int32_t v : down_order) {
-            Step s;
-            std::memset(&s, 0, sizeof(s));
-            s.node = v; s.parent = t->parent[v]; s.ent = t->ent_of_node[v];
-            s.slot = tslot[v];
-            s.child_begin = (int32_t)t->down_child.size();
-            s.n_child = t->first[v + 1] - t->first[v];
-            for (int k = 0; k < 2; k++) { s.c_node[k] = -1; s.c_slot[k] = -1; s.c_ent[k] = -1; }
-            int32_t n_int_child = 0;
-            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) {
-                const int32_t u = t->kids[e];
-                const int k = e - t->first[v];
-                int32_t sl = -1;
-                if (t->ent_of_node[u] >= 0) { sl = tpool.alloc(); tslot[u] = sl; n_int_child++; }
-                if (k < 2) { s.c_node[k] = u; s.c_slot[k] = sl; s.c_ent[k] = t->ent_of_node[u]; }
-                t->down_child.push_back(ChildRef{u, sl, t->ent_of_node[u]});
-            }
-            tpool.release(tslot[v]);  // after the children's slots: a child never reuses its parent's slot in the same step
-            // traceback slots
-            const int32_t p = t->parent[v];
-            s.pslot = (p >= 0) ? sslot[p] : -1;
-            if (p >= 0 && --remaining[p] == 0) spool.release(sslot[p]);
-            if (n_int_child > 0) { sslot[v] = spool.alloc(); remaining[v] = n_int_child; }
-            s.oslot = sslot[v];
-            t->down.push_back(s);
-        }
-        t->down_slots = tpool.next;
-        t->tb_slots = spool.next;
-    }
+    // narrow must be upward closed: a wide node's parent has a larger height, hence is narrow or wide
+    // at a higher level -- fine; but a root that was forced narrow may sit below wide_h: its
+    // descendants are still wide (downward closed), which is all the kernels need.
+    build_program(t, narrow, t->narrow);
 }
 
 }  // namespace bnk

@@ -1,0 +1,296 @@
+// wide.cu -- level kernels: all nodes of one height level in one launch, one COLUMN per thread.
+//
+// Where a height level of the tree holds many nodes (tree_plan.cpp: >= 16), every (node, column)
+// pair of the level is independent, so the level runs as one launch over a (column tiles x nodes)
+// grid -- the "level-order schedule" of BASELINE.json's north star.  A thread owns one column:
+// the 20-state vector it combines lives in registers, the node's 20x20 table sits in shared
+// memory and is read as warp-uniform broadcasts (one wavefront serves 32 columns), leaf children
+// are table lookups by the observed state, and messages travel through HBM in
+// [node][state][column] layout so that every load and store is a coalesced row.
+// This is the HBM-bound formulation of SURVEY.md 8(d); the column-owned walker (sweeps_fast.cu)
+// keeps the deep, narrow top of the tree, reading these messages as its leaf-level input.
+//
+// Same arithmetic as the walker (and the oracle): joint adds in child order then L_v[p][x] + G[x],
+// first strict maximum scanning x ascending; sum-product in linear space with an exact 2^-e
+// rescale per (node, column) whose exponents are summed into the log-likelihood.
+// Preconditions (checked by the host): nothing masked, evidence on childless nodes only, at most
+// two children per node, one rate category per column tile, wide nodes are never roots.
+#include "device_common.cuh"
+
+namespace bnk {
+
+constexpr int WT = 128;  // columns (= threads) per CTA
+
+template <int K>
+__device__ __forceinline__ void load_table(double *dst, const double *src, int pad)
+{
+    // dst rows of K + pad doubles
+    for (int q = threadIdx.x; q < K * K; q += WT) dst[(q / K) * (K + pad) + (q % K)] = src[q];
+}
+
+__device__ __forceinline__ double w_pow2_scale(int mhi, int &e)
+{
+    const int be = mhi >> 20;
+    if (be == 0) { e = 0; return 1.0; }
+    e = be - 1023;
+    return __hiloint2double((2046 - be) << 20, 0);
+}
+
+__device__ __forceinline__ double w_rcp(double s)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    r = fma(r, fma(-s, r, 1.0), r);
+    r = fma(r, fma(-s, r, 1.0), r);
+    return r;
+}
+
+// message of child e of node w for this thread's column, all K states.  MODE 0: log space, 1: linear.
+template <int K, int MODE>
+__device__ __forceinline__ void child_vector(const WideArgs &a, const WideNode &w, int e, size_t tb, int col, bool valid,
+                                             const double *lt_smem, double (&g)[K])
+{
+    const int cn = w.c_node[e];
+    if (w.c_ent[e] >= 0) {  // internal child: its message row-block in HBM
+        const double *m = a.msg + (size_t)w.c_ent[e] * K * a.ncols + col;
+#pragma unroll
+        for (int x = 0; x < K; x++) g[x] = m[(size_t)x * a.ncols];
+    } else {
+        const int ou = a.obs[(size_t)cn * a.ncols + col];
+        if (ou != BNK_NONE) {
+#pragma unroll
+            for (int x = 0; x < K; x++) g[x] = lt_smem[ou * (K + 1) + x];
+        } else {  // uninstantiated childless node: maximise / marginalise its own row
+            const double *L = a.T_row + (tb + cn) * (K * K);
+#pragma unroll
+            for (int x = 0; x < K; x++) {
+                double r = L[x * K];
+                for (int y = 1; y < K; y++) r = (MODE == 0) ? (L[x * K + y] > r ? L[x * K + y] : r) : r + L[x * K + y];
+                g[x] = r;
+            }
+        }
+    }
+    (void)valid;
+}
+
+// ------------------------------------------------------------------------------------
+// up-sweeps
+// ------------------------------------------------------------------------------------
+template <int K, int MODE>
+__global__ void __launch_bounds__(WT) up_wide_kernel(const WideArgs a)
+{
+    __shared__ __align__(16) double Ls[K * K];
+    __shared__ double LT0[K * (K + 1)], LT1[K * (K + 1)];
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const WideNode w = a.nodes[blockIdx.y];
+    const size_t tb = (size_t)tile.cat0 * a.n_nodes;
+    load_table<K>(Ls, a.T_row + (tb + w.node) * (K * K), 0);
+    if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
+    if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+    __syncthreads();
+    const bool valid = (int)threadIdx.x < tile.ncols;
+    const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
+
+    double G[K], g[K];
+    child_vector<K, MODE>(a, w, 0, tb, col, valid, LT0, G);
+    if (w.n_child > 1) {
+        child_vector<K, MODE>(a, w, 1, tb, col, valid, LT1, g);
+#pragma unroll
+        for (int x = 0; x < K; x++) G[x] = (MODE == 0) ? G[x] + g[x] : G[x] * g[x];
+    }
+    double *mout = a.msg + (size_t)w.ent * K * a.ncols + col;
+    if (MODE == 0) {
+        uint8_t *pout = a.ptr + (size_t)w.ent * K * a.ncols + col;
+#pragma unroll 2
+        for (int p = 0; p < K; p++) {
+            const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
+            double best = -CUDART_INF;
+            int bi = 0;
+#pragma unroll
+            for (int x2 = 0; x2 < K / 2; x2++) {
+                const double2 l = row2[x2];
+                const double v0 = l.x + G[2 * x2], v1 = l.y + G[2 * x2 + 1];
+                const bool t0 = v0 > best;
+                best = t0 ? v0 : best;
+                bi = t0 ? 2 * x2 : bi;
+                const bool t1 = v1 > best;
+                best = t1 ? v1 : best;
+                bi = t1 ? 2 * x2 + 1 : bi;
+            }
+            if (valid) {
+                mout[(size_t)p * a.ncols] = best;
+                pout[(size_t)p * a.ncols] = (uint8_t)bi;
+            }
+        }
+    } else {
+        int mhi = 0;
+#pragma unroll
+        for (int x = 0; x < K; x++) mhi = max(mhi, __double2hiint(G[x]));
+        int e;
+        const double scale = w_pow2_scale(mhi, e);
+#pragma unroll
+        for (int x = 0; x < K; x++) G[x] *= scale;  // exact: power of two
+#pragma unroll 2
+        for (int p = 0; p < K; p++) {
+            const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int x2 = 0; x2 < K / 2; x2++) {
+                const double2 l = row2[x2];
+                acc0 = fma(l.x, G[2 * x2], acc0);
+                acc1 = fma(l.y, G[2 * x2 + 1], acc1);
+            }
+            if (valid) mout[(size_t)p * a.ncols] = acc0 + acc1;
+        }
+        if (valid && a.escale) a.escale[(size_t)(a.wide_row0 + blockIdx.y) * a.ncols + col] = (int16_t)e;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// down-sweep: T (from above, HBM) -> D = P^T T -> posterior, and the children's from-above vectors
+// ------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(WT) down_wide_kernel(const WideArgs a)
+{
+    __shared__ __align__(16) double PTs[K * K];
+    __shared__ double LT0[K * (K + 1)], LT1[K * (K + 1)];
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const WideNode w = a.nodes[blockIdx.y];
+    const size_t tb = (size_t)tile.cat0 * a.n_nodes;
+    load_table<K>(PTs, a.T_col + (tb + w.node) * (K * K), 0);  // PT[x][xp] = P[xp][x]
+    if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
+    if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+    __syncthreads();
+    const bool valid = (int)threadIdx.x < tile.ncols;
+    const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
+
+    double T[K];
+    {
+        const double *t = a.tmsg + (size_t)w.ent * K * a.ncols + col;
+        int mhi = 0;
+#pragma unroll
+        for (int x = 0; x < K; x++) { T[x] = t[(size_t)x * a.ncols]; mhi = max(mhi, __double2hiint(T[x])); }
+        int e;
+        const double scale = w_pow2_scale(mhi, e);
+#pragma unroll
+        for (int x = 0; x < K; x++) T[x] *= scale;
+    }
+    double g0[K], g1[K];
+    child_vector<K, 1>(a, w, 0, tb, col, valid, LT0, g0);
+    if (w.n_child > 1) child_vector<K, 1>(a, w, 1, tb, col, valid, LT1, g1);
+    else {
+#pragma unroll
+        for (int x = 0; x < K; x++) g1[x] = 1.0;
+    }
+    const bool push0 = w.c_ent[0] >= 0, push1 = w.n_child > 1 && w.c_ent[1] >= 0;
+    double *t0 = push0 ? a.tmsg + (size_t)w.c_ent[0] * K * a.ncols + col : nullptr;
+    double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
+    double U[K], S = 0.0;
+#pragma unroll
+    for (int x = 0; x < K; x++) {
+        const double2 *row2 = reinterpret_cast<const double2 *>(PTs + x * K);
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int y2 = 0; y2 < K / 2; y2++) {
+            const double2 l = row2[y2];
+            acc0 = fma(l.x, T[2 * y2], acc0);
+            acc1 = fma(l.y, T[2 * y2 + 1], acc1);
+        }
+        const double D = acc0 + acc1;
+        if (valid && push0) t0[(size_t)x * a.ncols] = D * g1[x];
+        if (valid && push1) t1[(size_t)x * a.ncols] = D * g0[x];
+        U[x] = D * (g0[x] * g1[x]);
+        S += U[x];
+    }
+    const int q = a.qrow ? a.qrow[w.ent] : w.ent;
+    if (valid && q >= 0 && a.out_post) {
+        const double r = w_rcp(S);
+        double *o = a.out_post + ((size_t)q * a.ncols + a.orig_col[col]) * K;
+#pragma unroll
+        for (int x2 = 0; x2 < K / 2; x2++)
+            reinterpret_cast<double2 *>(o)[x2] = make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// traceback of one level (processed from the highest wide level down): one (node, column) per thread
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) traceback_wide_kernel(const WideArgs a, int K)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < a.col_lo || col >= a.col_hi) return;
+    const WideNode w = a.nodes[blockIdx.y];
+    const int sp = a.state_s[(size_t)w.parent * a.ncols + col];
+    a.state_s[(size_t)w.node * a.ncols + col] = a.ptr[((size_t)w.ent * K + sp) * a.ncols + col];
+}
+
+// sum of the per-node rescale exponents of the wide part: esum[col] = sum_rows escale[row][col]
+__global__ void sum_escale_kernel(const int16_t *__restrict__ escale, int n_rows, int ncols, int32_t *__restrict__ esum)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    int s = 0;
+    for (int r = 0; r < n_rows; r++) s += escale[(size_t)r * ncols + col];
+    esum[col] = s;
+}
+
+// out[row(node)][orig_col[c]] = in[row(node)][c] for the listed nodes (sorted -> original column order)
+__global__ void scatter_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                    const int32_t *__restrict__ nodes, const int32_t *__restrict__ orig_col, int ncols)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    const size_t row = (size_t)nodes[blockIdx.y] * ncols;
+    out[row + orig_col[c]] = in[row + c];
+}
+
+// ------------------------------------------------------------------------------------
+cudaError_t launch_up_wide(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st)
+{
+    if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
+    dim3 grid(n_tiles, n_nodes);
+    if (K == 20 && mode == 0) up_wide_kernel<20, 0><<<grid, WT, 0, st>>>(a);
+    else if (K == 20) up_wide_kernel<20, 1><<<grid, WT, 0, st>>>(a);
+    else if (mode == 0) up_wide_kernel<4, 0><<<grid, WT, 0, st>>>(a);
+    else up_wide_kernel<4, 1><<<grid, WT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_down_wide(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st)
+{
+    if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
+    dim3 grid(n_tiles, n_nodes);
+    if (K == 20) down_wide_kernel<20><<<grid, WT, 0, st>>>(a);
+    else down_wide_kernel<4><<<grid, WT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_traceback_wide(int K, const WideArgs &a, int n_nodes, cudaStream_t st)
+{
+    if (n_nodes == 0) return cudaSuccess;
+    dim3 grid((a.ncols + 255) / 256, n_nodes);
+    traceback_wide_kernel<<<grid, 256, 0, st>>>(a, K);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_escale(const int16_t *escale, int n_rows, int ncols, int32_t *esum, cudaStream_t st)
+{
+    sum_escale_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(escale, n_rows, ncols, esum);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_rows(const uint8_t *in, uint8_t *out, const int32_t *nodes, int n_rows,
+                                const int32_t *orig_col, int ncols, cudaStream_t st)
+{
+    if (n_rows == 0) return cudaSuccess;
+    for (int r0 = 0; r0 < n_rows; r0 += 65535) {
+        const int nr = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
+        dim3 grid((ncols + 255) / 256, nr);
+        scatter_rows_kernel<<<grid, 256, 0, st>>>(in, out, nodes + r0, orig_col, ncols);
+    }
+    return cudaGetLastError();
+}
+
+int wide_tile_cols() { return WT; }
+
+}  // namespace bnk

@@ -145,7 +145,7 @@ def test_full_size_properties_c3(bnk):
     assert np.isfinite(logl).all() and np.isclose(total, logl.sum(), rtol=1e-12)
     assert (st[~leaf] < 20).all() and np.array_equal(st[leaf], obs[leaf])
     # other tile geometry and the general kernels give bit-identical states
-    for tile, cpt in ((34, 2), (11, -1)):
+    for tile, cpt in ((34, 2), (11, -1), (-17, 1)):
         ws2 = bnk.Workspace(m, tree, n_cols)
         ws2.configure(tile, cpt)
         ws2.set_rates(n_cols, rates)

@@ -110,12 +110,14 @@ def test_ties_go_to_lowest_state(bnk, oracle):
         ws.close()
 
 
-@pytest.mark.parametrize("tile_cols,cpt", [(4, 1), (7, 1), (16, 2), (38, 1), (30, 4), (64, 2), (17, -1), (20, -2)])
+@pytest.mark.parametrize("tile_cols,cpt", [(4, 1), (7, 1), (16, 2), (38, 1), (30, 4), (64, 2), (17, -1), (20, -2), (-12, 2), (-30, 1)])
 def test_tile_geometries(bnk, oracle, tile_cols, cpt):
-    """cpt < 0 forces the general kernels on inputs the lean kernels would otherwise take."""
+    """cpt < 0 forces the general kernels on inputs the lean kernels would otherwise take;
+    tile_cols < 0 keeps the whole tree in the column-owned walker (no wide level launches)."""
     rng = np.random.default_rng(16)
     rates = rng.choice([0.3, 1.0, 2.5], size=257)
     _run_case(bnk, oracle, "LG", rng, 50, 257, rates=rates, tile_cols=tile_cols, cpt=cpt)
+    _run_case(bnk, oracle, "LG", rng, 300, 150, rates=rates[:150], tile_cols=tile_cols, cpt=cpt)   # has wide levels
     _run_case(bnk, oracle, "LG", rng, 21, 100, gap=0.5, mask=True, tile_cols=tile_cols, cpt=cpt)
 
 
