@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -73,6 +74,7 @@ struct bnk_ws {
     int64_t launches = 0, dev_bytes = 0;
     int cfg_tile_cols = 0, cfg_cpt = 0;
     bool force_generic = false;
+    int wide_tpc_max = 8;  // r1 sweep on C3a: 4-8 tiles per CTA best
     size_t table_budget = (size_t)12 << 30;
     // static device data
     DevBuf<double> d_model;  // evec | ievec | eval | prior | logprior
@@ -224,6 +226,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
         ws->own_stream = true;
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
+    if (const char *env = std::getenv("BNK_WIDE_TPC")) ws->wide_tpc_max = std::max(1, std::atoi(env));  // tuning knob
     // accounting hooks
     DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
                             &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_post, &ws->d_sum};
@@ -616,6 +619,8 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
     WideArgs w;
     std::memset(&w, 0, sizeof(w));
     w.tiles = ws->d_wtiles.p + ws->chunk_wtiles[ci].first;
+    w.n_tiles = ws->chunk_wtiles[ci].second - ws->chunk_wtiles[ci].first;
+    w.tiles_per_cta = 1;
     w.obs = obs_s;
     w.ncols = ws->ncols; w.n_nodes = ws->n;
     w.orig_col = ws->d_orig_col.p;
@@ -634,6 +639,11 @@ static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch)
             const int cnt = std::min(65535, ws->level_off[h + 1] - off);
             w.nodes = ws->d_wide.p + off;
             w.wide_row0 = off;
+            {   // several tiles per CTA amortise the table loads, as long as ~8 CTAs per SM remain
+                const int64_t ctas = (int64_t)cnt * w.n_tiles;
+                int tpc = (int)(ctas / ((int64_t)ws->sm_count * 8));
+                w.tiles_per_cta = std::max(1, std::min(tpc, ws->wide_tpc_max));
+            }
             CUDA_TRY(launch(w, cnt));
             ws->launches++;
         }

@@ -68,6 +68,7 @@ struct WalkArgs {
 struct WideArgs {
     const WideNode *nodes;   // the level (or a slice of it): gridDim.y entries
     const TileDesc *tiles;   // wide column tiles: one category each, <= 128 columns
+    int32_t n_tiles, tiles_per_cta;  // a CTA walks tiles_per_cta consecutive tiles (tables reloaded only when the category changes)
     const uint8_t *obs;
     int32_t ncols, n_nodes;
     const int32_t *orig_col;

@@ -77,72 +77,80 @@ __device__ __forceinline__ void child_vector(const WideArgs &a, const WideNode &
 // up-sweeps
 // ------------------------------------------------------------------------------------
 template <int K, int MODE>
-__global__ void __launch_bounds__(WT) up_wide_kernel(const WideArgs a)
+__global__ void __launch_bounds__(WT, 5) up_wide_kernel(const WideArgs a)
 {
     __shared__ __align__(16) double Ls[K * K];
     __shared__ double LT0[K * (K + 1)], LT1[K * (K + 1)];
-    const TileDesc tile = a.tiles[blockIdx.x];
     const WideNode w = a.nodes[blockIdx.y];
-    const size_t tb = (size_t)tile.cat0 * a.n_nodes;
-    load_table<K>(Ls, a.T_row + (tb + w.node) * (K * K), 0);
-    if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
-    if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
-    __syncthreads();
-    const bool valid = (int)threadIdx.x < tile.ncols;
-    const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
+    const int t_lo = blockIdx.x * a.tiles_per_cta, t_hi = min(t_lo + a.tiles_per_cta, a.n_tiles);
+    int cur_cat = -1;
+    for (int ti = t_lo; ti < t_hi; ti++) {
+        const TileDesc tile = a.tiles[ti];
+        const size_t tb = (size_t)tile.cat0 * a.n_nodes;
+        if (tile.cat0 != cur_cat) {  // uniform: tables of this node for the tile's rate category
+            __syncthreads();
+            load_table<K>(Ls, a.T_row + (tb + w.node) * (K * K), 0);
+            if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
+            if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+            __syncthreads();
+            cur_cat = tile.cat0;
+        }
+        const bool valid = (int)threadIdx.x < tile.ncols;
+        const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
 
-    double G[K], g[K];
-    child_vector<K, MODE>(a, w, 0, tb, col, valid, LT0, G);
-    if (w.n_child > 1) {
-        child_vector<K, MODE>(a, w, 1, tb, col, valid, LT1, g);
+        double G[K], g[K];
+        child_vector<K, MODE>(a, w, 0, tb, col, valid, LT0, G);
+        if (w.n_child > 1) {
+            child_vector<K, MODE>(a, w, 1, tb, col, valid, LT1, g);
 #pragma unroll
-        for (int x = 0; x < K; x++) G[x] = (MODE == 0) ? G[x] + g[x] : G[x] * g[x];
-    }
-    double *mout = a.msg + (size_t)w.ent * K * a.ncols + col;
-    if (MODE == 0) {
-        uint8_t *pout = a.ptr + (size_t)w.ent * K * a.ncols + col;
-#pragma unroll 2
-        for (int p = 0; p < K; p++) {
-            const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
-            double best = -CUDART_INF;
-            int bi = 0;
-#pragma unroll
-            for (int x2 = 0; x2 < K / 2; x2++) {
-                const double2 l = row2[x2];
-                const double v0 = l.x + G[2 * x2], v1 = l.y + G[2 * x2 + 1];
-                const bool t0 = v0 > best;
-                best = t0 ? v0 : best;
-                bi = t0 ? 2 * x2 : bi;
-                const bool t1 = v1 > best;
-                best = t1 ? v1 : best;
-                bi = t1 ? 2 * x2 + 1 : bi;
-            }
-            if (valid) {
-                mout[(size_t)p * a.ncols] = best;
-                pout[(size_t)p * a.ncols] = (uint8_t)bi;
-            }
+            for (int x = 0; x < K; x++) G[x] = (MODE == 0) ? G[x] + g[x] : G[x] * g[x];
         }
-    } else {
-        int mhi = 0;
+        double *mout = a.msg + (size_t)w.ent * K * a.ncols + col;
+        if (MODE == 0) {
+            uint8_t *pout = a.ptr + (size_t)w.ent * K * a.ncols + col;
+#pragma unroll 4
+            for (int p = 0; p < K; p++) {
+                const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
+                double best = -CUDART_INF;
+                int bi = 0;
 #pragma unroll
-        for (int x = 0; x < K; x++) mhi = max(mhi, __double2hiint(G[x]));
-        int e;
-        const double scale = w_pow2_scale(mhi, e);
-#pragma unroll
-        for (int x = 0; x < K; x++) G[x] *= scale;  // exact: power of two
-#pragma unroll 2
-        for (int p = 0; p < K; p++) {
-            const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-            for (int x2 = 0; x2 < K / 2; x2++) {
-                const double2 l = row2[x2];
-                acc0 = fma(l.x, G[2 * x2], acc0);
-                acc1 = fma(l.y, G[2 * x2 + 1], acc1);
+                for (int x2 = 0; x2 < K / 2; x2++) {
+                    const double2 l = row2[x2];
+                    const double v0 = l.x + G[2 * x2], v1 = l.y + G[2 * x2 + 1];
+                    const bool t0 = v0 > best;
+                    best = t0 ? v0 : best;
+                    bi = t0 ? 2 * x2 : bi;
+                    const bool t1 = v1 > best;
+                    best = t1 ? v1 : best;
+                    bi = t1 ? 2 * x2 + 1 : bi;
+                }
+                if (valid) {
+                    mout[(size_t)p * a.ncols] = best;
+                    pout[(size_t)p * a.ncols] = (uint8_t)bi;
+                }
             }
-            if (valid) mout[(size_t)p * a.ncols] = acc0 + acc1;
+        } else {
+            int mhi = 0;
+#pragma unroll
+            for (int x = 0; x < K; x++) mhi = max(mhi, __double2hiint(G[x]));
+            int e;
+            const double scale = w_pow2_scale(mhi, e);
+#pragma unroll
+            for (int x = 0; x < K; x++) G[x] *= scale;  // exact: power of two
+#pragma unroll 2
+            for (int p = 0; p < K; p++) {
+                const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int x2 = 0; x2 < K / 2; x2++) {
+                    const double2 l = row2[x2];
+                    acc0 = fma(l.x, G[2 * x2], acc0);
+                    acc1 = fma(l.y, G[2 * x2 + 1], acc1);
+                }
+                if (valid) mout[(size_t)p * a.ncols] = acc0 + acc1;
+            }
+            if (valid && a.escale) a.escale[(size_t)(a.wide_row0 + blockIdx.y) * a.ncols + col] = (int16_t)e;
         }
-        if (valid && a.escale) a.escale[(size_t)(a.wide_row0 + blockIdx.y) * a.ncols + col] = (int16_t)e;
     }
 }
 
@@ -150,65 +158,97 @@ __global__ void __launch_bounds__(WT) up_wide_kernel(const WideArgs a)
 // down-sweep: T (from above, HBM) -> D = P^T T -> posterior, and the children's from-above vectors
 // ------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(WT) down_wide_kernel(const WideArgs a)
+__global__ void __launch_bounds__(WT, 4) down_wide_kernel(const WideArgs a)
 {
     __shared__ __align__(16) double PTs[K * K];
     __shared__ double LT0[K * (K + 1)], LT1[K * (K + 1)];
-    const TileDesc tile = a.tiles[blockIdx.x];
     const WideNode w = a.nodes[blockIdx.y];
-    const size_t tb = (size_t)tile.cat0 * a.n_nodes;
-    load_table<K>(PTs, a.T_col + (tb + w.node) * (K * K), 0);  // PT[x][xp] = P[xp][x]
-    if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
-    if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
-    __syncthreads();
-    const bool valid = (int)threadIdx.x < tile.ncols;
-    const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
-
-    double T[K];
-    {
-        const double *t = a.tmsg + (size_t)w.ent * K * a.ncols + col;
-        int mhi = 0;
-#pragma unroll
-        for (int x = 0; x < K; x++) { T[x] = t[(size_t)x * a.ncols]; mhi = max(mhi, __double2hiint(T[x])); }
-        int e;
-        const double scale = w_pow2_scale(mhi, e);
-#pragma unroll
-        for (int x = 0; x < K; x++) T[x] *= scale;
-    }
-    double g0[K], g1[K];
-    child_vector<K, 1>(a, w, 0, tb, col, valid, LT0, g0);
-    if (w.n_child > 1) child_vector<K, 1>(a, w, 1, tb, col, valid, LT1, g1);
-    else {
-#pragma unroll
-        for (int x = 0; x < K; x++) g1[x] = 1.0;
-    }
-    const bool push0 = w.c_ent[0] >= 0, push1 = w.n_child > 1 && w.c_ent[1] >= 0;
-    double *t0 = push0 ? a.tmsg + (size_t)w.c_ent[0] * K * a.ncols + col : nullptr;
-    double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
-    double U[K], S = 0.0;
-#pragma unroll
-    for (int x = 0; x < K; x++) {
-        const double2 *row2 = reinterpret_cast<const double2 *>(PTs + x * K);
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-        for (int y2 = 0; y2 < K / 2; y2++) {
-            const double2 l = row2[y2];
-            acc0 = fma(l.x, T[2 * y2], acc0);
-            acc1 = fma(l.y, T[2 * y2 + 1], acc1);
-        }
-        const double D = acc0 + acc1;
-        if (valid && push0) t0[(size_t)x * a.ncols] = D * g1[x];
-        if (valid && push1) t1[(size_t)x * a.ncols] = D * g0[x];
-        U[x] = D * (g0[x] * g1[x]);
-        S += U[x];
-    }
+    const int t_lo = blockIdx.x * a.tiles_per_cta, t_hi = min(t_lo + a.tiles_per_cta, a.n_tiles);
+    const bool two = w.n_child > 1;
+    const bool leaf0 = w.c_ent[0] < 0, leaf1 = two && w.c_ent[1] < 0;
+    const bool push0 = !leaf0, push1 = two && !leaf1;
     const int q = a.qrow ? a.qrow[w.ent] : w.ent;
-    if (valid && q >= 0 && a.out_post) {
-        const double r = w_rcp(S);
-        double *o = a.out_post + ((size_t)q * a.ncols + a.orig_col[col]) * K;
+    int cur_cat = -1;
+    for (int ti = t_lo; ti < t_hi; ti++) {
+        const TileDesc tile = a.tiles[ti];
+        const size_t tb = (size_t)tile.cat0 * a.n_nodes;
+        if (tile.cat0 != cur_cat) {
+            __syncthreads();
+            load_table<K>(PTs, a.T_col + (tb + w.node) * (K * K), 0);  // PT[x][xp] = P[xp][x]
+            if (leaf0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
+            if (leaf1) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+            __syncthreads();
+            cur_cat = tile.cat0;
+        }
+        const bool valid = (int)threadIdx.x < tile.ncols;
+        const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
+
+        double T[K];
+        {
+            const double *t = a.tmsg + (size_t)w.ent * K * a.ncols + col;
+            int mhi = 0;
 #pragma unroll
-        for (int x2 = 0; x2 < K / 2; x2++)
-            reinterpret_cast<double2 *>(o)[x2] = make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r);
+            for (int x = 0; x < K; x++) { T[x] = t[(size_t)x * a.ncols]; mhi = max(mhi, __double2hiint(T[x])); }
+            int e;
+            const double scale = w_pow2_scale(mhi, e);
+#pragma unroll
+            for (int x = 0; x < K; x++) T[x] *= scale;
+        }
+        // children: an observed leaf is a row of its P^T table (shared memory), an internal child
+        // its up-message in HBM; uninstantiated leaves (rare) go through child_vector
+        int o0 = BNK_NONE, o1 = BNK_NONE;
+        if (leaf0) o0 = a.obs[(size_t)w.c_node[0] * a.ncols + col];
+        if (leaf1) o1 = a.obs[(size_t)w.c_node[1] * a.ncols + col];
+        const bool slow = (leaf0 && o0 == BNK_NONE) || (leaf1 && o1 == BNK_NONE);
+        const double *m0 = leaf0 ? nullptr : a.msg + (size_t)w.c_ent[0] * K * a.ncols + col;
+        const double *m1 = (two && !leaf1) ? a.msg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
+        double *t0 = push0 ? a.tmsg + (size_t)w.c_ent[0] * K * a.ncols + col : nullptr;
+        double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
+        double U[K], S = 0.0;
+        if (!slow) {
+#pragma unroll
+            for (int x = 0; x < K; x++) {
+                const double c0 = leaf0 ? LT0[o0 * (K + 1) + x] : m0[(size_t)x * a.ncols];
+                const double c1 = !two ? 1.0 : (leaf1 ? LT1[o1 * (K + 1) + x] : m1[(size_t)x * a.ncols]);
+                const double2 *row2 = reinterpret_cast<const double2 *>(PTs + x * K);
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int y2 = 0; y2 < K / 2; y2++) {
+                    const double2 l = row2[y2];
+                    acc0 = fma(l.x, T[2 * y2], acc0);
+                    acc1 = fma(l.y, T[2 * y2 + 1], acc1);
+                }
+                const double D = acc0 + acc1;
+                if (valid && push0) t0[(size_t)x * a.ncols] = D * c1;
+                if (valid && push1) t1[(size_t)x * a.ncols] = D * c0;
+                U[x] = D * (c0 * c1);
+                S += U[x];
+            }
+        } else {
+            double g0[K], g1[K];
+            child_vector<K, 1>(a, w, 0, tb, col, valid, LT0, g0);
+            if (two) child_vector<K, 1>(a, w, 1, tb, col, valid, LT1, g1);
+            else {
+#pragma unroll
+                for (int x = 0; x < K; x++) g1[x] = 1.0;
+            }
+#pragma unroll
+            for (int x = 0; x < K; x++) {
+                double D = 0.0;
+                for (int y = 0; y < K; y++) D = fma(PTs[x * K + y], T[y], D);
+                if (valid && push0) t0[(size_t)x * a.ncols] = D * g1[x];
+                if (valid && push1) t1[(size_t)x * a.ncols] = D * g0[x];
+                U[x] = D * (g0[x] * g1[x]);
+                S += U[x];
+            }
+        }
+        if (valid && q >= 0 && a.out_post) {
+            const double r = w_rcp(S);
+            double *o = a.out_post + ((size_t)q * a.ncols + a.orig_col[col]) * K;
+#pragma unroll
+            for (int x2 = 0; x2 < K / 2; x2++)
+                reinterpret_cast<double2 *>(o)[x2] = make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r);
+        }
     }
 }
 
@@ -224,14 +264,15 @@ __global__ void __launch_bounds__(256) traceback_wide_kernel(const WideArgs a, i
     a.state_s[(size_t)w.node * a.ncols + col] = a.ptr[((size_t)w.ent * K + sp) * a.ncols + col];
 }
 
-// sum of the per-node rescale exponents of the wide part: esum[col] = sum_rows escale[row][col]
+// sum of the per-node rescale exponents of the wide part: esum[col] += sum over a slab of rows
 __global__ void sum_escale_kernel(const int16_t *__restrict__ escale, int n_rows, int ncols, int32_t *__restrict__ esum)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncols) return;
+    const int r0 = blockIdx.y * 128, r1 = min(r0 + 128, n_rows);
     int s = 0;
-    for (int r = 0; r < n_rows; r++) s += escale[(size_t)r * ncols + col];
-    esum[col] = s;
+    for (int r = r0; r < r1; r++) s += escale[(size_t)r * ncols + col];
+    atomicAdd(esum + col, s);
 }
 
 // out[row(node)][orig_col[c]] = in[row(node)][c] for the listed nodes (sorted -> original column order)
@@ -248,7 +289,7 @@ __global__ void scatter_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__r
 cudaError_t launch_up_wide(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st)
 {
     if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
-    dim3 grid(n_tiles, n_nodes);
+    dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, n_nodes);
     if (K == 20 && mode == 0) up_wide_kernel<20, 0><<<grid, WT, 0, st>>>(a);
     else if (K == 20) up_wide_kernel<20, 1><<<grid, WT, 0, st>>>(a);
     else if (mode == 0) up_wide_kernel<4, 0><<<grid, WT, 0, st>>>(a);
@@ -259,7 +300,7 @@ cudaError_t launch_up_wide(int K, int mode, const WideArgs &a, int n_tiles, int 
 cudaError_t launch_down_wide(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st)
 {
     if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
-    dim3 grid(n_tiles, n_nodes);
+    dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, n_nodes);
     if (K == 20) down_wide_kernel<20><<<grid, WT, 0, st>>>(a);
     else down_wide_kernel<4><<<grid, WT, 0, st>>>(a);
     return cudaGetLastError();
@@ -275,7 +316,10 @@ cudaError_t launch_traceback_wide(int K, const WideArgs &a, int n_nodes, cudaStr
 
 cudaError_t launch_sum_escale(const int16_t *escale, int n_rows, int ncols, int32_t *esum, cudaStream_t st)
 {
-    sum_escale_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(escale, n_rows, ncols, esum);
+    cudaError_t e = cudaMemsetAsync(esum, 0, sizeof(int32_t) * ncols, st);
+    if (e != cudaSuccess || n_rows == 0) return e;
+    dim3 grid((ncols + 127) / 128, (n_rows + 127) / 128);
+    sum_escale_kernel<<<grid, 128, 0, st>>>(escale, n_rows, ncols, esum);
     return cudaGetLastError();
 }
 

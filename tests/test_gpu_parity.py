@@ -136,3 +136,29 @@ def test_deep_caterpillar_and_spill(bnk, oracle):
         _post_close(post, wpost[leaves_of(parent) == False])
         assert np.allclose(logl, wlogl, rtol=TOL)
         ws.close()
+
+
+def test_large_irregular_tree_hybrid(bnk, oracle):
+    """5,000-leaf random (agglomeration) tree: many wide height levels plus a long narrow tail for the
+    walker; joint bit-exact, posteriors / logL 1e-9, with Gamma categories."""
+    from bnkit_b200 import synth
+    rng = np.random.default_rng(18)
+    parent, dist = synth.random_tree(5000, seed=9)
+    m, om = bnk.Model("WAG"), oracle.Model("WAG")
+    n_cols = 96
+    rates = rng.choice(synth.gamma_category_rates(0.5, 4), size=n_cols)
+    obs = synth.simulate_alignment(parent, dist, m.parts(), n_cols, rates, seed=10)
+    tree = bnk.Tree(parent, dist)
+    ws = bnk.Workspace(m, tree, n_cols)
+    ws.set_rates(n_cols, rates)
+    assert np.array_equal(ws.joint(obs), oracle.fast_joint(om, parent, dist, obs, None, rates, nthreads=8))
+    post, logl = ws.marginal(obs)
+    wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, None, rates, nthreads=8)
+    _post_close(post, wpost[tree.internal_nodes()])
+    assert np.allclose(logl, wlogl, rtol=TOL)
+    l2, tot = ws.loglik(obs)
+    assert np.allclose(l2, wlogl, rtol=TOL) and np.isclose(tot, wlogl.sum(), rtol=TOL)
+    q = tree.internal_nodes()[::311]
+    p2, _ = ws.marginal(obs, query=q, want_logl=False)
+    assert np.allclose(p2, post[::311], rtol=1e-12, atol=0)
+    ws.close()
