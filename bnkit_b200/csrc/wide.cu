@@ -45,6 +45,21 @@ __device__ __forceinline__ double w_rcp(double s)
     return r;
 }
 
+// One candidate of the max-product scan: v = l + g; if (v > best) { best = v; bi = x; }  (strict '>',
+// so the first maximum in ascending x wins, Factorize.java:1472-1481).  The update re-issues the add
+// under the predicate instead of moving a 64-bit value with two selects: 4 issue slots per candidate
+// (DADD, DSETP, @P DADD, @P MOV) instead of 5 -- the kernel is issue-bound, the FP64 pipe has headroom.
+__device__ __forceinline__ void argmax_step(double &best, int &bi, double l, double g, int x)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .f64 v;\n\t"
+        "add.rn.f64 v, %2, %3;\n\t"
+        "setp.gt.f64 p, v, %0;\n\t"
+        "@p add.rn.f64 %0, v, 0d0000000000000000;\n\t"
+        "@p mov.s32 %1, %4;\n\t}"
+        : "+d"(best), "+r"(bi)
+        : "d"(l), "d"(g), "r"(x));
+}
+
 // message of child e of node w for this thread's column, all K states.  MODE 0: log space, 1: linear.
 template <int K, int MODE>
 __device__ __forceinline__ void child_vector(const WideArgs &a, const WideNode &w, int e, size_t tb, int col, bool valid,
@@ -116,13 +131,8 @@ __global__ void __launch_bounds__(WT, 5) up_wide_kernel(const WideArgs a)
 #pragma unroll
                 for (int x2 = 0; x2 < K / 2; x2++) {
                     const double2 l = row2[x2];
-                    const double v0 = l.x + G[2 * x2], v1 = l.y + G[2 * x2 + 1];
-                    const bool t0 = v0 > best;
-                    best = t0 ? v0 : best;
-                    bi = t0 ? 2 * x2 : bi;
-                    const bool t1 = v1 > best;
-                    best = t1 ? v1 : best;
-                    bi = t1 ? 2 * x2 + 1 : bi;
+                    argmax_step(best, bi, l.x, G[2 * x2], 2 * x2);
+                    argmax_step(best, bi, l.y, G[2 * x2 + 1], 2 * x2 + 1);
                 }
                 if (valid) {
                     mout[(size_t)p * a.ncols] = best;

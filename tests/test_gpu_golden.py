@@ -162,3 +162,64 @@ def test_full_size_properties_c3(bnk):
     post, _ = ws.marginal(np.ascontiguousarray(obs[:, perm]), query=q)
     assert np.allclose(post.sum(-1), 1.0, atol=1e-12) and (post >= 0).all()
     ws.close()
+
+
+def test_c4_full_size_properties(bnk):
+    """BASELINE configs[3]: 100,000-leaf random tree x 2,000 columns, WAG (one GPU's share and more):
+    hybrid schedule vs walker-only vs general kernels give bit-identical states and equal logL."""
+    from bnkit_b200 import synth
+    n_cols = 2000
+    parent, dist = synth.random_tree(100000, seed=5)
+    m = bnk.Model("WAG")
+    rng = np.random.default_rng(8)
+    leaf = leaves_of(parent)
+    obs = np.full((len(parent), n_cols), NONE, np.uint8)
+    base = rng.integers(0, 20, (int(leaf.sum()), 1)).astype(np.uint8)
+    noise = rng.integers(0, 20, (int(leaf.sum()), n_cols)).astype(np.uint8)
+    obs[leaf] = np.where(rng.random((int(leaf.sum()), n_cols)) < 0.2, noise, base)
+    tree = bnk.Tree(parent, dist)
+    assert tree.n == 199999 and tree.n_internal == 99999
+    ws = bnk.Workspace(m, tree, n_cols)
+    st = ws.joint(obs)
+    logl, total = ws.loglik(obs)
+    assert (st[~leaf] < 20).all() and np.array_equal(st[leaf], obs[leaf])
+    assert np.isfinite(logl).all() and np.isclose(total, logl.sum(), rtol=1e-12)
+    ws.close()
+    ws2 = bnk.Workspace(m, tree, n_cols)
+    ws2.configure(-24, 2)   # walker only
+    assert np.array_equal(ws2.joint(obs), st)
+    l2, _ = ws2.loglik(obs)
+    assert np.allclose(l2, logl, rtol=1e-11)
+    ws2.close()
+    # a column subset through the general kernels (masks all-present => same answer)
+    sub = np.ascontiguousarray(obs[:, :64])
+    ws3 = bnk.Workspace(m, tree, 64)
+    st3 = ws3.joint(sub, np.ones_like(sub))
+    assert np.array_equal(st3, st[:, :64])
+    ws3.close()
+
+
+def test_c5_likelihood_loop_matches_oracle(bnk, oracle):
+    """BASELINE configs[4]: repeated log-likelihood evaluations with perturbed per-column rates and a
+    perturbed branch length; the per-evaluation sum (the value the NCCL all-reduce carries) vs the oracle."""
+    from bnkit_b200 import synth
+    rng = np.random.default_rng(19)
+    parent, dist = synth.balanced_tree(300, seed=2)
+    m, om = bnk.Model("LG"), oracle.Model("LG")
+    n_cols = 160
+    obs = synth.simulate_alignment(parent, dist, m.parts(), n_cols, None, seed=4)
+    ws = bnk.Workspace(m, bnk.Tree(parent, dist), n_cols)
+    r4 = synth.gamma_category_rates(0.5, 4)
+    cat = rng.integers(0, 4, n_cols)
+    d = dist.copy()
+    for it in range(5):
+        rates = (r4 * (1.0 + 0.1 * it))[cat]
+        if it >= 3:
+            d = d.copy()
+            d[7] *= 1.5
+            ws.set_distances(d)
+        ws.set_rates(n_cols, rates)
+        logl, total = ws.loglik(obs)
+        _, wl = oracle.fast_marginal(om, parent, d, obs, None, rates, nthreads=8, want_post=False)
+        assert np.allclose(logl, wl, rtol=1e-9) and np.isclose(total, wl.sum(), rtol=1e-9)
+    ws.close()
