@@ -660,6 +660,8 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
     CUDA_TRY(cudaSetDevice(ws->device));
     TRY(ensure_rates(ws, n_cols));
     const int K = ws->K, nc = ws->ncols;
+    if (ws->tree->max_children > 31)
+        return fail(BNK_ERR_TREE, "max-product kernels handle at most 31 children per node (the tree has a node with %d)", ws->tree->max_children);
     bool general;
     const uint8_t *obs_s, *present_s;
     TRY(prepare_inputs(ws, d_obs, d_present, general, obs_s, present_s));

@@ -32,6 +32,7 @@ namespace bnk {
 constexpr int NSTAGE = 3;   // table ring depth
 constexpr int PCHUNK = 32;  // walk-program steps per shared-memory chunk (double buffered)
 constexpr int MAXDEG_LOCAL = 16;
+constexpr int MAXQ = 32;  // joint: at most MAXQ - 1 children per node in the general kernels
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
 {
@@ -242,38 +243,68 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
             bool first = !rootlike;
             int nk = 0;
             const bool need = pv && ov == BNK_NONE;  // only unobserved present nodes combine messages
-            // one child's contribution; the first two children use the values prefetched a step ago
-            auto take = [&](int cnode, int cslot, bool pu, uint8_t ou, bool pref, double gpref) {
-                if (!pu) return;
-                nk++;
-                if (!need) {
-                    if (MODE == 1 && GENERAL && pv && cslot < 0 && ou != BNK_NONE)  // observed v: scalar factor of an observed childless child
-                        logacc[j] += log(a.T_col[(tb[j] + cnode) * KK + ou * K + ov]);
-                    return;
-                }
-                double g;
-                if (ou != BNK_NONE) {
-                    g = pref ? gpref : a.T_col[(tb[j] + cnode) * KK + ou * K + p];
-                } else if (cslot < 0) {  // unobserved childless node: maximise / marginalise its own row
+            // value of one present child's message for entry p of this column; the first two children use
+            // the values prefetched a step ago
+            auto child_g = [&](int cnode, int cslot, uint8_t ou, bool pref, double gpref) -> double {
+                if (ou != BNK_NONE) return pref ? gpref : a.T_col[(tb[j] + cnode) * KK + ou * K + p];
+                if (cslot < 0) {  // unobserved childless node: maximise / marginalise its own row
                     const double *row = a.T_row + (tb[j] + cnode) * KK + p * K;
-                    g = row[0];
+                    double g = row[0];
                     for (int x = 1; x < K; x++) g = (MODE == 0) ? (row[x] > g ? row[x] : g) : g + row[x];
-                } else if (cslot < a.smem_slots) {
-                    g = sm.stack[((size_t)cslot * tcpad + lc[j]) * K + p];
-                } else {
-                    g = a.spill[((size_t)(cslot - a.smem_slots) * a.ncols + col[j]) * K + p];
+                    return g;
                 }
-                if (MODE == 0) G = first ? g : G + g;
-                else G = first ? g : G * g;
-                first = false;
+                if (cslot < a.smem_slots) return sm.stack[((size_t)cslot * tcpad + lc[j]) * K + p];
+                return a.spill[((size_t)(cslot - a.smem_slots) * a.ncols + col[j]) * K + p];
             };
-            if (st.n_child > 0) take(st.c_node[0], st.c_slot[0], b.pu[0] != 0, b.ou[0], true, L0[j].g[0]);
-            if (st.n_child > 1) take(st.c_node[1], st.c_slot[1], b.pu[1] != 0, b.ou[1], true, L0[j].g[1]);
-            for (int e = 2; e < st.n_child; e++) {
-                const ChildRef ch = a.up_child[st.child_begin + e];
-                const bool pu = !(GENERAL && a.present) || a.present[(size_t)ch.node * a.ncols + col[j]] != 0;
-                const uint8_t ou = (GENERAL || ch.slot < 0) ? a.obs[(size_t)ch.node * a.ncols + col[j]] : (uint8_t)BNK_NONE;
-                take(ch.node, ch.slot, pu, ou, false, 0.0);
+            auto child_info = [&](int e, int &cnode, int &cslot, bool &pu, uint8_t &ou) {
+                if (e < 2) {
+                    cnode = st.c_node[e]; cslot = st.c_slot[e];
+                    pu = (e == 0 ? b.pu[0] : b.pu[1]) != 0; ou = (e == 0) ? b.ou[0] : b.ou[1];
+                } else {
+                    const ChildRef ch = a.up_child[st.child_begin + e];
+                    cnode = ch.node; cslot = ch.slot;
+                    pu = !(GENERAL && a.present) || a.present[(size_t)cnode * a.ncols + col[j]] != 0;
+                    ou = (GENERAL || cslot < 0) ? a.obs[(size_t)cnode * a.ncols + col[j]] : (uint8_t)BNK_NONE;
+                }
+            };
+            if (MODE == 0 && st.n_child > 2 && need) {
+                // >= 3 single-variable factors: the reference multiplies them along Factorize.getProductTree
+                // (Factorize.java:331-375) = queue pairing over [base, observed children, unobserved children]
+                double q[2 * MAXQ + 1];
+                int m = 0;
+                if (rootlike) q[m++] = G;
+                for (int pass = 0; pass < 2; pass++) {
+                    for (int e = 0; e < st.n_child && e < MAXQ - 1; e++) {
+                        int cnode, cslot; bool pu; uint8_t ou;
+                        child_info(e, cnode, cslot, pu, ou);
+                        if (!pu) continue;
+                        if (pass == 0) nk++;
+                        if ((ou != BNK_NONE) != (pass == 0)) continue;
+                        q[m++] = child_g(cnode, cslot, ou, e < 2, e == 0 ? L0[j].g[0] : L0[j].g[1]);
+                    }
+                }
+                int head = 0, tail = m;
+                while (tail - head > 1) {
+                    const double x0 = q[head++], x1 = q[head++];
+                    q[tail++] = x0 + x1;
+                }
+                G = m > 0 ? q[head] : 0.0;
+            } else {
+                for (int e = 0; e < st.n_child; e++) {
+                    int cnode, cslot; bool pu; uint8_t ou;
+                    child_info(e, cnode, cslot, pu, ou);
+                    if (!pu) continue;
+                    nk++;
+                    if (!need) {
+                        if (MODE == 1 && GENERAL && pv && cslot < 0 && ou != BNK_NONE)  // observed v: scalar factor of an observed childless child
+                            logacc[j] += log(a.T_col[(tb[j] + cnode) * KK + ou * K + ov]);
+                        continue;
+                    }
+                    const double g = child_g(cnode, cslot, ou, e < 2, e == 0 ? L0[j].g[0] : L0[j].g[1]);
+                    if (MODE == 0) G = first ? g : G + g;
+                    else G = first ? g : G * g;
+                    first = false;
+                }
             }
             if (!pv) kind[j] = KIND_NONE;
             else if (ov != BNK_NONE) kind[j] = KIND_OBS;

@@ -18,9 +18,18 @@
  *   src/asr/MaxLhoodJoint.java:119-170       observed values pass through; unconnected nodes untouched
  *   test/asr/MaxLhoodJointTest.java:318-350  brute-force enumeration (first strict maximum)
  *
- * Association order of the log-space additions:
- *   non-root, parent unobserved:  L_v[p][x] + ((g1[x] + g2[x]) + g3[x] ...)   children in index order
- *   root / parent observed:       ((base[x] + g1[x]) + g2[x]) ...             base = log prior or L_v[obs_p][x]
+ * Association order of the log-space additions.  A bucket's factors are multiplied along the tree
+ * Factorize.getProductTree builds (Factorize.java:331-375): repeatedly the FIRST cheapest pair (i < j)
+ * of the pool is replaced by its product, appended at the END of the pool.  Single-variable factors
+ * (cost 20) therefore combine before the 400-entry CPT factor, and among themselves by "queue pairing":
+ *     Q = [f1, f2, ..., fm];  while |Q| > 1:  a = pop_front, b = pop_front, push_back(a + b)
+ * The bucket list holds the factors made directly from nodes first (VarElim.java:211-236: the prior or
+ * the observed-parent row of the node itself, and the evidence factors of its OBSERVED children), then
+ * the messages of its unobserved children as their buckets finish (:306-316).  Within each group the
+ * reference's order depends on identity hash codes (HashMap / HashSet iteration); the canonical order
+ * used here -- one of its possible outcomes -- is base, observed children by index, unobserved children
+ * by index.  Then:   non-root, parent unobserved:  L_v[p][x] + Q(x)      root-like:  Q(x) with base first.
+ * For nodes with at most two children every order gives the same bits (fp addition commutes).
  */
 #include "bnk_oracle.h"
 #include <math.h>
@@ -94,6 +103,37 @@ static void table_body(void *c_, int tid, long lo, long hi)
 #define PRESENT(c, v, col) ((c)->present == NULL || (c)->present[(size_t)(v) * (c)->ncols + (col)])
 #define OBS(c, v, col) ((c)->obs[(size_t)(v) * (c)->ncols + (col)])
 
+/* queue pairing of m values (m >= 1): the association Factorize.getProductTree produces for m
+ * equal-cost factors */
+static double queue_pair(double *q, int m)
+{
+    int head = 0, tail = m;
+    while (tail - head > 1) {
+        const double a = q[head++], b = q[head++];
+        q[tail++] = a + b;
+    }
+    return q[head];
+}
+
+/* the single-variable factors of node v's bucket for state x of v, canonical order; returns their count */
+static int gather_factors(const sweep_ctx *c, int v, int col, const double *M, int x, int rootlike, const double *base,
+                          double *q)
+{
+    const int K = c->K, KK = K * K;
+    int m = 0;
+    if (rootlike) q[m++] = base[x];
+    for (int pass = 0; pass < 2; pass++) {
+        for (int e = c->first[v]; e < c->first[v + 1]; e++) {
+            const int u = c->kids[e];
+            if (!PRESENT(c, u, col)) continue;
+            const uint8_t ou = OBS(c, u, col);
+            if ((ou != OM_NONE) != (pass == 0)) continue;
+            q[m++] = (ou != OM_NONE) ? c->logP[(size_t)u * KK + x * K + ou] : M[(size_t)u * K + x];
+        }
+    }
+    return m;
+}
+
 /* ---------- joint (max-product) ---------- */
 static void joint_body(void *c_, int tid, long lo, long hi)
 {
@@ -103,6 +143,9 @@ static void joint_body(void *c_, int tid, long lo, long hi)
     uint8_t *ptr = (uint8_t *)malloc((size_t)n * K);
     uint8_t *rstate = (uint8_t *)malloc(n);
     uint8_t *kind = (uint8_t *)malloc(n); /* 0 skip, 1 message node, 2 root-like, 3 observed */
+    int maxdeg = 0;
+    for (int v = 0; v < n; v++) if (c->first[v + 1] - c->first[v] > maxdeg) maxdeg = c->first[v + 1] - c->first[v];
+    double *q = (double *)malloc(sizeof(double) * (2 * (maxdeg + 1) + 1));
     (void)tid;
     for (long ci = lo; ci < hi; ci++) {
         const int col = c->cols[ci];
@@ -129,35 +172,20 @@ static void joint_body(void *c_, int tid, long lo, long hi)
                 continue;
             }
             const int rootlike = (pe < 0) || (OBS(c, pe, col) != OM_NONE);
-            if (rootlike) {
-                const double *base = (pe < 0) ? c->logprior : Lv + (size_t)OBS(c, pe, col) * K;
-                for (int x = 0; x < K; x++) G[x] = base[x];
-                for (int e = c->first[v]; e < c->first[v + 1]; e++) {
-                    int u = c->kids[e];
-                    if (!PRESENT(c, u, col)) continue;
-                    const uint8_t ou = OBS(c, u, col);
-                    const double *Lu = c->logP + (size_t)u * KK;
-                    for (int x = 0; x < K; x++)
-                        G[x] = G[x] + ((ou != OM_NONE) ? Lu[x * K + ou] : M[(size_t)u * K + x]);
+            {
+                const double *base = !rootlike ? NULL : (pe < 0) ? c->logprior : Lv + (size_t)OBS(c, pe, col) * K;
+                for (int x = 0; x < K; x++) {
+                    const int m = gather_factors(c, v, col, M, x, rootlike, base, q);
+                    G[x] = m > 0 ? queue_pair(q, m) : 0.0;
                 }
+            }
+            if (rootlike) {
                 double max = -INFINITY; int maxidx = 0;
                 for (int x = 0; x < K; x++) if (G[x] > max) { max = G[x]; maxidx = x; }
                 rstate[v] = (uint8_t)maxidx;
                 logmax += max;
                 kind[v] = 2;
             } else {
-                int firstk = 1;
-                for (int e = c->first[v]; e < c->first[v + 1]; e++) {
-                    int u = c->kids[e];
-                    if (!PRESENT(c, u, col)) continue;
-                    const uint8_t ou = OBS(c, u, col);
-                    const double *Lu = c->logP + (size_t)u * KK;
-                    for (int x = 0; x < K; x++) {
-                        double g = (ou != OM_NONE) ? Lu[x * K + ou] : M[(size_t)u * K + x];
-                        G[x] = firstk ? g : G[x] + g;
-                    }
-                    firstk = 0;
-                }
                 for (int p = 0; p < K; p++) {
                     double max = -INFINITY; int maxidx = 0;
                     for (int x = 0; x < K; x++) {
@@ -182,7 +210,7 @@ static void joint_body(void *c_, int tid, long lo, long hi)
         }
         if (c->out_logmax) c->out_logmax[col] = logmax;
     }
-    free(M); free(ptr); free(rstate); free(kind);
+    free(M); free(ptr); free(rstate); free(kind); free(q);
 }
 
 /* ---------- marginal (sum-product, log space) ---------- */

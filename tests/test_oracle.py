@@ -193,3 +193,54 @@ def test_documented_recon_output_c1(oracle):
         cols = [c for c in range(C) if present[anc, c]]
         assert cols == doc["indices"]
         assert [AA[st[anc, c]] for c in cols] == doc["values"]
+
+
+def test_generic_bucket_elimination_agrees_with_tree_sweeps(oracle):
+    """bnk_ve.c (factor tables + buckets + product trees, no tree knowledge) vs bnk_sweeps.c: identical
+    joint states -- including on multifurcations, where the association of the additions follows
+    Factorize.getProductTree -- and posteriors / log-likelihoods equal to rounding."""
+    cases = 0
+    for name, K in (("JC", 4), ("LG", 20)):
+        m = oracle.Model(name)
+        for seed in range(30 if K == 4 else 10):
+            rng = np.random.default_rng(4000 + seed)
+            parent, dist = random_tree(rng, int(rng.integers(3, 14)), max_children=int(rng.integers(2, 6)))
+            obs = random_obs(rng, parent, 3, K, gap_prob=0.2, internal_obs_prob=0.15 if seed % 2 else 0.0)
+            present = random_present(rng, parent, obs, absent_prob=0.25) if seed % 3 == 0 else None
+            rate = float(rng.choice([0.3, 1.0, 2.2]))
+            st = oracle.fast_joint(m, parent, dist, obs, present, np.full(3, rate))
+            post, logl = oracle.fast_marginal(m, parent, dist, obs, present, np.full(3, rate))
+            for c in range(3):
+                pc = None if present is None else np.ascontiguousarray(present[:, c])
+                oc = np.ascontiguousarray(obs[:, c])
+                vst, _ = oracle.ve_joint(m, parent, dist, oc, pc, rate)
+                assert np.array_equal(vst, st[:, c]), (name, seed, c)
+                # single tree: VarElim.logLikelihood; forests: all components (see bnk_ve.c)
+                assert np.isclose(oracle.ve_loglik(m, parent, dist, oc, pc, rate), logl[c], rtol=1e-12, atol=1e-12)
+                for v in range(len(parent)):
+                    vp = oracle.ve_marginal(m, parent, dist, oc, v, pc, rate)
+                    if vp is None:
+                        assert np.isnan(post[v, c]).all()
+                    else:
+                        assert np.allclose(vp, post[v, c], rtol=1e-10, atol=1e-14), (name, seed, c, v)
+                        cases += 1
+    assert cases > 300
+
+
+def test_association_order_is_pinned_bitwise(oracle):
+    """On single trees with leaf evidence only, the maximal log-probability the tree sweep reports must
+    equal the generic bucket elimination's BIT FOR BIT: that is only true if every log-space addition
+    happens in the same association (Factorize.getProductTree order) -- checked on multifurcations."""
+    m = oracle.Model("LG")
+    checked = 0
+    for seed in range(40):
+        rng = np.random.default_rng(6000 + seed)
+        parent, dist = random_tree(rng, int(rng.integers(4, 30)), max_children=int(rng.integers(3, 7)))
+        obs = random_obs(rng, parent, 2, 20)
+        st, lm = oracle.fast_joint(m, parent, dist, obs, None, None, want_logmax=True)
+        for c in range(2):
+            vst, vlm = oracle.ve_joint(m, parent, dist, np.ascontiguousarray(obs[:, c]))
+            assert np.array_equal(vst, st[:, c])
+            assert vlm == lm[c], (seed, c, vlm, lm[c])
+            checked += 1
+    assert checked == 80
