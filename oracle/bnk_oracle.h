@@ -18,7 +18,7 @@
  * build container (no JDK), so the oracle is pinned against the reference's own
  * printed known answers (tutorial_ML.html), its brute-force test method
  * (MaxLhoodJointTest / MaxLhoodMarginalTest), the IdxTreeTest prune fixture and
- * the documented Recon output in docs/json-api.md -- see tests/test_oracle_*.py.
+ * the documented Recon output in docs/json-api.md -- see tests/test_oracle.py.
  */
 #ifndef BNK_ORACLE_H
 #define BNK_ORACLE_H
