@@ -639,6 +639,7 @@ static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch)
             const int cnt = std::min(65535, ws->level_off[h + 1] - off);
             w.nodes = ws->d_wide.p + off;
             w.wide_row0 = off;
+            w.cherry = (h == 0);
             {   // several tiles per CTA amortise the table loads, as long as ~8 CTAs per SM remain
                 const int64_t ctas = (int64_t)cnt * w.n_tiles;
                 int tpc = (int)(ctas / ((int64_t)ws->sm_count * 8));

@@ -77,6 +77,7 @@ struct WideArgs {
     uint8_t *ptr;            // wide nodes: [ent][K][ncols]
     int16_t *escale;         // [wide row][ncols] rescale exponent of each (node, column)
     int32_t wide_row0;       // wide row of nodes[0]
+    int32_t cherry;          // the level is height 1: every child is childless
     double *tmsg;
     double *out_post;
     const int32_t *qrow;

@@ -167,15 +167,17 @@ __global__ void __launch_bounds__(WT, 5) up_wide_kernel(const WideArgs a)
 // ------------------------------------------------------------------------------------
 // down-sweep: T (from above, HBM) -> D = P^T T -> posterior, and the children's from-above vectors
 // ------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(WT, 4) down_wide_kernel(const WideArgs a)
+// CHERRY: every node of the level has only childless children (height 1): nothing is pushed down,
+// far fewer live registers, more resident warps.
+template <int K, bool CHERRY>
+__global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const WideArgs a)
 {
     __shared__ __align__(16) double PTs[K * K];
     __shared__ double LT0[K * (K + 1)], LT1[K * (K + 1)];
     const WideNode w = a.nodes[blockIdx.y];
     const int t_lo = blockIdx.x * a.tiles_per_cta, t_hi = min(t_lo + a.tiles_per_cta, a.n_tiles);
     const bool two = w.n_child > 1;
-    const bool leaf0 = w.c_ent[0] < 0, leaf1 = two && w.c_ent[1] < 0;
+    const bool leaf0 = CHERRY || w.c_ent[0] < 0, leaf1 = two && (CHERRY || w.c_ent[1] < 0);
     const bool push0 = !leaf0, push1 = two && !leaf1;
     const int q = a.qrow ? a.qrow[w.ent] : w.ent;
     int cur_cat = -1;
@@ -198,7 +200,9 @@ __global__ void __launch_bounds__(WT, 4) down_wide_kernel(const WideArgs a)
             const double *t = a.tmsg + (size_t)w.ent * K * a.ncols + col;
             int mhi = 0;
 #pragma unroll
-            for (int x = 0; x < K; x++) { T[x] = t[(size_t)x * a.ncols]; mhi = max(mhi, __double2hiint(T[x])); }
+            for (int x = 0; x < K; x++) { T[x] = t[(size_t)x * a.ncols]; }
+#pragma unroll
+            for (int x = 0; x < K; x++) mhi = max(mhi, __double2hiint(T[x]));
             int e;
             const double scale = w_pow2_scale(mhi, e);
 #pragma unroll
@@ -216,10 +220,10 @@ __global__ void __launch_bounds__(WT, 4) down_wide_kernel(const WideArgs a)
         double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
         double U[K], S = 0.0;
         if (!slow) {
+            // phase 1: D = P^T T for all states (registers only)
+            double D[K];
 #pragma unroll
             for (int x = 0; x < K; x++) {
-                const double c0 = leaf0 ? LT0[o0 * (K + 1) + x] : m0[(size_t)x * a.ncols];
-                const double c1 = !two ? 1.0 : (leaf1 ? LT1[o1 * (K + 1) + x] : m1[(size_t)x * a.ncols]);
                 const double2 *row2 = reinterpret_cast<const double2 *>(PTs + x * K);
                 double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
@@ -228,10 +232,22 @@ __global__ void __launch_bounds__(WT, 4) down_wide_kernel(const WideArgs a)
                     acc0 = fma(l.x, T[2 * y2], acc0);
                     acc1 = fma(l.y, T[2 * y2 + 1], acc1);
                 }
-                const double D = acc0 + acc1;
-                if (valid && push0) t0[(size_t)x * a.ncols] = D * c1;
-                if (valid && push1) t1[(size_t)x * a.ncols] = D * c0;
-                U[x] = D * (c0 * c1);
+                D[x] = acc0 + acc1;
+            }
+            // phase 2: every child value is requested before anything is stored (the stores below may
+            // alias these loads as far as the compiler knows, which would serialise them)
+            double c0[K], c1[K];
+#pragma unroll
+            for (int x = 0; x < K; x++) {
+                c0[x] = leaf0 ? LT0[o0 * (K + 1) + x] : __ldg(m0 + (size_t)x * a.ncols);
+                c1[x] = !two ? 1.0 : (leaf1 ? LT1[o1 * (K + 1) + x] : __ldg(m1 + (size_t)x * a.ncols));
+            }
+            // phase 3: from-above vectors of internal children, unnormalised posterior
+#pragma unroll
+            for (int x = 0; x < K; x++) {
+                if (valid && push0) t0[(size_t)x * a.ncols] = D[x] * c1[x];
+                if (valid && push1) t1[(size_t)x * a.ncols] = D[x] * c0[x];
+                U[x] = D[x] * (c0[x] * c1[x]);
                 S += U[x];
             }
         } else {
@@ -253,11 +269,12 @@ __global__ void __launch_bounds__(WT, 4) down_wide_kernel(const WideArgs a)
             }
         }
         if (valid && q >= 0 && a.out_post) {
+            // each thread writes its column's 160 contiguous bytes (staging the tile through shared
+            // memory for wider stores was measured: no gain, two extra barriers)
             const double r = w_rcp(S);
-            double *o = a.out_post + ((size_t)q * a.ncols + a.orig_col[col]) * K;
+            double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)q * a.ncols + a.orig_col[col]) * K);
 #pragma unroll
-            for (int x2 = 0; x2 < K / 2; x2++)
-                reinterpret_cast<double2 *>(o)[x2] = make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r);
+            for (int x2 = 0; x2 < K / 2; x2++) __stcs(o + x2, make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r));
         }
     }
 }
@@ -311,8 +328,9 @@ cudaError_t launch_down_wide(int K, const WideArgs &a, int n_tiles, int n_nodes,
 {
     if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
     dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, n_nodes);
-    if (K == 20) down_wide_kernel<20><<<grid, WT, 0, st>>>(a);
-    else down_wide_kernel<4><<<grid, WT, 0, st>>>(a);
+    if (K == 20 && a.cherry) down_wide_kernel<20, true><<<grid, WT, 0, st>>>(a);
+    else if (K == 20) down_wide_kernel<20, false><<<grid, WT, 0, st>>>(a);
+    else down_wide_kernel<4, false><<<grid, WT, 0, st>>>(a);
     return cudaGetLastError();
 }
 
