@@ -34,6 +34,9 @@ WORKLOADS = {
     "c3a": dict(tree="balanced", leaves=10000, cols=5000, model="LG", ncat=4, name="C3a balanced 10k-leaf x 5k-col LG+G4"),
     "c3b": dict(tree="caterpillar", leaves=10000, cols=5000, model="LG", ncat=4, name="C3b caterpillar 10k-leaf x 5k-col LG+G4"),
     "small": dict(tree="balanced", leaves=512, cols=1024, model="LG", ncat=4, name="small 512-leaf x 1024-col LG+G4"),
+    # BASELINE configs[4]: repeated log-likelihood evaluations (rates perturbed every iteration => tables rebuilt)
+    # with an all-reduce of the per-GPU sum of column log-likelihoods
+    "c5": dict(tree="balanced", leaves=10000, cols=5000, model="LG", ncat=4, name="C5 logL loop on C3a, rates perturbed per evaluation, all-reduce of sum(logL)", loop=True),
 }
 
 
@@ -185,10 +188,21 @@ def main():
 
     d_obs = torch.from_numpy(obs).to(dev)
     d_state = torch.empty((n, n_cols), dtype=torch.uint8, device=dev)
-    d_post = torch.empty((n_int, n_cols, K), dtype=torch.float64, device=dev)
+    d_post = torch.empty((1 if spec.get("loop") else n_int, n_cols, K), dtype=torch.float64, device=dev)
     d_logl = torch.empty((n_cols,), dtype=torch.float64, device=dev)
 
+    loop_mode = bool(spec.get("loop"))
+    d_sum = torch.zeros((1,), dtype=torch.float64, device=dev)
+    it_count = [0]
+
     def step_resident():
+        if loop_mode:  # one log-likelihood evaluation of an optimisation loop
+            it_count[0] += 1
+            ws.set_rates(n_cols, rates * (1.0 + 0.01 * (it_count[0] % 7)))
+            ws.loglik_dev(n_cols, d_obs, None, d_logl, d_sum)
+            if world > 1:
+                dist_.all_reduce(d_sum, op=dist_.ReduceOp.SUM)  # the only data-path collective: one double
+            return
         ws.set_rates(n_cols, rates)  # marks the tables dirty: every step rebuilds P(t) / log P(t)
         ws.joint_dev(n_cols, d_obs, None, d_state)
         ws.marginal_dev(n_cols, d_obs, None, d_post, d_logl)
@@ -221,6 +235,9 @@ def main():
 
     # ---- end to end through the host-buffer ABI (pinned host memory, copies inside the timed region)
     e2e = None
+    if loop_mode:
+        args.no_e2e = True
+        args.no_cpu = True
     if not args.no_e2e:
         h_obs = torch.from_numpy(obs).pin_memory()
         h_state = torch.empty((n, n_cols), dtype=torch.uint8).pin_memory()
@@ -254,7 +271,7 @@ def main():
             dist_.destroy_process_group()
         return
 
-    updates_step = 3.0 * n_int * n_cols * world
+    updates_step = (1.0 if loop_mode else 3.0) * n_int * n_cols * world
     ms_per_step = tmax / args.steps
     value = updates_step / (ms_per_step * 1e-3)
     peaks = {}

@@ -90,7 +90,8 @@ struct bnk_ws {
     // rates / categories / tiles
     int ncols = -1;  // columns of the current rate assignment
     bool identity_perm = true;
-    std::vector<double> cat_rate;
+    std::vector<double> cat_rate, last_rates;
+    bool rates_null = true;
     std::vector<int32_t> orig_col, col_cat_global, cat_of_col;
     std::vector<TileDesc> tiles, wtiles;   // walker tiles; wide tiles (one category, <= 128 columns)
     std::vector<Chunk> chunks;
@@ -332,6 +333,14 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             if (!(rates[c] >= 0.0) || std::isinf(rates[c])) return fail(BNK_ERR_ARG, "set_rates: rate[%d] is negative or not finite", c);
     CUDA_TRY(cudaSetDevice(ws->device));
     const int K = ws->K;
+    // same assignment as last time (an optimisation loop re-evaluating, a second pass over the same
+    // alignment): keep categories, tiles and their device copies; only the tables are marked stale
+    if (ws->ncols == n_cols && ws->rates_null == (rates == nullptr) &&
+        (rates == nullptr || (ws->last_rates.size() == (size_t)n_cols &&
+                              std::memcmp(ws->last_rates.data(), rates, sizeof(double) * n_cols) == 0))) {
+        ws->tables_log_valid = ws->tables_lin_valid = false;
+        return BNK_OK;
+    }
     // distinct rates, ascending; columns sorted by (rate, index)
     ws->orig_col.resize(n_cols);
     for (int32_t c = 0; c < n_cols; c++) ws->orig_col[c] = c;
@@ -433,6 +442,8 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_wtiles, ws->wtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
+    ws->rates_null = rates == nullptr;
+    if (rates) ws->last_rates.assign(rates, rates + n_cols); else ws->last_rates.clear();
     ws->tables_log_valid = ws->tables_lin_valid = false;
     return BNK_OK;
 }
@@ -506,19 +517,8 @@ static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_pre
         CUDA_TRY(cudaStreamSynchronize(ws->stream));
         general = flag != 0;
     }
+    // inputs are consumed in the caller's column order (the kernels index them through orig_col)
     obs_s = d_obs; present_s = d_present;
-    if (!ws->identity_perm) {
-        CUDA_TRY(ws->d_obs_s.ensure((size_t)n * nc));
-        CUDA_TRY(launch_gather_cols(d_obs, ws->d_obs_s.p, ws->d_orig_col.p, n, nc, ws->stream));
-        ws->launches++;
-        obs_s = ws->d_obs_s.p;
-        if (d_present) {
-            CUDA_TRY(ws->d_present_s.ensure((size_t)n * nc));
-            CUDA_TRY(launch_gather_cols(d_present, ws->d_present_s.p, ws->d_orig_col.p, n, nc, ws->stream));
-            ws->launches++;
-            present_s = ws->d_present_s.p;
-        }
-    }
     return BNK_OK;
 }
 
@@ -699,7 +699,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             std::memset(&ta, 0, sizeof(ta));
             ta.down = s.a.down; ta.n_steps = s.a.n_steps; ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
             ta.ptr = ws->d_ptr.p; ta.kind = s.fast ? nullptr : ws->d_kind.p;
-            ta.obs_s = obs_s; ta.state_s = state_s; ta.tb_slots = s.tb_slots;
+            ta.obs = d_obs; ta.orig_col = ws->d_orig_col.p; ta.state_s = state_s; ta.tb_slots = s.tb_slots;
             ta.col_lo = w.col_lo; ta.col_hi = w.col_hi;
             CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
             CUDA_TRY(launch_traceback(ta, ws->stream));

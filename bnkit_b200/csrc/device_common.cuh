@@ -37,7 +37,7 @@ struct WalkArgs {
     const TileDesc *tiles;
     int32_t ncg;       // column groups per CTA (threads = ncg * K, rounded up to a warp)
     int32_t ncat_max;  // largest TileDesc::ncat
-    // inputs, category-sorted column space, [node][ncols]
+    // inputs in the CALLER's (original) column order, [node][ncols]; kernels read them through orig_col
     const uint8_t *obs, *present;  // present == nullptr: everything present
     int32_t ncols, n_nodes;
     const int32_t *orig_col;  // sorted -> original column index
@@ -119,7 +119,7 @@ struct TracebackArgs {
     int32_t n_steps, ncols, n_nodes, K;
     // walk traceback: everything in SORTED column space
     const uint8_t *ptr, *kind;      // kind == nullptr: root steps are KIND_ROOT, all others KIND_MSG
-    const uint8_t *obs_s;           // sorted-space observations (KIND_OBS pass-through)
+    const int32_t *orig_col;        // sorted -> original column (KIND_OBS pass-through reads obs)
     uint8_t *state_s;               // [node][ncols] sorted space
     int32_t col_lo, col_hi;         // sorted columns of the chunk being processed
     int32_t tb_slots;

@@ -123,7 +123,7 @@ struct Looks {
 };
 
 template <bool GENERAL>
-__device__ __forceinline__ Bytes load_bytes(const WalkArgs &a, const Step &s, int col, bool down)
+__device__ __forceinline__ Bytes load_bytes(const WalkArgs &a, const Step &s, int col /* ORIGINAL column */, bool down)
 {
     Bytes b;
     b.ov = BNK_NONE; b.op = BNK_NONE; b.pv = 1; b.pp = s.parent >= 0;
@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
     Looks L0[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; j++) {
-        if (act[j] && n_steps > 0) B0[j] = load_bytes<GENERAL>(a, step_ref(0), col[j], false);
-        if (act[j] && n_steps > 1) B1[j] = load_bytes<GENERAL>(a, step_ref(1), col[j], false);
+        if (act[j] && n_steps > 0) B0[j] = load_bytes<GENERAL>(a, step_ref(0), ocol[j], false);
+        if (act[j] && n_steps > 1) B1[j] = load_bytes<GENERAL>(a, step_ref(1), ocol[j], false);
         if (act[j] && n_steps > 0) L0[j] = load_looks(step_ref(0), B0[j], j);
     }
 
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             if (!act[j]) continue;
-            if (i + 2 < n_steps) B2[j] = load_bytes<GENERAL>(a, step_ref(i + 2), col[j], false);
+            if (i + 2 < n_steps) B2[j] = load_bytes<GENERAL>(a, step_ref(i + 2), ocol[j], false);
             if (i + 1 < n_steps) L1[j] = load_looks(step_ref(i + 1), B1[j], j);
         }
         // ---------------- fold the children ----------------
@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
                 } else {
                     const ChildRef ch = a.up_child[st.child_begin + e];
                     cnode = ch.node; cslot = ch.slot;
-                    pu = !(GENERAL && a.present) || a.present[(size_t)cnode * a.ncols + col[j]] != 0;
-                    ou = (GENERAL || cslot < 0) ? a.obs[(size_t)cnode * a.ncols + col[j]] : (uint8_t)BNK_NONE;
+                    pu = !(GENERAL && a.present) || a.present[(size_t)cnode * a.ncols + ocol[j]] != 0;
+                    ou = (GENERAL || cslot < 0) ? a.obs[(size_t)cnode * a.ncols + ocol[j]] : (uint8_t)BNK_NONE;
                 }
             };
             if (MODE == 0 && st.n_child > 2 && need) {
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
     auto step_ref = [&](int i) -> const Step & { return sm.prog[((i / PCHUNK) & 1) * PCHUNK + (i % PCHUNK)]; };
     auto load_dbytes = [&](const Step &s, int j) -> DownBytes {
         DownBytes d;
-        d.b = load_bytes<GENERAL>(a, s, col[j], true);
+        d.b = load_bytes<GENERAL>(a, s, ocol[j], true);
         d.kind = GENERAL ? a.kindm[(size_t)s.ent * a.ncols + col[j]] : (s.parent < 0 ? KIND_ROOT : KIND_MSG);
         return d;
     };
@@ -545,10 +545,10 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
                     const ChildRef ch = a.down_child[st.child_begin + e];
                     gv[e] = 1.0; push[e] = 0;
                     const bool pu = (e == 0) ? (b.pu[0] != 0) : (e == 1) ? (b.pu[1] != 0)
-                                  : (!(GENERAL && a.present) || a.present[(size_t)ch.node * a.ncols + col[j]] != 0);
+                                  : (!(GENERAL && a.present) || a.present[(size_t)ch.node * a.ncols + ocol[j]] != 0);
                     if (!pu) continue;
                     const uint8_t ou = (e == 0) ? b.ou[0] : (e == 1) ? b.ou[1]
-                                     : ((GENERAL || ch.ent < 0) ? a.obs[(size_t)ch.node * a.ncols + col[j]] : (uint8_t)BNK_NONE);
+                                     : ((GENERAL || ch.ent < 0) ? a.obs[(size_t)ch.node * a.ncols + ocol[j]] : (uint8_t)BNK_NONE);
                     if (e == 0) {
                         gv[e] = child_value(a, st, b, L0[j], 0, tb[j], col[j], p, K);
                     } else if (e == 1) {

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
         ocol[j] = a.orig_col[col];
         sidx[j] = (lc * K + p) * 8;
         gsw[j] = lc * LROW * 8;
-        obs_c[j] = a.obs + col;
+        obs_c[j] = a.obs + ocol[j];  // inputs stay in the caller's column order
         scol[j] = col;
         ptr_o[j] = (MODE == 0) ? a.ptr + (size_t)col * K + p : nullptr;
         msg_o[j] = (MODE == 1 && a.msg) ? a.msg + (size_t)col * K + p : nullptr;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
         sidx[j] = (lc * K + p) * 8;
         srd[j] = lc * K * 8;
         gsw[j] = lc * LROW * 8;
-        obs_c[j] = a.obs + col;
+        obs_c[j] = a.obs + a.orig_col[col];  // inputs stay in the caller's column order
         msg_i[j] = a.msg + (size_t)col * K + p;
         wmsg_p[j] = a.msg + (size_t)p * ncols + col;                      // wide layout [ent][K][ncols]
         tmsg_p[j] = a.tmsg ? a.tmsg + (size_t)p * ncols + col : nullptr;  // likewise

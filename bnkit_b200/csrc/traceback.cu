@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
                 src = st[pslot];
             }
             int s = __shfl_sync(FULL, byte[u], src & 31);
-            if (kind == KIND_OBS) s = a.obs_s[(size_t)(unsigned)node * ncols_u + col];
+            if (kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + a.orig_col[col]];
             else if (kind != KIND_MSG && kind != KIND_ROOT) s = BNK_NONE;
             if (REGSTACK) {
                 if (lane == oslot) stack_reg = s;
@@ -100,39 +100,40 @@ cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t st)
 // (first strict maximum), or the root-like rule when the parent is observed.
 __global__ void leaf_states_kernel(const TracebackArgs a)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)a.n_leaves * a.ncols) return;
-    const int li = (int)(idx / a.ncols), col = (int)(idx % a.ncols);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.ncols) return;
     const int gcat = a.cat_of_col[col];
     if (gcat < a.cat_lo || gcat >= a.cat_hi) return;
-    const int u = a.leaf_nodes[li], par = a.leaf_parent[li];
-    const size_t uc = (size_t)u * a.ncols + col;
-    uint8_t s = BNK_NONE;
-    if (a.present == nullptr || a.present[uc]) {
-        s = a.obs[uc];
-        if (s == BNK_NONE && par >= 0 && (a.present == nullptr || a.present[(size_t)par * a.ncols + col])) {
-            // parent's state: observed, or already written by the traceback kernel
-            const uint8_t ps = a.out_state[(size_t)par * a.ncols + col];
-            if (ps != BNK_NONE) {
-                const int K = a.K;
-                const int cat = gcat - a.cat_lo;
-                const double *row = a.L + (((size_t)cat * a.n_nodes + u) * K + ps) * K;
-                double best = -CUDART_INF;
-                int bi = 0;
-                for (int x = 0; x < K; x++)
-                    if (row[x] > best) { best = row[x]; bi = x; }
-                s = (uint8_t)bi;
+    for (int li = blockIdx.y; li < a.n_leaves; li += gridDim.y) {
+        const int u = a.leaf_nodes[li], par = a.leaf_parent[li];
+        const size_t uc = (size_t)u * a.ncols + col;
+        uint8_t s = BNK_NONE;
+        if (a.present == nullptr || a.present[uc]) {
+            s = a.obs[uc];
+            if (s == BNK_NONE && par >= 0 && (a.present == nullptr || a.present[(size_t)par * a.ncols + col])) {
+                // parent's state: observed, or already written by the traceback kernels
+                const uint8_t ps = a.out_state[(size_t)par * a.ncols + col];
+                if (ps != BNK_NONE) {
+                    const int K = a.K;
+                    const int cat = gcat - a.cat_lo;
+                    const double *row = a.L + (((size_t)cat * a.n_nodes + u) * K + ps) * K;
+                    double best = -CUDART_INF;
+                    int bi = 0;
+                    for (int x = 0; x < K; x++)
+                        if (row[x] > best) { best = row[x]; bi = x; }
+                    s = (uint8_t)bi;
+                }
             }
         }
+        a.out_state[uc] = s;
     }
-    a.out_state[uc] = s;
 }
 
 cudaError_t launch_leaf_states(const TracebackArgs &a, cudaStream_t st)
 {
-    const size_t total = (size_t)a.n_leaves * a.ncols;
-    if (total == 0) return cudaSuccess;
-    leaf_states_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    if (a.n_leaves == 0 || a.ncols == 0) return cudaSuccess;
+    dim3 grid((a.ncols + 255) / 256, a.n_leaves < 8192 ? a.n_leaves : 8192);
+    leaf_states_kernel<<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -158,12 +159,11 @@ cudaError_t launch_gather_cols(const uint8_t *in, uint8_t *out, const int32_t *o
 __global__ void scan_internal_obs_kernel(const uint8_t *__restrict__ obs, const int32_t *__restrict__ node_of_ent,
                                          int n_int, int ncols, int32_t *flag)
 {
-    const size_t total = (size_t)n_int * ncols;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     int found = 0;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int e = (int)(idx / ncols), c = (int)(idx % ncols);
-        if (obs[(size_t)node_of_ent[e] * ncols + c] != BNK_NONE) found = 1;
-    }
+    if (c < ncols)
+        for (int e = blockIdx.y; e < n_int; e += gridDim.y)
+            if (obs[(size_t)node_of_ent[e] * ncols + c] != BNK_NONE) found = 1;
     if (__syncthreads_or(found) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 
@@ -171,7 +171,8 @@ cudaError_t launch_scan_internal_obs(const uint8_t *obs, const int32_t *node_of_
                                      int32_t *flag, cudaStream_t st)
 {
     if (n_int == 0 || ncols == 0) return cudaSuccess;
-    scan_internal_obs_kernel<<<148 * 4, 256, 0, st>>>(obs, node_of_ent, n_int, ncols, flag);
+    dim3 grid((ncols + 255) / 256, n_int < 2048 ? n_int : 2048);
+    scan_internal_obs_kernel<<<grid, 256, 0, st>>>(obs, node_of_ent, n_int, ncols, flag);
     return cudaGetLastError();
 }
 

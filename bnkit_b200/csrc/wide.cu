@@ -71,7 +71,7 @@ __device__ __forceinline__ void child_vector(const WideArgs &a, const WideNode &
 #pragma unroll
         for (int x = 0; x < K; x++) g[x] = m[(size_t)x * a.ncols];
     } else {
-        const int ou = a.obs[(size_t)cn * a.ncols + col];
+        const int ou = a.obs[(size_t)cn * a.ncols + a.orig_col[col]];  // inputs stay in the caller's column order
         if (ou != BNK_NONE) {
 #pragma unroll
             for (int x = 0; x < K; x++) g[x] = lt_smem[ou * (K + 1) + x];
@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
         // children: an observed leaf is a row of its P^T table (shared memory), an internal child
         // its up-message in HBM; uninstantiated leaves (rare) go through child_vector
         int o0 = BNK_NONE, o1 = BNK_NONE;
-        if (leaf0) o0 = a.obs[(size_t)w.c_node[0] * a.ncols + col];
-        if (leaf1) o1 = a.obs[(size_t)w.c_node[1] * a.ncols + col];
+        const int ocol = a.orig_col[col];  // inputs stay in the caller's column order
+        if (leaf0) o0 = a.obs[(size_t)w.c_node[0] * a.ncols + ocol];
+        if (leaf1) o1 = a.obs[(size_t)w.c_node[1] * a.ncols + ocol];
         const bool slow = (leaf0 && o0 == BNK_NONE) || (leaf1 && o1 == BNK_NONE);
         const double *m0 = leaf0 ? nullptr : a.msg + (size_t)w.c_ent[0] * K * a.ncols + col;
         const double *m1 = (two && !leaf1) ? a.msg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
             // each thread writes its column's 160 contiguous bytes (staging the tile through shared
             // memory for wider stores was measured: no gain, two extra barriers)
             const double r = w_rcp(S);
-            double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)q * a.ncols + a.orig_col[col]) * K);
+            double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)q * a.ncols + ocol) * K);
 #pragma unroll
             for (int x2 = 0; x2 < K / 2; x2++) __stcs(o + x2, make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r));
         }
