@@ -291,6 +291,13 @@ def main():
                       "achieved_GBps": round(v[1] / 1e9 / (v[0] * 1e-3), 1) if v[0] > 0 else None,
                       "frac": round(v[1] / 1e9 / (v[0] * 1e-3) / peak, 4) if v[0] > 0 else None} for k, v in kern.items()}
     achieved = kern[dom][1] / 1e9 / (kern[dom][0] * 1e-3)
+    traffic = None  # DRAM bytes of the dominant sweep per step, from the committed ncu capture of this workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if tr.get("workload") == args.workload and n_cols == spec["cols"]:
+            traffic = tr["bytes_per_step"].get(dom)
+    except Exception:
+        pass
     line = {"metric": "column x node partial updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -299,7 +306,8 @@ def main():
                          "traceback": round(float(phase_ms[2]), 4), "sum_up": round(float(phase_ms[3]), 4),
                          "sum_down": round(float(phase_ms[4]), 4)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "traffic_note": "DRAM bytes per step of the dominant sweep (all its launches), profiles/roofline_traffic.json",
                          "algorithmic_bytes": "SURVEY.md 8(d) per-update figures x %d updates + table bytes" % int(upd),
                          "per_kernel": per_kernel},
             "clocks": clocks}

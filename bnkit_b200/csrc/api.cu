@@ -539,6 +539,13 @@ static int build_tables(bnk_ws *ws, const Chunk &ck, bool log_space)
         CUDA_TRY(ws->d_PT.ensure(elems));
         ts.P = ws->d_P.p; ts.PT = ws->d_PT.p;
     }
+    // a workspace that has already served the other kind of pass gets both table sets from one launch
+    // (the P(t) entries are computed either way; a joint + marginal step then builds tables once)
+    bool &other_valid = log_space ? ws->tables_lin_valid : ws->tables_log_valid;
+    if (single && !other_valid) {
+        if (log_space && ws->d_P.cap >= elems && ws->d_PT.cap >= elems) { ts.P = ws->d_P.p; ts.PT = ws->d_PT.p; other_valid = true; }
+        if (!log_space && ws->d_L.cap >= elems && ws->d_LT.cap >= elems) { ts.L = ws->d_L.p; ts.LT = ws->d_LT.p; other_valid = true; }
+    }
     CUDA_TRY(cudaEventRecord(ws->ev[0][0], ws->stream));
     launch_build_tables(K, ws->md(), ws->d_dist.p, ws->d_parent.p, ws->d_cat_rate.p + ck.cat_lo, ws->n, ncat, ts, ws->stream);
     ws->launches++;

@@ -1,15 +1,15 @@
 #!/usr/bin/env python3
 """Summarise gpurun_out ncu artefacts into profiles/ (tracked).
 
-    python tools/summarize_profiles.py <tag> <launches.csv> <report.ncu-rep> [bench.json]
+    python tools/summarize_profiles.py <tag> <launches.csv> <bench.json> <report.ncu-rep> [more reports ...]
 """
 import csv, json, shutil, subprocess, sys
 from collections import defaultdict
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-tag, launches, rep = sys.argv[1], Path(sys.argv[2]), Path(sys.argv[3])
-bench = Path(sys.argv[4]) if len(sys.argv) > 4 else None
+tag, launches, bench = sys.argv[1], Path(sys.argv[2]), Path(sys.argv[3])
+reps = [Path(x) for x in sys.argv[4:]]
 out = ROOT / "profiles"
 out.mkdir(exist_ok=True)
 
@@ -36,8 +36,20 @@ lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append("| `%s` | %d | %.3f | %.3f | %.3f |" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
 
-raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+rr = None
+for rep in reps:
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if len(part) < 3:
+        continue
+    if rr is None:
+        rr = part
+    else:
+        pix = {x: i for i, x in enumerate(part[0])}
+        for r in part[2:]:
+            rr.append([r[pix[x]] if x in pix else "" for x in rr[0]])
+if rr is None:
+    rr = [[], []]
 h = rr[0]; ix = {x: i for i, x in enumerate(h)}
 want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
@@ -50,7 +62,7 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
 stalls = [x for x in h if "issue_stalled" in x and x.endswith("_per_issue_active.ratio")]
 lines += ["", "## `ncu --set full --clock-control none --import-source on` (one launch each)", ""]
 for r in rr[2:]:
-    lines.append("### `%s`" % r[ix["Kernel Name"]])
+    lines.append("### `%s`  grid %s" % (r[ix["Kernel Name"]], r[ix["launch__grid_size"]] if "launch__grid_size" in ix else "?"))
     lines.append("")
     for key, name in want:
         if key in ix:
