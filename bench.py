@@ -34,6 +34,8 @@ WORKLOADS = {
     "c3a": dict(tree="balanced", leaves=10000, cols=5000, model="LG", ncat=4, name="C3a balanced 10k-leaf x 5k-col LG+G4"),
     "c3b": dict(tree="caterpillar", leaves=10000, cols=5000, model="LG", ncat=4, name="C3b caterpillar 10k-leaf x 5k-col LG+G4"),
     "small": dict(tree="balanced", leaves=512, cols=1024, model="LG", ncat=4, name="small 512-leaf x 1024-col LG+G4"),
+    # BASELINE configs[3]: 100k-leaf random tree x 2k columns, WAG, one rate (use --no-e2e: 32 GB of posteriors)
+    "c4": dict(tree="random", leaves=100000, cols=2000, model="WAG", ncat=1, name="C4 random 100k-leaf x 2k-col WAG"),
     # BASELINE configs[4]: repeated log-likelihood evaluations (rates perturbed every iteration => tables rebuilt)
     # with an all-reduce of the per-GPU sum of column log-likelihoods
     "c5": dict(tree="balanced", leaves=10000, cols=5000, model="LG", ncat=4, name="C5 logL loop on C3a, rates perturbed per evaluation, all-reduce of sum(logL)", loop=True),
@@ -51,10 +53,19 @@ def make_workload(spec, rank, cols=None):
     else:
         parent, dist = synth.random_tree(leaves, seed=5)
     model = lib.Model(spec["model"])
-    cat_rates = synth.gamma_category_rates(0.5, spec["ncat"])
+    cat_rates = synth.gamma_category_rates(0.5, spec["ncat"]) if spec["ncat"] > 1 else np.ones(1)
     rng = np.random.default_rng(4 + 1000 * rank)
     rates = cat_rates[rng.integers(0, spec["ncat"], n_cols)]
-    obs = synth.simulate_alignment(parent, dist, model.parts(), n_cols, rates, seed=3 + 1000 * rank)
+    if leaves <= 20000:
+        obs = synth.simulate_alignment(parent, dist, model.parts(), n_cols, rates, seed=3 + 1000 * rank)
+    else:  # very large trees: a conserved base state per leaf with 20 % noise (numpy simulation would take minutes)
+        leaf = np.ones(len(parent), dtype=bool)
+        leaf[parent[parent >= 0]] = False
+        nl = int(leaf.sum())
+        base = rng.integers(0, model.K, (nl, 1)).astype(np.uint8)
+        noise = rng.integers(0, model.K, (nl, n_cols)).astype(np.uint8)
+        obs = np.full((len(parent), n_cols), 255, dtype=np.uint8)
+        obs[leaf] = np.where(rng.random((nl, n_cols)) < 0.2, noise, base)
     return model, parent, dist, rates, obs
 
 
@@ -126,6 +137,7 @@ def main():
     ap.add_argument("--cols", type=int, default=0, help="columns per GPU (default: the workload's)")
     ap.add_argument("--tile-cols", type=int, default=0)
     ap.add_argument("--cpt", type=int, default=0)
+    ap.add_argument("--gaps", type=float, default=0.0, help="gap fraction at the leaves; > 0 adds a per-column presence mask (general kernels)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
@@ -186,6 +198,19 @@ def main():
     if args.tile_cols or args.cpt:
         ws.configure(args.tile_cols, args.cpt)
 
+    d_present = None
+    if args.gaps > 0:  # per-column forests: gaps at the leaves, ancestors present on paths between present leaves
+        from bnkit_b200 import synth
+        g_rng = np.random.default_rng(77 + rank)
+        leaf = np.ones(n, dtype=bool)
+        leaf[parent[parent >= 0]] = False
+        obs = obs.copy()
+        obs[(g_rng.random(obs.shape) < args.gaps) & leaf[:, None]] = 255
+        present = synth.path_presence_mask(parent, (obs != 255) & leaf[:, None])
+        d_present = torch.from_numpy(present).to(dev)
+        config["gaps"] = args.gaps
+        args.no_e2e = True
+        args.no_cpu = True
     d_obs = torch.from_numpy(obs).to(dev)
     d_state = torch.empty((n, n_cols), dtype=torch.uint8, device=dev)
     d_post = torch.empty((1 if spec.get("loop") else n_int, n_cols, K), dtype=torch.float64, device=dev)
@@ -204,8 +229,8 @@ def main():
                 dist_.all_reduce(d_sum, op=dist_.ReduceOp.SUM)  # the only data-path collective: one double
             return
         ws.set_rates(n_cols, rates)  # marks the tables dirty: every step rebuilds P(t) / log P(t)
-        ws.joint_dev(n_cols, d_obs, None, d_state)
-        ws.marginal_dev(n_cols, d_obs, None, d_post, d_logl)
+        ws.joint_dev(n_cols, d_obs, d_present, d_state)
+        ws.marginal_dev(n_cols, d_obs, d_present, d_post, d_logl)
 
     def barrier():
         if world > 1:

@@ -14,6 +14,7 @@ UNITS = [
     ("sweeps.cu", []),
     ("sweeps_fast.cu", []),
     ("wide.cu", []),
+    ("wide_general.cu", []),
     ("traceback.cu", []),
     ("api.cu", []),
     ("subst_model.cpp", ["-fmad=false"]),

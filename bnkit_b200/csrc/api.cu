@@ -104,7 +104,7 @@ struct bnk_ws {
     DevBuf<int32_t> d_esum_wide;
     bool tables_log_valid = false, tables_lin_valid = false;  // only meaningful with a single chunk
     // buffers
-    DevBuf<double> d_P, d_PT, d_L, d_LT, d_spill, d_msg, d_tmsg, d_logl, d_post, d_sum;
+    DevBuf<double> d_P, d_PT, d_L, d_LT, d_spill, d_msg, d_tmsg, d_logl, d_logl_wide, d_post, d_sum;
     DevBuf<uint8_t> d_obs_in, d_present_in, d_obs_s, d_present_s, d_ptr, d_kind, d_kindm, d_state, d_state_s;
     cudaEvent_t ev[5][2] = {};
     bool ev_valid[5] = {false, false, false, false, false};
@@ -183,7 +183,7 @@ static void ws_free(bnk_ws *ws)
     cudaSetDevice(ws->device);
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
-                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_post, &ws->d_sum};
+                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_logl_wide, &ws->d_post, &ws->d_sum};
     for (auto *b : dd) b->release();
     DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
                              &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state, &ws->d_state_s};
@@ -230,7 +230,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     if (const char *env = std::getenv("BNK_WIDE_TPC")) ws->wide_tpc_max = std::max(1, std::atoi(env));  // tuning knob
     // accounting hooks
     DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
-                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_post, &ws->d_sum};
+                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_logl_wide, &ws->d_post, &ws->d_sum};
     for (auto *b : dd) b->acct = &ws->dev_bytes;
     DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
                              &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state, &ws->d_state_s};
@@ -604,7 +604,10 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
             return BNK_OK;
         }
     }
-    const int slots_needed = use_program(false);
+    // general kernels (masks, evidence anywhere, any arity); the wide levels still run as level
+    // launches when the tree is at most binary (wide_general.cu)
+    s.hybrid = t->wide_h > 0 && !ws->no_wide;
+    const int slots_needed = use_program(s.hybrid);
     // stack slots: as many as fit in shared memory, the rest spill to global memory
     const size_t base = walk_smem_bytes(K, ws->cpt, ws->ncg, ck.ncat_max, 0);
     const size_t per_slot = sizeof(double) * (size_t)ws->ncg * ws->cpt * K;
@@ -690,12 +693,15 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             s.a.ptr = ws->d_ptr.p; s.a.kind = ws->d_kind.p;
             WideArgs w = wide_args(ws, ci, obs_s);
             w.T_row = ws->d_L.p; w.T_col = ws->d_LT.p; w.ptr = ws->d_ptr.p; w.state_s = state_s;
+            w.present = present_s; w.prior = ws->md().logprior; w.kind = ws->d_kind.p;
             const int n_wt = ws->chunk_wtiles[ci].second - ws->chunk_wtiles[ci].first;
+            const bool gen = !s.fast;
             CUDA_TRY(cudaEventRecord(ws->ev[1][0], ws->stream));
             if (s.hybrid) {
                 CUDA_TRY(ws->d_msg.ensure((size_t)ws->n_int * nc * K));
                 w.msg = ws->d_msg.p; s.a.msg = ws->d_msg.p;
-                TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) { return launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
+                TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
+                    return gen ? launch_up_wide_gen(K, 0, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
             }
             CUDA_TRY(s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;
@@ -712,7 +718,8 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             CUDA_TRY(launch_traceback(ta, ws->stream));
             ws->launches++;
             if (s.hybrid)
-                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) { return launch_traceback_wide(K, wa, cnt, ws->stream); }));
+                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
+                    return gen ? launch_traceback_wide_gen(K, wa, cnt, ws->stream) : launch_traceback_wide(K, wa, cnt, ws->stream); }));
         } else {
             CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
         }
@@ -817,17 +824,30 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
         s.a.out_logl = logl;
         WideArgs w = wide_args(ws, ci, obs_s);
         w.T_row = ws->d_P.p; w.T_col = ws->d_PT.p;
+        w.present = present_s; w.prior = ws->md().prior;
         const int n_wt = ws->chunk_wtiles[ci].second - ws->chunk_wtiles[ci].first;
+        const bool gen = !s.fast;
         CUDA_TRY(cudaEventRecord(ws->ev[3][0], ws->stream));
         if (s.hybrid) {
             CUDA_TRY(ws->d_msg.ensure((size_t)ws->n_int * nc * K));  // the walker reads the wide messages even for logL only
             w.msg = ws->d_msg.p; s.a.msg = ws->d_msg.p;
+            if (gen) {
+                CUDA_TRY(ws->d_kindm.ensure((size_t)ws->n_int * nc));
+                w.kindm = ws->d_kindm.p; s.a.kindm = ws->d_kindm.p;
+            }
             if (logl) {
                 CUDA_TRY(ws->d_escale.ensure((size_t)std::max(t->n_wide, 1) * nc));
                 CUDA_TRY(ws->d_esum_wide.ensure(nc));
                 w.escale = ws->d_escale.p;
+                if (gen) {  // component roots and scalar factors inside the wide part
+                    CUDA_TRY(ws->d_logl_wide.ensure(nc));
+                    if (ci == 0) CUDA_TRY(cudaMemsetAsync(ws->d_logl_wide.p, 0, sizeof(double) * nc, ws->stream));
+                    w.logl_acc = ws->d_logl_wide.p;
+                    s.a.logl_wide = ws->d_logl_wide.p;
+                }
             }
-            TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) { return launch_up_wide(K, 1, wa, n_wt, cnt, ws->stream); }));
+            TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
+                return gen ? launch_up_wide_gen(K, 1, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 1, wa, n_wt, cnt, ws->stream); }));
             if (logl) {
                 CUDA_TRY(launch_sum_escale(ws->d_escale.p, t->n_wide, nc, ws->d_esum_wide.p, ws->stream));
                 ws->launches++;
@@ -851,7 +871,8 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
             ws->launches++;
             if (s.hybrid) {
                 w.tmsg = ws->d_tmsg.p; w.out_post = d_out_post; w.qrow = s.a.qrow;
-                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) { return launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
+                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
+                    return gen ? launch_down_wide_gen(K, wa, n_wt, cnt, ws->stream) : launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][1], ws->stream));
             ws->ev_valid[4] = true;

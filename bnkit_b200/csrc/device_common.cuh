@@ -62,6 +62,7 @@ struct WalkArgs {
     // hybrid schedule (lean kernels only): children handled by the wide level kernels
     double *tmsg;               // from-above vectors handed to wide children, [ent][K][ncols]
     const int32_t *esum_wide;   // [ncols] rescale exponents accumulated by the wide sum up-sweep (or nullptr)
+    const double *logl_wide;    // [ncols] log-likelihood terms the general wide kernels accumulated (or nullptr)
 };
 
 // arguments of the level kernels (wide.cu); all column indices are in sorted space
@@ -83,7 +84,15 @@ struct WideArgs {
     const int32_t *qrow;
     uint8_t *state_s;        // [node][ncols]
     int32_t col_lo, col_hi;  // traceback: columns of the chunk being processed
+    // general level kernels (wide_general.cu)
+    const uint8_t *present;  // original column order, or nullptr
+    const double *prior;     // log prior (joint) / prior (sum)
+    uint8_t *kind, *kindm;   // [ent][ncols] node kinds (joint / sum)
+    double *logl_acc;        // [ncols] += log of component-root totals and scalar factors (atomic)
 };
+cudaError_t launch_up_wide_gen(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
+cudaError_t launch_down_wide_gen(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
+cudaError_t launch_traceback_wide_gen(int K, const WideArgs &a, int n_nodes, cudaStream_t st);
 cudaError_t launch_up_wide(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_down_wide(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_traceback_wide(int K, const WideArgs &a, int n_nodes, cudaStream_t st);

@@ -245,8 +245,10 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
             const bool need = pv && ov == BNK_NONE;  // only unobserved present nodes combine messages
             // value of one present child's message for entry p of this column; the first two children use
             // the values prefetched a step ago
-            auto child_g = [&](int cnode, int cslot, uint8_t ou, bool pref, double gpref) -> double {
+            auto child_g = [&](int cnode, int cslot, int cent, uint8_t ou, bool pref, double gpref) -> double {
                 if (ou != BNK_NONE) return pref ? gpref : a.T_col[(tb[j] + cnode) * KK + ou * K + p];
+                if (cslot == SLOT_WIDE)  // handled by a level kernel: message in HBM, [ent][K][ncols]
+                    return a.msg[((size_t)cent * K + p) * a.ncols + col[j]];
                 if (cslot < 0) {  // unobserved childless node: maximise / marginalise its own row
                     const double *row = a.T_row + (tb[j] + cnode) * KK + p * K;
                     double g = row[0];
@@ -256,13 +258,13 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
                 if (cslot < a.smem_slots) return sm.stack[((size_t)cslot * tcpad + lc[j]) * K + p];
                 return a.spill[((size_t)(cslot - a.smem_slots) * a.ncols + col[j]) * K + p];
             };
-            auto child_info = [&](int e, int &cnode, int &cslot, bool &pu, uint8_t &ou) {
+            auto child_info = [&](int e, int &cnode, int &cslot, int &cent, bool &pu, uint8_t &ou) {
                 if (e < 2) {
-                    cnode = st.c_node[e]; cslot = st.c_slot[e];
+                    cnode = st.c_node[e]; cslot = st.c_slot[e]; cent = st.c_ent[e];
                     pu = (e == 0 ? b.pu[0] : b.pu[1]) != 0; ou = (e == 0) ? b.ou[0] : b.ou[1];
                 } else {
                     const ChildRef ch = a.up_child[st.child_begin + e];
-                    cnode = ch.node; cslot = ch.slot;
+                    cnode = ch.node; cslot = ch.slot; cent = ch.ent;
                     pu = !(GENERAL && a.present) || a.present[(size_t)cnode * a.ncols + ocol[j]] != 0;
                     ou = (GENERAL || cslot < 0) ? a.obs[(size_t)cnode * a.ncols + ocol[j]] : (uint8_t)BNK_NONE;
                 }
@@ -275,12 +277,12 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
                 if (rootlike) q[m++] = G;
                 for (int pass = 0; pass < 2; pass++) {
                     for (int e = 0; e < st.n_child && e < MAXQ - 1; e++) {
-                        int cnode, cslot; bool pu; uint8_t ou;
-                        child_info(e, cnode, cslot, pu, ou);
+                        int cnode, cslot, cent; bool pu; uint8_t ou;
+                        child_info(e, cnode, cslot, cent, pu, ou);
                         if (!pu) continue;
                         if (pass == 0) nk++;
                         if ((ou != BNK_NONE) != (pass == 0)) continue;
-                        q[m++] = child_g(cnode, cslot, ou, e < 2, e == 0 ? L0[j].g[0] : L0[j].g[1]);
+                        q[m++] = child_g(cnode, cslot, cent, ou, e < 2, e == 0 ? L0[j].g[0] : L0[j].g[1]);
                     }
                 }
                 int head = 0, tail = m;
@@ -290,17 +292,22 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
                 }
                 G = m > 0 ? q[head] : 0.0;
             } else {
+                // root-like nodes combine [base, observed children, unobserved children]; with two children
+                // of mixed status that order differs from index order in the last bit, so take two passes
+                const int passes = (MODE == 0 && rootlike && st.n_child == 2) ? 2 : 1;
+                for (int pass = 0; pass < passes; pass++)
                 for (int e = 0; e < st.n_child; e++) {
-                    int cnode, cslot; bool pu; uint8_t ou;
-                    child_info(e, cnode, cslot, pu, ou);
+                    int cnode, cslot, cent; bool pu; uint8_t ou;
+                    child_info(e, cnode, cslot, cent, pu, ou);
                     if (!pu) continue;
+                    if (passes == 2 && (ou != BNK_NONE) != (pass == 0)) continue;
                     nk++;
                     if (!need) {
-                        if (MODE == 1 && GENERAL && pv && cslot < 0 && ou != BNK_NONE)  // observed v: scalar factor of an observed childless child
+                        if (MODE == 1 && GENERAL && pv && cslot == SLOT_CHILDLESS && ou != BNK_NONE)  // observed v: scalar factor of an observed childless child
                             logacc[j] += log(a.T_col[(tb[j] + cnode) * KK + ou * K + ov]);
                         continue;
                     }
-                    const double g = child_g(cnode, cslot, ou, e < 2, e == 0 ? L0[j].g[0] : L0[j].g[1]);
+                    const double g = child_g(cnode, cslot, cent, ou, e < 2, e == 0 ? L0[j].g[0] : L0[j].g[1]);
                     if (MODE == 0) G = first ? g : G + g;
                     else G = first ? g : G * g;
                     first = false;
@@ -380,7 +387,11 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
     if (MODE == 1 && a.out_logl && p == 0) {
 #pragma unroll
         for (int j = 0; j < CPT; j++)
-            if (act[j]) a.out_logl[ocol[j]] = logacc[j] + (double)esum[j] * 0.693147180559945309417232121458;
+            if (act[j]) {
+                const int ew = a.esum_wide ? a.esum_wide[col[j]] : 0;
+                const double lw = a.logl_wide ? a.logl_wide[col[j]] : 0.0;
+                a.out_logl[ocol[j]] = logacc[j] + lw + (double)(esum[j] + ew) * 0.693147180559945309417232121458;
+            }
     }
 }
 
@@ -459,6 +470,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
             for (int e = 0; e < 2; e++) {
                 if (e >= s.n_child || !d.b.pu[e]) continue;
                 if (d.b.ou[e] != BNK_NONE) l.g[e] = a.T_col[(tb[j] + s.c_node[e]) * KK + d.b.ou[e] * K + p];
+                else if (s.c_slot[e] == SLOT_WIDE) l.g[e] = a.msg[((size_t)s.c_ent[e] * K + p) * a.ncols + col[j]];
                 else if (s.c_ent[e] >= 0) l.g[e] = a.msg[((size_t)s.c_ent[e] * a.ncols + col[j]) * K + p];
             }
         }
@@ -527,13 +539,15 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
                 if (st.n_child > 0 && b.pu[0] && b.ou[0] == BNK_NONE && st.c_ent[0] >= 0) {
                     const double t = D * g1;
                     const int sl = st.c_slot[0];
-                    if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                    if (sl == SLOT_WIDE) a.tmsg[((size_t)st.c_ent[0] * K + p) * a.ncols + col[j]] = t;
+                    else if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
                     else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
                 }
                 if (st.n_child > 1 && b.pu[1] && b.ou[1] == BNK_NONE && st.c_ent[1] >= 0) {
                     const double t = D * g0;
                     const int sl = st.c_slot[1];
-                    if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                    if (sl == SLOT_WIDE) a.tmsg[((size_t)st.c_ent[1] * K + p) * a.ncols + col[j]] = t;
+                    else if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
                     else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
                 }
             } else {

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
 
     // pipeline registers: observed states of childless children (two steps ahead) and their
     // table entries (one step ahead)
-    int ob1[CPT][2], ob2[CPT][2];
+    int ob0[CPT][2], ob1[CPT][2], ob2[CPT][2];
     double g0[CPT][2], g1[CPT][2];
     auto load_obs = [&](int po, int k, int j, int e) -> int {
         const int cn = (e == 0) ? STEP_AT(po, k, c_node[0]) : STEP_AT(po, k, c_node[1]);
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int o0 = n_steps > 0 ? load_obs(0, 0, j, e) : BNK_NONE;
+            ob0[j][e] = o0;
             ob1[j][e] = n_steps > 1 ? load_obs(0, 1, j, e) : BNK_NONE;
             g0[j][e] = n_steps > 0 ? load_look(0, 0, o0, j, e) : ident;
         }
@@ -249,7 +250,14 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             const double s0 = SM_D(so0 + sidx[j]), s1 = SM_D(so1 + sidx[j]);
-            const double c0 = in0 ? s0 : g0[j][0], c1 = in1 ? s1 : g0[j][1];
+            double c0 = in0 ? s0 : g0[j][0], c1 = in1 ? s1 : g0[j][1];
+            if (MODE == 0 && rootstep) {
+                // a root combines [prior, observed children, unobserved children] (the order the factors
+                // sit in the reference's bucket); with one child of each kind that fixes the association
+                const bool o0 = cs0 == SLOT_CHILDLESS && ob0[j][0] != BNK_NONE;
+                const bool o1 = cs1 == SLOT_CHILDLESS && ob0[j][1] != BNK_NONE;
+                if (!o0 && o1) { const double t = c0; c0 = c1; c1 = t; }
+            }
             double G;
             if (MODE == 0) G = ((rootstep ? prior_p : 0.0) + c0) + c1;
             else G = ((rootstep ? prior_p : 1.0) * c0) * c1;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
 #pragma unroll
-            for (int e = 0; e < 2; e++) { ob1[j][e] = ob2[j][e]; g0[j][e] = g1[j][e]; }
+            for (int e = 0; e < 2; e++) { ob0[j][e] = ob1[j][e]; ob1[j][e] = ob2[j][e]; g0[j][e] = g1[j][e]; }
         }
     }
     if (MODE == 1 && a.out_logl && p == 0) {

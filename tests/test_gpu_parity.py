@@ -162,3 +162,45 @@ def test_large_irregular_tree_hybrid(bnk, oracle):
     p2, _ = ws.marginal(obs, query=q, want_logl=False)
     assert np.allclose(p2, post[::311], rtol=1e-12, atol=0)
     ws.close()
+
+
+def test_large_tree_with_masks_and_evidence_hybrid(bnk, oracle):
+    """Per-column forests on a 3,000-leaf tree (wide levels + walker, general kernels): gaps, presence
+    masks from the stand-in indel rule, orphan pruning, a sprinkle of evidence on internal nodes."""
+    from bnkit_b200 import synth
+    rng = np.random.default_rng(23)
+    m, om = bnk.Model("JTT"), oracle.Model("JTT")
+    n_cols = 80
+    for maker, seed in ((synth.balanced_tree, 11), (synth.random_tree, 12)):
+        parent, dist = maker(3000, seed=seed)
+        rates = rng.choice([0.4, 1.0, 2.5], size=n_cols)
+        obs = synth.simulate_alignment(parent, dist, m.parts(), n_cols, rates, seed=seed, gap_fraction=0.55)
+        leaf = leaves_of(parent)
+        present = synth.path_presence_mask(parent, (obs != NONE) & leaf[:, None])
+        # knock out random ancestors too (forests with many components), then prune orphans like GRASP does
+        present[(rng.random(present.shape) < 0.05) & ~leaf[:, None]] = 0
+        tree = bnk.Tree(parent, dist)
+        present = tree.prune_orphans(present)
+        ev = (rng.random(obs.shape) < 0.01) & ~leaf[:, None] & (present == 1)
+        obs[ev] = rng.integers(0, 20, int(ev.sum()))
+        ws = bnk.Workspace(m, tree, n_cols)
+        ws.set_rates(n_cols, rates)
+        got = ws.joint(obs, present)
+        want = oracle.fast_joint(om, parent, dist, obs, present, rates, nthreads=8)
+        assert np.array_equal(got, want), (got != want).sum()
+        post, logl = ws.marginal(obs, present)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, present, rates, nthreads=8)
+        _post_close(post, wpost[tree.internal_nodes()])
+        assert np.allclose(logl, wlogl, rtol=TOL, atol=1e-9)
+        l2, tot = ws.loglik(obs, present)
+        assert np.allclose(l2, wlogl, rtol=TOL, atol=1e-9)
+        ws.close()
+        # the same through the walker only
+        ws2 = bnk.Workspace(m, tree, n_cols)
+        ws2.configure(-16, 1)
+        ws2.set_rates(n_cols, rates)
+        assert np.array_equal(ws2.joint(obs, present), want)
+        p2, l3 = ws2.marginal(obs, present)
+        _post_close(p2, wpost[tree.internal_nodes()])
+        assert np.allclose(l3, wlogl, rtol=TOL, atol=1e-9)
+        ws2.close()
