@@ -573,6 +573,8 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
                         double s = 0.0;
                         for (int x = 0; x < K; x++) s += a.T_col[(tb[j] + ch.node) * KK + x * K + p];
                         gv[e] = s;
+                    } else if (ch.slot == SLOT_WIDE) {
+                        gv[e] = a.msg[((size_t)ch.ent * K + p) * a.ncols + col[j]];
                     } else {
                         gv[e] = a.msg[((size_t)ch.ent * a.ncols + col[j]) * K + p];
                     }
@@ -587,9 +589,11 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
                 double pre = D;
                 for (int e = 0; e < nch; e++) {
                     if (push[e]) {
-                        const int sl = a.down_child[st.child_begin + e].slot;
+                        const ChildRef chp = a.down_child[st.child_begin + e];
+                        const int sl = chp.slot;
                         const double t = pre * suf[e];
-                        if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                        if (sl == SLOT_WIDE) a.tmsg[((size_t)chp.ent * K + p) * a.ncols + col[j]] = t;
+                        else if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
                         else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
                     }
                     pre *= gv[e];

@@ -188,16 +188,25 @@ static void build_plan(bnk_tree *t)
     std::vector<int32_t> width(hmax + 2, 0);
     for (int32_t i = 0; i < n; i++)
         if (t->ent_of_node[i] >= 0) width[t->height[i]]++;
+    // the level kernels handle nodes with at most two children: a multifurcation and everything above
+    // it stays with the walker (the wide set must be closed under taking descendants)
+    std::vector<uint8_t> poly(n, 0);
+    for (int32_t i = n - 1; i >= 0; i--) {
+        if (t->first[i + 1] - t->first[i] > 2) poly[i] = 1;
+        if (poly[i] && t->parent[i] >= 0) poly[t->parent[i]] = 1;
+    }
+    std::fill(width.begin(), width.end(), 0);
+    for (int32_t i = 0; i < n; i++)
+        if (t->ent_of_node[i] >= 0 && !poly[i] && t->parent[i] >= 0) width[t->height[i]]++;
     t->wide_h = 0;
-    if (t->max_children <= 2)
-        while (t->wide_h + 1 <= hmax && width[t->wide_h + 1] >= WIDE_MIN_NODES) t->wide_h++;
+    while (t->wide_h + 1 <= hmax && width[t->wide_h + 1] >= WIDE_MIN_NODES) t->wide_h++;
     // the root of a tree is never wide (its level has one node), so the narrow set is never empty
     std::vector<uint8_t> narrow(n, 0);
     t->levels.assign(t->wide_h, {});
     t->n_wide = 0;
     for (int32_t i = 0; i < n; i++) {
         if (t->ent_of_node[i] < 0) continue;
-        if (t->height[i] > t->wide_h || t->parent[i] < 0) { narrow[i] = 1; continue; }
+        if (t->height[i] > t->wide_h || t->parent[i] < 0 || poly[i]) { narrow[i] = 1; continue; }
         WideNode w;
         w.node = i; w.parent = t->parent[i]; w.ent = t->ent_of_node[i];
         w.n_child = t->first[i + 1] - t->first[i];

@@ -171,8 +171,10 @@ def test_large_tree_with_masks_and_evidence_hybrid(bnk, oracle):
     rng = np.random.default_rng(23)
     m, om = bnk.Model("JTT"), oracle.Model("JTT")
     n_cols = 80
-    for maker, seed in ((synth.balanced_tree, 11), (synth.random_tree, 12)):
-        parent, dist = maker(3000, seed=seed)
+    makers = ((synth.balanced_tree, 11, {}), (synth.random_tree, 12, {}),
+              (synth.random_tree, 13, {"max_children": 4}))   # polytomies: wide levels below them, walker above
+    for maker, seed, kw in makers:
+        parent, dist = maker(3000, seed=seed, **kw)
         rates = rng.choice([0.4, 1.0, 2.5], size=n_cols)
         obs = synth.simulate_alignment(parent, dist, m.parts(), n_cols, rates, seed=seed, gap_fraction=0.55)
         leaf = leaves_of(parent)
