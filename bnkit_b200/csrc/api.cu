@@ -228,6 +228,8 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_WIDE_TPC")) ws->wide_tpc_max = std::max(1, std::atoi(env));  // tuning knob
+    if (const char *env = std::getenv("BNK_TABLE_BUDGET_MB"))  // bytes of P(t) tables held at once (tests force several chunks)
+        ws->table_budget = (size_t)std::max(1, std::atoi(env)) << 20;
     // accounting hooks
     DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
                             &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_logl_wide, &ws->d_post, &ws->d_sum};

@@ -206,3 +206,26 @@ def test_large_tree_with_masks_and_evidence_hybrid(bnk, oracle):
         _post_close(p2, wpost[tree.internal_nodes()])
         assert np.allclose(l3, wlogl, rtol=TOL, atol=1e-9)
         ws2.close()
+
+
+def test_rate_category_chunks(bnk, oracle, monkeypatch):
+    """Every column its own rate => as many categories as columns; a tiny table budget forces the
+    categories through several chunks (tables rebuilt per chunk, per-chunk traceback column ranges)."""
+    monkeypatch.setenv("BNK_TABLE_BUDGET_MB", "1")
+    rng = np.random.default_rng(29)
+    for name, leaves, mc, gap in (("LG", 40, 2, 0.0), ("WAG", 30, 3, 0.4), ("LG", 220, 2, 0.0), ("JTT", 220, 2, 0.3)):
+        m, om = bnk.Model(name), oracle.Model(name)
+        parent, dist = random_tree(rng, leaves, max_children=mc)
+        n_cols = 57
+        rates = rng.gamma(0.7, 1.5, size=n_cols) + 0.01
+        obs = random_obs(rng, parent, n_cols, 20, gap_prob=gap)
+        present = random_present(rng, parent, obs) if gap else None
+        tree = bnk.Tree(parent, dist)
+        ws = bnk.Workspace(m, tree, n_cols)
+        ws.set_rates(n_cols, rates)
+        assert np.array_equal(ws.joint(obs, present), oracle.fast_joint(om, parent, dist, obs, present, rates))
+        post, logl = ws.marginal(obs, present)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, present, rates)
+        _post_close(post, wpost[tree.internal_nodes()])
+        assert np.allclose(logl, wlogl, rtol=TOL, atol=1e-10)
+        ws.close()
