@@ -15,6 +15,7 @@ UNITS = [
     ("sweeps_fast.cu", []),
     ("wide.cu", []),
     ("wide_general.cu", []),
+    ("cherry.cu", []),
     ("traceback.cu", []),
     ("api.cu", []),
     ("subst_model.cpp", ["-fmad=false"]),

@@ -95,6 +95,16 @@ struct bnk_ws {
     std::vector<int32_t> orig_col, col_cat_global, cat_of_col;
     std::vector<TileDesc> tiles, wtiles;   // walker tiles; wide tiles (one category, <= 128 columns)
     std::vector<Chunk> chunks;
+    std::vector<TileDesc> cgroups;         // cherry groups (one category, <= cherry_group_cols() columns)
+    std::vector<std::pair<int, int>> chunk_cgroups;
+    DevBuf<TileDesc> d_cgroups;
+    std::vector<int> chunk_crecs;          // per chunk: result records per height-1 node (sum of the groups' capacities)
+    DevBuf<uint8_t> d_cscratch;
+    DevBuf<int16_t> d_cslots;
+    std::vector<TileDesc> ctiles;          // expansion tiles of the cherry groups (16-column aligned starts)
+    std::vector<std::pair<int, int>> chunk_ctiles;
+    DevBuf<TileDesc> d_ctiles;
+    bool no_cherry = false;                // BNK_NO_CHERRY=1: height-1 level through the plain level kernel (A/B, tests)
     std::vector<std::pair<int, int>> chunk_wtiles, chunk_cols;  // per chunk: wide tile range, sorted column range
     int tile_cols = 0, cpt = 1, ncg = 0, threads = 0;
     DevBuf<double> d_cat_rate;
@@ -193,7 +203,7 @@ static void ws_free(bnk_ws *ws)
     for (auto *b : di) b->release();
     ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
     ws->d_up_n.release(); ws->d_down_n.release(); ws->d_up_child_n.release(); ws->d_down_child_n.release();
-    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
+    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
     if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
@@ -227,6 +237,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
         ws->own_stream = true;
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
+    if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_WIDE_TPC")) ws->wide_tpc_max = std::max(1, std::atoi(env));  // tuning knob
     if (const char *env = std::getenv("BNK_TABLE_BUDGET_MB"))  // bytes of P(t) tables held at once (tests force several chunks)
         ws->table_budget = (size_t)std::max(1, std::atoi(env)) << 20;
@@ -389,7 +400,8 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     int cats_per_chunk = (int)std::max<size_t>(1, ws->table_budget / std::max<size_t>(per_cat, 1));
     if (cats_per_chunk > 60000) cats_per_chunk = 60000;
     ws->chunks.clear(); ws->wtiles.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
-    const int wt = wide_tile_cols();
+    ws->cgroups.clear(); ws->chunk_cgroups.clear(); ws->chunk_crecs.clear(); ws->ctiles.clear(); ws->chunk_ctiles.clear();
+    const int wt = wide_tile_cols(), cg = cherry_group_cols();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
         const int hi = std::min(ncat, lo + cats_per_chunk);
         Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
@@ -400,6 +412,19 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             for (int q = 0; q < nt; q++) {
                 const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
                 ws->wtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+            }
+        }
+        const int g0 = (int)ws->cgroups.size();
+        const int ct0 = (int)ws->ctiles.size();
+        int crecs = 0;  // TileDesc::ncat of a cherry group = offset of its result records inside a node's region
+        for (int k = lo; k < hi; k++) {
+            const int nc = cat_begin[k + 1] - cat_begin[k];
+            const int nt = (nc + cg - 1) / cg;
+            for (int q = 0; q < nt; q++) {
+                const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                for (int c = a0 & ~15; c < a1; c += wt) ws->ctiles.push_back(TileDesc{c, wt, (int)ws->cgroups.size() - g0, 0});
+                ws->cgroups.push_back(TileDesc{a0, a1 - a0, k - lo, crecs});
+                crecs += cherry_group_capacity(K, a1 - a0);  // distinct (state, state) pairs of two children
             }
         }
         TileDesc cur{0, 0, 0, 0};
@@ -426,6 +451,9 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         if (ck.tile_hi > ck.tile_lo) {
             ws->chunks.push_back(ck);
             ws->chunk_wtiles.push_back({w0, (int)ws->wtiles.size()});
+            ws->chunk_cgroups.push_back({g0, (int)ws->cgroups.size()});
+            ws->chunk_crecs.push_back(crecs);
+            ws->chunk_ctiles.push_back({ct0, (int)ws->ctiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
         }
     }
@@ -442,6 +470,8 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_cat_of_col, ws->cat_of_col, ws->stream));
     TRY(upload(ws->d_tiles, ws->tiles, ws->stream));
     TRY(upload(ws->d_wtiles, ws->wtiles, ws->stream));
+    TRY(upload(ws->d_cgroups, ws->cgroups, ws->stream));
+    TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
     ws->rates_null = rates == nullptr;
@@ -633,6 +663,20 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
     w.tiles = ws->d_wtiles.p + ws->chunk_wtiles[ci].first;
     w.n_tiles = ws->chunk_wtiles[ci].second - ws->chunk_wtiles[ci].first;
     w.tiles_per_cta = 1;
+    {   // site-pattern compression of the height-1 level pays when a group holds enough columns to repeat
+        const int g0 = ws->chunk_cgroups[ci].first, ng = ws->chunk_cgroups[ci].second - g0;
+        const int cols = ws->chunk_cols[ci].second - ws->chunk_cols[ci].first;
+        const int n_h1 = ws->tree->wide_h > 0 ? std::min(65535, ws->level_off[1] - ws->level_off[0]) : 0;
+        if (!ws->no_cherry && ng > 0 && cols / ng >= 64 && n_h1 > 0 &&
+            ws->d_cscratch.ensure((size_t)n_h1 * ws->chunk_crecs[ci] * cherry_record_bytes(ws->K)) == cudaSuccess &&
+            ws->d_cslots.ensure((size_t)n_h1 * ws->ncols) == cudaSuccess) {
+            w.cgroups = ws->d_cgroups.p + g0; w.n_cgroups = ng;
+            w.cscratch = ws->d_cscratch.p; w.crecs_per_node = ws->chunk_crecs[ci];
+            w.cslots = ws->d_cslots.p;
+            w.ctiles = ws->d_ctiles.p + ws->chunk_ctiles[ci].first;
+            w.n_ctiles = ws->chunk_ctiles[ci].second - ws->chunk_ctiles[ci].first;
+        }
+    }
     w.obs = obs_s;
     w.ncols = ws->ncols; w.n_nodes = ws->n;
     w.orig_col = ws->d_orig_col.p;

@@ -79,6 +79,13 @@ struct WideArgs {
     int16_t *escale;         // [wide row][ncols] rescale exponent of each (node, column)
     int32_t wide_row0;       // wide row of nodes[0]
     int32_t cherry;          // the level is height 1: every child is childless
+    const TileDesc *cgroups; // cherry.cu: column groups of one category, <= cherry_group_cols() columns (nullptr: not used)
+    int32_t n_cgroups;
+    uint8_t *cscratch;       // cherry.cu: result records of the distinct pairs, [level node][crecs_per_node] records
+    int32_t crecs_per_node;  //   (the record offset of a group inside a node's region is cgroups[].ncat)
+    int16_t *cslots;         // cherry.cu: record index of every column, [level node][ncols]
+    const TileDesc *ctiles;  // cherry.cu expansion tiles: col0 = 16-aligned start, cat0 = group
+    int32_t n_ctiles;
     double *tmsg;
     double *out_post;
     const int32_t *qrow;
@@ -100,6 +107,10 @@ cudaError_t launch_sum_escale(const int16_t *escale, int n_rows, int ncols, int3
 cudaError_t launch_scatter_rows(const uint8_t *in, uint8_t *out, const int32_t *nodes, int n_rows,
                                 const int32_t *orig_col, int ncols, cudaStream_t st);
 int wide_tile_cols();
+cudaError_t launch_up_cherry(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st);
+int cherry_group_cols();
+size_t cherry_record_bytes(int K);
+int cherry_group_capacity(int K, int ncols);
 
 void launch_build_tables(int K, const ModelDev &md, const double *times, const int32_t *skip,
                          const double *rates, int n_nodes, int n_cat, const TableSet &ts, cudaStream_t st);

@@ -35,13 +35,7 @@ __device__ __forceinline__ void child_vector(const WideArgs &a, const WideNode &
 #pragma unroll
             for (int x = 0; x < K; x++) g[x] = lt_smem[ou * (K + 1) + x];
         } else {  // uninstantiated childless node: maximise / marginalise its own row
-            const double *L = a.T_row + (tb + cn) * (K * K);
-#pragma unroll
-            for (int x = 0; x < K; x++) {
-                double r = L[x * K];
-                for (int y = 1; y < K; y++) r = (MODE == 0) ? (L[x * K + y] > r ? L[x * K + y] : r) : r + L[x * K + y];
-                g[x] = r;
-            }
+            self_vector<K, MODE>(a.T_row + (tb + cn) * (K * K), g);
         }
     }
     (void)valid;
@@ -66,6 +60,7 @@ __global__ void __launch_bounds__(WT, 5) up_wide_kernel(const WideArgs a)
             load_table<K>(Ls, a.T_row + (tb + w.node) * (K * K), 0);
             if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
             if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+            tables_wait();
             __syncthreads();
             cur_cat = tile.cat0;
         }
@@ -82,17 +77,11 @@ __global__ void __launch_bounds__(WT, 5) up_wide_kernel(const WideArgs a)
         double *mout = a.msg + (size_t)w.ent * K * a.ncols + col;
         if (MODE == 0) {
             uint8_t *pout = a.ptr + (size_t)w.ent * K * a.ncols + col;
-#pragma unroll 4
+#pragma unroll 2
             for (int p = 0; p < K; p++) {
-                const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
-                double best = -CUDART_INF;
-                int bi = 0;
-#pragma unroll
-                for (int x2 = 0; x2 < K / 2; x2++) {
-                    const double2 l = row2[x2];
-                    argmax_step(best, bi, l.x, G[2 * x2], 2 * x2);
-                    argmax_step(best, bi, l.y, G[2 * x2 + 1], 2 * x2 + 1);
-                }
+                double best;
+                int bi;
+                argmax_row<K>(Ls + p * K, G, best, bi);
                 if (valid) {
                     mout[(size_t)p * a.ncols] = best;
                     pout[(size_t)p * a.ncols] = (uint8_t)bi;
@@ -148,6 +137,7 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
             load_table<K>(PTs, a.T_col + (tb + w.node) * (K * K), 0);  // PT[x][xp] = P[xp][x]
             if (leaf0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
             if (leaf1) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+            tables_wait();
             __syncthreads();
             cur_cat = tile.cat0;
         }
@@ -276,6 +266,7 @@ __global__ void scatter_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__r
 cudaError_t launch_up_wide(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st)
 {
     if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
+    if (a.cherry && a.cgroups) return launch_up_cherry(K, mode, a, n_nodes, st);  // site-pattern compression (cherry.cu)
     dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, n_nodes);
     if (K == 20 && mode == 0) up_wide_kernel<20, 0><<<grid, WT, 0, st>>>(a);
     else if (K == 20) up_wide_kernel<20, 1><<<grid, WT, 0, st>>>(a);

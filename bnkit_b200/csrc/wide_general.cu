@@ -59,13 +59,7 @@ __device__ __forceinline__ void child_vector_gen(const WideArgs &a, const WideNo
 #pragma unroll
         for (int x = 0; x < K; x++) g[x] = m[(size_t)x * a.ncols];
     } else {  // uninstantiated childless node: maximise / marginalise its own row
-        const double *L = a.T_row + (tb + cn) * (K * K);
-#pragma unroll
-        for (int x = 0; x < K; x++) {
-            double r = L[x * K];
-            for (int y = 1; y < K; y++) r = (MODE == 0) ? (L[x * K + y] > r ? L[x * K + y] : r) : r + L[x * K + y];
-            g[x] = r;
-        }
+        self_vector<K, MODE>(a.T_row + (tb + cn) * (K * K), g);
     }
 }
 
@@ -87,6 +81,7 @@ __global__ void __launch_bounds__(WT, 4) up_wide_gen_kernel(const WideArgs a)
             load_table<K>(Ls, a.T_row + (tb + w.node) * (K * K), 0);
             if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
             if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+            tables_wait();
             __syncthreads();
             cur_cat = tile.cat0;
         }
@@ -149,15 +144,9 @@ __global__ void __launch_bounds__(WT, 4) up_wide_gen_kernel(const WideArgs a)
             }
 #pragma unroll 2
             for (int p = 0; p < K; p++) {
-                const double2 *row2 = reinterpret_cast<const double2 *>(Ls + p * K);
-                double best = -CUDART_INF;
-                int bi = 0;
-#pragma unroll
-                for (int x2 = 0; x2 < K / 2; x2++) {
-                    const double2 l = row2[x2];
-                    argmax_step(best, bi, l.x, G[2 * x2], 2 * x2);
-                    argmax_step(best, bi, l.y, G[2 * x2 + 1], 2 * x2 + 1);
-                }
+                double best;
+                int bi;
+                argmax_row<K>(Ls + p * K, G, best, bi);
                 mout[(size_t)p * a.ncols] = best;
                 pout[(size_t)p * a.ncols] = (uint8_t)bi;
             }
@@ -211,6 +200,7 @@ __global__ void __launch_bounds__(WT, 3) down_wide_gen_kernel(const WideArgs a)
             load_table<K>(PTs, a.T_col + (tb + w.node) * (K * K), 0);  // PT[x][xp] = P[xp][x]
             if (w.n_child > 0 && w.c_ent[0] < 0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
             if (w.n_child > 1 && w.c_ent[1] < 0) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
+            tables_wait();
             __syncthreads();
             cur_cat = tile.cat0;
         }

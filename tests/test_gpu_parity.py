@@ -229,3 +229,36 @@ def test_rate_category_chunks(bnk, oracle, monkeypatch):
         _post_close(post, wpost[tree.internal_nodes()])
         assert np.allclose(logl, wlogl, rtol=TOL, atol=1e-10)
         ws.close()
+
+
+def test_cherry_pattern_compression(bnk, oracle, monkeypatch):
+    """The height-1 level with site-pattern compression (cherry.cu): one evaluation per distinct pair of
+    child states and category.  Against the oracle, and bit-identical to the plain level kernel
+    (BNK_NO_CHERRY=1), incl. uninstantiated leaves, unary height-1 nodes, 3 categories with ragged sizes,
+    a group boundary (> 2048 columns in one category) and a 4-state model."""
+    from bnkit_b200 import synth
+    rng = np.random.default_rng(31)
+    for name, K, leaves, n_cols, gap in (("LG", 20, 700, 2600, 0.0), ("JTT", 20, 400, 900, 0.03), ("JC", 4, 300, 700, 0.02)):
+        m, om = bnk.Model(name), oracle.Model(name)
+        parent, dist = synth.random_tree(leaves, seed=leaves)
+        rates = rng.choice([0.3, 1.0, 2.2], size=n_cols, p=[0.85, 0.1, 0.05]) if n_cols > 2048 else rng.choice([0.3, 1.0, 2.2], size=n_cols)
+        obs = synth.simulate_alignment(parent, dist, m.parts(), n_cols, rates, seed=leaves + 1, gap_fraction=gap)
+        tree = bnk.Tree(parent, dist)
+        sub = slice(0, n_cols, 9)  # the oracle on a sample of the columns
+        want = oracle.fast_joint(om, parent, dist, np.ascontiguousarray(obs[:, sub]), None, rates[sub], nthreads=8)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, np.ascontiguousarray(obs[:, sub]), None, rates[sub], nthreads=8)
+        res = []
+        for no_cherry in ("0", "1"):
+            monkeypatch.setenv("BNK_NO_CHERRY", no_cherry)
+            ws = bnk.Workspace(m, tree, n_cols)
+            ws.set_rates(n_cols, rates)
+            st = ws.joint(obs, None)
+            post, logl = ws.marginal(obs, None)
+            ws.close()
+            assert np.array_equal(st[:, sub], want)
+            _post_close(post[:, sub], wpost[tree.internal_nodes()])
+            assert np.allclose(logl[sub], wlogl, rtol=TOL, atol=1e-9)
+            res.append((st, post, logl))
+        assert np.array_equal(res[0][0], res[1][0])
+        assert np.array_equal(res[0][1], res[1][1], equal_nan=True)
+        assert np.array_equal(res[0][2], res[1][2])
