@@ -378,7 +378,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     // defaults from the r1 sweep on C3 (profiles/): 2 columns per thread, ~2.8 CTAs per SM
     int cpt = ws->cfg_cpt ? ws->cfg_cpt : (K == 20 ? 2 : 1);
     int tc = ws->cfg_tile_cols;
-    const int max_threads = cpt == 1 ? 768 : (cpt == 2 ? 512 : 256);  // the kernels' __launch_bounds__
+    const int max_threads = cpt == 1 ? 512 : (cpt == 2 ? 384 : 256);  // the kernels' __launch_bounds__
     const int tc_cap = (max_threads / K) * cpt;
     if (tc <= 0) {
         const int target_tiles = ws->sm_count * 3 - ws->sm_count / 6;

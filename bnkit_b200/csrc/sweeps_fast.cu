@@ -15,10 +15,17 @@
 
 namespace bnk {
 
-constexpr int FSTAGE = 4;   // table ring depth (power of two)
+constexpr int FSTAGE = 8;   // table ring depth (power of two)
 constexpr int FRING = 64;   // walk-program ring: two 32-step chunks ...
 constexpr int FCHUNK = 32;
-constexpr int FGUARD = 4;   // ... plus a mirror of its first steps, so look-ahead never wraps
+constexpr int FGUARD = 8;   // ... plus a mirror of its first steps, so look-ahead never wraps
+// Depth of the per-thread register pipeline that feeds the childless children: the observed state of step
+// i + F_OA is requested while step i runs, the table entry it selects at step i + F_LA.  A step of a deep tree
+// takes ~300-500 cycles once nothing stalls, a DRAM round trip ~1,500: with the r1 depths (2 and 1) every step
+// of the 10,000-level caterpillar waited for both loads (1.43 us per step, profiles/r1_v12_bench_caterpillar).
+constexpr int F_LA = 4;
+constexpr int F_OA = 8;
+static_assert(F_OA <= FGUARD && F_LA < F_OA, "look-ahead must stay inside the program ring's guard");
 
 __device__ __forceinline__ void f_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -130,7 +137,7 @@ __device__ __forceinline__ double f_rcp(double s)
 // active" branch at all.
 // ------------------------------------------------------------------------------------
 template <int K, int CPT, int MODE>
-__global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fast_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(CPT == 1 ? 512 : (CPT == 2 ? 384 : 256)) up_fast_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using LY = FLayout<K>;
@@ -187,10 +194,12 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
         f_cp_async_commit();
     }
 
-    // pipeline registers: observed states of childless children (two steps ahead) and their
-    // table entries (one step ahead)
-    int ob0[CPT][2], ob1[CPT][2], ob2[CPT][2];
-    double g0[CPT][2], g1[CPT][2];
+    // pipeline registers (rings shifted once per step): obr[k] = observed state of the child at step
+    // i + F_LA + k, gr[k] = its value at step i + k, isobs bit (2k + e) = "child e of step i + k is observed"
+    constexpr int NOB = F_OA - F_LA + 1, NG = F_LA + 1;
+    int obr[CPT][2][NOB];
+    double gr[CPT][2][NG];
+    unsigned isobs[CPT];
     auto load_obs = [&](int po, int k, int j, int e) -> int {
         const int cn = (e == 0) ? STEP_AT(po, k, c_node[0]) : STEP_AT(po, k, c_node[1]);
         return obs_c[j][(size_t)(unsigned)(cn < 0 ? 0 : cn) * ncols_u];
@@ -216,12 +225,19 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
     };
 #pragma unroll
     for (int j = 0; j < CPT; j++) {
+        isobs[j] = 0;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int o0 = n_steps > 0 ? load_obs(0, 0, j, e) : BNK_NONE;
-            ob0[j][e] = o0;
-            ob1[j][e] = n_steps > 1 ? load_obs(0, 1, j, e) : BNK_NONE;
-            g0[j][e] = n_steps > 0 ? load_look(0, 0, o0, j, e) : ident;
+            int o[F_OA];
+#pragma unroll
+            for (int k = 0; k < F_OA; k++) o[k] = k < n_steps ? load_obs(0, k, j, e) : BNK_NONE;
+#pragma unroll
+            for (int k = 0; k < F_LA; k++) {
+                gr[j][e][k] = k < n_steps ? load_look(0, k, o[k], j, e) : ident;
+                isobs[j] |= (unsigned)(o[k] != BNK_NONE) << (2 * k + e);
+            }
+#pragma unroll
+            for (int k = 0; k < NOB - 1; k++) obr[j][e][k] = o[F_LA + k];
         }
     }
 
@@ -231,15 +247,16 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
         const int cs0 = STEP_AT(po, 0, c_slot[0]), cs1 = STEP_AT(po, 0, c_slot[1]);
         const bool rootstep = STEP_AT(po, 0, parent) < 0;
         const int gs_off = LY::GS + (i & 1) * ly.gs_bytes;
-        // ---- pipeline: states for step i+2, table entries for step i+1 ----
+        // ---- pipeline: states for step i + F_OA, table entries for step i + F_LA ----
         {
-            const bool h2 = i + 2 < n_steps, h1 = i + 1 < n_steps;
+            const bool ho = i + F_OA < n_steps, hl = i + F_LA < n_steps;
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    ob2[j][e] = h2 ? load_obs(po, 2, j, e) : BNK_NONE;
-                    g1[j][e] = h1 ? load_look(po, 1, ob1[j][e], j, e) : ident;
+                    obr[j][e][NOB - 1] = ho ? load_obs(po, F_OA, j, e) : BNK_NONE;
+                    gr[j][e][NG - 1] = hl ? load_look(po, F_LA, obr[j][e][0], j, e) : ident;
+                    isobs[j] |= (unsigned)(obr[j][e][0] != BNK_NONE) << (2 * F_LA + e);
                 }
             }
         }
@@ -250,12 +267,12 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             const double s0 = SM_D(so0 + sidx[j]), s1 = SM_D(so1 + sidx[j]);
-            double c0 = in0 ? s0 : g0[j][0], c1 = in1 ? s1 : g0[j][1];
+            double c0 = in0 ? s0 : gr[j][0][0], c1 = in1 ? s1 : gr[j][1][0];
             if (MODE == 0 && rootstep) {
                 // a root combines [prior, observed children, unobserved children] (the order the factors
                 // sit in the reference's bucket); with one child of each kind that fixes the association
-                const bool o0 = cs0 == SLOT_CHILDLESS && ob0[j][0] != BNK_NONE;
-                const bool o1 = cs1 == SLOT_CHILDLESS && ob0[j][1] != BNK_NONE;
+                const bool o0 = cs0 == SLOT_CHILDLESS && (isobs[j] & 1u);
+                const bool o1 = cs1 == SLOT_CHILDLESS && (isobs[j] & 2u);
                 if (!o0 && o1) { const double t = c0; c0 = c1; c1 = t; }
             }
             double G;
@@ -327,8 +344,14 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
         }
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
+            isobs[j] >>= 2;
 #pragma unroll
-            for (int e = 0; e < 2; e++) { ob0[j][e] = ob1[j][e]; ob1[j][e] = ob2[j][e]; g0[j][e] = g1[j][e]; }
+            for (int e = 0; e < 2; e++) {
+#pragma unroll
+                for (int k = 0; k < NOB - 1; k++) obr[j][e][k] = obr[j][e][k + 1];
+#pragma unroll
+                for (int k = 0; k < NG - 1; k++) gr[j][e][k] = gr[j][e][k + 1];
+            }
         }
     }
     if (MODE == 1 && a.out_logl && p == 0) {
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_fa
 // down-sweep (see sweeps.cu for the recurrences)
 // ------------------------------------------------------------------------------------
 template <int K, int CPT>
-__global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_fast_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(CPT == 1 ? 512 : (CPT == 2 ? 384 : 256)) down_fast_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using LY = FLayout<K>;
@@ -396,9 +419,10 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
         if (s < n_steps) tcopy.issue(tab_cat + (size_t)STEP_FIELD(s, node) * (KK * 8), sbase + LY::TAB + s * LY::STAGE_BYTES);
         f_cp_async_commit();
     }
-    int ob1[CPT][2], ob2[CPT][2];
-    double g0[CPT][2], g1[CPT][2];
-    int q0 = 0, q1 = 0;
+    constexpr int NOB = F_OA - F_LA + 1, NG = F_LA + 1;
+    int obr[CPT][2][NOB];  // rings as in up_fast_kernel
+    double gr[CPT][2][NG];
+    int qr[NG];            // posterior row of steps i .. i + F_LA
     auto load_obs = [&](int po, int k, int j, int e) -> int {
         const int cn = (e == 0) ? STEP_AT(po, k, c_node[0]) : STEP_AT(po, k, c_node[1]);
         return obs_c[j][(size_t)(unsigned)(cn < 0 ? 0 : cn) * ncols_u];
@@ -426,12 +450,17 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
     for (int j = 0; j < CPT; j++) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int o0 = n_steps > 0 ? load_obs(0, 0, j, e) : BNK_NONE;
-            ob1[j][e] = n_steps > 1 ? load_obs(0, 1, j, e) : BNK_NONE;
-            g0[j][e] = n_steps > 0 ? load_val(0, 0, o0, j, e) : 1.0;
+            int o[F_OA];
+#pragma unroll
+            for (int k = 0; k < F_OA; k++) o[k] = k < n_steps ? load_obs(0, k, j, e) : BNK_NONE;
+#pragma unroll
+            for (int k = 0; k < F_LA; k++) gr[j][e][k] = k < n_steps ? load_val(0, k, o[k], j, e) : 1.0;
+#pragma unroll
+            for (int k = 0; k < NOB - 1; k++) obr[j][e][k] = o[F_LA + k];
         }
     }
-    if (n_steps > 0) q0 = a.qrow ? a.qrow[STEP_FIELD(0, ent)] : STEP_FIELD(0, ent);
+#pragma unroll
+    for (int k = 0; k < F_LA; k++) qr[k] = k < n_steps ? (a.qrow ? a.qrow[STEP_FIELD(k, ent)] : STEP_FIELD(k, ent)) : -1;
     f_cp_async_wait<FSTAGE - 1>();
     __syncthreads();
 
@@ -447,16 +476,16 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
         const int so1 = in1 ? ly.stack + dcs1 * ly.slot_bytes : dummy_off;
         const int gs_off = LY::GS + (i & 1) * ly.gs_bytes;
         {
-            const bool h2 = i + 2 < n_steps, h1 = i + 1 < n_steps;
+            const bool ho = i + F_OA < n_steps, hl = i + F_LA < n_steps;
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    ob2[j][e] = h2 ? load_obs(po, 2, j, e) : BNK_NONE;
-                    g1[j][e] = h1 ? load_val(po, 1, ob1[j][e], j, e) : 1.0;
+                    obr[j][e][NOB - 1] = ho ? load_obs(po, F_OA, j, e) : BNK_NONE;
+                    gr[j][e][NG - 1] = hl ? load_val(po, F_LA, obr[j][e][0], j, e) : 1.0;
                 }
             }
-            q1 = h1 ? (a.qrow ? a.qrow[STEP_AT(po, 1, ent)] : STEP_AT(po, 1, ent)) : -1;
+            qr[NG - 1] = hl ? (a.qrow ? a.qrow[STEP_AT(po, F_LA, ent)] : STEP_AT(po, F_LA, ent)) : -1;
         }
         // ---- from-above vector: D = P^T T (scaled by a power of two), or the prior at a root ----
         const int row_off = LY::TAB + (i & (FSTAGE - 1)) * LY::STAGE_BYTES + rowoff;
@@ -481,7 +510,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
             int e;
             const double scale = f_pow2_scale(mhi[j], e);
             const double D = rootstep ? prior_p : (acc0[j] + acc1[j]) * scale;
-            const double c0 = g0[j][0], c1 = g0[j][1];
+            const double c0 = gr[j][0][0], c1 = gr[j][1][0];
             U[j] = D * (c0 * c1);
             SM_D(gs_off + gsw[j] + p * 8) = U[j];
             // child slots never alias this step's own slot (tree_plan.cpp)
@@ -499,6 +528,7 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
         if ((i & (FCHUNK - 1)) == 0) f_issue_prog(a.down, n_steps, (i >> 5) + 1, sbase + LY::PROG);
         f_cp_async_commit();
         // ---- normalise and emit the posterior ----
+        const int q0 = qr[0];
         if (q0 >= 0 && a.out_post) {
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
@@ -508,11 +538,17 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
                 post_o[j][(size_t)(unsigned)q0 * row_stride] = U[j] * f_rcp(s);
             }
         }
-        q0 = q1;
+#pragma unroll
+        for (int k = 0; k < NG - 1; k++) qr[k] = qr[k + 1];
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
 #pragma unroll
-            for (int e = 0; e < 2; e++) { ob1[j][e] = ob2[j][e]; g0[j][e] = g1[j][e]; }
+            for (int e = 0; e < 2; e++) {
+#pragma unroll
+                for (int k = 0; k < NOB - 1; k++) obr[j][e][k] = obr[j][e][k + 1];
+#pragma unroll
+                for (int k = 0; k < NG - 1; k++) gr[j][e][k] = gr[j][e][k + 1];
+            }
         }
     }
 }
