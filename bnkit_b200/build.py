@@ -13,6 +13,7 @@ UNITS = [
     ("tables.cu", ["-fmad=false"]),
     ("sweeps.cu", []),
     ("sweeps_fast.cu", []),
+    ("sweeps_warp.cu", []),
     ("wide.cu", []),
     ("wide_general.cu", []),
     ("cherry.cu", []),

@@ -104,6 +104,13 @@ struct bnk_ws {
     std::vector<TileDesc> ctiles;          // expansion tiles of the cherry groups (16-column aligned starts)
     std::vector<std::pair<int, int>> chunk_ctiles;
     DevBuf<TileDesc> d_ctiles;
+    // warp-tiled walker (sweeps_warp.cu): tiles of one category, <= 6 * xw columns
+    std::vector<TileDesc> xtiles;
+    std::vector<std::pair<int, int>> chunk_xtiles;
+    DevBuf<TileDesc> d_xtiles;
+    int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
+    int walker_mode = 0;                   // BNK_WALKER: 0 auto (warp-tiled where eligible), 1 lean CTA walker
+    int cfg_xw = 0, cfg_xns = 0, cfg_xc = 0;  // BNK_WARP_W / BNK_WARP_NS / BNK_WARP_C (tuning knobs, tests)
     bool no_cherry = false;                // BNK_NO_CHERRY=1: height-1 level through the plain level kernel (A/B, tests)
     std::vector<std::pair<int, int>> chunk_wtiles, chunk_cols;  // per chunk: wide tile range, sorted column range
     int tile_cols = 0, cpt = 1, ncg = 0, threads = 0;
@@ -203,7 +210,7 @@ static void ws_free(bnk_ws *ws)
     for (auto *b : di) b->release();
     ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
     ws->d_up_n.release(); ws->d_down_n.release(); ws->d_up_child_n.release(); ws->d_down_child_n.release();
-    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
+    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_xtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
     if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
@@ -238,6 +245,10 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
+    if (const char *env = std::getenv("BNK_WALKER")) ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : 0;
+    if (const char *env = std::getenv("BNK_WARP_W")) ws->cfg_xw = std::atoi(env);
+    if (const char *env = std::getenv("BNK_WARP_NS")) ws->cfg_xns = std::atoi(env);
+    if (const char *env = std::getenv("BNK_WARP_C")) ws->cfg_xc = std::atoi(env);
     if (const char *env = std::getenv("BNK_WIDE_TPC")) ws->wide_tpc_max = std::max(1, std::atoi(env));  // tuning knob
     if (const char *env = std::getenv("BNK_TABLE_BUDGET_MB"))  // bytes of P(t) tables held at once (tests force several chunks)
         ws->table_budget = (size_t)std::max(1, std::atoi(env)) << 20;
@@ -401,6 +412,21 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     if (cats_per_chunk > 60000) cats_per_chunk = 60000;
     ws->chunks.clear(); ws->wtiles.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
     ws->cgroups.clear(); ws->chunk_cgroups.clear(); ws->chunk_crecs.clear(); ws->ctiles.clear(); ws->chunk_ctiles.clear();
+    ws->xtiles.clear(); ws->chunk_xtiles.clear();
+    {   // warp-tiled walker geometry: W consumer warps of 6 x C columns per CTA.  Every CTA of the grid should be
+        // resident at once (a walk is one long dependent chain per column), so prefer the W that fills the
+        // SMs most evenly: cost = rounds of CTAs per SM x warps per CTA.
+        ws->xc = (ws->cfg_xc >= 1 && ws->cfg_xc <= 3) ? ws->cfg_xc : 2;
+        const int cw = warp_walk_cols_per_warp(ws->xc);
+        int best_w = 2; int64_t best_cost = -1;
+        for (int w = 2; w <= 4 && w * cw <= 64; w++) {
+            int64_t nt = 0;
+            for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
+            const int64_t cost = ((nt + ws->sm_count - 1) / ws->sm_count) * w;
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_w = w; }
+        }
+        ws->xw = (ws->cfg_xw >= 1 && ws->cfg_xw <= 5 && ws->cfg_xw * cw <= 64) ? ws->cfg_xw : best_w;
+    }
     const int wt = wide_tile_cols(), cg = cherry_group_cols();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
         const int hi = std::min(ncat, lo + cats_per_chunk);
@@ -412,6 +438,18 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             for (int q = 0; q < nt; q++) {
                 const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
                 ws->wtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+            }
+        }
+        const int x0 = (int)ws->xtiles.size();
+        {
+            const int xt = ws->xw * warp_walk_cols_per_warp(ws->xc);
+            for (int k = lo; k < hi; k++) {
+                const int nc = cat_begin[k + 1] - cat_begin[k];
+                const int nt = (nc + xt - 1) / xt;
+                for (int q = 0; q < nt; q++) {
+                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                    ws->xtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+                }
             }
         }
         const int g0 = (int)ws->cgroups.size();
@@ -454,6 +492,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             ws->chunk_cgroups.push_back({g0, (int)ws->cgroups.size()});
             ws->chunk_crecs.push_back(crecs);
             ws->chunk_ctiles.push_back({ct0, (int)ws->ctiles.size()});
+            ws->chunk_xtiles.push_back({x0, (int)ws->xtiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
         }
     }
@@ -472,6 +511,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_wtiles, ws->wtiles, ws->stream));
     TRY(upload(ws->d_cgroups, ws->cgroups, ws->stream));
     TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
+    TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
     ws->rates_null = rates == nullptr;
@@ -593,6 +633,8 @@ struct WalkSetup {
     WalkLaunch wl;
     bool fast = false;    // lean kernels of sweeps_fast.cu apply
     bool hybrid = false;  // wide height levels run as level launches (wide.cu); the walker takes the narrow top
+    bool warp = false;    // fast, and the warp-tiled kernels of sweeps_warp.cu take the walk
+    int xw = 0, xc = 0, xns = 0, n_xtiles = 0;
     int tb_slots = 0;
 };
 
@@ -601,6 +643,7 @@ struct WalkSetup {
 static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down, const uint8_t *obs_s,
                       const uint8_t *present_s, WalkSetup &s)
 {
+    const size_t ci = (size_t)(&ck - ws->chunks.data());
     const int K = ws->K;
     std::memset(&s.a, 0, sizeof(s.a));
     const bnk_tree *t = ws->tree;
@@ -625,6 +668,23 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
     // lean kernels: nothing masked, evidence on childless nodes only, binary (or unary) nodes,
     // one category per tile, whole stack in shared memory
     s.fast = false; s.hybrid = false;
+    s.warp = false;
+    if (!general && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode == 0) {
+        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
+        const int slots = use_program(hybrid);
+        // ring stages: as many as let two CTAs share an SM (the grid is sized to be resident at once)
+        int ns = ws->cfg_xns >= 2 && ws->cfg_xns <= 8 ? ws->cfg_xns : 8;
+        if (!(ws->cfg_xns >= 2 && ws->cfg_xns <= 8))
+            while (ns > 3 && warp_walk_smem_bytes(ws->xw, ws->xc, ns, slots, want_down) > (size_t)ws->smem_optin / 2 - 1024) ns--;
+        if (warp_walk_smem_bytes(ws->xw, ws->xc, ns, slots, want_down) <= (size_t)ws->smem_optin) {
+            s.fast = true; s.warp = true; s.hybrid = hybrid;
+            s.xw = ws->xw; s.xc = ws->xc; s.xns = ns;
+            s.n_xtiles = ws->chunk_xtiles[ci].second - ws->chunk_xtiles[ci].first;
+            s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
+            s.a.smem_slots = slots;
+            return BNK_OK;
+        }
+    }
     if (!general && !ws->force_generic && t->max_children <= 2 && ck.ncat_max == 1) {
         const bool hybrid = t->wide_h > 0 && !ws->no_wide;
         const int slots = use_program(hybrid);
@@ -749,7 +809,8 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
                 TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
                     return gen ? launch_up_wide_gen(K, 0, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
             }
-            CUDA_TRY(s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
+            CUDA_TRY(s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+                            : s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;
             CUDA_TRY(cudaEventRecord(ws->ev[1][1], ws->stream));
             ws->ev_valid[1] = true;
@@ -900,12 +961,14 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
                 s.a.esum_wide = ws->d_esum_wide.p;
             }
         }
-        CUDA_TRY(s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
+        CUDA_TRY(s.warp ? launch_sum_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+                        : s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
         ws->launches++;
         CUDA_TRY(cudaEventRecord(ws->ev[3][1], ws->stream));
         ws->ev_valid[3] = true;
         if (want_post) {
             s.a.T_row = ws->d_PT.p;
+            s.a.T_aux = ws->d_P.p;
             s.a.out_post = d_out_post;
             s.a.qrow = (n_query < 0) ? nullptr : ws->d_qrow.p;
             if (s.hybrid) {
@@ -913,7 +976,8 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
                 s.a.tmsg = ws->d_tmsg.p;
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
-            CUDA_TRY(s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
+            CUDA_TRY(s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+                            : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;
             if (s.hybrid) {
                 w.tmsg = ws->d_tmsg.p; w.out_post = d_out_post; w.qrow = s.a.qrow;

@@ -45,6 +45,7 @@ struct WalkArgs {
     // tables of the current category chunk
     const double *T_row;  // matvec rows: L (joint up), P (sum up), PT (down)
     const double *T_col;  // lookups [obs][x]: LT (joint), PT (sum up / down)
+    const double *T_aux;  // warp-tiled down-sweep (sweeps_warp.cu): P, read as rows [p][x .. x + 3]
     const double *prior;  // log prior (joint) or prior (sum)
     // message stack: slots < smem_slots live in shared memory, the rest in spill[(slot - smem_slots)][ncols][K]
     int32_t smem_slots;
@@ -133,6 +134,15 @@ size_t fast_smem_bytes(int K, int cpt, int ncg, int slots);
 cudaError_t launch_joint_up_fast(const WalkLaunch &wl, const WalkArgs &a);
 cudaError_t launch_sum_up_fast(const WalkLaunch &wl, const WalkArgs &a);
 cudaError_t launch_sum_down_fast(const WalkLaunch &wl, const WalkArgs &a);
+
+// warp-tiled walker (sweeps_warp.cu): K = 20, same eligibility as the lean kernels; a.tiles = tiles of one
+// category and at most W * warp_walk_cols_per_warp(C) (<= 64) columns; W consumer warps (+ 1 producer warp),
+// C columns per lane, ns ring stages
+size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down);
+int warp_walk_cols_per_warp(int C);
+cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
+cudaError_t launch_sum_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
+cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
 
 struct TracebackArgs {
     const Step *down;

@@ -1,0 +1,692 @@
+// sweeps_warp.cu -- warp-tiled walker: the three tree sweeps for deep trees (and narrow tops), K = 20.
+//
+// Same walk programs, arithmetic and association order as sweeps_fast.cu; what changes is who owns what.
+// There a CTA owned a tile of columns, 20 threads shared a column (one output each) and every step of
+// the walk ended in a CTA barrier; on a 10,000-level caterpillar that cost ~400 issued instructions per
+// warp and step at 40 % issue utilisation (profiles/r1_v12_bench_caterpillar.json: 1.4 us per step).
+// Here
+//   * a WARP owns 6 x C columns; 5 lanes share a column and each computes 4 of the 20 outputs for C columns
+//     (C = 1..3 columns per lane, register-tiled), so one 128-bit shared-memory read of the node's table
+//     feeds 2 x C multiply-adds (or add/compare/selects).  Shared-memory wavefronts are what bounds a walk
+//     (profiles/r1_v13_*: a non-uniform LDS.128 costs four wavefronts, one per quarter-warp, however many
+//     lanes share an address), so what matters is bytes fetched per column: lane q owns outputs
+//     {2q, 2q+1, 10+2q, 11+2q}, which makes the five lanes of a column read 80 contiguous bytes of a table
+//     row per load (no bank conflict), and the table traffic is shared by the C columns of a lane;
+//   * warps never meet at a CTA barrier: the node's table, the tables of its childless children and (going
+//     down) the stored up-messages of its internal children arrive in a ring of shared-memory stages filled
+//     by a producer warp with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx), one full / empty
+//     mbarrier pair per stage; the observed states of childless children travel in the same stage (the
+//     producer requests them XPD steps ahead), so the consumers' loop contains no global load at all
+//     unless a child was handled by a wide level kernel;
+//   * the walk program itself streams through a second small ring (32-step chunks, bulk copies).
+// Requirements (the host falls back to sweeps_fast.cu / sweeps.cu otherwise): no presence mask, evidence
+// on childless nodes only, at most two children per node, one rate category per tile, whole message stack
+// in shared memory.
+#include "device_common.cuh"
+
+#include <cstddef>
+
+namespace bnk {
+
+namespace {
+constexpr int XK = 20;
+constexpr int XCW = 6;             // columns per warp (5 lanes each; lanes 30, 31 shadow lanes 25, 26)
+constexpr int XPD = 8;             // producer: observed states are requested this many steps ahead
+constexpr int XPB = 4;             // walk-program ring: chunks of 32 steps
+constexpr int XTAB = XK * XK * 8;  // one table, bytes
+constexpr int XGROW = XK + 2;      // padded row (doubles) of a warp's exchange buffer: 6 rows hit distinct banks
+constexpr int XPROG = 256;         // byte offsets inside dynamic shared memory: barriers first, ...
+constexpr int XSTAGE0 = XPROG + XPB * 32 * (int)sizeof(Step);
+constexpr int XMAXNS = 8, XMAXW = 5;
+
+constexpr int XOBS = 128;          // a stage starts with the observed states: 2 children x 64 tile columns
+// area of one child inside a stage: its table (childless) or, going down, the stored up-messages of the tile
+__host__ __device__ inline int x_child_bytes(int tile_cols, bool down) { return (down && tile_cols * XK * 8 > XTAB) ? tile_cols * XK * 8 : XTAB; }
+// stage = [observed states][table of the node][area of child 0][area of child 1]
+__host__ __device__ inline int x_stage_bytes(int chb) { return XOBS + XTAB + 2 * chb; }
+__host__ __device__ inline int x_warp_bytes(int C, int slots) { return 2 * XCW * C * XGROW * 8 + (slots + 1) * XCW * C * XK * 8; }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ double x_pow2_scale(int mhi, int &e)
+{
+    const int be = mhi >> 20;
+    if (be == 0) { e = 0; return 1.0; }
+    e = be - 1023;
+    return __hiloint2double((2046 - be) << 20, 0);
+}
+__device__ __forceinline__ double x_rcp(double s)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    r = fma(r, fma(-s, r, 1.0), r);
+    r = fma(r, fma(-s, r, 1.0), r);
+    return r;
+}
+
+#define XS_I32(off) (*reinterpret_cast<const int32_t *>(smem_raw + (off)))
+#define XS_D2(off) (*reinterpret_cast<double2 *>(smem_raw + (off)))
+#define XSTEP(po, member) XS_I32((po) + (int)offsetof(Step, member))
+
+struct XGeom {
+    int chb, stage_bytes;
+    unsigned bar_full, bar_empty, bar_prog;
+};
+
+// barriers + role split shared by the kernels
+__device__ __forceinline__ XGeom x_setup(unsigned sbase, int W, int ns, int chb)
+{
+    XGeom g;
+    g.chb = chb;
+    g.stage_bytes = x_stage_bytes(chb);
+    g.bar_full = sbase;
+    g.bar_empty = sbase + 8 * XMAXNS;
+    g.bar_prog = sbase + 16 * XMAXNS;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ns; s++) {
+            mbar_init(g.bar_full + 8 * s, 32);  // every producer lane arrives (lane 0 with the byte count)
+            mbar_init(g.bar_empty + 8 * s, W);  // lane 0 of every consumer warp
+        }
+        for (int b = 0; b < XPB; b++) mbar_init(g.bar_prog + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    return g;
+}
+
+// The producer warp.  DOWN = false: up-sweeps (tables from T_col); DOWN = true: node table from T_aux,
+// child tables from T_col, stored up-messages of walker-internal children from a.msg.
+template <bool DOWN>
+__device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &tile, const XGeom &g, unsigned char *smem_raw,
+                                           unsigned sbase, int ns, int lane)
+{
+    const Step *prog = DOWN ? a.down : a.up;
+    const int n_steps = a.n_steps;
+    const size_t ncols = (size_t)a.ncols;
+    const size_t cat_off = (size_t)tile.cat0 * a.n_nodes * (XK * XK);
+    const double *tab_node = (DOWN ? a.T_aux : a.T_col) + cat_off;
+    const double *tab_child = a.T_col + cat_off;
+    // lane l fetches the observed states of tile columns l and l + 32
+    const uint8_t *obs_a = a.obs + a.orig_col[tile.col0 + (lane < tile.ncols ? lane : tile.ncols - 1)];
+    const uint8_t *obs_b = a.obs + a.orig_col[tile.col0 + (lane + 32 < tile.ncols ? lane + 32 : tile.ncols - 1)];
+    const unsigned msg_bytes = (unsigned)tile.ncols * XK * 8;
+
+    auto issue_chunk = [&](int j) {
+        if (lane == 0 && j * 32 < n_steps) {
+            const int cnt = n_steps - j * 32 < 32 ? n_steps - j * 32 : 32;
+            const unsigned bar = g.bar_prog + (j & (XPB - 1)) * 8;
+            mbar_arrive_tx(bar, cnt * (unsigned)sizeof(Step));
+            bulk_g2s(sbase + XPROG + (j & (XPB - 1)) * 32 * (int)sizeof(Step), prog + (size_t)j * 32, cnt * (unsigned)sizeof(Step), bar);
+        }
+    };
+    int chunk_ready = -1;
+    auto need_chunk = [&](int j) {
+        while (chunk_ready < j) {
+            ++chunk_ready;
+            mbar_wait(g.bar_prog + (chunk_ready & (XPB - 1)) * 8, (chunk_ready >> 2) & 1);
+        }
+    };
+    // observed states of childless child e of step i: byte 0 = column `lane`, byte 1 = column `lane + 32`
+    auto fetch_obs = [&](int i, int e) -> int {
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
+        const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
+        if (!(cn >= 0 && ce < 0)) return BNK_NONE | (BNK_NONE << 8);
+        const size_t off = (size_t)(unsigned)cn * ncols;
+        return (int)obs_a[off] | ((int)obs_b[off] << 8);
+    };
+    issue_chunk(0);
+    issue_chunk(1);
+    need_chunk(0);
+    int o0[XPD], o1[XPD];
+#pragma unroll
+    for (int k = 0; k < XPD; k++) {
+        o0[k] = k < n_steps ? fetch_obs(k, 0) : 0;
+        o1[k] = k < n_steps ? fetch_obs(k, 1) : 0;
+    }
+    int s = 0, ph = 0;
+    for (int i0 = 0; i0 < n_steps; i0 += XPD) {
+#pragma unroll
+        for (int k = 0; k < XPD; k++) {
+            const int i = i0 + k;
+            if (i < n_steps) {
+                if ((i & 31) == 0) issue_chunk((i >> 5) + 2);
+                need_chunk(i >> 5);
+                if (i >= ns) mbar_wait(g.bar_empty + s * 8, ph ^ 1);
+                const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+                const int node = XSTEP(po, node), parent = XSTEP(po, parent);
+                const int cn0 = XSTEP(po, c_node[0]), cn1 = XSTEP(po, c_node[1]);
+                const int ce0 = XSTEP(po, c_ent[0]), ce1 = XSTEP(po, c_ent[1]);
+                const int cs0 = XSTEP(po, c_slot[0]), cs1 = XSTEP(po, c_slot[1]);
+                const int so = XSTAGE0 + s * g.stage_bytes;
+                smem_raw[so + lane] = (unsigned char)o0[k];
+                smem_raw[so + 32 + lane] = (unsigned char)(o0[k] >> 8);
+                smem_raw[so + 64 + lane] = (unsigned char)o1[k];
+                smem_raw[so + 96 + lane] = (unsigned char)(o1[k] >> 8);
+                const unsigned bar = g.bar_full + s * 8;
+                if (lane == 0) {
+                    const bool tn = parent >= 0;  // a root contracts with the unit table / uses the prior
+                    const bool t0 = cn0 >= 0 && ce0 < 0, t1 = cn1 >= 0 && ce1 < 0;
+                    const bool m0 = DOWN && ce0 >= 0 && cs0 != SLOT_WIDE, m1 = DOWN && ce1 >= 0 && cs1 != SLOT_WIDE;
+                    const unsigned bytes = (tn ? XTAB : 0) + (t0 ? XTAB : 0) + (t1 ? XTAB : 0) + (m0 ? msg_bytes : 0) + (m1 ? msg_bytes : 0);
+                    if (bytes) mbar_arrive_tx(bar, bytes); else mbar_arrive(bar);
+                    const unsigned stg = sbase + so;
+                    if (tn) bulk_g2s(stg + XOBS, tab_node + (size_t)(unsigned)node * (XK * XK), XTAB, bar);
+                    if (t0) bulk_g2s(stg + XOBS + XTAB, tab_child + (size_t)(unsigned)cn0 * (XK * XK), XTAB, bar);
+                    if (t1) bulk_g2s(stg + XOBS + XTAB + g.chb, tab_child + (size_t)(unsigned)cn1 * (XK * XK), XTAB, bar);
+                    if (m0) bulk_g2s(stg + XOBS + XTAB, a.msg + ((size_t)(unsigned)ce0 * ncols + tile.col0) * XK, msg_bytes, bar);
+                    if (m1) bulk_g2s(stg + XOBS + XTAB + g.chb, a.msg + ((size_t)(unsigned)ce1 * ncols + tile.col0) * XK, msg_bytes, bar);
+                } else {
+                    mbar_arrive(bar);
+                }
+                const int ip = i + XPD;
+                if (ip < n_steps) {
+                    need_chunk(ip >> 5);
+                    o0[k] = fetch_obs(ip, 0);
+                    o1[k] = fetch_obs(ip, 1);
+                }
+                if (++s == ns) { s = 0; ph ^= 1; }
+            }
+        }
+    }
+}
+
+// Lane geometry: lane = 5 c + q (c = 0..5, q = 0..4; lanes 30, 31 shadow lanes 25, 26).  Lane q owns the
+// outputs {2q, 2q+1} and {10+2q, 11+2q} of C columns: tile columns warp * 6C + j * 6 + c, j < C.
+template <int C>
+struct XLane {
+    int c, q, p0, p1;      // p0 = 2q, p1 = 10 + 2q
+    int lc[C], col[C], ocol[C];
+    __device__ XLane(const WalkArgs &a, const TileDesc &tile, int warp, int lane)
+    {
+        c = lane < 30 ? lane / 5 : 5;
+        q = lane < 30 ? lane - 5 * c : lane - 30;
+        p0 = 2 * q; p1 = 10 + 2 * q;
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            lc[j] = (warp * C + j) * XCW + c;
+            if (lc[j] >= tile.ncols) lc[j] = tile.ncols - 1;  // spare lanes shadow the tile's last column
+            col[j] = tile.col0 + lc[j];
+            ocol[j] = a.orig_col[col[j]];
+        }
+    }
+};
+
+// a lane's four entries of a 20-vector stored at byte offset `off`: v[0..1] = entries p0.., v[2..3] = entries p1..
+#define XLD4(v, off, q)                                                            \
+    do {                                                                           \
+        const double2 u_ = XS_D2((off) + (q) * 16), w_ = XS_D2((off) + 80 + (q) * 16); \
+        (v)[0] = u_.x; (v)[1] = u_.y; (v)[2] = w_.x; (v)[3] = w_.y;                \
+    } while (0)
+#define XST4(off, q, v)                                          \
+    do {                                                         \
+        XS_D2((off) + (q) * 16) = make_double2((v)[0], (v)[1]);  \
+        XS_D2((off) + 80 + (q) * 16) = make_double2((v)[2], (v)[3]); \
+    } while (0)
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// up-sweeps.  MODE 0: max-product in log space (joint), MODE 1: sum-product, linear, rescaled.
+// ------------------------------------------------------------------------------------
+template <int MODE, int C>
+__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const XGeom g = x_setup(sbase, W, ns, chb);
+    if (warp == W) {
+        x_producer<false>(a, tile, g, smem_raw, sbase, ns, lane);
+        return;
+    }
+    const XLane<C> L(a, tile, warp, lane);
+    const int q = L.q;
+    const int n_steps = a.n_steps;
+    const size_t ncols = (size_t)a.ncols;
+    const int wbase = XSTAGE0 + ns * g.stage_bytes + warp * x_warp_bytes(C, a.smem_slots);
+    const int gbuf_bytes = XCW * C * XGROW * 8;
+    const int stack0 = wbase + 2 * gbuf_bytes;
+    const int slot_bytes = XCW * C * XK * 8;
+    const int dummy = stack0 + a.smem_slots * slot_bytes;
+    int own[C], gsw[C];  // this lane's columns inside a stack slot / inside an exchange buffer
+#pragma unroll
+    for (int j = 0; j < C; j++) { own[j] = (j * XCW + L.c) * XK * 8; gsw[j] = (j * XCW + L.c) * XGROW * 8; }
+    const double ident = MODE == 0 ? 0.0 : 1.0;
+    const double prior4[4] = {a.prior[L.p0], a.prior[L.p0 + 1], a.prior[L.p1], a.prior[L.p1 + 1]};
+    int esum[C];
+    double logacc[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) { esum[j] = 0; logacc[j] = 0.0; }
+
+    int s = 0, ph = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
+        const bool rootstep = XSTEP(po, parent) < 0;
+        const int so = XSTAGE0 + s * g.stage_bytes;
+        mbar_wait(g.bar_full + s * 8, ph);
+        // ---- the (at most two) children ----
+        double cv[C][2][4];
+        bool isob[C][2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
+            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
+            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                isob[j][e] = false;
+                if (cs >= 0) {  // message left on this warp's stack
+                    XLD4(cv[j][e], stack0 + cs * slot_bytes + own[j], q);
+                } else if (cs == SLOT_WIDE) {  // message a wide level kernel left in HBM, [ent][K][ncols]
+                    const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + L.col[j];
+                    cv[j][e][0] = src[(size_t)L.p0 * ncols]; cv[j][e][1] = src[(size_t)(L.p0 + 1) * ncols];
+                    cv[j][e][2] = src[(size_t)L.p1 * ncols]; cv[j][e][3] = src[(size_t)(L.p1 + 1) * ncols];
+                } else if (cn >= 0) {  // childless child: a row of its transposed table, picked by the observed state
+                    const int tb = so + XOBS + XTAB + e * g.chb;
+                    const int ob = smem_raw[so + e * 64 + L.lc[j]];
+                    if (ob != BNK_NONE) {
+                        XLD4(cv[j][e], tb + ob * (XK * 8), q);
+                        isob[j][e] = true;
+                    } else {  // uninstantiated childless node: maximise / marginalise its own state
+                        XLD4(cv[j][e], tb, q);
+                        for (int x = 1; x < XK; x++) {
+                            double t4[4];
+                            XLD4(t4, tb + x * (XK * 8), q);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                if (MODE == 0) cv[j][e][k] = t4[k] > cv[j][e][k] ? t4[k] : cv[j][e][k];
+                                else cv[j][e][k] += t4[k];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) cv[j][e][k] = ident;
+                }
+            }
+        }
+        const int gb = wbase + (i & 1) * gbuf_bytes;
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            // a root combines [prior, observed children, unobserved children] (the order the factors sit in the
+            // reference's bucket); with one child of each kind that fixes the association
+            const bool swap = MODE == 0 && rootstep && !isob[j][0] && isob[j][1];
+            double G[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double c0 = swap ? cv[j][1][k] : cv[j][0][k], c1 = swap ? cv[j][0][k] : cv[j][1][k];
+                if (MODE == 0) G[k] = ((rootstep ? prior4[k] : 0.0) + c0) + c1;
+                else G[k] = ((rootstep ? prior4[k] : 1.0) * c0) * c1;
+            }
+            XST4(gb + gsw[j], q, G);
+        }
+        __syncwarp();
+        // ---- contract with the node's table: out[p] = op_x T[x][p] (.) G[x] for the lane's four p ----
+        const int tv = so + XOBS;
+        const int sdst = slot >= 0 ? stack0 + slot * slot_bytes : dummy;
+        if (MODE == 0) {
+            double best[C][4];
+            int bi[C][4];
+#pragma unroll
+            for (int j = 0; j < C; j++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) { best[j][k] = -CUDART_INF; bi[j][k] = 0; }
+            if (!rootstep) {
+#pragma unroll
+                for (int x2 = 0; x2 < XK / 2; x2++) {
+                    double2 gg[C];
+#pragma unroll
+                    for (int j = 0; j < C; j++) gg[j] = XS_D2(gb + gsw[j] + x2 * 16);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int x = 2 * x2 + h;
+                        double t4[4];
+                        XLD4(t4, tv + x * (XK * 8), q);
+#pragma unroll
+                        for (int j = 0; j < C; j++) {
+                            const double gx = h == 0 ? gg[j].x : gg[j].y;
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const double val = t4[k] + gx;
+                                const bool t = val > best[j][k];
+                                best[j][k] = t ? val : best[j][k];
+                                bi[j][k] = t ? x : bi[j][k];
+                            }
+                        }
+                    }
+                }
+            } else {  // unit table: every output is max_x G[x]
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    double b = -CUDART_INF;
+                    int bx = 0;
+#pragma unroll
+                    for (int x2 = 0; x2 < XK / 2; x2++) {
+                        const double2 gg = XS_D2(gb + gsw[j] + x2 * 16);
+                        const double v0 = 0.0 + gg.x, v1 = 0.0 + gg.y;
+                        if (v0 > b) { b = v0; bx = 2 * x2; }
+                        if (v1 > b) { b = v1; bx = 2 * x2 + 1; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { best[j][k] = b; bi[j][k] = bx; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                XST4(sdst + own[j], q, best[j]);
+                uint8_t *pr = a.ptr + ((size_t)(unsigned)ent * ncols + L.col[j]) * XK;
+                *reinterpret_cast<uint16_t *>(pr + L.p0) = (uint16_t)(bi[j][0] | (bi[j][1] << 8));
+                *reinterpret_cast<uint16_t *>(pr + L.p1) = (uint16_t)(bi[j][2] | (bi[j][3] << 8));
+            }
+        } else {
+            double acc[C][4], acb[C][4];
+            int mhi[C];
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                mhi[j] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { acc[j][k] = 0.0; acb[j][k] = 0.0; }
+            }
+            if (!rootstep) {
+#pragma unroll
+                for (int x2 = 0; x2 < XK / 2; x2++) {
+                    double ta[4], tb4[4];
+                    XLD4(ta, tv + (2 * x2) * (XK * 8), q);
+                    XLD4(tb4, tv + (2 * x2 + 1) * (XK * 8), q);
+#pragma unroll
+                    for (int j = 0; j < C; j++) {
+                        const double2 gg = XS_D2(gb + gsw[j] + x2 * 16);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            acc[j][k] = fma(ta[k], gg.x, acc[j][k]);
+                            acb[j][k] = fma(tb4[k], gg.y, acb[j][k]);
+                        }
+                        mhi[j] = max(mhi[j], max(__double2hiint(gg.x), __double2hiint(gg.y)));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+#pragma unroll
+                    for (int x2 = 0; x2 < XK / 2; x2++) {
+                        const double2 gg = XS_D2(gb + gsw[j] + x2 * 16);
+                        acc[j][0] += gg.x; acb[j][0] += gg.y;
+                        mhi[j] = max(mhi[j], max(__double2hiint(gg.x), __double2hiint(gg.y)));
+                    }
+#pragma unroll
+                    for (int k = 1; k < 4; k++) { acc[j][k] = acc[j][0]; acb[j][k] = acb[j][0]; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                int e;
+                const double scale = x_pow2_scale(mhi[j], e);
+                double m[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) m[k] = (acc[j][k] + acb[j][k]) * scale;
+                esum[j] += e;
+                XST4(sdst + own[j], q, m);
+                if (rootstep) logacc[j] += log(m[0]);
+                else if (a.msg) {
+                    double *dst = a.msg + ((size_t)(unsigned)ent * ncols + L.col[j]) * XK;
+                    *reinterpret_cast<double2 *>(dst + L.p0) = make_double2(m[0], m[1]);
+                    *reinterpret_cast<double2 *>(dst + L.p1) = make_double2(m[2], m[3]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
+        if (++s == ns) { s = 0; ph ^= 1; }
+    }
+    if (MODE == 1 && a.out_logl && q == 0) {
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const int ew = a.esum_wide ? a.esum_wide[L.col[j]] : 0;
+            a.out_logl[L.ocol[j]] = logacc[j] + (double)(esum[j] + ew) * 0.693147180559945309417232121458;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// down-sweep (see sweeps.cu for the recurrences): from-above vector D = P^T T, posterior
+// D * prod(children) normalised, T_child = D * prod(siblings)
+// ------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const XGeom g = x_setup(sbase, W, ns, chb);
+    if (warp == W) {
+        x_producer<true>(a, tile, g, smem_raw, sbase, ns, lane);
+        return;
+    }
+    const XLane<C> L(a, tile, warp, lane);
+    const int q = L.q;
+    const int n_steps = a.n_steps;
+    const size_t ncols = (size_t)a.ncols;
+    const int wbase = XSTAGE0 + ns * g.stage_bytes + warp * x_warp_bytes(C, a.smem_slots);
+    const int gbuf_bytes = XCW * C * XGROW * 8;
+    const int stack0 = wbase + 2 * gbuf_bytes;
+    const int slot_bytes = XCW * C * XK * 8;
+    const int dummy = stack0 + a.smem_slots * slot_bytes;
+    int own[C], gsw[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) { own[j] = (j * XCW + L.c) * XK * 8; gsw[j] = (j * XCW + L.c) * XGROW * 8; }
+    const double prior4[4] = {a.prior[L.p0], a.prior[L.p0 + 1], a.prior[L.p1], a.prior[L.p1 + 1]};
+
+    int s = 0, ph = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
+        const bool rootstep = XSTEP(po, parent) < 0;
+        const int so = XSTAGE0 + s * g.stage_bytes;
+        const int tsrc = slot >= 0 ? stack0 + slot * slot_bytes : dummy;
+        mbar_wait(g.bar_full + s * 8, ph);
+        // ---- from-above vector of this node: D[x] = sum_p P[p][x] T[p], scaled by a power of two ----
+        double D[C][4];
+        if (!rootstep) {
+            const int tv = so + XOBS;
+            double acc[C][4], acb[C][4];
+            int mhi[C];
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                mhi[j] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { acc[j][k] = 0.0; acb[j][k] = 0.0; }
+            }
+#pragma unroll
+            for (int x2 = 0; x2 < XK / 2; x2++) {
+                double ta[4], tb4[4];
+                XLD4(ta, tv + (2 * x2) * (XK * 8), q);
+                XLD4(tb4, tv + (2 * x2 + 1) * (XK * 8), q);
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    const double2 tt = XS_D2(tsrc + own[j] + x2 * 16);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        acc[j][k] = fma(ta[k], tt.x, acc[j][k]);
+                        acb[j][k] = fma(tb4[k], tt.y, acb[j][k]);
+                    }
+                    mhi[j] = max(mhi[j], max(__double2hiint(tt.x), __double2hiint(tt.y)));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                int e;
+                const double scale = x_pow2_scale(mhi[j], e);
+#pragma unroll
+                for (int k = 0; k < 4; k++) D[j][k] = (acc[j][k] + acb[j][k]) * scale;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; j++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) D[j][k] = prior4[k];
+        }
+        // ---- children: stored up-message (internal), table row (observed childless), row sums, or 1 ----
+        double cv[C][2][4];
+        int cslot[2], cent[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
+            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
+            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
+            cslot[e] = cs; cent[e] = ce;
+            const int area = so + XOBS + XTAB + e * g.chb;
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                if (cs == SLOT_WIDE) {
+                    const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + L.col[j];
+                    cv[j][e][0] = src[(size_t)L.p0 * ncols]; cv[j][e][1] = src[(size_t)(L.p0 + 1) * ncols];
+                    cv[j][e][2] = src[(size_t)L.p1 * ncols]; cv[j][e][3] = src[(size_t)(L.p1 + 1) * ncols];
+                } else if (ce >= 0) {  // walker-internal child: its up-message came with the stage, [tile column][K]
+                    XLD4(cv[j][e], area + L.lc[j] * (XK * 8), q);
+                } else if (cn >= 0) {
+                    const int ob = smem_raw[so + e * 64 + L.lc[j]];
+                    if (ob != BNK_NONE) {
+                        XLD4(cv[j][e], area + ob * (XK * 8), q);
+                    } else {
+                        cv[j][e][0] = cv[j][e][1] = cv[j][e][2] = cv[j][e][3] = 0.0;
+                        for (int x = 0; x < XK; x++) {
+                            double t4[4];
+                            XLD4(t4, area + x * (XK * 8), q);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) cv[j][e][k] += t4[k];
+                        }
+                    }
+                } else {
+                    cv[j][e][0] = cv[j][e][1] = cv[j][e][2] = cv[j][e][3] = 1.0;
+                }
+            }
+        }
+        const int gb = wbase + (i & 1) * gbuf_bytes;
+        double U[C][4], T0[C][4], T1[C][4];
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                U[j][k] = D[j][k] * (cv[j][0][k] * cv[j][1][k]);
+                T0[j][k] = D[j][k] * cv[j][1][k];
+                T1[j][k] = D[j][k] * cv[j][0][k];
+            }
+            XST4(gb + gsw[j], q, U[j]);
+        }
+        // every lane has read this node's from-above vector before the barrier; the children's slots never alias
+        // this step's own slot (tree_plan.cpp), and they are written after it
+        __syncwarp();
+        {
+            const int d0 = cslot[0] >= 0 ? stack0 + cslot[0] * slot_bytes : dummy;
+            const int d1 = cslot[1] >= 0 ? stack0 + cslot[1] * slot_bytes : dummy;
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                XST4(d0 + own[j], q, T0[j]);
+                XST4(d1 + own[j], q, T1[j]);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    if (cslot[e] == SLOT_WIDE) {  // handed to the wide level kernels through HBM, [ent][K][ncols]
+                        double *dst = a.tmsg + (size_t)(unsigned)cent[e] * (ncols * XK) + L.col[j];
+                        const double *Tv = e == 0 ? T0[j] : T1[j];
+                        dst[(size_t)L.p0 * ncols] = Tv[0]; dst[(size_t)(L.p0 + 1) * ncols] = Tv[1];
+                        dst[(size_t)L.p1 * ncols] = Tv[2]; dst[(size_t)(L.p1 + 1) * ncols] = Tv[3];
+                    }
+                }
+            }
+        }
+        // ---- normalise and emit the posterior ----
+        const int q0 = a.qrow ? a.qrow[ent] : ent;
+        if (a.out_post && q0 >= 0) {
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                double sum = 0.0;
+#pragma unroll
+                for (int x2 = 0; x2 < XK / 2; x2++) { const double2 gg = XS_D2(gb + gsw[j] + x2 * 16); sum += gg.x; sum += gg.y; }
+                const double r = x_rcp(sum);
+                double *dst = a.out_post + ((size_t)(unsigned)q0 * ncols + L.ocol[j]) * XK;
+                *reinterpret_cast<double2 *>(dst + L.p0) = make_double2(U[j][0] * r, U[j][1] * r);
+                *reinterpret_cast<double2 *>(dst + L.p1) = make_double2(U[j][2] * r, U[j][3] * r);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
+        if (++s == ns) { s = 0; ph ^= 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+int warp_walk_cols_per_warp(int C) { return XCW * C; }
+size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down)
+{
+    return (size_t)XSTAGE0 + (size_t)ns * x_stage_bytes(x_child_bytes(W * XCW * C, down)) + (size_t)W * x_warp_bytes(C, slots);
+}
+
+template <typename KernelT>
+static cudaError_t launch_warp(KernelT kern, const WalkArgs &a, int n_tiles, int W, int C, int ns, bool down, cudaStream_t st)
+{
+    if (W < 1 || W > XMAXW || ns < 2 || ns > XMAXNS || W * XCW * C > 64) return cudaErrorInvalidValue;
+    const size_t smem = warp_walk_smem_bytes(W, C, ns, a.smem_slots, down);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<n_tiles, (W + 1) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * XCW * C, down));
+    return cudaGetLastError();
+}
+cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
+{
+    if (C == 1) return launch_warp(up_warp_kernel<0, 1>, a, n_tiles, W, C, ns, false, st);
+    if (C == 2) return launch_warp(up_warp_kernel<0, 2>, a, n_tiles, W, C, ns, false, st);
+    if (C == 3) return launch_warp(up_warp_kernel<0, 3>, a, n_tiles, W, C, ns, false, st);
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_sum_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
+{
+    if (C == 1) return launch_warp(up_warp_kernel<1, 1>, a, n_tiles, W, C, ns, false, st);
+    if (C == 2) return launch_warp(up_warp_kernel<1, 2>, a, n_tiles, W, C, ns, false, st);
+    if (C == 3) return launch_warp(up_warp_kernel<1, 3>, a, n_tiles, W, C, ns, false, st);
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
+{
+    if (C == 1) return launch_warp(down_warp_kernel<1>, a, n_tiles, W, C, ns, true, st);
+    if (C == 2) return launch_warp(down_warp_kernel<2>, a, n_tiles, W, C, ns, true, st);
+    if (C == 3) return launch_warp(down_warp_kernel<3>, a, n_tiles, W, C, ns, true, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace bnk

@@ -111,14 +111,66 @@ def test_ties_go_to_lowest_state(bnk, oracle):
 
 
 @pytest.mark.parametrize("tile_cols,cpt", [(4, 1), (7, 1), (16, 2), (38, 1), (30, 4), (64, 2), (17, -1), (20, -2), (-12, 2), (-30, 1)])
-def test_tile_geometries(bnk, oracle, tile_cols, cpt):
+def test_tile_geometries(bnk, oracle, tile_cols, cpt, monkeypatch):
     """cpt < 0 forces the general kernels on inputs the lean kernels would otherwise take;
-    tile_cols < 0 keeps the whole tree in the column-owned walker (no wide level launches)."""
+    tile_cols < 0 keeps the whole tree in the column-owned walker (no wide level launches).
+    The geometry applies to the CTA-tiled walkers, so the warp-tiled one is switched off here."""
+    monkeypatch.setenv("BNK_WALKER", "lean")
     rng = np.random.default_rng(16)
     rates = rng.choice([0.3, 1.0, 2.5], size=257)
     _run_case(bnk, oracle, "LG", rng, 50, 257, rates=rates, tile_cols=tile_cols, cpt=cpt)
     _run_case(bnk, oracle, "LG", rng, 300, 150, rates=rates[:150], tile_cols=tile_cols, cpt=cpt)   # has wide levels
     _run_case(bnk, oracle, "LG", rng, 21, 100, gap=0.5, mask=True, tile_cols=tile_cols, cpt=cpt)
+
+
+@pytest.mark.parametrize("env", [{}, {"BNK_WARP_W": "2", "BNK_WARP_NS": "2", "BNK_WARP_C": "1"},
+                                 {"BNK_WARP_W": "3", "BNK_WARP_NS": "5", "BNK_WARP_C": "3"},
+                                 {"BNK_WARP_W": "4", "BNK_WARP_NS": "8", "BNK_WARP_C": "2"},
+                                 {"BNK_WARP_W": "5", "BNK_WARP_NS": "3", "BNK_WARP_C": "1"},
+                                 {"BNK_WARP_W": "1", "BNK_WARP_NS": "4", "BNK_WARP_C": "2"}, {"BNK_WALKER": "lean"}])
+def test_warp_tiled_walker(bnk, oracle, env, monkeypatch):
+    """sweeps_warp.cu (warp-owned columns, TMA-fed stage ring) against the oracle for every CTA shape and ring
+    depth, and against the lean CTA walker: deep chains (> 4 program chunks), category tiles narrower than a
+    warp, uninstantiated childless nodes without a mask, hybrid trees (children handed over by the level
+    kernels), whole trees in the walker, forests."""
+    from bnkit_b200 import synth
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(31)
+    m, om = bnk.Model("LG"), oracle.Model("LG")
+    rates5 = rng.choice([0.2, 0.7, 1.0, 1.9, 4.0], size=77, p=[0.05, 0.3, 0.3, 0.3, 0.05])
+    cases = []
+    parent, dist = synth.caterpillar_tree(333, seed=5)
+    cases.append((parent, dist, random_obs(rng, parent, 77, 20, few_states=5), rates5, 0))
+    cases.append((parent, dist, random_obs(rng, parent, 77, 20, gap_prob=0.2), None, 0))
+    parent, dist = random_tree(rng, 300, zero_branch_prob=0.05)
+    cases.append((parent, dist, random_obs(rng, parent, 77, 20, gap_prob=0.05), rates5, 0))    # hybrid
+    cases.append((parent, dist, random_obs(rng, parent, 77, 20), rates5, -8))                   # walker only
+    pa, da = random_tree(rng, 40)
+    pb, db = synth.caterpillar_tree(25, seed=6)
+    parent = np.concatenate([pa, np.where(pb < 0, -1, pb + len(pa))]).astype(np.int32)          # two roots
+    dist = np.concatenate([da, db])
+    cases.append((parent, dist, random_obs(rng, parent, 13, 20, gap_prob=0.1), None, 0))
+    for parent, dist, obs, rates, tc in cases:
+        n_cols = obs.shape[1]
+        tree = bnk.Tree(parent, dist)
+        ws = bnk.Workspace(m, tree, n_cols)
+        if tc:
+            ws.configure(tc, 0)
+        ws.set_rates(n_cols, rates)
+        got = ws.joint(obs)
+        want = oracle.fast_joint(om, parent, dist, obs, None, rates, nthreads=4)
+        assert np.array_equal(got, want), "joint states differ at %d of %d" % ((got != want).sum(), got.size)
+        post, logl = ws.marginal(obs)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, None, rates, nthreads=4)
+        _post_close(post, wpost[tree.internal_nodes()])
+        assert np.allclose(logl, wlogl, rtol=TOL, atol=1e-12)
+        l2, tot = ws.loglik(obs)
+        assert np.allclose(l2, wlogl, rtol=TOL, atol=1e-12) and np.isclose(tot, wlogl.sum(), rtol=TOL)
+        q = tree.internal_nodes()[::7]
+        p2, _ = ws.marginal(obs, query=q, want_logl=False)
+        assert np.array_equal(np.isnan(p2), np.isnan(post[::7])) and np.allclose(p2, post[::7], rtol=1e-12, atol=0, equal_nan=True)
+        ws.close()
 
 
 def test_deep_caterpillar_and_spill(bnk, oracle):
