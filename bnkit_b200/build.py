@@ -18,6 +18,8 @@ UNITS = [
     ("wide_general.cu", []),
     ("cherry.cu", []),
     ("traceback.cu", []),
+    ("bep.cu", []),
+    ("bep_api.cu", []),
     ("api.cu", []),
     ("subst_model.cpp", ["-fmad=false"]),
     ("tree_plan.cpp", []),

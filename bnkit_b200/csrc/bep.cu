@@ -1,0 +1,248 @@
+// bep.cu -- bi-directional edge parsimony (BEP), the reference's default indel inference: which ancestors
+// exist in which alignment column.  It is the step right before the substitution-model sweeps:
+// its result is the per-column presence mask those sweeps take.
+//
+// Reference: asr.Prediction.PredictByBidirEdgeParsimony (src/asr/Prediction.java:1443-1524) builds, for every
+// column i in -1..nPos and both directions, a TreeInstance whose leaf values are "the next (previous) occupied
+// column of this sequence" (POGTree.getEdgeInstance, src/dat/pog/POGTree.java:450-487) and runs
+// asr.Parsimony on it (unit-cost Sankoff keeping ALL optimal states, src/asr/Parsimony.java:215-412), one job
+// per instance on a thread pool (ThreadedDecorators).  The instances are independent: here one THREAD owns one
+// instance and the whole tree, lanes of a warp own neighbouring columns, so every load and store of the
+// per-node state is a coalesced row.
+//
+// Unit costs make the Sankoff tables collapse to bit sets.  With m_c = min_j S_c(j) a child contributes
+// min(S_c(i), m_c + 1) = m_c + [i not in A_c] to its parent's score for state i, where A_c is the child's arg-min
+// set, so S_b(i) = sum_c m_c + #{c : i not in A_c}: only A (score == min) and B (score == min + 1) are ever
+// needed.  Forward: count, per state, the children whose A misses it (bit-sliced counters), A_b / B_b = states at
+// the lowest / next count.  Backward (all optimal states, Parsimony.java:327-389): opt_root = A_root and
+//   opt_c = (opt_b & (A_c | B_c)) | (A_c if opt_b has a state outside A_c)
+// which is exactly the union over parent states i of the child states j minimising S_c(j) + [i != j].
+// oracle/bep.py keeps the reference's explicit score tables and traceback lists; tests compare the two.
+#include "bep.cuh"
+
+namespace bnk {
+
+
+// next / prev occupied column of every childless node, extended index e = column + 1 in 0 .. n_pos + 1:
+//   nxt[leaf][e] (e <= n_pos)  = POGTree.getEdgeInstance(e - 1, forward)  for that leaf
+//   prv[leaf][e] (e >= 1)      = POGTree.getEdgeInstance(e - 1, backward)
+__global__ void bep_next_prev_kernel(const uint8_t *obs, const int32_t *leaf_nodes, int n_leaves, int n_pos, int32_t *nxt,
+                                     int32_t *prv)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_leaves) return;
+    const uint8_t *row = obs + (size_t)leaf_nodes[l] * n_pos;
+    int32_t *nx = nxt + (size_t)l * (n_pos + 2), *pv = prv + (size_t)l * (n_pos + 2);
+    int cur = BEP_NONE;  // next occupied column seen so far, scanning right to left
+    for (int c = n_pos - 1; c >= 0; c--) {
+        const bool occ = row[c] != BNK_NONE;
+        nx[c + 1] = occ ? (cur == BEP_NONE ? n_pos : cur) : BEP_NONE;
+        if (occ) cur = c;
+    }
+    nx[0] = cur;               // column -1: the first occupied column (none: the sequence is empty)
+    nx[n_pos + 1] = BEP_NONE;  // (nPos, forward) is never instantiated
+    cur = BEP_NONE;
+    for (int c = 0; c < n_pos; c++) {
+        const bool occ = row[c] != BNK_NONE;
+        pv[c + 1] = occ ? (cur == BEP_NONE ? -1 : cur) : BEP_NONE;
+        if (occ) cur = c;
+    }
+    pv[n_pos + 1] = cur;
+    pv[0] = BEP_NONE;
+}
+
+
+__device__ __forceinline__ int bep_leaf_value(const BepArgs &a, int leaf, int e, bool fwd)
+{
+    return (fwd ? a.nxt : a.prv)[(size_t)leaf * (a.n_pos + 2) + e];
+}
+
+// distinct non-null leaf values of each instance, in first-occurrence order over the leaves (TreeInstance ctor)
+__global__ void bep_dict_kernel(const BepArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_inst) return;
+    const int e = a.inst_e[t];
+    const bool fwd = a.inst_fwd[t] != 0;
+    int n = 0;
+    for (int l = 0; l < a.n_leaves; l++) {
+        const int v = bep_leaf_value(a, l, e, fwd);
+        if (v == BEP_NONE) continue;
+        int k = 0;
+        while (k < n && a.dict[(size_t)k * a.n_inst + t] != v) k++;
+        if (k == n) {
+            if (n < a.max_sym) a.dict[(size_t)n * a.n_inst + t] = v;
+            n++;
+        }
+    }
+    if (n > a.max_sym) { atomicOr(a.flag, 1); n = a.max_sym; }
+    a.nsym[t] = n;
+}
+
+// symbol bit of a childless node: its value's dictionary index, the NULL symbol, or "every state costs nothing"
+template <int W>
+__device__ __forceinline__ void bep_leaf_set(const BepArgs &a, int t, int leaf, int e, bool fwd, int n, const uint32_t *valid,
+                                             uint32_t *out)
+{
+#pragma unroll
+    for (int w = 0; w < W; w++) out[w] = 0;
+    const int v = bep_leaf_value(a, leaf, e, fwd);
+    if (v == BEP_NONE) {
+        if (a.recode_null) out[n >> 5] |= 1u << (n & 31);  // NULL = symbol n
+        else {
+#pragma unroll
+            for (int w = 0; w < W; w++) out[w] = valid[w];  // un-instantiated leaf (Parsimony.java:259-264)
+        }
+        return;
+    }
+    int k = 0;
+    while (k < n && a.dict[(size_t)k * a.n_inst + t] != v) k++;
+    out[k >> 5] |= 1u << (k & 31);
+}
+
+template <int W>
+__global__ void bep_forward_kernel(const BepArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_inst) return;
+    const int e = a.inst_e[t];
+    const bool fwd = a.inst_fwd[t] != 0;
+    const int n = a.nsym[t];
+    const int ntot = n + (a.recode_null ? 1 : 0);
+    uint32_t valid[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        const int lo = w * 32;
+        valid[w] = ntot >= lo + 32 ? 0xffffffffu : (ntot > lo ? (1u << (ntot - lo)) - 1u : 0u);
+    }
+    const size_t ni = (size_t)a.n_inst;
+    constexpr int P = 6;  // bit-sliced counters: up to 63 children per node
+    for (int v = a.n_nodes - 1; v >= 0; v--) {
+        const int ent = a.ent_of_node[v];
+        if (ent < 0) continue;
+        uint32_t plane[P][W];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+#pragma unroll
+            for (int w = 0; w < W; w++) plane[p][w] = 0;
+        const int c0 = a.first[v], c1 = a.first[v + 1];
+        for (int ci = c0; ci < c1; ci++) {
+            const int u = a.kids[ci];
+            const int ue = a.ent_of_node[u];
+            uint32_t Ac[W];
+            if (ue >= 0) {
+#pragma unroll
+                for (int w = 0; w < W; w++) Ac[w] = a.A[((size_t)ue * W + w) * ni + t];
+            } else {
+                bep_leaf_set<W>(a, t, a.leaf_of_node[u], e, fwd, n, valid, Ac);
+            }
+            // counters += (state not in A_c)
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                uint32_t carry = ~Ac[w] & valid[w];
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const uint32_t s = plane[p][w] ^ carry;
+                    carry &= plane[p][w];
+                    plane[p][w] = s;
+                }
+            }
+        }
+        // states at the lowest count, and at the next one
+        const int nch = c1 - c0;
+        uint32_t Ab[W], Bb[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) { Ab[w] = 0; Bb[w] = 0; }
+        for (int k = 0; k <= nch; k++) {
+            uint32_t any = 0, m[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                m[w] = valid[w];
+#pragma unroll
+                for (int p = 0; p < P; p++) m[w] &= ((k >> p) & 1) ? plane[p][w] : ~plane[p][w];
+                any |= m[w];
+            }
+            if (any) {
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    Ab[w] = m[w];
+                    uint32_t m1 = valid[w];
+#pragma unroll
+                    for (int p = 0; p < P; p++) m1 &= (((k + 1) >> p) & 1) ? plane[p][w] : ~plane[p][w];
+                    Bb[w] = k + 1 <= nch ? m1 : 0u;
+                }
+                break;
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            a.A[((size_t)ent * W + w) * ni + t] = Ab[w];
+            a.B[((size_t)ent * W + w) * ni + t] = Bb[w];
+        }
+    }
+}
+
+// all optimal states of every internal node, root first (node 0; parent[v] < v); written over B, NULL symbol removed
+// at the end by the host (it has to take part in the propagation)
+template <int W>
+__global__ void bep_backward_kernel(const BepArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_inst) return;
+    const size_t ni = (size_t)a.n_inst;
+    for (int v = 0; v < a.n_nodes; v++) {
+        const int ent = a.ent_of_node[v];
+        if (ent < 0) continue;
+        uint32_t Av[W], Bv[W], opt[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) { Av[w] = a.A[((size_t)ent * W + w) * ni + t]; Bv[w] = a.B[((size_t)ent * W + w) * ni + t]; }
+        const int par = a.parent[v];
+        if (par < 0) {
+#pragma unroll
+            for (int w = 0; w < W; w++) opt[w] = Av[w];
+        } else {
+            const int pe = a.ent_of_node[par];
+            uint32_t outside = 0, ob[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) { ob[w] = a.B[((size_t)pe * W + w) * ni + t]; outside |= ob[w] & ~Av[w]; }
+#pragma unroll
+            for (int w = 0; w < W; w++) opt[w] = (ob[w] & (Av[w] | Bv[w])) | (outside ? Av[w] : 0u);
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) a.B[((size_t)ent * W + w) * ni + t] = opt[w];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-callable launchers (bep_host.cpp)
+// ---------------------------------------------------------------------------------------------------
+cudaError_t bep_launch_next_prev(const uint8_t *obs, const int32_t *leaf_nodes, int n_leaves, int n_pos, int32_t *nxt, int32_t *prv,
+                                 cudaStream_t st)
+{
+    if (n_leaves == 0) return cudaSuccess;
+    bep_next_prev_kernel<<<(n_leaves + 127) / 128, 128, 0, st>>>(obs, leaf_nodes, n_leaves, n_pos, nxt, prv);
+    return cudaGetLastError();
+}
+
+cudaError_t bep_launch_dict(const BepArgs &a, cudaStream_t st)
+{
+    if (a.n_inst == 0) return cudaSuccess;
+    bep_dict_kernel<<<(a.n_inst + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t bep_launch_sweeps(const BepArgs &a, int W, cudaStream_t st)
+{
+    if (a.n_inst == 0) return cudaSuccess;
+    const int grid = (a.n_inst + 63) / 64;
+    switch (W) {
+    case 1: bep_forward_kernel<1><<<grid, 64, 0, st>>>(a); bep_backward_kernel<1><<<grid, 64, 0, st>>>(a); break;
+    case 2: bep_forward_kernel<2><<<grid, 64, 0, st>>>(a); bep_backward_kernel<2><<<grid, 64, 0, st>>>(a); break;
+    case 4: bep_forward_kernel<4><<<grid, 64, 0, st>>>(a); bep_backward_kernel<4><<<grid, 64, 0, st>>>(a); break;
+    case 8: bep_forward_kernel<8><<<grid, 64, 0, st>>>(a); bep_backward_kernel<8><<<grid, 64, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace bnk

@@ -1,0 +1,33 @@
+// bep.cuh -- shared by bep.cu (kernels) and bep_api.cu (host side of bnk_bep_presence)
+#pragma once
+#include "device_common.cuh"
+
+#include <climits>
+
+namespace bnk {
+
+constexpr int BEP_NONE = INT_MIN;  // "null" leaf value: the sequence has no residue in this column
+
+struct BepArgs {
+    const int32_t *inst_e;    // [n_inst] extended column index of the instance
+    const uint8_t *inst_fwd;  // [n_inst] 1 = forward
+    int32_t n_inst, n_pos, n_nodes, n_leaves, n_int;
+    const int32_t *nxt, *prv;            // [leaf][n_pos + 2]
+    const int32_t *first, *kids;         // children CSR
+    const int32_t *leaf_of_node;         // node -> leaf row or -1
+    const int32_t *ent_of_node;          // node -> internal row or -1
+    const int32_t *parent;
+    int32_t recode_null;                 // GRASP.RECODE_NULL: childless nodes without a value carry a NULL symbol
+    int32_t max_sym;                     // dictionary capacity (32 * W - 1: one bit is kept for NULL)
+    int32_t *dict;                       // [max_sym][n_inst] distinct leaf values of the instance
+    int32_t *nsym;                       // [n_inst] number of them
+    uint32_t *A, *B;                     // [n_int][W][n_inst]; B is overwritten by the optimal sets going down
+    int32_t *flag;                       // |= 1: an instance has more than max_sym distinct values
+};
+
+cudaError_t bep_launch_next_prev(const uint8_t *obs, const int32_t *leaf_nodes, int n_leaves, int n_pos, int32_t *nxt, int32_t *prv,
+                                 cudaStream_t st);
+cudaError_t bep_launch_dict(const BepArgs &a, cudaStream_t st);
+cudaError_t bep_launch_sweeps(const BepArgs &a, int W, cudaStream_t st);  // forward + backward; W in {1, 2, 4, 8}
+
+}  // namespace bnk

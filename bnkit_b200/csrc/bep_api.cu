@@ -1,0 +1,364 @@
+// bep_api.cu -- bnk_bep_presence: the per-column presence mask of every ancestor by bi-directional edge
+// parsimony, as asr.Prediction.PredictByBidirEdgeParsimony + patchAncestorsWithBEP produce it
+// (src/asr/Prediction.java:1443-1590) and Prediction.getTree consumes it (:336-349).
+//
+// Device: the parsimony sweeps of all 2 (nPos + 1) edge instances (bep.cu).  Host: what the reference does per
+// ancestor after inference -- assemble the partial-order graph from the optimal edges (POGraph.createFromEdgeMap,
+// src/dat/pog/POGraph.java:544-559), test it for a start-to-end path (isContiguous :314-335), remove nodes that
+// stick out (nibble :566-617), and for graphs without a path re-infer the protruding columns without the NULL
+// symbol until a path exists (patchAncestorsWithBEP; those re-inferences run on the device again).
+#include "bep.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <set>
+#include <vector>
+
+using namespace bnk;
+
+#define BEP_CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            rc = fail(e_ == cudaErrorMemoryAllocation ? BNK_ERR_NOMEM : BNK_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                      cudaGetErrorString(e_), __FILE__, __LINE__);                                          \
+            goto done;                                                                                      \
+        }                                                                                                   \
+    } while (0)
+
+namespace {
+
+// dat.pog.POGraph restricted to what BEP needs: directed, terminated, nodes = alignment columns
+struct Pog {
+    int n = 0;
+    std::vector<char> node;
+    std::vector<std::vector<int>> fwd, bwd;
+    std::vector<char> is_start, is_end;
+    std::vector<int> touched;  // nodes ever added (for cheap reuse)
+
+    void reset(int n_pos)
+    {
+        if (n != n_pos) {
+            n = n_pos;
+            node.assign(n, 0); fwd.assign(n, {}); bwd.assign(n, {}); is_start.assign(n, 0); is_end.assign(n, 0);
+            touched.clear();
+            return;
+        }
+        for (int i : touched) { node[i] = 0; fwd[i].clear(); bwd[i].clear(); is_start[i] = 0; is_end[i] = 0; }
+        touched.clear();
+    }
+    bool is_node(int i) const { return i >= 0 && i < n && node[i]; }
+    void add_node(int i)  // IdxGraph.addNode (src/dat/pog/IdxGraph.java:346-357)
+    {
+        node[i] = 1; fwd[i].clear(); bwd[i].clear();
+        touched.push_back(i);
+    }
+    static bool has(const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+    bool add_edge(int a, int b)  // IdxGraph.addEdge (:402-419); returns whether the graph changed
+    {
+        if (is_node(a) && is_node(b)) {
+            if (has(fwd[a], b)) return false;
+            fwd[a].push_back(b); bwd[b].push_back(a);
+            return true;
+        }
+        if (a == -1 && is_node(b)) { const bool c = !is_start[b]; is_start[b] = 1; return c; }
+        if (is_node(a) && b == n) { const bool c = !is_end[a]; is_end[a] = 1; return c; }
+        return false;
+    }
+    void remove_node(int i)  // IdxGraph.removeNode (:373-391)
+    {
+        for (int nx : fwd[i]) { auto &v = bwd[nx]; v.erase(std::remove(v.begin(), v.end(), i), v.end()); }
+        for (int pv : bwd[i]) { auto &v = fwd[pv]; v.erase(std::remove(v.begin(), v.end(), i), v.end()); }
+        node[i] = 0; fwd[i].clear(); bwd[i].clear(); is_start[i] = 0; is_end[i] = 0;
+    }
+    std::vector<int> order() const  // ascending = a topological order (every edge runs to a higher column)
+    {
+        std::vector<int> o;
+        for (int i : touched) if (node[i]) o.push_back(i);
+        std::sort(o.begin(), o.end());
+        o.erase(std::unique(o.begin(), o.end()), o.end());
+        return o;
+    }
+    bool is_contiguous() const  // isPath(-1, N)
+    {
+        std::vector<int> stack;
+        std::vector<char> seen(n, 0);
+        for (int i : touched) if (node[i] && is_start[i] && !seen[i]) { seen[i] = 1; stack.push_back(i); }
+        while (!stack.empty()) {
+            const int v = stack.back(); stack.pop_back();
+            if (is_end[v]) return true;
+            for (int nx : fwd[v]) if (!seen[nx]) { seen[nx] = 1; stack.push_back(nx); }
+        }
+        return false;
+    }
+    bool sticks_out(int i, bool from_start) const  // POGraph.nibble(index, direction) (:566-581)
+    {
+        if (from_start) return !is_start[i] && bwd[i].empty();
+        return !is_end[i] && fwd[i].empty();
+    }
+    void nibble()  // (:588-617)
+    {
+        const std::vector<int> o = order();
+        for (int i : o) if (node[i] && sticks_out(i, true)) remove_node(i);
+        for (auto it = o.rbegin(); it != o.rend(); ++it) if (node[*it] && sticks_out(*it, false)) remove_node(*it);
+    }
+    std::set<int> protruding() const  // getProtruding (:622-646): +i sticks out towards the end, -i towards the start
+    {
+        std::set<int> cols;
+        const std::vector<int> o = order();
+        for (int i : o) if (sticks_out(i, false)) cols.insert(i);
+        for (auto it = o.rbegin(); it != o.rend(); ++it) if (sticks_out(*it, true)) cols.insert(-*it);
+        return cols;
+    }
+    void from_edges(int n_pos, const std::vector<std::pair<int, int>> &edges)  // createFromEdgeMap (:544-559)
+    {
+        reset(n_pos);
+        for (const auto &ed : edges) {
+            if (ed.first != -1 && !is_node(ed.first)) add_node(ed.first);
+            if (ed.second != n_pos && !is_node(ed.second)) add_node(ed.second);
+            add_edge(ed.first, ed.second);
+        }
+    }
+};
+
+template <typename T>
+struct Dev {
+    T *p = nullptr;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    ~Dev() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
+                                int32_t *info_or_null)
+{
+    if (!t || !obs || !present_out || n_cols < 1) return fail(BNK_ERR_ARG, "bep: bad argument");
+    if (t->root_count != 1 || t->parent[0] >= 0)
+        return fail(BNK_ERR_TREE, "bep: the tree must have a single root at index 0 (asr.Parsimony starts at branch point 0)");
+    if (t->max_children > 63) return fail(BNK_ERR_TREE, "bep: at most 63 children per node (the tree has a node with %d)", t->max_children);
+    int rc = BNK_OK;
+    const int n = t->n, n_pos = n_cols, n_int = t->n_int;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BNK_ERR_CUDA, "bep: no CUDA device visible (libbnkgpu has no CPU fallback)");
+    }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return fail(BNK_ERR_CUDA, "bep: cannot select device %d", device);
+    std::vector<int32_t> leaf_nodes, leaf_of_node(n, -1);
+    for (int v = 0; v < n; v++)
+        if (t->ent_of_node[v] < 0) { leaf_of_node[v] = (int32_t)leaf_nodes.size(); leaf_nodes.push_back(v); }
+    const int n_leaves = (int)leaf_nodes.size();
+    // extant rows pass through; ancestors are filled in below
+    for (int v = 0; v < n; v++) {
+        uint8_t *row = present_out + (size_t)v * n_pos;
+        if (t->ent_of_node[v] < 0) for (int c = 0; c < n_pos; c++) row[c] = obs[(size_t)v * n_pos + c] != BNK_NONE;
+        else std::memset(row, 0, n_pos);
+    }
+    if (n_int == 0) return BNK_OK;
+
+    cudaStream_t st = nullptr;
+    Dev<uint8_t> d_obs, d_fwd;
+    Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag;
+    Dev<uint32_t> d_A, d_B;
+    const int MAXSYM = 255;
+    int info[4] = {0, 0, 0, 0};  // crippled ancestors after the first pass, patch rounds, largest symbol count, kernel launches
+    Pog pog;
+    std::map<int, Pog> crippled_pog;  // ancestors without a start-to-end path (node index -> its graph)
+    std::map<int, std::set<int>> crippled;
+    std::vector<int32_t> h_nsym, h_dict;
+    std::vector<uint32_t> h_opt;
+
+    // one batch of instances through the device; results land in h_nsym / h_dict / h_opt ([ent][W][n_inst])
+    auto run = [&](const std::vector<int32_t> &ie, const std::vector<uint8_t> &ifw, int recode_null, int &W) -> int {
+        int rc = BNK_OK;
+        const int n_inst = (int)ie.size();
+        BepArgs a;
+        std::memset(&a, 0, sizeof(a));
+        int32_t flag = 0, mx = 0;
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_inst_e.p, ie.data(), sizeof(int32_t) * n_inst, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_fwd.p, ifw.data(), n_inst, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int32_t), st));
+        a.inst_e = d_inst_e.p; a.inst_fwd = d_fwd.p; a.n_inst = n_inst; a.n_pos = n_pos; a.n_nodes = n; a.n_leaves = n_leaves; a.n_int = n_int;
+        a.nxt = d_nxt.p; a.prv = d_prv.p; a.first = d_first.p; a.kids = d_kids.p; a.leaf_of_node = d_leaf_of_node.p;
+        a.ent_of_node = d_ent.p; a.parent = d_parent.p; a.recode_null = recode_null; a.max_sym = MAXSYM;
+        a.dict = d_dict.p; a.nsym = d_nsym.p; a.A = d_A.p; a.B = d_B.p; a.flag = d_flag.p;
+        BEP_CUDA_TRY(bep_launch_dict(a, st));
+        info[3]++;
+        h_nsym.resize(n_inst);
+        BEP_CUDA_TRY(cudaMemcpyAsync(h_nsym.data(), d_nsym.p, sizeof(int32_t) * n_inst, cudaMemcpyDeviceToHost, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BEP_CUDA_TRY(cudaStreamSynchronize(st));
+        if (flag) { rc = fail(BNK_ERR_ARG, "bep: a column has more than %d distinct edge targets", MAXSYM); goto done; }
+        for (int x : h_nsym) mx = std::max(mx, x);
+        info[2] = std::max(info[2], mx);
+        W = mx + 1 <= 32 ? 1 : (mx + 1 <= 64 ? 2 : (mx + 1 <= 128 ? 4 : 8));
+        BEP_CUDA_TRY(bep_launch_sweeps(a, W, st));
+        info[3] += 2;
+        h_dict.resize((size_t)std::max(mx, 1) * n_inst);
+        h_opt.resize((size_t)n_int * W * n_inst);
+        BEP_CUDA_TRY(cudaMemcpyAsync(h_dict.data(), d_dict.p, sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst, cudaMemcpyDeviceToHost, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(h_opt.data(), d_B.p, sizeof(uint32_t) * h_opt.size(), cudaMemcpyDeviceToHost, st));
+        BEP_CUDA_TRY(cudaStreamSynchronize(st));
+    done:
+        return rc;
+    };
+    // optimal non-NULL values of ancestor row `ent` in instance k of the last batch
+    auto for_each_optimal = [&](int ent, int k, int n_inst, int W, auto &&fn) {
+        const int ns = h_nsym[k];
+        for (int w = 0; w < W; w++) {
+            uint32_t bits = h_opt[((size_t)ent * W + w) * n_inst + k];
+            while (bits) {
+                const int b = __builtin_ctz(bits);
+                bits &= bits - 1;
+                const int sym = w * 32 + b;
+                if (sym < ns) fn(h_dict[(size_t)sym * n_inst + k]);  // sym == ns is the NULL symbol
+            }
+        }
+    };
+    auto emit_row = [&](int v, const Pog &g) {
+        uint8_t *row = present_out + (size_t)v * n_pos;
+        for (int c = 0; c < n_pos; c++) row[c] = g.node[c] ? 1 : 0;
+    };
+
+    {
+        const int n_inst_max = 2 * (n_pos + 1);
+        std::vector<int32_t> ie;
+        std::vector<uint8_t> ifw;
+        int W = 1;
+        BEP_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        BEP_CUDA_TRY(d_obs.alloc((size_t)n * n_pos));
+        BEP_CUDA_TRY(d_leaf_nodes.alloc(n_leaves));
+        BEP_CUDA_TRY(d_leaf_of_node.alloc(n));
+        BEP_CUDA_TRY(d_ent.alloc(n));
+        BEP_CUDA_TRY(d_parent.alloc(n));
+        BEP_CUDA_TRY(d_first.alloc(n + 1));
+        BEP_CUDA_TRY(d_kids.alloc(t->kids.size()));
+        BEP_CUDA_TRY(d_nxt.alloc((size_t)n_leaves * (n_pos + 2)));
+        BEP_CUDA_TRY(d_prv.alloc((size_t)n_leaves * (n_pos + 2)));
+        BEP_CUDA_TRY(d_inst_e.alloc(n_inst_max));
+        BEP_CUDA_TRY(d_fwd.alloc(n_inst_max));
+        BEP_CUDA_TRY(d_dict.alloc((size_t)MAXSYM * n_inst_max));
+        BEP_CUDA_TRY(d_nsym.alloc(n_inst_max));
+        BEP_CUDA_TRY(d_flag.alloc(1));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_obs.p, obs, (size_t)n * n_pos, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_leaf_nodes.p, leaf_nodes.data(), sizeof(int32_t) * n_leaves, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_leaf_of_node.p, leaf_of_node.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_ent.p, t->ent_of_node.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_parent.p, t->parent.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_first.p, t->first.data(), sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+        if (!t->kids.empty())
+            BEP_CUDA_TRY(cudaMemcpyAsync(d_kids.p, t->kids.data(), sizeof(int32_t) * t->kids.size(), cudaMemcpyHostToDevice, st));
+        BEP_CUDA_TRY(bep_launch_next_prev(d_obs.p, d_leaf_nodes.p, n_leaves, n_pos, d_nxt.p, d_prv.p, st));
+        info[3]++;
+        // the bit sets of the widest case (8 words) bound the allocation; most alignments need one word
+        {
+            // allocate for one word first; grow if the dictionary pass asks for more
+            // (the first batch decides: the patch batches are subsets of its instances without the NULL symbol)
+            BEP_CUDA_TRY(d_A.alloc((size_t)n_int * n_inst_max));
+            BEP_CUDA_TRY(d_B.alloc((size_t)n_int * n_inst_max));
+        }
+        // ---- every (column, direction) instance with RECODE_NULL (Prediction.java:1453-1477) ----
+        for (int e = 0; e <= n_pos; e++) { ie.push_back(e); ifw.push_back(1); }       // forward: columns -1 .. nPos - 1
+        for (int e = 1; e <= n_pos + 1; e++) { ie.push_back(e); ifw.push_back(0); }   // backward: columns 0 .. nPos
+        {
+            // dictionary pass once to size the bit sets
+            BepArgs a;
+            std::memset(&a, 0, sizeof(a));
+            int32_t flag = 0, mx = 0;
+            const int n_inst = (int)ie.size();
+            BEP_CUDA_TRY(cudaMemcpyAsync(d_inst_e.p, ie.data(), sizeof(int32_t) * n_inst, cudaMemcpyHostToDevice, st));
+            BEP_CUDA_TRY(cudaMemcpyAsync(d_fwd.p, ifw.data(), n_inst, cudaMemcpyHostToDevice, st));
+            BEP_CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int32_t), st));
+            a.inst_e = d_inst_e.p; a.inst_fwd = d_fwd.p; a.n_inst = n_inst; a.n_pos = n_pos; a.n_nodes = n; a.n_leaves = n_leaves;
+            a.nxt = d_nxt.p; a.prv = d_prv.p; a.max_sym = MAXSYM; a.dict = d_dict.p; a.nsym = d_nsym.p; a.flag = d_flag.p;
+            BEP_CUDA_TRY(bep_launch_dict(a, st));
+            info[3]++;
+            h_nsym.resize(n_inst);
+            BEP_CUDA_TRY(cudaMemcpyAsync(h_nsym.data(), d_nsym.p, sizeof(int32_t) * n_inst, cudaMemcpyDeviceToHost, st));
+            BEP_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            BEP_CUDA_TRY(cudaStreamSynchronize(st));
+            if (flag) { rc = fail(BNK_ERR_ARG, "bep: a column has more than %d distinct edge targets", MAXSYM); goto done; }
+            for (int x : h_nsym) mx = std::max(mx, x);
+            const int Wn = mx + 1 <= 32 ? 1 : (mx + 1 <= 64 ? 2 : (mx + 1 <= 128 ? 4 : 8));
+            if (Wn > 1) {
+                cudaFree(d_A.p); d_A.p = nullptr; cudaFree(d_B.p); d_B.p = nullptr;
+                BEP_CUDA_TRY(d_A.alloc((size_t)n_int * Wn * n_inst_max));
+                BEP_CUDA_TRY(d_B.alloc((size_t)n_int * Wn * n_inst_max));
+            }
+        }
+        rc = run(ie, ifw, 1, W);
+        if (rc != BNK_OK) goto done;
+        {
+            const int n_inst = (int)ie.size();
+            std::vector<std::pair<int, int>> edges;
+            for (int v = 0; v < n; v++) {
+                const int ent = t->ent_of_node[v];
+                if (ent < 0) continue;
+                edges.clear();
+                for (int k = 0; k < n_inst; k++) {
+                    if (h_nsym[k] < 1) continue;  // nothing to infer: the reference makes no Parsimony object (:1466-1468)
+                    const int i = ie[k] - 1;
+                    if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back({i, to}); });
+                    else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back({from, i}); });
+                }
+                std::sort(edges.begin(), edges.end());
+                edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                pog.from_edges(n_pos, edges);
+                if (!pog.is_contiguous()) {
+                    crippled[v] = pog.protruding();
+                    crippled_pog[v] = pog;
+                } else {
+                    pog.nibble();  // GRASP.NIBBLE = true
+                    emit_row(v, pog);
+                }
+            }
+        }
+        info[0] = (int)crippled.size();
+        // ---- patchAncestorsWithBEP: re-infer the protruding columns without the NULL symbol (:1551-1588) ----
+        for (;;) {
+            std::set<int> columns;
+            for (const auto &kv : crippled) columns.insert(kv.second.begin(), kv.second.end());
+            if (columns.empty()) break;
+            const std::vector<int> cols(columns.begin(), columns.end());
+            ie.clear(); ifw.clear();
+            for (int idx : cols) { ie.push_back(std::abs(idx) + 1); ifw.push_back(idx > 0 ? 1 : 0); }
+            rc = run(ie, ifw, 0, W);
+            if (rc != BNK_OK) goto done;
+            info[1]++;
+            bool changed = false;
+            const int n_inst = (int)ie.size();
+            std::vector<int> fixme;
+            for (const auto &kv : crippled) fixme.push_back(kv.first);
+            for (int v : fixme) {
+                Pog &g = crippled_pog[v];
+                const std::set<int> &idxs = crippled[v];
+                const int ent = t->ent_of_node[v];
+                for (int k = 0; k < n_inst; k++) {
+                    const int idx = cols[k], col = std::abs(idx);
+                    if (!idxs.count(idx)) continue;
+                    for_each_optimal(ent, k, n_inst, W, [&](int inferred) {
+                        if (!g.is_node(inferred) && inferred != n_pos && inferred != -1) { g.add_node(inferred); changed = true; }
+                        changed |= idx > 0 ? g.add_edge(col, inferred) : g.add_edge(inferred, col);
+                    });
+                }
+                if (!g.is_contiguous()) {
+                    crippled[v] = g.protruding();
+                } else {
+                    g.nibble();
+                    emit_row(v, g);
+                    crippled.erase(v);
+                    crippled_pog.erase(v);
+                }
+            }
+            // the reference loops `while (columns.size() > 0)` and would spin if a round adds nothing; stop instead
+            if (!changed) break;
+        }
+        for (const auto &kv : crippled_pog) emit_row(kv.first, kv.second);  // still without a path: nodes as they stand
+        if (info_or_null) { std::memcpy(info_or_null, info, sizeof(info)); }
+    }
+done:
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}

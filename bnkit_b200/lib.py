@@ -34,7 +34,7 @@ SYMBOLS = [
     "bnk_ws_create", "bnk_ws_destroy", "bnk_ws_sync", "bnk_ws_configure", "bnk_ws_launch_count",
     "bnk_ws_device_bytes", "bnk_set_rates", "bnk_set_distances", "bnk_probs",
     "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
-    "bnk_ws_phase_ms",
+    "bnk_ws_phase_ms", "bnk_bep_presence",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     L.bnk_marginal_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _ip, C.c_int32, _vp, _vp]
     L.bnk_loglik_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
     L.bnk_ws_phase_ms.argtypes = [_vp, C.c_int, C.POINTER(C.c_float)]
+    L.bnk_bep_presence.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip]
     _LIB = L
     return L
 
@@ -174,6 +175,18 @@ class Tree:
         out = np.empty_like(present)
         check(lib().bnk_tree_prune_orphans(self.h, present.shape[1], present.ctypes.data_as(_bp), out.ctypes.data_as(_bp)))
         return out
+
+
+    def bep_presence(self, obs, device=-1, want_info=False):
+        """Prediction.PredictByBidirEdgeParsimony as a mask transform: obs [n][n_cols] (255 = gap; only the
+        rows of childless nodes are read) -> present [n][n_cols] (extants: residue present; ancestors: the
+        columns of their inferred partial-order graph).  info = (ancestors without a start-to-end path after
+        the first pass, patch rounds, largest number of distinct edge targets in a column, kernel launches)."""
+        obs = np.ascontiguousarray(obs, dtype=np.uint8)
+        out = np.empty_like(obs)
+        info = np.zeros(4, dtype=np.int32)
+        check(lib().bnk_bep_presence(self.h, obs.shape[1], obs.ctypes.data_as(_bp), int(device), out.ctypes.data_as(_bp), _i(info)))
+        return (out, info) if want_info else out
 
 
 class Workspace:

@@ -58,6 +58,19 @@ const char *bnk_version(void);
 /* number of visible CUDA devices of compute capability 10.x; < 0 on runtime failure */
 int bnk_device_count(void);
 
+/* ---- indel inference: the per-column presence mask (what the sweeps below take as `present`) -------- */
+/* asr.Prediction.PredictByBidirEdgeParsimony + patchAncestorsWithBEP (src/asr/Prediction.java:1443-1590) with
+ * GRASP's defaults RECODE_NULL = true, NIBBLE = true (src/asr/GRASP.java:36-40), as a mask transform:
+ *   obs         [n_nodes][n_cols]  alignment rows of the childless nodes (BNK_NONE = gap); other rows are ignored
+ *   present_out [n_nodes][n_cols]  extants: 1 where the sequence has a residue; ancestors: 1 where the column is a
+ *                                  node of the ancestor's inferred partial-order graph (Prediction.getTree :336-349)
+ * The parsimony sweeps of all 2 (n_cols + 1) edge instances (asr.Parsimony, src/asr/Parsimony.java:215-412) run on
+ * `device` (< 0: current); graph assembly / nibbling / patching is host-side integer work.  Host buffers.
+ * info_or_null[4]: ancestors without a start-to-end path after the first pass, patch rounds, largest number of
+ * distinct edge targets in one column, kernels launched.  The tree needs a single root at index 0. */
+int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
+                     int32_t *info_or_null);
+
 /* ---- substitution models ------------------------------------------------------------ */
 /* SubstModel.createModel(name) / createModel(name, empiricalFreqs)  (SubstModel.java:334-385).
  * name in {"LG","JTT","WAG","Dayhoff","JC","Yang"}; F_or_null = 20 (or 4) frequencies. */

@@ -1,0 +1,189 @@
+"""Bi-directional edge parsimony: oracle/bep.py against the reference's documented output, the
+bit-set formulation the device kernels use against the oracle's explicit Sankoff tables (CPU), and
+bnk_bep_presence (C ABI, device sweeps) against the oracle (GPU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import NONE, random_tree
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def gold(name):
+    with open(os.path.join(HERE, "golden", name)) as fh:
+        return json.load(fh)
+
+
+def fixture_rows(fx):
+    """(parent, rows, n_pos, obs): alignment rows placed at their tree nodes."""
+    parent = fx["tree"]["Parents"]
+    labels = fx["tree"]["Labels"]
+    n, n_pos = len(parent), len(fx["seqs"][0])
+    rows = [None] * n
+    obs = np.full((n, n_pos), NONE, np.uint8)
+    for name, seq in zip(fx["names"], fx["seqs"]):
+        v = labels.index(name)
+        rows[v] = [ch != "-" for ch in seq]
+        for c, ch in enumerate(seq):
+            if ch != "-":
+                obs[v, c] = AA.index(ch)
+    return parent, rows, n_pos, obs
+
+
+def random_case(rng, n_leaves, n_pos, gap, max_children=2):
+    parent, dist = random_tree(rng, n_leaves, max_children=max_children)
+    has_child = np.zeros(len(parent), bool)
+    has_child[parent[parent >= 0]] = True
+    obs = np.full((len(parent), n_pos), NONE, np.uint8)
+    rows = [None] * len(parent)
+    for v in range(len(parent)):
+        if not has_child[v]:
+            occ = rng.random(n_pos) > gap
+            rows[v] = occ.tolist()
+            obs[v, occ] = rng.integers(0, 20, size=int(occ.sum()))
+    return parent, dist, rows, obs
+
+
+def test_oracle_reproduces_documented_recon_graphs():
+    """docs/json-api.md:113-122: ancestors 0, 1, 2 of data/66.* get nodes {2, 4}, edges (-1,2), (2,4), (4,5)."""
+    from oracle import bep
+    parent, rows, n_pos, _ = fixture_rows(gold("c1_66.json"))
+    mask, anc = bep.presence_mask(parent, rows, n_pos)
+    doc = gold("c1_66.json")["doc_result"]
+    for j in (0, 1, 2):
+        assert [c for c in range(n_pos) if anc[j].node[c]] == doc["indices"]
+        assert sorted(anc[j].edges()) == [(-1, 2), (2, 4), (4, 5)]
+        assert sorted(anc[j].start) == [2] and sorted(anc[j].end) == [4]
+
+
+def _bitset_parsimony(children, inst, recode_null):
+    """bep.cu's forward / backward on Python ints (A = arg-min set, B = states one above it)."""
+    n = len(children)
+    vals = []
+    for v in inst:
+        if v is not None and v not in vals:
+            vals.append(v)
+    ns = len(vals)
+    ntot = ns + (1 if recode_null else 0)
+    valid = (1 << ntot) - 1
+    A, B, opt, parent = [0] * n, [0] * n, [0] * n, [-1] * n
+    for v in range(n - 1, -1, -1):
+        for u in children[v]:
+            parent[u] = v
+        if not children[v] or ntot == 0:
+            continue
+        cnt = [0] * ntot
+        for u in children[v]:
+            Au = A[u] if children[u] else ((1 << ns) if recode_null else valid) if inst[u] is None else 1 << vals.index(inst[u])
+            for i in range(ntot):
+                cnt[i] += not (Au >> i) & 1
+        A[v] = sum(1 << i for i in range(ntot) if cnt[i] == min(cnt))
+        B[v] = sum(1 << i for i in range(ntot) if cnt[i] == min(cnt) + 1)
+    out = [None] * n
+    for v in range(n):
+        if children[v]:
+            ob = opt[parent[v]] if parent[v] >= 0 else 0
+            opt[v] = A[v] if parent[v] < 0 else (ob & (A[v] | B[v])) | (A[v] if ob & ~A[v] else 0)
+            out[v] = sorted(vals[i] for i in range(ns) if (opt[v] >> i) & 1)
+    return out
+
+
+def test_bitset_formulation_equals_sankoff_tables():
+    """Unit costs collapse asr.Parsimony's score tables and traceback lists to two bit sets per node."""
+    from oracle import bep
+    rng = np.random.default_rng(1)
+    checked = 0
+    for trial in range(60):
+        parent, _, rows, _ = random_case(rng, int(rng.integers(3, 22)), int(rng.integers(2, 10)),
+                                         float(rng.choice([0.2, 0.5, 0.7])), max_children=int(rng.integers(2, 5)))
+        children = bep.children_of(parent.tolist())
+        is_leaf = [len(c) == 0 for c in children]
+        n_pos = len(rows[[i for i, r in enumerate(rows) if r is not None][0]])
+        for recode in (True, False):
+            for i in range(-1, n_pos + 1):
+                for fwd in (True, False):
+                    inst = bep.edge_instance(rows, i, fwd, n_pos)
+                    if all(x is None for x in inst):
+                        continue
+                    ref = bep.parsimony(children, inst, is_leaf, recode)
+                    got = _bitset_parsimony(children, inst, recode)
+                    for v in range(len(parent)):
+                        if children[v]:
+                            assert sorted(ref[v] or []) == got[v]
+                            checked += 1
+    assert checked > 5000
+
+
+@pytest.mark.gpu
+def test_gpu_bep_c1_c2(bnk):
+    from oracle import bep
+    for name in ("c1_66.json", "c2_3_2_1_1_filt.json"):
+        parent, rows, n_pos, obs = fixture_rows(gold(name))
+        want, _ = bep.presence_mask(parent, rows, n_pos)
+        tree = bnk.Tree(np.asarray(parent, np.int32), np.asarray(gold(name)["tree"]["Distances"]))
+        got, info = tree.bep_presence(obs, want_info=True)
+        assert np.array_equal(got, np.asarray(want, np.uint8)), "%s: %d entries differ" % (name, (got != np.asarray(want)).sum())
+        assert info[3] >= 4
+
+
+@pytest.mark.gpu
+def test_gpu_bep_random_alignments(bnk):
+    """Random trees (binary and multifurcating) and gappy alignments, including discontinuous ancestors that
+    go through the patch rounds; one case with more than 31 distinct edge targets (two-word bit sets)."""
+    from oracle import bep
+    rng = np.random.default_rng(7)
+    patched = 0
+    for trial in range(40):
+        parent, dist, rows, obs = random_case(rng, int(rng.integers(3, 40)), int(rng.integers(1, 30)),
+                                              float(rng.choice([0.05, 0.3, 0.6, 0.85])), max_children=int(rng.integers(2, 6)))
+        n_pos = obs.shape[1]
+        want, _ = bep.presence_mask(parent.tolist(), rows, n_pos)
+        got, info = bnk.Tree(parent, dist).bep_presence(obs, want_info=True)
+        assert np.array_equal(got, np.asarray(want, np.uint8)), "trial %d: %d entries differ" % (trial, (got != np.asarray(want)).sum())
+        patched += int(info[0] > 0)
+    assert patched > 0
+    # 45 sequences that all occupy column 0 and then one column each: 45 distinct targets from column 0
+    parent, dist = random_tree(rng, 45)
+    has_child = np.zeros(len(parent), bool)
+    has_child[parent[parent >= 0]] = True
+    n_pos = 50
+    obs = np.full((len(parent), n_pos), NONE, np.uint8)
+    rows = [None] * len(parent)
+    for k, v in enumerate(np.nonzero(~has_child)[0]):
+        obs[v, 0] = 0
+        obs[v, 1 + k] = 1
+        rows[v] = (obs[v] != NONE).tolist()
+    want, _ = bep.presence_mask(parent.tolist(), rows, n_pos)
+    got, info = bnk.Tree(parent, dist).bep_presence(obs, want_info=True)
+    assert info[2] >= 45
+    assert np.array_equal(got, np.asarray(want, np.uint8))
+
+
+@pytest.mark.gpu
+def test_gpu_bep_feeds_the_sweeps(bnk, oracle):
+    """End to end on data/66.*: BEP mask (device) -> orphan pruning -> joint reconstruction (device) equals the
+    oracle chain, and reproduces the documented states A, H of ancestors 0-2 under JTT."""
+    from oracle import bep
+    fx = gold("c1_66.json")
+    parent, rows, n_pos, obs = fixture_rows(fx)
+    parent = np.asarray(parent, np.int32)
+    dist = np.asarray(fx["tree"]["Distances"])
+    tree = bnk.Tree(parent, dist)
+    present = tree.prune_orphans(tree.bep_presence(obs))
+    m = bnk.Model("JTT")
+    ws = bnk.Workspace(m, tree, n_pos)
+    st = ws.joint(obs, present)
+    want_mask, _ = bep.presence_mask(parent.tolist(), rows, n_pos)
+    want_present = np.stack([oracle.prune(parent, np.ascontiguousarray(np.asarray(want_mask, np.uint8)[:, c]), True)[0]
+                             for c in range(n_pos)], axis=1)
+    assert np.array_equal(present, want_present)
+    assert np.array_equal(st, oracle.fast_joint(oracle.Model("JTT"), parent, dist, obs, present))
+    for anc in (0, 1, 2):
+        cols = [c for c in range(n_pos) if present[anc, c]]
+        assert cols == fx["doc_result"]["indices"]
+        assert [AA[st[anc, c]] for c in cols] == fx["doc_result"]["values"]
+    ws.close()
