@@ -10,6 +10,7 @@
 #include "bep.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <set>
@@ -159,21 +160,44 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     if (n_int == 0) return BNK_OK;
 
     cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Dev<uint8_t> d_obs, d_fwd;
     Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag;
     Dev<uint32_t> d_A, d_B;
     const int MAXSYM = 255;
-    int info[4] = {0, 0, 0, 0};  // crippled ancestors after the first pass, patch rounds, largest symbol count, kernel launches
+    // crippled ancestors after the first pass, patch rounds, largest symbol count, kernel launches,
+    // microseconds: device sweeps (incl. their copies), host graph assembly, whole call, kernels alone (CUDA events)
+    int info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto us_since = [](std::chrono::steady_clock::time_point t0) {
+        return (int)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    };
     Pog pog;
-    std::map<int, Pog> crippled_pog;  // ancestors without a start-to-end path (node index -> its graph)
+    // ancestors without a start-to-end path: their edges so far (the graph is rebuilt in `pog` when needed) and
+    // the columns that stick out
+    std::map<int, std::vector<std::pair<int, int>>> crippled_edges;
     std::map<int, std::set<int>> crippled;
-    std::vector<int32_t> h_nsym, h_dict;
-    std::vector<uint32_t> h_opt;
+    std::vector<int32_t> h_nsym;
+    struct Pinned {  // page-locked staging for the two large device->host copies
+        void *p = nullptr; size_t cap = 0;
+        cudaError_t ensure(size_t bytes) {
+            if (bytes <= cap) return cudaSuccess;
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            cudaError_t e = cudaMallocHost(&p, bytes);
+            if (e == cudaSuccess) cap = bytes;
+            return e;
+        }
+        ~Pinned() { if (p) cudaFreeHost(p); }
+    } pin_dict, pin_opt;
+    const int32_t *h_dict = nullptr;
+    const uint32_t *h_opt = nullptr;
 
     // one batch of instances through the device; results land in h_nsym / h_dict / h_opt ([ent][W][n_inst])
     auto run = [&](const std::vector<int32_t> &ie, const std::vector<uint8_t> &ifw, int recode_null, int &W) -> int {
         int rc = BNK_OK;
         const int n_inst = (int)ie.size();
+        const auto t0 = std::chrono::steady_clock::now();
         BepArgs a;
         std::memset(&a, 0, sizeof(a));
         int32_t flag = 0, mx = 0;
@@ -184,6 +208,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         a.nxt = d_nxt.p; a.prv = d_prv.p; a.first = d_first.p; a.kids = d_kids.p; a.leaf_of_node = d_leaf_of_node.p;
         a.ent_of_node = d_ent.p; a.parent = d_parent.p; a.recode_null = recode_null; a.max_sym = MAXSYM;
         a.dict = d_dict.p; a.nsym = d_nsym.p; a.A = d_A.p; a.B = d_B.p; a.flag = d_flag.p;
+        BEP_CUDA_TRY(cudaEventRecord(ev0, st));
         BEP_CUDA_TRY(bep_launch_dict(a, st));
         info[3]++;
         h_nsym.resize(n_inst);
@@ -195,12 +220,20 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         info[2] = std::max(info[2], mx);
         W = mx + 1 <= 32 ? 1 : (mx + 1 <= 64 ? 2 : (mx + 1 <= 128 ? 4 : 8));
         BEP_CUDA_TRY(bep_launch_sweeps(a, W, st));
+        BEP_CUDA_TRY(cudaEventRecord(ev1, st));
         info[3] += 2;
-        h_dict.resize((size_t)std::max(mx, 1) * n_inst);
-        h_opt.resize((size_t)n_int * W * n_inst);
-        BEP_CUDA_TRY(cudaMemcpyAsync(h_dict.data(), d_dict.p, sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst, cudaMemcpyDeviceToHost, st));
-        BEP_CUDA_TRY(cudaMemcpyAsync(h_opt.data(), d_B.p, sizeof(uint32_t) * h_opt.size(), cudaMemcpyDeviceToHost, st));
+        BEP_CUDA_TRY(pin_dict.ensure(sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst));
+        BEP_CUDA_TRY(pin_opt.ensure(sizeof(uint32_t) * (size_t)n_int * W * n_inst));
+        h_dict = static_cast<const int32_t *>(pin_dict.p);
+        h_opt = static_cast<const uint32_t *>(pin_opt.p);
+        BEP_CUDA_TRY(cudaMemcpyAsync(pin_dict.p, d_dict.p, sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst, cudaMemcpyDeviceToHost, st));
+        BEP_CUDA_TRY(cudaMemcpyAsync(pin_opt.p, d_B.p, sizeof(uint32_t) * (size_t)n_int * W * n_inst, cudaMemcpyDeviceToHost, st));
         BEP_CUDA_TRY(cudaStreamSynchronize(st));
+        info[4] += us_since(t0);
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) info[7] += (int)(ms * 1000.f);
+        }
     done:
         return rc;
     };
@@ -228,6 +261,8 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         std::vector<uint8_t> ifw;
         int W = 1;
         BEP_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        BEP_CUDA_TRY(cudaEventCreate(&ev0));
+        BEP_CUDA_TRY(cudaEventCreate(&ev1));
         BEP_CUDA_TRY(d_obs.alloc((size_t)n * n_pos));
         BEP_CUDA_TRY(d_leaf_nodes.alloc(n_leaves));
         BEP_CUDA_TRY(d_leaf_of_node.alloc(n));
@@ -292,6 +327,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         if (rc != BNK_OK) goto done;
         {
             const int n_inst = (int)ie.size();
+            const auto t0 = std::chrono::steady_clock::now();
             std::vector<std::pair<int, int>> edges;
             for (int v = 0; v < n; v++) {
                 const int ent = t->ent_of_node[v];
@@ -308,12 +344,13 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                 pog.from_edges(n_pos, edges);
                 if (!pog.is_contiguous()) {
                     crippled[v] = pog.protruding();
-                    crippled_pog[v] = pog;
+                    crippled_edges[v] = edges;
                 } else {
                     pog.nibble();  // GRASP.NIBBLE = true
                     emit_row(v, pog);
                 }
             }
+            info[5] += us_since(t0);
         }
         info[0] = (int)crippled.size();
         // ---- patchAncestorsWithBEP: re-infer the protruding columns without the NULL symbol (:1551-1588) ----
@@ -327,38 +364,48 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
             rc = run(ie, ifw, 0, W);
             if (rc != BNK_OK) goto done;
             info[1]++;
+            const auto t0 = std::chrono::steady_clock::now();
             bool changed = false;
             const int n_inst = (int)ie.size();
+            std::map<int, int> inst_of;  // protruding index -> instance of this round
+            for (int k = 0; k < n_inst; k++) inst_of[cols[k]] = k;
             std::vector<int> fixme;
             for (const auto &kv : crippled) fixme.push_back(kv.first);
             for (int v : fixme) {
-                Pog &g = crippled_pog[v];
-                const std::set<int> &idxs = crippled[v];
+                std::vector<std::pair<int, int>> &edges = crippled_edges[v];
+                pog.from_edges(n_pos, edges);
                 const int ent = t->ent_of_node[v];
-                for (int k = 0; k < n_inst; k++) {
-                    const int idx = cols[k], col = std::abs(idx);
-                    if (!idxs.count(idx)) continue;
+                for (int idx : crippled[v]) {  // ascending, as cols_ordered
+                    const int k = inst_of[idx], col = std::abs(idx);
                     for_each_optimal(ent, k, n_inst, W, [&](int inferred) {
-                        if (!g.is_node(inferred) && inferred != n_pos && inferred != -1) { g.add_node(inferred); changed = true; }
-                        changed |= idx > 0 ? g.add_edge(col, inferred) : g.add_edge(inferred, col);
+                        if (!pog.is_node(inferred) && inferred != n_pos && inferred != -1) { pog.add_node(inferred); changed = true; }
+                        const std::pair<int, int> ed = idx > 0 ? std::make_pair(col, inferred) : std::make_pair(inferred, col);
+                        if (pog.add_edge(ed.first, ed.second)) { edges.push_back(ed); changed = true; }
                     });
                 }
-                if (!g.is_contiguous()) {
-                    crippled[v] = g.protruding();
+                if (!pog.is_contiguous()) {
+                    crippled[v] = pog.protruding();
                 } else {
-                    g.nibble();
-                    emit_row(v, g);
+                    pog.nibble();
+                    emit_row(v, pog);
                     crippled.erase(v);
-                    crippled_pog.erase(v);
+                    crippled_edges.erase(v);
                 }
             }
+            info[5] += us_since(t0);
             // the reference loops `while (columns.size() > 0)` and would spin if a round adds nothing; stop instead
             if (!changed) break;
         }
-        for (const auto &kv : crippled_pog) emit_row(kv.first, kv.second);  // still without a path: nodes as they stand
-        if (info_or_null) { std::memcpy(info_or_null, info, sizeof(info)); }
+        for (const auto &kv : crippled_edges) {  // still without a path: nodes as they stand
+            pog.from_edges(n_pos, kv.second);
+            emit_row(kv.first, pog);
+        }
+        info[6] = us_since(t_begin);
+        if (info_or_null) std::memcpy(info_or_null, info, sizeof(info));
     }
 done:
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
     return rc;
 }

@@ -34,7 +34,6 @@ constexpr int XCW = 6;             // columns per warp (5 lanes each; lanes 30, 
 constexpr int XPD = 8;             // producer: observed states are requested this many steps ahead
 constexpr int XPB = 4;             // walk-program ring: chunks of 32 steps
 constexpr int XTAB = XK * XK * 8;  // one table, bytes
-constexpr int XGROW = XK + 2;      // padded row (doubles) of a warp's exchange buffer: 6 rows hit distinct banks
 constexpr int XPROG = 256;         // byte offsets inside dynamic shared memory: barriers first, ...
 constexpr int XSTAGE0 = XPROG + XPB * 32 * (int)sizeof(Step);
 constexpr int XMAXNS = 8, XMAXW = 5;
@@ -44,7 +43,10 @@ constexpr int XOBS = 128;          // a stage starts with the observed states: 2
 __host__ __device__ inline int x_child_bytes(int tile_cols, bool down) { return (down && tile_cols * XK * 8 > XTAB) ? tile_cols * XK * 8 : XTAB; }
 // stage = [observed states][table of the node][area of child 0][area of child 1]
 __host__ __device__ inline int x_stage_bytes(int chb) { return XOBS + XTAB + 2 * chb; }
-__host__ __device__ inline int x_warp_bytes(int C, int slots) { return 2 * XCW * C * XGROW * 8 + (slots + 1) * XCW * C * XK * 8; }
+// a warp's private area: two exchange buffers and the message stack (+ 1 dummy slot), all "planar" vectors:
+// entries 0..9 of column c at c * 80, entries 10..19 at plane + c * 80 (plane = columns * 80 bytes), so that
+// consecutive lanes touch consecutive 16-byte chunks and no quarter-warp sees a bank twice
+__host__ __device__ inline int x_warp_bytes(int C, int slots) { return (2 + slots + 1) * XCW * C * XK * 8; }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
@@ -249,6 +251,18 @@ struct XLane {
         const double2 u_ = XS_D2((off) + (q) * 16), w_ = XS_D2((off) + 80 + (q) * 16); \
         (v)[0] = u_.x; (v)[1] = u_.y; (v)[2] = w_.x; (v)[3] = w_.y;                \
     } while (0)
+#define XLD4P(v, off, q, plane)                                                        \
+    do {                                                                               \
+        const double2 u_ = XS_D2((off) + (q) * 16), w_ = XS_D2((off) + (plane) + (q) * 16); \
+        (v)[0] = u_.x; (v)[1] = u_.y; (v)[2] = w_.x; (v)[3] = w_.y;                    \
+    } while (0)
+#define XST4P(off, q, v, plane)                                           \
+    do {                                                                  \
+        XS_D2((off) + (q) * 16) = make_double2((v)[0], (v)[1]);           \
+        XS_D2((off) + (plane) + (q) * 16) = make_double2((v)[2], (v)[3]); \
+    } while (0)
+// the pair (entries 2 x2, 2 x2 + 1) of a planar vector
+#define XPAIR(off, x2, plane) XS_D2((off) + ((x2) < 5 ? (x2) * 16 : (plane) + ((x2) - 5) * 16))
 #define XST4(off, q, v)                                          \
     do {                                                         \
         XS_D2((off) + (q) * 16) = make_double2((v)[0], (v)[1]);  \
@@ -276,13 +290,13 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
     const int n_steps = a.n_steps;
     const size_t ncols = (size_t)a.ncols;
     const int wbase = XSTAGE0 + ns * g.stage_bytes + warp * x_warp_bytes(C, a.smem_slots);
-    const int gbuf_bytes = XCW * C * XGROW * 8;
-    const int stack0 = wbase + 2 * gbuf_bytes;
-    const int slot_bytes = XCW * C * XK * 8;
+    constexpr int PLANE = XCW * C * 80;  // bytes between the two halves of a planar vector
+    const int slot_bytes = 2 * PLANE;
+    const int stack0 = wbase + 2 * slot_bytes;  // after the two exchange buffers
     const int dummy = stack0 + a.smem_slots * slot_bytes;
-    int own[C], gsw[C];  // this lane's columns inside a stack slot / inside an exchange buffer
+    int own[C];  // this lane's columns inside a stack slot / an exchange buffer
 #pragma unroll
-    for (int j = 0; j < C; j++) { own[j] = (j * XCW + L.c) * XK * 8; gsw[j] = (j * XCW + L.c) * XGROW * 8; }
+    for (int j = 0; j < C; j++) own[j] = (j * XCW + L.c) * 80;
     const double ident = MODE == 0 ? 0.0 : 1.0;
     const double prior4[4] = {a.prior[L.p0], a.prior[L.p0 + 1], a.prior[L.p1], a.prior[L.p1 + 1]};
     int esum[C];
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
             for (int j = 0; j < C; j++) {
                 isob[j][e] = false;
                 if (cs >= 0) {  // message left on this warp's stack
-                    XLD4(cv[j][e], stack0 + cs * slot_bytes + own[j], q);
+                    XLD4P(cv[j][e], stack0 + cs * slot_bytes + own[j], q, PLANE);
                 } else if (cs == SLOT_WIDE) {  // message a wide level kernel left in HBM, [ent][K][ncols]
                     const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + L.col[j];
                     cv[j][e][0] = src[(size_t)L.p0 * ncols]; cv[j][e][1] = src[(size_t)(L.p0 + 1) * ncols];
@@ -339,7 +353,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
                 }
             }
         }
-        const int gb = wbase + (i & 1) * gbuf_bytes;
+        const int gb = wbase + (i & 1) * slot_bytes;
 #pragma unroll
         for (int j = 0; j < C; j++) {
             // a root combines [prior, observed children, unobserved children] (the order the factors sit in the
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
                 if (MODE == 0) G[k] = ((rootstep ? prior4[k] : 0.0) + c0) + c1;
                 else G[k] = ((rootstep ? prior4[k] : 1.0) * c0) * c1;
             }
-            XST4(gb + gsw[j], q, G);
+            XST4P(gb + own[j], q, G, PLANE);
         }
         __syncwarp();
         // ---- contract with the node's table: out[p] = op_x T[x][p] (.) G[x] for the lane's four p ----
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
                 for (int x2 = 0; x2 < XK / 2; x2++) {
                     double2 gg[C];
 #pragma unroll
-                    for (int j = 0; j < C; j++) gg[j] = XS_D2(gb + gsw[j] + x2 * 16);
+                    for (int j = 0; j < C; j++) gg[j] = XPAIR(gb + own[j], x2, PLANE);
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int x = 2 * x2 + h;
@@ -396,7 +410,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
                     int bx = 0;
 #pragma unroll
                     for (int x2 = 0; x2 < XK / 2; x2++) {
-                        const double2 gg = XS_D2(gb + gsw[j] + x2 * 16);
+                        const double2 gg = XPAIR(gb + own[j], x2, PLANE);
                         const double v0 = 0.0 + gg.x, v1 = 0.0 + gg.y;
                         if (v0 > b) { b = v0; bx = 2 * x2; }
                         if (v1 > b) { b = v1; bx = 2 * x2 + 1; }
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
             }
 #pragma unroll
             for (int j = 0; j < C; j++) {
-                XST4(sdst + own[j], q, best[j]);
+                XST4P(sdst + own[j], q, best[j], PLANE);
                 uint8_t *pr = a.ptr + ((size_t)(unsigned)ent * ncols + L.col[j]) * XK;
                 *reinterpret_cast<uint16_t *>(pr + L.p0) = (uint16_t)(bi[j][0] | (bi[j][1] << 8));
                 *reinterpret_cast<uint16_t *>(pr + L.p1) = (uint16_t)(bi[j][2] | (bi[j][3] << 8));
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
                     XLD4(tb4, tv + (2 * x2 + 1) * (XK * 8), q);
 #pragma unroll
                     for (int j = 0; j < C; j++) {
-                        const double2 gg = XS_D2(gb + gsw[j] + x2 * 16);
+                        const double2 gg = XPAIR(gb + own[j], x2, PLANE);
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             acc[j][k] = fma(ta[k], gg.x, acc[j][k]);
@@ -443,7 +457,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
                 for (int j = 0; j < C; j++) {
 #pragma unroll
                     for (int x2 = 0; x2 < XK / 2; x2++) {
-                        const double2 gg = XS_D2(gb + gsw[j] + x2 * 16);
+                        const double2 gg = XPAIR(gb + own[j], x2, PLANE);
                         acc[j][0] += gg.x; acb[j][0] += gg.y;
                         mhi[j] = max(mhi[j], max(__double2hiint(gg.x), __double2hiint(gg.y)));
                     }
@@ -459,7 +473,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
 #pragma unroll
                 for (int k = 0; k < 4; k++) m[k] = (acc[j][k] + acb[j][k]) * scale;
                 esum[j] += e;
-                XST4(sdst + own[j], q, m);
+                XST4P(sdst + own[j], q, m, PLANE);
                 if (rootstep) logacc[j] += log(m[0]);
                 else if (a.msg) {
                     double *dst = a.msg + ((size_t)(unsigned)ent * ncols + L.col[j]) * XK;
@@ -502,13 +516,13 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
     const int n_steps = a.n_steps;
     const size_t ncols = (size_t)a.ncols;
     const int wbase = XSTAGE0 + ns * g.stage_bytes + warp * x_warp_bytes(C, a.smem_slots);
-    const int gbuf_bytes = XCW * C * XGROW * 8;
-    const int stack0 = wbase + 2 * gbuf_bytes;
-    const int slot_bytes = XCW * C * XK * 8;
+    constexpr int PLANE = XCW * C * 80;
+    const int slot_bytes = 2 * PLANE;
+    const int stack0 = wbase + 2 * slot_bytes;
     const int dummy = stack0 + a.smem_slots * slot_bytes;
-    int own[C], gsw[C];
+    int own[C];
 #pragma unroll
-    for (int j = 0; j < C; j++) { own[j] = (j * XCW + L.c) * XK * 8; gsw[j] = (j * XCW + L.c) * XGROW * 8; }
+    for (int j = 0; j < C; j++) own[j] = (j * XCW + L.c) * 80;
     const double prior4[4] = {a.prior[L.p0], a.prior[L.p0 + 1], a.prior[L.p1], a.prior[L.p1 + 1]};
 
     int s = 0, ph = 0;
@@ -539,7 +553,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
                 XLD4(tb4, tv + (2 * x2 + 1) * (XK * 8), q);
 #pragma unroll
                 for (int j = 0; j < C; j++) {
-                    const double2 tt = XS_D2(tsrc + own[j] + x2 * 16);
+                    const double2 tt = XPAIR(tsrc + own[j], x2, PLANE);
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         acc[j][k] = fma(ta[k], tt.x, acc[j][k]);
@@ -597,7 +611,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
                 }
             }
         }
-        const int gb = wbase + (i & 1) * gbuf_bytes;
+        const int gb = wbase + (i & 1) * slot_bytes;
         double U[C][4], T0[C][4], T1[C][4];
 #pragma unroll
         for (int j = 0; j < C; j++) {
@@ -607,7 +621,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
                 T0[j][k] = D[j][k] * cv[j][1][k];
                 T1[j][k] = D[j][k] * cv[j][0][k];
             }
-            XST4(gb + gsw[j], q, U[j]);
+            XST4P(gb + own[j], q, U[j], PLANE);
         }
         // every lane has read this node's from-above vector before the barrier; the children's slots never alias
         // this step's own slot (tree_plan.cpp), and they are written after it
@@ -617,8 +631,8 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
             const int d1 = cslot[1] >= 0 ? stack0 + cslot[1] * slot_bytes : dummy;
 #pragma unroll
             for (int j = 0; j < C; j++) {
-                XST4(d0 + own[j], q, T0[j]);
-                XST4(d1 + own[j], q, T1[j]);
+                XST4P(d0 + own[j], q, T0[j], PLANE);
+                XST4P(d1 + own[j], q, T1[j], PLANE);
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     if (cslot[e] == SLOT_WIDE) {  // handed to the wide level kernels through HBM, [ent][K][ncols]
@@ -637,7 +651,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
             for (int j = 0; j < C; j++) {
                 double sum = 0.0;
 #pragma unroll
-                for (int x2 = 0; x2 < XK / 2; x2++) { const double2 gg = XS_D2(gb + gsw[j] + x2 * 16); sum += gg.x; sum += gg.y; }
+                for (int x2 = 0; x2 < XK / 2; x2++) { const double2 gg = XPAIR(gb + own[j], x2, PLANE); sum += gg.x; sum += gg.y; }
                 const double r = x_rcp(sum);
                 double *dst = a.out_post + ((size_t)(unsigned)q0 * ncols + L.ocol[j]) * XK;
                 *reinterpret_cast<double2 *>(dst + L.p0) = make_double2(U[j][0] * r, U[j][1] * r);

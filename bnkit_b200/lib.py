@@ -181,10 +181,11 @@ class Tree:
         """Prediction.PredictByBidirEdgeParsimony as a mask transform: obs [n][n_cols] (255 = gap; only the
         rows of childless nodes are read) -> present [n][n_cols] (extants: residue present; ancestors: the
         columns of their inferred partial-order graph).  info = (ancestors without a start-to-end path after
-        the first pass, patch rounds, largest number of distinct edge targets in a column, kernel launches)."""
+        the first pass, patch rounds, largest number of distinct edge targets in a column, kernel launches, us on the device sweeps incl.
+        their copies, us of host graph assembly, us in total, us in the kernels alone)."""
         obs = np.ascontiguousarray(obs, dtype=np.uint8)
         out = np.empty_like(obs)
-        info = np.zeros(4, dtype=np.int32)
+        info = np.zeros(8, dtype=np.int32)
         check(lib().bnk_bep_presence(self.h, obs.shape[1], obs.ctypes.data_as(_bp), int(device), out.ctypes.data_as(_bp), _i(info)))
         return (out, info) if want_info else out
 

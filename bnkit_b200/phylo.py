@@ -339,6 +339,24 @@ class Prediction:
         self._ws = None
         self._ws_model = None
 
+    @staticmethod
+    def PredictByBidirEdgeParsimony(tree, states, device=-1):
+        """asr.Prediction.PredictByBidirEdgeParsimony (src/asr/Prediction.java:1443-1524): indel inference by
+        bi-directional edge parsimony; the returned Prediction carries the per-column trees Prediction.getTree
+        (:329-402) would build -- ancestors present where their partial-order graph has the column, then
+        (GRASP.REMOVE_INDEL_ORPHANS, src/asr/GRASP.java:42) subtrees without an extant removed."""
+        n = tree.getSize()
+        n_cols = len(states[0]) if len(states) else 0
+        occ = np.full((n, n_cols), NONE, dtype=np.uint8)
+        for v in range(n):
+            if tree.isLeaf(v):
+                for c in range(n_cols):
+                    if states[v][c] is not None:
+                        occ[v, c] = 0
+        h = tree.handle()
+        present = h.prune_orphans(h.bep_presence(occ, device=device))
+        return Prediction(tree, states, present, device)
+
     def _obs(self, model):
         n = self.tree.getSize()
         obs = np.full((n, self.n_cols), NONE, dtype=np.uint8)

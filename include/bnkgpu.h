@@ -66,8 +66,9 @@ int bnk_device_count(void);
  *                                  node of the ancestor's inferred partial-order graph (Prediction.getTree :336-349)
  * The parsimony sweeps of all 2 (n_cols + 1) edge instances (asr.Parsimony, src/asr/Parsimony.java:215-412) run on
  * `device` (< 0: current); graph assembly / nibbling / patching is host-side integer work.  Host buffers.
- * info_or_null[4]: ancestors without a start-to-end path after the first pass, patch rounds, largest number of
- * distinct edge targets in one column, kernels launched.  The tree needs a single root at index 0. */
+ * info_or_null[8]: ancestors without a start-to-end path after the first pass, patch rounds, largest number of
+ * distinct edge targets in one column, kernels launched, microseconds spent in the device sweeps (with their
+ * copies) / in host graph assembly / in total / in the kernels alone (CUDA events).  The tree needs a single root at index 0. */
 int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
                      int32_t *info_or_null);
 

@@ -123,6 +123,26 @@ def test_prediction_batch_entry_points(bnk, oracle):
     pred.close()
 
 
+def test_documented_recon_through_the_java_api_mirror(bnk):
+    """docs/json-api.md:97-122 end to end through the reference-shaped calls: Prediction.PredictByBidirEdgeParsimony
+    (device BEP) then getJoint under JTT gives ancestors 0, 1, 2 the states A, H at columns 2, 4 and null elsewhere."""
+    from bnkit_b200.phylo import IdxTree, Prediction, SubstModel
+    d, parent, dist, obs, _ = _dataset("c1_66.json")
+    tree = IdxTree.fromJSON(d["tree"])
+    states = [[None] * obs.shape[1] for _ in range(tree.getSize())]
+    for name_, seq in zip(d["names"], d["seqs"]):
+        states[tree.getIndex(name_)] = [None if ch == "-" else ch for ch in seq]
+    pred = Prediction.PredictByBidirEdgeParsimony(tree, states)
+    joint = pred.getJoint(SubstModel.createModel("JTT"))
+    doc = d["doc_result"]
+    for anc in (0, 1, 2):
+        assert tree.getLabel(anc) in (str(anc), "N%d" % anc)   # branch points 0, 1, 2 are ancestors "0", "1", "2"
+        row = joint[anc]
+        assert [c for c, x in enumerate(row) if x is not None] == doc["indices"]
+        assert [x for x in row if x is not None] == doc["values"]
+    pred.close()
+
+
 def test_full_size_properties_c3(bnk):
     """BASELINE configs[2] at full size (10,000 leaves x 5,000 columns, LG + Gamma4): properties that
     need no oracle -- tile-geometry invariance (bit-identical states), column-permutation
