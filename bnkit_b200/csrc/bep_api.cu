@@ -13,7 +13,9 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
+#include <thread>
 #include <vector>
 
 using namespace bnk;
@@ -123,6 +125,24 @@ struct Pog {
     }
 };
 
+// Ancestors are independent after inference (the reference's own TODO: "use threads here too",
+// Prediction.java:1483): static slices of the work list over the host's hardware threads.
+template <typename F>
+void parallel_slices(int n_items, F fn)
+{
+    int nt = (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 32) nt = 32;
+    if (n_items < 64) nt = 1;
+    if (nt == 1) { fn(0, n_items); return; }
+    std::vector<std::thread> th;
+    for (int k = 0; k < nt; k++) {
+        const int lo = (int)((int64_t)n_items * k / nt), hi = (int)((int64_t)n_items * (k + 1) / nt);
+        if (hi > lo) th.emplace_back([=] { fn(lo, hi); });
+    }
+    for (auto &x : th) x.join();
+}
+
 template <typename T>
 struct Dev {
     T *p = nullptr;
@@ -172,7 +192,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     auto us_since = [](std::chrono::steady_clock::time_point t0) {
         return (int)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     };
-    Pog pog;
+    Pog pog;  // scratch for the serial tail
     // ancestors without a start-to-end path: their edges so far (the graph is rebuilt in `pog` when needed) and
     // the columns that stick out
     std::map<int, std::vector<std::pair<int, int>>> crippled_edges;
@@ -328,28 +348,33 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         {
             const int n_inst = (int)ie.size();
             const auto t0 = std::chrono::steady_clock::now();
-            std::vector<std::pair<int, int>> edges;
-            for (int v = 0; v < n; v++) {
-                const int ent = t->ent_of_node[v];
-                if (ent < 0) continue;
-                edges.clear();
-                for (int k = 0; k < n_inst; k++) {
-                    if (h_nsym[k] < 1) continue;  // nothing to infer: the reference makes no Parsimony object (:1466-1468)
-                    const int i = ie[k] - 1;
-                    if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back({i, to}); });
-                    else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back({from, i}); });
+            std::mutex mu;
+            parallel_slices(n_int, [&](int lo, int hi) {
+                Pog g;
+                std::vector<std::pair<int, int>> edges;
+                for (int ent = lo; ent < hi; ent++) {
+                    const int v = t->node_of_ent[ent];
+                    edges.clear();
+                    for (int k = 0; k < n_inst; k++) {
+                        if (h_nsym[k] < 1) continue;  // nothing to infer: the reference makes no Parsimony object (:1466-1468)
+                        const int i = ie[k] - 1;
+                        if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back({i, to}); });
+                        else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back({from, i}); });
+                    }
+                    std::sort(edges.begin(), edges.end());
+                    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                    g.from_edges(n_pos, edges);
+                    if (!g.is_contiguous()) {
+                        std::set<int> pr = g.protruding();
+                        std::lock_guard<std::mutex> lk(mu);
+                        crippled[v] = std::move(pr);
+                        crippled_edges[v] = edges;
+                    } else {
+                        g.nibble();  // GRASP.NIBBLE = true
+                        emit_row(v, g);
+                    }
                 }
-                std::sort(edges.begin(), edges.end());
-                edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
-                pog.from_edges(n_pos, edges);
-                if (!pog.is_contiguous()) {
-                    crippled[v] = pog.protruding();
-                    crippled_edges[v] = edges;
-                } else {
-                    pog.nibble();  // GRASP.NIBBLE = true
-                    emit_row(v, pog);
-                }
-            }
+            });
             info[5] += us_since(t0);
         }
         info[0] = (int)crippled.size();
@@ -371,26 +396,36 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
             for (int k = 0; k < n_inst; k++) inst_of[cols[k]] = k;
             std::vector<int> fixme;
             for (const auto &kv : crippled) fixme.push_back(kv.first);
-            for (int v : fixme) {
-                std::vector<std::pair<int, int>> &edges = crippled_edges[v];
-                pog.from_edges(n_pos, edges);
-                const int ent = t->ent_of_node[v];
-                for (int idx : crippled[v]) {  // ascending, as cols_ordered
-                    const int k = inst_of[idx], col = std::abs(idx);
-                    for_each_optimal(ent, k, n_inst, W, [&](int inferred) {
-                        if (!pog.is_node(inferred) && inferred != n_pos && inferred != -1) { pog.add_node(inferred); changed = true; }
-                        const std::pair<int, int> ed = idx > 0 ? std::make_pair(col, inferred) : std::make_pair(inferred, col);
-                        if (pog.add_edge(ed.first, ed.second)) { edges.push_back(ed); changed = true; }
-                    });
+            std::vector<char> fixed(fixme.size(), 0), grew(fixme.size(), 0);
+            std::vector<std::set<int>> next_pr(fixme.size());
+            parallel_slices((int)fixme.size(), [&](int lo, int hi) {
+                Pog g;
+                for (int f = lo; f < hi; f++) {
+                    const int v = fixme[f];
+                    std::vector<std::pair<int, int>> &edges = crippled_edges.find(v)->second;  // maps are only read here
+                    g.from_edges(n_pos, edges);
+                    const int ent = t->ent_of_node[v];
+                    for (int idx : crippled.find(v)->second) {  // ascending, as cols_ordered
+                        const int k = inst_of.find(idx)->second, col = std::abs(idx);
+                        for_each_optimal(ent, k, n_inst, W, [&](int inferred) {
+                            if (!g.is_node(inferred) && inferred != n_pos && inferred != -1) { g.add_node(inferred); grew[f] = 1; }
+                            const std::pair<int, int> ed = idx > 0 ? std::make_pair(col, inferred) : std::make_pair(inferred, col);
+                            if (g.add_edge(ed.first, ed.second)) { edges.push_back(ed); grew[f] = 1; }
+                        });
+                    }
+                    if (!g.is_contiguous()) {
+                        next_pr[f] = g.protruding();
+                    } else {
+                        g.nibble();
+                        emit_row(v, g);
+                        fixed[f] = 1;
+                    }
                 }
-                if (!pog.is_contiguous()) {
-                    crippled[v] = pog.protruding();
-                } else {
-                    pog.nibble();
-                    emit_row(v, pog);
-                    crippled.erase(v);
-                    crippled_edges.erase(v);
-                }
+            });
+            for (size_t f = 0; f < fixme.size(); f++) {
+                changed |= grew[f] != 0;
+                if (fixed[f]) { crippled.erase(fixme[f]); crippled_edges.erase(fixme[f]); }
+                else crippled[fixme[f]] = std::move(next_pr[f]);
             }
             info[5] += us_since(t0);
             // the reference loops `while (columns.size() > 0)` and would spin if a round adds nothing; stop instead
