@@ -143,6 +143,18 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: libraries that write to file descriptor 1 on their own (NCCL prints
+    # its version banner there) are sent to stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,7 +188,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample,
                                  "note": "C restatement of bnkit's VarElim path (oracle/); the JVM reference cannot run here (no JDK)"},
                 "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -342,7 +354,8 @@ def main():
     if world == 1 and not args.no_cpu:
         v, sample, _ = cpu_oracle_rate(spec, spec["model"], parent, dist, rates, obs, args.cpu_budget, threads)
         line["cpu_baseline"] = {"value": v, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist_.destroy_process_group()
 

@@ -101,6 +101,111 @@ __device__ __forceinline__ void bep_leaf_set(const BepArgs &a, int t, int leaf, 
 }
 
 template <int W>
+__device__ __forceinline__ void bep_valid_mask(const BepArgs &a, int n, uint32_t *valid)
+{
+    const int ntot = n + (a.recode_null ? 1 : 0);
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        const int lo = w * 32;
+        valid[w] = ntot >= lo + 32 ? 0xffffffffu : (ntot > lo ? (1u << (ntot - lo)) - 1u : 0u);
+    }
+}
+
+// forward step of one internal node v (row ent) of instance t: A = states at the lowest count of children whose
+// arg-min set misses them, B = states one count above
+template <int W>
+__device__ __forceinline__ void bep_node_forward(const BepArgs &a, int t, int v, int ent, int e, bool fwd, int n, const uint32_t *valid)
+{
+    const size_t ni = (size_t)a.n_inst;
+    constexpr int P = 6;  // bit-sliced counters: up to 63 children per node
+    uint32_t plane[P][W];
+#pragma unroll
+    for (int p = 0; p < P; p++)
+#pragma unroll
+        for (int w = 0; w < W; w++) plane[p][w] = 0;
+    const int c0 = a.first[v], c1 = a.first[v + 1];
+    for (int ci = c0; ci < c1; ci++) {
+        const int u = a.kids[ci];
+        const int ue = a.ent_of_node[u];
+        uint32_t Ac[W];
+        if (ue >= 0) {
+#pragma unroll
+            for (int w = 0; w < W; w++) Ac[w] = a.A[((size_t)ue * W + w) * ni + t];
+        } else {
+            bep_leaf_set<W>(a, t, a.leaf_of_node[u], e, fwd, n, valid, Ac);
+        }
+        // counters += (state not in A_c)
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            uint32_t carry = ~Ac[w] & valid[w];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const uint32_t s = plane[p][w] ^ carry;
+                carry &= plane[p][w];
+                plane[p][w] = s;
+            }
+        }
+    }
+    // states at the lowest count, and at the next one
+    const int nch = c1 - c0;
+    uint32_t Ab[W], Bb[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) { Ab[w] = 0; Bb[w] = 0; }
+    for (int k = 0; k <= nch; k++) {
+        uint32_t any = 0, m[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            m[w] = valid[w];
+#pragma unroll
+            for (int p = 0; p < P; p++) m[w] &= ((k >> p) & 1) ? plane[p][w] : ~plane[p][w];
+            any |= m[w];
+        }
+        if (any) {
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                Ab[w] = m[w];
+                uint32_t m1 = valid[w];
+#pragma unroll
+                for (int p = 0; p < P; p++) m1 &= (((k + 1) >> p) & 1) ? plane[p][w] : ~plane[p][w];
+                Bb[w] = k + 1 <= nch ? m1 : 0u;
+            }
+            break;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        a.A[((size_t)ent * W + w) * ni + t] = Ab[w];
+        a.B[((size_t)ent * W + w) * ni + t] = Bb[w];
+    }
+}
+
+// backward step: all optimal states of node v given its parent's (already final, stored over the parent's B)
+template <int W>
+__device__ __forceinline__ void bep_node_backward(const BepArgs &a, int t, int v, int ent)
+{
+    const size_t ni = (size_t)a.n_inst;
+    uint32_t Av[W], Bv[W], opt[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) { Av[w] = a.A[((size_t)ent * W + w) * ni + t]; Bv[w] = a.B[((size_t)ent * W + w) * ni + t]; }
+    const int par = a.parent[v];
+    if (par < 0) {
+#pragma unroll
+        for (int w = 0; w < W; w++) opt[w] = Av[w];
+    } else {
+        const int pe = a.ent_of_node[par];
+        uint32_t outside = 0, ob[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) { ob[w] = a.B[((size_t)pe * W + w) * ni + t]; outside |= ob[w] & ~Av[w]; }
+#pragma unroll
+        for (int w = 0; w < W; w++) opt[w] = (ob[w] & (Av[w] | Bv[w])) | (outside ? Av[w] : 0u);
+    }
+#pragma unroll
+    for (int w = 0; w < W; w++) a.B[((size_t)ent * W + w) * ni + t] = opt[w];
+}
+
+// Schedule 1 -- one thread walks the whole tree of its instance (any tree shape, two launches in total):
+// children before parents going up (parent[v] < v), root first going down.
+template <int W>
 __global__ void bep_forward_kernel(const BepArgs a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,108 +213,49 @@ __global__ void bep_forward_kernel(const BepArgs a)
     const int e = a.inst_e[t];
     const bool fwd = a.inst_fwd[t] != 0;
     const int n = a.nsym[t];
-    const int ntot = n + (a.recode_null ? 1 : 0);
     uint32_t valid[W];
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        const int lo = w * 32;
-        valid[w] = ntot >= lo + 32 ? 0xffffffffu : (ntot > lo ? (1u << (ntot - lo)) - 1u : 0u);
-    }
-    const size_t ni = (size_t)a.n_inst;
-    constexpr int P = 6;  // bit-sliced counters: up to 63 children per node
+    bep_valid_mask<W>(a, n, valid);
     for (int v = a.n_nodes - 1; v >= 0; v--) {
         const int ent = a.ent_of_node[v];
-        if (ent < 0) continue;
-        uint32_t plane[P][W];
-#pragma unroll
-        for (int p = 0; p < P; p++)
-#pragma unroll
-            for (int w = 0; w < W; w++) plane[p][w] = 0;
-        const int c0 = a.first[v], c1 = a.first[v + 1];
-        for (int ci = c0; ci < c1; ci++) {
-            const int u = a.kids[ci];
-            const int ue = a.ent_of_node[u];
-            uint32_t Ac[W];
-            if (ue >= 0) {
-#pragma unroll
-                for (int w = 0; w < W; w++) Ac[w] = a.A[((size_t)ue * W + w) * ni + t];
-            } else {
-                bep_leaf_set<W>(a, t, a.leaf_of_node[u], e, fwd, n, valid, Ac);
-            }
-            // counters += (state not in A_c)
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                uint32_t carry = ~Ac[w] & valid[w];
-#pragma unroll
-                for (int p = 0; p < P; p++) {
-                    const uint32_t s = plane[p][w] ^ carry;
-                    carry &= plane[p][w];
-                    plane[p][w] = s;
-                }
-            }
-        }
-        // states at the lowest count, and at the next one
-        const int nch = c1 - c0;
-        uint32_t Ab[W], Bb[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) { Ab[w] = 0; Bb[w] = 0; }
-        for (int k = 0; k <= nch; k++) {
-            uint32_t any = 0, m[W];
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                m[w] = valid[w];
-#pragma unroll
-                for (int p = 0; p < P; p++) m[w] &= ((k >> p) & 1) ? plane[p][w] : ~plane[p][w];
-                any |= m[w];
-            }
-            if (any) {
-#pragma unroll
-                for (int w = 0; w < W; w++) {
-                    Ab[w] = m[w];
-                    uint32_t m1 = valid[w];
-#pragma unroll
-                    for (int p = 0; p < P; p++) m1 &= (((k + 1) >> p) & 1) ? plane[p][w] : ~plane[p][w];
-                    Bb[w] = k + 1 <= nch ? m1 : 0u;
-                }
-                break;
-            }
-        }
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            a.A[((size_t)ent * W + w) * ni + t] = Ab[w];
-            a.B[((size_t)ent * W + w) * ni + t] = Bb[w];
-        }
+        if (ent >= 0) bep_node_forward<W>(a, t, v, ent, e, fwd, n, valid);
     }
 }
-
-// all optimal states of every internal node, root first (node 0; parent[v] < v); written over B, NULL symbol removed
-// at the end by the host (it has to take part in the propagation)
 template <int W>
 __global__ void bep_backward_kernel(const BepArgs a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_inst) return;
-    const size_t ni = (size_t)a.n_inst;
     for (int v = 0; v < a.n_nodes; v++) {
         const int ent = a.ent_of_node[v];
-        if (ent < 0) continue;
-        uint32_t Av[W], Bv[W], opt[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) { Av[w] = a.A[((size_t)ent * W + w) * ni + t]; Bv[w] = a.B[((size_t)ent * W + w) * ni + t]; }
-        const int par = a.parent[v];
-        if (par < 0) {
-#pragma unroll
-            for (int w = 0; w < W; w++) opt[w] = Av[w];
-        } else {
-            const int pe = a.ent_of_node[par];
-            uint32_t outside = 0, ob[W];
-#pragma unroll
-            for (int w = 0; w < W; w++) { ob[w] = a.B[((size_t)pe * W + w) * ni + t]; outside |= ob[w] & ~Av[w]; }
-#pragma unroll
-            for (int w = 0; w < W; w++) opt[w] = (ob[w] & (Av[w] | Bv[w])) | (outside ? Av[w] : 0u);
-        }
-#pragma unroll
-        for (int w = 0; w < W; w++) a.B[((size_t)ent * W + w) * ni + t] = opt[w];
+        if (ent >= 0) bep_node_backward<W>(a, t, v, ent);
+    }
+}
+
+// Schedule 2 -- one launch per height level, one thread per (instance, node of the level): the children of a
+// node sit on lower levels, its parent on a higher one.  (instance, node) parallelism instead of ~10,000 threads.
+template <int W>
+__global__ void bep_forward_level_kernel(const BepArgs a, const int32_t *nodes, int n_level)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_inst) return;
+    const int e = a.inst_e[t];
+    const bool fwd = a.inst_fwd[t] != 0;
+    const int n = a.nsym[t];
+    uint32_t valid[W];
+    bep_valid_mask<W>(a, n, valid);
+    for (int k = blockIdx.y; k < n_level; k += gridDim.y) {
+        const int v = nodes[k];
+        bep_node_forward<W>(a, t, v, a.ent_of_node[v], e, fwd, n, valid);
+    }
+}
+template <int W>
+__global__ void bep_backward_level_kernel(const BepArgs a, const int32_t *nodes, int n_level)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_inst) return;
+    for (int k = blockIdx.y; k < n_level; k += gridDim.y) {
+        const int v = nodes[k];
+        bep_node_backward<W>(a, t, v, a.ent_of_node[v]);
     }
 }
 
@@ -243,6 +289,36 @@ cudaError_t bep_launch_sweeps(const BepArgs &a, int W, cudaStream_t st)
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+
+
+template <int W>
+static cudaError_t bep_levels_impl(const BepArgs &a, const int32_t *d_nodes, const int32_t *level_off, int n_levels, cudaStream_t st)
+{
+    const unsigned gx = (a.n_inst + 127) / 128;
+    for (int h = 0; h < n_levels; h++) {
+        const int cnt = level_off[h + 1] - level_off[h];
+        if (cnt > 0) bep_forward_level_kernel<W><<<dim3(gx, cnt < 32768 ? cnt : 32768), 128, 0, st>>>(a, d_nodes + level_off[h], cnt);
+    }
+    for (int h = n_levels - 1; h >= 0; h--) {
+        const int cnt = level_off[h + 1] - level_off[h];
+        if (cnt > 0) bep_backward_level_kernel<W><<<dim3(gx, cnt < 32768 ? cnt : 32768), 128, 0, st>>>(a, d_nodes + level_off[h], cnt);
+    }
+    return cudaGetLastError();
+}
+
+// d_nodes: internal nodes grouped by height (device), level_off: [n_levels + 1] offsets (host), lowest level first
+cudaError_t bep_launch_sweeps_levels(const BepArgs &a, int W, const int32_t *d_nodes, const int32_t *level_off, int n_levels,
+                                     cudaStream_t st)
+{
+    if (a.n_inst == 0) return cudaSuccess;
+    switch (W) {
+    case 1: return bep_levels_impl<1>(a, d_nodes, level_off, n_levels, st);
+    case 2: return bep_levels_impl<2>(a, d_nodes, level_off, n_levels, st);
+    case 4: return bep_levels_impl<4>(a, d_nodes, level_off, n_levels, st);
+    case 8: return bep_levels_impl<8>(a, d_nodes, level_off, n_levels, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace bnk

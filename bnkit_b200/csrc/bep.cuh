@@ -29,5 +29,8 @@ cudaError_t bep_launch_next_prev(const uint8_t *obs, const int32_t *leaf_nodes, 
                                  cudaStream_t st);
 cudaError_t bep_launch_dict(const BepArgs &a, cudaStream_t st);
 cudaError_t bep_launch_sweeps(const BepArgs &a, int W, cudaStream_t st);  // forward + backward; W in {1, 2, 4, 8}
+// the same sweeps as one launch per height level (d_nodes: internal nodes grouped by height, lowest first)
+cudaError_t bep_launch_sweeps_levels(const BepArgs &a, int W, const int32_t *d_nodes, const int32_t *level_off, int n_levels,
+                                     cudaStream_t st);
 
 }  // namespace bnk

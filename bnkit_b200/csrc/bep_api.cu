@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -171,6 +172,19 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     for (int v = 0; v < n; v++)
         if (t->ent_of_node[v] < 0) { leaf_of_node[v] = (int32_t)leaf_nodes.size(); leaf_nodes.push_back(v); }
     const int n_leaves = (int)leaf_nodes.size();
+    // internal nodes grouped by height (1 = all children childless): the level schedule of the sweeps
+    int n_levels = 0;
+    for (int v = 0; v < n; v++) if (t->ent_of_node[v] >= 0) n_levels = std::max(n_levels, (int)t->height[v]);
+    std::vector<int32_t> level_off(n_levels + 1, 0), level_nodes(t->n_int);
+    for (int v = 0; v < n; v++) if (t->ent_of_node[v] >= 0) level_off[t->height[v]]++;
+    for (int h = 0; h < n_levels; h++) level_off[h + 1] += level_off[h];
+    {
+        std::vector<int32_t> fill(level_off.begin(), level_off.end() - 1);
+        for (int v = 0; v < n; v++) if (t->ent_of_node[v] >= 0) level_nodes[fill[t->height[v] - 1]++] = v;
+    }
+    // one launch per level pays while levels are wide; a very deep tree (caterpillar) keeps one thread per instance
+    bool by_levels = n_levels <= 4096;
+    if (const char *env = std::getenv("BNK_BEP_SCHEDULE")) by_levels = std::strcmp(env, "instance") != 0;
     // extant rows pass through; ancestors are filled in below
     for (int v = 0; v < n; v++) {
         uint8_t *row = present_out + (size_t)v * n_pos;
@@ -182,7 +196,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Dev<uint8_t> d_obs, d_fwd;
-    Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag;
+    Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag, d_level_nodes;
     Dev<uint32_t> d_A, d_B;
     const int MAXSYM = 255;
     // crippled ancestors after the first pass, patch rounds, largest symbol count, kernel launches,
@@ -211,10 +225,11 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         ~Pinned() { if (p) cudaFreeHost(p); }
     } pin_dict, pin_opt;
     const int32_t *h_dict = nullptr;
-    const uint32_t *h_opt = nullptr;
+    const uint32_t *h_opt = nullptr;  // optimal sets of ancestor rows opt_ent0 .. (a chunk, or all rows)
+    int opt_ent0 = 0;
 
     // one batch of instances through the device; results land in h_nsym / h_dict / h_opt ([ent][W][n_inst])
-    auto run = [&](const std::vector<int32_t> &ie, const std::vector<uint8_t> &ifw, int recode_null, int &W) -> int {
+    auto run = [&](const std::vector<int32_t> &ie, const std::vector<uint8_t> &ifw, int recode_null, int &W, bool copy_opt) -> int {
         int rc = BNK_OK;
         const int n_inst = (int)ie.size();
         const auto t0 = std::chrono::steady_clock::now();
@@ -239,15 +254,23 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         for (int x : h_nsym) mx = std::max(mx, x);
         info[2] = std::max(info[2], mx);
         W = mx + 1 <= 32 ? 1 : (mx + 1 <= 64 ? 2 : (mx + 1 <= 128 ? 4 : 8));
-        BEP_CUDA_TRY(bep_launch_sweeps(a, W, st));
+        if (by_levels) {
+            BEP_CUDA_TRY(bep_launch_sweeps_levels(a, W, d_level_nodes.p, level_off.data(), n_levels, st));
+            info[3] += 2 * n_levels;
+        } else {
+            BEP_CUDA_TRY(bep_launch_sweeps(a, W, st));
+            info[3] += 2;
+        }
         BEP_CUDA_TRY(cudaEventRecord(ev1, st));
-        info[3] += 2;
         BEP_CUDA_TRY(pin_dict.ensure(sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst));
-        BEP_CUDA_TRY(pin_opt.ensure(sizeof(uint32_t) * (size_t)n_int * W * n_inst));
         h_dict = static_cast<const int32_t *>(pin_dict.p);
-        h_opt = static_cast<const uint32_t *>(pin_opt.p);
         BEP_CUDA_TRY(cudaMemcpyAsync(pin_dict.p, d_dict.p, sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst, cudaMemcpyDeviceToHost, st));
-        BEP_CUDA_TRY(cudaMemcpyAsync(pin_opt.p, d_B.p, sizeof(uint32_t) * (size_t)n_int * W * n_inst, cudaMemcpyDeviceToHost, st));
+        if (copy_opt) {
+            BEP_CUDA_TRY(pin_opt.ensure(sizeof(uint32_t) * (size_t)n_int * W * n_inst));
+            h_opt = static_cast<const uint32_t *>(pin_opt.p);
+            opt_ent0 = 0;
+            BEP_CUDA_TRY(cudaMemcpyAsync(pin_opt.p, d_B.p, sizeof(uint32_t) * (size_t)n_int * W * n_inst, cudaMemcpyDeviceToHost, st));
+        }
         BEP_CUDA_TRY(cudaStreamSynchronize(st));
         info[4] += us_since(t0);
         {
@@ -261,7 +284,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     auto for_each_optimal = [&](int ent, int k, int n_inst, int W, auto &&fn) {
         const int ns = h_nsym[k];
         for (int w = 0; w < W; w++) {
-            uint32_t bits = h_opt[((size_t)ent * W + w) * n_inst + k];
+            uint32_t bits = h_opt[((size_t)(ent - opt_ent0) * W + w) * n_inst + k];
             while (bits) {
                 const int b = __builtin_ctz(bits);
                 bits &= bits - 1;
@@ -297,6 +320,8 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         BEP_CUDA_TRY(d_dict.alloc((size_t)MAXSYM * n_inst_max));
         BEP_CUDA_TRY(d_nsym.alloc(n_inst_max));
         BEP_CUDA_TRY(d_flag.alloc(1));
+        BEP_CUDA_TRY(d_level_nodes.alloc(level_nodes.size()));
+        BEP_CUDA_TRY(cudaMemcpyAsync(d_level_nodes.p, level_nodes.data(), sizeof(int32_t) * level_nodes.size(), cudaMemcpyHostToDevice, st));
         BEP_CUDA_TRY(cudaMemcpyAsync(d_obs.p, obs, (size_t)n * n_pos, cudaMemcpyHostToDevice, st));
         BEP_CUDA_TRY(cudaMemcpyAsync(d_leaf_nodes.p, leaf_nodes.data(), sizeof(int32_t) * n_leaves, cudaMemcpyHostToDevice, st));
         BEP_CUDA_TRY(cudaMemcpyAsync(d_leaf_of_node.p, leaf_of_node.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
@@ -343,38 +368,66 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                 BEP_CUDA_TRY(d_B.alloc((size_t)n_int * Wn * n_inst_max));
             }
         }
-        rc = run(ie, ifw, 1, W);
+        rc = run(ie, ifw, 1, W, false);
         if (rc != BNK_OK) goto done;
         {
             const int n_inst = (int)ie.size();
             const auto t0 = std::chrono::steady_clock::now();
             std::mutex mu;
-            parallel_slices(n_int, [&](int lo, int hi) {
-                Pog g;
-                std::vector<std::pair<int, int>> edges;
-                for (int ent = lo; ent < hi; ent++) {
-                    const int v = t->node_of_ent[ent];
-                    edges.clear();
-                    for (int k = 0; k < n_inst; k++) {
-                        if (h_nsym[k] < 1) continue;  // nothing to infer: the reference makes no Parsimony object (:1466-1468)
-                        const int i = ie[k] - 1;
-                        if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back({i, to}); });
-                        else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back({from, i}); });
+            // the optimal sets come back in chunks of ancestor rows through two page-locked buffers: the copy of
+            // chunk c + 1 runs while the host's threads assemble the graphs of chunk c
+            const size_t row_words = (size_t)W * n_inst;
+            const int chunk_rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_int, ((size_t)96 << 20) / (row_words * 4)));
+            const int n_chunks = (n_int + chunk_rows - 1) / chunk_rows;
+            BEP_CUDA_TRY(pin_opt.ensure(2 * (size_t)chunk_rows * row_words * 4));
+            uint32_t *buf[2] = {static_cast<uint32_t *>(pin_opt.p), static_cast<uint32_t *>(pin_opt.p) + (size_t)chunk_rows * row_words};
+            cudaEvent_t cev[2] = {nullptr, nullptr};
+            BEP_CUDA_TRY(cudaEventCreate(&cev[0]));
+            BEP_CUDA_TRY(cudaEventCreate(&cev[1]));
+            auto issue = [&](int c) -> cudaError_t {
+                const int lo = c * chunk_rows, hi = std::min(n_int, lo + chunk_rows);
+                cudaError_t e = cudaMemcpyAsync(buf[c & 1], d_B.p + (size_t)lo * row_words, (size_t)(hi - lo) * row_words * 4, cudaMemcpyDeviceToHost, st);
+                return e != cudaSuccess ? e : cudaEventRecord(cev[c & 1], st);
+            };
+            cudaError_t ce = issue(0);
+            for (int c = 0; c < n_chunks && ce == cudaSuccess; c++) {
+                if (c + 1 < n_chunks) ce = issue(c + 1);
+                if (ce == cudaSuccess) ce = cudaEventSynchronize(cev[c & 1]);
+                if (ce != cudaSuccess) break;
+                const int lo = c * chunk_rows, hi = std::min(n_int, lo + chunk_rows);
+                h_opt = buf[c & 1];
+                opt_ent0 = lo;
+                parallel_slices(hi - lo, [&](int slo, int shi) {
+                    Pog g;
+                    std::vector<std::pair<int, int>> edges;
+                    for (int ent = lo + slo; ent < lo + shi; ent++) {
+                        const int v = t->node_of_ent[ent];
+                        edges.clear();
+                        for (int k = 0; k < n_inst; k++) {
+                            if (h_nsym[k] < 1) continue;  // nothing to infer: the reference makes no Parsimony object (:1466-1468)
+                            const int i = ie[k] - 1;
+                            if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back({i, to}); });
+                            else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back({from, i}); });
+                        }
+                        std::sort(edges.begin(), edges.end());
+                        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                        g.from_edges(n_pos, edges);
+                        if (!g.is_contiguous()) {
+                            std::set<int> pr = g.protruding();
+                            std::lock_guard<std::mutex> lk(mu);
+                            crippled[v] = std::move(pr);
+                            crippled_edges[v] = edges;
+                        } else {
+                            g.nibble();  // GRASP.NIBBLE = true
+                            emit_row(v, g);
+                        }
                     }
-                    std::sort(edges.begin(), edges.end());
-                    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
-                    g.from_edges(n_pos, edges);
-                    if (!g.is_contiguous()) {
-                        std::set<int> pr = g.protruding();
-                        std::lock_guard<std::mutex> lk(mu);
-                        crippled[v] = std::move(pr);
-                        crippled_edges[v] = edges;
-                    } else {
-                        g.nibble();  // GRASP.NIBBLE = true
-                        emit_row(v, g);
-                    }
-                }
-            });
+                });
+            }
+            cudaStreamSynchronize(st);
+            cudaEventDestroy(cev[0]);
+            cudaEventDestroy(cev[1]);
+            BEP_CUDA_TRY(ce);
             info[5] += us_since(t0);
         }
         info[0] = (int)crippled.size();
@@ -386,7 +439,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
             const std::vector<int> cols(columns.begin(), columns.end());
             ie.clear(); ifw.clear();
             for (int idx : cols) { ie.push_back(std::abs(idx) + 1); ifw.push_back(idx > 0 ? 1 : 0); }
-            rc = run(ie, ifw, 0, W);
+            rc = run(ie, ifw, 0, W, true);
             if (rc != BNK_OK) goto done;
             info[1]++;
             const auto t0 = std::chrono::steady_clock::now();

@@ -131,10 +131,13 @@ def test_gpu_bep_c1_c2(bnk):
 
 
 @pytest.mark.gpu
-def test_gpu_bep_random_alignments(bnk):
+@pytest.mark.parametrize("schedule", ["levels", "instance"])
+def test_gpu_bep_random_alignments(bnk, schedule, monkeypatch):
     """Random trees (binary and multifurcating) and gappy alignments, including discontinuous ancestors that
-    go through the patch rounds; one case with more than 31 distinct edge targets (two-word bit sets)."""
+    go through the patch rounds; one case with more than 31 distinct edge targets (two-word bit sets).  Both
+    schedules of the device sweeps: one launch per height level, and one thread per instance walking the tree."""
     from oracle import bep
+    monkeypatch.setenv("BNK_BEP_SCHEDULE", schedule)
     rng = np.random.default_rng(7)
     patched = 0
     for trial in range(40):
