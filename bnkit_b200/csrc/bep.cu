@@ -57,29 +57,47 @@ __device__ __forceinline__ int bep_leaf_value(const BepArgs &a, int leaf, int e,
     return (fwd ? a.nxt : a.prv)[(size_t)leaf * (a.n_pos + 2) + e];
 }
 
-// distinct non-null leaf values of each instance, in first-occurrence order over the leaves (TreeInstance ctor)
-__global__ void bep_dict_kernel(const BepArgs a)
+// Symbols of an instance = its distinct non-null leaf values (TreeInstance ctor; the order is immaterial to the
+// bit-set sweeps, so values are numbered in ascending order).  Two passes over a byte map [instance][value + 1]:
+// every (leaf, instance) pair marks its value, then one warp per instance numbers the marked values (ballot +
+// prefix count), leaving symbol + 1 in the map -- the O(1) lookup the sweeps use for childless nodes -- and the
+// value of every symbol in dict[symbol][instance] for the host.
+__global__ void bep_mark_kernel(const BepArgs a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_inst) return;
     const int e = a.inst_e[t];
     const bool fwd = a.inst_fwd[t] != 0;
-    int n = 0;
-    for (int l = 0; l < a.n_leaves; l++) {
+    uint8_t *row = a.symmap + (size_t)t * (a.n_pos + 2);
+    for (int l = blockIdx.y; l < a.n_leaves; l += gridDim.y) {
         const int v = bep_leaf_value(a, l, e, fwd);
-        if (v == BEP_NONE) continue;
-        int k = 0;
-        while (k < n && a.dict[(size_t)k * a.n_inst + t] != v) k++;
-        if (k == n) {
-            if (n < a.max_sym) a.dict[(size_t)n * a.n_inst + t] = v;
-            n++;
-        }
+        if (v != BEP_NONE) row[v + 1] = 1;
     }
-    if (n > a.max_sym) { atomicOr(a.flag, 1); n = a.max_sym; }
-    a.nsym[t] = n;
+}
+__global__ void bep_number_kernel(const BepArgs a)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= a.n_inst) return;
+    uint8_t *row = a.symmap + (size_t)t * (a.n_pos + 2);
+    int n = 0;
+    for (int base = 0; base < a.n_pos + 2; base += 32) {
+        const int i = base + lane;
+        const bool on = i < a.n_pos + 2 && row[i] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int k = n + __popc(m & ((1u << lane) - 1u));
+            if (k < a.max_sym) { row[i] = (uint8_t)(k + 1); a.dict[(size_t)k * a.n_inst + t] = i - 1; }
+            else row[i] = 0;
+        }
+        n += __popc(m);
+    }
+    if (lane == 0) {
+        if (n > a.max_sym) { atomicOr(a.flag, 1); n = a.max_sym; }
+        a.nsym[t] = n;
+    }
 }
 
-// symbol bit of a childless node: its value's dictionary index, the NULL symbol, or "every state costs nothing"
+// symbol bit of a childless node: its value's symbol, the NULL symbol, or "every state costs nothing"
 template <int W>
 __device__ __forceinline__ void bep_leaf_set(const BepArgs &a, int t, int leaf, int e, bool fwd, int n, const uint32_t *valid,
                                              uint32_t *out)
@@ -95,9 +113,8 @@ __device__ __forceinline__ void bep_leaf_set(const BepArgs &a, int t, int leaf, 
         }
         return;
     }
-    int k = 0;
-    while (k < n && a.dict[(size_t)k * a.n_inst + t] != v) k++;
-    out[k >> 5] |= 1u << (k & 31);
+    const int k = (int)a.symmap[(size_t)t * (a.n_pos + 2) + v + 1] - 1;
+    if (k >= 0) out[k >> 5] |= 1u << (k & 31);
 }
 
 template <int W>
@@ -273,7 +290,11 @@ cudaError_t bep_launch_next_prev(const uint8_t *obs, const int32_t *leaf_nodes, 
 cudaError_t bep_launch_dict(const BepArgs &a, cudaStream_t st)
 {
     if (a.n_inst == 0) return cudaSuccess;
-    bep_dict_kernel<<<(a.n_inst + 127) / 128, 128, 0, st>>>(a);
+    cudaError_t e = cudaMemsetAsync(a.symmap, 0, (size_t)a.n_inst * (a.n_pos + 2), st);
+    if (e != cudaSuccess) return e;
+    if (a.n_leaves > 0)
+        bep_mark_kernel<<<dim3((a.n_inst + 127) / 128, a.n_leaves < 4096 ? a.n_leaves : 4096), 128, 0, st>>>(a);
+    bep_number_kernel<<<(a.n_inst + 3) / 4, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 

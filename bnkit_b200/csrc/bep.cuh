@@ -19,6 +19,7 @@ struct BepArgs {
     const int32_t *parent;
     int32_t recode_null;                 // GRASP.RECODE_NULL: childless nodes without a value carry a NULL symbol
     int32_t max_sym;                     // dictionary capacity (32 * W - 1: one bit is kept for NULL)
+    uint8_t *symmap;                     // [n_inst][n_pos + 2] value + 1 -> symbol + 1 (0: no leaf has the value)
     int32_t *dict;                       // [max_sym][n_inst] distinct leaf values of the instance
     int32_t *nsym;                       // [n_inst] number of them
     uint32_t *A, *B;                     // [n_int][W][n_inst]; B is overwritten by the optimal sets going down

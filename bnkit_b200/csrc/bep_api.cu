@@ -195,7 +195,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
 
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    Dev<uint8_t> d_obs, d_fwd;
+    Dev<uint8_t> d_obs, d_fwd, d_symmap;
     Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag, d_level_nodes;
     Dev<uint32_t> d_A, d_B;
     const int MAXSYM = 255;
@@ -242,7 +242,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         a.inst_e = d_inst_e.p; a.inst_fwd = d_fwd.p; a.n_inst = n_inst; a.n_pos = n_pos; a.n_nodes = n; a.n_leaves = n_leaves; a.n_int = n_int;
         a.nxt = d_nxt.p; a.prv = d_prv.p; a.first = d_first.p; a.kids = d_kids.p; a.leaf_of_node = d_leaf_of_node.p;
         a.ent_of_node = d_ent.p; a.parent = d_parent.p; a.recode_null = recode_null; a.max_sym = MAXSYM;
-        a.dict = d_dict.p; a.nsym = d_nsym.p; a.A = d_A.p; a.B = d_B.p; a.flag = d_flag.p;
+        a.dict = d_dict.p; a.nsym = d_nsym.p; a.A = d_A.p; a.B = d_B.p; a.flag = d_flag.p; a.symmap = d_symmap.p;
         BEP_CUDA_TRY(cudaEventRecord(ev0, st));
         BEP_CUDA_TRY(bep_launch_dict(a, st));
         info[3]++;
@@ -319,6 +319,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         BEP_CUDA_TRY(d_fwd.alloc(n_inst_max));
         BEP_CUDA_TRY(d_dict.alloc((size_t)MAXSYM * n_inst_max));
         BEP_CUDA_TRY(d_nsym.alloc(n_inst_max));
+        BEP_CUDA_TRY(d_symmap.alloc((size_t)n_inst_max * (n_pos + 2)));
         BEP_CUDA_TRY(d_flag.alloc(1));
         BEP_CUDA_TRY(d_level_nodes.alloc(level_nodes.size()));
         BEP_CUDA_TRY(cudaMemcpyAsync(d_level_nodes.p, level_nodes.data(), sizeof(int32_t) * level_nodes.size(), cudaMemcpyHostToDevice, st));
@@ -352,7 +353,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
             BEP_CUDA_TRY(cudaMemcpyAsync(d_fwd.p, ifw.data(), n_inst, cudaMemcpyHostToDevice, st));
             BEP_CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int32_t), st));
             a.inst_e = d_inst_e.p; a.inst_fwd = d_fwd.p; a.n_inst = n_inst; a.n_pos = n_pos; a.n_nodes = n; a.n_leaves = n_leaves;
-            a.nxt = d_nxt.p; a.prv = d_prv.p; a.max_sym = MAXSYM; a.dict = d_dict.p; a.nsym = d_nsym.p; a.flag = d_flag.p;
+            a.nxt = d_nxt.p; a.prv = d_prv.p; a.max_sym = MAXSYM; a.dict = d_dict.p; a.nsym = d_nsym.p; a.flag = d_flag.p; a.symmap = d_symmap.p;
             BEP_CUDA_TRY(bep_launch_dict(a, st));
             info[3]++;
             h_nsym.resize(n_inst);
