@@ -414,18 +414,26 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     ws->cgroups.clear(); ws->chunk_cgroups.clear(); ws->chunk_crecs.clear(); ws->ctiles.clear(); ws->chunk_ctiles.clear();
     ws->xtiles.clear(); ws->chunk_xtiles.clear();
     {   // warp-tiled walker geometry: W consumer warps of 6 x C columns per CTA.  Every CTA of the grid should be
-        // resident at once (a walk is one long dependent chain per column), so prefer the W that fills the
-        // SMs most evenly: cost = rounds of CTAs per SM x warps per CTA.
-        ws->xc = (ws->cfg_xc >= 1 && ws->cfg_xc <= 3) ? ws->cfg_xc : 2;
-        const int cw = warp_walk_cols_per_warp(ws->xc);
-        int best_w = 2; int64_t best_cost = -1;
-        for (int w = 2; w <= 4 && w * cw <= 64; w++) {
-            int64_t nt = 0;
-            for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
-            const int64_t cost = ((nt + ws->sm_count - 1) / ws->sm_count) * w;
-            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_w = w; }
+        // resident at once (a walk is one long dependent chain per column), so prefer the tile width that fills
+        // the SMs most evenly -- cost = rounds of CTAs per SM x columns per CTA -- and, for a given width, one
+        // column per lane (more warps to hide the shared-memory latency: C3b 35.5 vs 37.5 ms per step)
+        int best_w = 2, best_c = 1;
+        double best_cost = -1.0;
+        for (int c = 1; c <= 2; c++) {
+            if (ws->cfg_xc >= 1 && ws->cfg_xc <= 3 && c != ws->cfg_xc) continue;
+            const int cw = warp_walk_cols_per_warp(c);
+            for (int w = 2; w <= 7 && w * cw <= 64; w++) {
+                if (c == 2 && w > 4) continue;
+                int64_t nt = 0;
+                for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
+                const double cost = (double)((nt + ws->sm_count - 1) / ws->sm_count) * w * c * (c == 1 ? 1.0 : 1.06);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; best_c = c; }
+            }
         }
-        ws->xw = (ws->cfg_xw >= 1 && ws->cfg_xw <= 5 && ws->cfg_xw * cw <= 64) ? ws->cfg_xw : best_w;
+        ws->xc = (ws->cfg_xc >= 1 && ws->cfg_xc <= 3) ? ws->cfg_xc : best_c;
+        const int cw = warp_walk_cols_per_warp(ws->xc);
+        if (ws->cfg_xc == 3) best_w = 2;
+        ws->xw = (ws->cfg_xw >= 1 && ws->cfg_xw <= 7 && ws->cfg_xw * cw <= 64) ? ws->cfg_xw : best_w;
     }
     const int wt = wide_tile_cols(), cg = cherry_group_cols();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
@@ -578,7 +586,7 @@ static int ensure_rates(bnk_ws *ws, int32_t n_cols)
 static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_present, bool &general,
                           const uint8_t *&obs_s, const uint8_t *&present_s)
 {
-    const int n = ws->n, nc = ws->ncols;
+    const int nc = ws->ncols;
     general = d_present != nullptr;
     if (!general && ws->n_int > 0) {
         int32_t flag = 0;

@@ -36,7 +36,7 @@ constexpr int XPB = 4;             // walk-program ring: chunks of 32 steps
 constexpr int XTAB = XK * XK * 8;  // one table, bytes
 constexpr int XPROG = 256;         // byte offsets inside dynamic shared memory: barriers first, ...
 constexpr int XSTAGE0 = XPROG + XPB * 32 * (int)sizeof(Step);
-constexpr int XMAXNS = 8, XMAXW = 5;
+constexpr int XMAXNS = 8, XMAXW = 7;
 
 constexpr int XOBS = 128;          // a stage starts with the observed states: 2 children x 64 tile columns
 // area of one child inside a stage: its table (childless) or, going down, the stored up-messages of the tile
@@ -135,6 +135,7 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
 {
     const Step *prog = DOWN ? a.down : a.up;
     const int n_steps = a.n_steps;
+    if (n_steps <= 0) return;  // nothing to stream (and nobody would complete the first program chunk)
     const size_t ncols = (size_t)a.ncols;
     const size_t cat_off = (size_t)tile.cat0 * a.n_nodes * (XK * XK);
     const double *tab_node = (DOWN ? a.T_aux : a.T_col) + cat_off;

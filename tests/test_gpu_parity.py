@@ -127,7 +127,8 @@ def test_tile_geometries(bnk, oracle, tile_cols, cpt, monkeypatch):
                                  {"BNK_WARP_W": "3", "BNK_WARP_NS": "5", "BNK_WARP_C": "3"},
                                  {"BNK_WARP_W": "4", "BNK_WARP_NS": "8", "BNK_WARP_C": "2"},
                                  {"BNK_WARP_W": "5", "BNK_WARP_NS": "3", "BNK_WARP_C": "1"},
-                                 {"BNK_WARP_W": "1", "BNK_WARP_NS": "4", "BNK_WARP_C": "2"}, {"BNK_WALKER": "lean"}])
+                                 {"BNK_WARP_W": "1", "BNK_WARP_NS": "4", "BNK_WARP_C": "2"},
+                                 {"BNK_WARP_W": "7", "BNK_WARP_NS": "6", "BNK_WARP_C": "1"}, {"BNK_WALKER": "lean"}])
 def test_warp_tiled_walker(bnk, oracle, env, monkeypatch):
     """sweeps_warp.cu (warp-owned columns, TMA-fed stage ring) against the oracle for every CTA shape and ring
     depth, and against the lean CTA walker: deep chains (> 4 program chunks), category tiles narrower than a
