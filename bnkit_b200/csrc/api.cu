@@ -426,7 +426,9 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 if (c == 2 && w > 4) continue;
                 int64_t nt = 0;
                 for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
-                const double cost = (double)((nt + ws->sm_count - 1) / ws->sm_count) * w * c * (c == 1 ? 1.0 : 1.06);
+                const int64_t rounds = (nt + ws->sm_count - 1) / ws->sm_count;
+                // at equal cost fewer, wider CTAs win (one resident CTA per SM: no second producer, no imbalance)
+                const double cost = (double)rounds * w * c * (c == 1 ? 1.0 : 1.06) * (1.0 + 0.05 * (double)(rounds - 1));
                 if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; best_c = c; }
             }
         }
