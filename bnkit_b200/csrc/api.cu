@@ -105,11 +105,14 @@ struct bnk_ws {
     std::vector<std::pair<int, int>> chunk_ctiles;
     DevBuf<TileDesc> d_ctiles;
     // warp-tiled walker (sweeps_warp.cu): tiles of one category, <= 6 * xw columns
-    std::vector<TileDesc> xtiles;
-    std::vector<std::pair<int, int>> chunk_xtiles;
-    DevBuf<TileDesc> d_xtiles;
+    std::vector<TileDesc> xtiles, mtiles;  // mtiles: the DMMA sum-product variants (<= 8 * mw columns)
+    std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles;
+    DevBuf<TileDesc> d_xtiles, d_mtiles;
+    int mw = 0;                            // consumer warps per CTA of the DMMA variants
+    bool mma_down = false;                 // BNK_MMA_DOWN=1: the down-sweep on DMMA too (measured slower: 12.7 vs 11.7 ms on C3b)
     int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
-    int walker_mode = 0;                   // BNK_WALKER: 0 auto (warp-tiled where eligible), 1 lean CTA walker
+    int walker_mode = 0;                   // BNK_WALKER: 0 auto (warp-tiled where eligible), 1 lean CTA walker,
+                                           // 2 warp-tiled with the scalar sum-product kernels (no DMMA)
     int cfg_xw = 0, cfg_xns = 0, cfg_xc = 0;  // BNK_WARP_W / BNK_WARP_NS / BNK_WARP_C (tuning knobs, tests)
     bool no_cherry = false;                // BNK_NO_CHERRY=1: height-1 level through the plain level kernel (A/B, tests)
     std::vector<std::pair<int, int>> chunk_wtiles, chunk_cols;  // per chunk: wide tile range, sorted column range
@@ -210,7 +213,7 @@ static void ws_free(bnk_ws *ws)
     for (auto *b : di) b->release();
     ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
     ws->d_up_n.release(); ws->d_down_n.release(); ws->d_up_child_n.release(); ws->d_down_child_n.release();
-    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_xtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
+    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_xtiles.release(); ws->d_mtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
     if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
@@ -245,7 +248,10 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
-    if (const char *env = std::getenv("BNK_WALKER")) ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : 0;
+    if (const char *env = std::getenv("BNK_WALKER"))
+        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : 0);
+    if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
+    if (const char *env = std::getenv("BNK_MMA_DOWN")) ws->mma_down = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_WARP_W")) ws->cfg_xw = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_NS")) ws->cfg_xns = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_C")) ws->cfg_xc = std::atoi(env);
@@ -437,7 +443,21 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         if (ws->cfg_xc == 3) best_w = 2;
         ws->xw = (ws->cfg_xw >= 1 && ws->cfg_xw <= 7 && ws->cfg_xw * cw <= 64) ? ws->cfg_xw : best_w;
     }
+    {   // DMMA variants: 8 columns per warp, same cost model
+        int best_w = 2; double best_cost = -1.0;
+        const int cw = mma_walk_cols_per_warp();
+        for (int w = 2; w <= 7 && w * cw <= 64; w++) {
+            int64_t nt = 0;
+            for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
+            const int64_t rounds = (nt + ws->sm_count - 1) / ws->sm_count;
+            const double cost = (double)rounds * w * (1.0 + 0.05 * (double)(rounds - 1));
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
+        }
+        if (ws->mw < 0 && -ws->mw <= 7) ws->mw = ws->mw;  // forced by BNK_MMA_W (kept negative as the marker)
+        else ws->mw = best_w;
+    }
     const int wt = wide_tile_cols(), cg = cherry_group_cols();
+    ws->mtiles.clear(); ws->chunk_mtiles.clear();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
         const int hi = std::min(ncat, lo + cats_per_chunk);
         Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
@@ -459,6 +479,18 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 for (int q = 0; q < nt; q++) {
                     const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
                     ws->xtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+                }
+            }
+        }
+        const int m0 = (int)ws->mtiles.size();
+        {
+            const int mt = std::abs(ws->mw) * mma_walk_cols_per_warp();
+            for (int k = lo; k < hi; k++) {
+                const int nc = cat_begin[k + 1] - cat_begin[k];
+                const int nt = (nc + mt - 1) / mt;
+                for (int q = 0; q < nt; q++) {
+                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                    ws->mtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
                 }
             }
         }
@@ -503,6 +535,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             ws->chunk_crecs.push_back(crecs);
             ws->chunk_ctiles.push_back({ct0, (int)ws->ctiles.size()});
             ws->chunk_xtiles.push_back({x0, (int)ws->xtiles.size()});
+            ws->chunk_mtiles.push_back({m0, (int)ws->mtiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
         }
     }
@@ -522,6 +555,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_cgroups, ws->cgroups, ws->stream));
     TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
     TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
+    TRY(upload(ws->d_mtiles, ws->mtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
     ws->rates_null = rates == nullptr;
@@ -645,6 +679,9 @@ struct WalkSetup {
     bool hybrid = false;  // wide height levels run as level launches (wide.cu); the walker takes the narrow top
     bool warp = false;    // fast, and the warp-tiled kernels of sweeps_warp.cu take the walk
     int xw = 0, xc = 0, xns = 0, n_xtiles = 0;
+    bool mma = false;     // warp, and the sum-product sweeps run the DMMA variants
+    int mw = 0, mns = 0, n_mtiles = 0;
+    const TileDesc *mtiles = nullptr;
     int tb_slots = 0;
 };
 
@@ -679,7 +716,8 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
     // one category per tile, whole stack in shared memory
     s.fast = false; s.hybrid = false;
     s.warp = false;
-    if (!general && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode == 0) {
+    s.mma = false;
+    if (!general && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode != 1) {
         const bool hybrid = t->wide_h > 0 && !ws->no_wide;
         const int slots = use_program(hybrid);
         // ring stages: as many as let two CTAs share an SM (the grid is sized to be resident at once)
@@ -692,6 +730,17 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
             s.n_xtiles = ws->chunk_xtiles[ci].second - ws->chunk_xtiles[ci].first;
             s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
             s.a.smem_slots = slots;
+            if (ws->walker_mode == 0) {  // sum-product sweeps: the DMMA variants
+                const int mw = std::abs(ws->mw);
+                int mns = ws->cfg_xns >= 2 && ws->cfg_xns <= 8 ? ws->cfg_xns : 8;
+                if (!(ws->cfg_xns >= 2 && ws->cfg_xns <= 8))
+                    while (mns > 3 && mma_walk_smem_bytes(mw, mns, slots, want_down) > (size_t)ws->smem_optin / 2 - 1024) mns--;
+                if (mma_walk_smem_bytes(mw, mns, slots, want_down) <= (size_t)ws->smem_optin) {
+                    s.mma = true; s.mw = mw; s.mns = mns;
+                    s.n_mtiles = ws->chunk_mtiles[ci].second - ws->chunk_mtiles[ci].first;
+                    s.mtiles = ws->d_mtiles.p + ws->chunk_mtiles[ci].first;
+                }
+            }
             return BNK_OK;
         }
     }
@@ -971,8 +1020,10 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
                 s.a.esum_wide = ws->d_esum_wide.p;
             }
         }
-        CUDA_TRY(s.warp ? launch_sum_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
-                        : s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
+        if (s.mma) s.a.tiles = s.mtiles;
+        CUDA_TRY(s.mma ? launch_sum_up_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
+                 : s.warp ? launch_sum_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+                          : s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
         ws->launches++;
         CUDA_TRY(cudaEventRecord(ws->ev[3][1], ws->stream));
         ws->ev_valid[3] = true;
@@ -986,8 +1037,10 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
                 s.a.tmsg = ws->d_tmsg.p;
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
-            CUDA_TRY(s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
-                            : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
+            if (s.mma && !ws->mma_down) s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
+            CUDA_TRY(s.mma && ws->mma_down ? launch_sum_down_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
+                     : s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+                              : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;
             if (s.hybrid) {
                 w.tmsg = ws->d_tmsg.p; w.out_post = d_out_post; w.qrow = s.a.qrow;

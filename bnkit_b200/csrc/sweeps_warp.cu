@@ -160,24 +160,27 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
             mbar_wait(g.bar_prog + (chunk_ready & (XPB - 1)) * 8, (chunk_ready >> 2) & 1);
         }
     };
-    // observed states of childless child e of step i: byte 0 = column `lane`, byte 1 = column `lane + 32`
-    auto fetch_obs = [&](int i, int e) -> int {
+    // observed states of childless child e of step i for tile columns `lane` (half 0) and `lane + 32` (half 1).
+    // The loaded byte must not be touched before it is stored XPD steps later: any arithmetic on it here would
+    // make the producer wait for DRAM once per step (it did: profiles/r1_v18 -- one step per memory round trip).
+    auto fetch_obs = [&](int i, int e, int half) -> uint8_t {
         const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
         const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
         const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
-        if (!(cn >= 0 && ce < 0)) return BNK_NONE | (BNK_NONE << 8);
-        const size_t off = (size_t)(unsigned)cn * ncols;
-        return (int)obs_a[off] | ((int)obs_b[off] << 8);
+        const bool leaf = cn >= 0 && ce < 0;  // childless child
+        const uint8_t *src = (half == 0 ? obs_a : obs_b) + (size_t)(unsigned)(leaf ? cn : 0) * ncols;
+        return leaf ? *src : (uint8_t)BNK_NONE;
     };
     issue_chunk(0);
     issue_chunk(1);
     need_chunk(0);
-    int o0[XPD], o1[XPD];
+    uint8_t o[2][2][XPD];  // [child][column half][ring position]
 #pragma unroll
-    for (int k = 0; k < XPD; k++) {
-        o0[k] = k < n_steps ? fetch_obs(k, 0) : 0;
-        o1[k] = k < n_steps ? fetch_obs(k, 1) : 0;
-    }
+    for (int k = 0; k < XPD; k++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) o[e][hf][k] = k < n_steps ? fetch_obs(k, e, hf) : (uint8_t)BNK_NONE;
     int s = 0, ph = 0;
     for (int i0 = 0; i0 < n_steps; i0 += XPD) {
 #pragma unroll
@@ -193,10 +196,10 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
                 const int ce0 = XSTEP(po, c_ent[0]), ce1 = XSTEP(po, c_ent[1]);
                 const int cs0 = XSTEP(po, c_slot[0]), cs1 = XSTEP(po, c_slot[1]);
                 const int so = XSTAGE0 + s * g.stage_bytes;
-                smem_raw[so + lane] = (unsigned char)o0[k];
-                smem_raw[so + 32 + lane] = (unsigned char)(o0[k] >> 8);
-                smem_raw[so + 64 + lane] = (unsigned char)o1[k];
-                smem_raw[so + 96 + lane] = (unsigned char)(o1[k] >> 8);
+                smem_raw[so + lane] = o[0][0][k];
+                smem_raw[so + 32 + lane] = o[0][1][k];
+                smem_raw[so + 64 + lane] = o[1][0][k];
+                smem_raw[so + 96 + lane] = o[1][1][k];
                 const unsigned bar = g.bar_full + s * 8;
                 if (lane == 0) {
                     const bool tn = parent >= 0;  // a root contracts with the unit table / uses the prior
@@ -216,8 +219,10 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
                 const int ip = i + XPD;
                 if (ip < n_steps) {
                     need_chunk(ip >> 5);
-                    o0[k] = fetch_obs(ip, 0);
-                    o1[k] = fetch_obs(ip, 1);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++) o[e][hf][k] = fetch_obs(ip, e, hf);
                 }
                 if (++s == ns) { s = 0; ph ^= 1; }
             }
@@ -666,6 +671,314 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
 }
 
 // ------------------------------------------------------------------------------------
+// Sum-product sweeps on the FP64 tensor-core path (DMMA.8x8x4, mma.sync m8n8k4).
+//
+// The contraction of a step, out[p][col] = sum_x T[p][x] * G[x][col], is a 20 x 20 by 20 x 8 matrix product once a
+// warp owns 8 columns.  What that buys here is not flops but shared-memory traffic, the walkers' bound: an A
+// fragment is ONE 8-byte load per lane (conflict-free on the raw table layout) and feeds all 8 columns, and the
+// B fragments -- G itself -- are built in registers straight from the children's data, so the exchange buffer and
+// its 10 LDS.128 per column disappear: ~15 shared-memory wavefronts per column and step instead of ~37.
+// Fragment layout (PTX ISA, mma.m8n8k4 .f64): A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4],
+// C/D[row = lane / 4][col = 2 (lane % 4) + {0, 1}].  Rows 20..23 of the third row tile are padding: they read
+// whatever follows the table row and are never stored.  Max-product has no such form; the joint sweep keeps
+// up_warp_kernel.  Tolerance-checked (1e-9) like every sum-product kernel; the accumulation order inside a DMMA
+// differs from the scalar kernels'.
+// ------------------------------------------------------------------------------------
+namespace {
+constexpr int MCW = 8;  // columns per warp
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#define XS_D(off) (*reinterpret_cast<double *>(smem_raw + (off)))
+
+struct MLane {
+    int xr, g;            // lane % 4, lane / 4
+    int lcb, colb, ocolb; // the column this lane feeds as B operand (g)
+    int lcc[2], colc[2], ocolc[2];  // the two columns it holds results for (2 xr + i)
+    __device__ MLane(const WalkArgs &a, const TileDesc &tile, int warp, int lane)
+    {
+        xr = lane & 3; g = lane >> 2;
+        lcb = warp * MCW + g;
+        if (lcb >= tile.ncols) lcb = tile.ncols - 1;
+        colb = tile.col0 + lcb; ocolb = a.orig_col[colb];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            lcc[i] = warp * MCW + 2 * xr + i;
+            if (lcc[i] >= tile.ncols) lcc[i] = tile.ncols - 1;
+            colc[i] = tile.col0 + lcc[i]; ocolc[i] = a.orig_col[colc[i]];
+        }
+    }
+};
+__host__ __device__ inline int m_warp_bytes(int slots) { return (slots + 1) * MCW * XK * 8; }
+}  // namespace
+
+__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const XGeom g = x_setup(sbase, W, ns, chb);
+    if (warp == W) {
+        x_producer<false>(a, tile, g, smem_raw, sbase, ns, lane);
+        return;
+    }
+    const MLane L(a, tile, warp, lane);
+    const int n_steps = a.n_steps;
+    const size_t ncols = (size_t)a.ncols;
+    const int slot_bytes = MCW * XK * 8;  // [column][20]
+    const int stack0 = XSTAGE0 + ns * g.stage_bytes + warp * m_warp_bytes(a.smem_slots);
+    const int dummy = stack0 + a.smem_slots * slot_bytes;
+    const unsigned FULL = 0xffffffffu;
+    double prior5[5];
+#pragma unroll
+    for (int kt = 0; kt < 5; kt++) prior5[kt] = a.prior[4 * kt + L.xr];
+    int esum = 0;        // of column L.colb (identical in the 4 lanes of a group)
+    double logacc = 0.0;
+
+    int s = 0, ph = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
+        const bool rootstep = XSTEP(po, parent) < 0;
+        const int so = XSTAGE0 + s * g.stage_bytes;
+        mbar_wait(g.bar_full + s * 8, ph);
+        // ---- G as B fragments: entries x = 4 kt + xr of column g ----
+        double G[5];
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++) G[kt] = rootstep ? prior5[kt] : 1.0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
+            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
+            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
+            double cv[5];
+            if (cs >= 0) {
+                const int src = stack0 + cs * slot_bytes + L.g * (XK * 8) + L.xr * 8;
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) cv[kt] = XS_D(src + kt * 32);
+            } else if (cs == SLOT_WIDE) {
+                const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + L.colb;
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) cv[kt] = src[(size_t)(4 * kt + L.xr) * ncols];
+            } else if (cn >= 0) {
+                const int tb = so + XOBS + XTAB + e * g.chb + L.xr * 8;
+                const int ob = smem_raw[so + e * 64 + L.lcb];
+                if (ob != BNK_NONE) {
+#pragma unroll
+                    for (int kt = 0; kt < 5; kt++) cv[kt] = XS_D(tb + ob * (XK * 8) + kt * 32);
+                } else {  // uninstantiated childless node: marginalise its own state
+#pragma unroll
+                    for (int kt = 0; kt < 5; kt++) cv[kt] = 0.0;
+                    for (int x = 0; x < XK; x++) {
+#pragma unroll
+                        for (int kt = 0; kt < 5; kt++) cv[kt] += XS_D(tb + x * (XK * 8) + kt * 32);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) cv[kt] = 1.0;
+            }
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++) G[kt] *= cv[kt];
+        }
+        int mhi = 0;
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++) mhi = max(mhi, __double2hiint(G[kt]));
+        mhi = max(mhi, __shfl_xor_sync(FULL, mhi, 1));
+        mhi = max(mhi, __shfl_xor_sync(FULL, mhi, 2));
+        int eb;
+        const double scale_b = x_pow2_scale(mhi, eb);  // of column g
+        esum += eb;
+        if (!rootstep) {
+            // ---- out[p][col] = sum_x T[x][p] G[x][col]: 3 row tiles x 5 k tiles ----
+            const int tv = so + XOBS + L.xr * (XK * 8) + L.g * 8;
+            double D[3][2];
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) {  // two accumulator chains per row tile (k tiles 0, 2, 4 and 1, 3): shorter dependent chains
+                double E0 = 0.0, E1 = 0.0;
+                D[mt][0] = 0.0; D[mt][1] = 0.0;
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) {
+                    const double av = XS_D(tv + kt * (4 * XK * 8) + mt * 64);
+                    if (kt & 1) dmma(E0, E1, av, G[kt]);
+                    else dmma(D[mt][0], D[mt][1], av, G[kt]);
+                }
+                D[mt][0] += E0; D[mt][1] += E1;
+            }
+            double sc[2];
+            sc[0] = __shfl_sync(FULL, scale_b, 8 * L.xr);      // lane 4 * (2 xr)
+            sc[1] = __shfl_sync(FULL, scale_b, 8 * L.xr + 4);  // lane 4 * (2 xr + 1)
+            const int sdst = slot >= 0 ? stack0 + slot * slot_bytes : dummy;
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) {
+                const int p = 8 * mt + L.g;
+                if (p < XK) {
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; c2++) {
+                        const double m = D[mt][c2] * sc[c2];
+                        XS_D(sdst + (2 * L.xr + c2) * (XK * 8) + p * 8) = m;
+                        if (a.msg) a.msg[((size_t)(unsigned)ent * ncols + L.colc[c2]) * XK + p] = m;
+                    }
+                }
+            }
+        } else {  // unit table: the column's total, into the log-likelihood
+            double tot = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++) tot += G[kt];
+            tot += __shfl_xor_sync(FULL, tot, 1);
+            tot += __shfl_xor_sync(FULL, tot, 2);
+            logacc += log(tot * scale_b);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
+        if (++s == ns) { s = 0; ph ^= 1; }
+    }
+    if (a.out_logl && L.xr == 0) {
+        const int ew = a.esum_wide ? a.esum_wide[L.colb] : 0;
+        a.out_logl[L.ocolb] = logacc + (double)(esum + ew) * 0.693147180559945309417232121458;
+    }
+}
+
+__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const XGeom g = x_setup(sbase, W, ns, chb);
+    if (warp == W) {
+        x_producer<true>(a, tile, g, smem_raw, sbase, ns, lane);
+        return;
+    }
+    const MLane L(a, tile, warp, lane);
+    const int n_steps = a.n_steps;
+    const size_t ncols = (size_t)a.ncols;
+    const int slot_bytes = MCW * XK * 8;
+    const int stack0 = XSTAGE0 + ns * g.stage_bytes + warp * m_warp_bytes(a.smem_slots);
+    const int dummy = stack0 + a.smem_slots * slot_bytes;
+    const unsigned FULL = 0xffffffffu;
+    double prior3[3];
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++) prior3[mt] = a.prior[8 * mt + L.g < XK ? 8 * mt + L.g : 0];
+
+    int s = 0, ph = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
+        const bool rootstep = XSTEP(po, parent) < 0;
+        const int so = XSTAGE0 + s * g.stage_bytes;
+        mbar_wait(g.bar_full + s * 8, ph);
+        // ---- from-above vector D[x][col] = sum_p P[p][x] T[p][col], scaled by a power of two per column ----
+        double D[3][2];
+        if (!rootstep) {
+            const int tsrc = (slot >= 0 ? stack0 + slot * slot_bytes : dummy) + L.g * (XK * 8) + L.xr * 8;
+            double T[5];
+            int mhi = 0;
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++) { T[kt] = XS_D(tsrc + kt * 32); mhi = max(mhi, __double2hiint(T[kt])); }
+            mhi = max(mhi, __shfl_xor_sync(FULL, mhi, 1));
+            mhi = max(mhi, __shfl_xor_sync(FULL, mhi, 2));
+            int eb;
+            const double scale_b = x_pow2_scale(mhi, eb);
+            const int tv = so + XOBS + L.xr * (XK * 8) + L.g * 8;  // P[p = 4 kt + xr][x = 8 mt + g]
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) {
+                D[mt][0] = 0.0; D[mt][1] = 0.0;
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) dmma(D[mt][0], D[mt][1], XS_D(tv + kt * (4 * XK * 8) + mt * 64), T[kt]);
+            }
+            const double sc0 = __shfl_sync(FULL, scale_b, 8 * L.xr), sc1 = __shfl_sync(FULL, scale_b, 8 * L.xr + 4);
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) { D[mt][0] *= sc0; D[mt][1] *= sc1; }
+        } else {
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) { D[mt][0] = prior3[mt]; D[mt][1] = prior3[mt]; }
+        }
+        // ---- children, in result layout: x = 8 mt + g (rows >= 20 are padding), columns 2 xr + {0, 1} ----
+        double cv[2][3][2];
+        int cslot[2], cent[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
+            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
+            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
+            cslot[e] = cs; cent[e] = ce;
+            const int area = so + XOBS + XTAB + e * g.chb;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++) {
+                const int ob = (cs != SLOT_WIDE && ce < 0 && cn >= 0) ? (int)smem_raw[so + e * 64 + L.lcc[c2]] : BNK_NONE;
+#pragma unroll
+                for (int mt = 0; mt < 3; mt++) {
+                    const int x = 8 * mt + L.g < XK ? 8 * mt + L.g : XK - 1;  // padding rows repeat row 19 (never stored)
+                    double v;
+                    if (cs == SLOT_WIDE) v = a.msg[((size_t)(unsigned)ce * XK + x) * ncols + L.colc[c2]];
+                    else if (ce >= 0) v = XS_D(area + L.lcc[c2] * (XK * 8) + x * 8);  // up-message that came with the stage
+                    else if (cn >= 0) {
+                        if (ob != BNK_NONE) v = XS_D(area + ob * (XK * 8) + x * 8);
+                        else {
+                            v = 0.0;
+                            for (int y = 0; y < XK; y++) v += XS_D(area + y * (XK * 8) + x * 8);
+                        }
+                    } else v = 1.0;
+                    cv[e][mt][c2] = v;
+                }
+            }
+        }
+        double U[3][2], sum[2] = {0.0, 0.0};
+        const int d0 = cslot[0] >= 0 ? stack0 + cslot[0] * slot_bytes : dummy;
+        const int d1 = cslot[1] >= 0 ? stack0 + cslot[1] * slot_bytes : dummy;
+        // this node's own slot was read above by every lane of the warp before any lane gets here? not necessarily:
+        // order the reads of T before the stores to the children's slots (they never alias T's slot, but dummy may)
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 3; mt++) {
+            const int x = 8 * mt + L.g;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++) {
+                const double t0 = D[mt][c2] * cv[1][mt][c2], t1 = D[mt][c2] * cv[0][mt][c2];
+                U[mt][c2] = D[mt][c2] * (cv[0][mt][c2] * cv[1][mt][c2]);
+                if (x < XK) {
+                    sum[c2] += U[mt][c2];
+                    const int off = (2 * L.xr + c2) * (XK * 8) + x * 8;
+                    XS_D(d0 + off) = t0;
+                    XS_D(d1 + off) = t1;
+                    if (cslot[0] == SLOT_WIDE) a.tmsg[((size_t)(unsigned)cent[0] * XK + x) * ncols + L.colc[c2]] = t0;
+                    if (cslot[1] == SLOT_WIDE) a.tmsg[((size_t)(unsigned)cent[1] * XK + x) * ncols + L.colc[c2]] = t1;
+                }
+            }
+        }
+        // ---- normalise and emit the posterior: column totals over the 8 lanes that share xr ----
+        const int q0 = a.qrow ? a.qrow[ent] : ent;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; c2++) {
+            sum[c2] += __shfl_xor_sync(FULL, sum[c2], 4);
+            sum[c2] += __shfl_xor_sync(FULL, sum[c2], 8);
+            sum[c2] += __shfl_xor_sync(FULL, sum[c2], 16);
+        }
+        if (a.out_post && q0 >= 0) {
+#pragma unroll
+            for (int c2 = 0; c2 < 2; c2++) {
+                const double r = x_rcp(sum[c2]);
+                double *dst = a.out_post + ((size_t)(unsigned)q0 * ncols + L.ocolc[c2]) * XK;
+#pragma unroll
+                for (int mt = 0; mt < 3; mt++) {
+                    const int x = 8 * mt + L.g;
+                    if (x < XK) dst[x] = U[mt][c2] * r;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
+        if (++s == ns) { s = 0; ph ^= 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 int warp_walk_cols_per_warp(int C) { return XCW * C; }
 size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down)
 {
@@ -703,5 +1016,25 @@ cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, i
     if (C == 3) return launch_warp(down_warp_kernel<3>, a, n_tiles, W, C, ns, true, st);
     return cudaErrorInvalidValue;
 }
+
+
+// DMMA variants: 8 columns per warp, tiles of at most 8 W columns
+int mma_walk_cols_per_warp() { return MCW; }
+size_t mma_walk_smem_bytes(int W, int ns, int slots, bool down)
+{
+    return (size_t)XSTAGE0 + (size_t)ns * x_stage_bytes(x_child_bytes(W * MCW, down)) + (size_t)W * m_warp_bytes(slots);
+}
+template <typename KernelT>
+static cudaError_t launch_mma(KernelT kern, const WalkArgs &a, int n_tiles, int W, int ns, bool down, cudaStream_t st)
+{
+    if (W < 1 || W > XMAXW || ns < 2 || ns > XMAXNS || W * MCW > 64) return cudaErrorInvalidValue;
+    const size_t smem = mma_walk_smem_bytes(W, ns, a.smem_slots, down);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<n_tiles, (W + 1) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * MCW, down));
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_up_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st) { return launch_mma(up_mma_kernel, a, n_tiles, W, ns, false, st); }
+cudaError_t launch_sum_down_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st) { return launch_mma(down_mma_kernel, a, n_tiles, W, ns, true, st); }
 
 }  // namespace bnk
