@@ -127,6 +127,25 @@ def cpu_oracle_rate(spec, model_name, parent, dist, rates, obs, budget_s, thread
         nc, obs.shape[1], len(parent), threads, t), t
 
 
+def host_memory_available():
+    """Bytes of host memory this process may still take: free memory, capped by the cgroup limit if there is one."""
+    avail = None
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    try:
+        mx = open("/sys/fs/cgroup/memory.max").read().strip()
+        if mx != "max":
+            cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+            lim = int(mx) - cur
+            avail = lim if avail is None else min(avail, lim)
+    except Exception:
+        pass
+    return avail if avail is not None else 1 << 62
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,15 +294,33 @@ def main():
     if loop_mode:
         args.no_e2e = True
         args.no_cpu = True
+    e2e_cols = n_cols
     if not args.no_e2e:
-        h_obs = torch.from_numpy(obs).pin_memory()
-        h_state = torch.empty((n, n_cols), dtype=torch.uint8).pin_memory()
-        h_post = torch.empty((n_int, n_cols, K), dtype=torch.float64).pin_memory()
-        h_logl = np.empty(n_cols)
+        # The leg pins n_int x n_cols x K doubles of host memory per rank (8 GB at C3).  On a box whose host memory
+        # (or cgroup limit) cannot hold that for every local rank, the leg runs on a column prefix instead and says
+        # so: the rate is D2H-bound per column either way.  Rank 0 decides for everybody.
+        need = n_int * n_cols * K * 8 + 3 * n * n_cols
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        avail = host_memory_available()
+        budget = 0.5 * avail / max(local_world, 1)
+        if need > budget:
+            e2e_cols = max(64, min(n_cols, int(n_cols * budget / need)))
+        if os.environ.get("BNK_BENCH_E2E_COLS"):
+            e2e_cols = min(n_cols, int(os.environ["BNK_BENCH_E2E_COLS"]))
+        if world > 1:
+            tcols = torch.tensor([e2e_cols], dtype=torch.int64, device=dev)
+            dist_.broadcast(tcols, src=0)
+            e2e_cols = int(tcols[0])
+        e_obs = obs if e2e_cols == n_cols else np.ascontiguousarray(obs[:, :e2e_cols])
+        e_rates = rates if (rates is None or e2e_cols == n_cols) else np.ascontiguousarray(rates[:e2e_cols])
+        h_obs = torch.from_numpy(e_obs).pin_memory()
+        h_state = torch.empty((n, e2e_cols), dtype=torch.uint8).pin_memory()
+        h_post = torch.empty((n_int, e2e_cols, K), dtype=torch.float64).pin_memory()
+        h_logl = np.empty(e2e_cols)
         def step_e2e():
-            ws.set_rates(n_cols, rates)
-            lib.check(lib.lib().bnk_joint(ws.h, n_cols, h_obs.data_ptr(), None, h_state.data_ptr()))
-            lib.check(lib.lib().bnk_marginal(ws.h, n_cols, h_obs.data_ptr(), None, None, -1, h_post.data_ptr(),
+            ws.set_rates(e2e_cols, e_rates)
+            lib.check(lib.lib().bnk_joint(ws.h, e2e_cols, h_obs.data_ptr(), None, h_state.data_ptr()))
+            lib.check(lib.lib().bnk_marginal(ws.h, e2e_cols, h_obs.data_ptr(), None, None, -1, h_post.data_ptr(),
                                              h_logl.ctypes.data))
         step_e2e()
         barrier()
@@ -293,8 +330,8 @@ def main():
             step_e2e()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
-        h2d = 2 * n * n_cols
-        d2h = n * n_cols + n_int * n_cols * K * 8 + n_cols * 8
+        h2d = 2 * n * e2e_cols
+        d2h = n * e2e_cols + n_int * e2e_cols * K * 8 + e2e_cols * 8
         # parity of what came back (cheap invariants): posteriors sum to 1, states in range
         assert abs(float(h_post[0, 0].sum()) - 1.0) < 1e-9 and int(h_state.max()) < K
     # ---- max over ranks
@@ -349,8 +386,11 @@ def main():
                          "per_kernel": per_kernel},
             "clocks": clocks}
     if not args.no_e2e:
-        line["e2e"] = {"value": updates_step / (e2emax * 1e-3), "unit": "updates/s", "ms_per_step": e2emax,
+        line["e2e"] = {"value": updates_step * (e2e_cols / n_cols) / (e2emax * 1e-3), "unit": "updates/s", "ms_per_step": e2emax,
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        if e2e_cols != n_cols:
+            line["e2e"]["note"] = ("host memory limit: this leg ran on the first %d of %d columns per GPU "
+                                   "(it pins %.1f GB per rank at full width)" % (e2e_cols, n_cols, need / 1e9))
     if world == 1 and not args.no_cpu:
         v, sample, _ = cpu_oracle_rate(spec, spec["model"], parent, dist, rates, obs, args.cpu_budget, threads)
         line["cpu_baseline"] = {"value": v, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample}
