@@ -167,6 +167,46 @@ def test_gpu_bep_random_alignments(bnk, schedule, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_gpu_bep_edge_cases(bnk):
+    """Degenerate inputs: a single column, all-gap columns, an empty sequence, every sequence empty, two leaves,
+    a star tree, a gap-free alignment (every ancestor present everywhere)."""
+    from oracle import bep
+    rng = np.random.default_rng(3)
+
+    def check(parent, obs):
+        parent = np.asarray(parent, np.int32)
+        has_child = np.zeros(len(parent), bool)
+        has_child[parent[parent >= 0]] = True
+        rows = [None if has_child[v] else (obs[v] != NONE).tolist() for v in range(len(parent))]
+        want, _ = bep.presence_mask(parent.tolist(), rows, obs.shape[1])
+        got = bnk.Tree(parent, np.full(len(parent), 0.1)).bep_presence(obs)
+        assert np.array_equal(got, np.asarray(want, np.uint8))
+        return got
+
+    two = [-1, 0, 0]
+    for n_pos in (1, 2, 7):
+        for trial in range(6):
+            obs = np.full((3, n_pos), NONE, np.uint8)
+            obs[1:] = np.where(rng.random((2, n_pos)) < 0.5, 0, NONE)
+            check(two, obs)
+    parent, _ = random_tree(rng, 12)
+    leaves = np.nonzero(np.bincount(parent[parent >= 0], minlength=len(parent)) == 0)[0]
+    obs = np.full((len(parent), 9), NONE, np.uint8)
+    check(parent, obs)                                   # every sequence empty
+    obs[leaves] = 3
+    got = check(parent, obs)                             # no gaps at all
+    assert got.all()
+    obs[leaves[0]] = NONE                                # one empty sequence
+    obs[:, 4] = NONE                                     # an all-gap column
+    got = check(parent, obs)
+    assert not got[:, 4].any()
+    star = [-1] + [0] * 9                                # one ancestor, nine children
+    obs = np.full((10, 6), NONE, np.uint8)
+    obs[1:] = np.where(rng.random((9, 6)) < 0.6, 1, NONE)
+    check(star, obs)
+
+
+@pytest.mark.gpu
 def test_gpu_bep_feeds_the_sweeps(bnk, oracle):
     """End to end on data/66.*: BEP mask (device) -> orphan pruning -> joint reconstruction (device) equals the
     oracle chain, and reproduces the documented states A, H of ancestors 0-2 under JTT."""
