@@ -62,9 +62,13 @@ __device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes)
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
+    // test_wait first: in steady state the phase has completed long before anybody asks (the ring runs several
+    // steps ahead), and the non-blocking probe returns at once where try_wait may park the warp for a while
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
         "LAB_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
         "@P1 bra DONE;\n"
@@ -72,6 +76,18 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
+}
+// non-blocking probe; true = the phase with this parity has completed (acquire, like a successful wait)
+__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
@@ -116,7 +132,7 @@ __device__ __forceinline__ XGeom x_setup(unsigned sbase, int W, int ns, int chb)
     g.bar_prog = sbase + 16 * XMAXNS;
     if (threadIdx.x == 0) {
         for (int s = 0; s < ns; s++) {
-            mbar_init(g.bar_full + 8 * s, 32);  // every producer lane arrives (lane 0 with the byte count)
+            mbar_init(g.bar_full + 8 * s, 33);  // the 32 lanes of the obs warp + the issuing lane of the TMA warp
             mbar_init(g.bar_empty + 8 * s, W);  // lane 0 of every consumer warp
         }
         for (int b = 0; b < XPB; b++) mbar_init(g.bar_prog + 8 * b, 1);
@@ -127,11 +143,18 @@ __device__ __forceinline__ XGeom x_setup(unsigned sbase, int W, int ns, int chb)
     return g;
 }
 
-// The producer warp.  DOWN = false: up-sweeps (tables from T_col); DOWN = true: node table from T_aux,
-// child tables from T_col, stored up-messages of walker-internal children from a.msg.
+// Two producer warps feed the ring (one alone spent ~860 cycles per step on its own instructions -- as long as
+// a consumer step -- and the two kept blocking each other, profiles/r1_v19):
+//   warp W      issues the TMA bulk copies of a step (one elected lane): the node's table, the tables of its
+//               childless children and, going down, the stored up-messages of its walker-internal children;
+//               DOWN = false: tables from T_col; DOWN = true: node table from T_aux, child tables from T_col;
+//               it also streams the walk program (32-step chunks);
+//   warp W + 1  stores the observed states of the childless children, which it requested XPD steps earlier.
+// A stage is full when the 32 lanes of the second and the issuing lane of the first have arrived and the bytes
+// have landed.
 template <bool DOWN>
-__device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &tile, const XGeom &g, unsigned char *smem_raw,
-                                           unsigned sbase, int ns, int lane)
+__device__ __forceinline__ void x_producer_tma(const WalkArgs &a, const TileDesc &tile, const XGeom &g, unsigned char *smem_raw,
+                                               unsigned sbase, int ns, int lane)
 {
     const Step *prog = DOWN ? a.down : a.up;
     const int n_steps = a.n_steps;
@@ -140,11 +163,7 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
     const size_t cat_off = (size_t)tile.cat0 * a.n_nodes * (XK * XK);
     const double *tab_node = (DOWN ? a.T_aux : a.T_col) + cat_off;
     const double *tab_child = a.T_col + cat_off;
-    // lane l fetches the observed states of tile columns l and l + 32
-    const uint8_t *obs_a = a.obs + a.orig_col[tile.col0 + (lane < tile.ncols ? lane : tile.ncols - 1)];
-    const uint8_t *obs_b = a.obs + a.orig_col[tile.col0 + (lane + 32 < tile.ncols ? lane + 32 : tile.ncols - 1)];
     const unsigned msg_bytes = (unsigned)tile.ncols * XK * 8;
-
     auto issue_chunk = [&](int j) {
         if (lane == 0 && j * 32 < n_steps) {
             const int cnt = n_steps - j * 32 < 32 ? n_steps - j * 32 : 32;
@@ -153,6 +172,50 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
             bulk_g2s(sbase + XPROG + (j & (XPB - 1)) * 32 * (int)sizeof(Step), prog + (size_t)j * 32, cnt * (unsigned)sizeof(Step), bar);
         }
     };
+    issue_chunk(0);
+    issue_chunk(1);
+    int s = 0, ph = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if ((i & 31) == 0) {
+            issue_chunk((i >> 5) + 2);
+            mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
+        }
+        if (i >= ns) mbar_wait(g.bar_empty + s * 8, ph ^ 1);
+        if (lane == 0) {
+            const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+            const int node = XSTEP(po, node), parent = XSTEP(po, parent);
+            const int cn0 = XSTEP(po, c_node[0]), cn1 = XSTEP(po, c_node[1]);
+            const int ce0 = XSTEP(po, c_ent[0]), ce1 = XSTEP(po, c_ent[1]);
+            const int cs0 = XSTEP(po, c_slot[0]), cs1 = XSTEP(po, c_slot[1]);
+            const int so = XSTAGE0 + s * g.stage_bytes;
+            const unsigned bar = g.bar_full + s * 8;
+            const bool tn = parent >= 0;  // a root contracts with the unit table / uses the prior
+            const bool t0 = cn0 >= 0 && ce0 < 0, t1 = cn1 >= 0 && ce1 < 0;
+            const bool m0 = DOWN && ce0 >= 0 && cs0 != SLOT_WIDE, m1 = DOWN && ce1 >= 0 && cs1 != SLOT_WIDE;
+            const unsigned bytes = (tn ? XTAB : 0) + (t0 ? XTAB : 0) + (t1 ? XTAB : 0) + (m0 ? msg_bytes : 0) + (m1 ? msg_bytes : 0);
+            if (bytes) mbar_arrive_tx(bar, bytes); else mbar_arrive(bar);
+            const unsigned stg = sbase + so;
+            if (tn) bulk_g2s(stg + XOBS, tab_node + (size_t)(unsigned)node * (XK * XK), XTAB, bar);
+            if (t0) bulk_g2s(stg + XOBS + XTAB, tab_child + (size_t)(unsigned)cn0 * (XK * XK), XTAB, bar);
+            if (t1) bulk_g2s(stg + XOBS + XTAB + g.chb, tab_child + (size_t)(unsigned)cn1 * (XK * XK), XTAB, bar);
+            if (m0) bulk_g2s(stg + XOBS + XTAB, a.msg + ((size_t)(unsigned)ce0 * ncols + tile.col0) * XK, msg_bytes, bar);
+            if (m1) bulk_g2s(stg + XOBS + XTAB + g.chb, a.msg + ((size_t)(unsigned)ce1 * ncols + tile.col0) * XK, msg_bytes, bar);
+        }
+        __syncwarp();
+        if (++s == ns) { s = 0; ph ^= 1; }
+    }
+}
+
+template <bool DOWN>
+__device__ __forceinline__ void x_producer_obs(const WalkArgs &a, const TileDesc &tile, const XGeom &g, unsigned char *smem_raw,
+                                               int ns, int lane)
+{
+    const int n_steps = a.n_steps;
+    if (n_steps <= 0) return;
+    const size_t ncols = (size_t)a.ncols;
+    // lane l fetches the observed states of tile columns l and l + 32
+    const uint8_t *obs_a = a.obs + a.orig_col[tile.col0 + (lane < tile.ncols ? lane : tile.ncols - 1)];
+    const uint8_t *obs_b = a.obs + a.orig_col[tile.col0 + (lane + 32 < tile.ncols ? lane + 32 : tile.ncols - 1)];
     int chunk_ready = -1;
     auto need_chunk = [&](int j) {
         while (chunk_ready < j) {
@@ -162,7 +225,7 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
     };
     // observed states of childless child e of step i for tile columns `lane` (half 0) and `lane + 32` (half 1).
     // The loaded byte must not be touched before it is stored XPD steps later: any arithmetic on it here would
-    // make the producer wait for DRAM once per step (it did: profiles/r1_v18 -- one step per memory round trip).
+    // make this warp wait for DRAM once per step (it did: profiles/r1_v18 -- one step per memory round trip).
     auto fetch_obs = [&](int i, int e, int half) -> uint8_t {
         const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
         const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
@@ -171,8 +234,6 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
         const uint8_t *src = (half == 0 ? obs_a : obs_b) + (size_t)(unsigned)(leaf ? cn : 0) * ncols;
         return leaf ? *src : (uint8_t)BNK_NONE;
     };
-    issue_chunk(0);
-    issue_chunk(1);
     need_chunk(0);
     uint8_t o[2][2][XPD];  // [child][column half][ring position]
 #pragma unroll
@@ -187,35 +248,13 @@ __device__ __forceinline__ void x_producer(const WalkArgs &a, const TileDesc &ti
         for (int k = 0; k < XPD; k++) {
             const int i = i0 + k;
             if (i < n_steps) {
-                if ((i & 31) == 0) issue_chunk((i >> 5) + 2);
-                need_chunk(i >> 5);
                 if (i >= ns) mbar_wait(g.bar_empty + s * 8, ph ^ 1);
-                const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
-                const int node = XSTEP(po, node), parent = XSTEP(po, parent);
-                const int cn0 = XSTEP(po, c_node[0]), cn1 = XSTEP(po, c_node[1]);
-                const int ce0 = XSTEP(po, c_ent[0]), ce1 = XSTEP(po, c_ent[1]);
-                const int cs0 = XSTEP(po, c_slot[0]), cs1 = XSTEP(po, c_slot[1]);
                 const int so = XSTAGE0 + s * g.stage_bytes;
                 smem_raw[so + lane] = o[0][0][k];
                 smem_raw[so + 32 + lane] = o[0][1][k];
                 smem_raw[so + 64 + lane] = o[1][0][k];
                 smem_raw[so + 96 + lane] = o[1][1][k];
-                const unsigned bar = g.bar_full + s * 8;
-                if (lane == 0) {
-                    const bool tn = parent >= 0;  // a root contracts with the unit table / uses the prior
-                    const bool t0 = cn0 >= 0 && ce0 < 0, t1 = cn1 >= 0 && ce1 < 0;
-                    const bool m0 = DOWN && ce0 >= 0 && cs0 != SLOT_WIDE, m1 = DOWN && ce1 >= 0 && cs1 != SLOT_WIDE;
-                    const unsigned bytes = (tn ? XTAB : 0) + (t0 ? XTAB : 0) + (t1 ? XTAB : 0) + (m0 ? msg_bytes : 0) + (m1 ? msg_bytes : 0);
-                    if (bytes) mbar_arrive_tx(bar, bytes); else mbar_arrive(bar);
-                    const unsigned stg = sbase + so;
-                    if (tn) bulk_g2s(stg + XOBS, tab_node + (size_t)(unsigned)node * (XK * XK), XTAB, bar);
-                    if (t0) bulk_g2s(stg + XOBS + XTAB, tab_child + (size_t)(unsigned)cn0 * (XK * XK), XTAB, bar);
-                    if (t1) bulk_g2s(stg + XOBS + XTAB + g.chb, tab_child + (size_t)(unsigned)cn1 * (XK * XK), XTAB, bar);
-                    if (m0) bulk_g2s(stg + XOBS + XTAB, a.msg + ((size_t)(unsigned)ce0 * ncols + tile.col0) * XK, msg_bytes, bar);
-                    if (m1) bulk_g2s(stg + XOBS + XTAB + g.chb, a.msg + ((size_t)(unsigned)ce1 * ncols + tile.col0) * XK, msg_bytes, bar);
-                } else {
-                    mbar_arrive(bar);
-                }
+                mbar_arrive(g.bar_full + s * 8);
                 const int ip = i + XPD;
                 if (ip < n_steps) {
                     need_chunk(ip >> 5);
@@ -280,15 +319,16 @@ struct XLane {
 // up-sweeps.  MODE 0: max-product in log space (joint), MODE 1: sum-product, linear, rescaled.
 // ------------------------------------------------------------------------------------
 template <int MODE, int C>
-__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+__global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileDesc tile = a.tiles[blockIdx.x];
     const XGeom g = x_setup(sbase, W, ns, chb);
-    if (warp == W) {
-        x_producer<false>(a, tile, g, smem_raw, sbase, ns, lane);
+    if (warp >= W) {
+        if (warp == W) x_producer_tma<false>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<false>(a, tile, g, smem_raw, ns, lane);
         return;
     }
     const XLane<C> L(a, tile, warp, lane);
@@ -311,13 +351,18 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
     for (int j = 0; j < C; j++) { esum[j] = 0; logacc[j] = 0.0; }
 
     int s = 0, ph = 0;
+    unsigned ready = 0;  // result of the early probe of this step's stage
     for (int i = 0; i < n_steps; i++) {
         if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
         const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
         const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
         const bool rootstep = XSTEP(po, parent) < 0;
         const int so = XSTAGE0 + s * g.stage_bytes;
-        mbar_wait(g.bar_full + s * 8, ph);
+        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
+        {   // probe the next stage now: the probe's round trip (a few hundred cycles) hides behind this step
+            const int sn = s + 1 == ns ? 0 : s + 1;
+            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
+        }
         // ---- the (at most two) children ----
         double cv[C][2][4];
         bool isob[C][2];
@@ -506,15 +551,16 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_warp_kernel(const Walk
 // D * prod(children) normalised, T_child = D * prod(siblings)
 // ------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+__global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileDesc tile = a.tiles[blockIdx.x];
     const XGeom g = x_setup(sbase, W, ns, chb);
-    if (warp == W) {
-        x_producer<true>(a, tile, g, smem_raw, sbase, ns, lane);
+    if (warp >= W) {
+        if (warp == W) x_producer_tma<true>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<true>(a, tile, g, smem_raw, ns, lane);
         return;
     }
     const XLane<C> L(a, tile, warp, lane);
@@ -532,6 +578,7 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
     const double prior4[4] = {a.prior[L.p0], a.prior[L.p0 + 1], a.prior[L.p1], a.prior[L.p1 + 1]};
 
     int s = 0, ph = 0;
+    unsigned ready = 0;  // result of the early probe of this step's stage
     for (int i = 0; i < n_steps; i++) {
         if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
         const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
@@ -539,7 +586,11 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_warp_kernel(const Wa
         const bool rootstep = XSTEP(po, parent) < 0;
         const int so = XSTAGE0 + s * g.stage_bytes;
         const int tsrc = slot >= 0 ? stack0 + slot * slot_bytes : dummy;
-        mbar_wait(g.bar_full + s * 8, ph);
+        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
+        {   // probe the next stage now: the probe's round trip (a few hundred cycles) hides behind this step
+            const int sn = s + 1 == ns ? 0 : s + 1;
+            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
+        }
         // ---- from-above vector of this node: D[x] = sum_p P[p][x] T[p], scaled by a power of two ----
         double D[C][4];
         if (!rootstep) {
@@ -714,15 +765,16 @@ struct MLane {
 __host__ __device__ inline int m_warp_bytes(int slots) { return (slots + 1) * MCW * XK * 8; }
 }  // namespace
 
-__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+__global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileDesc tile = a.tiles[blockIdx.x];
     const XGeom g = x_setup(sbase, W, ns, chb);
-    if (warp == W) {
-        x_producer<false>(a, tile, g, smem_raw, sbase, ns, lane);
+    if (warp >= W) {
+        if (warp == W) x_producer_tma<false>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<false>(a, tile, g, smem_raw, ns, lane);
         return;
     }
     const MLane L(a, tile, warp, lane);
@@ -739,13 +791,18 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_mma_kernel(const WalkA
     double logacc = 0.0;
 
     int s = 0, ph = 0;
+    unsigned ready = 0;  // result of the early probe of this step's stage
     for (int i = 0; i < n_steps; i++) {
         if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
         const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
         const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
         const bool rootstep = XSTEP(po, parent) < 0;
         const int so = XSTAGE0 + s * g.stage_bytes;
-        mbar_wait(g.bar_full + s * 8, ph);
+        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
+        {   // probe the next stage now: the probe's round trip (a few hundred cycles) hides behind this step
+            const int sn = s + 1 == ns ? 0 : s + 1;
+            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
+        }
         // ---- G as B fragments: entries x = 4 kt + xr of column g ----
         double G[5];
 #pragma unroll
@@ -843,15 +900,16 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) up_mma_kernel(const WalkA
     }
 }
 
-__global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+__global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileDesc tile = a.tiles[blockIdx.x];
     const XGeom g = x_setup(sbase, W, ns, chb);
-    if (warp == W) {
-        x_producer<true>(a, tile, g, smem_raw, sbase, ns, lane);
+    if (warp >= W) {
+        if (warp == W) x_producer_tma<true>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<true>(a, tile, g, smem_raw, ns, lane);
         return;
     }
     const MLane L(a, tile, warp, lane);
@@ -866,13 +924,18 @@ __global__ void __launch_bounds__((XMAXW + 1) * 32, 1) down_mma_kernel(const Wal
     for (int mt = 0; mt < 3; mt++) prior3[mt] = a.prior[8 * mt + L.g < XK ? 8 * mt + L.g : 0];
 
     int s = 0, ph = 0;
+    unsigned ready = 0;  // result of the early probe of this step's stage
     for (int i = 0; i < n_steps; i++) {
         if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
         const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
         const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
         const bool rootstep = XSTEP(po, parent) < 0;
         const int so = XSTAGE0 + s * g.stage_bytes;
-        mbar_wait(g.bar_full + s * 8, ph);
+        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
+        {   // probe the next stage now: the probe's round trip (a few hundred cycles) hides behind this step
+            const int sn = s + 1 == ns ? 0 : s + 1;
+            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
+        }
         // ---- from-above vector D[x][col] = sum_p P[p][x] T[p][col], scaled by a power of two per column ----
         double D[3][2];
         if (!rootstep) {
@@ -992,7 +1055,7 @@ static cudaError_t launch_warp(KernelT kern, const WalkArgs &a, int n_tiles, int
     const size_t smem = warp_walk_smem_bytes(W, C, ns, a.smem_slots, down);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_tiles, (W + 1) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * XCW * C, down));
+    kern<<<n_tiles, (W + 2) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * XCW * C, down));
     return cudaGetLastError();
 }
 cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
@@ -1031,7 +1094,7 @@ static cudaError_t launch_mma(KernelT kern, const WalkArgs &a, int n_tiles, int 
     const size_t smem = mma_walk_smem_bytes(W, ns, a.smem_slots, down);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_tiles, (W + 1) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * MCW, down));
+    kern<<<n_tiles, (W + 2) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * MCW, down));
     return cudaGetLastError();
 }
 cudaError_t launch_sum_up_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st) { return launch_mma(up_mma_kernel, a, n_tiles, W, ns, false, st); }
