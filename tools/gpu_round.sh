@@ -15,5 +15,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 260 --csv --log-file gpurun_out/traffic_$tag.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu2_$tag.log 2>&1
 # full captures: the level kernels of the default workload, then the warp-tiled walker on the caterpillar
 ncu --set full --clock-control none --import-source on -k regex:"down_wide_kernel|up_wide_kernel|cherry" -c 14 -o gpurun_out/prof_${tag}_wide python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu3_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"warp_kernel|traceback_kernel" -c 4 -o gpurun_out/prof_${tag}_walker python bench.py --workload c3b --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu4_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"warp_kernel|mma_kernel|traceback_kernel" -c 4 -o gpurun_out/prof_${tag}_walker python bench.py --workload c3b --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu4_$tag.log 2>&1
 ls -la gpurun_out/*$tag* | awk '{print $5, $9}'
