@@ -127,6 +127,29 @@ def cpu_oracle_rate(spec, model_name, parent, dist, rates, obs, budget_s, thread
         nc, obs.shape[1], len(parent), threads, t), t
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so that the 8 GB result
+    copies of several ranks do not cross sockets.  Best effort: any missing piece leaves the affinity untouched."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def host_memory_available():
     """Bytes of host memory this process may still take: free memory, capped by the cgroup limit if there is one."""
     avail = None
@@ -217,6 +240,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libbnkgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -388,6 +412,8 @@ def main():
     if not args.no_e2e:
         line["e2e"] = {"value": updates_step * (e2e_cols / n_cols) / (e2emax * 1e-3), "unit": "updates/s", "ms_per_step": e2emax,
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        if numa_node is not None:
+            line["e2e"]["numa"] = "ranks bound to their GPU's NUMA node"
         if e2e_cols != n_cols:
             line["e2e"]["note"] = ("host memory limit: this leg ran on the first %d of %d columns per GPU "
                                    "(it pins %.1f GB per rank at full width)" % (e2e_cols, n_cols, need / 1e9))
