@@ -105,9 +105,11 @@ struct bnk_ws {
     std::vector<std::pair<int, int>> chunk_ctiles;
     DevBuf<TileDesc> d_ctiles;
     // warp-tiled walker (sweeps_warp.cu): tiles of one category, <= 6 * xw columns
-    std::vector<TileDesc> xtiles, mtiles;  // mtiles: the DMMA sum-product variants (<= 8 * mw columns)
-    std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles;
-    DevBuf<TileDesc> d_xtiles, d_mtiles;
+    std::vector<TileDesc> xtiles, mtiles, jtiles;  // mtiles: DMMA sum-product variants (<= 8 * mw columns); jtiles: joint10 (<= 3 * jw)
+    std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles, chunk_jtiles;
+    DevBuf<TileDesc> d_xtiles, d_mtiles, d_jtiles;
+    int jw = 0;                            // consumer warps per CTA of the ten-lanes-per-column joint up-sweep
+    bool joint10 = false;                  // BNK_JOINT10=1: joint up-sweep with ten lanes per column (parity-tested; measured slower: 11.9 vs 10.3 ms on C3b)
     int mw = 0;                            // consumer warps per CTA of the DMMA variants
     bool mma_down = false;                 // BNK_MMA_DOWN=1: the down-sweep on DMMA too (measured slower: 12.7 vs 11.7 ms on C3b)
     int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
@@ -213,7 +215,7 @@ static void ws_free(bnk_ws *ws)
     for (auto *b : di) b->release();
     ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
     ws->d_up_n.release(); ws->d_down_n.release(); ws->d_up_child_n.release(); ws->d_down_child_n.release();
-    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_xtiles.release(); ws->d_mtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
+    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_xtiles.release(); ws->d_mtiles.release(); ws->d_jtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
     if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
     delete ws;
@@ -252,6 +254,8 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
         ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : 0);
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
     if (const char *env = std::getenv("BNK_MMA_DOWN")) ws->mma_down = std::atoi(env) != 0;
+    if (const char *env = std::getenv("BNK_JOINT10")) ws->joint10 = std::atoi(env) != 0;
+    if (const char *env = std::getenv("BNK_JOINT10_W")) ws->jw = -std::atoi(env);  // negative: forced
     if (const char *env = std::getenv("BNK_WARP_W")) ws->cfg_xw = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_NS")) ws->cfg_xns = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_C")) ws->cfg_xc = std::atoi(env);
@@ -456,8 +460,21 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         if (ws->mw < 0 && -ws->mw <= 7) ws->mw = ws->mw;  // forced by BNK_MMA_W (kept negative as the marker)
         else ws->mw = best_w;
     }
+    {   // joint10: 3 columns per warp, same cost model
+        int best_w = 2; double best_cost = -1.0;
+        const int cw = joint10_cols_per_warp();
+        for (int w = 2; w <= 14; w++) {
+            int64_t nt = 0;
+            for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
+            const int64_t rounds = (nt + ws->sm_count - 1) / ws->sm_count;
+            const double cost = (double)rounds * w * (1.0 + 0.05 * (double)(rounds - 1));
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
+        }
+        if (!(ws->jw < 0 && -ws->jw <= 14)) ws->jw = best_w;
+    }
     const int wt = wide_tile_cols(), cg = cherry_group_cols();
     ws->mtiles.clear(); ws->chunk_mtiles.clear();
+    ws->jtiles.clear(); ws->chunk_jtiles.clear();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
         const int hi = std::min(ncat, lo + cats_per_chunk);
         Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
@@ -491,6 +508,18 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 for (int q = 0; q < nt; q++) {
                     const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
                     ws->mtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+                }
+            }
+        }
+        const int j0 = (int)ws->jtiles.size();
+        {
+            const int jt = std::abs(ws->jw) * joint10_cols_per_warp();
+            for (int k = lo; k < hi; k++) {
+                const int nc = cat_begin[k + 1] - cat_begin[k];
+                const int nt = (nc + jt - 1) / jt;
+                for (int q = 0; q < nt; q++) {
+                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                    ws->jtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
                 }
             }
         }
@@ -536,6 +565,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             ws->chunk_ctiles.push_back({ct0, (int)ws->ctiles.size()});
             ws->chunk_xtiles.push_back({x0, (int)ws->xtiles.size()});
             ws->chunk_mtiles.push_back({m0, (int)ws->mtiles.size()});
+            ws->chunk_jtiles.push_back({j0, (int)ws->jtiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
         }
     }
@@ -556,6 +586,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
     TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
     TRY(upload(ws->d_mtiles, ws->mtiles, ws->stream));
+    TRY(upload(ws->d_jtiles, ws->jtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
     ws->rates_null = rates == nullptr;
@@ -868,6 +899,19 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
                 TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
                     return gen ? launch_up_wide_gen(K, 0, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
             }
+            bool j10 = false;
+            int jns = 8;
+            if (s.warp && ws->joint10 && ws->walker_mode == 0) {
+                const int jw = std::abs(ws->jw);
+                if (ws->cfg_xns >= 2 && ws->cfg_xns <= 8) jns = ws->cfg_xns;
+                else while (jns > 3 && joint10_smem_bytes(jw, jns, s.a.smem_slots) > (size_t)ws->smem_optin / 2 - 1024) jns--;
+                j10 = joint10_smem_bytes(jw, jns, s.a.smem_slots) <= (size_t)ws->smem_optin;
+            }
+            if (j10) {
+                WalkArgs ja = s.a;
+                ja.tiles = ws->d_jtiles.p + ws->chunk_jtiles[ci].first;
+                CUDA_TRY(launch_joint_up_10(ja, ws->chunk_jtiles[ci].second - ws->chunk_jtiles[ci].first, std::abs(ws->jw), jns, ws->stream));
+            } else
             CUDA_TRY(s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                             : s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;

@@ -547,6 +547,139 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
 }
 
 // ------------------------------------------------------------------------------------
+// Max-product up-sweep with TEN lanes per column (lane q owns outputs 2q, 2q + 1; 3 columns per warp).  The
+// joint sweep is bound by the add / compare / select chain, not by shared memory: halving the work of a lane
+// doubles the warps that can hide each other's latency (12 consumer warps per CTA for the same 36 columns).
+// Same arithmetic and scan order as up_warp_kernel<0, C>; vectors in shared memory are plain [column][20].
+// ------------------------------------------------------------------------------------
+namespace {
+constexpr int JCW = 3;  // columns per warp
+__host__ __device__ inline int j_warp_bytes(int slots) { return (2 + slots + 1) * JCW * XK * 8; }
+}  // namespace
+
+__global__ void __launch_bounds__(16 * 32, 1) up_joint10_kernel(const WalkArgs a, const int W, const int ns, const int chb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const XGeom g = x_setup(sbase, W, ns, chb);
+    if (warp >= W) {
+        if (warp == W) x_producer_tma<false>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<false>(a, tile, g, smem_raw, ns, lane);
+        return;
+    }
+    const int c = lane < 30 ? lane / 10 : 2;            // lanes 30, 31 shadow lanes 20, 21
+    const int q = lane < 30 ? lane - 10 * c : lane - 30;
+    int lc = warp * JCW + c;
+    if (lc >= tile.ncols) lc = tile.ncols - 1;
+    const int col = tile.col0 + lc;
+    const int n_steps = a.n_steps;
+    const size_t ncols = (size_t)a.ncols;
+    const int slot_bytes = JCW * XK * 8;
+    const int wbase = XSTAGE0 + ns * g.stage_bytes + warp * j_warp_bytes(a.smem_slots);
+    const int stack0 = wbase + 2 * slot_bytes;
+    const int dummy = stack0 + a.smem_slots * slot_bytes;
+    const int own = c * (XK * 8) + q * 16;  // this lane's pair inside a [column][20] vector
+    const double prior2[2] = {a.prior[2 * q], a.prior[2 * q + 1]};
+
+    int s = 0, ph = 0;
+    unsigned ready = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
+        const bool rootstep = XSTEP(po, parent) < 0;
+        const int so = XSTAGE0 + s * g.stage_bytes;
+        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
+        {
+            const int sn = s + 1 == ns ? 0 : s + 1;
+            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
+        }
+        double cv[2][2];
+        bool isob[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
+            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
+            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
+            isob[e] = false;
+            if (cs >= 0) {
+                const double2 u = XS_D2(stack0 + cs * slot_bytes + own);
+                cv[e][0] = u.x; cv[e][1] = u.y;
+            } else if (cs == SLOT_WIDE) {
+                const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + col;
+                cv[e][0] = src[(size_t)(2 * q) * ncols]; cv[e][1] = src[(size_t)(2 * q + 1) * ncols];
+            } else if (cn >= 0) {
+                const int tb = so + XOBS + XTAB + e * g.chb + q * 16;
+                const int ob = smem_raw[so + e * 64 + lc];
+                if (ob != BNK_NONE) {
+                    const double2 u = XS_D2(tb + ob * (XK * 8));
+                    cv[e][0] = u.x; cv[e][1] = u.y;
+                    isob[e] = true;
+                } else {  // uninstantiated childless node: maximise over its own state
+                    double2 u = XS_D2(tb);
+                    for (int x = 1; x < XK; x++) {
+                        const double2 t = XS_D2(tb + x * (XK * 8));
+                        u.x = t.x > u.x ? t.x : u.x; u.y = t.y > u.y ? t.y : u.y;
+                    }
+                    cv[e][0] = u.x; cv[e][1] = u.y;
+                }
+            } else {
+                cv[e][0] = 0.0; cv[e][1] = 0.0;
+            }
+        }
+        const bool swap = rootstep && !isob[0] && isob[1];  // root: [prior, observed children, unobserved children]
+        const int gb = wbase + (i & 1) * slot_bytes + c * (XK * 8);
+        {
+            double G[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const double c0 = swap ? cv[1][k] : cv[0][k], c1 = swap ? cv[0][k] : cv[1][k];
+                G[k] = ((rootstep ? prior2[k] : 0.0) + c0) + c1;
+            }
+            XS_D2(gb + q * 16) = make_double2(G[0], G[1]);
+        }
+        __syncwarp();
+        double best[2] = {-CUDART_INF, -CUDART_INF};
+        int bi[2] = {0, 0};
+        if (!rootstep) {
+            const int tv = so + XOBS + q * 16;
+#pragma unroll
+            for (int x2 = 0; x2 < XK / 2; x2++) {
+                const double2 gg = XS_D2(gb + x2 * 16);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int x = 2 * x2 + h;
+                    const double gx = h == 0 ? gg.x : gg.y;
+                    const double2 t = XS_D2(tv + x * (XK * 8));
+                    const double v0 = t.x + gx, v1 = t.y + gx;
+                    const bool t0 = v0 > best[0], t1 = v1 > best[1];
+                    best[0] = t0 ? v0 : best[0]; bi[0] = t0 ? x : bi[0];
+                    best[1] = t1 ? v1 : best[1]; bi[1] = t1 ? x : bi[1];
+                }
+            }
+        } else {
+            double b = -CUDART_INF;
+            int bx = 0;
+#pragma unroll
+            for (int x2 = 0; x2 < XK / 2; x2++) {
+                const double2 gg = XS_D2(gb + x2 * 16);
+                const double v0 = 0.0 + gg.x, v1 = 0.0 + gg.y;
+                if (v0 > b) { b = v0; bx = 2 * x2; }
+                if (v1 > b) { b = v1; bx = 2 * x2 + 1; }
+            }
+            best[0] = best[1] = b; bi[0] = bi[1] = bx;
+        }
+        XS_D2((slot >= 0 ? stack0 + slot * slot_bytes : dummy) + own) = make_double2(best[0], best[1]);
+        *reinterpret_cast<uint16_t *>(a.ptr + ((size_t)(unsigned)ent * ncols + col) * XK + 2 * q) = (uint16_t)(bi[0] | (bi[1] << 8));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
+        if (++s == ns) { s = 0; ph ^= 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // down-sweep (see sweeps.cu for the recurrences): from-above vector D = P^T T, posterior
 // D * prod(children) normalised, T_child = D * prod(siblings)
 // ------------------------------------------------------------------------------------
@@ -1080,6 +1213,22 @@ cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, i
     return cudaErrorInvalidValue;
 }
 
+
+// joint up-sweep with ten lanes per column: 3 columns per warp, up to 14 consumer warps
+int joint10_cols_per_warp() { return JCW; }
+size_t joint10_smem_bytes(int W, int ns, int slots)
+{
+    return (size_t)XSTAGE0 + (size_t)ns * x_stage_bytes(XTAB) + (size_t)W * j_warp_bytes(slots);
+}
+cudaError_t launch_joint_up_10(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st)
+{
+    if (W < 1 || W > 14 || ns < 2 || ns > XMAXNS || W * JCW > 64) return cudaErrorInvalidValue;
+    const size_t smem = joint10_smem_bytes(W, ns, a.smem_slots);
+    cudaError_t e = cudaFuncSetAttribute(up_joint10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    up_joint10_kernel<<<n_tiles, (W + 2) * 32, smem, st>>>(a, W, ns, XTAB);
+    return cudaGetLastError();
+}
 
 // DMMA variants: 8 columns per warp, tiles of at most 8 W columns
 int mma_walk_cols_per_warp() { return MCW; }
