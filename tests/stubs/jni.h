@@ -1,0 +1,21 @@
+/* syntax-check stub only (NOT a JNI implementation) */
+#include <stdint.h>
+typedef int32_t jint; typedef int64_t jlong; typedef double jdouble; typedef int32_t jsize; typedef unsigned char jboolean;
+typedef void *jobject; typedef jobject jclass; typedef jobject jstring; typedef jobject jintArray; typedef jobject jdoubleArray;
+#define JNIEXPORT
+#define JNICALL
+#define JNI_ABORT 2
+struct JNINativeInterface_;
+typedef const struct JNINativeInterface_ *JNIEnv;
+struct JNINativeInterface_ {
+    jclass (*FindClass)(JNIEnv *, const char *);
+    jint (*ThrowNew)(JNIEnv *, jclass, const char *);
+    void *(*GetDirectBufferAddress)(JNIEnv *, jobject);
+    const char *(*GetStringUTFChars)(JNIEnv *, jstring, jboolean *);
+    void (*ReleaseStringUTFChars)(JNIEnv *, jstring, const char *);
+    jdouble *(*GetDoubleArrayElements)(JNIEnv *, jdoubleArray, jboolean *);
+    void (*ReleaseDoubleArrayElements)(JNIEnv *, jdoubleArray, jdouble *, jint);
+    jint *(*GetIntArrayElements)(JNIEnv *, jintArray, jboolean *);
+    void (*ReleaseIntArrayElements)(JNIEnv *, jintArray, jint *, jint);
+    jsize (*GetArrayLength)(JNIEnv *, jobject);
+};

@@ -109,3 +109,22 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "bnk_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_jni_shim_matches_the_header():
+    """integration/jni/bnkgpu_jni.c (the binding a bnkit maintainer would add; no JDK in the image) must at least
+    type-check against include/bnkgpu.h: compiled with -fsyntax-only against a stub jni.h that declares just the
+    JNI calls the shim uses, and every native method of NativeInference.java must have its Java_asr_... function."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "integration", "jni", "bnkgpu_jni.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "tests", "stubs"),
+                        "-I", os.path.join(root, "include"), shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    java = open(os.path.join(root, "integration", "java", "asr", "NativeInference.java")).read()
+    natives = re.findall(r"static native \w+ (\w+)\(", java)
+    csrc = open(shim).read()
+    assert len(natives) >= 12
+    for name in natives:
+        assert "Java_asr_NativeInference_%s(" % name in csrc, name
