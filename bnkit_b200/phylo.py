@@ -449,3 +449,26 @@ def load_alignment(path):
         s = "".join(seqs[nm])
         rows.append([None if ch == "-" else ch for ch in s])
     return names, rows
+
+
+def load_rates(path):
+    """Position-specific evolutionary rates as asr.GRASP reads them (src/asr/GRASP.java:433-456): a tab-separated
+    file with a header; the column named "Rate" holds the rates (first column if there is no such name) and the
+    optional column "Site" the 1-based alignment column each rate belongs to (file order otherwise) -- e.g. the
+    output of IQ-TREE's --rate.  Lines starting with '#' are comments.  Returns a float64 array."""
+    with open(path) as fh:
+        lines = [ln.rstrip("\n") for ln in fh if ln.strip() and not ln.startswith("#")]
+    if not lines:
+        raise ASRRuntimeException("Rates file is empty: %s" % path)
+    header = lines[0].split("\t")
+    rate_col = header.index("Rate") if "Rate" in header else 0
+    site_col = header.index("Site") if "Site" in header else -1
+    rows = [ln.split("\t") for ln in lines[1:]]
+    rates = np.zeros(len(rows), dtype=np.float64)
+    for i, r in enumerate(rows):
+        try:
+            idx = i if site_col < 0 else int(r[site_col]) - 1
+            rates[idx] = float(r[rate_col])
+        except (ValueError, IndexError):
+            raise ASRRuntimeException("Rates file has invalid number format: %s" % "\t".join(r))
+    return rates

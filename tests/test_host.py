@@ -90,3 +90,18 @@ def test_shard_columns(bnk):
             assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
             sizes = [hi - lo for lo, hi in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_rates_file_as_grasp_reads_it(tmp_path):
+    """GRASP -rf: "Rate" column (else the first), optional 1-based "Site" column (src/asr/GRASP.java:433-456)."""
+    from bnkit_b200.phylo import ASRRuntimeException, load_rates
+    f = tmp_path / "r.tsv"
+    f.write_text("# IQ-TREE style\nSite\tRate\tCat\n2\t0.5\t1\n1\t2.25\t3\n3\t1e-3\t0\n")
+    assert list(load_rates(str(f))) == [2.25, 0.5, 1e-3]
+    f.write_text("Rate\n1.0\n0.25\n")
+    assert list(load_rates(str(f))) == [1.0, 0.25]
+    f.write_text("whatever\tx\n0.7\ta\n1.3\tb\n")
+    assert list(load_rates(str(f))) == [0.7, 1.3]
+    f.write_text("Site\tRate\n1\tabc\n")
+    with pytest.raises(ASRRuntimeException):
+        load_rates(str(f))
