@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -206,6 +207,8 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     auto us_since = [](std::chrono::steady_clock::time_point t0) {
         return (int)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     };
+    const bool trace = std::getenv("BNK_BEP_TRACE") != nullptr;  // stderr: microseconds since entry at a few marks
+    auto mark = [&](const char *what) { if (trace) std::fprintf(stderr, "bep %8d us  %s\n", us_since(t_begin), what); };
     Pog pog;  // scratch for the serial tail
     // ancestors without a start-to-end path: their edges so far (the graph is rebuilt in `pog` when needed) and
     // the columns that stick out
@@ -331,6 +334,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         BEP_CUDA_TRY(cudaMemcpyAsync(d_first.p, t->first.data(), sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, st));
         if (!t->kids.empty())
             BEP_CUDA_TRY(cudaMemcpyAsync(d_kids.p, t->kids.data(), sizeof(int32_t) * t->kids.size(), cudaMemcpyHostToDevice, st));
+        mark("allocations + input copies issued");
         BEP_CUDA_TRY(bep_launch_next_prev(d_obs.p, d_leaf_nodes.p, n_leaves, n_pos, d_nxt.p, d_prv.p, st));
         info[3]++;
         // the bit sets of the widest case (8 words) bound the allocation; most alignments need one word
@@ -369,8 +373,10 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                 BEP_CUDA_TRY(d_B.alloc((size_t)n_int * Wn * n_inst_max));
             }
         }
+        mark("sizing pass done");
         rc = run(ie, ifw, 1, W, false);
         if (rc != BNK_OK) goto done;
+        mark("main sweeps done");
         {
             const int n_inst = (int)ie.size();
             const auto t0 = std::chrono::steady_clock::now();
@@ -432,6 +438,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
             info[5] += us_since(t0);
         }
         info[0] = (int)crippled.size();
+        mark("first-pass graph assembly done");
         // ---- patchAncestorsWithBEP: re-infer the protruding columns without the NULL symbol (:1551-1588) ----
         for (;;) {
             std::set<int> columns;
@@ -489,10 +496,12 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
             pog.from_edges(n_pos, kv.second);
             emit_row(kv.first, pog);
         }
+        mark("patch rounds done");
         info[6] = us_since(t_begin);
         if (info_or_null) std::memcpy(info_or_null, info, sizeof(info));
     }
 done:
+    mark("before cleanup");
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
