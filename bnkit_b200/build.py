@@ -21,6 +21,7 @@ UNITS = [
     ("bep.cu", []),
     ("bep_api.cu", []),
     ("api.cu", []),
+    ("multi.cu", []),
     ("subst_model.cpp", ["-fmad=false"]),
     ("tree_plan.cpp", []),
 ]
@@ -70,7 +71,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libbnkgpu build failed")
-    cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
     return OUT
 

@@ -25,117 +25,11 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t e_ = (expr);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(e_ == cudaErrorMemoryAllocation ? BNK_ERR_NOMEM : BNK_ERR_CUDA, "%s: %s (%s:%d)", \
-                        #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
-    } while (0)
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;  // elements
-    int64_t *acct = nullptr;
-    cudaError_t ensure(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); if (acct) *acct -= (int64_t)(cap * sizeof(T)); p = nullptr; cap = 0; }
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        cap = n;
-        if (acct) *acct += (int64_t)(n * sizeof(T));
-        return cudaSuccess;
-    }
-    void release()
-    {
-        if (p) { cudaFree(p); if (acct) *acct -= (int64_t)(cap * sizeof(T)); }
-        p = nullptr; cap = 0;
-    }
-};
-
-struct Chunk {
-    int cat_lo, cat_hi;    // global category range
-    int tile_lo, tile_hi;  // tiles of this chunk
-    int ncat_max;          // largest category span of one of its tiles
-};
-
 }  // namespace bnk
 
-using namespace bnk;
+#include "workspace.cuh"
 
-struct bnk_ws {
-    bnk_model model;
-    const bnk_tree *tree = nullptr;
-    int K = 0, n = 0, n_int = 0, max_cols = 0, device = 0, sm_count = 148, smem_optin = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int64_t launches = 0, dev_bytes = 0;
-    int cfg_tile_cols = 0, cfg_cpt = 0;
-    bool force_generic = false;
-    int wide_tpc_max = 8;  // r1 sweep on C3a: 4-8 tiles per CTA best
-    size_t table_budget = (size_t)12 << 30;
-    // static device data
-    DevBuf<double> d_model;  // evec | ievec | eval | prior | logprior
-    DevBuf<Step> d_up, d_down, d_up_n, d_down_n;             // full / narrow walk programs
-    DevBuf<ChildRef> d_up_child, d_down_child, d_up_child_n, d_down_child_n;
-    DevBuf<WideNode> d_wide;                                  // wide levels, concatenated (height 1 first)
-    std::vector<int32_t> level_off;                           // [wide_h + 1] into d_wide
-    bool no_wide = false;                                     // bnk_ws_configure: walker only (tests, profiling)
-    DevBuf<int32_t> d_parent, d_node_of_ent, d_leaf_nodes, d_leaf_parent;
-    DevBuf<double> d_dist;
-    std::vector<double> dist;
-    int n_leaves = 0;
-    // rates / categories / tiles
-    int ncols = -1;  // columns of the current rate assignment
-    bool identity_perm = true;
-    std::vector<double> cat_rate, last_rates;
-    bool rates_null = true;
-    std::vector<int32_t> orig_col, col_cat_global, cat_of_col;
-    std::vector<TileDesc> tiles, wtiles;   // walker tiles; wide tiles (one category, <= 128 columns)
-    std::vector<Chunk> chunks;
-    std::vector<TileDesc> cgroups;         // cherry groups (one category, <= cherry_group_cols() columns)
-    std::vector<std::pair<int, int>> chunk_cgroups;
-    DevBuf<TileDesc> d_cgroups;
-    std::vector<int> chunk_crecs;          // per chunk: result records per height-1 node (sum of the groups' capacities)
-    DevBuf<uint8_t> d_cscratch;
-    DevBuf<int16_t> d_cslots;
-    std::vector<TileDesc> ctiles;          // expansion tiles of the cherry groups (16-column aligned starts)
-    std::vector<std::pair<int, int>> chunk_ctiles;
-    DevBuf<TileDesc> d_ctiles;
-    // warp-tiled walker (sweeps_warp.cu): tiles of one category, <= 6 * xw columns
-    std::vector<TileDesc> xtiles, mtiles, jtiles;  // mtiles: DMMA sum-product variants (<= 8 * mw columns); jtiles: joint10 (<= 3 * jw)
-    std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles, chunk_jtiles;
-    DevBuf<TileDesc> d_xtiles, d_mtiles, d_jtiles;
-    int jw = 0;                            // consumer warps per CTA of the ten-lanes-per-column joint up-sweep
-    bool joint10 = false;                  // BNK_JOINT10=1: joint up-sweep with ten lanes per column (parity-tested; measured slower: 11.9 vs 10.3 ms on C3b)
-    int mw = 0;                            // consumer warps per CTA of the DMMA variants
-    bool mma_down = false;                 // BNK_MMA_DOWN=1: the down-sweep on DMMA too (measured slower: 12.7 vs 11.7 ms on C3b)
-    int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
-    int walker_mode = 0;                   // BNK_WALKER: 0 auto (warp-tiled where eligible), 1 lean CTA walker,
-                                           // 2 warp-tiled with the scalar sum-product kernels (no DMMA)
-    int cfg_xw = 0, cfg_xns = 0, cfg_xc = 0;  // BNK_WARP_W / BNK_WARP_NS / BNK_WARP_C (tuning knobs, tests)
-    bool no_cherry = false;                // BNK_NO_CHERRY=1: height-1 level through the plain level kernel (A/B, tests)
-    std::vector<std::pair<int, int>> chunk_wtiles, chunk_cols;  // per chunk: wide tile range, sorted column range
-    int tile_cols = 0, cpt = 1, ncg = 0, threads = 0;
-    DevBuf<double> d_cat_rate;
-    DevBuf<int32_t> d_orig_col, d_col_cat, d_cat_of_col, d_qrow, d_flag;
-    DevBuf<TileDesc> d_tiles, d_wtiles;
-    DevBuf<int16_t> d_escale;
-    DevBuf<int32_t> d_esum_wide;
-    bool tables_log_valid = false, tables_lin_valid = false;  // only meaningful with a single chunk
-    // buffers
-    DevBuf<double> d_P, d_PT, d_L, d_LT, d_spill, d_msg, d_tmsg, d_logl, d_logl_wide, d_post, d_sum;
-    DevBuf<uint8_t> d_obs_in, d_present_in, d_obs_s, d_present_s, d_ptr, d_kind, d_kindm, d_state, d_state_s;
-    cudaEvent_t ev[5][2] = {};
-    bool ev_valid[5] = {false, false, false, false, false};
-    ModelDev md() const
-    {
-        const double *b = d_model.p;
-        return ModelDev{b, b + K * K, b + 2 * K * K, b + 2 * K * K + K, b + 2 * K * K + 2 * K, K};
-    }
-};
+using namespace bnk;
 
 // --------------------------------------------------------------------------------------
 extern "C" const char *bnk_last_error(void) { return g_err.c_str(); }
@@ -193,31 +87,17 @@ static int upload(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st)
     return BNK_OK;
 }
 
-#define TRY(expr)                       \
-    do {                                \
-        int rc_ = (expr);               \
-        if (rc_ != BNK_OK) return rc_;  \
-    } while (0)
-
-static void ws_free(bnk_ws *ws)
+void bnk::ws_free(bnk_ws *ws)
 {
     if (!ws) return;
-    cudaSetDevice(ws->device);
+    DeviceGuard guard(ws->device);
     if (ws->stream) cudaStreamSynchronize(ws->stream);
-    DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
-                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_logl_wide, &ws->d_post, &ws->d_sum};
-    for (auto *b : dd) b->release();
-    DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
-                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state, &ws->d_state_s};
-    for (auto *b : db) b->release();
-    DevBuf<int32_t> *di[] = {&ws->d_parent, &ws->d_node_of_ent, &ws->d_leaf_nodes, &ws->d_leaf_parent,
-                             &ws->d_orig_col, &ws->d_col_cat, &ws->d_cat_of_col, &ws->d_qrow, &ws->d_flag};
-    for (auto *b : di) b->release();
-    ws->d_up.release(); ws->d_down.release(); ws->d_up_child.release(); ws->d_down_child.release(); ws->d_tiles.release();
-    ws->d_up_n.release(); ws->d_down_n.release(); ws->d_up_child_n.release(); ws->d_down_child_n.release();
-    ws->d_wide.release(); ws->d_wtiles.release(); ws->d_cgroups.release(); ws->d_cscratch.release(); ws->d_cslots.release(); ws->d_ctiles.release(); ws->d_xtiles.release(); ws->d_mtiles.release(); ws->d_jtiles.release(); ws->d_escale.release(); ws->d_esum_wide.release();
+    for (bnk_ws *sub : ws->subs) ws_free(sub);
+    ws->subs.clear();
+    for (DevBufBase *b : ws->reg.all) b->release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
     if (ws->own_stream && ws->stream) cudaStreamDestroy(ws->stream);
+    if (ws->tree) tree_release(const_cast<bnk_tree *>(ws->tree));  // the workspace held a reference
     delete ws;
 }
 
@@ -231,7 +111,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
         return fail(BNK_ERR_CUDA, "ws: no CUDA device visible (libbnkgpu has no CPU fallback)");
     }
     if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     int major = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     if (major != 10) return fail(BNK_ERR_CUDA, "ws: device %d is sm_%dx; libbnkgpu is built for sm_100a only", device, major);
@@ -239,13 +119,14 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     if (!ws) return fail(BNK_ERR_NOMEM, "ws: out of host memory");
     ws->model = *m;
     ws->tree = t;
+    tree_retain(const_cast<bnk_tree *>(t));
     ws->K = m->K; ws->n = t->n; ws->n_int = t->n_int; ws->max_cols = max_cols; ws->device = device;
     cudaDeviceGetAttribute(&ws->sm_count, cudaDevAttrMultiProcessorCount, device);
     ws->smem_optin = walk_max_smem_optin(device);
     if (stream) ws->stream = (cudaStream_t)stream;
     else {
         cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { delete ws; return fail(BNK_ERR_CUDA, "ws: cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { ws->stream = nullptr; ws_free(ws); return fail(BNK_ERR_CUDA, "ws: cudaStreamCreate: %s", cudaGetErrorString(e)); }
         ws->own_stream = true;
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
@@ -262,13 +143,6 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     if (const char *env = std::getenv("BNK_WIDE_TPC")) ws->wide_tpc_max = std::max(1, std::atoi(env));  // tuning knob
     if (const char *env = std::getenv("BNK_TABLE_BUDGET_MB"))  // bytes of P(t) tables held at once (tests force several chunks)
         ws->table_budget = (size_t)std::max(1, std::atoi(env)) << 20;
-    // accounting hooks
-    DevBuf<double> *dd[] = {&ws->d_model, &ws->d_dist, &ws->d_cat_rate, &ws->d_P, &ws->d_PT, &ws->d_L, &ws->d_LT,
-                            &ws->d_spill, &ws->d_msg, &ws->d_tmsg, &ws->d_logl, &ws->d_logl_wide, &ws->d_post, &ws->d_sum};
-    for (auto *b : dd) b->acct = &ws->dev_bytes;
-    DevBuf<uint8_t> *db[] = {&ws->d_obs_in, &ws->d_present_in, &ws->d_obs_s, &ws->d_present_s,
-                             &ws->d_ptr, &ws->d_kind, &ws->d_kindm, &ws->d_state, &ws->d_state_s};
-    for (auto *b : db) b->acct = &ws->dev_bytes;
 
     const int K = ws->K;
     std::vector<double> mh(2 * K * K + 3 * K, 0.0);
@@ -277,8 +151,11 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     std::memcpy(&mh[2 * K * K], m->eval, sizeof(double) * K);
     std::memcpy(&mh[2 * K * K + K], m->prior, sizeof(double) * K);
     std::vector<int32_t> leaf_nodes, leaf_parent;
-    for (int32_t v = 0; v < t->n; v++)
+    std::vector<uint8_t> has_child(t->n, 0);
+    for (int32_t v = 0; v < t->n; v++) {
         if (t->ent_of_node[v] < 0) { leaf_nodes.push_back(v); leaf_parent.push_back(t->parent[v]); }
+        else has_child[v] = 1;
+    }
     ws->n_leaves = (int)leaf_nodes.size();
     ws->dist = t->dist;
     int rc = BNK_OK;
@@ -303,6 +180,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     step(upload(ws->d_node_of_ent, t->node_of_ent, ws->stream));
     step(upload(ws->d_leaf_nodes, leaf_nodes, ws->stream));
     step(upload(ws->d_leaf_parent, leaf_parent, ws->stream));
+    step(upload(ws->d_has_child, has_child, ws->stream));
     step(upload(ws->d_dist, ws->dist, ws->stream));
     if (rc == BNK_OK && ws->d_flag.ensure(1) != cudaSuccess) rc = fail(BNK_ERR_NOMEM, "ws: device allocation failed");
     if (rc == BNK_OK && ws->d_sum.ensure(1) != cudaSuccess) rc = fail(BNK_ERR_NOMEM, "ws: device allocation failed");
@@ -338,12 +216,39 @@ extern "C" int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread)
     if (tile_cols < 0) tile_cols = -tile_cols;
     ws->cfg_tile_cols = tile_cols;
     ws->cfg_cpt = cols_per_thread;
-    ws->ncols = -1;  // tiles are rebuilt by the next bnk_set_rates
+    ws->retile = true;  // tiles are rebuilt, for the rates already set, by the next call that needs them
     return BNK_OK;
 }
 
-extern "C" int64_t bnk_ws_launch_count(const bnk_ws *ws) { return ws ? ws->launches : 0; }
-extern "C" int64_t bnk_ws_device_bytes(const bnk_ws *ws) { return ws ? ws->dev_bytes : 0; }
+extern "C" int bnk_ws_set_pipeline(bnk_ws *ws, int32_t chunk_cols)
+{
+    if (!ws) return fail(BNK_ERR_ARG, "ws: null");
+    ws->pipeline_cols = chunk_cols;
+    return BNK_OK;
+}
+
+extern "C" int bnk_ws_set_evidence_mode(bnk_ws *ws, int mode)
+{
+    if (!ws || mode < BNK_EVIDENCE_AUTO || mode > BNK_EVIDENCE_ANYWHERE) return fail(BNK_ERR_ARG, "evidence mode: bad argument");
+    ws->evidence_mode = mode;
+    for (bnk_ws *sub : ws->subs) sub->evidence_mode = mode;
+    return BNK_OK;
+}
+
+extern "C" int64_t bnk_ws_launch_count(const bnk_ws *ws)
+{
+    if (!ws) return 0;
+    int64_t l = ws->launches;
+    for (const bnk_ws *sub : ws->subs) l += sub->launches;
+    return l;
+}
+extern "C" int64_t bnk_ws_device_bytes(const bnk_ws *ws)
+{
+    if (!ws) return 0;
+    int64_t b = ws->reg.bytes;
+    for (const bnk_ws *sub : ws->subs) b += sub->reg.bytes;
+    return b;
+}
 
 extern "C" int bnk_ws_phase_ms(bnk_ws *ws, int phase, float *ms)
 {
@@ -365,16 +270,17 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     if (rates)
         for (int32_t c = 0; c < n_cols; c++)
             if (!(rates[c] >= 0.0) || std::isinf(rates[c])) return fail(BNK_ERR_ARG, "set_rates: rate[%d] is negative or not finite", c);
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     const int K = ws->K;
     // same assignment as last time (an optimisation loop re-evaluating, a second pass over the same
     // alignment): keep categories, tiles and their device copies; only the tables are marked stale
-    if (ws->ncols == n_cols && ws->rates_null == (rates == nullptr) &&
+    if (!ws->retile && ws->ncols == n_cols && ws->rates_null == (rates == nullptr) &&
         (rates == nullptr || (ws->last_rates.size() == (size_t)n_cols &&
-                              std::memcmp(ws->last_rates.data(), rates, sizeof(double) * n_cols) == 0))) {
-        ws->tables_log_valid = ws->tables_lin_valid = false;
-        return BNK_OK;
-    }
+                              std::memcmp(ws->last_rates.data(), rates, sizeof(double) * n_cols) == 0)))
+        return BNK_OK;  // the tables depend on (rates, distances) only: still valid (bnk_set_distances marks them stale)
+    std::vector<double> kept;  // rates may alias last_rates (re-tiling after bnk_ws_configure)
+    if (rates && !ws->last_rates.empty() && rates == ws->last_rates.data()) { kept = ws->last_rates; rates = kept.data(); }
+    ws->retile = false;
     // distinct rates, ascending; columns sorted by (rate, index)
     ws->orig_col.resize(n_cols);
     for (int32_t c = 0; c < n_cols; c++) ws->orig_col[c] = c;
@@ -600,8 +506,9 @@ extern "C" int bnk_set_distances(bnk_ws *ws, const double *dist)
     if (!ws || !dist) return fail(BNK_ERR_ARG, "set_distances: bad argument");
     for (int32_t i = 0; i < ws->n; i++)
         if (ws->tree->parent[i] >= 0 && !(dist[i] >= 0.0)) return fail(BNK_ERR_TREE, "set_distances: distance[%d] is negative or NaN", i);
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     ws->dist.assign(dist, dist + ws->n);
+    ws->dist_version++;
     CUDA_TRY(cudaMemcpyAsync(ws->d_dist.p, ws->dist.data(), sizeof(double) * ws->n, cudaMemcpyHostToDevice, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
     ws->tables_log_valid = ws->tables_lin_valid = false;
@@ -611,7 +518,7 @@ extern "C" int bnk_set_distances(bnk_ws *ws, const double *dist)
 extern "C" int bnk_probs(bnk_ws *ws, int32_t n_t, const double *t, double *P, double *logP)
 {
     if (!ws || !t || n_t < 1) return fail(BNK_ERR_ARG, "probs: bad argument");
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     const int KK = ws->K * ws->K;
     DevBuf<double> dt, dP, dL, dr;
     int rc = BNK_OK;
@@ -644,25 +551,31 @@ static int ensure_rates(bnk_ws *ws, int32_t n_cols)
 {
     if (n_cols < 1) return fail(BNK_ERR_ARG, "n_cols must be >= 1");
     if (ws->ncols < 0) return bnk_set_rates(ws, n_cols, nullptr);
+    if (ws->retile) TRY(bnk_set_rates(ws, ws->ncols, ws->rates_null ? nullptr : ws->last_rates.data()));
     if (ws->ncols != n_cols)
         return fail(BNK_ERR_STATE, "n_cols = %d but rates were set for %d columns (call bnk_set_rates first)", n_cols, ws->ncols);
     return BNK_OK;
 }
 
-// decides FAST vs GENERAL kernels and produces the category-sorted copies of the inputs
+// Decides lean vs general kernels.  BNK_EVIDENCE_AUTO scans the observation matrix on the device (one launch):
+// evidence on a node with children selects the general kernels, a byte that is neither BNK_NONE nor a state
+// index is an error -- that costs one 4-byte read-back and a stream synchronisation per call.  The other two
+// modes take the caller's word (bnk_ws_set_evidence_mode), launch nothing and never synchronise.
 static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_present, bool &general,
                           const uint8_t *&obs_s, const uint8_t *&present_s)
 {
     const int nc = ws->ncols;
-    general = d_present != nullptr;
-    if (!general && ws->n_int > 0) {
+    general = d_present != nullptr || ws->evidence_mode == BNK_EVIDENCE_ANYWHERE;
+    if (ws->evidence_mode == BNK_EVIDENCE_AUTO) {
         int32_t flag = 0;
         CUDA_TRY(cudaMemsetAsync(ws->d_flag.p, 0, sizeof(int32_t), ws->stream));
-        CUDA_TRY(launch_scan_internal_obs(d_obs, ws->d_node_of_ent.p, ws->n_int, nc, ws->d_flag.p, ws->stream));
+        CUDA_TRY(launch_scan_obs(d_obs, ws->d_has_child.p, ws->n, nc, ws->K, ws->d_flag.p, ws->stream));
         ws->launches++;
         CUDA_TRY(cudaMemcpyAsync(&flag, ws->d_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->stream));
         CUDA_TRY(cudaStreamSynchronize(ws->stream));
-        general = flag != 0;
+        if (flag & 2)
+            return fail(BNK_ERR_ARG, "observed states must be < %d (the model's alphabet size) or BNK_NONE (255)", ws->K);
+        if (flag & 1) general = true;
     }
     // inputs are consumed in the caller's column order (the kernels index them through orig_col)
     obs_s = d_obs; present_s = d_present;
@@ -802,6 +715,12 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
         s.a.spill = ws->d_spill.p;
     }
     s.wl.smem_bytes = base + per_slot * smem_slots;
+    if (t->max_children >= 32) {  // joint up-sweep: the pairwise-addition queue of big multifurcations lives in global scratch
+        const int32_t stride = 2 * t->max_children + 2;
+        CUDA_TRY(ws->d_qscratch.ensure((size_t)s.wl.n_tiles * ws->threads * ws->cpt * stride));
+        s.a.qscratch = ws->d_qscratch.p;
+        s.a.qstride = stride;
+    }
     return BNK_OK;
 }
 
@@ -864,11 +783,9 @@ static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch)
 extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present, uint8_t *d_out_state)
 {
     if (!ws || !d_obs || !d_out_state) return fail(BNK_ERR_ARG, "joint: null argument");
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
     const int K = ws->K, nc = ws->ncols;
-    if (ws->tree->max_children > 31)
-        return fail(BNK_ERR_TREE, "max-product kernels handle at most 31 children per node (the tree has a node with %d)", ws->tree->max_children);
     bool general;
     const uint8_t *obs_s, *present_s;
     TRY(prepare_inputs(ws, d_obs, d_present, general, obs_s, present_s));
@@ -962,8 +879,12 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
 extern "C" int bnk_joint(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present, uint8_t *out_state)
 {
     if (!ws || !obs || !out_state) return fail(BNK_ERR_ARG, "joint: null argument");
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
+    if (ws_wants_pipeline(ws, n_cols)) {
+        HostCall hc{0, n_cols, 0, n_cols, obs, present, ws->rates_null ? nullptr : ws->last_rates.data(), out_state, nullptr, 0, nullptr, nullptr, nullptr};
+        return ws_run_host_range(ws, hc);
+    }
     const size_t bytes = (size_t)ws->n * n_cols;
     CUDA_TRY(ws->d_obs_in.ensure(bytes));
     CUDA_TRY(ws->d_state.ensure(bytes));
@@ -981,34 +902,51 @@ extern "C" int bnk_joint(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const u
 // --------------------------------------------------------------------------------------
 // marginal / log-likelihood
 // --------------------------------------------------------------------------------------
-static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present, const int32_t *query_nodes,
+int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present, const int32_t *query_nodes,
                    int32_t n_query, double *d_out_post, double *d_out_logl, double *d_out_sum)
 {
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
     const bnk_tree *t = ws->tree;
     const int K = ws->K, nc = ws->ncols;
     const bool want_post = d_out_post != nullptr;
-    for (int32_t v = 0; v < t->n; v++)
-        if (t->first[v + 1] - t->first[v] > 16)
-            return fail(BNK_ERR_TREE, "sum-product kernels handle at most 16 children per node (node %d has %d)", v, t->first[v + 1] - t->first[v]);
-    // query rows
+    // query rows.  A node asked for twice is computed once and its row copied; a childless node gets its
+    // posterior from its parent's row (leaf_post_kernel), which is computed into an extra row when the
+    // parent itself was not asked for.
     std::vector<int32_t> qrow(std::max(ws->n_int, 1), -1);
+    struct LeafQuery { int32_t q, node, parent, parent_row; };
+    std::vector<LeafQuery> leaf_queries;
+    std::vector<std::pair<int32_t, int32_t>> dup_rows;  // (computed row, row to fill)
+    int32_t n_rows = n_query < 0 ? ws->n_int : n_query;
+    double *post_base = d_out_post;
     if (want_post) {
         if (n_query < 0) {
             for (int32_t e = 0; e < ws->n_int; e++) qrow[e] = e;
         } else {
             if (!query_nodes && n_query > 0) return fail(BNK_ERR_ARG, "marginal: query_nodes is null");
+            std::vector<int32_t> leaf_first(t->n, -1);
             for (int32_t q = 0; q < n_query; q++) {
                 const int32_t v = query_nodes[q];
                 if (v < 0 || v >= t->n) return fail(BNK_ERR_QUERY, "marginal: query node %d is not a node of the tree", v);
                 if (t->ent_of_node[v] >= 0) {
-                    if (qrow[t->ent_of_node[v]] >= 0) return fail(BNK_ERR_QUERY, "marginal: node %d queried twice", v);
-                    qrow[t->ent_of_node[v]] = q;
-                } else {  // childless node: no posterior is produced (NaN row)
-                    CUDA_TRY(launch_fill_f64(d_out_post + (size_t)q * nc * K, (size_t)nc * K, NAN, ws->stream));
-                    ws->launches++;
+                    if (qrow[t->ent_of_node[v]] >= 0) dup_rows.push_back({qrow[t->ent_of_node[v]], q});
+                    else qrow[t->ent_of_node[v]] = q;
+                } else if (leaf_first[v] >= 0) {
+                    dup_rows.push_back({leaf_first[v], q});
+                } else {
+                    leaf_first[v] = q;
+                    leaf_queries.push_back(LeafQuery{q, v, t->parent[v], -1});
                 }
+            }
+            for (LeafQuery &lq : leaf_queries) {
+                if (lq.parent < 0) continue;
+                int32_t &r = qrow[t->ent_of_node[lq.parent]];
+                if (r < 0) r = n_rows++;  // extra row behind the caller's
+                lq.parent_row = r;
+            }
+            if (n_rows > n_query) {  // the sweep writes into a private buffer; the caller's rows are copied out below
+                CUDA_TRY(ws->d_post_x.ensure((size_t)n_rows * nc * K));
+                post_base = ws->d_post_x.p;
             }
         }
         TRY(upload(ws->d_qrow, qrow, ws->stream));
@@ -1074,7 +1012,7 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
         if (want_post) {
             s.a.T_row = ws->d_PT.p;
             s.a.T_aux = ws->d_P.p;
-            s.a.out_post = d_out_post;
+            s.a.out_post = post_base;
             s.a.qrow = (n_query < 0) ? nullptr : ws->d_qrow.p;
             if (s.hybrid) {
                 CUDA_TRY(ws->d_tmsg.ensure((size_t)ws->n_int * nc * K));
@@ -1087,16 +1025,36 @@ static int run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
                               : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;
             if (s.hybrid) {
-                w.tmsg = ws->d_tmsg.p; w.out_post = d_out_post; w.qrow = s.a.qrow;
+                w.tmsg = ws->d_tmsg.p; w.out_post = post_base; w.qrow = s.a.qrow;
                 TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
                     return gen ? launch_down_wide_gen(K, wa, n_wt, cnt, ws->stream) : launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
+            }
+            for (const LeafQuery &lq : leaf_queries) {
+                LeafPostArgs la;
+                std::memset(&la, 0, sizeof(la));
+                la.node = lq.node; la.parent = lq.parent; la.ncols = nc; la.n_nodes = ws->n; la.K = K;
+                la.obs = d_obs; la.present = d_present; la.P = ws->d_P.p;
+                la.cat_of_col = ws->d_cat_of_col.p; la.cat_lo = ck.cat_lo; la.cat_hi = ck.cat_hi;
+                la.parent_row = lq.parent_row >= 0 ? post_base + (size_t)lq.parent_row * nc * K : nullptr;
+                la.out_row = post_base + (size_t)lq.q * nc * K;
+                CUDA_TRY(launch_leaf_post(la, ws->stream));
+                ws->launches++;
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][1], ws->stream));
             ws->ev_valid[4] = true;
         }
     }
+    if (want_post && ws->n_int == 0)  // a forest of single nodes: nothing has a BN variable
+        for (const LeafQuery &lq : leaf_queries) {
+            CUDA_TRY(launch_fill_f64(post_base + (size_t)lq.q * nc * K, (size_t)nc * K, NAN, ws->stream));
+            ws->launches++;
+        }
+    if (want_post && post_base != d_out_post && n_query > 0)
+        CUDA_TRY(cudaMemcpyAsync(d_out_post, post_base, sizeof(double) * (size_t)n_query * nc * K, cudaMemcpyDeviceToDevice, ws->stream));
+    for (const auto &dr : dup_rows)
+        CUDA_TRY(cudaMemcpyAsync(d_out_post + (size_t)dr.second * nc * K, d_out_post + (size_t)dr.first * nc * K,
+                                 sizeof(double) * (size_t)nc * K, cudaMemcpyDeviceToDevice, ws->stream));
     if (d_out_sum) { CUDA_TRY(launch_sum_f64(logl, nc, d_out_sum, ws->stream)); ws->launches++; }
-    if (want_post) CUDA_TRY(cudaStreamSynchronize(ws->stream));  // qrow (host vector) was uploaded asynchronously
     return BNK_OK;
 }
 
@@ -1104,14 +1062,14 @@ extern "C" int bnk_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs
                                 const int32_t *query_nodes_host, int32_t n_query, double *d_out_post, double *d_out_logl)
 {
     if (!ws || !d_obs) return fail(BNK_ERR_ARG, "marginal: null argument");
-    return run_sum(ws, n_cols, d_obs, d_present, query_nodes_host, n_query, d_out_post, d_out_logl, nullptr);
+    return ws_run_sum(ws, n_cols, d_obs, d_present, query_nodes_host, n_query, d_out_post, d_out_logl, nullptr);
 }
 
 extern "C" int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present,
                               double *d_out_logl, double *d_out_sum)
 {
     if (!ws || !d_obs) return fail(BNK_ERR_ARG, "loglik: null argument");
-    return run_sum(ws, n_cols, d_obs, d_present, nullptr, 0, nullptr, d_out_logl, d_out_sum);
+    return ws_run_sum(ws, n_cols, d_obs, d_present, nullptr, 0, nullptr, d_out_logl, d_out_sum);
 }
 
 static int stage_inputs(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present)
@@ -1130,14 +1088,18 @@ extern "C" int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, cons
                             const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl)
 {
     if (!ws || !obs) return fail(BNK_ERR_ARG, "marginal: null argument");
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
+    if (ws_wants_pipeline(ws, n_cols)) {
+        HostCall hc{1, n_cols, 0, n_cols, obs, present, ws->rates_null ? nullptr : ws->last_rates.data(), nullptr, query_nodes, n_query, out_post, out_logl, nullptr};
+        return ws_run_host_range(ws, hc);
+    }
     TRY(stage_inputs(ws, n_cols, obs, present));
     const int nq = n_query < 0 ? ws->n_int : n_query;
     const size_t post_elems = (size_t)nq * n_cols * ws->K;
     if (out_post && post_elems) CUDA_TRY(ws->d_post.ensure(post_elems));
     if (out_logl) CUDA_TRY(ws->d_logl.ensure(n_cols));
-    TRY(run_sum(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, query_nodes, n_query,
+    TRY(ws_run_sum(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, query_nodes, n_query,
                 (out_post && post_elems) ? ws->d_post.p : nullptr, out_logl ? ws->d_logl.p : nullptr, nullptr));
     if (out_post && post_elems)
         CUDA_TRY(cudaMemcpyAsync(out_post, ws->d_post.p, post_elems * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
@@ -1149,11 +1111,18 @@ extern "C" int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, cons
 extern "C" int bnk_loglik(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present, double *out_logl, double *out_sum)
 {
     if (!ws || !obs) return fail(BNK_ERR_ARG, "loglik: null argument");
-    CUDA_TRY(cudaSetDevice(ws->device));
+    ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
+    if (ws_wants_pipeline(ws, n_cols)) {
+        double total = 0.0;
+        HostCall hc{2, n_cols, 0, n_cols, obs, present, ws->rates_null ? nullptr : ws->last_rates.data(), nullptr, nullptr, 0, nullptr, out_logl, &total};
+        TRY(ws_run_host_range(ws, hc));
+        if (out_sum) *out_sum = total;
+        return BNK_OK;
+    }
     TRY(stage_inputs(ws, n_cols, obs, present));
     CUDA_TRY(ws->d_logl.ensure(n_cols));
-    TRY(run_sum(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, nullptr, 0, nullptr, ws->d_logl.p,
+    TRY(ws_run_sum(ws, n_cols, ws->d_obs_in.p, present ? ws->d_present_in.p : nullptr, nullptr, 0, nullptr, ws->d_logl.p,
                 out_sum ? ws->d_sum.p : nullptr));
     if (out_logl) CUDA_TRY(cudaMemcpyAsync(out_logl, ws->d_logl.p, sizeof(double) * n_cols, cudaMemcpyDeviceToHost, ws->stream));
     if (out_sum) CUDA_TRY(cudaMemcpyAsync(out_sum, ws->d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));

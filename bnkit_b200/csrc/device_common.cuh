@@ -64,6 +64,9 @@ struct WalkArgs {
     double *tmsg;               // from-above vectors handed to wide children, [ent][K][ncols]
     const int32_t *esum_wide;   // [ncols] rescale exponents accumulated by the wide sum up-sweep (or nullptr)
     const double *logl_wide;    // [ncols] log-likelihood terms the general wide kernels accumulated (or nullptr)
+    // general joint up-sweep, nodes with >= 32 children: queue of the pairwise additions, one region per (thread, column)
+    double *qscratch;
+    int32_t qstride;
 };
 
 // arguments of the level kernels (wide.cu); all column indices are in sorted space
@@ -179,11 +182,22 @@ struct TracebackArgs {
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t st);
 cudaError_t launch_leaf_states(const TracebackArgs &a, cudaStream_t st);
 
+struct LeafPostArgs {
+    int32_t node, parent, ncols, n_nodes, K;
+    const uint8_t *obs, *present;   // original column order
+    const double *P;                // [cat][node][K*K] tables of the chunk being processed
+    const int32_t *cat_of_col;      // original column -> global category
+    int32_t cat_lo, cat_hi;
+    const double *parent_row;       // [ncols][K] posterior of the parent (NaN rows where it has none)
+    double *out_row;                // [ncols][K]
+};
+cudaError_t launch_leaf_post(const LeafPostArgs &a, cudaStream_t st);
+
 cudaError_t launch_gather_cols(const uint8_t *in, uint8_t *out, const int32_t *orig_col, int n_rows,
                                int ncols, cudaStream_t st);
-// flag[0] |= 1 if any internal-node row of obs holds an observation
-cudaError_t launch_scan_internal_obs(const uint8_t *obs, const int32_t *node_of_ent, int n_int, int ncols,
-                                     int32_t *flag, cudaStream_t st);
+// flag[0] |= 1 if a node with children holds an observation, |= 2 if a byte is neither BNK_NONE nor < K
+cudaError_t launch_scan_obs(const uint8_t *obs, const uint8_t *has_child, int n_nodes, int ncols, int K,
+                            int32_t *flag, cudaStream_t st);
 cudaError_t launch_fill_f64(double *p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_sum_f64(const double *in, int n, double *out, cudaStream_t st);
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/bnkgpu.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -27,6 +28,8 @@ int model_from_rates(int K, const double *F, const double *M, bool symmetric, bo
 int model_by_name(const char *name, const double *F_override, bnk_model **out);
 int model_from_eigen(int K, const double *F, const double *evec, const double *ievec,
                      const double *eval, bnk_model **out);
+void tree_retain(bnk_tree *t);
+void tree_release(bnk_tree *t);  // deletes the tree when the last reference goes
 
 // One step of the column-tile walk = one internal node (a node with >= 1 child in the
 // static tree).  Childless nodes never get a step: their message is a table lookup made
@@ -76,6 +79,9 @@ constexpr int32_t SLOT_WIDE = -2;       // Step::c_slot: the child was handled b
 }  // namespace bnk
 
 struct bnk_tree {
+    // reference count: bnk_tree_create = 1, every workspace holds one more, bnk_tree_destroy drops the
+    // caller's -- so a tree destroyed before its workspaces stays alive until the last of them is gone
+    std::atomic<int> refs{1};
     int32_t n = 0, n_int = 0, root_count = 0;
     std::vector<int32_t> parent;
     std::vector<double> dist;

@@ -272,11 +272,13 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) up_ke
             if (MODE == 0 && st.n_child > 2 && need) {
                 // >= 3 single-variable factors: the reference multiplies them along Factorize.getProductTree
                 // (Factorize.java:331-375) = queue pairing over [base, observed children, unobserved children]
-                double q[2 * MAXQ + 1];
+                double qloc[2 * MAXQ + 1];
+                double *q = qloc;  // nodes with MAXQ or more children keep the queue in global scratch (any arity)
+                if (st.n_child >= MAXQ) q = a.qscratch + ((size_t)(blockIdx.x * blockDim.x + tid) * CPT + j) * a.qstride;
                 int m = 0;
                 if (rootlike) q[m++] = G;
                 for (int pass = 0; pass < 2; pass++) {
-                    for (int e = 0; e < st.n_child && e < MAXQ - 1; e++) {
+                    for (int e = 0; e < st.n_child; e++) {
                         int cnode, cslot, cent; bool pu; uint8_t ou;
                         child_info(e, cnode, cslot, cent, pu, ou);
                         if (!pu) continue;
@@ -551,52 +553,63 @@ __global__ void __launch_bounds__(CPT == 1 ? 768 : (CPT == 2 ? 512 : 256)) down_
                     else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
                 }
             } else {
-                double gv[MAXDEG_LOCAL], suf[MAXDEG_LOCAL];
-                uint8_t push[MAXDEG_LOCAL];
-                const int nch = st.n_child < MAXDEG_LOCAL ? st.n_child : MAXDEG_LOCAL;
-                double G = 1.0;
-                for (int e = 0; e < nch; e++) {
+                // value of child e's message for entry p, and whether the child receives a from-above vector
+                auto child_val = [&](int e, bool &push) -> double {
                     const ChildRef ch = a.down_child[st.child_begin + e];
-                    gv[e] = 1.0; push[e] = 0;
+                    push = false;
                     const bool pu = (e == 0) ? (b.pu[0] != 0) : (e == 1) ? (b.pu[1] != 0)
                                   : (!(GENERAL && a.present) || a.present[(size_t)ch.node * a.ncols + ocol[j]] != 0);
-                    if (!pu) continue;
+                    if (!pu) return 1.0;
                     const uint8_t ou = (e == 0) ? b.ou[0] : (e == 1) ? b.ou[1]
                                      : ((GENERAL || ch.ent < 0) ? a.obs[(size_t)ch.node * a.ncols + ocol[j]] : (uint8_t)BNK_NONE);
-                    if (e == 0) {
-                        gv[e] = child_value(a, st, b, L0[j], 0, tb[j], col[j], p, K);
-                    } else if (e == 1) {
-                        gv[e] = child_value(a, st, b, L0[j], 1, tb[j], col[j], p, K);
-                    } else if (ou != BNK_NONE) {
-                        gv[e] = a.T_col[(tb[j] + ch.node) * KK + ou * K + p];
-                    } else if (ch.ent < 0) {
+                    push = (ou == BNK_NONE && ch.ent >= 0);
+                    if (e == 0) return child_value(a, st, b, L0[j], 0, tb[j], col[j], p, K);
+                    if (e == 1) return child_value(a, st, b, L0[j], 1, tb[j], col[j], p, K);
+                    if (ou != BNK_NONE) return a.T_col[(tb[j] + ch.node) * KK + ou * K + p];
+                    if (ch.ent < 0) {
                         double s = 0.0;
                         for (int x = 0; x < K; x++) s += a.T_col[(tb[j] + ch.node) * KK + x * K + p];
-                        gv[e] = s;
-                    } else if (ch.slot == SLOT_WIDE) {
-                        gv[e] = a.msg[((size_t)ch.ent * K + p) * a.ncols + col[j]];
-                    } else {
-                        gv[e] = a.msg[((size_t)ch.ent * a.ncols + col[j]) * K + p];
+                        return s;
                     }
-                    push[e] = (ou == BNK_NONE && ch.ent >= 0);
-                    G *= gv[e];
-                }
-                U[j] = D * G;
-                {
-                    double s = 1.0;
-                    for (int e = nch - 1; e >= 0; e--) { suf[e] = s; s *= gv[e]; }
-                }
-                double pre = D;
-                for (int e = 0; e < nch; e++) {
-                    if (push[e]) {
-                        const ChildRef chp = a.down_child[st.child_begin + e];
-                        const int sl = chp.slot;
-                        const double t = pre * suf[e];
-                        if (sl == SLOT_WIDE) a.tmsg[((size_t)chp.ent * K + p) * a.ncols + col[j]] = t;
-                        else if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
-                        else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
+                    if (ch.slot == SLOT_WIDE) return a.msg[((size_t)ch.ent * K + p) * a.ncols + col[j]];
+                    return a.msg[((size_t)ch.ent * a.ncols + col[j]) * K + p];
+                };
+                auto push_t = [&](int e, double t) {
+                    const ChildRef chp = a.down_child[st.child_begin + e];
+                    const int sl = chp.slot;
+                    if (sl == SLOT_WIDE) a.tmsg[((size_t)chp.ent * K + p) * a.ncols + col[j]] = t;
+                    else if (sl < a.smem_slots) sm.stack[((size_t)sl * tcpad + lc[j]) * K + p] = t;
+                    else a.spill[((size_t)(sl - a.smem_slots) * a.ncols + col[j]) * K + p] = t;
+                };
+                if (st.n_child <= MAXDEG_LOCAL) {  // prefix / suffix products in registers
+                    double gv[MAXDEG_LOCAL], suf[MAXDEG_LOCAL];
+                    bool push[MAXDEG_LOCAL];
+                    const int nch = st.n_child;
+                    double G = 1.0;
+                    for (int e = 0; e < nch; e++) { gv[e] = child_val(e, push[e]); G *= gv[e]; }
+                    U[j] = D * G;
+                    {
+                        double s = 1.0;
+                        for (int e = nch - 1; e >= 0; e--) { suf[e] = s; s *= gv[e]; }
                     }
-                    pre *= gv[e];
+                    double pre = D;
+                    for (int e = 0; e < nch; e++) {
+                        if (push[e]) push_t(e, pre * suf[e]);
+                        pre *= gv[e];
+                    }
+                } else {  // any arity (Factorize.getProduct multiplies any number of factors): values re-read per child
+                    double G = 1.0;
+                    for (int e = 0; e < st.n_child; e++) { bool pe; G *= child_val(e, pe); }
+                    U[j] = D * G;
+                    for (int e = 0; e < st.n_child; e++) {
+                        bool pe, dummy;
+                        (void)child_val(e, pe);
+                        if (!pe) continue;
+                        double t = D;
+                        for (int w = 0; w < st.n_child; w++)
+                            if (w != e) t *= child_val(w, dummy);
+                        push_t(e, t);
+                    }
                 }
             }
             gs[(size_t)lc[j] * LROW + p] = U[j];

@@ -137,6 +137,59 @@ cudaError_t launch_leaf_states(const TracebackArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// Posterior of an uninstantiated CHILDLESS node v (possible after orphan flooding, IdxTree.java:429-432): the
+// reference's elimination gives it a distribution like any other variable.  v sends its parent p the message
+// g_v[xp] = sum_x P_v[xp][x], so with the parent's (normalised) posterior U_p the vector from above is
+// T[xp] = U_p[xp] / g_v[xp] and post_v[x] ~ sum_xp P_v[xp][x] T[xp]; under an observed parent it is the
+// normalised row P_v[obs_p][.].  One thread per column; rows of NaN where v has no BN variable.
+__global__ void leaf_post_kernel(const LeafPostArgs a)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;  // ORIGINAL column
+    if (col >= a.ncols) return;
+    const int gcat = a.cat_of_col[col];
+    if (gcat < a.cat_lo || gcat >= a.cat_hi) return;
+    const int K = a.K;
+    double *out = a.out_row + (size_t)col * K;
+    const size_t vc = (size_t)a.node * a.ncols + col, pc = (size_t)(a.parent < 0 ? 0 : a.parent) * a.ncols + col;
+    const bool pv = a.present == nullptr || a.present[vc];
+    const bool pp = a.parent >= 0 && (a.present == nullptr || a.present[pc]);
+    bool ok = pv && pp && a.obs[vc] == BNK_NONE;
+    const double *P = a.P + ((size_t)(gcat - a.cat_lo) * a.n_nodes + a.node) * K * K;
+    double y[BNK_MAXK];
+    if (ok) {
+        const int op = a.obs[pc];
+        if (op != BNK_NONE) {
+            for (int x = 0; x < K; x++) y[x] = P[op * K + x];
+        } else {
+            const double *up = a.parent_row + (size_t)col * K;
+            if (up[0] != up[0]) ok = false;
+            else {
+                for (int x = 0; x < K; x++) y[x] = 0.0;
+                for (int xp = 0; xp < K; xp++) {
+                    double g = 0.0;
+                    for (int x = 0; x < K; x++) g += P[xp * K + x];
+                    const double t = up[xp] / g;
+                    for (int x = 0; x < K; x++) y[x] = fma(P[xp * K + x], t, y[x]);
+                }
+            }
+        }
+    }
+    if (ok) {
+        double s = 0.0;
+        for (int x = 0; x < K; x++) s += y[x];
+        for (int x = 0; x < K; x++) out[x] = y[x] / s;
+    } else {
+        for (int x = 0; x < K; x++) out[x] = CUDART_NAN;
+    }
+}
+
+cudaError_t launch_leaf_post(const LeafPostArgs &a, cudaStream_t st)
+{
+    if (a.ncols == 0) return cudaSuccess;
+    leaf_post_kernel<<<(a.ncols + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 // out[row][c] = in[row][orig_col[c]]
 __global__ void gather_cols_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                                    const int32_t *__restrict__ orig_col, int n_rows, int ncols)
@@ -156,23 +209,46 @@ cudaError_t launch_gather_cols(const uint8_t *in, uint8_t *out, const int32_t *o
     return cudaGetLastError();
 }
 
-__global__ void scan_internal_obs_kernel(const uint8_t *__restrict__ obs, const int32_t *__restrict__ node_of_ent,
-                                         int n_int, int ncols, int32_t *flag)
+// One pass over the whole observation matrix: flag |= 1 if a node with children carries an observation (the
+// lean kernels assume evidence on childless nodes only), flag |= 2 if any byte is neither BNK_NONE nor a state
+// index < K (it would index past the K x K tables: ADVICE r1).  Rows are read 4 bytes per thread when aligned.
+__global__ void __launch_bounds__(256) scan_obs_kernel(const uint8_t *__restrict__ obs, const uint8_t *__restrict__ has_child,
+                                                       int n_nodes, int ncols, int K, int vec4, int32_t *flag)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     int found = 0;
-    if (c < ncols)
-        for (int e = blockIdx.y; e < n_int; e += gridDim.y)
-            if (obs[(size_t)node_of_ent[e] * ncols + c] != BNK_NONE) found = 1;
-    if (__syncthreads_or(found) && threadIdx.x == 0) atomicOr(flag, 1);
+    if (vec4) {
+        const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (c4 * 4 < ncols)
+            for (int v = blockIdx.y; v < n_nodes; v += gridDim.y) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(obs + (size_t)v * ncols + 4 * c4);
+                if (w == 0xffffffffu) continue;
+                const int hc = has_child[v];
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int o = (w >> (8 * b)) & 0xff;
+                    if (o != BNK_NONE) found |= (hc ? 1 : 0) | (o >= K ? 2 : 0);
+                }
+            }
+    } else {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        if (c < ncols)
+            for (int v = blockIdx.y; v < n_nodes; v += gridDim.y) {
+                const int o = obs[(size_t)v * ncols + c];
+                if (o != BNK_NONE) found |= (has_child[v] ? 1 : 0) | (o >= K ? 2 : 0);
+            }
+    }
+    const int any1 = __syncthreads_or(found & 1), any2 = __syncthreads_or(found & 2);
+    if (threadIdx.x == 0 && (any1 || any2)) atomicOr(flag, (any1 ? 1 : 0) | (any2 ? 2 : 0));
 }
 
-cudaError_t launch_scan_internal_obs(const uint8_t *obs, const int32_t *node_of_ent, int n_int, int ncols,
-                                     int32_t *flag, cudaStream_t st)
+cudaError_t launch_scan_obs(const uint8_t *obs, const uint8_t *has_child, int n_nodes, int ncols, int K,
+                            int32_t *flag, cudaStream_t st)
 {
-    if (n_int == 0 || ncols == 0) return cudaSuccess;
-    dim3 grid((ncols + 255) / 256, n_int < 2048 ? n_int : 2048);
-    scan_internal_obs_kernel<<<grid, 256, 0, st>>>(obs, node_of_ent, n_int, ncols, flag);
+    if (n_nodes == 0 || ncols == 0) return cudaSuccess;
+    const int vec4 = (ncols % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 3) == 0);
+    const int per = vec4 ? ncols / 4 : ncols;
+    dim3 grid((per + 255) / 256, n_nodes < 4096 ? n_nodes : 4096);
+    scan_obs_kernel<<<grid, 256, 0, st>>>(obs, has_child, n_nodes, ncols, K, vec4, flag);
     return cudaGetLastError();
 }
 

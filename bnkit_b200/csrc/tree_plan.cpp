@@ -250,7 +250,14 @@ extern "C" int bnk_tree_create(int32_t n_nodes, const int32_t *parent, const dou
     return BNK_OK;
 }
 
-extern "C" void bnk_tree_destroy(bnk_tree *t) { delete t; }
+namespace bnk {
+void tree_retain(bnk_tree *t) { if (t) t->refs.fetch_add(1, std::memory_order_relaxed); }
+void tree_release(bnk_tree *t)
+{
+    if (t && t->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) delete t;
+}
+}  // namespace bnk
+extern "C" void bnk_tree_destroy(bnk_tree *t) { tree_release(t); }
 extern "C" int bnk_tree_size(const bnk_tree *t) { return t ? t->n : fail(BNK_ERR_ARG, "tree: null"); }
 extern "C" int bnk_tree_n_internal(const bnk_tree *t) { return t ? t->n_int : fail(BNK_ERR_ARG, "tree: null"); }
 

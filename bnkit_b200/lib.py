@@ -35,7 +35,12 @@ SYMBOLS = [
     "bnk_ws_device_bytes", "bnk_set_rates", "bnk_set_distances", "bnk_probs",
     "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
     "bnk_ws_phase_ms", "bnk_bep_presence",
+    "bnk_ws_set_evidence_mode", "bnk_ws_set_pipeline",
+    "bnk_mgpu_create", "bnk_mgpu_destroy", "bnk_mgpu_n_devices", "bnk_mgpu_shard", "bnk_mgpu_set_rates",
+    "bnk_mgpu_set_distances", "bnk_mgpu_joint", "bnk_mgpu_marginal", "bnk_mgpu_loglik", "bnk_mgpu_upload",
+    "bnk_mgpu_loglik_resident", "bnk_mgpu_reduction", "bnk_mgpu_launch_count",
 ]
+EVIDENCE_AUTO, EVIDENCE_LEAVES, EVIDENCE_ANYWHERE = 0, 1, 2
 
 
 def lib():
@@ -82,6 +87,24 @@ def lib():
     L.bnk_loglik_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
     L.bnk_ws_phase_ms.argtypes = [_vp, C.c_int, C.POINTER(C.c_float)]
     L.bnk_bep_presence.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip]
+    L.bnk_ws_set_evidence_mode.argtypes = [_vp, C.c_int]
+    L.bnk_ws_set_pipeline.argtypes = [_vp, C.c_int32]
+    L.bnk_mgpu_create.argtypes = [_vp, _vp, C.c_int32, C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
+    L.bnk_mgpu_destroy.argtypes = [_vp]
+    L.bnk_mgpu_destroy.restype = None
+    L.bnk_mgpu_n_devices.argtypes = [_vp]
+    L.bnk_mgpu_shard.argtypes = [_vp, C.c_int32, C.c_int, _ip, _ip]
+    L.bnk_mgpu_set_rates.argtypes = [_vp, C.c_int32, _dp]
+    L.bnk_mgpu_set_distances.argtypes = [_vp, _dp]
+    L.bnk_mgpu_joint.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
+    L.bnk_mgpu_marginal.argtypes = [_vp, C.c_int32, _vp, _vp, _ip, C.c_int32, _vp, _vp]
+    L.bnk_mgpu_loglik.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
+    L.bnk_mgpu_upload.argtypes = [_vp, C.c_int32, _vp, _vp]
+    L.bnk_mgpu_loglik_resident.argtypes = [_vp, _dp]
+    L.bnk_mgpu_reduction.argtypes = [_vp]
+    L.bnk_mgpu_reduction.restype = C.c_char_p
+    L.bnk_mgpu_launch_count.argtypes = [_vp]
+    L.bnk_mgpu_launch_count.restype = C.c_int64
     _LIB = L
     return L
 
@@ -241,10 +264,28 @@ class Workspace:
         return ms.value
 
     # ---- host-buffer entry points (numpy or pinned torch tensors) ----
+    def set_evidence_mode(self, mode):
+        """EVIDENCE_AUTO (scan + validate per call), EVIDENCE_LEAVES / EVIDENCE_ANYWHERE (caller's word, no sync)."""
+        check(lib().bnk_ws_set_evidence_mode(self.h, int(mode)))
+
+    def set_pipeline(self, chunk_cols):
+        """column chunking of the host-buffer calls: 0 automatic, < 0 off, > 0 columns per chunk"""
+        check(lib().bnk_ws_set_pipeline(self.h, int(chunk_cols)))
+
+    def _check_shapes(self, obs, present, out=None, out_shape=None):
+        """a short host array would make the library read / write past its end"""
+        if len(obs.shape) != 2 or obs.shape[0] != self.n:
+            raise ValueError("obs must be [n_nodes = %d][n_cols], got %r" % (self.n, tuple(obs.shape)))
+        if present is not None and tuple(present.shape) != tuple(obs.shape):
+            raise ValueError("present must have the shape of obs %r, got %r" % (tuple(obs.shape), tuple(present.shape)))
+        if out is not None and out_shape is not None and tuple(out.shape) != tuple(out_shape):
+            raise ValueError("output buffer must be %r, got %r" % (tuple(out_shape), tuple(out.shape)))
+
     def joint(self, obs, present=None, out=None):
         obs = _as_u8(obs)
         n_cols = obs.shape[1]
         present = None if present is None else _as_u8(present)
+        self._check_shapes(obs, present, out, (self.n, n_cols))
         if out is None:
             out = np.empty((self.n, n_cols), dtype=np.uint8)
         check(lib().bnk_joint(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(out)))
@@ -260,6 +301,7 @@ class Workspace:
         else:
             q = np.ascontiguousarray(query, dtype=np.int32)
             nq = rows = len(q)
+        self._check_shapes(obs, present, out, (rows, n_cols, self.K))
         if out is None:
             out = np.empty((rows, n_cols, self.K))
         logl = np.empty(n_cols) if want_logl else None
@@ -270,6 +312,7 @@ class Workspace:
         obs = _as_u8(obs)
         n_cols = obs.shape[1]
         present = None if present is None else _as_u8(present)
+        self._check_shapes(obs, present)
         logl = np.empty(n_cols)
         total = np.zeros(1)
         check(lib().bnk_loglik(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(logl), _ptr(total)))
@@ -290,6 +333,91 @@ class Workspace:
 
     def loglik_dev(self, n_cols, d_obs, d_present, d_out_logl, d_out_sum):
         check(lib().bnk_loglik_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _ptr(d_out_logl), _ptr(d_out_sum)))
+
+
+class MultiGPU:
+    """bnk_mgpu handle: one process, several devices, columns in contiguous blocks (the device-side counterpart of
+    the reference's thread pool over columns, ThreadedDecorators.java:28-72).  Host buffers in, host buffers out."""
+
+    def __init__(self, model, tree, max_cols, n_devices=0, devices=None):
+        self.model, self.tree = model, tree
+        h = _vp()
+        dv = None
+        if devices is not None:
+            dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+            n_devices = len(devices)
+        check(lib().bnk_mgpu_create(model.h, tree.h, int(max_cols), int(n_devices), dv, C.byref(h)))
+        self.h = h
+        self.K, self.n = model.K, tree.n
+        self.n_devices = lib().bnk_mgpu_n_devices(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bnk_mgpu_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def shard(self, n_cols, idx):
+        c0, nc = C.c_int32(0), C.c_int32(0)
+        check(lib().bnk_mgpu_shard(self.h, int(n_cols), int(idx), C.byref(c0), C.byref(nc)))
+        return c0.value, nc.value
+
+    def set_rates(self, n_cols, rates=None):
+        r = None if rates is None else np.ascontiguousarray(rates, dtype=np.float64)
+        check(lib().bnk_mgpu_set_rates(self.h, int(n_cols), _d(r)))
+
+    def set_distances(self, dist):
+        d = np.ascontiguousarray(dist, dtype=np.float64)
+        check(lib().bnk_mgpu_set_distances(self.h, _d(d)))
+
+    def joint(self, obs, present=None, out=None):
+        obs = _as_u8(obs)
+        present = None if present is None else _as_u8(present)
+        n_cols = obs.shape[1]
+        if out is None:
+            out = np.empty((self.n, n_cols), dtype=np.uint8)
+        check(lib().bnk_mgpu_joint(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(out)))
+        return out
+
+    def marginal(self, obs, present=None, query=None, want_logl=True, out=None):
+        obs = _as_u8(obs)
+        present = None if present is None else _as_u8(present)
+        n_cols = obs.shape[1]
+        if query is None:
+            nq, q, rows = -1, None, self.tree.n_internal
+        else:
+            q = np.ascontiguousarray(query, dtype=np.int32)
+            nq = rows = len(q)
+        if out is None:
+            out = np.empty((rows, n_cols, self.K))
+        logl = np.empty(n_cols) if want_logl else None
+        check(lib().bnk_mgpu_marginal(self.h, n_cols, _ptr(obs), _ptr(present), _i(q), nq, _ptr(out), _ptr(logl)))
+        return out, logl
+
+    def loglik(self, obs, present=None):
+        obs = _as_u8(obs)
+        present = None if present is None else _as_u8(present)
+        n_cols = obs.shape[1]
+        logl, total = np.empty(n_cols), np.zeros(1)
+        check(lib().bnk_mgpu_loglik(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(logl), _ptr(total)))
+        return logl, float(total[0])
+
+    def upload(self, obs, present=None):
+        obs = _as_u8(obs)
+        present = None if present is None else _as_u8(present)
+        check(lib().bnk_mgpu_upload(self.h, obs.shape[1], _ptr(obs), _ptr(present)))
+
+    def loglik_resident(self):
+        total = np.zeros(1)
+        check(lib().bnk_mgpu_loglik_resident(self.h, _d(total)))
+        return float(total[0])
+
+    def reduction(self):
+        return lib().bnk_mgpu_reduction(self.h).decode()
+
+    def launch_count(self):
+        return lib().bnk_mgpu_launch_count(self.h)
 
 
 def _as_u8(a):

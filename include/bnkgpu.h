@@ -23,6 +23,10 @@
  *     alignment row per node (dat.EnumSeq order), n_cols bytes per row.
  *   - a workspace owns its device buffers and a CUDA stream; calls on one workspace are
  *     serialised by the caller, different workspaces are independent.
+ *   - lifetimes: a workspace copies the model and holds a reference on the tree, so both handles may be
+ *     destroyed before the workspace (the tree's memory goes with its last workspace).
+ *   - every entry point selects the workspace's device for the duration of the call and restores the
+ *     caller's current device before it returns.
  *   - there is no CPU fallback: every entry point that computes fails with
  *     BNK_ERR_CUDA when no sm_100-class device is usable.
  */
@@ -111,6 +115,20 @@ void bnk_ws_destroy(bnk_ws *ws);
 int bnk_ws_sync(bnk_ws *ws);
 /* tuning knobs (0 = automatic): columns per CTA tile, columns per thread */
 int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread);
+/* Where may observed states sit?  AUTO (default) scans the observation matrix on the device in every call: it
+ * selects the general kernels when a node with children carries evidence (SubstNode.makeDenseFactor cases 2-4,
+ * src/bn/ctmc/SubstNode.java:538-590) and rejects bytes that are neither BNK_NONE nor < K (BNK_ERR_ARG) -- at
+ * the price of one 4-byte read-back + stream synchronisation per call.  LEAVES / ANYWHERE take the caller's
+ * word instead (GRASP only instantiates extants, POGTree.getNodeInstance src/dat/pog/POGTree.java:419-436):
+ * nothing is scanned or validated, *_dev calls only enqueue work and can be captured in a CUDA graph. */
+#define BNK_EVIDENCE_AUTO 0
+#define BNK_EVIDENCE_LEAVES 1
+#define BNK_EVIDENCE_ANYWHERE 2
+int bnk_ws_set_evidence_mode(bnk_ws *ws, int mode);
+/* Host-buffer calls (bnk_joint / bnk_marginal / bnk_loglik) on wide alignments run as column chunks through
+ * two internal workspaces on their own streams, so the result copy of a chunk overlaps the kernels of the
+ * next.  chunk_cols: 0 = automatic (default), < 0 = never chunk, > 0 = columns per chunk. */
+int bnk_ws_set_pipeline(bnk_ws *ws, int32_t chunk_cols);
 /* kernels launched by this workspace since creation (bench.py's gpu_launches) */
 int64_t bnk_ws_launch_count(const bnk_ws *ws);
 /* bytes of device memory currently held */
@@ -136,8 +154,10 @@ int bnk_probs(bnk_ws *ws, int32_t n_t, const double *t, double *P, double *logP)
 int bnk_joint(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
               uint8_t *out_state);
 /* query_nodes: n_query node indices, or NULL with n_query = -1 for every internal node in
- * index order.  out_post [n_query][n_cols][K] (NaN where the node has no posterior in that
- * column); out_logl [n_cols] = VarElim.logLikelihood() of the column; either may be NULL. */
+ * index order.  A node may be listed more than once; a childless node that is present but not instantiated
+ * (possible after orphan flooding, IdxTree.java:429-432) gets its distribution like any other variable.
+ * out_post [n_query][n_cols][K] (NaN where the node has no posterior in that column: absent, observed or
+ * unconnected); out_logl [n_cols] = VarElim.logLikelihood() of the column; either may be NULL. */
 int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
                  const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl);
 /* out_logl [n_cols] (may be NULL), *out_sum = sum over columns (may be NULL) */
@@ -156,6 +176,36 @@ int bnk_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uin
  * NCCL all-reduce of an optimisation loop) */
 int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,
                    double *d_out_logl, double *d_out_sum);
+
+/* ---- several devices in one process ------------------------------------------------------- */
+/* The reference spreads columns over a thread pool (ThreadedDecorators, src/asr/ThreadedDecorators.java:28-72,
+ * sized by GRASP.NTHREADS, src/asr/GRASP.java:35); bnk_mgpu spreads them over devices: contiguous blocks of
+ * ceil(n_cols / n_devices) columns, one workspace + streams + host thread per device, results written straight
+ * into the caller's rows (no gather).  devices_or_null: CUDA device ordinals (NULL: 0 .. n_devices-1;
+ * n_devices <= 0: every visible sm_100 device).  Same argument meaning as the single-device calls. */
+typedef struct bnk_mgpu bnk_mgpu;
+int bnk_mgpu_create(const bnk_model *m, const bnk_tree *t, int32_t max_cols, int n_devices,
+                    const int *devices_or_null, bnk_mgpu **out);
+void bnk_mgpu_destroy(bnk_mgpu *g);
+int bnk_mgpu_n_devices(const bnk_mgpu *g);
+/* the column block device idx receives for an alignment of n_cols columns */
+int bnk_mgpu_shard(const bnk_mgpu *g, int32_t n_cols, int idx, int32_t *col0, int32_t *ncols);
+int bnk_mgpu_set_rates(bnk_mgpu *g, int32_t n_cols, const double *rates_or_null);
+int bnk_mgpu_set_distances(bnk_mgpu *g, const double *dist);
+int bnk_mgpu_joint(bnk_mgpu *g, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
+                   uint8_t *out_state);
+int bnk_mgpu_marginal(bnk_mgpu *g, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
+                      const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl);
+int bnk_mgpu_loglik(bnk_mgpu *g, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
+                    double *out_logl, double *out_sum);
+/* Optimisation loops (the shape of IndelPeeler.optimiseMuLambda, src/asr/IndelPeeler.java:469-510: evaluate all
+ * columns, sum, iterate): upload the alignment once, then per evaluation change rates / distances and call
+ * bnk_mgpu_loglik_resident -- kernels on every device, then ONE all-reduce of the per-device sums
+ * (ncclAllReduce over NVLink when libnccl.so.2 can be loaded; bnk_mgpu_reduction() says which path ran). */
+int bnk_mgpu_upload(bnk_mgpu *g, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null);
+int bnk_mgpu_loglik_resident(bnk_mgpu *g, double *out_sum);
+const char *bnk_mgpu_reduction(const bnk_mgpu *g);
+int64_t bnk_mgpu_launch_count(const bnk_mgpu *g);
 
 /* ---- instrumentation ------------------------------------------------------------------ */
 /* CUDA-event time (ms) of the kernels of the most recent *_dev / host call, by phase:
