@@ -1,21 +1,26 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the GRASP per-column tree-inference path on B200.
 
-One step = one pass of the hot path over one batch of synthetic columns:
+One step = one pass of the hot path over the batch of synthetic columns:
     P(t)/log P(t) table build  +  joint reconstruction (max-product up-sweep + traceback)
     +  marginal reconstruction of ALL ancestors (sum-product up-sweep + down-sweep) + log-likelihoods
-on BASELINE.json configs[2] (C3a): 10,000-leaf balanced tree x 5,000 columns per GPU, LG + Gamma4
-(per-column category rates), FP64.  Metric = column x node partial updates / s, one update = one
-(column, internal node) message computation in one sweep: 3 sweeps per step.
+on BASELINE.json configs[2] (C3a): 10,000-leaf balanced tree x 5,000 columns, LG + Gamma4 (per-column category
+rates), FP64.  Metric = column x node partial updates / s, one update = one (column, internal node) message
+computation in one sweep: 3 sweeps per step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3a|c3b|small] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3a|c3b|c4|small] [--impl reference]
 
-N > 1 is launched by torchrun (one rank per GPU); columns are sharded, 5,000 per GPU (weak scaling),
-no data-path collective; the only collective is the barrier / max-reduce of the timing.
+N > 1 is launched by torchrun (one rank per GPU).  The FIXED problem is sharded: rank r owns a contiguous block
+of 5000 / N columns ("scaling": "strong"); no sweep contains a data-path collective.  The same JSON line
+carries sub-results measured the same way (barrier + CUDA events, max over ranks) for the other BASELINE
+configurations: C3b (caterpillar), C4 (100,000 leaves x 2,000 columns, WAG, sharded) and the C5 optimisation
+loop -- per evaluation a rate change, a table rebuild, a log-likelihood sweep and the NCCL all-reduce of the
+per-rank sums INSIDE the timed region, plus one gather of reconstructed states.
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -34,16 +39,25 @@ WORKLOADS = {
     "c3a": dict(tree="balanced", leaves=10000, cols=5000, model="LG", ncat=4, name="C3a balanced 10k-leaf x 5k-col LG+G4"),
     "c3b": dict(tree="caterpillar", leaves=10000, cols=5000, model="LG", ncat=4, name="C3b caterpillar 10k-leaf x 5k-col LG+G4"),
     "small": dict(tree="balanced", leaves=512, cols=1024, model="LG", ncat=4, name="small 512-leaf x 1024-col LG+G4"),
-    # BASELINE configs[3]: 100k-leaf random tree x 2k columns, WAG, one rate (use --no-e2e: 32 GB of posteriors)
+    # BASELINE configs[3]: 100k-leaf random tree x 2k columns, WAG, one rate
     "c4": dict(tree="random", leaves=100000, cols=2000, model="WAG", ncat=1, name="C4 random 100k-leaf x 2k-col WAG"),
-    # BASELINE configs[4]: repeated log-likelihood evaluations (rates perturbed every iteration => tables rebuilt)
-    # with an all-reduce of the per-GPU sum of column log-likelihoods
-    "c5": dict(tree="balanced", leaves=10000, cols=5000, model="LG", ncat=4, name="C5 logL loop on C3a, rates perturbed per evaluation, all-reduce of sum(logL)", loop=True),
 }
+CPU_SAMPLE_COLS = 256  # columns of the CPU arm's sample (64 per rate category): the same for cpu_baseline and --impl reference
 
 
-def make_workload(spec, rank, cols=None):
-    from bnkit_b200 import lib, synth
+def model_parts(name, impl):
+    """eigensystem / prior of the model for the alignment simulator: from the library in the B200 arm, from the
+    oracle in the reference arm (which must not map libbnkgpu.so at all)"""
+    if impl == "reference":
+        from oracle import oracle as O
+        return O.Model(name).parts()
+    from bnkit_b200 import lib
+    return lib.Model(name).parts()
+
+
+def make_workload(spec, rank=0, cols=None, impl="b200"):
+    """the FIXED problem of a workload (same on every rank): (model name, parent, dist, rates, obs [n][cols])"""
+    from bnkit_b200 import synth  # workload generator only (numpy)
     leaves = spec["leaves"]
     n_cols = cols or spec["cols"]
     if spec["tree"] == "balanced":
@@ -52,21 +66,23 @@ def make_workload(spec, rank, cols=None):
         parent, dist = synth.caterpillar_tree(leaves, seed=2)
     else:
         parent, dist = synth.random_tree(leaves, seed=5)
-    model = lib.Model(spec["model"])
+    parts = model_parts(spec["model"], impl)
+    K = len(parts["prior"])
     cat_rates = synth.gamma_category_rates(0.5, spec["ncat"]) if spec["ncat"] > 1 else np.ones(1)
-    rng = np.random.default_rng(4 + 1000 * rank)
+    rng = np.random.default_rng(4)
     rates = cat_rates[rng.integers(0, spec["ncat"], n_cols)]
     if leaves <= 20000:
-        obs = synth.simulate_alignment(parent, dist, model.parts(), n_cols, rates, seed=3 + 1000 * rank)
+        obs = synth.simulate_alignment(parent, dist, parts, n_cols, rates, seed=3)
     else:  # very large trees: a conserved base state per leaf with 20 % noise (numpy simulation would take minutes)
         leaf = np.ones(len(parent), dtype=bool)
         leaf[parent[parent >= 0]] = False
         nl = int(leaf.sum())
-        base = rng.integers(0, model.K, (nl, 1)).astype(np.uint8)
-        noise = rng.integers(0, model.K, (nl, n_cols)).astype(np.uint8)
+        base = rng.integers(0, K, (nl, 1)).astype(np.uint8)
+        noise = rng.integers(0, K, (nl, n_cols)).astype(np.uint8)
         obs = np.full((len(parent), n_cols), 255, dtype=np.uint8)
         obs[leaf] = np.where(rng.random((nl, n_cols)) < 0.2, noise, base)
-    return model, parent, dist, rates, obs
+    del rank
+    return spec["model"], parent, dist, rates, obs
 
 
 class ClockSampler(threading.Thread):
@@ -101,53 +117,47 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(spec, model_name, parent, dist, rates, obs, budget_s, threads):
-    """Times the CPU restatement (oracle/) on a bounded column sample; returns (updates/s, sample text)."""
+def n_internal(parent):
+    return int((np.bincount(parent[parent >= 0], minlength=len(parent)) > 0).sum())
+
+
+def sample_columns(rates, per_cat, seed=0):
+    rng = np.random.default_rng(seed)
+    sel = []
+    for r in np.unique(rates):
+        idx = np.nonzero(rates == r)[0]
+        sel.extend(rng.choice(idx, size=min(per_cat, len(idx)), replace=False).tolist())
+    return np.array(sorted(sel), dtype=np.int64)
+
+
+def cpu_oracle_rate(model_name, parent, dist, rates, obs, threads, n_sample=CPU_SAMPLE_COLS):
+    """Times the CPU restatement (oracle/) on a fixed column sample; returns (updates/s, sample text, seconds)."""
     from oracle import oracle as O
     O.build()
     om = O.Model(model_name)
-    n_int = int((np.bincount(parent[parent >= 0], minlength=len(parent)) > 0).sum())
-    def run(nc):
-        o = np.ascontiguousarray(obs[:, :nc])
-        r = np.ascontiguousarray(rates[:nc])
-        t0 = time.perf_counter()
-        O.fast_joint(om, parent, dist, o, None, r, nthreads=threads)
-        O.fast_marginal(om, parent, dist, o, None, r, nthreads=threads, want_post=True)
-        return time.perf_counter() - t0
-    nc = min(obs.shape[1], threads)
-    run(nc)                       # warm (page in the library)
-    t = run(nc)
-    for _ in range(4):            # grow the sample until it costs about budget_s (the per-rate table build is a fixed cost)
-        if t >= 0.7 * budget_s or nc >= obs.shape[1]:
-            break
-        grow = min(4.0, max(1.5, budget_s / max(t, 1e-3)))
-        nc = min(obs.shape[1], max(nc + threads, int(nc * grow) // threads * threads))
-        t = run(nc)
-    return 3.0 * n_int * nc / t, "%d of %d columns, all %d nodes, joint + marginal(all ancestors), %d threads, %.1f s" % (
-        nc, obs.shape[1], len(parent), threads, t), t
+    sel = sample_columns(rates, max(1, n_sample // max(1, len(np.unique(rates)))))
+    o = np.ascontiguousarray(obs[:, sel])
+    r = np.ascontiguousarray(rates[sel])
+    t0 = time.perf_counter()
+    O.fast_joint(om, parent, dist, o, None, r, nthreads=threads)
+    O.fast_marginal(om, parent, dist, o, None, r, nthreads=threads, want_post=True)
+    t = time.perf_counter() - t0
+    nc = len(sel)
+    return 3.0 * n_internal(parent) * nc / t, "%d of %d columns (%d per rate category), all %d nodes, joint + marginal(all ancestors), %d threads, %.1f s" % (
+        nc, obs.shape[1], nc // max(1, len(np.unique(rates))), len(parent), threads, t), t
 
 
-def bind_to_gpu_numa_node(local_rank):
-    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so that the 8 GB result
-    copies of several ranks do not cross sockets.  Best effort: any missing piece leaves the affinity untouched."""
+def java_probe():
+    """BASELINE.md section 3 asks for bnkit's own JVM path when a JDK exists on the box: probe and say so."""
+    exe = shutil.which("java")
+    if not exe:
+        return "absent (no `java` on PATH): the CPU arm is the C restatement of the reference's algorithm (kind: port)"
     try:
-        import torch
-        pr = torch.cuda.get_device_properties(local_rank)
-        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        out = subprocess.run([exe, "-version"], capture_output=True, text=True, timeout=20)
+        return "present (%s) but /root/reference is not on the GPU box and no bnkit.jar ships: CPU arm stays the port" % (
+            (out.stderr or out.stdout).strip().splitlines()[0])
+    except Exception as e:  # pragma: no cover
+        return "probe failed: %r" % (e,)
 
 
 def host_memory_available():
@@ -169,6 +179,111 @@ def host_memory_available():
     return avail if avail is not None else 1 << 62
 
 
+class Shard:
+    """One rank's device-resident share of a workload: workspace + buffers for its column block."""
+
+    def __init__(self, lib, torch, spec, model_name, parent, dist, rates, obs, world, rank, local_rank, weak_cols=0,
+                 want_post=True, present=None):
+        from bnkit_b200 import dist as bd
+        self.lib, self.torch = lib, torch
+        self.dev = torch.device("cuda", local_rank)
+        self.model = lib.Model(model_name)
+        self.tree = lib.Tree(parent, dist)
+        self.n, self.n_int, self.K = self.tree.n, self.tree.n_internal, self.model.K
+        self.total_cols = obs.shape[1]
+        if weak_cols:  # the old weak-scaling layout: every rank runs the whole problem
+            self.lo, self.hi = 0, self.total_cols
+        else:
+            self.lo, self.hi = bd.shard_columns(self.total_cols, world, rank)
+        self.ncols = self.hi - self.lo
+        self.dist0 = np.ascontiguousarray(dist, dtype=np.float64)
+        self.rates = np.ascontiguousarray(rates[self.lo:self.hi])
+        self.obs_local = np.ascontiguousarray(obs[:, self.lo:self.hi])
+        self.present_local = None if present is None else np.ascontiguousarray(present[:, self.lo:self.hi])
+        nc = max(self.ncols, 1)
+        self.ws = lib.Workspace(self.model, self.tree, nc, device=local_rank, stream=torch.cuda.current_stream().cuda_stream)
+        # GRASP instantiates extants only (POGTree.getNodeInstance): the resident loop asserts it instead of
+        # paying a scan + host round trip per call; the host-buffer (e2e) calls below run with AUTO
+        self.ws.set_evidence_mode(lib.EVIDENCE_LEAVES)
+        self.ws.set_rates(nc, self.rates if self.ncols else None)
+        self.d_obs = torch.from_numpy(self.obs_local if self.ncols else np.full((self.n, 1), 255, np.uint8)).to(self.dev)
+        self.d_present = None if self.present_local is None else torch.from_numpy(self.present_local).to(self.dev)
+        self.d_state = torch.empty((self.n, nc), dtype=torch.uint8, device=self.dev)
+        self.d_post = torch.empty((self.n_int if want_post else 1, nc, self.K), dtype=torch.float64, device=self.dev)
+        self.d_logl = torch.empty((nc,), dtype=torch.float64, device=self.dev)
+        self.d_sum = torch.zeros((1,), dtype=torch.float64, device=self.dev)
+
+    def step(self):
+        """tables (marked stale by the distance upload, as in an optimisation step) + joint + marginal"""
+        if self.ncols == 0:
+            return
+        self.ws.set_distances(self.dist0)
+        self.ws.joint_dev(self.ncols, self.d_obs, self.d_present, self.d_state)
+        self.ws.marginal_dev(self.ncols, self.d_obs, self.d_present, self.d_post, self.d_logl)
+
+    def close(self):
+        self.ws.close()
+        for k in ("d_obs", "d_present", "d_state", "d_post", "d_logl", "d_sum"):
+            setattr(self, k, None)
+        self.torch.cuda.empty_cache()
+
+
+def timed_steps(torch, dist_, world, fn, warmup, steps, after_step=None):
+    """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events on the launching
+    stream; returns this rank's milliseconds (the caller takes the max over ranks)"""
+    def barrier():
+        if world > 1:
+            dist_.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+        if after_step:
+            after_step()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def max_over_ranks(torch, dist_, world, dev, values):
+    if world == 1:
+        return [float(v) for v in values]
+    t = torch.tensor(list(values), dtype=torch.float64, device=dev)
+    dist_.all_reduce(t, op=dist_.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def parity_sample(torch, shard, model_name, parent, dist, per_cat, query=None):
+    """compare a column sample of the rank's own device buffers (as the timed loop left them) with the oracle"""
+    from oracle import oracle as O
+    O.build()
+    om = O.Model(model_name)
+    sel = sample_columns(shard.rates, per_cat)
+    tsel = torch.from_numpy(sel).to(shard.dev)
+    st = shard.d_state[:, tsel].cpu().numpy()
+    post = shard.d_post[:, tsel, :].cpu().numpy()
+    logl = shard.d_logl[tsel].cpu().numpy()
+    o = np.ascontiguousarray(shard.obs_local[:, sel])
+    p = None if shard.present_local is None else np.ascontiguousarray(shard.present_local[:, sel])
+    r = np.ascontiguousarray(shard.rates[sel])
+    threads = os.cpu_count() or 1
+    want = O.fast_joint(om, parent, dist, o, p, r, nthreads=threads)
+    wpost, wlogl = O.fast_marginal(om, parent, dist, o, p, r, nthreads=threads)
+    internal = shard.tree.internal_nodes()
+    wp = wpost[internal if query is None else query]
+    nan_same = bool(np.array_equal(np.isnan(post), np.isnan(wp)))
+    ok = ~np.isnan(wp) & (np.abs(wp) >= 1e-300) & ~np.isnan(post)
+    rel = float((np.abs(post[ok] - wp[ok]) / np.abs(wp[ok])).max()) if ok.any() else 0.0
+    lrel = float((np.abs(logl - wlogl) / np.abs(wlogl)).max())
+    return {"cols": int(len(sel)), "nodes": int(len(parent)), "joint_equal": bool(np.array_equal(st, want)),
+            "joint_mismatches": int((st != want).sum()), "post_nan_pattern_equal": nan_same,
+            "post_max_rel": rel, "logl_max_rel": lrel, "against": "oracle/ (C restatement of VarElim), same inputs"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,13 +291,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3a", choices=sorted(WORKLOADS))
-    ap.add_argument("--cols", type=int, default=0, help="columns per GPU (default: the workload's)")
+    ap.add_argument("--cols", type=int, default=0, help="columns of the problem (default: the workload's)")
+    ap.add_argument("--weak", action="store_true", help="every rank runs the whole problem (r1's weak-scaling layout)")
     ap.add_argument("--tile-cols", type=int, default=0)
     ap.add_argument("--cpt", type=int, default=0)
-    ap.add_argument("--gaps", type=float, default=0.0, help="gap fraction at the leaves; > 0 adds a per-column presence mask (general kernels)")
+    ap.add_argument("--gaps", type=float, default=0.0, help="gap fraction at the leaves; > 0 adds the BEP presence mask (general kernels)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-sub", action="store_true", help="skip the C3b / C4 / C5 sub-results")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sub", default="c3b,c4,c5", help="which sub-results to run")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: libraries that write to file descriptor 1 on their own (NCCL prints
@@ -203,32 +321,33 @@ def main():
     spec = WORKLOADS[args.workload]
     n_cols = args.cols or spec["cols"]
     threads = os.cpu_count() or 1
-    config = {"workload": spec["name"], "tree": spec["tree"], "leaves": spec["leaves"], "cols_per_gpu": n_cols,
+    config = {"workload": spec["name"], "tree": spec["tree"], "leaves": spec["leaves"], "cols": n_cols,
               "model": spec["model"] + "+G%d" % spec["ncat"], "passes": "tables + joint(up+traceback) + marginal(up+down, all ancestors)",
-              "sharding": "columns, %d per GPU" % n_cols,
+              "sharding": ("every rank runs all %d columns" % n_cols) if args.weak else
+                          "the fixed %d columns in contiguous blocks of %d / N per GPU; no data-path collective in a sweep" % (n_cols, n_cols),
               "schedule": "wide height levels as level launches (one column per thread, messages through HBM) + column-owned walker for the narrow top",
               "l2": "per-step working set (messages 8 GB + posteriors 8 GB + pointers 2 GB at C3) >> 126 MB L2; no flush needed"}
+    scaling = "weak" if args.weak else "strong"
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        from bnkit_b200 import synth  # workload generator only (numpy)
-        model, parent, dist, rates, obs = make_workload(spec, 0, min(n_cols, 4 * threads * 8))
-        per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+        model_name, parent, dist, rates, obs = make_workload(spec, 0, n_cols, impl="reference")
         vals, sample = [], ""
         for i in range(args.warmup + args.steps):
-            v, sample, _ = cpu_oracle_rate(spec, spec["model"], parent, dist, rates, obs, per_step, threads)
+            v, sample, _ = cpu_oracle_rate(model_name, parent, dist, rates, obs, threads)
             if i >= args.warmup:
                 vals.append(v)
         value = float(np.mean(vals))
-        n_int = int((np.bincount(parent[parent >= 0], minlength=len(parent)) > 0).sum())
         line = {"impl": "reference", "metric": "column x node partial updates/s", "value": value, "unit": "updates/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * 3.0 * n_int * n_cols / value, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * 3.0 * n_internal(parent) * n_cols / value, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample,
-                                 "note": "C restatement of bnkit's VarElim path (oracle/); the JVM reference cannot run here (no JDK)"},
+                                 "note": "C restatement of bnkit's VarElim path (oracle/); every step times the SAME sample "
+                                         "as the B200 arm's cpu_baseline; ms_per_step = the whole workload at that rate",
+                                 "jvm": java_probe()},
                 "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return
@@ -237,139 +356,136 @@ def main():
     import torch
     import torch.distributed as dist_
     from bnkit_b200 import lib
+    from bnkit_b200 import dist as bd
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libbnkgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    model, parent, dist, rates, obs = make_workload(spec, rank, n_cols)
-    tree = lib.Tree(parent, dist)
-    n, n_int, K = tree.n, tree.n_internal, model.K
-    stream = torch.cuda.current_stream()
-    ws = lib.Workspace(model, tree, n_cols, device=local_rank, stream=stream.cuda_stream)
-    if args.tile_cols or args.cpt:
-        ws.configure(args.tile_cols, args.cpt)
-
-    d_present = None
-    if args.gaps > 0:  # per-column forests: gaps at the leaves, ancestors present on paths between present leaves
-        from bnkit_b200 import synth
-        g_rng = np.random.default_rng(77 + rank)
-        leaf = np.ones(n, dtype=bool)
+    model_name, parent, dist, rates, obs = make_workload(spec, rank, n_cols)
+    present = None
+    if args.gaps > 0:  # per-column forests: gaps at the leaves, presence mask from the device BEP + orphan pruning
+        g_rng = np.random.default_rng(77)
+        leaf = np.ones(len(parent), dtype=bool)
         leaf[parent[parent >= 0]] = False
         obs = obs.copy()
         obs[(g_rng.random(obs.shape) < args.gaps) & leaf[:, None]] = 255
-        present = synth.path_presence_mask(parent, (obs != 255) & leaf[:, None])
-        d_present = torch.from_numpy(present).to(dev)
+        t_ = lib.Tree(parent, dist)
+        present = t_.prune_orphans(t_.bep_presence(obs, device=local_rank))
         config["gaps"] = args.gaps
-        args.no_e2e = True
+        config["mask"] = "bnk_bep_presence (bi-directional edge parsimony) + bnk_tree_prune_orphans"
         args.no_cpu = True
-    d_obs = torch.from_numpy(obs).to(dev)
-    d_state = torch.empty((n, n_cols), dtype=torch.uint8, device=dev)
-    d_post = torch.empty((1 if spec.get("loop") else n_int, n_cols, K), dtype=torch.float64, device=dev)
-    d_logl = torch.empty((n_cols,), dtype=torch.float64, device=dev)
+    sh = Shard(lib, torch, spec, model_name, parent, dist, rates, obs, world, rank, local_rank, weak_cols=args.weak,
+               present=present)
+    if args.tile_cols or args.cpt:
+        sh.ws.configure(args.tile_cols, args.cpt)
+    n, n_int, K = sh.n, sh.n_int, sh.K
 
-    loop_mode = bool(spec.get("loop"))
-    d_sum = torch.zeros((1,), dtype=torch.float64, device=dev)
-    it_count = [0]
+    phase_ms = np.zeros(5)
 
-    def step_resident():
-        if loop_mode:  # one log-likelihood evaluation of an optimisation loop
-            it_count[0] += 1
-            ws.set_rates(n_cols, rates * (1.0 + 0.01 * (it_count[0] % 7)))
-            ws.loglik_dev(n_cols, d_obs, None, d_logl, d_sum)
-            if world > 1:
-                dist_.all_reduce(d_sum, op=dist_.ReduceOp.SUM)  # the only data-path collective: one double
-            return
-        ws.set_rates(n_cols, rates)  # marks the tables dirty: every step rebuilds P(t) / log P(t)
-        ws.joint_dev(n_cols, d_obs, d_present, d_state)
-        ws.marginal_dev(n_cols, d_obs, d_present, d_post, d_logl)
-
-    def barrier():
-        if world > 1:
-            dist_.barrier()
-        torch.cuda.synchronize()
+    def collect_phases():
+        sh.ws.sync()
+        phase_ms[:] += [sh.ws.phase_ms(i) for i in range(5)]
 
     for _ in range(args.warmup):
-        step_resident()
-    barrier()
+        sh.step()
+    if world > 1:
+        dist_.barrier()
+    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    phase_ms = np.zeros(5)
-    launches0 = ws.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-        ws.sync()
-        phase_ms += [ws.phase_ms(i) for i in range(5)]
-    e1.record()
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    launches = ws.launch_count() - launches0
+    launches0 = sh.ws.launch_count()
+    total_ms = timed_steps(torch, dist_, world, sh.step, 0, args.steps, after_step=collect_phases)
+    launches = sh.ws.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     phase_ms /= args.steps
 
+    # ---- parity of what the timed loop left in the device buffers (rank 0's block)
+    parity = None
+    if rank == 0 and not args.no_parity and sh.ncols > 0:
+        parity = parity_sample(torch, sh, model_name, parent, dist, 16)
+
     # ---- end to end through the host-buffer ABI (pinned host memory, copies inside the timed region)
     e2e = None
-    if loop_mode:
-        args.no_e2e = True
-        args.no_cpu = True
-    e2e_cols = n_cols
-    if not args.no_e2e:
-        # The leg pins n_int x n_cols x K doubles of host memory per rank (8 GB at C3).  On a box whose host memory
-        # (or cgroup limit) cannot hold that for every local rank, the leg runs on a column prefix instead and says
-        # so: the rate is D2H-bound per column either way.  Rank 0 decides for everybody.
-        need = n_int * n_cols * K * 8 + 3 * n * n_cols
+    if not args.no_e2e and sh.ncols > 0:
+        nc = sh.ncols
+        # the leg pins n_int x ncols x K doubles of host memory per rank (8 GB / N at C3); if the box (or its cgroup)
+        # cannot hold that, the leg runs on a column prefix and says so
+        need = n_int * nc * K * 8 + 3 * n * nc
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        avail = host_memory_available()
-        budget = 0.5 * avail / max(local_world, 1)
-        if need > budget:
-            e2e_cols = max(64, min(n_cols, int(n_cols * budget / need)))
+        budget = 0.5 * host_memory_available() / max(local_world, 1)
+        e_cols = nc if need <= budget else max(64, int(nc * budget / need))
         if os.environ.get("BNK_BENCH_E2E_COLS"):
-            e2e_cols = min(n_cols, int(os.environ["BNK_BENCH_E2E_COLS"]))
+            e_cols = min(nc, int(os.environ["BNK_BENCH_E2E_COLS"]))
         if world > 1:
-            tcols = torch.tensor([e2e_cols], dtype=torch.int64, device=dev)
-            dist_.broadcast(tcols, src=0)
-            e2e_cols = int(tcols[0])
-        e_obs = obs if e2e_cols == n_cols else np.ascontiguousarray(obs[:, :e2e_cols])
-        e_rates = rates if (rates is None or e2e_cols == n_cols) else np.ascontiguousarray(rates[:e2e_cols])
+            tcols = torch.tensor([e_cols], dtype=torch.int64, device=dev)
+            dist_.all_reduce(tcols, op=dist_.ReduceOp.MIN)
+            e_cols = int(tcols[0])
+        e_obs = sh.obs_local if e_cols == nc else np.ascontiguousarray(sh.obs_local[:, :e_cols])
+        e_pres = None if sh.present_local is None else np.ascontiguousarray(sh.present_local[:, :e_cols])
+        e_rates = np.ascontiguousarray(sh.rates[:e_cols])
         h_obs = torch.from_numpy(e_obs).pin_memory()
-        h_state = torch.empty((n, e2e_cols), dtype=torch.uint8).pin_memory()
-        h_post = torch.empty((n_int, e2e_cols, K), dtype=torch.float64).pin_memory()
-        h_logl = np.empty(e2e_cols)
-        def step_e2e():
-            ws.set_rates(e2e_cols, e_rates)
-            lib.check(lib.lib().bnk_joint(ws.h, e2e_cols, h_obs.data_ptr(), None, h_state.data_ptr()))
-            lib.check(lib.lib().bnk_marginal(ws.h, e2e_cols, h_obs.data_ptr(), None, None, -1, h_post.data_ptr(),
-                                             h_logl.ctypes.data))
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        k_e2e = max(1, min(args.steps, 3))
-        for _ in range(k_e2e):
-            step_e2e()
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
-        h2d = 2 * n * e2e_cols
-        d2h = n * e2e_cols + n_int * e2e_cols * K * 8 + e2e_cols * 8
-        # parity of what came back (cheap invariants): posteriors sum to 1, states in range
-        assert abs(float(h_post[0, 0].sum()) - 1.0) < 1e-9 and int(h_state.max()) < K
-    # ---- max over ranks
-    tmax, e2emax = total_ms, (e2e_ms if not args.no_e2e else 0.0)
-    if world > 1:
-        tt = torch.tensor([total_ms, e2emax], dtype=torch.float64, device=dev)
-        dist_.all_reduce(tt, op=dist_.ReduceOp.MAX)
-        tmax, e2emax = float(tt[0]), float(tt[1])
-    if rank != 0:
-        if world > 1:
-            dist_.destroy_process_group()
-        return
+        h_pres = None if e_pres is None else torch.from_numpy(e_pres).pin_memory()
+        h_state = torch.empty((n, e_cols), dtype=torch.uint8).pin_memory()
+        h_post = torch.empty((n_int, e_cols, K), dtype=torch.float64).pin_memory()
+        h_one = torch.empty((1, e_cols, K), dtype=torch.float64).pin_memory()
+        h_logl = torch.empty((e_cols,), dtype=torch.float64).pin_memory()
+        ws2 = lib.Workspace(sh.model, sh.tree, e_cols, device=local_rank)   # AUTO evidence mode, private stream, pipelined
+        L = lib.lib()
+        one_q = np.array([int(sh.tree.internal_nodes()[n_int // 2])], dtype=np.int32)
+        pp = None if h_pres is None else h_pres.data_ptr()
 
-    updates_step = (1.0 if loop_mode else 3.0) * n_int * n_cols * world
+        def e_joint():
+            ws2.set_distances(sh.dist0)
+            ws2.set_rates(e_cols, e_rates)
+            lib.check(L.bnk_joint(ws2.h, e_cols, h_obs.data_ptr(), pp, h_state.data_ptr()))
+
+        def e_marg():
+            ws2.set_distances(sh.dist0)
+            lib.check(L.bnk_marginal(ws2.h, e_cols, h_obs.data_ptr(), pp, None, -1, h_post.data_ptr(), h_logl.data_ptr()))
+
+        def e_one():  # what a GRASP `-m N<k>` call costs: Prediction.getMarginal returns ONE ancestor (Prediction.java:555-597)
+            ws2.set_distances(sh.dist0)
+            lib.check(L.bnk_marginal(ws2.h, e_cols, h_obs.data_ptr(), pp, lib._i(one_q), 1, h_one.data_ptr(), h_logl.data_ptr()))
+
+        def wall(fn, reps):
+            fn()
+            if world > 1:
+                dist_.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist_.barrier()
+            return (time.perf_counter() - t0) * 1e3 / reps
+        k_e2e = max(1, min(args.steps, 3))
+        j_ms, m_ms, o_ms = wall(e_joint, k_e2e), wall(e_marg, k_e2e), wall(e_one, k_e2e)
+        # the box's pinned device->host rate, every rank copying at once (the ceiling of the marginal leg)
+        d_tmp = sh.d_post.view(-1)[: min(sh.d_post.numel(), h_post.numel(), 1 << 27)]
+        h_tmp = h_post.view(-1)[: d_tmp.numel()]
+
+        def d2h():
+            h_tmp.copy_(d_tmp, non_blocking=True)
+        d2h_ms = wall(d2h, 3)
+        d2h_gbs = d_tmp.numel() * 8 / 1e9 / (d2h_ms * 1e-3)
+        if present is None:  # cheap invariants of what came back: posteriors sum to 1, states in range
+            assert abs(float(h_post[0, 0].sum()) - 1.0) < 1e-9 and int(h_state.max()) < K
+        e2e = dict(cols=e_cols, joint_ms=j_ms, marginal_ms=m_ms, one_ancestor_ms=o_ms, d2h_gbs=d2h_gbs,
+                   h2d=n * e_cols * (2 if present is not None else 1),
+                   d2h=n * e_cols + n_int * e_cols * K * 8 + e_cols * 8, need=need, launches=ws2.launch_count())
+        ws2.close()
+        del h_post, h_state, h_obs
+    # ---- max over ranks
+    e_vals = [e2e["joint_ms"], e2e["marginal_ms"], e2e["one_ancestor_ms"], -e2e["d2h_gbs"]] if e2e else [0.0, 0.0, 0.0, 0.0]
+    tmax, ej, em, eo, ed = max_over_ranks(torch, dist_, world, dev, [total_ms] + e_vals)
+
+    main_cols = n_cols * (world if args.weak else 1)
+    updates_step = 3.0 * n_int * main_cols
     ms_per_step = tmax / args.steps
     value = updates_step / (ms_per_step * 1e-3)
     peaks = {}
@@ -379,7 +495,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    upd = float(n_int) * n_cols
+    upd = float(n_int) * sh.ncols   # rank 0's block: the kernels whose phase times are reported
     tbl = TABLE_BYTES * (n - 1) * spec["ncat"]
     kern = {"joint_up+traceback": (phase_ms[1] + phase_ms[2], BYTES_PER_UPDATE["joint_up+traceback"] * upd + tbl),
             "sum_up": (phase_ms[3], BYTES_PER_UPDATE["sum_up"] * upd + tbl),
@@ -389,38 +505,132 @@ def main():
                       "achieved_GBps": round(v[1] / 1e9 / (v[0] * 1e-3), 1) if v[0] > 0 else None,
                       "frac": round(v[1] / 1e9 / (v[0] * 1e-3) / peak, 4) if v[0] > 0 else None} for k, v in kern.items()}
     achieved = kern[dom][1] / 1e9 / (kern[dom][0] * 1e-3)
-    traffic = None  # DRAM bytes of the dominant sweep per step, from the committed ncu capture of this workload
+    traffic, traffic_src = None, None  # DRAM bytes of the dominant sweep per step, from this round's committed ncu capture
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        if tr.get("workload") == args.workload and n_cols == spec["cols"]:
+        if tr.get("workload") == args.workload and sh.ncols == spec["cols"] and present is None:
             traffic = tr["bytes_per_step"].get(dom)
+            traffic_src = tr.get("source")
     except Exception:
         pass
+
     line = {"metric": "column x node partial updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "gpu_launches": int(launches),
+            "cols_per_gpu": sh.ncols,
             "phase_ms": {"tables": round(float(phase_ms[0]), 4), "joint_up": round(float(phase_ms[1]), 4),
                          "traceback": round(float(phase_ms[2]), 4), "sum_up": round(float(phase_ms[3]), 4),
-                         "sum_down": round(float(phase_ms[4]), 4)},
+                         "sum_down": round(float(phase_ms[4]), 4), "of": "rank 0's block of %d columns" % sh.ncols},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "traffic_note": "DRAM bytes per step of the dominant sweep (all its launches), profiles/roofline_traffic.json",
+                         "traffic_note": "DRAM bytes per step of the dominant sweep (all its launches): " + str(traffic_src),
                          "algorithmic_bytes": "SURVEY.md 8(d) per-update figures x %d updates + table bytes" % int(upd),
                          "per_kernel": per_kernel},
             "clocks": clocks}
-    if not args.no_e2e:
-        line["e2e"] = {"value": updates_step * (e2e_cols / n_cols) / (e2emax * 1e-3), "unit": "updates/s", "ms_per_step": e2emax,
-                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
-        if numa_node is not None:
-            line["e2e"]["numa"] = "ranks bound to their GPU's NUMA node"
-        if e2e_cols != n_cols:
+    if parity is not None:
+        line["parity"] = parity
+    if e2e:
+        scale = e2e["cols"] / max(sh.ncols, 1)
+        both = ej + em
+        line["e2e"] = {"value": updates_step * scale / (both * 1e-3), "unit": "updates/s", "ms_per_step": both,
+                       "h2d_bytes_per_step": int(2 * e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                       "api": "bnk_joint + bnk_marginal (all ancestors) with pinned host buffers; each call runs column chunks "
+                              "through two internal workspaces so copies overlap kernels",
+                       "per_pass": {"joint": {"ms": ej, "updates_per_s": n_int * main_cols * scale / (ej * 1e-3),
+                                              "d2h_bytes": int(n * e2e["cols"])},
+                                    "marginal_all_ancestors": {"ms": em, "updates_per_s": 2.0 * n_int * main_cols * scale / (em * 1e-3),
+                                                               "d2h_bytes": int(n_int * e2e["cols"] * K * 8)},
+                                    "marginal_one_ancestor": {"ms": eo, "note": "Prediction.getMarginal(N<k>): one posterior row out"}},
+                       "pinned_d2h_GBps_per_gpu_all_ranks_copying": -ed,
+                       "marginal_floor_ms_at_that_rate": n_int * e2e["cols"] * K * 8 / 1e9 / (-ed) * 1e3,
+                       "gpu_launches_e2e_leg": int(e2e["launches"])}
+        if e2e["cols"] != sh.ncols:
             line["e2e"]["note"] = ("host memory limit: this leg ran on the first %d of %d columns per GPU "
-                                   "(it pins %.1f GB per rank at full width)" % (e2e_cols, n_cols, need / 1e9))
-    if world == 1 and not args.no_cpu:
-        v, sample, _ = cpu_oracle_rate(spec, spec["model"], parent, dist, rates, obs, args.cpu_budget, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample}
+                                   "(it pins %.1f GB per rank at full width)" % (e2e["cols"], sh.ncols, e2e["need"] / 1e9))
+    sh.close()
+
+    # ------------------------------------------------------------------ sub-results: the other BASELINE configurations
+    subs = {}
+    want_sub = [] if (args.no_sub or args.workload != "c3a" or args.weak or args.gaps > 0) else [s for s in args.sub.split(",") if s]
+    sub_steps, sub_warm = max(3, min(args.steps, 5)), 3
+    for name in want_sub:
+        if name in ("c3b", "c4"):
+            sspec = WORKLOADS[name]
+            mname, sp, sd, sr, so = make_workload(sspec, rank)
+            s2 = Shard(lib, torch, sspec, mname, sp, sd, sr, so, world, rank, local_rank)
+            ph = np.zeros(5)
+
+            def coll():
+                s2.ws.sync()
+                ph[:] += [s2.ws.phase_ms(i) for i in range(5)]
+            ms = timed_steps(torch, dist_, world, s2.step, sub_warm, sub_steps, after_step=coll)
+            par = None
+            if rank == 0 and not args.no_parity and s2.ncols > 0:
+                par = parity_sample(torch, s2, mname, sp, sd, 8 if name == "c3b" else 6)
+            (ms,) = max_over_ranks(torch, dist_, world, dev, [ms])
+            ni = s2.n_int
+            u = 3.0 * ni * sspec["cols"]
+            ph /= sub_steps
+            tb = TABLE_BYTES * (s2.n - 1) * sspec["ncat"]
+            algo = sum(BYTES_PER_UPDATE.values()) * ni * s2.ncols + 3 * tb
+            subs[name] = {"workload": sspec["name"], "cols_per_gpu": s2.ncols, "steps": sub_steps, "warmup": sub_warm,
+                          "ms_per_step": ms / sub_steps, "updates_per_s": u / (ms / sub_steps * 1e-3),
+                          "phase_ms": {"tables": round(float(ph[0]), 4), "joint_up": round(float(ph[1]), 4),
+                                       "traceback": round(float(ph[2]), 4), "sum_up": round(float(ph[3]), 4),
+                                       "sum_down": round(float(ph[4]), 4)},
+                          "roofline_frac_step_rank0": algo / 1e9 / (float(ph.sum()) * 1e-3) / peak if ph.sum() > 0 else None,
+                          "parity": par}
+            s2.close()
+            del s2, so
+        elif name == "c5":
+            # the optimisation loop on C3a: per evaluation new rates (tables rebuilt), a log-likelihood sweep of the
+            # rank's block, and the all-reduce of the per-rank sums -- all inside the timed region
+            mname, sp, sd, sr, so = model_name, parent, dist, rates, obs
+            s5 = Shard(lib, torch, spec, mname, sp, sd, sr, so, world, rank, local_rank, want_post=False)
+            run = bd.ShardedRun(s5.ws, s5.total_cols, sr, s5.d_obs, None, s5.d_state, s5.d_logl, s5.d_sum)
+            it = [0]
+            sums = []
+
+            def evaluate():
+                it[0] += 1
+                run.evaluate(rate_scale=1.0 + 0.01 * (it[0] % 7))
+            evals = max(10, args.steps)
+            ms = timed_steps(torch, dist_, world, evaluate, 3, evals)
+            # the value the all-reduce carries, against the oracle on a sample of the rank's block is covered by
+            # tests/test_gpu_golden.py::test_c5_likelihood_loop_matches_oracle; here: every rank holds the same sum
+            total = float(run.sum.cpu()[0])
+            sums.append(total)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist_.barrier()
+            torch.cuda.synchronize()
+            g0.record()
+            full = run.joint_and_gather(dst=0)
+            g1.record()
+            torch.cuda.synchronize()
+            gather_ms = g0.elapsed_time(g1)
+            ok_shape = (full is None) or (tuple(full.shape) == (s5.n, s5.total_cols))
+            ms, gather_ms = max_over_ranks(torch, dist_, world, dev, [ms, gather_ms])
+            same = max_over_ranks(torch, dist_, world, dev, [total, -total])
+            subs["c5"] = {"workload": "C5 optimisation loop on C3a: rates perturbed per evaluation (tables rebuilt), logL sweep, "
+                                      "all-reduce(sum) of the per-rank sums inside the timed region",
+                          "cols_per_gpu": s5.ncols, "evaluations": evals, "ms_per_evaluation": ms / evals,
+                          "updates_per_s": float(s5.n_int) * s5.total_cols / (ms / evals * 1e-3),
+                          "collective": ("torch.distributed all_reduce (NCCL) of 1 x f64 per evaluation" if world > 1 else "none (one rank)"),
+                          "sum_logl": total, "all_ranks_hold_the_same_sum": bool(same[0] == -same[1]),
+                          "joint_plus_state_gather_ms": gather_ms,
+                          "gathered_shape_ok": bool(ok_shape)}
+            s5.close()
+            del s5
+
     if rank == 0:
+        if subs:
+            line["sub_results"] = subs
+        if world == 1 and not args.no_cpu:
+            v, sample, _ = cpu_oracle_rate(model_name, parent, dist, rates, obs, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample,
+                                    "jvm": java_probe()}
         emit(line)
     if world > 1:
         dist_.destroy_process_group()

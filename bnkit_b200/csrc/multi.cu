@@ -178,9 +178,10 @@ struct bnk_mgpu {
 
 static void shard_of(int n_dev, int32_t n_cols, int idx, int32_t &c0, int32_t &nc)
 {
-    const int32_t per = (n_cols + n_dev - 1) / n_dev;  // contiguous blocks of ceil(C / G) columns
-    c0 = std::min<int64_t>((int64_t)per * idx, n_cols);
-    nc = std::min<int32_t>(per, n_cols - c0);
+    // contiguous blocks whose sizes differ by at most one column (bnkit_b200/dist.py: shard_columns)
+    const int32_t base = n_cols / n_dev, rem = n_cols % n_dev;
+    c0 = idx * base + std::min(idx, rem);
+    nc = base + (idx < rem ? 1 : 0);
 }
 
 extern "C" int bnk_mgpu_create(const bnk_model *m, const bnk_tree *t, int32_t max_cols, int n_devices, const int *devices,

@@ -180,7 +180,7 @@ int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8
 /* ---- several devices in one process ------------------------------------------------------- */
 /* The reference spreads columns over a thread pool (ThreadedDecorators, src/asr/ThreadedDecorators.java:28-72,
  * sized by GRASP.NTHREADS, src/asr/GRASP.java:35); bnk_mgpu spreads them over devices: contiguous blocks of
- * ceil(n_cols / n_devices) columns, one workspace + streams + host thread per device, results written straight
+ * n_cols / n_devices columns (sizes differ by at most one), one workspace + streams + host thread per device, results written straight
  * into the caller's rows (no gather).  devices_or_null: CUDA device ordinals (NULL: 0 .. n_devices-1;
  * n_devices <= 0: every visible sm_100 device).  Same argument meaning as the single-device calls. */
 typedef struct bnk_mgpu bnk_mgpu;

@@ -244,3 +244,33 @@ def test_association_order_is_pinned_bitwise(oracle):
             assert vlm == lm[c], (seed, c, vlm, lm[c])
             checked += 1
     assert checked == 80
+
+
+@pytest.mark.parametrize("name", ["LG", "JTT", "WAG", "Dayhoff", "JC", "Yang"])
+def test_transition_probabilities_against_an_independent_matrix_exponential(oracle, bnk, name):
+    """The eigensolver of the oracle (oracle/bnk_oracle.c) and of the product's host set-up
+    (bnkit_b200/csrc/subst_eigen.inc) are the same EISPACK transliteration of Matrix.java, so comparing them with
+    each other pins nothing.  Independent check: P(t) = expm(R t) with scipy's Pade
+    scaling-and-squaring, for the rate matrix R both report, to 1e-12 absolute over four decades of t; and the
+    rate matrix itself against its definition (S.pi off the diagonal, zero row sums, one expected substitution
+    per unit time -- SubstModel.java:80-110, 192-219)."""
+    from scipy.linalg import expm
+    om = oracle.Model(name)
+    hm = bnk.Model(name)                     # host-side model set-up of the library (no GPU involved)
+    for parts in (om.parts(), hm.parts()):
+        R, F = parts["R"], parts["F"]
+        K = len(F)
+        assert np.allclose(R.sum(1), 0.0, atol=1e-13)
+        if name != "JC":   # JC.java builds its matrix un-normalised (rate 0.25 per pair: 0.75 substitutions per unit time)
+            assert np.isclose(-(np.diag(R) * F).sum(), 1.0, rtol=1e-12)
+        # detailed balance of a reversible model: pi_i R_ij = pi_j R_ji
+        if name in ("LG", "JTT", "WAG", "Dayhoff"):   # built from a symmetric S (Yang is given as a full Q)
+            piR = (F / F.sum())[:, None] * R
+            assert np.allclose(piR, piR.T, atol=1e-12)
+        ev, iev, lam = parts["evec"], parts["ievec"], parts["eval"]
+        assert np.allclose(ev @ iev, np.eye(K), atol=1e-10)
+        for t in (1e-5, 0.003, 0.01, 0.07, 0.22, 1.0, 3.7, 25.0):
+            want = expm(R * t)
+            got = np.abs((ev * np.exp(lam * t)[None, :]) @ iev)
+            assert np.abs(got - want).max() < 1e-12, (name, t)
+            assert np.abs(om.probs(t) - want).max() < 1e-12, (name, t)
