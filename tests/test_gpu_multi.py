@@ -56,7 +56,7 @@ def test_mgpu_matches_one_workspace_and_the_oracle(bnk, oracle):
         assert np.array_equal(np.nan_to_num(p), np.nan_to_num(p1)) and np.array_equal(l, l1)
         ll, total = g.loglik(obs, present)
         assert np.array_equal(ll, l1) and np.isclose(total, l1.sum(), rtol=1e-13)
-        q = np.array([0, 7, 3], dtype=np.int32)
+        q = tree.internal_nodes()[[0, 5, 2]].astype(np.int32)
         pq, _ = g.marginal(obs, present, query=q)
         ents = {int(v): i for i, v in enumerate(tree.internal_nodes())}
         for i, v in enumerate(q):
