@@ -14,6 +14,7 @@ UNITS = [
     ("sweeps.cu", []),
     ("sweeps_fast.cu", []),
     ("sweeps_warp.cu", []),
+    ("sweeps_lane.cu", []),
     ("wide.cu", []),
     ("wide_general.cu", []),
     ("cherry.cu", []),

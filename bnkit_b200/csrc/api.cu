@@ -132,7 +132,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_WALKER"))
-        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : 0);
+        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : 0));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
     if (const char *env = std::getenv("BNK_MMA_DOWN")) ws->mma_down = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_JOINT10")) ws->joint10 = std::atoi(env) != 0;
@@ -329,6 +329,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     ws->chunks.clear(); ws->wtiles.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
     ws->cgroups.clear(); ws->chunk_cgroups.clear(); ws->chunk_crecs.clear(); ws->ctiles.clear(); ws->chunk_ctiles.clear();
     ws->xtiles.clear(); ws->chunk_xtiles.clear();
+    ws->ltiles.clear(); ws->chunk_ltiles.clear();
     {   // warp-tiled walker geometry: W consumer warps of 6 x C columns per CTA.  Every CTA of the grid should be
         // resident at once (a walk is one long dependent chain per column), so prefer the tile width that fills
         // the SMs most evenly -- cost = rounds of CTAs per SM x columns per CTA -- and, for a given width, one
@@ -405,6 +406,18 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 }
             }
         }
+        const int l0 = (int)ws->ltiles.size();
+        {
+            const int lt = lane_walk_cols();
+            for (int k = lo; k < hi; k++) {
+                const int nc = cat_begin[k + 1] - cat_begin[k];
+                const int nt = (nc + lt - 1) / lt;
+                for (int q = 0; q < nt; q++) {
+                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+                    ws->ltiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+                }
+            }
+        }
         const int m0 = (int)ws->mtiles.size();
         {
             const int mt = std::abs(ws->mw) * mma_walk_cols_per_warp();
@@ -470,6 +483,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             ws->chunk_crecs.push_back(crecs);
             ws->chunk_ctiles.push_back({ct0, (int)ws->ctiles.size()});
             ws->chunk_xtiles.push_back({x0, (int)ws->xtiles.size()});
+            ws->chunk_ltiles.push_back({l0, (int)ws->ltiles.size()});
             ws->chunk_mtiles.push_back({m0, (int)ws->mtiles.size()});
             ws->chunk_jtiles.push_back({j0, (int)ws->jtiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
@@ -491,6 +505,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_cgroups, ws->cgroups, ws->stream));
     TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
     TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
+    TRY(upload(ws->d_ltiles, ws->ltiles, ws->stream));
     TRY(upload(ws->d_mtiles, ws->mtiles, ws->stream));
     TRY(upload(ws->d_jtiles, ws->jtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
@@ -621,6 +636,8 @@ struct WalkSetup {
     WalkLaunch wl;
     bool fast = false;    // lean kernels of sweeps_fast.cu apply
     bool hybrid = false;  // wide height levels run as level launches (wide.cu); the walker takes the narrow top
+    bool lane = false;    // fast, and the lane walker of sweeps_lane.cu takes the walk
+    int n_ltiles = 0;
     bool warp = false;    // fast, and the warp-tiled kernels of sweeps_warp.cu take the walk
     int xw = 0, xc = 0, xns = 0, n_xtiles = 0;
     bool mma = false;     // warp, and the sum-product sweeps run the DMMA variants
@@ -661,6 +678,27 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
     s.fast = false; s.hybrid = false;
     s.warp = false;
     s.mma = false;
+    s.lane = false;
+    if (!general && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode == 0) {
+        // lane walker: a thread owns a column, the outputs of a step are split over four warps
+        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
+        const int slots = use_program(hybrid);
+        if (lane_walk_smem_bytes(slots, want_down) <= (size_t)ws->smem_optin) {
+            s.fast = true; s.lane = true; s.hybrid = hybrid;
+            s.n_ltiles = ws->chunk_ltiles[ci].second - ws->chunk_ltiles[ci].first;
+            s.a.tiles = ws->d_ltiles.p + ws->chunk_ltiles[ci].first;
+            s.a.tile_base = ws->chunk_ltiles[ci].first;
+            s.a.tile_stride = (int32_t)ws->ltiles.size() * lane_walk_cols();
+            s.a.smem_slots = slots;
+            // the tiled copy of the observation matrix (childless children are looked up through it)
+            CUDA_TRY(ws->d_obs_t.ensure((size_t)ws->n * s.a.tile_stride));
+            CUDA_TRY(launch_tile_bytes(obs_s, ws->d_orig_col.p, ws->d_ltiles.p + ws->chunk_ltiles[ci].first, s.n_ltiles,
+                                       s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_obs_t.p, ws->stream));
+            ws->launches++;
+            s.a.obs_t = ws->d_obs_t.p;
+            return BNK_OK;
+        }
+    }
     if (!general && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode != 1) {
         const bool hybrid = t->wide_h > 0 && !ws->no_wide;
         const int slots = use_program(hybrid);
@@ -674,7 +712,7 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
             s.n_xtiles = ws->chunk_xtiles[ci].second - ws->chunk_xtiles[ci].first;
             s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
             s.a.smem_slots = slots;
-            if (ws->walker_mode == 0) {  // sum-product sweeps: the DMMA variants
+            if (ws->walker_mode == 0 || ws->walker_mode == 3) {  // sum-product sweeps: the DMMA variants
                 const int mw = std::abs(ws->mw);
                 int mns = ws->cfg_xns >= 2 && ws->cfg_xns <= 8 ? ws->cfg_xns : 8;
                 if (!(ws->cfg_xns >= 2 && ws->cfg_xns <= 8))
@@ -818,7 +856,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             }
             bool j10 = false;
             int jns = 8;
-            if (s.warp && ws->joint10 && ws->walker_mode == 0) {
+            if (s.warp && ws->joint10 && (ws->walker_mode == 0 || ws->walker_mode == 3)) {
                 const int jw = std::abs(ws->jw);
                 if (ws->cfg_xns >= 2 && ws->cfg_xns <= 8) jns = ws->cfg_xns;
                 else while (jns > 3 && joint10_smem_bytes(jw, jns, s.a.smem_slots) > (size_t)ws->smem_optin / 2 - 1024) jns--;
@@ -829,7 +867,8 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
                 ja.tiles = ws->d_jtiles.p + ws->chunk_jtiles[ci].first;
                 CUDA_TRY(launch_joint_up_10(ja, ws->chunk_jtiles[ci].second - ws->chunk_jtiles[ci].first, std::abs(ws->jw), jns, ws->stream));
             } else
-            CUDA_TRY(s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+            CUDA_TRY(s.lane ? launch_lane_up(0, s.a, s.n_ltiles, ws->stream)
+                     : s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                             : s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;
             CUDA_TRY(cudaEventRecord(ws->ev[1][1], ws->stream));
@@ -1003,7 +1042,8 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
             }
         }
         if (s.mma) s.a.tiles = s.mtiles;
-        CUDA_TRY(s.mma ? launch_sum_up_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
+        CUDA_TRY(s.lane ? launch_lane_up(1, s.a, s.n_ltiles, ws->stream)
+                 : s.mma ? launch_sum_up_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
                  : s.warp ? launch_sum_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                           : s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
         ws->launches++;
@@ -1020,7 +1060,8 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
             if (s.mma && !ws->mma_down) s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
-            CUDA_TRY(s.mma && ws->mma_down ? launch_sum_down_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
+            CUDA_TRY(s.lane ? launch_lane_down(s.a, s.n_ltiles, ws->stream)
+                     : s.mma && ws->mma_down ? launch_sum_down_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
                      : s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                               : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;

@@ -64,6 +64,10 @@ struct WalkArgs {
     double *tmsg;               // from-above vectors handed to wide children, [ent][K][ncols]
     const int32_t *esum_wide;   // [ncols] rescale exponents accumulated by the wide sum up-sweep (or nullptr)
     const double *logl_wide;    // [ncols] log-likelihood terms the general wide kernels accumulated (or nullptr)
+    // lane walker (sweeps_lane.cu): tiled copies of the inputs, [node][tile_stride] bytes, 32 per (node, tile);
+    // tile_base = index of a.tiles[0] among all lane tiles of the workspace
+    const uint8_t *obs_t, *present_t;
+    int32_t tile_stride, tile_base;
     // general joint up-sweep, nodes with >= 32 children: queue of the pairwise additions, one region per (thread, column)
     double *qscratch;
     int32_t qstride;
@@ -146,6 +150,16 @@ int warp_walk_cols_per_warp(int C);
 cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
 cudaError_t launch_sum_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
 cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
+
+// lane walker (sweeps_lane.cu): K = 20, a thread owns a column (32 per CTA), the 20 outputs of a step are split over
+// four warps; a.tiles = tiles of one category and at most lane_walk_cols() columns; a.obs_t must be set when the
+// program has childless children
+size_t lane_walk_smem_bytes(int slots, bool down);
+int lane_walk_cols();
+cudaError_t launch_lane_up(int mode, const WalkArgs &a, int n_tiles, cudaStream_t st);
+cudaError_t launch_lane_down(const WalkArgs &a, int n_tiles, cudaStream_t st);
+cudaError_t launch_tile_bytes(const uint8_t *in, const int32_t *orig_col, const TileDesc *tiles, int n_tiles, int tile_base,
+                              int n_nodes, int ncols, int tile_stride, uint8_t *out, cudaStream_t st);
 
 // joint up-sweep of the warp-tiled walker with ten lanes per column (3 columns per warp, W <= 14 consumer warps);
 // a.tiles = tiles of one category and at most 3 W columns

@@ -103,8 +103,10 @@ static void build_program(const bnk_tree *t, const std::vector<uint8_t> &member,
                 if (k < 2) { s.c_node[k] = u; s.c_slot[k] = sl; s.c_ent[k] = t->ent_of_node[u]; }
                 pg.up_child.push_back(ChildRef{u, sl, t->ent_of_node[u]});
             }
-            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) pool.release(slot_of[t->kids[e]]);
+            // the node's slot is taken BEFORE its children's are released: a step never writes the slot it reads
+            // (the lane walker of sweeps_lane.cu hands messages from warp to warp with one barrier per step)
             s.slot = (t->parent[v] >= 0) ? pool.alloc() : -1;
+            for (int32_t e = t->first[v]; e < t->first[v + 1]; e++) pool.release(slot_of[t->kids[e]]);
             slot_of[v] = s.slot;
             pg.up.push_back(s);
         }
