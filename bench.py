@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3a", choices=sorted(WORKLOADS))
     ap.add_argument("--cols", type=int, default=0, help="columns of the problem (default: the workload's)")
+    ap.add_argument("--leaves", type=int, default=0, help="leaves of the tree (default: the workload's; smaller trees for profiling)")
     ap.add_argument("--weak", action="store_true", help="every rank runs the whole problem (r1's weak-scaling layout)")
     ap.add_argument("--tile-cols", type=int, default=0)
     ap.add_argument("--cpt", type=int, default=0)
@@ -318,7 +319,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    spec = WORKLOADS[args.workload]
+    spec = dict(WORKLOADS[args.workload])
+    if args.leaves:
+        spec["leaves"] = args.leaves
+        spec["name"] += " (reduced to %d leaves)" % args.leaves
     n_cols = args.cols or spec["cols"]
     threads = os.cpu_count() or 1
     config = {"workload": spec["name"], "tree": spec["tree"], "leaves": spec["leaves"], "cols": n_cols,

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
 #include <set>
 #include <thread>
 #include <vector>
@@ -32,7 +33,33 @@ using namespace bnk;
         }                                                                                                   \
     } while (0)
 
+// the ancestors' partial-order graphs as bnk_bep_infer hands them out (<-> Map<Object, POGraph> of asr.Prediction)
+struct bnk_pogs {
+    int32_t n_pos = 0;
+    std::vector<int32_t> ent_of_node;
+    std::vector<std::vector<int32_t>> from, to;   // per ancestor row: edges sorted by (from, to); -1 = start, n_pos = end
+    std::vector<std::vector<uint8_t>> flags;      // bit 0: inferred in the forward direction, bit 1: backward (POGraph.BidirEdge)
+};
+
 namespace {
+
+// an inferred edge: (from, to, direction flags)
+struct Edge3 {
+    int a, b;
+    uint8_t f;
+    bool operator<(const Edge3 &o) const { return a != o.a ? a < o.a : b < o.b; }
+};
+// sort, and merge duplicates by OR-ing their direction flags (EdgeMap.Directed.add, src/dat/pog/EdgeMap.java)
+inline void merge_edges(std::vector<Edge3> &e)
+{
+    std::sort(e.begin(), e.end());
+    size_t w = 0;
+    for (size_t r = 0; r < e.size(); r++) {
+        if (w > 0 && e[w - 1].a == e[r].a && e[w - 1].b == e[r].b) e[w - 1].f |= e[r].f;
+        else e[w++] = e[r];
+    }
+    e.resize(w);
+}
 
 // dat.pog.POGraph restricted to what BEP needs: directed, terminated, nodes = alignment columns
 struct Pog {
@@ -116,13 +143,32 @@ struct Pog {
         for (auto it = o.rbegin(); it != o.rend(); ++it) if (sticks_out(*it, true)) cols.insert(-*it);
         return cols;
     }
-    void from_edges(int n_pos, const std::vector<std::pair<int, int>> &edges)  // createFromEdgeMap (:544-559)
+    void from_edges(int n_pos, const std::vector<Edge3> &edges)  // createFromEdgeMap (:544-559)
     {
         reset(n_pos);
         for (const auto &ed : edges) {
-            if (ed.first != -1 && !is_node(ed.first)) add_node(ed.first);
-            if (ed.second != n_pos && !is_node(ed.second)) add_node(ed.second);
-            add_edge(ed.first, ed.second);
+            if (ed.a != -1 && !is_node(ed.a)) add_node(ed.a);
+            if (ed.b != n_pos && !is_node(ed.b)) add_node(ed.b);
+            add_edge(ed.a, ed.b);
+        }
+    }
+    // the graph as it stands, with the direction flags of `edges` (every edge of the graph is in that list)
+    void export_to(bnk_pogs *out, int ent, const std::vector<Edge3> &edges) const
+    {
+        auto flag_of = [&](int a, int b) -> uint8_t {
+            for (const Edge3 &e : edges) if (e.a == a && e.b == b) return e.f;   // lists are short; patched lists are unsorted
+            return 0;
+        };
+        std::vector<int32_t> &fr = out->from[ent], &to = out->to[ent];
+        std::vector<uint8_t> &fl = out->flags[ent];
+        fr.clear(); to.clear(); fl.clear();
+        const std::vector<int> o = order();
+        for (int i : o) if (is_start[i]) { fr.push_back(-1); to.push_back(i); fl.push_back(flag_of(-1, i)); }
+        for (int i : o) {
+            std::vector<int> nx = fwd[i];
+            std::sort(nx.begin(), nx.end());
+            for (int j : nx) { fr.push_back(i); to.push_back(j); fl.push_back(flag_of(i, j)); }
+            if (is_end[i]) { fr.push_back(i); to.push_back(n); fl.push_back(flag_of(i, n)); }
         }
     }
 };
@@ -154,8 +200,8 @@ struct Dev {
 
 }  // namespace
 
-extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
-                                int32_t *info_or_null)
+static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
+                   int32_t *info_or_null, bnk_pogs *pogs)
 {
     if (!t || !obs || !present_out || n_cols < 1) return fail(BNK_ERR_ARG, "bep: bad argument");
     if (t->root_count != 1 || t->parent[0] >= 0)
@@ -212,7 +258,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
     Pog pog;  // scratch for the serial tail
     // ancestors without a start-to-end path: their edges so far (the graph is rebuilt in `pog` when needed) and
     // the columns that stick out
-    std::map<int, std::vector<std::pair<int, int>>> crippled_edges;
+    std::map<int, std::vector<Edge3>> crippled_edges;
     std::map<int, std::set<int>> crippled;
     std::vector<int32_t> h_nsym;
     struct Pinned {  // page-locked staging for the two large device->host copies
@@ -406,18 +452,17 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                 opt_ent0 = lo;
                 parallel_slices(hi - lo, [&](int slo, int shi) {
                     Pog g;
-                    std::vector<std::pair<int, int>> edges;
+                    std::vector<Edge3> edges;
                     for (int ent = lo + slo; ent < lo + shi; ent++) {
                         const int v = t->node_of_ent[ent];
                         edges.clear();
                         for (int k = 0; k < n_inst; k++) {
                             if (h_nsym[k] < 1) continue;  // nothing to infer: the reference makes no Parsimony object (:1466-1468)
                             const int i = ie[k] - 1;
-                            if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back({i, to}); });
-                            else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back({from, i}); });
+                            if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back(Edge3{i, to, 1}); });
+                            else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back(Edge3{from, i, 2}); });
                         }
-                        std::sort(edges.begin(), edges.end());
-                        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                        merge_edges(edges);
                         g.from_edges(n_pos, edges);
                         if (!g.is_contiguous()) {
                             std::set<int> pr = g.protruding();
@@ -427,6 +472,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                         } else {
                             g.nibble();  // GRASP.NIBBLE = true
                             emit_row(v, g);
+                            if (pogs) g.export_to(pogs, ent, edges);
                         }
                     }
                 });
@@ -463,15 +509,19 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                 Pog g;
                 for (int f = lo; f < hi; f++) {
                     const int v = fixme[f];
-                    std::vector<std::pair<int, int>> &edges = crippled_edges.find(v)->second;  // maps are only read here
+                    std::vector<Edge3> &edges = crippled_edges.find(v)->second;  // maps are only read here
                     g.from_edges(n_pos, edges);
                     const int ent = t->ent_of_node[v];
                     for (int idx : crippled.find(v)->second) {  // ascending, as cols_ordered
                         const int k = inst_of.find(idx)->second, col = std::abs(idx);
                         for_each_optimal(ent, k, n_inst, W, [&](int inferred) {
                             if (!g.is_node(inferred) && inferred != n_pos && inferred != -1) { g.add_node(inferred); grew[f] = 1; }
-                            const std::pair<int, int> ed = idx > 0 ? std::make_pair(col, inferred) : std::make_pair(inferred, col);
-                            if (g.add_edge(ed.first, ed.second)) { edges.push_back(ed); grew[f] = 1; }
+                            // pog.addEdge(.., new BidirEdge(forward, !forward)) REPLACES the edge object of an existing edge
+                            // (IdxEdgeGraph.addEdge, src/dat/pog/IdxEdgeGraph.java:147-153): the flags are overwritten
+                            const Edge3 ed = idx > 0 ? Edge3{col, inferred, 1} : Edge3{inferred, col, 2};
+                            bool known = false;
+                            for (Edge3 &old : edges) if (old.a == ed.a && old.b == ed.b) { old.f = ed.f; known = true; }
+                            if (g.add_edge(ed.a, ed.b)) { if (!known) edges.push_back(ed); grew[f] = 1; }
                         });
                     }
                     if (!g.is_contiguous()) {
@@ -479,6 +529,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
                     } else {
                         g.nibble();
                         emit_row(v, g);
+                        if (pogs) g.export_to(pogs, ent, edges);
                         fixed[f] = 1;
                     }
                 }
@@ -495,6 +546,7 @@ extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t
         for (const auto &kv : crippled_edges) {  // still without a path: nodes as they stand
             pog.from_edges(n_pos, kv.second);
             emit_row(kv.first, pog);
+            if (pogs) pog.export_to(pogs, t->ent_of_node[kv.first], kv.second);
         }
         mark("patch rounds done");
         info[6] = us_since(t_begin);
@@ -506,4 +558,47 @@ done:
     if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
     return rc;
+}
+
+
+extern "C" int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
+                                int32_t *info_or_null)
+{
+    return bep_run(t, n_cols, obs, device, present_out, info_or_null, nullptr);
+}
+
+extern "C" int bnk_bep_infer(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
+                             int32_t *info_or_null, bnk_pogs **out)
+{
+    if (!out) return fail(BNK_ERR_ARG, "bep: null argument");
+    if (!t) return fail(BNK_ERR_ARG, "bep: bad argument");
+    bnk_pogs *p = new (std::nothrow) bnk_pogs();
+    if (!p) return fail(BNK_ERR_NOMEM, "bep: out of host memory");
+    p->n_pos = n_cols;
+    p->ent_of_node = t->ent_of_node;
+    p->from.assign(t->n_int, {}); p->to.assign(t->n_int, {}); p->flags.assign(t->n_int, {});
+    const int rc = bep_run(t, n_cols, obs, device, present_out, info_or_null, p);
+    if (rc != BNK_OK) { delete p; return rc; }
+    *out = p;
+    return BNK_OK;
+}
+
+extern "C" void bnk_pogs_destroy(bnk_pogs *p) { delete p; }
+
+extern "C" int bnk_pogs_n_edges(const bnk_pogs *p, int32_t node)
+{
+    if (!p || node < 0 || node >= (int32_t)p->ent_of_node.size() || p->ent_of_node[node] < 0)
+        return fail(BNK_ERR_QUERY, "pogs: node %d is not an ancestor", node);
+    return (int)p->from[p->ent_of_node[node]].size();
+}
+
+extern "C" int bnk_pogs_edges(const bnk_pogs *p, int32_t node, int32_t *from, int32_t *to, uint8_t *flags)
+{
+    const int n = bnk_pogs_n_edges(p, node);
+    if (n < 0) return n;
+    const int ent = p->ent_of_node[node];
+    if (from) std::memcpy(from, p->from[ent].data(), sizeof(int32_t) * n);
+    if (to) std::memcpy(to, p->to[ent].data(), sizeof(int32_t) * n);
+    if (flags) std::memcpy(flags, p->flags[ent].data(), n);
+    return n;
 }

@@ -36,6 +36,7 @@ SYMBOLS = [
     "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
     "bnk_ws_phase_ms", "bnk_bep_presence",
     "bnk_ws_set_evidence_mode", "bnk_ws_set_pipeline",
+    "bnk_bep_infer", "bnk_pogs_n_edges", "bnk_pogs_edges", "bnk_pogs_destroy",
     "bnk_mgpu_create", "bnk_mgpu_destroy", "bnk_mgpu_n_devices", "bnk_mgpu_shard", "bnk_mgpu_set_rates",
     "bnk_mgpu_set_distances", "bnk_mgpu_joint", "bnk_mgpu_marginal", "bnk_mgpu_loglik", "bnk_mgpu_upload",
     "bnk_mgpu_loglik_resident", "bnk_mgpu_reduction", "bnk_mgpu_launch_count",
@@ -87,6 +88,11 @@ def lib():
     L.bnk_loglik_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
     L.bnk_ws_phase_ms.argtypes = [_vp, C.c_int, C.POINTER(C.c_float)]
     L.bnk_bep_presence.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip]
+    L.bnk_bep_infer.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip, C.POINTER(_vp)]
+    L.bnk_pogs_n_edges.argtypes = [_vp, C.c_int32]
+    L.bnk_pogs_edges.argtypes = [_vp, C.c_int32, _ip, _ip, _bp]
+    L.bnk_pogs_destroy.argtypes = [_vp]
+    L.bnk_pogs_destroy.restype = None
     L.bnk_ws_set_evidence_mode.argtypes = [_vp, C.c_int]
     L.bnk_ws_set_pipeline.argtypes = [_vp, C.c_int32]
     L.bnk_mgpu_create.argtypes = [_vp, _vp, C.c_int32, C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
@@ -211,6 +217,28 @@ class Tree:
         info = np.zeros(8, dtype=np.int32)
         check(lib().bnk_bep_presence(self.h, obs.shape[1], obs.ctypes.data_as(_bp), int(device), out.ctypes.data_as(_bp), _i(info)))
         return (out, info) if want_info else out
+
+
+    def bep_infer(self, obs, device=-1):
+        """bep_presence plus the ancestors' partial-order graphs: returns (present, {node: (from[], to[], flags[])})
+        with from = -1 for the start terminal, to = n_cols for the end terminal, flags bit 0 / 1 = forward / backward."""
+        obs = np.ascontiguousarray(obs, dtype=np.uint8)
+        out = np.empty_like(obs)
+        info = np.zeros(8, dtype=np.int32)
+        h = _vp()
+        L = lib()
+        check(L.bnk_bep_infer(self.h, obs.shape[1], obs.ctypes.data_as(_bp), int(device), out.ctypes.data_as(_bp), _i(info), C.byref(h)))
+        graphs = {}
+        try:
+            for v in self.internal_nodes():
+                ne = check(L.bnk_pogs_n_edges(h, int(v)))
+                fr, to, fl = np.empty(ne, np.int32), np.empty(ne, np.int32), np.empty(ne, np.uint8)
+                if ne:
+                    check(L.bnk_pogs_edges(h, int(v), _i(fr), _i(to), fl.ctypes.data_as(_bp)))
+                graphs[int(v)] = (fr, to, fl)
+        finally:
+            L.bnk_pogs_destroy(h)
+        return out, graphs
 
 
 class Workspace:

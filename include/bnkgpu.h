@@ -76,6 +76,19 @@ int bnk_device_count(void);
 int bnk_bep_presence(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
                      int32_t *info_or_null);
 
+/* The same inference, also handing out the ancestors' partial-order graphs (<-> the Map<Object, POGraph> a
+ * Prediction holds, src/asr/Prediction.java:60-75): what Prediction.getConsensus / getSequence / toJSON need
+ * downstream of the sweeps.  Edges of ancestor `node` (tree index) sorted by (from, to); from = -1 is the start
+ * terminal, to = n_cols the end terminal; flags bit 0 / bit 1 = inferred by a forward / backward edge instance
+ * (POGraph.BidirEdge, src/dat/pog/POGraph.java:1039-1053; both = "Recip").  bnk_pogs_edges returns the edge count;
+ * any output array may be NULL. */
+typedef struct bnk_pogs bnk_pogs;
+int bnk_bep_infer(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int device, uint8_t *present_out,
+                  int32_t *info_or_null, bnk_pogs **out);
+int bnk_pogs_n_edges(const bnk_pogs *p, int32_t node);
+int bnk_pogs_edges(const bnk_pogs *p, int32_t node, int32_t *from, int32_t *to, uint8_t *flags);
+void bnk_pogs_destroy(bnk_pogs *p);
+
 /* ---- substitution models ------------------------------------------------------------ */
 /* SubstModel.createModel(name) / createModel(name, empiricalFreqs)  (SubstModel.java:334-385).
  * name in {"LG","JTT","WAG","Dayhoff","JC","Yang"}; F_or_null = 20 (or 4) frequencies. */
