@@ -21,16 +21,14 @@ import json
 import numpy as np
 
 from . import lib
+from . import pog as _pog
+from .pog import ASRRuntimeException, POGraph, POGTree  # noqa: F401  (re-exported: the mirror's public names)
 
 ALPHABETS = {
     "LG": "ARNDCQEGHILKMFPSTWYV", "JTT": "ARNDCQEGHILKMFPSTWYV", "WAG": "ARNDCQEGHILKMFPSTWYV",
     "Dayhoff": "ARNDCQEGHILKMFPSTWYV", "JC": "ACGT", "Yang": "ACGT",
 }
 NONE = lib.NONE
-
-
-class ASRRuntimeException(RuntimeError):
-    """asr.ASRRuntimeException (unchecked)"""
 
 
 class EnumDistrib:
@@ -92,7 +90,7 @@ class SubstModel:
 class IdxTree:
     """dat.phylo.IdxTree: nodes indexed depth-first, parent index < child index."""
 
-    def __init__(self, parents, distances=None, labels=None):
+    def __init__(self, parents, distances=None, labels=None, ancids=None):
         self.parent = np.asarray(parents, dtype=np.int32)
         n = len(self.parent)
         self.distance = np.zeros(n) if distances is None else np.asarray(distances, dtype=np.float64).copy()
@@ -101,6 +99,11 @@ class IdxTree:
         for i, p in enumerate(self.parent):
             if p >= 0:
                 self.children[p].append(i)
+        # BranchPoint.getID (src/dat/phylo/BranchPoint.java:88-90): a leaf's ID is its label, an ancestor's its ancestor
+        # number.  Default = what IdxTree.fromJSON assigns (:312-321): 0, 1, ... over the ancestors in index order.
+        if ancids is None:
+            ancids = {v: k for k, v in enumerate(i for i in range(n) if self.children[i])}
+        self.ancid = dict(ancids)
         self._handle = None
 
     # ---- construction ----
@@ -123,6 +126,7 @@ class IdxTree:
         if s.endswith(";"):
             s = s[:-1]
         parents, dists, labels = [], [], []
+        named = {}
         pos = 0
         anc = [0]
 
@@ -162,6 +166,8 @@ class IdxTree:
                     raise RuntimeError("A distance value couldn't be parsed as a number. The value is \"%s\"" % s[start:pos])
                 dists[idx] = 0.00001 if d == 0.0 else d
             labels[idx] = name if name else ("N%d" % my_anc if internal else "")
+            if internal:
+                named[idx] = bool(name)
             return idx
 
         import sys
@@ -171,7 +177,30 @@ class IdxTree:
             node(-1)
         finally:
             sys.setrecursionlimit(old)
-        return IdxTree(parents, dists, labels)
+        # ancestor numbers as Newick.parse assigns them (src/dat/file/Newick.java:217-254): a label N<number> fixes
+        # the number; every other ancestor takes the lowest numbers still free, in depth-first order
+        ancids, taken, rest = {}, set(), []
+        for idx in sorted(named):
+            lab = labels[idx]
+            if named[idx] and lab.startswith("N"):
+                try:
+                    k = int(lab[1:])
+                except ValueError:
+                    raise RuntimeError("Invalid ancestor name: " + lab + ". Needs to follow N<number> format.")
+                if k in taken:
+                    raise RuntimeError("Duplicate ancestor name/number: " + lab)
+                taken.add(k)
+                ancids[idx] = k
+            else:
+                rest.append(idx)
+        count = 0
+        for idx in rest:
+            while count in taken:
+                count += 1
+            ancids[idx] = count
+            taken.add(count)
+            count += 1
+        return IdxTree(parents, dists, labels, ancids)
 
     # ---- accessors (IdxTree.java) ----
     def getSize(self):
@@ -192,9 +221,26 @@ class IdxTree:
     def getLabel(self, idx):
         return self.labels[idx]
 
+    def getID(self, idx):
+        """BranchPoint.getID: the label of a leaf, the ancestor number (int) of an ancestor -- what the reference's
+        IdxTree.getLabel(idx) returns (src/dat/phylo/IdxTree.java:759-763)"""
+        return self.ancid[idx] if self.children[idx] else self.labels[idx]
+
     def getIndex(self, label):
-        for i, l in enumerate(self.labels):
-            if l == label:
+        """IdxTree.getIndex (:997-1022): a string matches a branch point's label or the text of its ID, then
+        "N<k>" the ancestor numbered k; an int matches an ancestor number; -1 if there is none"""
+        if isinstance(label, str):
+            for i, l in enumerate(self.labels):
+                if l == label or str(self.getID(i)) == label:
+                    return i
+            if label.startswith("N"):
+                try:
+                    return self.getIndex(int(label[1:]))
+                except ValueError:
+                    pass
+            return -1
+        for i, k in self.ancid.items():
+            if k == label:
                 return i
         return -1
 
@@ -330,7 +376,9 @@ class Prediction:
              (src/asr/Prediction.java:329-402) as a mask, or None when every node is present.
     """
 
-    def __init__(self, tree, states, present=None, device=-1):
+    JOINT, MARGINAL = "JOINT", "MARGINAL"   # GRASP.Inference
+
+    def __init__(self, tree, states, present=None, device=-1, ancestors=None):
         self.tree = tree
         self.states = states
         self.present = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
@@ -338,6 +386,12 @@ class Prediction:
         self.n_cols = len(states[0]) if len(states) else 0
         self._ws = None
         self._ws_model = None
+        # output side (section 8 f-2): the ancestors' partial-order graphs {branch point index: POGraph}, the extants'
+        # graphs, and what the last getJoint / getMarginal calls inferred
+        self.ancarr = ancestors
+        self._pogTree = None              # the extants' graphs, built when the output side first needs them
+        self.joint_states = None          # Object[][] states[bpidx][pos]
+        self.distribs = {}                # bpidx -> EnumDistrib[] over positions
 
     @staticmethod
     def PredictByBidirEdgeParsimony(tree, states, device=-1):
@@ -354,8 +408,40 @@ class Prediction:
                     if states[v][c] is not None:
                         occ[v, c] = 0
         h = tree.handle()
-        present = h.prune_orphans(h.bep_presence(occ, device=device))
-        return Prediction(tree, states, present, device)
+        raw, graphs = h.bep_infer(occ, device=device)
+        present = h.prune_orphans(raw)
+        anc = {v: POGraph.fromEdges(n_cols, fr, to, fl, name=Prediction._ancestor_id(tree, v)) for v, (fr, to, fl) in graphs.items()}
+        return Prediction(tree, states, present, device, ancestors=anc)
+
+    @property
+    def pogTree(self):
+        if self._pogTree is None:
+            self._pogTree = POGTree.fromAlignment(self.tree, self.states)
+        return self._pogTree
+
+    @pogTree.setter
+    def pogTree(self, value):
+        self._pogTree = value
+
+    @staticmethod
+    def _ancestor_id(tree, idx):
+        """the ancestor's ID as text: BranchPoint IDs of ancestors are integers (POGraph names, FASTA names N<id>)"""
+        return str(tree.getID(idx))
+
+    def getBranchpointIndex(self, ancID):
+        """index of the branch point with this ID in the tree, -1 if there is none (Prediction.java:453-456)"""
+        if isinstance(ancID, (int, np.integer)):
+            return self.tree.getIndex(int(ancID))
+        i = self.tree.getIndex(str(ancID))
+        if i == -1 and str(ancID).isdigit():
+            i = self.tree.getIndex(int(ancID))
+        return i
+
+    def getAncestorIndices(self):
+        return self.tree.getAncestors()
+
+    def getPositions(self):
+        return self.n_cols
 
     def _obs(self, model):
         n = self.tree.getSize()
@@ -385,14 +471,14 @@ class Prediction:
         ws = self._workspace(model, rates)
         st = ws.joint(self._obs(model), self.present)
         dom = model.domain
-        return [[None if s == NONE else dom[s] for s in row] for row in st]
+        self.joint_states = [[None if s == NONE else dom[s] for s in row] for row in st]
+        return self.joint_states
 
     def getMarginal(self, ancestor, model, rates=None):
-        """EnumDistrib[] over positions for one ancestor (index or label), None where it is absent
-        (Prediction.java:555-597); an unknown ancestor raises ASRRuntimeException (:561-562)."""
-        idx = ancestor if isinstance(ancestor, (int, np.integer)) else self.tree.getIndex(ancestor)
-        if isinstance(ancestor, str) and idx < 0 and ancestor.startswith("N"):
-            idx = self.tree.getIndex(ancestor[1:])
+        """EnumDistrib[] over positions for one ancestor, None where it is absent (Prediction.java:555-597); an
+        unknown ancestor raises ASRRuntimeException (:561-562).  `ancestor`: an ID as text ("N3", "3", a label) as
+        the reference takes it, or -- this mirror only -- an int = the branch point's index in the tree."""
+        idx = ancestor if isinstance(ancestor, (int, np.integer)) else self.getBranchpointIndex(ancestor)
         if idx < 0 or idx >= self.tree.getSize():
             raise ASRRuntimeException("Invalid ancestor ID " + str(ancestor))
         ws = self._workspace(model, rates)
@@ -402,7 +488,172 @@ class Prediction:
             if e.code == -7:
                 raise ASRRuntimeException("Invalid ancestor ID " + str(ancestor))
             raise
-        return [None if np.isnan(post[0, c]).any() else EnumDistrib(model.domain, post[0, c]) for c in range(self.n_cols)]
+        d = [None if np.isnan(post[0, c]).any() else EnumDistrib(model.domain, post[0, c]) for c in range(self.n_cols)]
+        self.distribs[idx] = d
+        return d
+
+    # ---- downstream assembly and outputs ----
+    def getAncestors(self, mode):
+        """{ancestor ID: POGraph} decorated with the inferred states (JOINT) or distributions (MARGINAL); ancestors
+        that have not been inferred are not included (Prediction.java:483-503)"""
+        if self.ancarr is None:
+            raise ASRRuntimeException("No ancestor POGs: indel inference has not been performed")
+        out = {}
+        for idx in self.getAncestorIndices():
+            g = self.ancarr.get(idx)
+            if g is None:
+                continue
+            if mode == Prediction.JOINT and self.joint_states is not None:
+                g.decorateNodes(self.joint_states[idx], "class dat.pog.SymNode")
+                out[Prediction._ancestor_id(self.tree, idx)] = g
+            elif mode == Prediction.MARGINAL and self.distribs.get(idx) is not None:
+                g.decorateNodes(self.distribs[idx], "class dat.pog.EnumNode")
+                out[Prediction._ancestor_id(self.tree, idx)] = g
+        return out
+
+    def getConsensus(self, anc):
+        """positions of the ancestor's POG that make up its most supported start-to-end path
+        (Prediction.getConsensus, src/asr/Prediction.java:723-780): every edge out of a visited node is weighted
+        -log of the length-weighted share of the extants below the ancestor that make the same jump
+        (POGTree.getEdgeRates), capped at 10000; then POGraph.getMostSupported (Dijkstra; unreciprocated edges
+        cost 1000 x)."""
+        bpidx = anc if isinstance(anc, (int, np.integer)) else self.getBranchpointIndex(anc)
+        if bpidx is None or bpidx < 0 or self.ancarr is None or self.ancarr.get(bpidx) is None:
+            raise ASRRuntimeException("Ancestor has not been inferred: index is " + str(bpidx))
+        g = self.ancarr[bpidx]
+        leaves = self._leaves_under(bpidx)
+        import heapq
+        queue = list(g.getForward())
+        heapq.heapify(queue)
+        visiting = set(queue)
+        while queue:
+            curr = heapq.heappop(queue)
+            nexts = g.getForward(curr)
+            if g.isEndNode(curr):
+                nexts = nexts + [g.maxsize()]
+            rates = self.pogTree.getEdgeRates(curr, nexts, leaves)
+            for nx, r in zip(nexts, rates):
+                edge = g.getEdge(curr, nx)
+                w = -np.log(r)
+                if edge is None:   # the target node may not have been inferred
+                    edge = _pog.BidirEdge(False, False)
+                    g.addEdge(curr, nx, edge)
+                edge.weight = 10000.0 if w > 10000 else float(w)
+            for nx in nexts:
+                if nx != g.maxsize() and nx not in visiting:
+                    heapq.heappush(queue, nx)
+                    visiting.add(nx)
+        return g.getMostSupported()
+
+    def _leaves_under(self, bpidx):
+        out, stack = [], [bpidx]
+        while stack:
+            v = stack.pop()
+            ch = self.tree.getChildren(v)
+            if not ch:
+                out.append(v)
+            stack.extend(reversed(ch))
+        return out
+
+    def getSequence(self, ancID, mode, gappy):
+        """the inferred ancestor as a sequence along its consensus path (Prediction.getSequence :674-708): gappy =
+        one entry per alignment column (None off the path), else only the path's entries"""
+        bpidx = self.getBranchpointIndex(ancID)
+        if bpidx == -1:
+            raise ASRRuntimeException("Invalid ancestor ID: " + str(ancID))
+        idxs = self.getConsensus(bpidx)
+        if idxs is None:
+            raise ASRRuntimeException("Failed to find optimal path for ancestor ID: " + str(ancID))
+        elems = [None] * (self.n_cols if gappy else len(idxs))
+        if mode == Prediction.JOINT:
+            if self.joint_states is None:
+                raise ASRRuntimeException("Joint inference has not been performed: " + str(ancID))
+            for i, c in enumerate(idxs):
+                elems[c if gappy else i] = self.joint_states[bpidx][c]
+        else:
+            d = self.distribs.get(bpidx)
+            if d is None:
+                raise ASRRuntimeException("Marginal inference has not been performed: " + str(ancID))
+            for i, c in enumerate(idxs):
+                elems[c if gappy else i] = d[c].getMax()
+        return elems
+
+    def ancestorsFasta(self, mode, gappy=True):
+        """the text of <prefix>_ancestors.fa as asr.GRASP writes it (src/asr/GRASP.java:531-596): every inferred
+        ancestor N<id> along its consensus path, in ancestor-ID order"""
+        pogs = self.getAncestors(mode)
+        ids = sorted(pogs, key=lambda k: (0, int(k)) if str(k).isdigit() else (1, str(k)))
+        return _pog.fasta_text(["N" + str(k) for k in ids], [self.getSequence(k, mode, gappy) for k in ids])
+
+    def distribTsv(self, ancID, model):
+        """the text of <prefix>_N<id>.tsv (GRASP's DISTRIB format, src/asr/GRASP.java:599-630)"""
+        bpidx = self.getBranchpointIndex(ancID)
+        d = self.distribs.get(bpidx)
+        if d is None:
+            raise ASRRuntimeException("Marginal inference has not been performed: " + str(ancID))
+        return _pog.distrib_tsv_text(d, model.getDomain())
+
+    def toJSON(self):
+        """ASR.json (Prediction.toJSON, src/asr/Prediction.java:213-226): version, datatype, the input (tree + extant
+        POGs) and the ancestors' POGs in ancestor order, each carrying the columns it is present at ("Indices" =
+        one row of the presence mask) and, once decorated, its node values"""
+        if self.ancarr is None:
+            raise ASRRuntimeException("No ancestor POGs: indel inference has not been performed")
+        return {"GRASP_version": _pog.GRASP_VERSION, "Datatype": "Prediction", "Input": self.pogTree.toJSON(),
+                "Ancestors": [self.ancarr[i].toJSON() for i in self.tree.getAncestors()]}
+
+    @staticmethod
+    def fromJSON(obj, device=-1):
+        """Prediction.fromJSON (:133-155): the tree, the extants and the ancestors' POGs of a saved run -- e.g. an
+        ASR.json a JVM GRASP wrote: its indel inference then feeds the GPU sweeps directly (GRASP -i <folder>,
+        src/asr/GRASP.java:468-474)"""
+        if isinstance(obj, str):
+            obj = json.loads(obj)
+        dt = obj.get("Datatype")
+        if dt is not None and dt != "Prediction":
+            raise ASRRuntimeException("Invalid input file: Wrong datatype " + str(dt) + " should be Prediction")
+        if obj.get("Input") is None:
+            raise ASRRuntimeException("Missing \"Input\" field in JSON")
+        pt = POGTree.fromJSON(obj["Input"], IdxTree)
+        jancs = obj.get("Ancestors")
+        if jancs is None:
+            raise ASRRuntimeException("Missing \"Ancestors\" field in JSON")
+        tree = pt.tree
+        if len(jancs) != len(tree.getAncestors()):
+            raise ASRRuntimeException("Number of ancestors %d does not match tree %d" % (len(jancs), len(tree.getAncestors())))
+        by_name = {}
+        for a in jancs:
+            g = POGraph.fromJSON(a)
+            by_name[str(g.getName())] = g
+        n_cols = jancs[0]["Size"] if jancs else 0
+        states = [[None] * n_cols for _ in range(tree.getSize())]
+        present = np.zeros((tree.getSize(), n_cols), dtype=np.uint8)
+        for v, g in pt.extants.items():
+            for c in g.getIndices():
+                states[v][c] = g.nodes[c]
+                present[v, c] = 1
+        anc = {}
+        for i in tree.getAncestors():
+            g = by_name.get(Prediction._ancestor_id(tree, i))
+            if g is None:
+                raise ASRRuntimeException("Ancestor %s is missing from the JSON" % tree.getLabel(i))
+            anc[i] = g
+            for c in g.getIndices():
+                present[i, c] = 1
+        present = tree.handle().prune_orphans(present)   # Prediction.getTree removes orphans (GRASP.REMOVE_INDEL_ORPHANS)
+        pred = Prediction(tree, states, present, device, ancestors=anc)
+        pred.pogTree = pt
+        return pred
+
+    def save(self, filename):
+        with open(filename, "w") as fh:
+            fh.write(json.dumps(self.toJSON()))
+            fh.write("\n")
+
+    @staticmethod
+    def load(filename, device=-1):
+        with open(filename) as fh:
+            return Prediction.fromJSON(json.loads(fh.read()), device)
 
     def getMarginalAll(self, model, rates=None):
         """All ancestors at once (what `-m` looped over every N<k> costs the reference 37 full passes)."""

@@ -370,44 +370,32 @@ def fasta_text(names, seqs, line_width=60):
 
 
 def java_double(x):
-    """Double.toString for the values a posterior holds (shortest repr that round-trips; scientific below 1e-3 and
-    from 1e7 on, 'E' exponent without sign padding)"""
+    """Double.toString(x) (what TSVFile.saveObjects writes for a Double): the shortest digits that round-trip,
+    plain decimal for 1e-3 <= |x| < 1e7 and d.dddE<n> otherwise, always at least one digit after the point"""
+    from decimal import Decimal
     x = float(x)
     if x != x:
         return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
     if x == 0.0:
-        return "0.0"
-    r = repr(x)
-    mant, _, exp = r.partition("e")
-    if exp:
-        e = int(exp)
-    else:
-        e = None
-    a = abs(x)
-    if 1e-3 <= a < 1e7:
-        s = r if exp == "" else ("%.17f" % x).rstrip("0")
-        if "e" in s or "E" in s:
-            s = ("%.20f" % x).rstrip("0")
-        if s.endswith("."):
-            s += "0"
-        if "." not in s:
-            s += ".0"
-        return s
-    # scientific: d.ddddE<exp>
-    digits = mant.replace("-", "").replace(".", "").lstrip("0") if exp else None
-    if digits is None:
-        m, e10 = ("%.16e" % x).split("e")
-        # shortest digits that round-trip
-        for p in range(1, 18):
-            t = "%.*e" % (p - 1, x)
-            if float(t) == x:
-                m, e10 = t.split("e")
-                break
-        e = int(e10)
-        mant = m
-    if "." not in mant:
-        mant += ".0"
-    return "%sE%d" % (mant, e)
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:   # normalise: no trailing zeros in the digit string
+        digits.pop()
+        exp += 1
+    e10 = exp + len(digits) - 1                  # x = d.ddd x 10^e10
+    ds = "".join(str(d) for d in digits)
+    pre = "-" if sign else ""
+    if -3 <= e10 < 7:
+        if e10 >= 0:
+            whole = ds[: e10 + 1].ljust(e10 + 1, "0")
+            frac = ds[e10 + 1:] or "0"
+        else:
+            whole, frac = "0", "0" * (-e10 - 1) + ds
+        return pre + whole + "." + frac
+    return pre + ds[0] + "." + (ds[1:] or "0") + "E" + str(e10)
 
 
 def distrib_tsv_text(distribs, domain):

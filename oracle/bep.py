@@ -139,6 +139,7 @@ class POG:
         self.bwd = [None] * n
         self.start = set()
         self.end = set()
+        self.flag = {}                       # (from, to) -> bit 0 forward | bit 1 backward (POGraph.BidirEdge, :1039-1053)
 
     def is_node(self, i):
         return 0 <= i < self.n and self.node[i]
@@ -148,7 +149,8 @@ class POG:
         self.fwd[i] = set()
         self.bwd[i] = set()
 
-    def add_edge(self, a, b):                # IdxGraph.addEdge (:402-419)
+    def add_edge(self, a, b, flags=None):    # IdxGraph.addEdge (:402-419); IdxEdgeGraph.addEdge (:147-153) then
+        # stores the edge object, replacing the one an earlier call put there
         if self.is_node(a) and self.is_node(b):
             self.bwd[b].add(a)
             self.fwd[a].add(b)
@@ -158,6 +160,8 @@ class POG:
             self.end.add(a)
         else:
             return False
+        if flags is not None:
+            self.flag[(a, b)] = flags
         return True
 
     def remove_node(self, i):                # IdxGraph.removeNode (:373-391)
@@ -233,15 +237,18 @@ class POG:
             e.add((i, self.n))
         return e
 
+    def edge_flags(self):                    # the BidirEdge of every edge the graph holds now
+        return {e: self.flag.get(e, 0) for e in self.edges()}
 
-def pog_from_edges(n_pos, edges):            # POGraph.createFromEdgeMap(nPos, Directed) (:544-559)
+
+def pog_from_edges(n_pos, edges, flags=None):   # POGraph.createFromEdgeMap(nPos, Directed) (:544-559)
     pog = POG(n_pos)
     for a, b in edges:
         if a != -1 and not pog.is_node(a):
             pog.add_node(a)
         if b != n_pos and not pog.is_node(b):
             pog.add_node(b)
-        pog.add_edge(a, b)
+        pog.add_edge(a, b, None if flags is None else flags[(a, b)])
     return pog
 
 
@@ -298,15 +305,15 @@ def predict(parent, rows, n_pos, recode_null=True, nibble=True, max_rounds=10000
     for j in range(n):
         if not children[j]:
             continue
-        edges = set()
+        edges = {}                           # EdgeMap.Directed.add(from, to, forward): the directions accumulate
         for i in range(-1, n_pos + 1):
             if i != n_pos and pif[i + 1] is not None:
                 for nxt in pif[i + 1][j] or []:
-                    edges.add((i, nxt))
+                    edges[(i, nxt)] = edges.get((i, nxt), 0) | 1
             if i != -1 and pib[i + 1] is not None:
                 for prv in pib[i + 1][j] or []:
-                    edges.add((prv, i))
-        ancestors[j] = pog_from_edges(n_pos, sorted(edges))
+                    edges[(prv, i)] = edges.get((prv, i), 0) | 2
+        ancestors[j] = pog_from_edges(n_pos, sorted(edges), edges)
     # patchAncestorsWithBEP (:1513-1590)
     crippled = {}
     for j, pog in ancestors.items():
@@ -337,10 +344,10 @@ def predict(parent, rows, n_pos, recode_null=True, nibble=True, max_rounds=10000
                             pog.add_node(inferred)
                             changed = True
                         before = len(pog.edges())
-                        if fwd:
-                            pog.add_edge(col, inferred)
+                        if fwd:              # new BidirEdge(true, false) / (false, true) replaces the edge's object
+                            pog.add_edge(col, inferred, 1)
                         else:
-                            pog.add_edge(inferred, col)
+                            pog.add_edge(inferred, col, 2)
                         changed |= len(pog.edges()) != before
             if not pog.is_contiguous():
                 crippled[j] = pog.protruding()

@@ -105,3 +105,23 @@ def test_rates_file_as_grasp_reads_it(tmp_path):
     f.write_text("Site\tRate\n1\tabc\n")
     with pytest.raises(ASRRuntimeException):
         load_rates(str(f))
+
+
+def test_ancestor_numbers_follow_the_reference_rules():
+    """Newick.parse (src/dat/file/Newick.java:217-254): a label N<number> fixes the ancestor's number, all other
+    ancestors (unlabelled or e.g. bootstrap values) take the lowest free numbers depth-first; IdxTree.fromJSON
+    (src/dat/phylo/IdxTree.java:312-321) numbers the ancestors 0, 1, ... in index order whatever their labels;
+    IdxTree.getIndex (:997-1022) finds "N<k>" and k."""
+    from bnkit_b200.phylo import IdxTree
+    t = IdxTree.fromNewick("((a:1,b:1)0.9:1,((c:1,d:1)N1:1,e:1)0.9:1)N3;")
+    anc = t.getAncestors()
+    assert [t.getID(i) for i in anc] == [3, 0, 2, 1]
+    assert t.getIndex("N2") == anc[2] and t.getIndex(1) == anc[3] and t.getIndex("N3") == 0 and t.getIndex("c") == t.labels.index("c")
+    assert t.getIndex("N9") == -1 and t.getIndex("zz") == -1
+    j = IdxTree.fromJSON(t.toJSON())
+    assert [j.getID(i) for i in j.getAncestors()] == [0, 1, 2, 3]
+    import pytest
+    with pytest.raises(RuntimeError):
+        IdxTree.fromNewick("((a:1,b:1)N1:1,(c:1,d:1)N1:1);")
+    with pytest.raises(RuntimeError):
+        IdxTree.fromNewick("((a:1,b:1)Nx:1,c:1);")

@@ -35,6 +35,9 @@ m = re.search(r'"Labels":\[([^\]]+)\]', doc)
 c1["doc_labels"] = json.loads("[" + m.group(1) + "]")
 c1["doc_result"] = {"model": "JTT", "mode": "joint", "indel": "BEP", "ancestors": ["0", "1", "2"],
                     "indices": [2, 4], "values": ["A", "H"], "source": "docs/json-api.md:113-122"}
+# the three ancestor POGs the documentation prints in full (docs/json-api.md:117-119), verbatim
+c1["doc_ancestors"] = [json.loads(x) for x in re.findall(r'^\s+(\{ "Adjacent".*"Edgetype":"class dat.pog.POGraph\$BidirEdge" \}),\s*$', doc, re.M)]
+assert len(c1["doc_ancestors"]) == 3
 (OUT / "c1_66.json").write_text(json.dumps(c1))
 (OUT / "c2_3_2_1_1_filt.json").write_text(json.dumps(dataset("3_2_1_1_filt")))
 
