@@ -367,6 +367,11 @@ def main():
     if world > 1:
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    # one explicit stream for everything that is timed: the workspaces launch on it (its handle is passed to
+    # bnk_ws_create), torch's events are recorded on it, NCCL calls are ordered after it.  (torch's default stream
+    # has the handle 0 = "no stream given"; r1 / r2_v1 lines were timed that way: kernels on a private stream,
+    # events on the default one, the step's own synchronising upload keeping the two within 2 % of each other.)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
 
     model_name, parent, dist, rates, obs = make_workload(spec, rank, n_cols)
     present = None

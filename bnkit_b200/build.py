@@ -19,6 +19,8 @@ UNITS = [
     ("wide_general.cu", []),
     ("cherry.cu", []),
     ("traceback.cu", []),
+    ("indel_tables.cu", ["-fmad=false"]),
+    ("indel.cu", []),
     ("bep.cu", []),
     ("bep_api.cu", []),
     ("api.cu", []),

@@ -58,6 +58,15 @@ extern "C" int bnk_model_create_from_eigen(int K, const double *F, const double 
 {
     return model_from_eigen(K, F, evec, ievec, eval, out);
 }
+extern "C" int bnk_ws_dims(const bnk_ws *ws, int32_t *n_nodes, int32_t *n_internal, int32_t *n_states)
+{
+    if (!ws) return fail(BNK_ERR_ARG, "ws: null");
+    if (n_nodes) *n_nodes = ws->n;
+    if (n_internal) *n_internal = ws->n_int;
+    if (n_states) *n_states = ws->K;
+    return BNK_OK;
+}
+extern "C" int bnk_indel_base_model(const char *name, bnk_model **out) { return indel_base_model_by_name(name, out); }
 extern "C" void bnk_model_destroy(bnk_model *m) { delete m; }
 extern "C" int bnk_model_nstates(const bnk_model *m) { return m ? m->K : fail(BNK_ERR_ARG, "model: null"); }
 extern "C" int bnk_model_get(const bnk_model *m, double *R, double *evec, double *ievec, double *eval, double *F, double *prior)

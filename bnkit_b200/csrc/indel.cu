@@ -1,0 +1,578 @@
+// indel.cu -- gap-augmented peeling on the device: asr.IndelPeeler (Rivas & Eddy 2008) for every alignment column,
+// and the optimisation loop built on it (the reference's real "C5").
+//
+//   IndelPeeler.decorate / felsensteinsExtendedPeeling      src/asr/IndelPeeler.java:229-356
+//   containsGap                                             :359-390
+//   computeColumnPriors (one pass per indel-rate category)  :93-123
+//   calcProbAlnGivenTree, probExtraCol                      :125-193
+//   optimiseMuLambda + LikelihoodEvaluator (Brent, mu = lambda) :469-560, src/smile/math/special/Minimise.java:8-107
+//   bn.ctmc.GapSubstModel                                   src/bn/ctmc/GapSubstModel.java:26-131, :166-247
+//
+// The reference runs one IndelPeeler per column on a thread pool, in log space: per (column, node, parent residue,
+// child) one logsumexp over 20-21 terms, each term a Math.log of a product -- ~17,000 log + 17,000 exp per node
+// and column.  Here a THREAD owns a column and a node's vector lives in registers, in LINEAR space with a
+// power-of-two exponent per (node, column) for the residue vector and another for the gap entry (the two differ
+// by thousands of binades as soon as one child is an all-gap clade and its sibling is not):
+//     R_v[p]  = prod_c ( sum_x A_c[p][x] R_c[x]  +  [c all gaps] del_c )
+//     Gap_v   = sum_c [c all gaps] ( sum_q R_c[q] ins_v[q] + Gap_c )          (a SUM over children, as the reference has it)
+//     column  = logsumexp( log Gap_root,  log(geom) + log sum_r F[r] R_root[r] )
+// with the per-branch tables A / del / ins of indel_tables.cu.  Messages travel through HBM as
+// [ancestor][state][column] rows (coalesced loads and stores).  Schedule: height levels with >= LEVEL_MIN_NODES
+// nodes are one launch each (grid = nodes x column tiles); the narrow rest of the tree -- an upward-closed set --
+// is walked by the same column-owning threads in one launch, children before parents (decreasing index).
+// Parity: oracle/bnk_indel.c (log space, literal), 1e-9 relative on every column's log-likelihood.
+#include "indel.cuh"
+#include "workspace.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace bnk {
+namespace {
+
+constexpr int IND_THREADS = 128;       // columns per CTA
+constexpr int LEVEL_MIN_NODES = 8;     // narrower height levels go to the walk kernel
+constexpr int E_ZERO = INT32_MIN / 2;  // exponent marking an exactly-zero gap entry
+
+struct IndelArgs {
+    const int32_t *first, *kids, *ent_of_node, *parent;
+    const uint8_t *obs;   // [node][ncols], BNK_NONE = gap; childless rows only
+    int32_t ncols;
+    IndelTables tb;
+    const double *F;      // K + 1
+    double *msg;          // [ent][K + 1][ncols]: residue mantissas (max in [1, 2)), gap mantissa
+    int32_t *eR, *eG;     // [ent][ncols]
+    uint8_t *cg;          // [ent][ncols] containsGap: every extant below is a gap
+    double log_geom;
+    double *out_logl;     // [ncols]
+    const int32_t *nodes; // the nodes of this launch (a level) / the narrow nodes in processing order
+    int32_t n_launch_nodes;
+};
+
+__device__ __forceinline__ double pow2i(int e) { return __hiloint2double((1023 + e) << 20, 0); }  // e in [-1022, 1023]
+__device__ __forceinline__ int exponent_of(double m) { return ((__double2hiint(m) >> 20) & 0x7ff) - 1023; }
+
+// a * 2^ea + b * 2^eb as (mantissa, exponent); a zero operand carries no exponent
+__device__ __forceinline__ void add_scaled(double a, int ea, double b, int eb, double &r, int &er)
+{
+    if (b == 0.0) { r = a; er = ea; return; }
+    if (a == 0.0) { r = b; er = eb; return; }
+    if (ea >= eb) {
+        const int d = eb - ea;
+        r = a + (d < -1000 ? 0.0 : b * pow2i(d));
+        er = ea;
+    } else {
+        const int d = ea - eb;
+        r = b + (d < -1000 ? 0.0 : a * pow2i(d));
+        er = eb;
+    }
+}
+
+// One node for one column per thread; every thread of the CTA works on the same node (tables staged in shared memory).
+template <int K>
+__device__ __forceinline__ void peel_node(const IndelArgs &a, int node, int col, bool valid, double *sA, double *s_ins)
+{
+    const int tid = threadIdx.x;
+    const int c0 = a.first[node], c1 = a.first[node + 1];
+    const size_t nc = (size_t)a.ncols;
+    double Rv[K];
+#pragma unroll
+    for (int p = 0; p < K; p++) Rv[p] = 1.0;
+    int eRv = 0;
+    double gm = 0.0;
+    int ge = 0;
+    bool cgv = true;
+    __syncthreads();   // the previous node's reads of s_ins / sA are done
+    if (tid < K) s_ins[tid] = a.tb.ins[(size_t)node * K + tid];
+    for (int k = c0; k < c1; k++) {
+        const int ch = a.kids[k];
+        if (k > c0) __syncthreads();
+        {
+            const double *src = a.tb.A + (size_t)ch * (K * K);
+            for (int i = tid; i < K * K; i += IND_THREADS) sA[i] = src[i];
+        }
+        __syncthreads();
+        if (!valid) continue;
+        const double del = a.tb.del[ch];
+        const int ent = a.ent_of_node[ch];
+        if (ent < 0) {   // an extant (calcLeafPeelingProbabilities :273-284)
+            const uint8_t o = a.obs[(size_t)ch * nc + col];
+            if (o == BNK_NONE) {
+#pragma unroll
+                for (int p = 0; p < K; p++) Rv[p] *= del;
+            } else {
+                cgv = false;
+#pragma unroll
+                for (int p = 0; p < K; p++) Rv[p] *= sA[p * K + o];
+            }
+        } else {
+            double Rc[K];
+            const double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
+#pragma unroll
+            for (int x = 0; x < K; x++) Rc[x] = m[(size_t)x * nc];
+            const int eRc = a.eR[(size_t)ent * nc + col];
+            const bool cgc = a.cg[(size_t)ent * nc + col] != 0;
+            if (cgc) {
+                // ancestral gap term of this child (:297-327): sum_q R_c[q] ins_v[q] + Gap_c
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < K; q++) s += Rc[q] * s_ins[q];
+                const double Gc = m[(size_t)K * nc];
+                const int eGc = a.eG[(size_t)ent * nc + col];
+                double tm;
+                int te;
+                add_scaled(s, eRc, Gc, eGc, tm, te);
+                add_scaled(gm, ge, tm, te, gm, ge);
+            } else {
+                cgv = false;
+            }
+            // ancestral residue terms (:329-356); the deletion term joins only below an all-gap child
+            const bool with_del = cgc && del > 0.0;
+            const double sc = with_del ? (eRc < -1000 ? 0.0 : pow2i(eRc)) : 1.0;   // messages are <= 1: eRc <= 0
+#pragma unroll
+            for (int p = 0; p < K; p++) {
+                double S = 0.0;
+#pragma unroll
+                for (int x = 0; x < K; x++) S += sA[p * K + x] * Rc[x];
+                Rv[p] *= with_del ? S * sc + del : S;
+            }
+            if (!with_del) eRv += eRc;
+        }
+        // keep the running product's largest entry in [1, 2)
+        double mx = Rv[0];
+#pragma unroll
+        for (int p = 1; p < K; p++) mx = fmax(mx, Rv[p]);
+        if (mx > 0.0) {
+            const int e = exponent_of(mx);
+            const double f = pow2i(-e);
+#pragma unroll
+            for (int p = 0; p < K; p++) Rv[p] *= f;
+            eRv += e;
+        }
+    }
+    if (!valid) return;
+    if (gm > 0.0) {
+        const int e = exponent_of(gm);
+        gm *= pow2i(-e);
+        ge += e;
+    } else {
+        gm = 0.0;
+        ge = E_ZERO;
+    }
+    const int ent = a.ent_of_node[node];
+    double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
+#pragma unroll
+    for (int p = 0; p < K; p++) m[(size_t)p * nc] = Rv[p];
+    m[(size_t)K * nc] = gm;
+    a.eR[(size_t)ent * nc + col] = eRv;
+    a.eG[(size_t)ent * nc + col] = ge;
+    a.cg[(size_t)ent * nc + col] = cgv ? 1 : 0;
+    if (a.parent[node] < 0) {   // decorate (:229-252)
+        const double LN2 = 0.693147180559945309417232121458;
+        double w = 0.0;
+#pragma unroll
+        for (int r = 0; r < K; r++) w += a.F[r] * Rv[r];
+        const double resL = w > 0.0 ? (log(w) + (double)eRv * LN2) + a.log_geom : -CUDART_INF;
+        const double gapL = gm > 0.0 ? log(gm) + (double)ge * LN2 : -CUDART_INF;
+        const double mxl = fmax(resL, gapL);
+        a.out_logl[col] = mxl == -CUDART_INF ? -CUDART_INF : mxl + log(exp(resL - mxl) + exp(gapL - mxl));
+    }
+}
+
+// one height level: grid = (nodes of the level, column tiles)
+template <int K>
+__global__ void __launch_bounds__(IND_THREADS) indel_level_kernel(IndelArgs a)
+{
+    __shared__ double sA[K * K];
+    __shared__ double s_ins[K];
+    const int node = a.nodes[blockIdx.x];
+    const int col = blockIdx.y * IND_THREADS + threadIdx.x;
+    peel_node<K>(a, node, col, col < a.ncols, sA, s_ins);
+}
+
+// the narrow rest of the tree: grid = column tiles, every CTA walks the node list (children before parents)
+template <int K>
+__global__ void __launch_bounds__(IND_THREADS) indel_walk_kernel(IndelArgs a)
+{
+    __shared__ double sA[K * K];
+    __shared__ double s_ins[K];
+    const int col = blockIdx.x * IND_THREADS + threadIdx.x;
+    const bool valid = col < a.ncols;
+    for (int i = 0; i < a.n_launch_nodes; i++) peel_node<K>(a, a.nodes[i], col, valid, sA, s_ins);
+}
+
+}  // namespace
+}  // namespace bnk
+
+// ---- the object behind bnk_indel_* -------------------------------------------------------------------------------
+struct bnk_indel {
+    BufRegistry reg;
+    bnk_model base;
+    bnk_tree *tree = nullptr;
+    int K = 0, K1 = 0, n = 0, n_int = 0, max_cols = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    int32_t ncols = -1;          // alignment columns uploaded (the device holds one more: the all-gap column)
+    GapModelHost gm;
+    bool model_set = false;
+    int64_t launches = 0;
+    std::vector<std::pair<int32_t, int32_t>> level_ranges;   // into d_nodes, height 1 first
+    std::pair<int32_t, int32_t> narrow_range{0, 0};
+    DevBuf<int32_t> d_first{&reg}, d_kids{&reg}, d_ent{&reg}, d_parent{&reg}, d_nodes{&reg}, d_eR{&reg}, d_eG{&reg};
+    DevBuf<double> d_dist{&reg}, d_gm{&reg}, d_A{&reg}, d_del{&reg}, d_ins{&reg}, d_msg{&reg}, d_logl{&reg}, d_probs{&reg};
+    DevBuf<uint8_t> d_obs{&reg}, d_cg{&reg};
+    std::vector<double> h_logl;
+    cudaEvent_t ev[3] = {};
+    float ms_tables = 0, ms_sweep = 0;
+    GapModelDev gmd() const
+    {
+        const double *b = d_gm.p;
+        return GapModelDev{b, b + K1 * K1, b + 2 * K1 * K1, b + 2 * K1 * K1 + K1, gm.mu, gm.lambda, K1};
+    }
+};
+
+namespace {
+
+template <typename T>
+int upload_vec(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st)
+{
+    CUDA_TRY(b.ensure(v.size() ? v.size() : 1));
+    if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return BNK_OK;
+}
+
+void indel_free(bnk_indel *h)
+{
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (DevBufBase *b : h->reg.all) b->release();
+    if (h->tree) tree_release(h->tree);
+    delete h;
+}
+
+// ksiT on the host (GapSubstModel.ksiT :184-192), for probExtraCol
+double ksi_host(const GapModelHost &g, double t)
+{
+    if (g.mu == 0 && g.lambda == 0) return 0.0;
+    const double insertionRate = g.lambda / (g.mu + g.lambda);
+    const double indelProp = 1 - std::exp(-((g.mu + g.lambda) * t));
+    return insertionRate * indelProp;
+}
+
+// MathEx.logm1exp (src/smile/math/MathEx.java:4573-4584)
+int logm1exp(double x, double *out)
+{
+    const double LOG_HALF = std::log(0.5);
+    if (x > 0) return fail(BNK_ERR_ARG, "indel: log P(all-gap column) = %g > 0", x);
+    *out = x <= LOG_HALF ? std::log1p(-std::exp(x)) : std::log(-std::expm1(x));
+    return BNK_OK;
+}
+
+// tables for `rate`, then the sweep over the uploaded columns + the all-gap column; leaves the column
+// log-likelihoods in h->h_logl (ncols + 1 values)
+int run_sweep(bnk_indel *h, double rate, double geom)
+{
+    if (h->ncols < 0) return fail(BNK_ERR_STATE, "indel: no alignment uploaded (bnk_indel_set_alignment)");
+    if (!h->model_set) return fail(BNK_ERR_STATE, "indel: no indel rates set (bnk_indel_set_rates)");
+    if (!(geom > 0.0)) return fail(BNK_ERR_ARG, "indel: the geometric sequence-length parameter must be > 0");
+    const int nc = h->ncols + 1, K = h->K;
+    cudaStream_t st = h->stream;
+    IndelTables tb{h->d_A.p, h->d_del.p, h->d_ins.p};
+    CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    launch_indel_tables(h->K1, h->gmd(), h->d_dist.p, h->d_parent.p, rate, h->n, tb, st);
+    h->launches++;
+    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    IndelArgs a{};
+    a.first = h->d_first.p; a.kids = h->d_kids.p; a.ent_of_node = h->d_ent.p; a.parent = h->d_parent.p;
+    a.obs = h->d_obs.p; a.ncols = nc; a.tb = tb; a.F = h->d_gm.p + 2 * h->K1 * h->K1 + h->K1;
+    a.msg = h->d_msg.p; a.eR = h->d_eR.p; a.eG = h->d_eG.p; a.cg = h->d_cg.p;
+    a.log_geom = std::log(geom); a.out_logl = h->d_logl.p;
+    const int tiles = (nc + IND_THREADS - 1) / IND_THREADS;
+    for (const auto &lr : h->level_ranges) {
+        a.nodes = h->d_nodes.p + lr.first; a.n_launch_nodes = lr.second - lr.first;
+        dim3 grid(a.n_launch_nodes, tiles);
+        if (K == 20) indel_level_kernel<20><<<grid, IND_THREADS, 0, st>>>(a);
+        else indel_level_kernel<4><<<grid, IND_THREADS, 0, st>>>(a);
+        h->launches++;
+    }
+    if (h->narrow_range.second > h->narrow_range.first) {
+        a.nodes = h->d_nodes.p + h->narrow_range.first; a.n_launch_nodes = h->narrow_range.second - h->narrow_range.first;
+        if (K == 20) indel_walk_kernel<20><<<tiles, IND_THREADS, 0, st>>>(a);
+        else indel_walk_kernel<4><<<tiles, IND_THREADS, 0, st>>>(a);
+        h->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    CUDA_TRY(cudaGetLastError());
+    h->h_logl.resize(nc);
+    CUDA_TRY(cudaMemcpyAsync(h->h_logl.data(), h->d_logl.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&h->ms_tables, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->ms_sweep, h->ev[1], h->ev[2]);
+    return BNK_OK;
+}
+
+// IndelPeeler.calcProbAlnGivenTree (:125-161) at the current (mu, lambda)
+int aln_logl(bnk_indel *h, double geom, double *out)
+{
+    TRY(run_sweep(h, 1.0, geom));
+    double logLikelihood = 0.0;
+    for (int c = 0; c < h->ncols; c++) logLikelihood += h->h_logl[c];
+    // probExtraCol (:163-193): tree distances without a rate
+    const bnk_tree *t = h->tree;
+    std::vector<double> pStar(h->n, 0.0);
+    for (int v = h->n - 1; v >= 0; v--) {
+        if (t->first[v + 1] == t->first[v]) { pStar[v] = 0.0; continue; }
+        double childrenLL = 0.0;
+        for (int k = t->first[v]; k < t->first[v + 1]; k++) {
+            const int u = t->kids[k];
+            childrenLL += pStar[u];
+            childrenLL += std::log(1 - ksi_host(h->gm, t->dist[u]));
+        }
+        pStar[v] = childrenLL;
+    }
+    double extra = 0.0;
+    extra += std::log(1 - geom);
+    extra += pStar[0];
+    double unobserved = 0.0;
+    TRY(logm1exp(h->h_logl[h->ncols], &unobserved));
+    *out = (extra - unobserved) + logLikelihood;
+    return BNK_OK;
+}
+
+int set_rates(bnk_indel *h, double mu, double lambda)
+{
+    TRY(gap_model_from_base(&h->base, mu, lambda, &h->gm));
+    const int K1 = h->K1;
+    std::vector<double> pack((size_t)2 * K1 * K1 + 2 * K1);
+    std::memcpy(pack.data(), h->gm.evec, sizeof(double) * K1 * K1);
+    std::memcpy(pack.data() + K1 * K1, h->gm.ievec, sizeof(double) * K1 * K1);
+    std::memcpy(pack.data() + 2 * K1 * K1, h->gm.eval, sizeof(double) * K1);
+    std::memcpy(pack.data() + 2 * K1 * K1 + K1, h->gm.F, sizeof(double) * K1);
+    TRY(upload_vec(h->d_gm, pack, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // `pack` goes out of scope
+    h->model_set = true;
+    return BNK_OK;
+}
+
+}  // namespace
+
+extern "C" int bnk_indel_create(const bnk_model *base, const bnk_tree *tree, int32_t max_cols, int device, bnk_indel **out)
+{
+    if (!base || !tree || !out) return fail(BNK_ERR_ARG, "indel: null argument");
+    if (base->K != 20 && base->K != 4) return fail(BNK_ERR_ARG, "indel: 20- or 4-state base models only");
+    if (!base->has_R) return fail(BNK_ERR_MODEL, "indel: the base model has no rate matrix (adopted eigensystem)");
+    if (max_cols < 1) return fail(BNK_ERR_ARG, "indel: max_cols must be >= 1");
+    if (tree->root_count != 1 || tree->parent[0] >= 0) return fail(BNK_ERR_TREE, "indel: one tree rooted at node 0 expected");
+    if (tree->n_int < 1) return fail(BNK_ERR_TREE, "indel: the tree has no ancestor");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(BNK_ERR_CUDA, "indel: no CUDA device"); }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) return fail(BNK_ERR_ARG, "indel: device %d of %d", device, ndev);
+    bnk_indel *h = new (std::nothrow) bnk_indel();
+    if (!h) return fail(BNK_ERR_NOMEM, "indel: out of host memory");
+    h->base = *base;
+    h->tree = const_cast<bnk_tree *>(tree);
+    tree_retain(h->tree);
+    h->K = base->K; h->K1 = base->K + 1; h->n = tree->n; h->n_int = tree->n_int; h->max_cols = max_cols; h->device = device;
+    auto bail = [&](int rc) { indel_free(h); return rc; };
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return bail(fail(BNK_ERR_CUDA, "indel: cudaSetDevice: %s", cudaGetErrorString(guard.err)));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+        return bail(fail(BNK_ERR_CUDA, "indel: device %d is not an sm_100-class GPU", device));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->stream = nullptr; return bail(fail(BNK_ERR_CUDA, "indel: cudaStreamCreate")); }
+    for (auto &e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(BNK_ERR_CUDA, "indel: cudaEventCreate"));
+    // schedule: height levels that are wide enough, then the rest in decreasing index order
+    int hmax = 0;
+    for (int v = 0; v < h->n; v++) hmax = std::max(hmax, tree->height[v]);
+    std::vector<int32_t> width(hmax + 2, 0);
+    for (int v = 0; v < h->n; v++) width[tree->height[v]]++;
+    int wide_h = 0;
+    while (wide_h + 1 <= hmax && width[wide_h + 1] >= LEVEL_MIN_NODES) wide_h++;
+    std::vector<int32_t> nodes;
+    for (int lv = 1; lv <= wide_h; lv++) {
+        const int32_t lo = (int32_t)nodes.size();
+        for (int v = 0; v < h->n; v++) if (tree->height[v] == lv) nodes.push_back(v);
+        h->level_ranges.push_back({lo, (int32_t)nodes.size()});
+    }
+    {
+        const int32_t lo = (int32_t)nodes.size();
+        for (int v = h->n - 1; v >= 0; v--) if (tree->height[v] > wide_h) nodes.push_back(v);
+        h->narrow_range = {lo, (int32_t)nodes.size()};
+    }
+    auto step = [&](int rc) { return rc; };
+    int rc = BNK_OK;
+    if ((rc = step(upload_vec(h->d_first, tree->first, h->stream))) != BNK_OK) return bail(rc);
+    if ((rc = step(upload_vec(h->d_kids, tree->kids, h->stream))) != BNK_OK) return bail(rc);
+    if ((rc = step(upload_vec(h->d_ent, tree->ent_of_node, h->stream))) != BNK_OK) return bail(rc);
+    if ((rc = step(upload_vec(h->d_parent, tree->parent, h->stream))) != BNK_OK) return bail(rc);
+    if ((rc = step(upload_vec(h->d_dist, tree->dist, h->stream))) != BNK_OK) return bail(rc);
+    if ((rc = step(upload_vec(h->d_nodes, nodes, h->stream))) != BNK_OK) return bail(rc);
+    const size_t nc = (size_t)max_cols + 1, K = h->K;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = h->d_A.ensure((size_t)h->n * K * K);
+    if (e == cudaSuccess) e = h->d_del.ensure(h->n);
+    if (e == cudaSuccess) e = h->d_ins.ensure((size_t)h->n * K);
+    if (e == cudaSuccess) e = h->d_obs.ensure((size_t)h->n * nc);
+    if (e == cudaSuccess) e = h->d_msg.ensure((size_t)h->n_int * (K + 1) * nc);
+    if (e == cudaSuccess) e = h->d_eR.ensure((size_t)h->n_int * nc);
+    if (e == cudaSuccess) e = h->d_eG.ensure((size_t)h->n_int * nc);
+    if (e == cudaSuccess) e = h->d_cg.ensure((size_t)h->n_int * nc);
+    if (e == cudaSuccess) e = h->d_logl.ensure(nc);
+    if (e == cudaSuccess) e = h->d_probs.ensure((size_t)h->K1 * h->K1);
+    if (e != cudaSuccess) return bail(fail(e == cudaErrorMemoryAllocation ? BNK_ERR_NOMEM : BNK_ERR_CUDA, "indel: device allocation: %s", cudaGetErrorString(e)));
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(BNK_ERR_CUDA, "indel: upload failed"));
+    *out = h;
+    return BNK_OK;
+}
+
+extern "C" void bnk_indel_destroy(bnk_indel *h) { indel_free(h); }
+
+extern "C" int bnk_indel_set_alignment(bnk_indel *h, int32_t n_cols, const uint8_t *obs)
+{
+    if (!h || !obs) return fail(BNK_ERR_ARG, "indel: null argument");
+    if (n_cols < 1 || n_cols > h->max_cols) return fail(BNK_ERR_ARG, "indel: n_cols %d outside 1..%d", n_cols, h->max_cols);
+    ENTER_DEVICE(h->device);
+    const bnk_tree *t = h->tree;
+    for (int v = 0; v < h->n; v++) {   // validate the extants' rows (a byte >= K would index past a table)
+        if (t->first[v + 1] != t->first[v]) continue;
+        const uint8_t *row = obs + (size_t)v * n_cols;
+        for (int c = 0; c < n_cols; c++)
+            if (row[c] != BNK_NONE && row[c] >= h->K) return fail(BNK_ERR_ARG, "indel: state %d at node %d, column %d (alphabet of %d)", row[c], v, c, h->K);
+    }
+    const size_t nc = (size_t)n_cols + 1;
+    // device layout [node][n_cols + 1]: the extra column is the all-gap column of calcProbAlnGivenTree (:139-158)
+    CUDA_TRY(cudaMemsetAsync(h->d_obs.p, BNK_NONE, (size_t)h->n * nc, h->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_obs.p, nc, obs, n_cols, n_cols, h->n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ncols = n_cols;
+    return BNK_OK;
+}
+
+extern "C" int bnk_indel_set_rates(bnk_indel *h, double mu, double lambda)
+{
+    if (!h) return fail(BNK_ERR_ARG, "indel: null argument");
+    ENTER_DEVICE(h->device);
+    return set_rates(h, mu, lambda);
+}
+
+extern "C" int bnk_indel_column_logl(bnk_indel *h, double rate, double geom, double *out_logl, double *out_sum_or_null)
+{
+    if (!h || !out_logl) return fail(BNK_ERR_ARG, "indel: null argument");
+    ENTER_DEVICE(h->device);
+    TRY(run_sweep(h, rate, geom));
+    std::memcpy(out_logl, h->h_logl.data(), sizeof(double) * h->ncols);
+    if (out_sum_or_null) {
+        double s = 0.0;
+        for (int c = 0; c < h->ncols; c++) s += h->h_logl[c];
+        *out_sum_or_null = s;
+    }
+    return BNK_OK;
+}
+
+extern "C" int bnk_indel_column_priors(bnk_indel *h, double geom, int32_t n_rates, const double *rates, double *out)
+{
+    if (!h || !rates || !out || n_rates < 1) return fail(BNK_ERR_ARG, "indel: invalid argument");
+    ENTER_DEVICE(h->device);
+    for (int r = 0; r < n_rates; r++) {
+        TRY(run_sweep(h, rates[r], geom));
+        for (int c = 0; c < h->ncols; c++) out[(size_t)c * n_rates + r] = h->h_logl[c];   // columnPriors[colIdx][rateIdx]
+    }
+    return BNK_OK;
+}
+
+extern "C" int bnk_indel_aln_logl(bnk_indel *h, double geom, double *out)
+{
+    if (!h || !out) return fail(BNK_ERR_ARG, "indel: null argument");
+    ENTER_DEVICE(h->device);
+    return aln_logl(h, geom, out);
+}
+
+// Minimise.brent (src/smile/math/special/Minimise.java:25-107) over mu = lambda, f = -calcProbAlnGivenTree; the
+// reference evaluates f(v), f(w), f(x) anew in every recursion -- f is deterministic, the values are kept here
+extern "C" int bnk_indel_optimise_mulambda(bnk_indel *h, double min_val, double max_val, double geom, double *out_mulambda,
+                                           int32_t *n_evals_or_null)
+{
+    if (!h || !out_mulambda) return fail(BNK_ERR_ARG, "indel: null argument");
+    if (!(min_val >= 0.0) || !(max_val > min_val)) return fail(BNK_ERR_ARG, "indel: invalid search interval");
+    ENTER_DEVICE(h->device);
+    const int MAX = 500;
+    const double EPS = 10e-6;
+    const double INVPHI = (1.0 + std::sqrt(5.0)) / 2.0 - 1.0;
+    const double RATIO = (3.0 - std::sqrt(5.0)) / 2;
+    std::vector<std::pair<double, double>> seen;
+    int status = BNK_OK;
+    auto f = [&](double x) -> double {
+        for (const auto &s : seen) if (s.first == x) return s.second;
+        double v = 0.0;
+        if (status == BNK_OK) status = set_rates(h, x, x);
+        if (status == BNK_OK) status = aln_logl(h, geom, &v);
+        seen.push_back({x, -v});
+        return -v;
+    };
+    double a = min_val, b = max_val, x = b + INVPHI * (a - b), v = x, w = x, dold = 0, eold = 0, m = 0;
+    for (int i = 0;; i++) {
+        const double fv = f(v), fw = f(w), fx = f(x);
+        if (status != BNK_OK) return status;
+        m = 0.5 * (a + b);
+        if (b - a <= EPS || i > MAX) break;
+        const double r = (x - w) * (fx - fv), tq = (x - v) * (fx - fw), tp = (x - v) * tq - (x - w) * r, tq2 = 2.0 * (tq - r);
+        const double p = tq2 > 0.0 ? -tp : tp, q = tq2 > 0.0 ? tq2 : -tq2;
+        const bool safe = q != 0.0;
+        const double deltax = safe ? p / q : 0.0;
+        const bool parabolic = safe && a < x + deltax && x + deltax < b && std::fabs(deltax) < 0.5 * std::fabs(eold);
+        const double e = parabolic ? dold : (x < m ? b - x : a - x);
+        const double d = parabolic ? deltax : RATIO * e;
+        const double u = x + d;
+        const double fu = f(u);
+        if (status != BNK_OK) return status;
+        if (fu <= fx) {
+            if (u < x) b = x; else a = x;
+            v = w; w = x; x = u;
+        } else {
+            if (u < x) a = u; else b = u;
+            if (fu <= fw || w == x) { v = w; w = u; }
+            else if (fu <= fv || v == x || v == w) { v = u; }
+        }
+        dold = d; eold = e;
+    }
+    *out_mulambda = m;
+    if (n_evals_or_null) *n_evals_or_null = (int32_t)seen.size();
+    return BNK_OK;
+}
+
+extern "C" int bnk_indel_probs(bnk_indel *h, double t, double *out_P, double *out_ksi_gamma_or_null, double *out_F_or_null)
+{
+    if (!h || !out_P) return fail(BNK_ERR_ARG, "indel: null argument");
+    if (!h->model_set) return fail(BNK_ERR_STATE, "indel: no indel rates set (bnk_indel_set_rates)");
+    ENTER_DEVICE(h->device);
+    launch_indel_probs(h->K1, h->gmd(), t, h->d_probs.p, h->stream);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_P, h->d_probs.p, sizeof(double) * h->K1 * h->K1, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (out_ksi_gamma_or_null) {
+        const double ksi = ksi_host(h->gm, t);
+        double gamma = 0.0;
+        if (!(h->gm.mu == 0 && h->gm.lambda == 0)) {
+            const double total = h->gm.mu + h->gm.lambda;
+            gamma = (h->gm.mu / total) * (1 - std::exp(-(total * t)));
+        }
+        out_ksi_gamma_or_null[0] = ksi;
+        out_ksi_gamma_or_null[1] = gamma;
+    }
+    if (out_F_or_null) std::memcpy(out_F_or_null, h->gm.F, sizeof(double) * h->K1);
+    return BNK_OK;
+}
+
+extern "C" double bnk_indel_phase_ms(const bnk_indel *h, int phase)
+{
+    if (!h) return -1.0;
+    return phase == 0 ? h->ms_tables : h->ms_sweep;
+}
+
+extern "C" int64_t bnk_indel_launch_count(const bnk_indel *h) { return h ? h->launches : 0; }
+extern "C" int64_t bnk_indel_device_bytes(const bnk_indel *h) { return h ? h->reg.bytes : 0; }

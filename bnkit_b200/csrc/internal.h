@@ -24,6 +24,19 @@ namespace bnk {
 
 int fail(int code, const char *fmt, ...);  // records the thread's last error, returns code
 
+// bn.ctmc.GapSubstModel on the host: the base alphabet plus the gap state (K1 = K + 1 <= 21)
+constexpr int GAP_MAXK = BNK_MAXK + 1;
+struct GapModelHost {
+    int K1 = 0;
+    double mu = 0, lambda = 0;
+    double F[GAP_MAXK] = {0};
+    double R[GAP_MAXK * GAP_MAXK] = {0};
+    double evec[GAP_MAXK * GAP_MAXK] = {0}, ievec[GAP_MAXK * GAP_MAXK] = {0};
+    double eval[GAP_MAXK] = {0};
+};
+int indel_base_model_by_name(const char *name, bnk_model **out);
+int gap_model_from_base(const bnk_model *base, double mu, double lambda, GapModelHost *g);
+
 int model_from_rates(int K, const double *F, const double *M, bool symmetric, bool normalise, bnk_model **out);
 int model_by_name(const char *name, const double *F_override, bnk_model **out);
 int model_from_eigen(int K, const double *F, const double *evec, const double *ievec,

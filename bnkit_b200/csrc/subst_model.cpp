@@ -10,6 +10,8 @@
 #include <cstring>
 #include <new>
 
+#define BNK_EIG_MAXK (BNK_MAXK + 1)  // + the gap state of bn.ctmc.GapSubstModel
+
 namespace bnk {
 namespace eig {
 #include "subst_eigen.inc"
@@ -25,8 +27,8 @@ namespace data {
 // Matrix.java:42-60: copy, elmhes, eltran, hqr2(dim, 1, dim), luinverse
 static int eigensystem(int n, const double *A, double *evec, double *wr, double *wi, double *ievec)
 {
-    double work[BNK_MAXK * BNK_MAXK];
-    int ordr[BNK_MAXK];
+    double work[BNK_EIG_MAXK * BNK_EIG_MAXK];
+    int ordr[BNK_EIG_MAXK];
     std::memcpy(work, A, sizeof(double) * n * n);
     std::memset(evec, 0, sizeof(double) * n * n);
     eig::elmhes(work, ordr, n);
@@ -118,6 +120,65 @@ int model_by_name(const char *name, const double *F_override, bnk_model **out)
     }
     if (rc == BNK_OK) std::snprintf((*out)->name, sizeof((*out)->name), "%s", name);
     return rc;
+}
+
+// The base model IndelPeeler.optimiseMuLambda builds for a model name (src/asr/IndelPeeler.java:474-503): always
+// new GapSubstModel(F, IRM, alpha, mu, lambda) = symmetric (upper triangle x F) AND normalised -- for JC and Yang
+// that is NOT the model SubstModel.createModel(name) gives (JC: unnormalised; Yang: its Q taken as a full matrix).
+int indel_base_model_by_name(const char *name, bnk_model **out)
+{
+    if (!name || !out) return fail(BNK_ERR_ARG, "model: null argument");
+    int rc;
+    if (!std::strcmp(name, "JC")) {
+        double Fj[4], Qj[16];
+        for (int r = 0; r < 4; r++) {
+            Fj[r] = 1.0 / 4;
+            for (int c = 0; c < 4; c++) Qj[r * 4 + c] = (r != c) ? 1.0 / 4 : 0.0;
+        }
+        rc = model_from_rates(4, Fj, Qj, true, true, out);
+    } else if (!std::strcmp(name, "Yang")) {
+        rc = model_from_rates(4, data::BNK_YANG_F, data::BNK_YANG_Q, true, true, out);
+    } else if (!std::strcmp(name, "LG") || !std::strcmp(name, "JTT") || !std::strcmp(name, "WAG") || !std::strcmp(name, "Dayhoff")) {
+        return model_by_name(name, nullptr, out);   // already symmetric + normalised
+    } else {
+        return fail(BNK_ERR_MODEL, "%s gap model not implemented yet", name);   // IllegalArgumentException, :502
+    }
+    if (rc == BNK_OK) std::snprintf((*out)->name, sizeof((*out)->name), "%s", name);
+    return rc;
+}
+
+// new GapSubstModel(F, IRM, alphabet, mu, lambda) on top of a constructed base model
+// (src/bn/ctmc/GapSubstModel.java:26-44): R_eps = [R - mu I | mu ; lambda * pi | -lambda] (constructIndelR, :61-86),
+// Exp(R_eps), stationary frequencies with the gap entry mu / (mu + lambda) (addGapToStationaryFreqs, :104-131)
+int gap_model_from_base(const bnk_model *base, double mu, double lambda, GapModelHost *g)
+{
+    if (!base || !g) return fail(BNK_ERR_ARG, "gap model: null argument");
+    if (!base->has_R) return fail(BNK_ERR_MODEL, "gap model: the base model was adopted from an eigensystem and has no rate matrix");
+    if (!(mu + lambda >= 0)) return fail(BNK_ERR_ARG, "gap model: mu + lambda must be >= 0");
+    const int K = base->K, K1 = K + 1;
+    g->K1 = K1; g->mu = mu; g->lambda = lambda;
+    std::memset(g->R, 0, sizeof(g->R));
+    for (int i = 0; i < K; i++) {
+        g->R[i * K1 + K] = mu;
+        for (int j = 0; j < K; j++) {
+            g->R[i * K1 + j] = base->R[i * K + j];
+            if (i == j) g->R[i * K1 + j] -= mu;
+        }
+    }
+    for (int j = 0; j < K; j++) g->R[K * K1 + j] = base->F[j] * lambda;
+    g->R[K * K1 + K] = -lambda;
+    double wi[BNK_EIG_MAXK];
+    const int rc = eigensystem(K1, g->R, g->evec, g->eval, wi, g->ievec);
+    if (rc != 0) return fail(BNK_ERR_MODEL, rc == -1 ? "gap model: eigenvalues not converged" : "gap model: singular eigenvector matrix");
+    if (mu + lambda > 0) {
+        const double gapFreq = mu / (mu + lambda);
+        for (int i = 0; i < K; i++) g->F[i] = (1 - gapFreq) * base->F[i];
+        g->F[K] = gapFreq;
+    } else {
+        for (int i = 0; i < K; i++) g->F[i] = base->F[i];
+        g->F[K] = 0.0;
+    }
+    return BNK_OK;
 }
 
 int model_from_eigen(int K, const double *F, const double *evec, const double *ievec,

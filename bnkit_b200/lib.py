@@ -31,7 +31,7 @@ SYMBOLS = [
     "bnk_model_create", "bnk_model_create_custom", "bnk_model_create_from_eigen", "bnk_model_destroy",
     "bnk_model_nstates", "bnk_model_get",
     "bnk_tree_create", "bnk_tree_destroy", "bnk_tree_size", "bnk_tree_n_internal", "bnk_tree_prune_orphans",
-    "bnk_ws_create", "bnk_ws_destroy", "bnk_ws_sync", "bnk_ws_configure", "bnk_ws_launch_count",
+    "bnk_ws_create", "bnk_ws_destroy", "bnk_ws_sync", "bnk_ws_dims", "bnk_ws_configure", "bnk_ws_launch_count",
     "bnk_ws_device_bytes", "bnk_set_rates", "bnk_set_distances", "bnk_probs",
     "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
     "bnk_ws_phase_ms", "bnk_bep_presence",
@@ -40,6 +40,9 @@ SYMBOLS = [
     "bnk_mgpu_create", "bnk_mgpu_destroy", "bnk_mgpu_n_devices", "bnk_mgpu_shard", "bnk_mgpu_set_rates",
     "bnk_mgpu_set_distances", "bnk_mgpu_joint", "bnk_mgpu_marginal", "bnk_mgpu_loglik", "bnk_mgpu_upload",
     "bnk_mgpu_loglik_resident", "bnk_mgpu_reduction", "bnk_mgpu_launch_count",
+    "bnk_indel_base_model", "bnk_indel_create", "bnk_indel_destroy", "bnk_indel_set_alignment", "bnk_indel_set_rates", "bnk_indel_column_logl",
+    "bnk_indel_column_priors", "bnk_indel_aln_logl", "bnk_indel_optimise_mulambda", "bnk_indel_probs",
+    "bnk_indel_phase_ms", "bnk_indel_launch_count", "bnk_indel_device_bytes",
 ]
 EVIDENCE_AUTO, EVIDENCE_LEAVES, EVIDENCE_ANYWHERE = 0, 1, 2
 
@@ -72,6 +75,7 @@ def lib():
     L.bnk_ws_destroy.argtypes = [_vp]
     L.bnk_ws_destroy.restype = None
     L.bnk_ws_sync.argtypes = [_vp]
+    L.bnk_ws_dims.argtypes = [_vp, _ip, _ip, _ip]
     L.bnk_ws_configure.argtypes = [_vp, C.c_int, C.c_int]
     L.bnk_ws_launch_count.argtypes = [_vp]
     L.bnk_ws_launch_count.restype = C.c_int64
@@ -111,6 +115,23 @@ def lib():
     L.bnk_mgpu_reduction.restype = C.c_char_p
     L.bnk_mgpu_launch_count.argtypes = [_vp]
     L.bnk_mgpu_launch_count.restype = C.c_int64
+    L.bnk_indel_base_model.argtypes = [C.c_char_p, C.POINTER(_vp)]
+    L.bnk_indel_create.argtypes = [_vp, _vp, C.c_int32, C.c_int, C.POINTER(_vp)]
+    L.bnk_indel_destroy.argtypes = [_vp]
+    L.bnk_indel_destroy.restype = None
+    L.bnk_indel_set_alignment.argtypes = [_vp, C.c_int32, _bp]
+    L.bnk_indel_set_rates.argtypes = [_vp, C.c_double, C.c_double]
+    L.bnk_indel_column_logl.argtypes = [_vp, C.c_double, C.c_double, _dp, _dp]
+    L.bnk_indel_column_priors.argtypes = [_vp, C.c_double, C.c_int32, _dp, _dp]
+    L.bnk_indel_aln_logl.argtypes = [_vp, C.c_double, _dp]
+    L.bnk_indel_optimise_mulambda.argtypes = [_vp, C.c_double, C.c_double, C.c_double, _dp, _ip]
+    L.bnk_indel_probs.argtypes = [_vp, C.c_double, _dp, _dp, _dp]
+    L.bnk_indel_phase_ms.argtypes = [_vp, C.c_int]
+    L.bnk_indel_phase_ms.restype = C.c_double
+    L.bnk_indel_launch_count.argtypes = [_vp]
+    L.bnk_indel_launch_count.restype = C.c_int64
+    L.bnk_indel_device_bytes.argtypes = [_vp]
+    L.bnk_indel_device_bytes.restype = C.c_int64
     _LIB = L
     return L
 
@@ -144,11 +165,13 @@ def _ptr(x):
 class Model:
     """bnk_model handle <-> bn.ctmc.SubstModel."""
 
-    def __init__(self, name=None, F=None, custom=None, eigen=None):
+    def __init__(self, name=None, F=None, custom=None, eigen=None, indel_base=False):
         L = lib()
         h = _vp()
         self._keep = []
-        if eigen is not None:
+        if indel_base:   # the base model IndelPeeler.optimiseMuLambda builds for a name
+            check(L.bnk_indel_base_model(name.encode(), C.byref(h)))
+        elif eigen is not None:
             K, Fe, evec, ievec, ev = eigen
             arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Fe, evec, ievec, ev)]
             check(L.bnk_model_create_from_eigen(int(K), *[_d(a) for a in arrs], C.byref(h)))
@@ -247,6 +270,11 @@ class Workspace:
     def __init__(self, model, tree, max_cols, device=-1, stream=None):
         self.model, self.tree = model, tree  # keep alive
         h = _vp()
+        # stream=None: a private non-blocking stream.  A caller that hands over torch's DEFAULT stream passes the
+        # handle 0, which is also NULL: map it to cudaStreamLegacy (0x1), the same stream under its explicit name,
+        # so the work is ordered with torch's events / NCCL calls on that stream instead of racing them.
+        if stream is not None and int(stream) == 0:
+            stream = 1
         check(lib().bnk_ws_create(model.h, tree.h, int(max_cols), int(device), stream, C.byref(h)))
         self.h = h
         self.K = model.K
@@ -361,6 +389,69 @@ class Workspace:
 
     def loglik_dev(self, n_cols, d_obs, d_present, d_out_logl, d_out_sum):
         check(lib().bnk_loglik_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _ptr(d_out_logl), _ptr(d_out_sum)))
+
+
+class Indel:
+    """bnk_indel handle: gap-augmented peeling (asr.IndelPeeler under bn.ctmc.GapSubstModel) of one alignment"""
+
+    def __init__(self, model, tree, max_cols, device=-1):
+        self.model, self.tree = model, tree
+        h = _vp()
+        check(lib().bnk_indel_create(model.h, tree.h, int(max_cols), int(device), C.byref(h)))
+        self.h = h
+        self.K, self.n, self.n_cols = model.K, tree.n, 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bnk_indel_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_alignment(self, obs):
+        obs = _as_u8(obs)
+        if obs.ndim != 2 or obs.shape[0] != self.n:
+            raise ValueError("obs must be [n_nodes][n_cols]")
+        check(lib().bnk_indel_set_alignment(self.h, obs.shape[1], obs.ctypes.data_as(_bp)))
+        self.n_cols = obs.shape[1]
+
+    def set_rates(self, mu, lam):
+        check(lib().bnk_indel_set_rates(self.h, float(mu), float(lam)))
+
+    def column_logl(self, rate=1.0, geom=0.01):
+        out = np.empty(self.n_cols)
+        s = C.c_double(0)
+        check(lib().bnk_indel_column_logl(self.h, float(rate), float(geom), _d(out), C.cast(C.byref(s), _dp)))
+        return out, s.value
+
+    def column_priors(self, rates, geom):
+        rates = np.ascontiguousarray(rates, dtype=np.float64)
+        out = np.empty((self.n_cols, len(rates)))
+        check(lib().bnk_indel_column_priors(self.h, float(geom), len(rates), _d(rates), _d(out)))
+        return out
+
+    def aln_logl(self, geom):
+        s = C.c_double(0)
+        check(lib().bnk_indel_aln_logl(self.h, float(geom), C.cast(C.byref(s), _dp)))
+        return s.value
+
+    def optimise_mulambda(self, lo, hi, geom):
+        x = C.c_double(0)
+        ne = C.c_int32(0)
+        check(lib().bnk_indel_optimise_mulambda(self.h, float(lo), float(hi), float(geom), C.cast(C.byref(x), _dp), C.cast(C.byref(ne), _ip)))
+        return x.value, ne.value
+
+    def probs(self, t):
+        K1 = self.K + 1
+        P, kg, F = np.empty((K1, K1)), np.empty(2), np.empty(K1)
+        check(lib().bnk_indel_probs(self.h, float(t), _d(P), _d(kg), _d(F)))
+        return P, kg[0], kg[1], F
+
+    def phase_ms(self, phase):
+        return lib().bnk_indel_phase_ms(self.h, int(phase))
+
+    def launch_count(self):
+        return lib().bnk_indel_launch_count(self.h)
 
 
 class MultiGPU:

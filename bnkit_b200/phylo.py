@@ -666,6 +666,92 @@ class Prediction:
             self._ws = None
 
 
+class GapSubstModel:
+    """bn.ctmc.GapSubstModel (src/bn/ctmc/GapSubstModel.java): a substitution model whose alphabet has the gap
+    state appended, with deletion rate mu and insertion rate lambda (Rivas & Eddy 2008)"""
+
+    def __init__(self, base, mu, lam):
+        self.base = base                      # a SubstModel (its handle carries R and F)
+        self.mu, self.lam = float(mu), float(lam)
+        if self.mu + self.lam < 0:
+            raise ValueError("mu + lambda must be >= 0")
+
+    def getMu(self):
+        return self.mu
+
+    def getLambda(self):
+        return self.lam
+
+    def getName(self):
+        return "GapSubstModel"
+
+    def getDomain(self):
+        return list(self.base.getDomain()) + ["-"]
+
+
+class IndelPeeler:
+    """asr.IndelPeeler's static entry points (src/asr/IndelPeeler.java) over bnk_indel_*: every column's
+    gap-augmented likelihood in one device sweep instead of one thread-pool job per column.
+    `states` is the alignment as Prediction takes it: states[node][col], None = gap, extants' rows only."""
+
+    def __init__(self, tree, states, base, device=-1):
+        self.tree, self.base = tree, base
+        n_cols = len(states[0]) if len(states) else 0
+        dom = {ch: i for i, ch in enumerate(base.getDomain())}
+        obs = np.full((tree.getSize(), n_cols), NONE, dtype=np.uint8)
+        for v in tree.getLeaves():
+            row = states[v]
+            if row is None:
+                continue
+            for c, ch in enumerate(row):
+                if ch is not None:
+                    if ch not in dom:
+                        raise ASRRuntimeException("Invalid character %r for model %s" % (ch, base.getName()))
+                    obs[v, c] = dom[ch]
+        self.obs = obs
+        self.h = lib.Indel(base.handle, tree.handle(), max(n_cols, 1), device)
+        self.h.set_alignment(obs)
+
+    def close(self):
+        self.h.close()
+
+    @staticmethod
+    def computeColumnPriors(tree, states, model, geometricSeqLenParam, rates, device=-1):
+        """double[numCols][numRates]: log P(column | rate) (IndelPeeler.java:93-123)"""
+        p = IndelPeeler(tree, states, model.base, device)
+        try:
+            p.h.set_rates(model.mu, model.lam)
+            return p.h.column_priors(rates, geometricSeqLenParam)
+        finally:
+            p.close()
+
+    @staticmethod
+    def calcProbAlnGivenTree(tree, states, model, geometricSeqLenParam, device=-1):
+        """log P(alignment | tree, model) incl. the normalisation for unobserved all-gap columns (:125-161)"""
+        p = IndelPeeler(tree, states, model.base, device)
+        try:
+            p.h.set_rates(model.mu, model.lam)
+            return p.h.aln_logl(geometricSeqLenParam)
+        finally:
+            p.close()
+
+    @staticmethod
+    def optimiseMuLambda(min_val, max_val, substModelName, tree, geometricSeqLenParam, states, device=-1):
+        """the mu = lambda that maximises calcProbAlnGivenTree, by Brent's method (:469-510); an unknown model
+        name raises ValueError as the reference raises IllegalArgumentException"""
+        try:
+            handle = lib.Model(substModelName, indel_base=True)
+        except lib.BnkError as e:
+            raise ValueError(str(e))
+        base = SubstModel(handle, substModelName, ALPHABETS[substModelName])
+        p = IndelPeeler(tree, states, base, device)
+        try:
+            x, _ = p.h.optimise_mulambda(min_val, max_val, geometricSeqLenParam)
+            return x
+        finally:
+            p.close()
+
+
 def load_alignment(path):
     """FASTA or CLUSTAL -> (names, rows of characters with '-' -> None)   (dat/file/Utils.java:103-138)."""
     names, seqs = [], {}

@@ -126,6 +126,8 @@ int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_cols, int d
                   void *stream, bnk_ws **out);
 void bnk_ws_destroy(bnk_ws *ws);
 int bnk_ws_sync(bnk_ws *ws);
+/* n_nodes of the tree, its ancestors (nodes with children) and the model's states; any output may be NULL */
+int bnk_ws_dims(const bnk_ws *ws, int32_t *n_nodes, int32_t *n_internal, int32_t *n_states);
 /* tuning knobs (0 = automatic): columns per CTA tile, columns per thread */
 int bnk_ws_configure(bnk_ws *ws, int tile_cols, int cols_per_thread);
 /* Where may observed states sit?  AUTO (default) scans the observation matrix on the device in every call: it
@@ -219,6 +221,46 @@ int bnk_mgpu_upload(bnk_mgpu *g, int32_t n_cols, const uint8_t *obs, const uint8
 int bnk_mgpu_loglik_resident(bnk_mgpu *g, double *out_sum);
 const char *bnk_mgpu_reduction(const bnk_mgpu *g);
 int64_t bnk_mgpu_launch_count(const bnk_mgpu *g);
+
+/* ---- gap-augmented peeling: indel-rate likelihoods ----------------------------
+ * What asr.IndelPeeler computes one column at a time on a thread pool (src/asr/IndelPeeler.java, Rivas & Eddy
+ * 2008) under bn.ctmc.GapSubstModel (src/bn/ctmc/GapSubstModel.java): the alphabet gains a gap state, gaps at
+ * extants are evidence (not pruned positions), and the column likelihood sums over residue and gap histories.
+ *   bnk_indel_create          one tree rooted at node 0 + the base substitution model (20 or 4 states, built
+ *                             from a rate matrix: the gap model needs R); max_cols bounds the alignment width
+ *   bnk_indel_set_alignment   obs [n_nodes][n_cols], BNK_NONE = gap; only the extants' rows are read
+ *                             (new POGTree(aln, tree), IndelPeeler.java:540)
+ *   bnk_indel_set_rates       new GapSubstModel(F, IRM, alphabet, mu, lambda) (GapSubstModel.java:26-50)
+ *   bnk_indel_column_logl     IndelPeeler.decorate() (:229-252) for every column at indel rate `rate`
+ *                             (branch time = distance * rate, PhyloBN.java:158); geom = the geometric
+ *                             sequence-length parameter; out_logl [n_cols]; *out_sum = their sum in column order
+ *   bnk_indel_column_priors   IndelPeeler.computeColumnPriors (:93-123): out [n_cols][n_rates]
+ *   bnk_indel_aln_logl        IndelPeeler.calcProbAlnGivenTree (:125-161): sum of the columns at rate 1
+ *                             + probExtraCol (:163-193) - log(1 - P(all-gap column))
+ *   bnk_indel_optimise_mulambda  IndelPeeler.optimiseMuLambda (:469-510): Minimise.brent over mu = lambda in
+ *                             [min_val, max_val] (src/smile/math/special/Minimise.java:25-107); *n_evals = distinct
+ *                             likelihood evaluations (each = new model + one sweep of all columns)
+ *   bnk_indel_probs           test probe: P_eps(t) [(K+1)][(K+1)] = GapSubstModel.getProbs(t), {ksiT(t), gammaT(t)},
+ *                             the K+1 stationary frequencies
+ *   bnk_indel_phase_ms        CUDA-event time of the last sweep: 0 tables, 1 peeling kernels
+ *   bnk_indel_base_model      the base model optimiseMuLambda builds from a model name (:474-503): F and IRM of
+ *                             the named matrix, always symmetric + normalised (differs from bnk_model_create for
+ *                             "JC" and "Yang"); unknown names -> BNK_ERR_MODEL (IllegalArgumentException) */
+typedef struct bnk_indel bnk_indel;
+int bnk_indel_base_model(const char *name, bnk_model **out);
+int bnk_indel_create(const bnk_model *base, const bnk_tree *t, int32_t max_cols, int device, bnk_indel **out);
+void bnk_indel_destroy(bnk_indel *h);
+int bnk_indel_set_alignment(bnk_indel *h, int32_t n_cols, const uint8_t *obs);
+int bnk_indel_set_rates(bnk_indel *h, double mu, double lambda);
+int bnk_indel_column_logl(bnk_indel *h, double rate, double geom, double *out_logl, double *out_sum_or_null);
+int bnk_indel_column_priors(bnk_indel *h, double geom, int32_t n_rates, const double *rates, double *out);
+int bnk_indel_aln_logl(bnk_indel *h, double geom, double *out);
+int bnk_indel_optimise_mulambda(bnk_indel *h, double min_val, double max_val, double geom, double *out_mulambda,
+                                int32_t *n_evals_or_null);
+int bnk_indel_probs(bnk_indel *h, double t, double *out_P, double *out_ksi_gamma_or_null, double *out_F_or_null);
+double bnk_indel_phase_ms(const bnk_indel *h, int phase);
+int64_t bnk_indel_launch_count(const bnk_indel *h);
+int64_t bnk_indel_device_bytes(const bnk_indel *h);
 
 /* ---- instrumentation ------------------------------------------------------------------ */
 /* CUDA-event time (ms) of the kernels of the most recent *_dev / host call, by phase:

@@ -47,4 +47,37 @@ public final class NativeInference {
     /** IdxTree.getPrunedIndex(pruneMe, true) as a mask transform; in and out may be the same buffer. */
     static native void pruneOrphans(long tree, int nCols, ByteBuffer presentIn, ByteBuffer presentOut);
     static native void destroy(long model, long tree, long ws);
+
+    // ---- Prediction.PredictByBidirEdgeParsimony incl. the ancestors' POGs (src/asr/Prediction.java:1443-1590) ----
+    /** as bepPresence, and returns a handle on every ancestor's edge list (a bnk_pogs*). */
+    static native long bepInfer(long tree, int nCols, ByteBuffer occupancy, int device, ByteBuffer present);
+    static native int pogEdgeCount(long pogs, int branchPointIndex);
+    /** edges sorted by (from, to); from = -1 start, to = nCols end; flags bit 0 / 1 = BidirEdge forward / backward. */
+    static native void pogEdges(long pogs, int branchPointIndex, int[] from, int[] to, ByteBuffer flags);
+    static native void pogsDestroy(long pogs);
+
+    // ---- every device of the node behind one handle: the GRASP.NTHREADS knob over GPUs (ThreadedDecorators.java:28-72) ----
+    /** nDevices = 0: all visible devices. Columns are split into contiguous blocks, one per device. Returns a bnk_mgpu*. */
+    static native long mgpuCreate(long model, long tree, int maxCols, int nDevices);
+    static native void mgpuSetRates(long mgpu, int nCols, double[] ratesOrNull);
+    static native void mgpuJoint(long mgpu, int nNodes, int nCols, ByteBuffer obs, ByteBuffer presentOrNull, ByteBuffer outState);
+    static native void mgpuMarginal(long mgpu, int nNodes, int nStates, int nCols, ByteBuffer obs, ByteBuffer presentOrNull,
+                                    int[] queryNodes, DoubleBuffer outPost, double[] outLoglOrNull);
+    /** sum over all columns (per-device sums all-reduced); outLogl may be null. */
+    static native double mgpuLogLik(long mgpu, int nNodes, int nCols, ByteBuffer obs, ByteBuffer presentOrNull, double[] outLoglOrNull);
+    static native void mgpuDestroy(long mgpu);
+
+    // ---- asr.IndelPeeler under bn.ctmc.GapSubstModel (src/asr/IndelPeeler.java) ----
+    /** the base model optimiseMuLambda builds for a name (:474-503); IllegalArgumentException for unknown names. */
+    static native long indelBaseModel(String substModelName);
+    /** aln: direct ByteBuffer n_nodes * nCols, 255 = gap, extants' rows only. Returns a bnk_indel*. */
+    static native long indelCreate(long baseModel, long tree, int nCols, ByteBuffer aln, int device);
+    static native void indelSetRates(long indel, double mu, double lambda);
+    /** computeColumnPriors: out[col * rates.length + rate]. */
+    static native void indelColumnPriors(long indel, double geometricSeqLenParam, int nCols, double[] rates, double[] out);
+    /** calcProbAlnGivenTree at the rates last set. */
+    static native double indelAlnLogl(long indel, double geometricSeqLenParam);
+    /** optimiseMuLambda: Brent over mu = lambda in [minVal, maxVal]. */
+    static native double indelOptimiseMuLambda(long indel, double minVal, double maxVal, double geometricSeqLenParam);
+    static native void indelDestroy(long indel);
 }

@@ -94,6 +94,30 @@ int om_brute(const om_model *m, int n, const int *parent, const double *dist,
              const uint8_t *present, const uint8_t *obs, double rate, long max_assign,
              uint8_t *best_state, double *best_p, double *post, double *total_p);
 
+/* ---- gap-augmented model + extended peeling (bnk_indel.c: GapSubstModel, asr.IndelPeeler) ---- */
+typedef struct om_gap_model om_gap_model;
+/* new GapSubstModel(F, IRM, alphabet, mu, lambda, ...) on top of an already constructed base model */
+om_gap_model *om_gap_model_create(const om_model *base, double mu, double lambda);
+void om_gap_model_free(om_gap_model *g);
+int om_gap_nstates(const om_gap_model *g); /* residues + 1 */
+void om_gap_get(const om_gap_model *g, double *R, double *F, double *evec, double *ievec, double *eval);
+void om_gap_getprobs(const om_gap_model *g, double t, double *P); /* (K+1)^2, P[parent][child] */
+double om_gap_ksi(const om_gap_model *g, double t);
+double om_gap_gamma(const om_gap_model *g, double t);
+double om_logsumexp(const double *a, int n);
+double om_logm1exp(double x);
+/* IndelPeeler.decorate for every column; obs [node][col], OM_NONE = gap (childless rows only) */
+int om_indel_column_logl(const om_gap_model *g, int n, const int *parent, const double *dist, int ncols,
+                         const uint8_t *obs, double rate, double geom, double *out_logl, int nthreads);
+double om_indel_prob_extra_col(const om_gap_model *g, int n, const int *parent, const double *dist, double geom);
+/* IndelPeeler.calcProbAlnGivenTree */
+int om_indel_aln_logl(const om_gap_model *g, int n, const int *parent, const double *dist, int ncols,
+                      const uint8_t *obs, double geom, double *out, int nthreads);
+/* IndelPeeler.optimiseMuLambda (Minimise.brent over mu = lambda); n_evals = distinct likelihood evaluations */
+double om_indel_optimise_mulambda(const om_model *base, int n, const int *parent, const double *dist, int ncols,
+                                  const uint8_t *obs, double geom, double min_val, double max_val, int *n_evals,
+                                  int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

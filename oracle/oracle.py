@@ -57,6 +57,21 @@ def lib():
         L.om_fast_joint.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_int, _bp, _bp, _dp, _bp, _dp, C.c_int]
         L.om_fast_marginal.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_int, _bp, _bp, _dp, _dp, _dp, C.c_int]
         L.om_brute.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _bp, _bp, C.c_double, C.c_long, _bp, _dp, _dp, _dp]
+        L.om_gap_model_create.restype = C.c_void_p; L.om_gap_model_create.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.om_gap_model_free.argtypes = [C.c_void_p]
+        L.om_gap_nstates.argtypes = [C.c_void_p]
+        L.om_gap_get.argtypes = [C.c_void_p] + [_dp] * 5
+        L.om_gap_getprobs.argtypes = [C.c_void_p, C.c_double, _dp]
+        for f in (L.om_gap_ksi, L.om_gap_gamma):
+            f.restype = C.c_double; f.argtypes = [C.c_void_p, C.c_double]
+        L.om_logsumexp.restype = C.c_double; L.om_logsumexp.argtypes = [_dp, C.c_int]
+        L.om_logm1exp.restype = C.c_double; L.om_logm1exp.argtypes = [C.c_double]
+        L.om_indel_column_logl.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_int, _bp, C.c_double, C.c_double, _dp, C.c_int]
+        L.om_indel_prob_extra_col.restype = C.c_double
+        L.om_indel_prob_extra_col.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_double]
+        L.om_indel_aln_logl.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_int, _bp, C.c_double, _dp, C.c_int]
+        L.om_indel_optimise_mulambda.restype = C.c_double
+        L.om_indel_optimise_mulambda.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_int, _bp, C.c_double, C.c_double, C.c_double, _ip, C.c_int]
         _LIB = L
     return _LIB
 
@@ -202,3 +217,78 @@ def ve_loglik(model, parent, dist, obs, present=None, rate=1.0):
                             C.byref(out))
     assert rc == 0, rc
     return out.value
+
+
+class GapModel:
+    """bn.ctmc.GapSubstModel over a base Model: K residues + the gap state (oracle/bnk_indel.c)"""
+
+    def __init__(self, base, mu, lam):
+        self.base = base
+        self.K1 = base.K + 1
+        self.mu, self.lam = float(mu), float(lam)
+        self.h = lib().om_gap_model_create(base.h, self.mu, self.lam)
+        if not self.h:
+            raise ValueError("gap model: eigen-decomposition failed or mu + lambda < 0")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().om_gap_model_free(self.h)
+            self.h = None
+
+    def parts(self):
+        K1 = self.K1
+        R, ev, iev = np.zeros((K1, K1)), np.zeros((K1, K1)), np.zeros((K1, K1))
+        F, ew = np.zeros(K1), np.zeros(K1)
+        lib().om_gap_get(self.h, _d(R), _d(F), _d(ev), _d(iev), _d(ew))
+        return {"R": R, "F": F, "evec": ev, "ievec": iev, "eval": ew}
+
+    def probs(self, t):
+        P = np.zeros((self.K1, self.K1))
+        lib().om_gap_getprobs(self.h, float(t), _d(P))
+        return P
+
+    def ksi(self, t):
+        return lib().om_gap_ksi(self.h, float(t))
+
+    def gamma(self, t):
+        return lib().om_gap_gamma(self.h, float(t))
+
+
+def logsumexp(a):
+    a = _arr(a, np.float64)
+    return lib().om_logsumexp(_d(a), len(a))
+
+
+def logm1exp(x):
+    return lib().om_logm1exp(float(x))
+
+
+def indel_column_logl(gm, parent, dist, obs, rate=1.0, geom=0.01, nthreads=1):
+    """IndelPeeler.decorate for every column of obs [node][col] (NONE = gap)"""
+    parent = _arr(parent, np.int32); dist = _arr(dist, np.float64); obs = _arr(obs, np.uint8)
+    out = np.zeros(obs.shape[1])
+    rc = lib().om_indel_column_logl(gm.h, len(parent), _i(parent), _d(dist), obs.shape[1], _b(obs), float(rate), float(geom), _d(out), int(nthreads))
+    assert rc == 0
+    return out
+
+
+def indel_prob_extra_col(gm, parent, dist, geom):
+    parent = _arr(parent, np.int32); dist = _arr(dist, np.float64)
+    return lib().om_indel_prob_extra_col(gm.h, len(parent), _i(parent), _d(dist), float(geom))
+
+
+def indel_aln_logl(gm, parent, dist, obs, geom, nthreads=1):
+    """IndelPeeler.calcProbAlnGivenTree"""
+    parent = _arr(parent, np.int32); dist = _arr(dist, np.float64); obs = _arr(obs, np.uint8)
+    out = C.c_double(0)
+    rc = lib().om_indel_aln_logl(gm.h, len(parent), _i(parent), _d(dist), obs.shape[1], _b(obs), float(geom), C.cast(C.byref(out), _dp), int(nthreads))
+    assert rc == 0
+    return out.value
+
+
+def indel_optimise_mulambda(base, parent, dist, obs, geom, lo, hi, nthreads=1):
+    """IndelPeeler.optimiseMuLambda: (mu = lambda at the optimum, number of distinct likelihood evaluations)"""
+    parent = _arr(parent, np.int32); dist = _arr(dist, np.float64); obs = _arr(obs, np.uint8)
+    ne = C.c_int(0)
+    m = lib().om_indel_optimise_mulambda(base.h, len(parent), _i(parent), _d(dist), obs.shape[1], _b(obs), float(geom), float(lo), float(hi), C.byref(ne), int(nthreads))
+    return m, ne.value

@@ -11,6 +11,8 @@ struct JNINativeInterface_ {
     jclass (*FindClass)(JNIEnv *, const char *);
     jint (*ThrowNew)(JNIEnv *, jclass, const char *);
     void *(*GetDirectBufferAddress)(JNIEnv *, jobject);
+    jlong (*GetDirectBufferCapacity)(JNIEnv *, jobject);
+    jboolean (*ExceptionCheck)(JNIEnv *);
     const char *(*GetStringUTFChars)(JNIEnv *, jstring, jboolean *);
     void (*ReleaseStringUTFChars)(JNIEnv *, jstring, const char *);
     jdouble *(*GetDoubleArrayElements)(JNIEnv *, jdoubleArray, jboolean *);
