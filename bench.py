@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the C3b / C4 / C5 sub-results")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--sub", default="c3b,c4,c5", help="which sub-results to run")
+    ap.add_argument("--sub", default="c3b,c4,c5,indel", help="which sub-results to run")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: libraries that write to file descriptor 1 on their own (NCCL prints
@@ -632,6 +632,72 @@ def main():
                           "gathered_shape_ok": bool(ok_shape)}
             s5.close()
             del s5
+        elif name == "indel":
+            # section 8 f-3, the reference's real optimisation loop (IndelPeeler.optimiseMuLambda): per evaluation a new
+            # GapSubstModel (host eigensystem 21 x 21), per-branch tables, the gap-augmented peel of the rank's column
+            # block at C3a size with 30 % clade-wise gaps, and the all-reduce of the per-rank sums
+            from bnkit_b200 import synth
+            lo, hi = bd.shard_columns(obs.shape[1], world, rank)
+            aln = np.ascontiguousarray(obs[:, lo:hi]).copy()
+            leafm = np.ones(len(parent), bool)
+            leafm[parent[parent >= 0]] = False
+            grng = np.random.default_rng(11 + lo)
+            size = np.ones(len(parent), np.int64)
+            for v in range(len(parent) - 1, 0, -1):
+                size[parent[v]] += size[v]
+            for cidx in range(aln.shape[1]):   # whole clades lose the column until ~30 % of the extants are gaps
+                gaps = 0
+                while gaps < 0.3 * leafm.sum():
+                    v = int(grng.integers(1, len(parent)))
+                    if size[v] > len(parent) // 8:
+                        continue
+                    aln[v:v + size[v], cidx] = 255
+                    gaps += (size[v] + 1) // 2
+            tree_i = lib.Tree(parent, dist)
+            hnd = lib.Indel(lib.Model(model_name), tree_i, max(aln.shape[1], 1))
+            hnd.set_alignment(aln)
+            geom = 1.0 / 3000.0
+            red = torch.zeros(1, dtype=torch.float64, device=dev)
+            it = [0]
+            last = [0.0]
+
+            def evaluate_indel():
+                it[0] += 1
+                hnd.set_rates(0.02 + 0.001 * (it[0] % 5), 0.02 + 0.001 * (it[0] % 5))
+                _, ssum = hnd.column_logl(1.0, geom)
+                red[0] = ssum
+                if world > 1:
+                    dist_.all_reduce(red, op=dist_.ReduceOp.SUM)
+                last[0] = float(red[0])
+            evals = max(5, min(args.steps, 10))
+            l0 = hnd.launch_count()
+            ms = timed_steps(torch, dist_, world, evaluate_indel, 3, evals)
+            sweep_ms, tab_ms = hnd.phase_ms(1), hnd.phase_ms(0)
+            (ms, sweep_ms) = max_over_ranks(torch, dist_, world, dev, [ms, sweep_ms])
+            par = None
+            if rank == 0 and not args.no_parity:
+                from oracle import oracle as O
+                O.build()
+                selc = np.linspace(0, aln.shape[1] - 1, 12).astype(int)
+                hnd.set_rates(0.02, 0.02)
+                got, _ = hnd.column_logl(1.0, geom)
+                want = O.indel_column_logl(O.GapModel(O.Model(model_name), 0.02, 0.02), parent, dist, np.ascontiguousarray(aln[:, selc]), 1.0, geom, nthreads=threads)
+                par = {"cols": int(len(selc)), "logl_max_rel": float(np.max(np.abs(got[selc] - want) / np.abs(want))),
+                       "against": "oracle/bnk_indel.c (IndelPeeler restated in log space), same inputs"}
+            ni = int(tree_i.n_internal)
+            # algorithmic bytes per (ancestor, column): the 21-entry message + two exponents + the all-gap flag, written
+            # once and read once by the parent
+            ibytes = 2.0 * (21 * 8 + 9) * ni * (aln.shape[1] + 1)
+            subs["indel"] = {"workload": "IndelPeeler.optimiseMuLambda evaluations on C3a with 30 % clade-wise gaps: new GapSubstModel + tables + "
+                                         "gap-augmented peel of all columns + all-reduce(sum) per evaluation",
+                             "cols_per_gpu": int(aln.shape[1]), "evaluations": evals, "ms_per_evaluation": ms / evals,
+                             "updates_per_s": float(ni) * obs.shape[1] / (ms / evals * 1e-3),
+                             "phase_ms": {"tables": round(float(tab_ms), 4), "peel": round(float(sweep_ms), 4)},
+                             "roofline_frac_peel_rank0": ibytes / 1e9 / (sweep_ms * 1e-3) / peak if sweep_ms > 0 else None,
+                             "gpu_launches_per_evaluation": int((hnd.launch_count() - l0) // (evals + 3)),
+                             "sum_logl": last[0], "parity": par}
+            hnd.close()
+            del hnd, aln
 
     if rank == 0:
         if subs:

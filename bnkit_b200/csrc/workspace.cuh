@@ -146,7 +146,7 @@ struct bnk_ws {
     int mw = 0;                            // consumer warps per CTA of the DMMA variants
     bool mma_down = false;                 // BNK_MMA_DOWN=1: the down-sweep on DMMA too (measured slower: 12.7 vs 11.7 ms on C3b)
     int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
-    int walker_mode = 0;                   // BNK_WALKER: 0 auto (lane walker where eligible), 1 lean CTA walker,
+    int walker_mode = 0;                   // BNK_WALKER: 0 auto (= warp-tiled + DMMA), 4 lane walker (sweeps_lane.cu), 1 lean CTA walker,
                                            // 2 warp-tiled with the scalar sum-product kernels (no DMMA), 3 warp-tiled (r1 default)
     int cfg_xw = 0, cfg_xns = 0, cfg_xc = 0;  // BNK_WARP_W / BNK_WARP_NS / BNK_WARP_C (tuning knobs, tests)
     bool no_cherry = false;                // BNK_NO_CHERRY=1: height-1 level through the plain level kernel (A/B, tests)

@@ -104,6 +104,9 @@ class IdxTree:
         if ancids is None:
             ancids = {v: k for k, v in enumerate(i for i in range(n) if self.children[i])}
         self.ancid = dict(ancids)
+        # which branch points carry a distance (BranchPoint.getDistance throws for the others, so Newick.sprint
+        # leaves ':d' out): all of them when built from arrays / JSON; from Newick text, those that had one
+        self.has_distance = [True] * n
         self._handle = None
 
     # ---- construction ----
@@ -122,11 +125,26 @@ class IdxTree:
     def fromNewick(text):
         """Newick -> IdxTree.  Ancestors are named N0, N1, ... in depth-first order unless labelled;
         a distance of exactly 0.0 becomes 1e-5 (Newick.java:54-56, :103-105)."""
-        s = "".join(text.split())
+        # white space is dropped outside quoted labels and [..] blocks (Newick.parse keeps those verbatim, :170-203)
+        buf, q = [], None
+        for ch in text:
+            if q is None:
+                if ch in "'[":
+                    q = "'" if ch == "'" else "]"
+                    buf.append(ch)
+                elif not ch.isspace():
+                    buf.append(ch)
+            else:
+                buf.append(ch)
+                if ch == q:
+                    q = None
+        if q is not None:
+            raise RuntimeError("Non-matched quotes, about here: " + "".join(buf)[-20:] if q == "'" else "Non-matched block, about here: " + "".join(buf)[-20:])
+        s = "".join(buf)
         if s.endswith(";"):
             s = s[:-1]
         parents, dists, labels = [], [], []
-        named = {}
+        named, with_dist = {}, set()
         pos = 0
         anc = [0]
 
@@ -151,10 +169,24 @@ class IdxTree:
                         pos += 1
                         break
                     raise ValueError("Newick: expected ',' or ')' at %d" % pos)
-            start = pos
+            name = ""
             while pos < len(s) and s[pos] not in ",():":
-                pos += 1
-            name = s[start:pos]
+                if s[pos] == "'":                      # a quoted label: taken verbatim without the quotes
+                    end = s.index("'", pos + 1)
+                    name += s[pos + 1:end]
+                    pos = end + 1
+                elif s[pos] == "[":                    # a block: label="..." inside it, else its content (:186-194)
+                    end = s.index("]", pos + 1)
+                    blk = s[pos:end + 1]
+                    k = blk.find('label="')
+                    if k >= 0:
+                        name = blk[k + 7:k + 7 + blk[k + 7:].index('"')]
+                    elif not name:
+                        name = blk[1:-1]
+                    pos = end + 1
+                else:
+                    name += s[pos]
+                    pos += 1
             if pos < len(s) and s[pos] == ":":
                 pos += 1
                 start = pos
@@ -165,6 +197,7 @@ class IdxTree:
                 except ValueError:
                     raise RuntimeError("A distance value couldn't be parsed as a number. The value is \"%s\"" % s[start:pos])
                 dists[idx] = 0.00001 if d == 0.0 else d
+                with_dist.add(idx)
             labels[idx] = name if name else ("N%d" % my_anc if internal else "")
             if internal:
                 named[idx] = bool(name)
@@ -200,7 +233,9 @@ class IdxTree:
             ancids[idx] = count
             taken.add(count)
             count += 1
-        return IdxTree(parents, dists, labels, ancids)
+        t = IdxTree(parents, dists, labels, ancids)
+        t.has_distance = [i in with_dist for i in range(len(parents))]
+        return t
 
     # ---- accessors (IdxTree.java) ----
     def getSize(self):
@@ -585,6 +620,19 @@ class Prediction:
         ids = sorted(pogs, key=lambda k: (0, int(k)) if str(k).isdigit() else (1, str(k)))
         return _pog.fasta_text(["N" + str(k) for k in ids], [self.getSequence(k, mode, gappy) for k in ids])
 
+    def ancestorsClustal(self, mode):
+        """the same sequences in CLUSTAL format (asr.GRASP -of CLUSTAL, dat.file.AlnWriter.save :92-120)"""
+        from . import files
+        pogs = self.getAncestors(mode)
+        ids = sorted(pogs, key=lambda k: (0, int(k)) if str(k).isdigit() else (1, str(k)))
+        return files.clustal_text(["N" + str(k) for k in ids], [self.getSequence(k, mode, True) for k in ids])
+
+    def treeNewick(self, ancestor_labels=True):
+        """the tree as asr.GRASP writes <prefix>_ancestors.nwk: Newick.save(tree, file, MODE_ANCESTOR) -- ancestors
+        labelled N<number> so that the FASTA / TSV outputs can be matched to branch points"""
+        from . import files
+        return files.newick_text(self.tree, files.NEWICK_ANCESTOR if ancestor_labels else files.NEWICK_DEFAULT)
+
     def distribTsv(self, ancID, model):
         """the text of <prefix>_N<id>.tsv (GRASP's DISTRIB format, src/asr/GRASP.java:599-630)"""
         bpidx = self.getBranchpointIndex(ancID)
@@ -752,40 +800,18 @@ class IndelPeeler:
             p.close()
 
 
-def load_alignment(path):
-    """FASTA or CLUSTAL -> (names, rows of characters with '-' -> None)   (dat/file/Utils.java:103-138)."""
-    names, seqs = [], {}
-    with open(path) as fh:
-        first = fh.readline()
-        fh.seek(0)
-        if first.startswith(">"):
-            cur = None
-            for line in fh:
-                line = line.strip()
-                if not line:
-                    continue
-                if line.startswith(">"):
-                    cur = line[1:].split()[0]
-                    names.append(cur)
-                    seqs[cur] = []
-                else:
-                    seqs[cur].append(line)
-        else:  # CLUSTAL
-            for line in fh:
-                if not line.strip() or line.startswith("CLUSTAL") or line[0] in " \t":
-                    continue
-                parts = line.split()
-                if len(parts) < 2:
-                    continue
-                if parts[0] not in seqs:
-                    names.append(parts[0])
-                    seqs[parts[0]] = []
-                seqs[parts[0]].append(parts[1])
-    rows = []
-    for nm in names:
-        s = "".join(seqs[nm])
-        rows.append([None if ch == "-" else ch for ch in s])
-    return names, rows
+def load_alignment(path, alphabet=None):
+    """FASTA or CLUSTAL -> (names, rows of characters with '-' -> None)   (dat/file/Utils.java:103-138); with an
+    alphabet (a model name or a string of symbols) unknown residues are an error as in the reference's readers"""
+    from . import files
+    if alphabet is None:
+        alphabet = "ABCDEFGHIJKLMNOPQRSTUVWXYZ*."      # harness use: no validation beyond the format
+    elif alphabet in ALPHABETS:
+        alphabet = ALPHABETS[alphabet]
+    try:
+        return files.loadAlignment(path, alphabet)
+    except files.ASRException as e:
+        raise ASRRuntimeException(str(e))
 
 
 def load_rates(path):

@@ -320,3 +320,20 @@ def test_gpu_c2_outputs_equal_the_oracle_chain(bnk, oracle):
     for v in tree.getAncestors():
         assert pred.getConsensus(v) == want.getConsensus(v)
     pred.close()
+
+
+def test_clustal_and_newick_outputs_of_a_prediction(oracle):
+    """asr.GRASP's other output formats over the same consensus sequences: CLUSTAL (AlnWriter) and the tree with
+    ancestors labelled N<number> (Newick.save MODE_ANCESTOR)"""
+    from bnkit_b200.files import loadAlignment
+    from bnkit_b200.phylo import IdxTree, Prediction
+    fx, tree, pred = _oracle_prediction("c1_66.json", oracle, "JTT")
+    aln = pred.ancestorsClustal(Prediction.JOINT)
+    names, rows = loadAlignment(aln, AA, is_text=True)
+    assert names[:3] == ["N0", "N1", "N2"] and rows[0] == [None, None, "A", None, "H"]
+    fa_names, fa_rows = loadAlignment(pred.ancestorsFasta(Prediction.JOINT), AA, is_text=True)
+    assert (fa_names, fa_rows) == (names, rows)
+    nwk = pred.treeNewick()
+    back = IdxTree.fromNewick(nwk)
+    assert np.array_equal(back.parent, tree.parent) and [back.getID(i) for i in back.getAncestors()] == [tree.getID(i) for i in tree.getAncestors()]
+    assert np.allclose(back.distance[1:], tree.distance[1:], rtol=0, atol=0)

@@ -48,4 +48,15 @@ cases = [  # (pruned indices, size delta, roots without orphan removal, size equ
 fix = {"source": "test/dat/phylo/IdxTreeTest.java:15-56 on test/resources/default.nwk",
        "parents": t.toJSON()["Parents"], "cases": [{"prune": c[0], "removed": c[1], "roots": c[2], "same_size_with_orphan_removal": c[3]} for c in cases]}
 (OUT / "idxtree_prune.json").write_text(json.dumps(fix))
+# small text files of the reference's own test resources, verbatim: golden vectors for the readers / writers
+# (test/dat/phylo/TreeTest.java:99-121 writes saveme.* and default.anwk with Newick.save)
+files = {}
+for rel in ("test/resources/saveme.nwk", "test/resources/saveme.anwk", "test/resources/saveme.snwk",
+            "test/resources/default.nwk", "test/resources/default.anwk", "test/resources/default.aln",
+            "test/resources/input_test_aln_diff_length_4.aln", "test/resources/input_test_aln_diff_length_4.nwk",
+            "test/resources/basic_5.aln"):
+    files[rel] = (REF / rel).read_text()
+files["data/66.aln"] = (REF / "data" / "66.aln").read_text()
+files["data/66.nwk"] = (REF / "data" / "66.nwk").read_text()
+(OUT / "reference_text_files.json").write_text(json.dumps(files))
 print("wrote", [p.name for p in OUT.iterdir()])
