@@ -22,6 +22,7 @@ UNITS = [
     ("indel_tables.cu", ["-fmad=false"]),
     ("indel.cu", []),
     ("bep.cu", []),
+    ("bep_reach.cu", []),
     ("bep_api.cu", []),
     ("api.cu", []),
     ("multi.cu", []),

@@ -34,4 +34,11 @@ cudaError_t bep_launch_sweeps(const BepArgs &a, int W, cudaStream_t st);  // for
 cudaError_t bep_launch_sweeps_levels(const BepArgs &a, int W, const int32_t *d_nodes, const int32_t *level_off, int n_levels,
                                      cudaStream_t st);
 
+// bep_reach.cu: graph assembly on the device (first pass: instance k = c + 1 forward, nPos + 1 + c backward)
+cudaError_t bep_launch_reach(const uint32_t *B, const int32_t *dict, const int32_t *nsym, int mx, int n_int, int n_inst, int n_pos, int W,
+                             uint32_t *A1, uint32_t *Z, uint8_t *contig, cudaStream_t st);
+cudaError_t bep_launch_rows(const uint8_t *obs, const int32_t *ent_of_node, const uint32_t *Z, int n_nodes, int n_int, int n_pos,
+                            uint8_t *present, cudaStream_t st);
+cudaError_t bep_launch_gather(const uint32_t *B, const int32_t *rows, int n_rows, size_t row_words, uint32_t *out, cudaStream_t st);
+
 }  // namespace bnk

@@ -191,12 +191,65 @@ void parallel_slices(int n_items, F fn)
     for (auto &x : th) x.join();
 }
 
+// a device buffer that keeps its allocation between calls (alloc = "make room for n elements")
 template <typename T>
 struct Dev {
     T *p = nullptr;
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
-    ~Dev() { if (p) cudaFree(p); }
+    size_t cap = 0;  // elements
+    cudaError_t alloc(size_t n)
+    {
+        n = std::max<size_t>(n, 1);
+        if (n <= cap) return cudaSuccess;
+        drop();
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = n;
+        return cudaSuccess;
+    }
+    void drop() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void trim(size_t max_bytes) { if (cap * sizeof(T) > max_bytes) drop(); }
 };
+
+// Per-device scratch that survives the call: stream, events and every buffer up to KEEP_BYTES.  At the sizes of the
+// reference's own data (C1: 66 x 5, C2: 39 x 1,307) a call used to be all fixed cost -- ~20 cudaMalloc, a stream,
+// page-locked staging -- and that cost is now paid once per process; large alignments give their memory back.
+struct Pinned {  // page-locked staging for device->host copies, kept between calls up to KEEP_BYTES
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void trim(size_t max_bytes) { if (cap > max_bytes) { cudaFreeHost(p); p = nullptr; cap = 0; } }
+};
+
+struct BepScratch {
+    std::mutex mu;
+    Pinned pin_dict, pin_opt;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Dev<uint8_t> d_obs, d_fwd, d_symmap, d_contig, d_present;
+    Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag, d_level_nodes, d_rows;
+    Dev<uint32_t> d_A, d_B, d_A1, d_Z, d_compact;
+    static constexpr size_t KEEP_BYTES = (size_t)64 << 20;
+    void trim()
+    {
+        d_obs.trim(KEEP_BYTES); d_fwd.trim(KEEP_BYTES); d_symmap.trim(KEEP_BYTES); d_contig.trim(KEEP_BYTES); d_present.trim(KEEP_BYTES);
+        d_leaf_nodes.trim(KEEP_BYTES); d_leaf_of_node.trim(KEEP_BYTES); d_ent.trim(KEEP_BYTES); d_parent.trim(KEEP_BYTES);
+        d_first.trim(KEEP_BYTES); d_kids.trim(KEEP_BYTES); d_nxt.trim(KEEP_BYTES); d_prv.trim(KEEP_BYTES); d_inst_e.trim(KEEP_BYTES);
+        d_dict.trim(KEEP_BYTES); d_nsym.trim(KEEP_BYTES); d_flag.trim(KEEP_BYTES); d_level_nodes.trim(KEEP_BYTES); d_rows.trim(KEEP_BYTES);
+        d_A.trim(KEEP_BYTES); d_B.trim(KEEP_BYTES); d_A1.trim(KEEP_BYTES); d_Z.trim(KEEP_BYTES); d_compact.trim(KEEP_BYTES);
+        pin_dict.trim(KEEP_BYTES); pin_opt.trim(KEEP_BYTES);
+    }
+};
+BepScratch &scratch_of(int device)
+{
+    static BepScratch pool[64];   // never destroyed: the CUDA context may already be gone at exit
+    return pool[device & 63];
+}
 
 }  // namespace
 
@@ -215,6 +268,10 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
         return fail(BNK_ERR_CUDA, "bep: no CUDA device visible (libbnkgpu has no CPU fallback)");
     }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return fail(BNK_ERR_CUDA, "bep: cannot select device %d", device);
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess) cur_dev = 0;
+    BepScratch &S = scratch_of(cur_dev);
+    std::lock_guard<std::mutex> scratch_lock(S.mu);   // one BEP call per device at a time
     std::vector<int32_t> leaf_nodes, leaf_of_node(n, -1);
     for (int v = 0; v < n; v++)
         if (t->ent_of_node[v] < 0) { leaf_of_node[v] = (int32_t)leaf_nodes.size(); leaf_nodes.push_back(v); }
@@ -232,19 +289,28 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
     // one launch per level pays while levels are wide; a very deep tree (caterpillar) keeps one thread per instance
     bool by_levels = n_levels <= 4096;
     if (const char *env = std::getenv("BNK_BEP_SCHEDULE")) by_levels = std::strcmp(env, "instance") != 0;
-    // extant rows pass through; ancestors are filled in below
-    for (int v = 0; v < n; v++) {
-        uint8_t *row = present_out + (size_t)v * n_pos;
-        if (t->ent_of_node[v] < 0) for (int c = 0; c < n_pos; c++) row[c] = obs[(size_t)v * n_pos + c] != BNK_NONE;
-        else std::memset(row, 0, n_pos);
+    // Graph assembly: on the device (bep_reach.cu) unless the caller wants the graphs themselves (bnk_bep_infer) or
+    // BNK_BEP_ASSEMBLY=host asks for the r1 path (A/B runs, tests)
+    bool device_assembly = pogs == nullptr;
+    if (const char *env = std::getenv("BNK_BEP_ASSEMBLY")) device_assembly = device_assembly && std::strcmp(env, "host") != 0;
+    if (!device_assembly || n_int == 0) {
+        // extant rows pass through; ancestors are filled in below
+        for (int v = 0; v < n; v++) {
+            uint8_t *row = present_out + (size_t)v * n_pos;
+            if (t->ent_of_node[v] < 0) for (int c = 0; c < n_pos; c++) row[c] = obs[(size_t)v * n_pos + c] != BNK_NONE;
+            else std::memset(row, 0, n_pos);
+        }
     }
     if (n_int == 0) return BNK_OK;
 
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    Dev<uint8_t> d_obs, d_fwd, d_symmap;
-    Dev<int32_t> d_leaf_nodes, d_leaf_of_node, d_ent, d_parent, d_first, d_kids, d_nxt, d_prv, d_inst_e, d_dict, d_nsym, d_flag, d_level_nodes;
-    Dev<uint32_t> d_A, d_B;
+    cudaStream_t &st = S.st;
+    cudaEvent_t &ev0 = S.ev0, &ev1 = S.ev1;
+    Dev<uint8_t> &d_obs = S.d_obs, &d_fwd = S.d_fwd, &d_symmap = S.d_symmap, &d_contig = S.d_contig, &d_present = S.d_present;
+    Dev<int32_t> &d_leaf_nodes = S.d_leaf_nodes, &d_leaf_of_node = S.d_leaf_of_node, &d_ent = S.d_ent, &d_parent = S.d_parent,
+                 &d_first = S.d_first, &d_kids = S.d_kids, &d_nxt = S.d_nxt, &d_prv = S.d_prv, &d_inst_e = S.d_inst_e, &d_dict = S.d_dict,
+                 &d_nsym = S.d_nsym, &d_flag = S.d_flag, &d_level_nodes = S.d_level_nodes, &d_rows = S.d_rows;
+    Dev<uint32_t> &d_A = S.d_A, &d_B = S.d_B, &d_A1 = S.d_A1, &d_Z = S.d_Z, &d_compact = S.d_compact;
+    std::vector<int32_t> opt_row_of;      // device assembly: ancestor row -> row of the compact copy of its optimal sets
     const int MAXSYM = 255;
     // crippled ancestors after the first pass, patch rounds, largest symbol count, kernel launches,
     // microseconds: device sweeps (incl. their copies), host graph assembly, whole call, kernels alone (CUDA events)
@@ -261,23 +327,13 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
     std::map<int, std::vector<Edge3>> crippled_edges;
     std::map<int, std::set<int>> crippled;
     std::vector<int32_t> h_nsym;
-    struct Pinned {  // page-locked staging for the two large device->host copies
-        void *p = nullptr; size_t cap = 0;
-        cudaError_t ensure(size_t bytes) {
-            if (bytes <= cap) return cudaSuccess;
-            if (p) cudaFreeHost(p);
-            p = nullptr; cap = 0;
-            cudaError_t e = cudaMallocHost(&p, bytes);
-            if (e == cudaSuccess) cap = bytes;
-            return e;
-        }
-        ~Pinned() { if (p) cudaFreeHost(p); }
-    } pin_dict, pin_opt;
+    Pinned &pin_dict = S.pin_dict, &pin_opt = S.pin_opt;
     const int32_t *h_dict = nullptr;
     const uint32_t *h_opt = nullptr;  // optimal sets of ancestor rows opt_ent0 .. (a chunk, or all rows)
     int opt_ent0 = 0;
 
     // one batch of instances through the device; results land in h_nsym / h_dict / h_opt ([ent][W][n_inst])
+    std::vector<int32_t> want_rows;       // patch rounds: the ancestor rows (ents) whose optimal sets the host needs
     auto run = [&](const std::vector<int32_t> &ie, const std::vector<uint8_t> &ifw, int recode_null, int &W, bool copy_opt) -> int {
         int rc = BNK_OK;
         const int n_inst = (int)ie.size();
@@ -314,10 +370,24 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
         BEP_CUDA_TRY(pin_dict.ensure(sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst));
         h_dict = static_cast<const int32_t *>(pin_dict.p);
         BEP_CUDA_TRY(cudaMemcpyAsync(pin_dict.p, d_dict.p, sizeof(int32_t) * (size_t)std::max(mx, 1) * n_inst, cudaMemcpyDeviceToHost, st));
-        if (copy_opt) {
+        if (copy_opt && !want_rows.empty()) {
+            // only the rows of the ancestors still without a path (r1 copied all n_int rows every round)
+            const size_t row_words = (size_t)W * n_inst;
+            BEP_CUDA_TRY(d_rows.alloc(want_rows.size()));
+            BEP_CUDA_TRY(d_compact.alloc(want_rows.size() * row_words));
+            BEP_CUDA_TRY(cudaMemcpyAsync(d_rows.p, want_rows.data(), sizeof(int32_t) * want_rows.size(), cudaMemcpyHostToDevice, st));
+            BEP_CUDA_TRY(bep_launch_gather(d_B.p, d_rows.p, (int)want_rows.size(), row_words, d_compact.p, st));
+            info[3]++;
+            BEP_CUDA_TRY(pin_opt.ensure(sizeof(uint32_t) * want_rows.size() * row_words));
+            h_opt = static_cast<const uint32_t *>(pin_opt.p);
+            opt_row_of.assign(n_int, -1);
+            for (size_t i = 0; i < want_rows.size(); i++) opt_row_of[want_rows[i]] = (int32_t)i;
+            BEP_CUDA_TRY(cudaMemcpyAsync(pin_opt.p, d_compact.p, sizeof(uint32_t) * want_rows.size() * row_words, cudaMemcpyDeviceToHost, st));
+        } else if (copy_opt) {
             BEP_CUDA_TRY(pin_opt.ensure(sizeof(uint32_t) * (size_t)n_int * W * n_inst));
             h_opt = static_cast<const uint32_t *>(pin_opt.p);
             opt_ent0 = 0;
+            opt_row_of.clear();
             BEP_CUDA_TRY(cudaMemcpyAsync(pin_opt.p, d_B.p, sizeof(uint32_t) * (size_t)n_int * W * n_inst, cudaMemcpyDeviceToHost, st));
         }
         BEP_CUDA_TRY(cudaStreamSynchronize(st));
@@ -333,7 +403,8 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
     auto for_each_optimal = [&](int ent, int k, int n_inst, int W, auto &&fn) {
         const int ns = h_nsym[k];
         for (int w = 0; w < W; w++) {
-            uint32_t bits = h_opt[((size_t)(ent - opt_ent0) * W + w) * n_inst + k];
+            const size_t orow = opt_row_of.empty() ? (size_t)(ent - opt_ent0) : (size_t)opt_row_of[ent];
+            uint32_t bits = h_opt[(orow * W + w) * n_inst + k];
             while (bits) {
                 const int b = __builtin_ctz(bits);
                 bits &= bits - 1;
@@ -352,9 +423,9 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
         std::vector<int32_t> ie;
         std::vector<uint8_t> ifw;
         int W = 1;
-        BEP_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        BEP_CUDA_TRY(cudaEventCreate(&ev0));
-        BEP_CUDA_TRY(cudaEventCreate(&ev1));
+        if (!st) BEP_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (!ev0) BEP_CUDA_TRY(cudaEventCreate(&ev0));
+        if (!ev1) BEP_CUDA_TRY(cudaEventCreate(&ev1));
         BEP_CUDA_TRY(d_obs.alloc((size_t)n * n_pos));
         BEP_CUDA_TRY(d_leaf_nodes.alloc(n_leaves));
         BEP_CUDA_TRY(d_leaf_of_node.alloc(n));
@@ -414,7 +485,6 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
             for (int x : h_nsym) mx = std::max(mx, x);
             const int Wn = mx + 1 <= 32 ? 1 : (mx + 1 <= 64 ? 2 : (mx + 1 <= 128 ? 4 : 8));
             if (Wn > 1) {
-                cudaFree(d_A.p); d_A.p = nullptr; cudaFree(d_B.p); d_B.p = nullptr;
                 BEP_CUDA_TRY(d_A.alloc((size_t)n_int * Wn * n_inst_max));
                 BEP_CUDA_TRY(d_B.alloc((size_t)n_int * Wn * n_inst_max));
             }
@@ -423,7 +493,86 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
         rc = run(ie, ifw, 1, W, false);
         if (rc != BNK_OK) goto done;
         mark("main sweeps done");
-        {
+        if (device_assembly) {
+            const int n_inst = (int)ie.size();
+            const auto t0 = std::chrono::steady_clock::now();
+            const int n_words = (n_pos + 31) / 32;
+            const size_t row_words = (size_t)W * n_inst;
+            std::vector<uint8_t> h_contig(n_int);
+            std::vector<int32_t> rows;
+            BEP_CUDA_TRY(d_A1.alloc((size_t)n_words * n_int));
+            BEP_CUDA_TRY(d_Z.alloc((size_t)n_words * n_int));
+            BEP_CUDA_TRY(d_contig.alloc(n_int));
+            BEP_CUDA_TRY(d_present.alloc((size_t)n * n_pos));
+            BEP_CUDA_TRY(cudaEventRecord(ev0, st));
+            BEP_CUDA_TRY(bep_launch_reach(d_B.p, d_dict.p, d_nsym.p, info[2], n_int, n_inst, n_pos, W, d_A1.p, d_Z.p, d_contig.p, st));
+            BEP_CUDA_TRY(bep_launch_rows(d_obs.p, d_ent.p, d_Z.p, n, n_int, n_pos, d_present.p, st));
+            BEP_CUDA_TRY(cudaEventRecord(ev1, st));
+            info[3] += 2;
+            BEP_CUDA_TRY(cudaMemcpyAsync(h_contig.data(), d_contig.p, n_int, cudaMemcpyDeviceToHost, st));
+            BEP_CUDA_TRY(cudaStreamSynchronize(st));
+            {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) info[7] += (int)(ms * 1000.f);
+            }
+            mark("device graph assembly done");
+            // ancestors without a start-to-end path: their optimal sets go to the host for the patch rounds
+            for (int ent = 0; ent < n_int; ent++) if (!h_contig[ent]) rows.push_back(ent);
+            if (!rows.empty()) {
+                BEP_CUDA_TRY(d_rows.alloc(rows.size()));
+                BEP_CUDA_TRY(d_compact.alloc(rows.size() * row_words));
+                BEP_CUDA_TRY(cudaMemcpyAsync(d_rows.p, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, st));
+                BEP_CUDA_TRY(bep_launch_gather(d_B.p, d_rows.p, (int)rows.size(), row_words, d_compact.p, st));
+                info[3]++;
+                BEP_CUDA_TRY(pin_opt.ensure(sizeof(uint32_t) * rows.size() * row_words));
+                BEP_CUDA_TRY(cudaMemcpyAsync(pin_opt.p, d_compact.p, sizeof(uint32_t) * rows.size() * row_words, cudaMemcpyDeviceToHost, st));
+            }
+            // every row of the mask (extants from their residues, ancestors with a path from alive2) in one copy;
+            // large masks go through a temporary page-lock of the caller's buffer (a pageable copy runs at ~3 GB/s)
+            {
+                const size_t mask_bytes = (size_t)n * n_pos;
+                const bool pinned = mask_bytes >= ((size_t)8 << 20) && cudaHostRegister(present_out, mask_bytes, cudaHostRegisterDefault) == cudaSuccess;
+                if (!pinned) cudaGetLastError();
+                cudaError_t ce = cudaMemcpyAsync(present_out, d_present.p, mask_bytes, cudaMemcpyDeviceToHost, st);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+                if (pinned) cudaHostUnregister(present_out);
+                BEP_CUDA_TRY(ce);
+            }
+            mark("mask + rows of ancestors without a path copied");
+            if (!rows.empty()) {
+                opt_row_of.assign(n_int, -1);
+                for (size_t i = 0; i < rows.size(); i++) opt_row_of[rows[i]] = (int32_t)i;
+                h_opt = static_cast<const uint32_t *>(pin_opt.p);
+                std::mutex mu;
+                parallel_slices((int)rows.size(), [&](int slo, int shi) {
+                    Pog g;
+                    std::vector<Edge3> edges;
+                    for (int r = slo; r < shi; r++) {
+                        const int ent = rows[r], v = t->node_of_ent[ent];
+                        edges.clear();
+                        for (int k = 0; k < n_inst; k++) {
+                            if (h_nsym[k] < 1) continue;
+                            const int i = ie[k] - 1;
+                            if (ifw[k]) for_each_optimal(ent, k, n_inst, W, [&](int to) { edges.push_back(Edge3{i, to, 1}); });
+                            else for_each_optimal(ent, k, n_inst, W, [&](int from) { edges.push_back(Edge3{from, i, 2}); });
+                        }
+                        merge_edges(edges);
+                        g.from_edges(n_pos, edges);
+                        if (!g.is_contiguous()) {
+                            std::set<int> pr = g.protruding();
+                            std::lock_guard<std::mutex> lk(mu);
+                            crippled[v] = std::move(pr);
+                            crippled_edges[v] = edges;
+                        } else {   // cannot happen (the device found no path); kept so that a disagreement is harmless
+                            g.nibble();
+                            emit_row(v, g);
+                        }
+                    }
+                });
+                opt_row_of.clear();
+            }
+            info[5] += us_since(t0);
+        } else {
             const int n_inst = (int)ie.size();
             const auto t0 = std::chrono::steady_clock::now();
             std::mutex mu;
@@ -493,6 +642,8 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
             const std::vector<int> cols(columns.begin(), columns.end());
             ie.clear(); ifw.clear();
             for (int idx : cols) { ie.push_back(std::abs(idx) + 1); ifw.push_back(idx > 0 ? 1 : 0); }
+            want_rows.clear();
+            for (const auto &kv : crippled) want_rows.push_back(t->ent_of_node[kv.first]);
             rc = run(ie, ifw, 0, W, true);
             if (rc != BNK_OK) goto done;
             info[1]++;
@@ -554,9 +705,8 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
     }
 done:
     mark("before cleanup");
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (st) cudaStreamDestroy(st);
+    if (st) cudaStreamSynchronize(st);
+    S.trim();
     return rc;
 }
 

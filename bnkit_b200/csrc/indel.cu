@@ -32,7 +32,9 @@
 namespace bnk {
 namespace {
 
-constexpr int IND_THREADS = 128;       // columns per CTA
+constexpr int IND_THREADS = 128;       // columns per CTA tile of the level kernel
+constexpr int LEVEL_TPC = 8;           // column tiles a level CTA walks with its children's tables staged once
+constexpr int WALK_THREADS = 128;      // columns per CTA of the walk kernel (measured: 64 ms on the 10k-level caterpillar; 122 ms with one-warp CTAs)
 constexpr int LEVEL_MIN_NODES = 8;     // narrower height levels go to the walk kernel
 constexpr int E_ZERO = INT32_MIN / 2;  // exponent marking an exactly-zero gap entry
 
@@ -70,137 +72,192 @@ __device__ __forceinline__ void add_scaled(double a, int ea, double b, int eb, d
     }
 }
 
-// One node for one column per thread; every thread of the CTA works on the same node (tables staged in shared memory).
+// Per-thread state of one (node, column) while its children are folded in.
 template <int K>
-__device__ __forceinline__ void peel_node(const IndelArgs &a, int node, int col, bool valid, double *sA, double *s_ins)
-{
-    const int tid = threadIdx.x;
-    const int c0 = a.first[node], c1 = a.first[node + 1];
-    const size_t nc = (size_t)a.ncols;
+struct PeelState {
     double Rv[K];
+    int eRv;
+    double gm;
+    int ge;
+    bool cgv;
+    __device__ __forceinline__ void init()
+    {
 #pragma unroll
-    for (int p = 0; p < K; p++) Rv[p] = 1.0;
-    int eRv = 0;
-    double gm = 0.0;
-    int ge = 0;
-    bool cgv = true;
-    __syncthreads();   // the previous node's reads of s_ins / sA are done
-    if (tid < K) s_ins[tid] = a.tb.ins[(size_t)node * K + tid];
-    for (int k = c0; k < c1; k++) {
-        const int ch = a.kids[k];
-        if (k > c0) __syncthreads();
-        {
-            const double *src = a.tb.A + (size_t)ch * (K * K);
-            for (int i = tid; i < K * K; i += IND_THREADS) sA[i] = src[i];
-        }
-        __syncthreads();
-        if (!valid) continue;
-        const double del = a.tb.del[ch];
-        const int ent = a.ent_of_node[ch];
-        if (ent < 0) {   // an extant (calcLeafPeelingProbabilities :273-284)
-            const uint8_t o = a.obs[(size_t)ch * nc + col];
-            if (o == BNK_NONE) {
-#pragma unroll
-                for (int p = 0; p < K; p++) Rv[p] *= del;
-            } else {
-                cgv = false;
-#pragma unroll
-                for (int p = 0; p < K; p++) Rv[p] *= sA[p * K + o];
-            }
-        } else {
-            double Rc[K];
-            const double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
-#pragma unroll
-            for (int x = 0; x < K; x++) Rc[x] = m[(size_t)x * nc];
-            const int eRc = a.eR[(size_t)ent * nc + col];
-            const bool cgc = a.cg[(size_t)ent * nc + col] != 0;
-            if (cgc) {
-                // ancestral gap term of this child (:297-327): sum_q R_c[q] ins_v[q] + Gap_c
-                double s = 0.0;
-#pragma unroll
-                for (int q = 0; q < K; q++) s += Rc[q] * s_ins[q];
-                const double Gc = m[(size_t)K * nc];
-                const int eGc = a.eG[(size_t)ent * nc + col];
-                double tm;
-                int te;
-                add_scaled(s, eRc, Gc, eGc, tm, te);
-                add_scaled(gm, ge, tm, te, gm, ge);
-            } else {
-                cgv = false;
-            }
-            // ancestral residue terms (:329-356); the deletion term joins only below an all-gap child
-            const bool with_del = cgc && del > 0.0;
-            const double sc = with_del ? (eRc < -1000 ? 0.0 : pow2i(eRc)) : 1.0;   // messages are <= 1: eRc <= 0
-#pragma unroll
-            for (int p = 0; p < K; p++) {
-                double S = 0.0;
-#pragma unroll
-                for (int x = 0; x < K; x++) S += sA[p * K + x] * Rc[x];
-                Rv[p] *= with_del ? S * sc + del : S;
-            }
-            if (!with_del) eRv += eRc;
-        }
-        // keep the running product's largest entry in [1, 2)
-        double mx = Rv[0];
-#pragma unroll
-        for (int p = 1; p < K; p++) mx = fmax(mx, Rv[p]);
-        if (mx > 0.0) {
-            const int e = exponent_of(mx);
-            const double f = pow2i(-e);
-#pragma unroll
-            for (int p = 0; p < K; p++) Rv[p] *= f;
-            eRv += e;
-        }
+        for (int p = 0; p < K; p++) Rv[p] = 1.0;
+        eRv = 0; gm = 0.0; ge = 0; cgv = true;
     }
-    if (!valid) return;
-    if (gm > 0.0) {
-        const int e = exponent_of(gm);
-        gm *= pow2i(-e);
-        ge += e;
+};
+
+// fold child `ch` (its table A_ch in shared memory at sA, the parent's insertion vector at s_ins) into the state
+template <int K>
+__device__ __forceinline__ void fold_child(const IndelArgs &a, int ch, int col, const double *sA, const double *s_ins, PeelState<K> &st)
+{
+    const size_t nc = (size_t)a.ncols;
+    const double del = a.tb.del[ch];
+    const int ent = a.ent_of_node[ch];
+    if (ent < 0) {   // an extant (calcLeafPeelingProbabilities :273-284)
+        const uint8_t o = a.obs[(size_t)ch * nc + col];
+        if (o == BNK_NONE) {
+#pragma unroll
+            for (int p = 0; p < K; p++) st.Rv[p] *= del;
+        } else {
+            st.cgv = false;
+#pragma unroll
+            for (int p = 0; p < K; p++) st.Rv[p] *= sA[p * K + o];
+        }
     } else {
-        gm = 0.0;
-        ge = E_ZERO;
+        double Rc[K];
+        const double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
+#pragma unroll
+        for (int x = 0; x < K; x++) Rc[x] = m[(size_t)x * nc];
+        const int eRc = a.eR[(size_t)ent * nc + col];
+        const bool cgc = a.cg[(size_t)ent * nc + col] != 0;
+        if (cgc) {
+            // ancestral gap term of this child (:297-327): sum_q R_c[q] ins_v[q] + Gap_c
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < K; q++) s += Rc[q] * s_ins[q];
+            const double Gc = m[(size_t)K * nc];
+            const int eGc = a.eG[(size_t)ent * nc + col];
+            double tm;
+            int te;
+            add_scaled(s, eRc, Gc, eGc, tm, te);
+            add_scaled(st.gm, st.ge, tm, te, st.gm, st.ge);
+        } else {
+            st.cgv = false;
+        }
+        // ancestral residue terms (:329-356); the deletion term joins only below an all-gap child
+        const bool with_del = cgc && del > 0.0;
+        const double sc = with_del ? (eRc < -1000 ? 0.0 : pow2i(eRc)) : 1.0;   // messages are <= 1: eRc <= 0
+#pragma unroll
+        for (int p = 0; p < K; p++) {
+            double S = 0.0;
+#pragma unroll
+            for (int x = 0; x < K; x++) S += sA[p * K + x] * Rc[x];
+            st.Rv[p] *= with_del ? S * sc + del : S;
+        }
+        if (!with_del) st.eRv += eRc;
+    }
+    // keep the running product's largest entry in [1, 2)
+    double mx = st.Rv[0];
+#pragma unroll
+    for (int p = 1; p < K; p++) mx = fmax(mx, st.Rv[p]);
+    if (mx > 0.0) {
+        const int e = exponent_of(mx);
+        const double f = pow2i(-e);
+#pragma unroll
+        for (int p = 0; p < K; p++) st.Rv[p] *= f;
+        st.eRv += e;
+    }
+}
+
+// store the node's message; the root also writes the column's log-likelihood
+template <int K>
+__device__ __forceinline__ void finish_node(const IndelArgs &a, int node, int col, PeelState<K> &st)
+{
+    const size_t nc = (size_t)a.ncols;
+    if (st.gm > 0.0) {
+        const int e = exponent_of(st.gm);
+        st.gm *= pow2i(-e);
+        st.ge += e;
+    } else {
+        st.gm = 0.0;
+        st.ge = E_ZERO;
     }
     const int ent = a.ent_of_node[node];
     double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
 #pragma unroll
-    for (int p = 0; p < K; p++) m[(size_t)p * nc] = Rv[p];
-    m[(size_t)K * nc] = gm;
-    a.eR[(size_t)ent * nc + col] = eRv;
-    a.eG[(size_t)ent * nc + col] = ge;
-    a.cg[(size_t)ent * nc + col] = cgv ? 1 : 0;
+    for (int p = 0; p < K; p++) m[(size_t)p * nc] = st.Rv[p];
+    m[(size_t)K * nc] = st.gm;
+    a.eR[(size_t)ent * nc + col] = st.eRv;
+    a.eG[(size_t)ent * nc + col] = st.ge;
+    a.cg[(size_t)ent * nc + col] = st.cgv ? 1 : 0;
     if (a.parent[node] < 0) {   // decorate (:229-252)
         const double LN2 = 0.693147180559945309417232121458;
         double w = 0.0;
 #pragma unroll
-        for (int r = 0; r < K; r++) w += a.F[r] * Rv[r];
-        const double resL = w > 0.0 ? (log(w) + (double)eRv * LN2) + a.log_geom : -CUDART_INF;
-        const double gapL = gm > 0.0 ? log(gm) + (double)ge * LN2 : -CUDART_INF;
+        for (int r = 0; r < K; r++) w += a.F[r] * st.Rv[r];
+        const double resL = w > 0.0 ? (log(w) + (double)st.eRv * LN2) + a.log_geom : -CUDART_INF;
+        const double gapL = st.gm > 0.0 ? log(st.gm) + (double)st.ge * LN2 : -CUDART_INF;
         const double mxl = fmax(resL, gapL);
         a.out_logl[col] = mxl == -CUDART_INF ? -CUDART_INF : mxl + log(exp(resL - mxl) + exp(gapL - mxl));
     }
 }
 
-// one height level: grid = (nodes of the level, column tiles)
+template <int K, int THREADS>
+__device__ __forceinline__ void stage_table(const IndelArgs &a, int ch, double *sA)
+{
+    const double *src = a.tb.A + (size_t)ch * (K * K);
+    for (int i = threadIdx.x; i < K * K; i += THREADS) sA[i] = src[i];
+}
+
+// One height level: grid = (nodes of the level, groups of LEVEL_TPC column tiles).  A CTA stages the tables of its
+// node's children ONCE (two at a time: binary nodes never re-stage) and then walks its column tiles.
 template <int K>
 __global__ void __launch_bounds__(IND_THREADS) indel_level_kernel(IndelArgs a)
 {
-    __shared__ double sA[K * K];
+    __shared__ __align__(16) double sA[2][K * K];
     __shared__ double s_ins[K];
     const int node = a.nodes[blockIdx.x];
-    const int col = blockIdx.y * IND_THREADS + threadIdx.x;
-    peel_node<K>(a, node, col, col < a.ncols, sA, s_ins);
+    const int c0 = a.first[node], c1 = a.first[node + 1];
+    const int tile0 = blockIdx.y * LEVEL_TPC;
+    if (threadIdx.x < K) s_ins[threadIdx.x] = a.tb.ins[(size_t)node * K + threadIdx.x];
+    if (c1 - c0 <= 2) {
+        for (int k = c0; k < c1; k++) stage_table<K, IND_THREADS>(a, a.kids[k], sA[k - c0]);
+        __syncthreads();
+        for (int tl = 0; tl < LEVEL_TPC; tl++) {
+            const int col = (tile0 + tl) * IND_THREADS + threadIdx.x;
+            if (col >= a.ncols) break;
+            PeelState<K> st;
+            st.init();
+            for (int k = c0; k < c1; k++) fold_child<K>(a, a.kids[k], col, sA[k - c0], s_ins, st);
+            finish_node<K>(a, node, col, st);
+        }
+        return;
+    }
+    // any arity: the children's tables pass through shared memory one at a time, per column tile
+    for (int tl = 0; tl < LEVEL_TPC; tl++) {
+        const int col = (tile0 + tl) * IND_THREADS + threadIdx.x;
+        if ((tile0 + tl) * IND_THREADS >= a.ncols) break;
+        const bool valid = col < a.ncols;
+        PeelState<K> st;
+        st.init();
+        for (int k = c0; k < c1; k++) {
+            __syncthreads();
+            stage_table<K, IND_THREADS>(a, a.kids[k], sA[0]);
+            __syncthreads();
+            if (valid) fold_child<K>(a, a.kids[k], col, sA[0], s_ins, st);
+        }
+        if (valid) finish_node<K>(a, node, col, st);
+    }
 }
 
-// the narrow rest of the tree: grid = column tiles, every CTA walks the node list (children before parents)
+// The narrow rest of the tree (deep trees: all of it): grid = tiles of WALK_THREADS columns, every CTA walks the node
+// list, children before parents.  (A 10,000-level caterpillar is one long dependent chain per column: 64 ms per
+// evaluation at 5,000 columns; one-warp CTAs on all SMs were slower, 122 ms -- the table staging of a step is a
+// serial chain of global loads that more threads per CTA shorten.)
 template <int K>
-__global__ void __launch_bounds__(IND_THREADS) indel_walk_kernel(IndelArgs a)
+__global__ void __launch_bounds__(WALK_THREADS) indel_walk_kernel(IndelArgs a)
 {
-    __shared__ double sA[K * K];
+    __shared__ __align__(16) double sA[K * K];
     __shared__ double s_ins[K];
-    const int col = blockIdx.x * IND_THREADS + threadIdx.x;
+    const int col = blockIdx.x * WALK_THREADS + threadIdx.x;
     const bool valid = col < a.ncols;
-    for (int i = 0; i < a.n_launch_nodes; i++) peel_node<K>(a, a.nodes[i], col, valid, sA, s_ins);
+    for (int i = 0; i < a.n_launch_nodes; i++) {
+        const int node = a.nodes[i];
+        const int c0 = a.first[node], c1 = a.first[node + 1];
+        PeelState<K> st;
+        st.init();
+        __syncthreads();
+        if (threadIdx.x < K) s_ins[threadIdx.x] = a.tb.ins[(size_t)node * K + threadIdx.x];
+        for (int k = c0; k < c1; k++) {
+            if (k > c0) __syncthreads();   // the previous table has been consumed
+            stage_table<K, WALK_THREADS>(a, a.kids[k], sA);
+            __syncthreads();
+            if (valid) fold_child<K>(a, a.kids[k], col, sA, s_ins, st);
+        }
+        if (valid) finish_node<K>(a, node, col, st);
+    }
 }
 
 }  // namespace
@@ -291,17 +348,19 @@ int run_sweep(bnk_indel *h, double rate, double geom)
     a.msg = h->d_msg.p; a.eR = h->d_eR.p; a.eG = h->d_eG.p; a.cg = h->d_cg.p;
     a.log_geom = std::log(geom); a.out_logl = h->d_logl.p;
     const int tiles = (nc + IND_THREADS - 1) / IND_THREADS;
+    const int tile_groups = (tiles + LEVEL_TPC - 1) / LEVEL_TPC;
     for (const auto &lr : h->level_ranges) {
         a.nodes = h->d_nodes.p + lr.first; a.n_launch_nodes = lr.second - lr.first;
-        dim3 grid(a.n_launch_nodes, tiles);
+        dim3 grid(a.n_launch_nodes, tile_groups);
         if (K == 20) indel_level_kernel<20><<<grid, IND_THREADS, 0, st>>>(a);
         else indel_level_kernel<4><<<grid, IND_THREADS, 0, st>>>(a);
         h->launches++;
     }
     if (h->narrow_range.second > h->narrow_range.first) {
         a.nodes = h->d_nodes.p + h->narrow_range.first; a.n_launch_nodes = h->narrow_range.second - h->narrow_range.first;
-        if (K == 20) indel_walk_kernel<20><<<tiles, IND_THREADS, 0, st>>>(a);
-        else indel_walk_kernel<4><<<tiles, IND_THREADS, 0, st>>>(a);
+        const int wtiles = (nc + WALK_THREADS - 1) / WALK_THREADS;
+        if (K == 20) indel_walk_kernel<20><<<wtiles, WALK_THREADS, 0, st>>>(a);
+        else indel_walk_kernel<4><<<wtiles, WALK_THREADS, 0, st>>>(a);
         h->launches++;
     }
     CUDA_TRY(cudaEventRecord(h->ev[2], st));

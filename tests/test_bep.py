@@ -230,3 +230,38 @@ def test_gpu_bep_feeds_the_sweeps(bnk, oracle):
         assert cols == fx["doc_result"]["indices"]
         assert [AA[st[anc, c]] for c in cols] == fx["doc_result"]["values"]
     ws.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bep_device_assembly_equals_host_assembly(bnk, monkeypatch):
+    """Graph assembly on the device (bep_reach.cu: alive1 / alive2 passes, only ancestors without a path go back to
+    the host) against the host assembly of the same optimal sets (BNK_BEP_ASSEMBLY=host, the r1 path) and against
+    the oracle: larger alignments than the random cases above -- columns beyond one 32-column tile, several
+    ancestors per CTA, clade-wise indels that leave many ancestors without a path"""
+    from oracle import bep
+    rng = np.random.default_rng(31)
+    crippled = 0
+    for trial in range(6):
+        parent, dist, rows, obs = random_case(rng, int(rng.integers(40, 120)), int(rng.integers(33, 150)),
+                                              float(rng.choice([0.3, 0.6])), max_children=int(rng.integers(2, 4)))
+        n = len(parent)
+        size = np.ones(n, np.int64)
+        for v in range(n - 1, 0, -1):
+            size[parent[v]] += size[v]
+        for c in range(0, obs.shape[1], 2):                  # clade-wise deletions
+            v = int(rng.integers(1, n))
+            obs[v:v + size[v], c] = NONE
+        has_child = np.zeros(n, bool)
+        has_child[parent[parent >= 0]] = True
+        rows = [None if has_child[v] else (obs[v] != NONE).tolist() for v in range(n)]
+        tree = bnk.Tree(parent, dist)
+        monkeypatch.delenv("BNK_BEP_ASSEMBLY", raising=False)
+        got, info = tree.bep_presence(obs, want_info=True)
+        monkeypatch.setenv("BNK_BEP_ASSEMBLY", "host")
+        host, hinfo = tree.bep_presence(obs, want_info=True)
+        assert np.array_equal(got, host) and info[0] == hinfo[0] and info[1] == hinfo[1]
+        crippled += int(info[0])
+        if trial < 3:
+            want, _ = bep.presence_mask(parent.tolist(), rows, obs.shape[1])
+            assert np.array_equal(got, np.asarray(want, np.uint8))
+    assert crippled > 0
