@@ -143,9 +143,6 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     if (const char *env = std::getenv("BNK_WALKER"))
         ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "lane") == 0 ? 4 : 0)));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
-    if (const char *env = std::getenv("BNK_MMA_DOWN")) ws->mma_down = std::atoi(env) != 0;
-    if (const char *env = std::getenv("BNK_JOINT10")) ws->joint10 = std::atoi(env) != 0;
-    if (const char *env = std::getenv("BNK_JOINT10_W")) ws->jw = -std::atoi(env);  // negative: forced
     if (const char *env = std::getenv("BNK_WARP_W")) ws->cfg_xw = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_NS")) ws->cfg_xns = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_C")) ws->cfg_xc = std::atoi(env);
@@ -376,21 +373,8 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         if (ws->mw < 0 && -ws->mw <= 7) ws->mw = ws->mw;  // forced by BNK_MMA_W (kept negative as the marker)
         else ws->mw = best_w;
     }
-    {   // joint10: 3 columns per warp, same cost model
-        int best_w = 2; double best_cost = -1.0;
-        const int cw = joint10_cols_per_warp();
-        for (int w = 2; w <= 14; w++) {
-            int64_t nt = 0;
-            for (int k = 0; k < ncat; k++) nt += (cat_begin[k + 1] - cat_begin[k] + w * cw - 1) / (w * cw);
-            const int64_t rounds = (nt + ws->sm_count - 1) / ws->sm_count;
-            const double cost = (double)rounds * w * (1.0 + 0.05 * (double)(rounds - 1));
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
-        }
-        if (!(ws->jw < 0 && -ws->jw <= 14)) ws->jw = best_w;
-    }
     const int wt = wide_tile_cols(), cg = cherry_group_cols();
     ws->mtiles.clear(); ws->chunk_mtiles.clear();
-    ws->jtiles.clear(); ws->chunk_jtiles.clear();
     for (int lo = 0; lo < ncat; lo += cats_per_chunk) {
         const int hi = std::min(ncat, lo + cats_per_chunk);
         Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
@@ -439,18 +423,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 }
             }
         }
-        const int j0 = (int)ws->jtiles.size();
-        {
-            const int jt = std::abs(ws->jw) * joint10_cols_per_warp();
-            for (int k = lo; k < hi; k++) {
-                const int nc = cat_begin[k + 1] - cat_begin[k];
-                const int nt = (nc + jt - 1) / jt;
-                for (int q = 0; q < nt; q++) {
-                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
-                    ws->jtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
-                }
-            }
-        }
         const int g0 = (int)ws->cgroups.size();
         const int ct0 = (int)ws->ctiles.size();
         int crecs = 0;  // TileDesc::ncat of a cherry group = offset of its result records inside a node's region
@@ -494,7 +466,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             ws->chunk_xtiles.push_back({x0, (int)ws->xtiles.size()});
             ws->chunk_ltiles.push_back({l0, (int)ws->ltiles.size()});
             ws->chunk_mtiles.push_back({m0, (int)ws->mtiles.size()});
-            ws->chunk_jtiles.push_back({j0, (int)ws->jtiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
         }
     }
@@ -516,7 +487,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
     TRY(upload(ws->d_ltiles, ws->ltiles, ws->stream));
     TRY(upload(ws->d_mtiles, ws->mtiles, ws->stream));
-    TRY(upload(ws->d_jtiles, ws->jtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
     ws->rates_null = rates == nullptr;
@@ -864,19 +834,6 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
                 TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
                     return gen ? launch_up_wide_gen(K, 0, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
             }
-            bool j10 = false;
-            int jns = 8;
-            if (s.warp && ws->joint10 && (ws->walker_mode == 0 || ws->walker_mode == 3)) {
-                const int jw = std::abs(ws->jw);
-                if (ws->cfg_xns >= 2 && ws->cfg_xns <= 8) jns = ws->cfg_xns;
-                else while (jns > 3 && joint10_smem_bytes(jw, jns, s.a.smem_slots) > (size_t)ws->smem_optin / 2 - 1024) jns--;
-                j10 = joint10_smem_bytes(jw, jns, s.a.smem_slots) <= (size_t)ws->smem_optin;
-            }
-            if (j10) {
-                WalkArgs ja = s.a;
-                ja.tiles = ws->d_jtiles.p + ws->chunk_jtiles[ci].first;
-                CUDA_TRY(launch_joint_up_10(ja, ws->chunk_jtiles[ci].second - ws->chunk_jtiles[ci].first, std::abs(ws->jw), jns, ws->stream));
-            } else
             CUDA_TRY(s.lane ? launch_lane_up(0, s.a, s.n_ltiles, ws->stream)
                      : s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                             : s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
@@ -1069,9 +1026,8 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
                 s.a.tmsg = ws->d_tmsg.p;
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
-            if (s.mma && !ws->mma_down) s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
+            if (s.mma) s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
             CUDA_TRY(s.lane ? launch_lane_down(s.a, s.n_ltiles, ws->stream)
-                     : s.mma && ws->mma_down ? launch_sum_down_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
                      : s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                               : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;

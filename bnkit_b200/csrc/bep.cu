@@ -130,11 +130,10 @@ __device__ __forceinline__ void bep_valid_mask(const BepArgs &a, int n, uint32_t
 
 // forward step of one internal node v (row ent) of instance t: A = states at the lowest count of children whose
 // arg-min set misses them, B = states one count above
-template <int W>
+template <int W, int P>   // P = bits of the bit-sliced counters: up to 2^P - 1 children per node
 __device__ __forceinline__ void bep_node_forward(const BepArgs &a, int t, int v, int ent, int e, bool fwd, int n, const uint32_t *valid)
 {
     const size_t ni = (size_t)a.n_inst;
-    constexpr int P = 6;  // bit-sliced counters: up to 63 children per node
     uint32_t plane[P][W];
 #pragma unroll
     for (int p = 0; p < P; p++)
@@ -222,7 +221,7 @@ __device__ __forceinline__ void bep_node_backward(const BepArgs &a, int t, int v
 
 // Schedule 1 -- one thread walks the whole tree of its instance (any tree shape, two launches in total):
 // children before parents going up (parent[v] < v), root first going down.
-template <int W>
+template <int W, int P>
 __global__ void bep_forward_kernel(const BepArgs a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,7 +233,7 @@ __global__ void bep_forward_kernel(const BepArgs a)
     bep_valid_mask<W>(a, n, valid);
     for (int v = a.n_nodes - 1; v >= 0; v--) {
         const int ent = a.ent_of_node[v];
-        if (ent >= 0) bep_node_forward<W>(a, t, v, ent, e, fwd, n, valid);
+        if (ent >= 0) bep_node_forward<W, P>(a, t, v, ent, e, fwd, n, valid);
     }
 }
 template <int W>
@@ -250,7 +249,7 @@ __global__ void bep_backward_kernel(const BepArgs a)
 
 // Schedule 2 -- one launch per height level, one thread per (instance, node of the level): the children of a
 // node sit on lower levels, its parent on a higher one.  (instance, node) parallelism instead of ~10,000 threads.
-template <int W>
+template <int W, int P>
 __global__ void bep_forward_level_kernel(const BepArgs a, const int32_t *nodes, int n_level)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,7 +261,7 @@ __global__ void bep_forward_level_kernel(const BepArgs a, const int32_t *nodes, 
     bep_valid_mask<W>(a, n, valid);
     for (int k = blockIdx.y; k < n_level; k += gridDim.y) {
         const int v = nodes[k];
-        bep_node_forward<W>(a, t, v, a.ent_of_node[v], e, fwd, n, valid);
+        bep_node_forward<W, P>(a, t, v, a.ent_of_node[v], e, fwd, n, valid);
     }
 }
 template <int W>
@@ -302,13 +301,17 @@ cudaError_t bep_launch_sweeps(const BepArgs &a, int W, cudaStream_t st)
 {
     if (a.n_inst == 0) return cudaSuccess;
     const int grid = (a.n_inst + 63) / 64;
+    // counters of 6 bits serve every tree with at most 63 children per node; wider multifurcations take 20 bits
+    const bool wide = a.max_children > 63;
+#define BEP_FWD(W_) (wide ? bep_forward_kernel<W_, 20><<<grid, 64, 0, st>>>(a) : bep_forward_kernel<W_, 6><<<grid, 64, 0, st>>>(a))
     switch (W) {
-    case 1: bep_forward_kernel<1><<<grid, 64, 0, st>>>(a); bep_backward_kernel<1><<<grid, 64, 0, st>>>(a); break;
-    case 2: bep_forward_kernel<2><<<grid, 64, 0, st>>>(a); bep_backward_kernel<2><<<grid, 64, 0, st>>>(a); break;
-    case 4: bep_forward_kernel<4><<<grid, 64, 0, st>>>(a); bep_backward_kernel<4><<<grid, 64, 0, st>>>(a); break;
-    case 8: bep_forward_kernel<8><<<grid, 64, 0, st>>>(a); bep_backward_kernel<8><<<grid, 64, 0, st>>>(a); break;
+    case 1: BEP_FWD(1); bep_backward_kernel<1><<<grid, 64, 0, st>>>(a); break;
+    case 2: BEP_FWD(2); bep_backward_kernel<2><<<grid, 64, 0, st>>>(a); break;
+    case 4: BEP_FWD(4); bep_backward_kernel<4><<<grid, 64, 0, st>>>(a); break;
+    case 8: BEP_FWD(8); bep_backward_kernel<8><<<grid, 64, 0, st>>>(a); break;
     default: return cudaErrorInvalidValue;
     }
+#undef BEP_FWD
     return cudaGetLastError();
 }
 
@@ -319,7 +322,11 @@ static cudaError_t bep_levels_impl(const BepArgs &a, const int32_t *d_nodes, con
     const unsigned gx = (a.n_inst + 127) / 128;
     for (int h = 0; h < n_levels; h++) {
         const int cnt = level_off[h + 1] - level_off[h];
-        if (cnt > 0) bep_forward_level_kernel<W><<<dim3(gx, cnt < 32768 ? cnt : 32768), 128, 0, st>>>(a, d_nodes + level_off[h], cnt);
+        if (cnt > 0) {
+            const dim3 grid(gx, cnt < 32768 ? cnt : 32768);
+            if (a.max_children > 63) bep_forward_level_kernel<W, 20><<<grid, 128, 0, st>>>(a, d_nodes + level_off[h], cnt);
+            else bep_forward_level_kernel<W, 6><<<grid, 128, 0, st>>>(a, d_nodes + level_off[h], cnt);
+        }
     }
     for (int h = n_levels - 1; h >= 0; h--) {
         const int cnt = level_off[h + 1] - level_off[h];

@@ -17,6 +17,7 @@ struct BepArgs {
     const int32_t *leaf_of_node;         // node -> leaf row or -1
     const int32_t *ent_of_node;          // node -> internal row or -1
     const int32_t *parent;
+    int32_t max_children;                // largest number of children of a node (selects the counter width)
     int32_t recode_null;                 // GRASP.RECODE_NULL: childless nodes without a value carry a NULL symbol
     int32_t max_sym;                     // dictionary capacity (32 * W - 1: one bit is kept for NULL)
     uint8_t *symmap;                     // [n_inst][n_pos + 2] value + 1 -> symbol + 1 (0: no leaf has the value)

@@ -259,7 +259,7 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
     if (!t || !obs || !present_out || n_cols < 1) return fail(BNK_ERR_ARG, "bep: bad argument");
     if (t->root_count != 1 || t->parent[0] >= 0)
         return fail(BNK_ERR_TREE, "bep: the tree must have a single root at index 0 (asr.Parsimony starts at branch point 0)");
-    if (t->max_children > 63) return fail(BNK_ERR_TREE, "bep: at most 63 children per node (the tree has a node with %d)", t->max_children);
+    if (t->max_children >= (1 << 20)) return fail(BNK_ERR_TREE, "bep: at most 2^20 - 1 children per node (the tree has a node with %d)", t->max_children);
     int rc = BNK_OK;
     const int n = t->n, n_pos = n_cols, n_int = t->n_int;
     int ndev = 0;
@@ -346,7 +346,7 @@ static int bep_run(const bnk_tree *t, int32_t n_cols, const uint8_t *obs, int de
         BEP_CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int32_t), st));
         a.inst_e = d_inst_e.p; a.inst_fwd = d_fwd.p; a.n_inst = n_inst; a.n_pos = n_pos; a.n_nodes = n; a.n_leaves = n_leaves; a.n_int = n_int;
         a.nxt = d_nxt.p; a.prv = d_prv.p; a.first = d_first.p; a.kids = d_kids.p; a.leaf_of_node = d_leaf_of_node.p;
-        a.ent_of_node = d_ent.p; a.parent = d_parent.p; a.recode_null = recode_null; a.max_sym = MAXSYM;
+        a.ent_of_node = d_ent.p; a.parent = d_parent.p; a.recode_null = recode_null; a.max_sym = MAXSYM; a.max_children = t->max_children;
         a.dict = d_dict.p; a.nsym = d_nsym.p; a.A = d_A.p; a.B = d_B.p; a.flag = d_flag.p; a.symmap = d_symmap.p;
         BEP_CUDA_TRY(cudaEventRecord(ev0, st));
         BEP_CUDA_TRY(bep_launch_dict(a, st));

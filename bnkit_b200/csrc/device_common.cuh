@@ -163,16 +163,12 @@ cudaError_t launch_tile_bytes(const uint8_t *in, const int32_t *orig_col, const 
 
 // joint up-sweep of the warp-tiled walker with ten lanes per column (3 columns per warp, W <= 14 consumer warps);
 // a.tiles = tiles of one category and at most 3 W columns
-size_t joint10_smem_bytes(int W, int ns, int slots);
-int joint10_cols_per_warp();
-cudaError_t launch_joint_up_10(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st);
 
 // sum-product sweeps of the warp-tiled walker on the FP64 tensor-core path (DMMA.8x8x4): 8 columns per warp,
 // a.tiles = tiles of one category and at most 8 W columns
 size_t mma_walk_smem_bytes(int W, int ns, int slots, bool down);
 int mma_walk_cols_per_warp();
 cudaError_t launch_sum_up_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st);
-cudaError_t launch_sum_down_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st);
 
 struct TracebackArgs {
     const Step *down;

@@ -547,139 +547,6 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
 }
 
 // ------------------------------------------------------------------------------------
-// Max-product up-sweep with TEN lanes per column (lane q owns outputs 2q, 2q + 1; 3 columns per warp).  The
-// joint sweep is bound by the add / compare / select chain, not by shared memory: halving the work of a lane
-// doubles the warps that can hide each other's latency (12 consumer warps per CTA for the same 36 columns).
-// Same arithmetic and scan order as up_warp_kernel<0, C>; vectors in shared memory are plain [column][20].
-// ------------------------------------------------------------------------------------
-namespace {
-constexpr int JCW = 3;  // columns per warp
-__host__ __device__ inline int j_warp_bytes(int slots) { return (2 + slots + 1) * JCW * XK * 8; }
-}  // namespace
-
-__global__ void __launch_bounds__(16 * 32, 1) up_joint10_kernel(const WalkArgs a, const int W, const int ns, const int chb)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TileDesc tile = a.tiles[blockIdx.x];
-    const XGeom g = x_setup(sbase, W, ns, chb);
-    if (warp >= W) {
-        if (warp == W) x_producer_tma<false>(a, tile, g, smem_raw, sbase, ns, lane);
-        else x_producer_obs<false>(a, tile, g, smem_raw, ns, lane);
-        return;
-    }
-    const int c = lane < 30 ? lane / 10 : 2;            // lanes 30, 31 shadow lanes 20, 21
-    const int q = lane < 30 ? lane - 10 * c : lane - 30;
-    int lc = warp * JCW + c;
-    if (lc >= tile.ncols) lc = tile.ncols - 1;
-    const int col = tile.col0 + lc;
-    const int n_steps = a.n_steps;
-    const size_t ncols = (size_t)a.ncols;
-    const int slot_bytes = JCW * XK * 8;
-    const int wbase = XSTAGE0 + ns * g.stage_bytes + warp * j_warp_bytes(a.smem_slots);
-    const int stack0 = wbase + 2 * slot_bytes;
-    const int dummy = stack0 + a.smem_slots * slot_bytes;
-    const int own = c * (XK * 8) + q * 16;  // this lane's pair inside a [column][20] vector
-    const double prior2[2] = {a.prior[2 * q], a.prior[2 * q + 1]};
-
-    int s = 0, ph = 0;
-    unsigned ready = 0;
-    for (int i = 0; i < n_steps; i++) {
-        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
-        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
-        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
-        const bool rootstep = XSTEP(po, parent) < 0;
-        const int so = XSTAGE0 + s * g.stage_bytes;
-        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
-        {
-            const int sn = s + 1 == ns ? 0 : s + 1;
-            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
-        }
-        double cv[2][2];
-        bool isob[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
-            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
-            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
-            isob[e] = false;
-            if (cs >= 0) {
-                const double2 u = XS_D2(stack0 + cs * slot_bytes + own);
-                cv[e][0] = u.x; cv[e][1] = u.y;
-            } else if (cs == SLOT_WIDE) {
-                const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + col;
-                cv[e][0] = src[(size_t)(2 * q) * ncols]; cv[e][1] = src[(size_t)(2 * q + 1) * ncols];
-            } else if (cn >= 0) {
-                const int tb = so + XOBS + XTAB + e * g.chb + q * 16;
-                const int ob = smem_raw[so + e * 64 + lc];
-                if (ob != BNK_NONE) {
-                    const double2 u = XS_D2(tb + ob * (XK * 8));
-                    cv[e][0] = u.x; cv[e][1] = u.y;
-                    isob[e] = true;
-                } else {  // uninstantiated childless node: maximise over its own state
-                    double2 u = XS_D2(tb);
-                    for (int x = 1; x < XK; x++) {
-                        const double2 t = XS_D2(tb + x * (XK * 8));
-                        u.x = t.x > u.x ? t.x : u.x; u.y = t.y > u.y ? t.y : u.y;
-                    }
-                    cv[e][0] = u.x; cv[e][1] = u.y;
-                }
-            } else {
-                cv[e][0] = 0.0; cv[e][1] = 0.0;
-            }
-        }
-        const bool swap = rootstep && !isob[0] && isob[1];  // root: [prior, observed children, unobserved children]
-        const int gb = wbase + (i & 1) * slot_bytes + c * (XK * 8);
-        {
-            double G[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const double c0 = swap ? cv[1][k] : cv[0][k], c1 = swap ? cv[0][k] : cv[1][k];
-                G[k] = ((rootstep ? prior2[k] : 0.0) + c0) + c1;
-            }
-            XS_D2(gb + q * 16) = make_double2(G[0], G[1]);
-        }
-        __syncwarp();
-        double best[2] = {-CUDART_INF, -CUDART_INF};
-        int bi[2] = {0, 0};
-        if (!rootstep) {
-            const int tv = so + XOBS + q * 16;
-#pragma unroll
-            for (int x2 = 0; x2 < XK / 2; x2++) {
-                const double2 gg = XS_D2(gb + x2 * 16);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int x = 2 * x2 + h;
-                    const double gx = h == 0 ? gg.x : gg.y;
-                    const double2 t = XS_D2(tv + x * (XK * 8));
-                    const double v0 = t.x + gx, v1 = t.y + gx;
-                    const bool t0 = v0 > best[0], t1 = v1 > best[1];
-                    best[0] = t0 ? v0 : best[0]; bi[0] = t0 ? x : bi[0];
-                    best[1] = t1 ? v1 : best[1]; bi[1] = t1 ? x : bi[1];
-                }
-            }
-        } else {
-            double b = -CUDART_INF;
-            int bx = 0;
-#pragma unroll
-            for (int x2 = 0; x2 < XK / 2; x2++) {
-                const double2 gg = XS_D2(gb + x2 * 16);
-                const double v0 = 0.0 + gg.x, v1 = 0.0 + gg.y;
-                if (v0 > b) { b = v0; bx = 2 * x2; }
-                if (v1 > b) { b = v1; bx = 2 * x2 + 1; }
-            }
-            best[0] = best[1] = b; bi[0] = bi[1] = bx;
-        }
-        XS_D2((slot >= 0 ? stack0 + slot * slot_bytes : dummy) + own) = make_double2(best[0], best[1]);
-        *reinterpret_cast<uint16_t *>(a.ptr + ((size_t)(unsigned)ent * ncols + col) * XK + 2 * q) = (uint16_t)(bi[0] | (bi[1] << 8));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
-        if (++s == ns) { s = 0; ph ^= 1; }
-    }
-}
-
-// ------------------------------------------------------------------------------------
 // down-sweep (see sweeps.cu for the recurrences): from-above vector D = P^T T, posterior
 // D * prod(children) normalised, T_child = D * prod(siblings)
 // ------------------------------------------------------------------------------------
@@ -1033,147 +900,6 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_mma_kernel(const WalkA
     }
 }
 
-__global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_mma_kernel(const WalkArgs a, const int W, const int ns, const int chb)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TileDesc tile = a.tiles[blockIdx.x];
-    const XGeom g = x_setup(sbase, W, ns, chb);
-    if (warp >= W) {
-        if (warp == W) x_producer_tma<true>(a, tile, g, smem_raw, sbase, ns, lane);
-        else x_producer_obs<true>(a, tile, g, smem_raw, ns, lane);
-        return;
-    }
-    const MLane L(a, tile, warp, lane);
-    const int n_steps = a.n_steps;
-    const size_t ncols = (size_t)a.ncols;
-    const int slot_bytes = MCW * XK * 8;
-    const int stack0 = XSTAGE0 + ns * g.stage_bytes + warp * m_warp_bytes(a.smem_slots);
-    const int dummy = stack0 + a.smem_slots * slot_bytes;
-    const unsigned FULL = 0xffffffffu;
-    double prior3[3];
-#pragma unroll
-    for (int mt = 0; mt < 3; mt++) prior3[mt] = a.prior[8 * mt + L.g < XK ? 8 * mt + L.g : 0];
-
-    int s = 0, ph = 0;
-    unsigned ready = 0;  // result of the early probe of this step's stage
-    for (int i = 0; i < n_steps; i++) {
-        if ((i & 31) == 0) mbar_wait(g.bar_prog + ((i >> 5) & (XPB - 1)) * 8, (i >> 7) & 1);
-        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
-        const int ent = XSTEP(po, ent), slot = XSTEP(po, slot);
-        const bool rootstep = XSTEP(po, parent) < 0;
-        const int so = XSTAGE0 + s * g.stage_bytes;
-        if (!ready) mbar_wait(g.bar_full + s * 8, ph);
-        {   // probe the next stage now: the probe's round trip (a few hundred cycles) hides behind this step
-            const int sn = s + 1 == ns ? 0 : s + 1;
-            ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
-        }
-        // ---- from-above vector D[x][col] = sum_p P[p][x] T[p][col], scaled by a power of two per column ----
-        double D[3][2];
-        if (!rootstep) {
-            const int tsrc = (slot >= 0 ? stack0 + slot * slot_bytes : dummy) + L.g * (XK * 8) + L.xr * 8;
-            double T[5];
-            int mhi = 0;
-#pragma unroll
-            for (int kt = 0; kt < 5; kt++) { T[kt] = XS_D(tsrc + kt * 32); mhi = max(mhi, __double2hiint(T[kt])); }
-            mhi = max(mhi, __shfl_xor_sync(FULL, mhi, 1));
-            mhi = max(mhi, __shfl_xor_sync(FULL, mhi, 2));
-            int eb;
-            const double scale_b = x_pow2_scale(mhi, eb);
-            const int tv = so + XOBS + L.xr * (XK * 8) + L.g * 8;  // P[p = 4 kt + xr][x = 8 mt + g]
-#pragma unroll
-            for (int mt = 0; mt < 3; mt++) {
-                D[mt][0] = 0.0; D[mt][1] = 0.0;
-#pragma unroll
-                for (int kt = 0; kt < 5; kt++) dmma(D[mt][0], D[mt][1], XS_D(tv + kt * (4 * XK * 8) + mt * 64), T[kt]);
-            }
-            const double sc0 = __shfl_sync(FULL, scale_b, 8 * L.xr), sc1 = __shfl_sync(FULL, scale_b, 8 * L.xr + 4);
-#pragma unroll
-            for (int mt = 0; mt < 3; mt++) { D[mt][0] *= sc0; D[mt][1] *= sc1; }
-        } else {
-#pragma unroll
-            for (int mt = 0; mt < 3; mt++) { D[mt][0] = prior3[mt]; D[mt][1] = prior3[mt]; }
-        }
-        // ---- children, in result layout: x = 8 mt + g (rows >= 20 are padding), columns 2 xr + {0, 1} ----
-        double cv[2][3][2];
-        int cslot[2], cent[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int cn = e == 0 ? XSTEP(po, c_node[0]) : XSTEP(po, c_node[1]);
-            const int cs = e == 0 ? XSTEP(po, c_slot[0]) : XSTEP(po, c_slot[1]);
-            const int ce = e == 0 ? XSTEP(po, c_ent[0]) : XSTEP(po, c_ent[1]);
-            cslot[e] = cs; cent[e] = ce;
-            const int area = so + XOBS + XTAB + e * g.chb;
-#pragma unroll
-            for (int c2 = 0; c2 < 2; c2++) {
-                const int ob = (cs != SLOT_WIDE && ce < 0 && cn >= 0) ? (int)smem_raw[so + e * 64 + L.lcc[c2]] : BNK_NONE;
-#pragma unroll
-                for (int mt = 0; mt < 3; mt++) {
-                    const int x = 8 * mt + L.g < XK ? 8 * mt + L.g : XK - 1;  // padding rows repeat row 19 (never stored)
-                    double v;
-                    if (cs == SLOT_WIDE) v = a.msg[((size_t)(unsigned)ce * XK + x) * ncols + L.colc[c2]];
-                    else if (ce >= 0) v = XS_D(area + L.lcc[c2] * (XK * 8) + x * 8);  // up-message that came with the stage
-                    else if (cn >= 0) {
-                        if (ob != BNK_NONE) v = XS_D(area + ob * (XK * 8) + x * 8);
-                        else {
-                            v = 0.0;
-                            for (int y = 0; y < XK; y++) v += XS_D(area + y * (XK * 8) + x * 8);
-                        }
-                    } else v = 1.0;
-                    cv[e][mt][c2] = v;
-                }
-            }
-        }
-        double U[3][2], sum[2] = {0.0, 0.0};
-        const int d0 = cslot[0] >= 0 ? stack0 + cslot[0] * slot_bytes : dummy;
-        const int d1 = cslot[1] >= 0 ? stack0 + cslot[1] * slot_bytes : dummy;
-        // this node's own slot was read above by every lane of the warp before any lane gets here? not necessarily:
-        // order the reads of T before the stores to the children's slots (they never alias T's slot, but dummy may)
-        __syncwarp();
-#pragma unroll
-        for (int mt = 0; mt < 3; mt++) {
-            const int x = 8 * mt + L.g;
-#pragma unroll
-            for (int c2 = 0; c2 < 2; c2++) {
-                const double t0 = D[mt][c2] * cv[1][mt][c2], t1 = D[mt][c2] * cv[0][mt][c2];
-                U[mt][c2] = D[mt][c2] * (cv[0][mt][c2] * cv[1][mt][c2]);
-                if (x < XK) {
-                    sum[c2] += U[mt][c2];
-                    const int off = (2 * L.xr + c2) * (XK * 8) + x * 8;
-                    XS_D(d0 + off) = t0;
-                    XS_D(d1 + off) = t1;
-                    if (cslot[0] == SLOT_WIDE) a.tmsg[((size_t)(unsigned)cent[0] * XK + x) * ncols + L.colc[c2]] = t0;
-                    if (cslot[1] == SLOT_WIDE) a.tmsg[((size_t)(unsigned)cent[1] * XK + x) * ncols + L.colc[c2]] = t1;
-                }
-            }
-        }
-        // ---- normalise and emit the posterior: column totals over the 8 lanes that share xr ----
-        const int q0 = a.qrow ? a.qrow[ent] : ent;
-#pragma unroll
-        for (int c2 = 0; c2 < 2; c2++) {
-            sum[c2] += __shfl_xor_sync(FULL, sum[c2], 4);
-            sum[c2] += __shfl_xor_sync(FULL, sum[c2], 8);
-            sum[c2] += __shfl_xor_sync(FULL, sum[c2], 16);
-        }
-        if (a.out_post && q0 >= 0) {
-#pragma unroll
-            for (int c2 = 0; c2 < 2; c2++) {
-                const double r = x_rcp(sum[c2]);
-                double *dst = a.out_post + ((size_t)(unsigned)q0 * ncols + L.ocolc[c2]) * XK;
-#pragma unroll
-                for (int mt = 0; mt < 3; mt++) {
-                    const int x = 8 * mt + L.g;
-                    if (x < XK) dst[x] = U[mt][c2] * r;
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(g.bar_empty + s * 8);
-        if (++s == ns) { s = 0; ph ^= 1; }
-    }
-}
-
 // ------------------------------------------------------------------------------------
 int warp_walk_cols_per_warp(int C) { return XCW * C; }
 size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down)
@@ -1214,22 +940,6 @@ cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, i
 }
 
 
-// joint up-sweep with ten lanes per column: 3 columns per warp, up to 14 consumer warps
-int joint10_cols_per_warp() { return JCW; }
-size_t joint10_smem_bytes(int W, int ns, int slots)
-{
-    return (size_t)XSTAGE0 + (size_t)ns * x_stage_bytes(XTAB) + (size_t)W * j_warp_bytes(slots);
-}
-cudaError_t launch_joint_up_10(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st)
-{
-    if (W < 1 || W > 14 || ns < 2 || ns > XMAXNS || W * JCW > 64) return cudaErrorInvalidValue;
-    const size_t smem = joint10_smem_bytes(W, ns, a.smem_slots);
-    cudaError_t e = cudaFuncSetAttribute(up_joint10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    up_joint10_kernel<<<n_tiles, (W + 2) * 32, smem, st>>>(a, W, ns, XTAB);
-    return cudaGetLastError();
-}
-
 // DMMA variants: 8 columns per warp, tiles of at most 8 W columns
 int mma_walk_cols_per_warp() { return MCW; }
 size_t mma_walk_smem_bytes(int W, int ns, int slots, bool down)
@@ -1247,6 +957,5 @@ static cudaError_t launch_mma(KernelT kern, const WalkArgs &a, int n_tiles, int 
     return cudaGetLastError();
 }
 cudaError_t launch_sum_up_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st) { return launch_mma(up_mma_kernel, a, n_tiles, W, ns, false, st); }
-cudaError_t launch_sum_down_mma(const WalkArgs &a, int n_tiles, int W, int ns, cudaStream_t st) { return launch_mma(down_mma_kernel, a, n_tiles, W, ns, true, st); }
 
 }  // namespace bnk

@@ -133,18 +133,15 @@ struct bnk_ws {
     std::vector<std::pair<int, int>> chunk_ctiles;
     DevBuf<TileDesc> d_ctiles{&reg};
     // warp-tiled walker (sweeps_warp.cu): tiles of one category, <= 6 * xw columns
-    std::vector<TileDesc> xtiles, mtiles, jtiles;  // mtiles: DMMA sum-product variants (<= 8 * mw columns); jtiles: joint10 (<= 3 * jw)
-    std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles, chunk_jtiles;
-    DevBuf<TileDesc> d_xtiles{&reg}, d_mtiles{&reg}, d_jtiles{&reg};
+    std::vector<TileDesc> xtiles, mtiles;  // mtiles: DMMA sum-product up-sweep (<= 8 * mw columns)
+    std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles;
+    DevBuf<TileDesc> d_xtiles{&reg}, d_mtiles{&reg};
     // lane walker (sweeps_lane.cu): tiles of one category, <= 32 columns; tiled copies of the inputs
     std::vector<TileDesc> ltiles;
     std::vector<std::pair<int, int>> chunk_ltiles;
     DevBuf<TileDesc> d_ltiles{&reg};
     DevBuf<uint8_t> d_obs_t{&reg}, d_present_t{&reg};
-    int jw = 0;                            // consumer warps per CTA of the ten-lanes-per-column joint up-sweep
-    bool joint10 = false;                  // BNK_JOINT10=1: joint up-sweep with ten lanes per column (parity-tested; measured slower: 11.9 vs 10.3 ms on C3b)
     int mw = 0;                            // consumer warps per CTA of the DMMA variants
-    bool mma_down = false;                 // BNK_MMA_DOWN=1: the down-sweep on DMMA too (measured slower: 12.7 vs 11.7 ms on C3b)
     int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
     int walker_mode = 0;                   // BNK_WALKER: 0 auto (= warp-tiled + DMMA), 4 lane walker (sweeps_lane.cu), 1 lean CTA walker,
                                            // 2 warp-tiled with the scalar sum-product kernels (no DMMA), 3 warp-tiled (r1 default)

@@ -265,3 +265,25 @@ def test_gpu_bep_device_assembly_equals_host_assembly(bnk, monkeypatch):
             want, _ = bep.presence_mask(parent.tolist(), rows, obs.shape[1])
             assert np.array_equal(got, np.asarray(want, np.uint8))
     assert crippled > 0
+
+
+@pytest.mark.gpu
+def test_gpu_bep_wide_multifurcations(bnk):
+    """more than 63 children under one ancestor (r1 refused them: 6-bit child counters): a 100-way star and a tree
+    with a 70-way node below the root, both assembly paths"""
+    from oracle import bep
+    rng = np.random.default_rng(12)
+    star = np.array([-1] + [0] * 100, np.int32)
+    mixed = np.array([-1, 0, 0] + [2] * 70 + [1, 1], np.int32)
+    for parent in (star, mixed):
+        n = len(parent)
+        has_child = np.zeros(n, bool)
+        has_child[parent[parent >= 0]] = True
+        obs = np.full((n, 12), NONE, np.uint8)
+        obs[~has_child] = np.where(rng.random((int((~has_child).sum()), 12)) < 0.55, 2, NONE)
+        rows = [None if has_child[v] else (obs[v] != NONE).tolist() for v in range(n)]
+        want, _ = bep.presence_mask(parent.tolist(), rows, 12)
+        tree = bnk.Tree(parent, np.full(n, 0.1))
+        assert np.array_equal(tree.bep_presence(obs), np.asarray(want, np.uint8))
+        mask, graphs = tree.bep_infer(obs)
+        assert np.array_equal(mask, np.asarray(want, np.uint8))

@@ -134,9 +134,7 @@ def test_tile_geometries(bnk, oracle, tile_cols, cpt, monkeypatch):
                                  {"BNK_WARP_W": "1", "BNK_WARP_NS": "4", "BNK_WARP_C": "2"},
                                  {"BNK_WARP_W": "7", "BNK_WARP_NS": "6", "BNK_WARP_C": "1"}, {"BNK_WALKER": "lean"},
                                  {"BNK_WALKER": "scalar"}, {"BNK_MMA_W": "1", "BNK_WARP_NS": "2"}, {"BNK_MMA_W": "3"},
-                                 {"BNK_MMA_W": "7", "BNK_WARP_NS": "5", "BNK_MMA_DOWN": "1"}, {"BNK_MMA_DOWN": "1"},
-                                 {"BNK_JOINT10": "1"}, {"BNK_JOINT10": "1", "BNK_JOINT10_W": "1", "BNK_WARP_NS": "2"},
-                                 {"BNK_JOINT10": "1", "BNK_JOINT10_W": "14"}, {"BNK_WALKER": "lane"}])
+                                 {"BNK_MMA_W": "7", "BNK_WARP_NS": "5"}, {"BNK_WALKER": "lane"}])
 def test_warp_tiled_walker(bnk, oracle, env, monkeypatch):
     """sweeps_warp.cu (warp-owned columns, TMA-fed stage ring; sum-product sweeps on DMMA by default, scalar with
     BNK_WALKER=scalar) against the oracle for every CTA shape and ring depth, and against the lean CTA walker: deep chains (> 4 program chunks), category tiles narrower than a
