@@ -102,6 +102,9 @@ void bnk::ws_free(bnk_ws *ws)
     DeviceGuard guard(ws->device);
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     for (bnk_ws *sub : ws->subs) ws_free(sub);
+    if (ws->copy_stream) { cudaStreamSynchronize(ws->copy_stream); cudaStreamDestroy(ws->copy_stream); }
+    for (auto &e : ws->chunk_done) if (e) cudaEventDestroy(e);
+    for (auto &e : ws->copy_done) if (e) cudaEventDestroy(e);
     ws->subs.clear();
     for (DevBufBase *b : ws->reg.all) b->release();
     for (auto &e : ws->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
@@ -141,7 +144,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_WALKER"))
-        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "lane") == 0 ? 4 : 0)));
+        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "lane") == 0 ? 4 : (std::strcmp(env, "general") == 0 ? 5 : 0))));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
     if (const char *env = std::getenv("BNK_WARP_W")) ws->cfg_xw = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_NS")) ws->cfg_xns = std::atoi(env);
@@ -560,6 +563,9 @@ static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_pre
 {
     const int nc = ws->ncols;
     general = d_present != nullptr || ws->evidence_mode == BNK_EVIDENCE_ANYWHERE;
+    // a presence mask with evidence on childless nodes only (what GRASP produces: per-column forests over extants'
+    // residues) keeps a fast walker for deep trees: the masked lane walker of sweeps_lane.cu
+    ws->masked_only = d_present != nullptr && ws->evidence_mode != BNK_EVIDENCE_ANYWHERE;
     if (ws->evidence_mode == BNK_EVIDENCE_AUTO) {
         int32_t flag = 0;
         CUDA_TRY(cudaMemsetAsync(ws->d_flag.p, 0, sizeof(int32_t), ws->stream));
@@ -569,7 +575,7 @@ static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_pre
         CUDA_TRY(cudaStreamSynchronize(ws->stream));
         if (flag & 2)
             return fail(BNK_ERR_ARG, "observed states must be < %d (the model's alphabet size) or BNK_NONE (255)", ws->K);
-        if (flag & 1) general = true;
+        if (flag & 1) { general = true; ws->masked_only = false; }
     }
     // inputs are consumed in the caller's column order (the kernels index them through orig_col)
     obs_s = d_obs; present_s = d_present;
@@ -676,6 +682,31 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
                                        s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_obs_t.p, ws->stream));
             ws->launches++;
             s.a.obs_t = ws->d_obs_t.p;
+            return BNK_OK;
+        }
+    }
+    if (general && ws->masked_only && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode != 5) {
+        // masked lane walker: per-column forests (presence mask, evidence on childless nodes only).  The wide levels
+        // keep the general level kernels (s.fast stays false); the walk -- all of a deep tree -- leaves the general
+        // walker of sweeps.cu (masked C3b: 115 ms there)
+        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
+        const int slots = use_program(hybrid);
+        if (lane_walk_smem_bytes(slots, want_down) <= (size_t)ws->smem_optin) {
+            s.lane = true; s.hybrid = hybrid;
+            s.n_ltiles = ws->chunk_ltiles[ci].second - ws->chunk_ltiles[ci].first;
+            s.a.tiles = ws->d_ltiles.p + ws->chunk_ltiles[ci].first;
+            s.a.tile_base = ws->chunk_ltiles[ci].first;
+            s.a.tile_stride = (int32_t)ws->ltiles.size() * lane_walk_cols();
+            s.a.smem_slots = slots;
+            CUDA_TRY(ws->d_obs_t.ensure((size_t)ws->n * s.a.tile_stride));
+            CUDA_TRY(ws->d_present_t.ensure((size_t)ws->n * s.a.tile_stride));
+            CUDA_TRY(launch_tile_bytes(obs_s, ws->d_orig_col.p, ws->d_ltiles.p + ws->chunk_ltiles[ci].first, s.n_ltiles,
+                                       s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_obs_t.p, ws->stream));
+            CUDA_TRY(launch_tile_bytes(present_s, ws->d_orig_col.p, ws->d_ltiles.p + ws->chunk_ltiles[ci].first, s.n_ltiles,
+                                       s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_present_t.p, ws->stream));
+            ws->launches += 2;
+            s.a.obs_t = ws->d_obs_t.p;
+            s.a.present_t = ws->d_present_t.p;
             return BNK_OK;
         }
     }

@@ -55,6 +55,11 @@ static int ensure_subs(bnk_ws *ws, int32_t chunk)
     }
     ws->sub_cols = chunk;
     ws->sub_dist_version = 0;
+    if (!ws->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ws->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : ws->chunk_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : ws->copy_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return BNK_OK;
 }
 
@@ -82,8 +87,12 @@ int ws_run_host_range(bnk_ws *ws, const HostCall &hc)
         const int32_t c0 = hc.col0 + (int32_t)((int64_t)hc.ncols * j / n_chunks);
         const int32_t nc = hc.col0 + (int32_t)((int64_t)hc.ncols * (j + 1) / n_chunks) - c0;
         auto body = [&]() -> int {
-            // bnk_set_rates synchronises w's stream: the copies of the chunk it served two rounds ago are done
+            // Results leave on ONE copy stream: chunk j's kernels (stream j & 1) -> event -> its D2H queued behind chunk
+            // j - 1's.  The buffers of this sub-workspace are free again when the copy of chunk j - 2 is done; its
+            // stream waits for that event, the host does not (r2 first cut: both D2H copies ran concurrently on the
+            // two streams, shared PCIe, finished together and left the link idle while the next chunk computed).
             TRY(bnk_set_rates(w, nc, hc.rates ? hc.rates + c0 : nullptr));
+            if (j >= 2) CUDA_TRY(cudaStreamWaitEvent(w->stream, ws->copy_done[j & 1], 0));
             const size_t bytes = (size_t)n * nc;
             CUDA_TRY(w->d_obs_in.ensure(bytes));
             CUDA_TRY(cudaMemcpy2DAsync(w->d_obs_in.p, nc, hc.obs + c0, stride, nc, n, cudaMemcpyHostToDevice, w->stream));
@@ -96,19 +105,25 @@ int ws_run_host_range(bnk_ws *ws, const HostCall &hc)
             if (hc.op == 0) {
                 CUDA_TRY(w->d_state.ensure(bytes));
                 TRY(bnk_joint_dev(w, nc, w->d_obs_in.p, d_present, w->d_state.p));
-                CUDA_TRY(cudaMemcpy2DAsync(hc.out_state + c0, stride, w->d_state.p, nc, nc, n, cudaMemcpyDeviceToHost, w->stream));
+                CUDA_TRY(cudaEventRecord(ws->chunk_done[j & 1], w->stream));
+                CUDA_TRY(cudaStreamWaitEvent(ws->copy_stream, ws->chunk_done[j & 1], 0));
+                CUDA_TRY(cudaMemcpy2DAsync(hc.out_state + c0, stride, w->d_state.p, nc, nc, n, cudaMemcpyDeviceToHost, ws->copy_stream));
+                CUDA_TRY(cudaEventRecord(ws->copy_done[j & 1], ws->copy_stream));
             } else if (hc.op == 1) {
                 const bool want_post = hc.out_post && nq > 0;
                 if (want_post) CUDA_TRY(w->d_post.ensure((size_t)nq * nc * K));
                 if (hc.out_logl) CUDA_TRY(w->d_logl.ensure(nc));
                 TRY(ws_run_sum(w, nc, w->d_obs_in.p, d_present, hc.query_nodes, hc.n_query, want_post ? w->d_post.p : nullptr,
                                hc.out_logl ? w->d_logl.p : nullptr, nullptr));
+                CUDA_TRY(cudaEventRecord(ws->chunk_done[j & 1], w->stream));
+                CUDA_TRY(cudaStreamWaitEvent(ws->copy_stream, ws->chunk_done[j & 1], 0));
                 if (want_post)
                     CUDA_TRY(cudaMemcpy2DAsync(hc.out_post + (size_t)c0 * K, stride * K * sizeof(double), w->d_post.p,
                                                (size_t)nc * K * sizeof(double), (size_t)nc * K * sizeof(double), nq,
-                                               cudaMemcpyDeviceToHost, w->stream));
+                                               cudaMemcpyDeviceToHost, ws->copy_stream));
                 if (hc.out_logl)
-                    CUDA_TRY(cudaMemcpyAsync(hc.out_logl + c0, w->d_logl.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, w->stream));
+                    CUDA_TRY(cudaMemcpyAsync(hc.out_logl + c0, w->d_logl.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, ws->copy_stream));
+                CUDA_TRY(cudaEventRecord(ws->copy_done[j & 1], ws->copy_stream));
             } else {
                 CUDA_TRY(w->d_logl.ensure(nc));
                 TRY(ws_run_sum(w, nc, w->d_obs_in.p, d_present, nullptr, 0, nullptr, w->d_logl.p, w->d_sum.p));
@@ -123,6 +138,10 @@ int ws_run_host_range(bnk_ws *ws, const HostCall &hc)
     for (bnk_ws *sub : ws->subs) {
         const cudaError_t e = cudaStreamSynchronize(sub->stream);
         if (e != cudaSuccess && rc == BNK_OK) rc = fail(BNK_ERR_CUDA, "pipeline: %s", cudaGetErrorString(e));
+    }
+    {
+        const cudaError_t e = cudaStreamSynchronize(ws->copy_stream);
+        if (e != cudaSuccess && rc == BNK_OK) rc = fail(BNK_ERR_CUDA, "pipeline copies: %s", cudaGetErrorString(e));
     }
     if (rc == BNK_OK && hc.out_sum)
         for (double p : partial) *hc.out_sum += p;

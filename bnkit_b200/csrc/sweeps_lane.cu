@@ -19,8 +19,12 @@
 // Arithmetic, association order and scan order are those of the other kernels (and of the oracle): joint adds
 // in child order then L_v[p][x] + G[x], first strict maximum scanning x ascending (argmax_row, wide_common.cuh);
 // sum-product in linear space with an exact 2^-e rescale per (node, column).
-// Lean preconditions (host-checked): nothing masked, evidence on childless nodes only, at most two children per
-// node, one rate category per tile.
+// Preconditions (host-checked): evidence on childless nodes only, at most two children per node, one rate category
+// per tile.  MASKED = true takes a presence mask (per-column forests, Prediction.getTree src/asr/Prediction.java:329-402):
+// the presence bytes of a step's node, its parent and its two children ride in the stage next to the observed
+// states, and every thread classifies its column -- absent / not connected (KIND_NONE), component root (KIND_ROOT:
+// the prior joins, the log-likelihood or the root state closes the component) or message (KIND_MSG) -- exactly as
+// the general walker of sweeps.cu does; absent children contribute the unit vector.
 #include "wide_common.cuh"
 
 #include <cstddef>
@@ -103,7 +107,7 @@ struct LaneCtx {
 // Requests everything step j needs into its ring stage (commit is the caller's).  DOWN = false: the up-sweeps
 // (node table and child tables from a.T_row; messages of SLOT_WIDE children from a.msg); DOWN = true: the
 // down-sweep (node table from a.T_row = P^T, child tables from a.T_aux = P, messages of ALL internal children).
-template <bool DOWN>
+template <bool DOWN, bool MASKED>
 __device__ __forceinline__ void issue_step(const WalkArgs &a, const LaneCtx &c, unsigned char *smem, unsigned sbase, int j)
 {
     if (j >= a.n_steps) return;
@@ -112,6 +116,12 @@ __device__ __forceinline__ void issue_step(const WalkArgs &a, const LaneCtx &c, 
     const unsigned sb = sbase + L_PROG + (j % LNS) * L_STAGE;
     const size_t ncols = (size_t)a.ncols;
     if (parent >= 0) copy_table(sb + L_OBS, a.T_row + c.cat_off + (size_t)(unsigned)node * (LK * LK), c.tid);
+    if (MASKED && c.tid >= 8 && c.tid < 16) {
+        // presence rows of the stage: 2 = node, 3 = parent, 4 / 5 = children (32 bytes each, two 16-byte pieces)
+        const int r = (c.tid - 8) >> 1, half = (c.tid - 8) & 1;
+        const int who = r == 0 ? node : (r == 1 ? parent : (r == 2 ? LREC(po, c_node[0]) : LREC(po, c_node[1])));
+        if (who >= 0) cp16(sb + (2 + r) * 32 + half * 16, a.present_t + (size_t)(unsigned)who * a.tile_stride + c.tile_col + half * 16);
+    }
     const double *ctab = DOWN ? a.T_aux : a.T_row;
 #pragma unroll
     for (int e = 0; e < 2; e++) {
@@ -194,7 +204,7 @@ int lane_walk_cols() { return LCOLS; }
 // ------------------------------------------------------------------------------------
 // up-sweeps.  MODE 0: max-product in log space (joint), MODE 1: sum-product, linear, rescaled.
 // ------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
 #pragma unroll
     for (int j = 0; j < LD; j++) {
         if (j == 0) copy_prog(sbase, a.up, n_steps, 1, c.tid);
-        issue_step<false>(a, c, smem, sbase, j);
+        issue_step<false, MASKED>(a, c, smem, sbase, j);
         cp_commit();
     }
     int esum = 0;
@@ -227,15 +237,29 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
         cp_wait<LD - 1>();  // this thread's copies for step i have landed ...
         cta_bar();          // ... and everybody's; the message written by step i - 1 is visible
         if ((i % LPCH) == 0 && i > 0) copy_prog(sbase, a.up, n_steps, i / LPCH + 1, c.tid);
-        issue_step<false>(a, c, smem, sbase, i + LD);
+        issue_step<false, MASKED>(a, c, smem, sbase, i + LD);
         cp_commit();
 
         const int po = rec_off(i);
         const int ent = LREC(po, ent), slot = LREC(po, slot);
-        const bool rootstep = LREC(po, parent) < 0;
-        const int cn0 = LREC(po, c_node[0]), cn1 = LREC(po, c_node[1]);
-        const int cs0 = LREC(po, c_slot[0]), cs1 = LREC(po, c_slot[1]);
         const int so = L_PROG + (i % LNS) * L_STAGE;
+        int cn0 = LREC(po, c_node[0]), cn1 = LREC(po, c_node[1]);
+        const int cs0 = LREC(po, c_slot[0]), cs1 = LREC(po, c_slot[1]);
+        // this column's case: root-like when the parent is absent (or there is none); children that are absent in
+        // this column vanish (cn < 0 from here on); KIND_NONE = the node is absent or has no BN variable
+        bool rootstep = LREC(po, parent) < 0;
+        int kind = rootstep ? KIND_ROOT : KIND_MSG;
+        if (MASKED) {
+            const bool pv = smem[so + 2 * 32 + c.lane] != 0;
+            if (!rootstep && smem[so + 3 * 32 + c.lane] == 0) rootstep = true;
+            if (cn0 >= 0 && smem[so + 4 * 32 + c.lane] == 0) cn0 = -1;
+            if (cn1 >= 0 && smem[so + 5 * 32 + c.lane] == 0) cn1 = -1;
+            kind = !pv ? KIND_NONE : (rootstep ? ((cn0 < 0 && cn1 < 0) ? KIND_NONE : KIND_ROOT) : KIND_MSG);
+            if (c.warp == 0 && c.valid) {
+                if (MODE == 0) a.kind[(size_t)(unsigned)ent * ncols + c.col] = (uint8_t)kind;
+                else if (a.kindm) a.kindm[(size_t)(unsigned)ent * ncols + c.col] = (uint8_t)kind;
+            }
+        }
 
         // ---- fold the (at most two) children: G lives in registers, identical in the four warps ----
         double G[LK];
@@ -260,7 +284,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
         const int tv = so + L_OBS;
         if (MODE == 0) {
             uint8_t *pr = a.ptr + ((size_t)(unsigned)ent * ncols + c.col) * LK + c.warp * LPW;
-            if (!rootstep) {
+            if (kind == KIND_MSG) {
 #pragma unroll
                 for (int k = 0; k < LPW; k++) {
                     const int p = c.warp * LPW + k;
@@ -270,7 +294,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
                     LS_F64(sdst + p * (LCOLS * 8)) = best;
                     if (c.valid) pr[k] = (uint8_t)bi;
                 }
-            } else {  // unit table: every output is max_x G[x]
+            } else if (kind == KIND_ROOT) {  // unit table: every output is max_x G[x]
                 double b = -CUDART_INF;
                 int bx = 0;
 #pragma unroll
@@ -284,14 +308,14 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
                     if (c.valid) pr[k] = (uint8_t)bx;
                 }
             }
-        } else {
+        } else if (kind != KIND_NONE) {
             int mhi = 0;
 #pragma unroll
             for (int x = 0; x < LK; x++) mhi = max(mhi, __double2hiint(G[x]));
             int e;
             const double scale = l_pow2_scale(mhi, e);
             esum += e;
-            if (!rootstep) {
+            if (kind == KIND_MSG) {
 #pragma unroll
                 for (int k = 0; k < LPW; k++) {
                     const int p = c.warp * LPW + k;
@@ -317,13 +341,15 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_up_kernel(const WalkArgs a)
     }
     if (MODE == 1 && a.out_logl && c.warp == 0 && c.valid) {
         const int ew = a.esum_wide ? a.esum_wide[c.col] : 0;
-        a.out_logl[c.ocol] = logacc + (double)(esum + ew) * 0.693147180559945309417232121458;
+        const double lw = (MASKED && a.logl_wide) ? a.logl_wide[c.col] : 0.0;   // components closed inside the wide levels
+        a.out_logl[c.ocol] = logacc + lw + (double)(esum + ew) * 0.693147180559945309417232121458;
     }
 }
 
 // ------------------------------------------------------------------------------------
 // down-sweep: T (from above, stack) -> D = P^T T -> posterior, and the from-above vectors of internal children
 // ------------------------------------------------------------------------------------
+template <bool MASKED>
 __global__ void __launch_bounds__(LTHREADS, 2) lane_down_kernel(const WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -346,7 +372,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_down_kernel(const WalkArgs a
 #pragma unroll
     for (int j = 0; j < LD; j++) {
         if (j == 0) copy_prog(sbase, a.down, n_steps, 1, c.tid);
-        issue_step<true>(a, c, smem, sbase, j);
+        issue_step<true, MASKED>(a, c, smem, sbase, j);
         cp_commit();
     }
     // the posterior of step i is normalised and stored after the barrier of step i + 1: warp w then owns tile
@@ -374,15 +400,26 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_down_kernel(const WalkArgs a
         cp_wait<LD - 1>();
         cta_bar();
         if ((i % LPCH) == 0 && i > 0) copy_prog(sbase, a.down, n_steps, i / LPCH + 1, c.tid);
-        issue_step<true>(a, c, smem, sbase, i + LD);
+        issue_step<true, MASKED>(a, c, smem, sbase, i + LD);
         cp_commit();
         if (i > 0) emit(i - 1, q_prev);
 
         const int po = rec_off(i);
         const int ent = LREC(po, ent), slot = LREC(po, slot);
-        const bool rootstep = LREC(po, parent) < 0;
         const int so = L_PROG + (i % LNS) * L_STAGE;
         q_prev = a.qrow ? a.qrow[ent] : ent;
+        // the same classification as in the up-sweep (no evidence on nodes with children): absent children count
+        // as the unit vector and receive nothing; a node without a BN variable emits NaN and pushes nothing
+        bool rootstep = LREC(po, parent) < 0;
+        bool pu[2] = {true, true};
+        bool none = false;
+        if (MASKED) {
+            const bool pv = smem[so + 2 * 32 + c.lane] != 0;
+            if (!rootstep && smem[so + 3 * 32 + c.lane] == 0) rootstep = true;
+            pu[0] = LREC(po, c_node[0]) >= 0 && smem[so + 4 * 32 + c.lane] != 0;
+            pu[1] = LREC(po, c_node[1]) >= 0 && smem[so + 5 * 32 + c.lane] != 0;
+            none = !pv || (rootstep && !pu[0] && !pu[1]);
+        }
 
         // ---- D[x] = sum_p P[p][x] T[p] for this warp's five x ----
         double D[LPW];
@@ -415,9 +452,10 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_down_kernel(const WalkArgs a
         bool push[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int cn = e == 0 ? LREC(po, c_node[0]) : LREC(po, c_node[1]);
+            int cn = e == 0 ? LREC(po, c_node[0]) : LREC(po, c_node[1]);
             const int ce = e == 0 ? LREC(po, c_ent[0]) : LREC(po, c_ent[1]);
-            push[e] = cn >= 0 && ce >= 0;
+            if (MASKED && !pu[e]) cn = -1;
+            push[e] = cn >= 0 && ce >= 0 && !none;
             const int area = so + L_OBS + L_TAB + e * L_CH;
             if (cn < 0) {
 #pragma unroll
@@ -456,7 +494,8 @@ __global__ void __launch_bounds__(LTHREADS, 2) lane_down_kernel(const WalkArgs a
         }
         const int ub = ut0 + (i & 1) * L_UT + c.lane * 8;
 #pragma unroll
-        for (int k = 0; k < LPW; k++) LS_F64(ub + (c.warp * LPW + k) * (L_UROW * 8)) = D[k] * (g[0][k] * g[1][k]);
+        for (int k = 0; k < LPW; k++)
+            LS_F64(ub + (c.warp * LPW + k) * (L_UROW * 8)) = (MASKED && none) ? CUDART_NAN : D[k] * (g[0][k] * g[1][k]);
     }
     cta_bar();
     emit(n_steps - 1, q_prev);
@@ -496,17 +535,21 @@ static cudaError_t launch_lane(KernelT kern, const WalkArgs &a, int n_tiles, siz
     return cudaGetLastError();
 }
 
+// a.present_t != nullptr selects the masked kernels
 cudaError_t launch_lane_up(int mode, const WalkArgs &a, int n_tiles, cudaStream_t st)
 {
     if (n_tiles == 0) return cudaSuccess;
     const size_t smem = lane_walk_smem_bytes(a.smem_slots, false);
-    return mode == 0 ? launch_lane(lane_up_kernel<0>, a, n_tiles, smem, st) : launch_lane(lane_up_kernel<1>, a, n_tiles, smem, st);
+    if (a.present_t)
+        return mode == 0 ? launch_lane(lane_up_kernel<0, true>, a, n_tiles, smem, st) : launch_lane(lane_up_kernel<1, true>, a, n_tiles, smem, st);
+    return mode == 0 ? launch_lane(lane_up_kernel<0, false>, a, n_tiles, smem, st) : launch_lane(lane_up_kernel<1, false>, a, n_tiles, smem, st);
 }
 
 cudaError_t launch_lane_down(const WalkArgs &a, int n_tiles, cudaStream_t st)
 {
     if (n_tiles == 0) return cudaSuccess;
-    return launch_lane(lane_down_kernel, a, n_tiles, lane_walk_smem_bytes(a.smem_slots, true), st);
+    const size_t smem = lane_walk_smem_bytes(a.smem_slots, true);
+    return a.present_t ? launch_lane(lane_down_kernel<true>, a, n_tiles, smem, st) : launch_lane(lane_down_kernel<false>, a, n_tiles, smem, st);
 }
 
 }  // namespace bnk

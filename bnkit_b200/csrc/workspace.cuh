@@ -93,6 +93,8 @@ struct bnk_ws {
     bool own_stream = false;
     int64_t launches = 0;
     std::vector<bnk_ws *> subs;  // column-chunk workspaces of the pipelined host-buffer path (owned)
+    cudaStream_t copy_stream = nullptr;          // result copies of the pipelined path: one queue, so that a chunk's D2H never
+    cudaEvent_t chunk_done[2] = {}, copy_done[2] = {};  // shares PCIe with its neighbour's and kernels restart as soon as a buffer is free
     int32_t pipeline_cols = 0;   // bnk_ws_set_pipeline: 0 automatic, < 0 off, > 0 columns per chunk
     int32_t sub_cols = 0;        // max_cols the sub-workspaces were created with
     uint64_t dist_version = 0, sub_dist_version = 0;  // bnk_set_distances calls seen / forwarded to the subs
@@ -111,6 +113,7 @@ struct bnk_ws {
     DevBuf<int32_t> d_parent{&reg}, d_node_of_ent{&reg}, d_leaf_nodes{&reg}, d_leaf_parent{&reg};
     DevBuf<uint8_t> d_has_child{&reg};                        // [n] 1 = the node has children (an ancestor)
     int evidence_mode = BNK_EVIDENCE_AUTO;                    // bnk_ws_set_evidence_mode
+    bool masked_only = false;                                 // last prepare_inputs: presence mask, evidence on childless nodes only
     bool retile = false;                                      // bnk_ws_configure changed the geometry: re-tile the current rates
     DevBuf<double> d_dist{&reg};
     std::vector<double> dist;

@@ -448,3 +448,41 @@ def test_device_tables_against_an_independent_matrix_exponential(bnk, name):
         big = want > 1e-3
         assert np.abs(L[i][big] - np.log(want[big])).max() < 1e-9, (name, t)
     ws.close()
+
+
+@pytest.mark.parametrize("walker", ["", "general"])
+def test_masked_walker_per_column_forests(bnk, oracle, walker, monkeypatch):
+    """Per-column forests (presence masks, evidence on extants only) through the masked lane walker (default) and
+    the general walker (BNK_WALKER=general): a 700-level caterpillar (walker only, > 20 program chunks), a balanced
+    tree (general level kernels + walker for the top), irregular binary trees with per-column rates, uninstantiated
+    present extants, fully absent columns and a column where only one extant is present -- against the oracle."""
+    from bnkit_b200 import synth
+    if walker:
+        monkeypatch.setenv("BNK_WALKER", walker)
+    rng = np.random.default_rng(71)
+    m, om = bnk.Model("LG"), oracle.Model("LG")
+    cases = [synth.caterpillar_tree(700, seed=5), synth.balanced_tree(700, seed=6), random_tree(rng, 300), random_tree(rng, 37)]
+    for k, (parent, dist) in enumerate(cases):
+        n_cols = [97, 130, 64, 33][k]
+        obs = random_obs(rng, parent, n_cols, 20, gap_prob=0.35, few_states=7)
+        present = random_present(rng, parent, obs, absent_prob=[0.25, 0.3, 0.5, 0.15][k])
+        leaf = leaves_of(parent)
+        # present extants without a state (maximised / marginalised), an all-absent column, a single present extant
+        un = (rng.random(obs.shape) < 0.03) & leaf[:, None] & (present == 1)
+        obs[un] = NONE
+        present[:, 0] = 0
+        present[:, 1] = 0
+        present[np.nonzero(leaf)[0][0], 1] = 1
+        rates = rng.choice([0.4, 1.0, 2.2], n_cols) if k >= 2 else None
+        ws = bnk.Workspace(m, bnk.Tree(parent, dist), n_cols)
+        ws.set_rates(n_cols, rates)
+        got = ws.joint(obs, present)
+        want = oracle.fast_joint(om, parent, dist, obs, present, rates, nthreads=8)
+        assert np.array_equal(got, want), "case %d: joint states differ at %d entries" % (k, (got != want).sum())
+        post, logl = ws.marginal(obs, present)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, present, rates, nthreads=8)
+        _post_close(post, wpost[~leaf])
+        assert np.allclose(logl, wlogl, rtol=TOL, atol=1e-12)
+        one, _ = ws.marginal(obs, present, query=[int(np.nonzero(~leaf)[0][-1])], want_logl=False)
+        _post_close(one, wpost[[int(np.nonzero(~leaf)[0][-1])]])
+        ws.close()

@@ -22,4 +22,9 @@ ncu --set full --clock-control none --import-source on -k regex:"down_wide_kerne
 ncu --set full --clock-control none --import-source on -k regex:"warp_kernel|mma_kernel|traceback_kernel" -c 4 -o gpurun_out/prof_${tag}_walker python bench.py --workload c3b --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu4_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"indel" -c 14 -o gpurun_out/prof_${tag}_indel python tools/bench_indel.py --evals 1 --parity-cols 0 > gpurun_out/ncu5_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"bep_reach|bep_forward_level|bep_backward_level" -c 8 -o gpurun_out/prof_${tag}_bep python tools/bench_bep.py --cpu-budget 0 > gpurun_out/ncu6_$tag.log 2>&1
+# gpurun merges at most 64 MiB back: keep the raw-metric pages as CSV and drop the reports
+for r in wide walker indel bep; do
+  ncu -i gpurun_out/prof_${tag}_$r.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_${r}_raw.csv 2>/dev/null
+  rm -f gpurun_out/prof_${tag}_$r.ncu-rep
+done
 ls -la gpurun_out/*$tag* | awk '{print $5, $9}'

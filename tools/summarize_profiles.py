@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise gpurun_out ncu artefacts into profiles/ (tracked).
 
-    python tools/summarize_profiles.py <tag> <launches.csv> <bench.json> <report.ncu-rep> [more reports ...]
+    python tools/summarize_profiles.py <tag> <launches.csv> <bench.json> <report.ncu-rep | raw.csv> [more reports ...]
 """
 import csv, json, shutil, subprocess, sys
 from collections import defaultdict
@@ -38,7 +38,10 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 
 rr = None
 for rep in reps:
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.suffix == ".csv":   # the raw page exported on the GPU box (tools/gpu_round.sh keeps these: the reports exceed gpurun's 64 MiB)
+        raw = rep.read_text()
+    else:
+        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     part = list(csv.reader(raw.splitlines()))
     if len(part) < 3:
         continue
