@@ -28,6 +28,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <thread>
 
 namespace bnk {
 namespace {
@@ -280,6 +281,9 @@ struct bnk_indel {
     DevBuf<double> d_dist{&reg}, d_gm{&reg}, d_A{&reg}, d_del{&reg}, d_ins{&reg}, d_msg{&reg}, d_logl{&reg}, d_probs{&reg};
     DevBuf<uint8_t> d_obs{&reg}, d_cg{&reg};
     std::vector<double> h_logl;
+    // bnk_indel_create_multi: this handle is a front; every part owns one device and a contiguous block of columns
+    std::vector<bnk_indel *> parts;
+    std::vector<int32_t> part_col0;      // [parts + 1]
     cudaEvent_t ev[3] = {};
     float ms_tables = 0, ms_sweep = 0;
     GapModelDev gmd() const
@@ -302,6 +306,9 @@ int upload_vec(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st)
 void indel_free(bnk_indel *h)
 {
     if (!h) return;
+    for (bnk_indel *p : h->parts) indel_free(p);
+    h->parts.clear();
+    if (!h->stream && h->reg.all.empty() && !h->tree) { delete h; return; }
     DeviceGuard guard(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -330,8 +337,47 @@ int logm1exp(double x, double *out)
 
 // tables for `rate`, then the sweep over the uploaded columns + the all-gap column; leaves the column
 // log-likelihoods in h->h_logl (ncols + 1 values)
+int run_sweep(bnk_indel *h, double rate, double geom);
+
+// the front of a multi-device handle: every part sweeps its column block on its own device at the same time (one
+// host thread each; the parts share nothing), then the column values are laid end to end -- so every sum over
+// columns downstream runs in column order whatever the number of devices (the reduction of
+// IndelPeeler.calcProbAlnGivenTree, src/asr/IndelPeeler.java:131-136; 8 bytes per column come back anyway)
+int run_sweep_multi(bnk_indel *h, double rate, double geom)
+{
+    if (h->ncols < 0) return fail(BNK_ERR_STATE, "indel: no alignment uploaded (bnk_indel_set_alignment)");
+    const size_t np = h->parts.size();
+    std::vector<int> rcs(np, BNK_OK);
+    std::vector<std::string> msgs(np);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < np; i++)
+        th.emplace_back([&, i] {
+            bnk_indel *p = h->parts[i];
+            if (p->ncols < 0) return;   // more devices than columns
+            DeviceGuard guard(p->device);
+            rcs[i] = guard.err == cudaSuccess ? run_sweep(p, rate, geom) : BNK_ERR_CUDA;
+            if (rcs[i] != BNK_OK) msgs[i] = bnk_last_error();
+        });
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < np; i++)
+        if (rcs[i] != BNK_OK) return fail(rcs[i], "indel (device %d): %s", h->parts[i]->device, msgs[i].c_str());
+    h->h_logl.assign((size_t)h->ncols + 1, 0.0);
+    h->ms_tables = 0; h->ms_sweep = 0; h->launches = 0;
+    for (size_t i = 0; i < np; i++) {
+        bnk_indel *p = h->parts[i];
+        if (p->ncols < 0) continue;
+        std::memcpy(h->h_logl.data() + h->part_col0[i], p->h_logl.data(), sizeof(double) * p->ncols);
+        if (i == 0) h->h_logl[h->ncols] = p->h_logl[p->ncols];   // the all-gap column: the same on every device
+        h->ms_tables = std::max(h->ms_tables, p->ms_tables);
+        h->ms_sweep = std::max(h->ms_sweep, p->ms_sweep);
+        h->launches += p->launches;
+    }
+    return BNK_OK;
+}
+
 int run_sweep(bnk_indel *h, double rate, double geom)
 {
+    if (!h->parts.empty()) return run_sweep_multi(h, rate, geom);
     if (h->ncols < 0) return fail(BNK_ERR_STATE, "indel: no alignment uploaded (bnk_indel_set_alignment)");
     if (!h->model_set) return fail(BNK_ERR_STATE, "indel: no indel rates set (bnk_indel_set_rates)");
     if (!(geom > 0.0)) return fail(BNK_ERR_ARG, "indel: the geometric sequence-length parameter must be > 0");
@@ -403,6 +449,16 @@ int aln_logl(bnk_indel *h, double geom, double *out)
 
 int set_rates(bnk_indel *h, double mu, double lambda)
 {
+    if (!h->parts.empty()) {
+        TRY(gap_model_from_base(&h->base, mu, lambda, &h->gm));   // the front keeps the host model (probExtraCol)
+        for (bnk_indel *p : h->parts) {
+            DeviceGuard guard(p->device);
+            if (guard.err != cudaSuccess) return fail(BNK_ERR_CUDA, "indel: cudaSetDevice(%d)", p->device);
+            TRY(set_rates(p, mu, lambda));
+        }
+        h->model_set = true;
+        return BNK_OK;
+    }
     TRY(gap_model_from_base(&h->base, mu, lambda, &h->gm));
     const int K1 = h->K1;
     std::vector<double> pack((size_t)2 * K1 * K1 + 2 * K1);
@@ -488,12 +544,62 @@ extern "C" int bnk_indel_create(const bnk_model *base, const bnk_tree *tree, int
     return BNK_OK;
 }
 
-extern "C" void bnk_indel_destroy(bnk_indel *h) { indel_free(h); }
+// All devices behind one handle (the GPU counterpart of GRASP.NTHREADS in runPeelingJobs, IndelPeeler.java:208-224):
+// contiguous column blocks, one per device; n_devices <= 0 = every visible device
+extern "C" int bnk_indel_create_multi(const bnk_model *base, const bnk_tree *tree, int32_t max_cols, int n_devices,
+                                      const int *devices_or_null, bnk_indel **out)
+{
+    if (!base || !tree || !out) return fail(BNK_ERR_ARG, "indel: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(BNK_ERR_CUDA, "indel: no CUDA device"); }
+    if (n_devices <= 0) n_devices = ndev;
+    if (!devices_or_null && n_devices > ndev) return fail(BNK_ERR_ARG, "indel: %d devices asked for, %d visible", n_devices, ndev);
+    bnk_indel *h = new (std::nothrow) bnk_indel();
+    if (!h) return fail(BNK_ERR_NOMEM, "indel: out of host memory");
+    h->base = *base;
+    h->K = base->K; h->K1 = base->K + 1; h->n = tree->n; h->n_int = tree->n_int; h->max_cols = max_cols;
+    const int32_t per = (max_cols + n_devices - 1) / n_devices;
+    for (int i = 0; i < n_devices; i++) {
+        bnk_indel *p = nullptr;
+        const int rc = bnk_indel_create(base, tree, std::max(per, 1), devices_or_null ? devices_or_null[i] : i, &p);
+        if (rc != BNK_OK) { indel_free(h); return rc; }
+        h->parts.push_back(p);
+    }
+    h->device = h->parts[0]->device;
+    h->tree = h->parts[0]->tree;   // probExtraCol reads the tree; the parts hold the references
+    *out = h;
+    return BNK_OK;
+}
+
+extern "C" void bnk_indel_destroy(bnk_indel *h)
+{
+    if (h && !h->parts.empty()) h->tree = nullptr;   // a front borrows its tree pointer from part 0
+    indel_free(h);
+}
 
 extern "C" int bnk_indel_set_alignment(bnk_indel *h, int32_t n_cols, const uint8_t *obs)
 {
     if (!h || !obs) return fail(BNK_ERR_ARG, "indel: null argument");
     if (n_cols < 1 || n_cols > h->max_cols) return fail(BNK_ERR_ARG, "indel: n_cols %d outside 1..%d", n_cols, h->max_cols);
+    if (!h->parts.empty()) {
+        // contiguous blocks whose sizes differ by at most one (the rule of bnk_mgpu_shard / dist.shard_columns)
+        const int np = (int)h->parts.size();
+        h->part_col0.assign(np + 1, 0);
+        std::vector<uint8_t> block;
+        for (int i = 0; i < np; i++) {
+            const int32_t base_w = n_cols / np, rem = n_cols % np;
+            const int32_t lo = i * base_w + std::min(i, rem), w = base_w + (i < rem ? 1 : 0);
+            h->part_col0[i] = lo; h->part_col0[i + 1] = lo + w;
+            bnk_indel *p = h->parts[i];
+            p->ncols = -1;
+            if (w == 0) continue;
+            block.resize((size_t)h->n * w);
+            for (int v = 0; v < h->n; v++) std::memcpy(block.data() + (size_t)v * w, obs + (size_t)v * n_cols + lo, w);
+            TRY(bnk_indel_set_alignment(p, w, block.data()));
+        }
+        h->ncols = n_cols;
+        return BNK_OK;
+    }
     ENTER_DEVICE(h->device);
     const bnk_tree *t = h->tree;
     for (int v = 0; v < h->n; v++) {   // validate the extants' rows (a byte >= K would index past a table)

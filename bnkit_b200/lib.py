@@ -40,7 +40,7 @@ SYMBOLS = [
     "bnk_mgpu_create", "bnk_mgpu_destroy", "bnk_mgpu_n_devices", "bnk_mgpu_shard", "bnk_mgpu_set_rates",
     "bnk_mgpu_set_distances", "bnk_mgpu_joint", "bnk_mgpu_marginal", "bnk_mgpu_loglik", "bnk_mgpu_upload",
     "bnk_mgpu_loglik_resident", "bnk_mgpu_reduction", "bnk_mgpu_launch_count",
-    "bnk_indel_base_model", "bnk_indel_create", "bnk_indel_destroy", "bnk_indel_set_alignment", "bnk_indel_set_rates", "bnk_indel_column_logl",
+    "bnk_indel_base_model", "bnk_indel_create", "bnk_indel_create_multi", "bnk_indel_destroy", "bnk_indel_set_alignment", "bnk_indel_set_rates", "bnk_indel_column_logl",
     "bnk_indel_column_priors", "bnk_indel_aln_logl", "bnk_indel_optimise_mulambda", "bnk_indel_probs",
     "bnk_indel_phase_ms", "bnk_indel_launch_count", "bnk_indel_device_bytes",
 ]
@@ -117,6 +117,7 @@ def lib():
     L.bnk_mgpu_launch_count.restype = C.c_int64
     L.bnk_indel_base_model.argtypes = [C.c_char_p, C.POINTER(_vp)]
     L.bnk_indel_create.argtypes = [_vp, _vp, C.c_int32, C.c_int, C.POINTER(_vp)]
+    L.bnk_indel_create_multi.argtypes = [_vp, _vp, C.c_int32, C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
     L.bnk_indel_destroy.argtypes = [_vp]
     L.bnk_indel_destroy.restype = None
     L.bnk_indel_set_alignment.argtypes = [_vp, C.c_int32, _bp]
@@ -394,10 +395,18 @@ class Workspace:
 class Indel:
     """bnk_indel handle: gap-augmented peeling (asr.IndelPeeler under bn.ctmc.GapSubstModel) of one alignment"""
 
-    def __init__(self, model, tree, max_cols, device=-1):
+    def __init__(self, model, tree, max_cols, device=-1, n_devices=None, devices=None):
+        """n_devices / devices given: one handle over several devices (bnk_indel_create_multi; 0 = all visible)"""
         self.model, self.tree = model, tree
         h = _vp()
-        check(lib().bnk_indel_create(model.h, tree.h, int(max_cols), int(device), C.byref(h)))
+        if n_devices is None and devices is None:
+            check(lib().bnk_indel_create(model.h, tree.h, int(max_cols), int(device), C.byref(h)))
+        else:
+            arr = None
+            if devices is not None:
+                arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+                n_devices = len(devices)
+            check(lib().bnk_indel_create_multi(model.h, tree.h, int(max_cols), int(n_devices), arr, C.byref(h)))
         self.h = h
         self.K, self.n, self.n_cols = model.K, tree.n, 0
 

@@ -502,11 +502,14 @@ class Prediction:
         return self._ws
 
     def getJoint(self, model, rates=None):
-        """Object[][] states[bpidx][pos]: Character from model.getDomain() or None (Prediction.java:614-649)."""
+        """Object[][] states[bpidx][pos]: Character from model.getDomain() or None (Prediction.java:614-649).  As in the
+        reference only the ancestors' rows are filled (`for idx in getAncestorIndices()`, :636-641): extants' rows stay
+        None -- the library's own output also carries the observed characters there (bnk_joint passes them through)."""
         ws = self._workspace(model, rates)
         st = ws.joint(self._obs(model), self.present)
         dom = model.domain
-        self.joint_states = [[None if s == NONE else dom[s] for s in row] for row in st]
+        leaf = [self.tree.isLeaf(v) for v in range(self.tree.getSize())]
+        self.joint_states = [[None] * self.n_cols if leaf[v] else [None if s == NONE else dom[s] for s in row] for v, row in enumerate(st)]
         return self.joint_states
 
     def getMarginal(self, ancestor, model, rates=None):

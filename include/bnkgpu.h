@@ -249,6 +249,11 @@ int64_t bnk_mgpu_launch_count(const bnk_mgpu *g);
 typedef struct bnk_indel bnk_indel;
 int bnk_indel_base_model(const char *name, bnk_model **out);
 int bnk_indel_create(const bnk_model *base, const bnk_tree *t, int32_t max_cols, int device, bnk_indel **out);
+/* every device of the node behind one handle (GRASP.NTHREADS -> ThreadedPeeler, IndelPeeler.java:208-224): contiguous
+ * column blocks, one per device, swept concurrently; every other bnk_indel_* call works on the handle unchanged and
+ * sums over columns run in column order whatever the device count.  n_devices <= 0: all visible devices. */
+int bnk_indel_create_multi(const bnk_model *base, const bnk_tree *t, int32_t max_cols, int n_devices,
+                           const int *devices_or_null, bnk_indel **out);
 void bnk_indel_destroy(bnk_indel *h);
 int bnk_indel_set_alignment(bnk_indel *h, int32_t n_cols, const uint8_t *obs);
 int bnk_indel_set_rates(bnk_indel *h, double mu, double lambda);

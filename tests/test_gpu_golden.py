@@ -121,7 +121,9 @@ def test_prediction_batch_entry_points(bnk, oracle):
     pred = Prediction(tree, states, present)
     joint = pred.getJoint(model)
     want = oracle.fast_joint(oracle.Model("LG"), parent, dist, obs, present)
-    assert [[None if s == NONE else AA[s] for s in row] for row in want] == joint
+    leaf = leaves_of(parent)
+    # ancestors' rows are filled, extants' rows stay null as in the reference (Prediction.java:636-641)
+    assert [[None if (s == NONE or leaf[v]) else AA[s] for s in row] for v, row in enumerate(want)] == joint
     marg = pred.getMarginal("N0", model)
     assert [x is None for x in marg] == [not present[0, c] for c in range(obs.shape[1])]
     with pytest.raises(ASRRuntimeException):
@@ -129,7 +131,7 @@ def test_prediction_batch_entry_points(bnk, oracle):
     rates = [0.5, 1.0, 2.0, 1.0, 0.25]
     j2 = pred.getJoint(model, rates)
     w2 = oracle.fast_joint(oracle.Model("LG"), parent, dist, obs, present, rates)
-    assert [[None if s == NONE else AA[s] for s in row] for row in w2] == j2
+    assert [[None if (s == NONE or leaf[v]) else AA[s] for s in row] for v, row in enumerate(w2)] == j2
     pred.close()
 
 
