@@ -72,6 +72,8 @@ public final class NativeInference {
     static native long indelBaseModel(String substModelName);
     /** aln: direct ByteBuffer n_nodes * nCols, 255 = gap, extants' rows only. Returns a bnk_indel*. */
     static native long indelCreate(long baseModel, long tree, int nCols, ByteBuffer aln, int device);
+    /** the same handle over nDevices GPUs (0 = all visible): column blocks swept concurrently, sums in column order. */
+    static native long indelCreateMulti(long baseModel, long tree, int nCols, ByteBuffer aln, int nDevices);
     static native void indelSetRates(long indel, double mu, double lambda);
     /** computeColumnPriors: out[col * rates.length + rate]. */
     static native void indelColumnPriors(long indel, double geometricSeqLenParam, int nCols, double[] rates, double[] out);

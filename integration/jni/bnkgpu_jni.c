@@ -389,6 +389,22 @@ JNIEXPORT jlong JNICALL Java_asr_NativeInference_indelCreate(JNIEnv *env, jclass
     return (jlong)(intptr_t)h;
 }
 
+/* the same over nDevices devices (0 = all visible): GRASP.NTHREADS in IndelPeeler.runPeelingJobs */
+JNIEXPORT jlong JNICALL Java_asr_NativeInference_indelCreateMulti(JNIEnv *env, jclass c, jlong model, jlong tree, jint nCols, jobject obs,
+                                                                  jint nDevices)
+{
+    (void)c;
+    int bad = 0, rc;
+    bnk_indel *h = NULL;
+    const uint8_t *o = (const uint8_t *)buf(env, obs, (jlong)bnk_tree_size((const bnk_tree *)(intptr_t)tree) * nCols, &bad);
+    if (bad) return 0;
+    if (!o) { throw_arg(env, "bnkgpu: the alignment buffer is required"); return 0; }
+    rc = bnk_indel_create_multi((const bnk_model *)(intptr_t)model, (const bnk_tree *)(intptr_t)tree, nCols, nDevices, NULL, &h);
+    if (rc == BNK_OK) rc = bnk_indel_set_alignment(h, nCols, o);
+    if (rc != BNK_OK) { if (h) bnk_indel_destroy(h); raise(env, rc); return 0; }
+    return (jlong)(intptr_t)h;
+}
+
 JNIEXPORT void JNICALL Java_asr_NativeInference_indelSetRates(JNIEnv *env, jclass c, jlong h, jdouble mu, jdouble lambda)
 {
     (void)c;

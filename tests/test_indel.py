@@ -354,3 +354,36 @@ def test_gpu_indel_java_api_mirror_and_base_models(bnk, oracle):
         ref = oracle.Model(custom=custom).parts()
         assert np.array_equal(got["R"], ref["R"]) and np.array_equal(got["F"], ref["F"])
         assert not np.array_equal(got["R"], bnk.Model(name).parts()["R"])
+
+
+@pytest.mark.gpu
+def test_gpu_indel_several_devices_behind_one_handle(bnk, oracle):
+    """bnk_indel_create_multi: column blocks on several devices (here: three parts, on as many devices as the box
+    has -- a device may serve several parts), results identical to the single-device handle column by column, sums in
+    column order, the same Brent trajectory; more parts than columns is legal"""
+    rng = np.random.default_rng(29)
+    m = bnk.Model("JTT")
+    parent, dist = random_tree(rng, 60, max_children=3)
+    n_cols = 101
+    obs = _random_alignment(rng, parent, n_cols, 20, 0.4)
+    _clade_gaps(rng, parent, obs, range(0, n_cols, 2))
+    tree = bnk.Tree(parent, dist)
+    nd = max(bnk.device_count(), 1)
+    one = bnk.Indel(m, tree, n_cols)
+    multi = bnk.Indel(m, tree, n_cols, devices=[0 % nd, 1 % nd, 2 % nd])
+    for h in (one, multi):
+        h.set_alignment(obs)
+        h.set_rates(0.06, 0.04)
+    a, sa = one.column_logl(1.3, 0.02)
+    b, sb = multi.column_logl(1.3, 0.02)
+    assert np.array_equal(a, b) and sa == sb
+    assert one.aln_logl(0.02) == multi.aln_logl(0.02)
+    assert np.array_equal(one.column_priors([0.5, 2.0], 0.02), multi.column_priors([0.5, 2.0], 0.02))
+    assert one.optimise_mulambda(1e-4, 1.0, 0.02) == multi.optimise_mulambda(1e-4, 1.0, 0.02)
+    tiny = bnk.Indel(m, tree, 2, devices=[0] * 5)          # five parts, two columns
+    tiny.set_alignment(obs[:, :2])
+    tiny.set_rates(0.06, 0.04)
+    one.set_alignment(obs[:, :2])
+    assert np.array_equal(tiny.column_logl(1.0, 0.02)[0], one.column_logl(1.0, 0.02)[0])
+    for h in (one, multi, tiny):
+        h.close()
