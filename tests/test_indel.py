@@ -384,6 +384,7 @@ def test_gpu_indel_several_devices_behind_one_handle(bnk, oracle):
     tiny.set_alignment(obs[:, :2])
     tiny.set_rates(0.06, 0.04)
     one.set_alignment(obs[:, :2])
+    one.set_rates(0.06, 0.04)                              # (the Brent search above left its last evaluation's rates)
     assert np.array_equal(tiny.column_logl(1.0, 0.02)[0], one.column_logl(1.0, 0.02)[0])
     for h in (one, multi, tiny):
         h.close()
