@@ -52,6 +52,7 @@ struct IndelArgs {
     double *out_logl;     // [ncols]
     const int32_t *nodes; // the nodes of this launch (a level) / the narrow nodes in processing order
     int32_t n_launch_nodes;
+    const int4 *wdesc;    // walk kernel: two int4 per step {node, ent, n_children, first child index} {child 0, child 1, ent 0, ent 1}
 };
 
 __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((1023 + e) << 20, 0); }  // e in [-1022, 1023]
@@ -90,36 +91,43 @@ struct PeelState {
 };
 
 // fold child `ch` (its table A_ch in shared memory at sA, the parent's insertion vector at s_ins) into the state
+// prev / prev_ent: the state this thread computed in its previous walk step (registers); a child that IS that node --
+// the chain of a deep tree -- is not read back from HBM
+// ent_known / ob_known / del_known: values the walk kernel fetched a step ahead (ent_known = INT_MIN: look them up here)
 template <int K>
-__device__ __forceinline__ void fold_child(const IndelArgs &a, int ch, int col, const double *sA, const double *s_ins, PeelState<K> &st)
+__device__ __forceinline__ void fold_child(const IndelArgs &a, int ch, int col, const double *sA, const double *s_ins, PeelState<K> &st,
+                                           const PeelState<K> *prev = nullptr, int prev_ent = -1, int ent_known = INT32_MIN,
+                                           uint8_t ob_known = 0, double del_known = 0.0)
 {
     const size_t nc = (size_t)a.ncols;
-    const double del = a.tb.del[ch];
-    const int ent = a.ent_of_node[ch];
+    const bool known = ent_known != INT32_MIN;
+    const double del = known ? del_known : a.tb.del[ch];
+    const int ent = known ? ent_known : a.ent_of_node[ch];
     if (ent < 0) {   // an extant (calcLeafPeelingProbabilities :273-284)
-        const uint8_t o = a.obs[(size_t)ch * nc + col];
+        const uint8_t o = known ? ob_known : a.obs[(size_t)ch * nc + col];
         if (o == BNK_NONE) {
 #pragma unroll
             for (int p = 0; p < K; p++) st.Rv[p] *= del;
         } else {
             st.cgv = false;
 #pragma unroll
-            for (int p = 0; p < K; p++) st.Rv[p] *= sA[p * K + o];
+            for (int p = 0; p < K; p++) st.Rv[p] *= sA[o * K + p];
         }
     } else {
         double Rc[K];
+        const bool reuse = prev != nullptr && ent == prev_ent;
         const double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
 #pragma unroll
-        for (int x = 0; x < K; x++) Rc[x] = m[(size_t)x * nc];
-        const int eRc = a.eR[(size_t)ent * nc + col];
-        const bool cgc = a.cg[(size_t)ent * nc + col] != 0;
+        for (int x = 0; x < K; x++) Rc[x] = reuse ? prev->Rv[x] : m[(size_t)x * nc];
+        const int eRc = reuse ? prev->eRv : a.eR[(size_t)ent * nc + col];
+        const bool cgc = reuse ? prev->cgv : a.cg[(size_t)ent * nc + col] != 0;
         if (cgc) {
             // ancestral gap term of this child (:297-327): sum_q R_c[q] ins_v[q] + Gap_c
             double s = 0.0;
 #pragma unroll
             for (int q = 0; q < K; q++) s += Rc[q] * s_ins[q];
-            const double Gc = m[(size_t)K * nc];
-            const int eGc = a.eG[(size_t)ent * nc + col];
+            const double Gc = reuse ? prev->gm : m[(size_t)K * nc];
+            const int eGc = reuse ? prev->ge : a.eG[(size_t)ent * nc + col];
             double tm;
             int te;
             add_scaled(s, eRc, Gc, eGc, tm, te);
@@ -130,13 +138,18 @@ __device__ __forceinline__ void fold_child(const IndelArgs &a, int ch, int col, 
         // ancestral residue terms (:329-356); the deletion term joins only below an all-gap child
         const bool with_del = cgc && del > 0.0;
         const double sc = with_del ? (eRc < -1000 ? 0.0 : pow2i(eRc)) : 1.0;   // messages are <= 1: eRc <= 0
+        // S[p] = sum_x A[x][p] R_c[x]: K independent accumulators, one table row (contiguous in p) per child residue
+        double S[K];
 #pragma unroll
-        for (int p = 0; p < K; p++) {
-            double S = 0.0;
+        for (int p = 0; p < K; p++) S[p] = 0.0;
 #pragma unroll
-            for (int x = 0; x < K; x++) S += sA[p * K + x] * Rc[x];
-            st.Rv[p] *= with_del ? S * sc + del : S;
+        for (int x = 0; x < K; x++) {
+            const double rc = Rc[x];
+#pragma unroll
+            for (int p = 0; p < K; p++) S[p] = fma(sA[x * K + p], rc, S[p]);
         }
+#pragma unroll
+        for (int p = 0; p < K; p++) st.Rv[p] *= with_del ? S[p] * sc + del : S[p];
         if (!with_del) st.eRv += eRc;
     }
     // keep the running product's largest entry in [1, 2)
@@ -153,8 +166,9 @@ __device__ __forceinline__ void fold_child(const IndelArgs &a, int ch, int col, 
 }
 
 // store the node's message; the root also writes the column's log-likelihood
+// ent_known / root_known: from the walk descriptor (no dependent lookups on the walker's critical path)
 template <int K>
-__device__ __forceinline__ void finish_node(const IndelArgs &a, int node, int col, PeelState<K> &st)
+__device__ __forceinline__ void finish_node(const IndelArgs &a, int node, int col, PeelState<K> &st, int ent_known = -1, int root_known = -1)
 {
     const size_t nc = (size_t)a.ncols;
     if (st.gm > 0.0) {
@@ -165,7 +179,7 @@ __device__ __forceinline__ void finish_node(const IndelArgs &a, int node, int co
         st.gm = 0.0;
         st.ge = E_ZERO;
     }
-    const int ent = a.ent_of_node[node];
+    const int ent = ent_known >= 0 ? ent_known : a.ent_of_node[node];
     double *m = a.msg + ((size_t)ent * (K + 1)) * nc + col;
 #pragma unroll
     for (int p = 0; p < K; p++) m[(size_t)p * nc] = st.Rv[p];
@@ -173,7 +187,7 @@ __device__ __forceinline__ void finish_node(const IndelArgs &a, int node, int co
     a.eR[(size_t)ent * nc + col] = st.eRv;
     a.eG[(size_t)ent * nc + col] = st.ge;
     a.cg[(size_t)ent * nc + col] = st.cgv ? 1 : 0;
-    if (a.parent[node] < 0) {   // decorate (:229-252)
+    if (root_known >= 0 ? root_known != 0 : a.parent[node] < 0) {   // decorate (:229-252)
         const double LN2 = 0.693147180559945309417232121458;
         double w = 0.0;
 #pragma unroll
@@ -234,30 +248,95 @@ __global__ void __launch_bounds__(IND_THREADS) indel_level_kernel(IndelArgs a)
 }
 
 // The narrow rest of the tree (deep trees: all of it): grid = tiles of WALK_THREADS columns, every CTA walks the node
-// list, children before parents.  (A 10,000-level caterpillar is one long dependent chain per column: 64 ms per
-// evaluation at 5,000 columns; one-warp CTAs on all SMs were slower, 122 ms -- the table staging of a step is a
-// serial chain of global loads that more threads per CTA shorten.)
+// list, children before parents.  A 10,000-level caterpillar is one long dependent chain per column, so what a step
+// costs is latency: the tables of step i + 1 (its children's A, its own insertion vector) are requested with cp.async
+// while step i computes (two shared-memory buffers), and the message a thread wrote in step i stays in its registers
+// for step i + 1, whose child it usually is.  Nodes with more than two children stage their tables one by one.
 template <int K>
 __global__ void __launch_bounds__(WALK_THREADS) indel_walk_kernel(IndelArgs a)
 {
-    __shared__ __align__(16) double sA[K * K];
-    __shared__ double s_ins[K];
+    __shared__ __align__(16) double sA[2][2][K * K];
+    __shared__ __align__(16) double s_ins[2][K];
     const int col = blockIdx.x * WALK_THREADS + threadIdx.x;
     const bool valid = col < a.ncols;
-    for (int i = 0; i < a.n_launch_nodes; i++) {
-        const int node = a.nodes[i];
-        const int c0 = a.first[node], c1 = a.first[node + 1];
+    const size_t nc = (size_t)a.ncols;
+    const int n = a.n_launch_nodes;
+    struct Desc { int4 h, c; };   // h = {node, ent, n_children | root << 16, first child index}, c = {child 0, child 1, ent 0, ent 1}
+    auto load_desc = [&](int i) -> Desc {
+        Desc d;
+        if (i < n) { d.h = a.wdesc[2 * i]; d.c = a.wdesc[2 * i + 1]; }
+        else { d.h = make_int4(0, -1, 0, 0); d.c = make_int4(-1, -1, -1, -1); }
+        return d;
+    };
+    // tables and insertion vector of the step described by d, into buffer buf (one commit group)
+    auto prefetch = [&](const Desc &d, int buf) {
+        if (threadIdx.x < K / 2) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_ins[buf][threadIdx.x * 2]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(a.tb.ins + (size_t)d.h.x * K + threadIdx.x * 2) : "memory");
+        }
+        if ((d.h.z & 0xffff) <= 2)
+            for (int k = 0; k < (d.h.z & 0xffff); k++) {
+                const double *src = a.tb.A + (size_t)(k == 0 ? d.c.x : d.c.y) * (K * K);
+                for (int q = threadIdx.x; q < K * K / 2; q += WALK_THREADS) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&sA[buf][k][q * 2]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + q * 2) : "memory");
+                }
+            }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    // what a thread needs of the step's (at most two) children besides their tables: observed byte of an extant, del
+    struct Side { uint8_t ob[2]; double del[2]; };
+    auto load_side = [&](const Desc &d) -> Side {
+        Side sd;
+        sd.ob[0] = sd.ob[1] = BNK_NONE; sd.del[0] = sd.del[1] = 0.0;
+        const int nch = d.h.z & 0xffff;
+        if (nch <= 2) {
+            if (nch > 0) { sd.del[0] = a.tb.del[d.c.x]; if (d.c.z < 0 && valid) sd.ob[0] = a.obs[(size_t)d.c.x * nc + col]; }
+            if (nch > 1) { sd.del[1] = a.tb.del[d.c.y]; if (d.c.w < 0 && valid) sd.ob[1] = a.obs[(size_t)d.c.y * nc + col]; }
+        }
+        return sd;
+    };
+    if (n <= 0) return;
+    Desc d0 = load_desc(0), d1 = load_desc(1);
+    prefetch(d0, 0);
+    Side s0 = load_side(d0);
+    PeelState<K> prev;
+    prev.init();
+    int prev_ent = -1;
+    for (int i = 0; i < n; i++) {
+        const int buf = i & 1;
+        const Desc d2 = load_desc(i + 2);        // two steps ahead: in registers by the time its tables are requested
+        Side s1;
+        if (i + 1 < n) {
+            prefetch(d1, buf ^ 1);
+            s1 = load_side(d1);                  // consumed in the next iteration
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            s1 = s0;
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncthreads();
+        const int node = d0.h.x, nch = d0.h.z & 0xffff, is_root = d0.h.z >> 16;
         PeelState<K> st;
         st.init();
-        __syncthreads();
-        if (threadIdx.x < K) s_ins[threadIdx.x] = a.tb.ins[(size_t)node * K + threadIdx.x];
-        for (int k = c0; k < c1; k++) {
-            if (k > c0) __syncthreads();   // the previous table has been consumed
-            stage_table<K, WALK_THREADS>(a, a.kids[k], sA);
-            __syncthreads();
-            if (valid) fold_child<K>(a, a.kids[k], col, sA, s_ins, st);
+        if (nch <= 2) {
+            if (valid) {
+                if (nch > 0) fold_child<K>(a, d0.c.x, col, sA[buf][0], s_ins[buf], st, &prev, prev_ent, d0.c.z, s0.ob[0], s0.del[0]);
+                if (nch > 1) fold_child<K>(a, d0.c.y, col, sA[buf][1], s_ins[buf], st, &prev, prev_ent, d0.c.w, s0.ob[1], s0.del[1]);
+            }
+        } else {
+            for (int k = 0; k < nch; k++) {
+                if (k > 0) __syncthreads();   // the previous table has been consumed
+                stage_table<K, WALK_THREADS>(a, a.kids[d0.h.w + k], sA[buf][0]);
+                __syncthreads();
+                if (valid) fold_child<K>(a, a.kids[d0.h.w + k], col, sA[buf][0], s_ins[buf], st, &prev, prev_ent);
+            }
         }
-        if (valid) finish_node<K>(a, node, col, st);
+        if (valid) finish_node<K>(a, node, col, st, d0.h.y, is_root);
+        prev = st;
+        prev_ent = d0.h.y;
+        d0 = d1; d1 = d2; s0 = s1;
+        __syncthreads();   // buffer `buf` is free for the prefetch of step i + 2
     }
 }
 
@@ -277,7 +356,7 @@ struct bnk_indel {
     int64_t launches = 0;
     std::vector<std::pair<int32_t, int32_t>> level_ranges;   // into d_nodes, height 1 first
     std::pair<int32_t, int32_t> narrow_range{0, 0};
-    DevBuf<int32_t> d_first{&reg}, d_kids{&reg}, d_ent{&reg}, d_parent{&reg}, d_nodes{&reg}, d_eR{&reg}, d_eG{&reg};
+    DevBuf<int32_t> d_first{&reg}, d_kids{&reg}, d_ent{&reg}, d_parent{&reg}, d_nodes{&reg}, d_eR{&reg}, d_eG{&reg}, d_wdesc{&reg};
     DevBuf<double> d_dist{&reg}, d_gm{&reg}, d_A{&reg}, d_del{&reg}, d_ins{&reg}, d_msg{&reg}, d_logl{&reg}, d_probs{&reg};
     DevBuf<uint8_t> d_obs{&reg}, d_cg{&reg};
     std::vector<double> h_logl;
@@ -404,6 +483,7 @@ int run_sweep(bnk_indel *h, double rate, double geom)
     }
     if (h->narrow_range.second > h->narrow_range.first) {
         a.nodes = h->d_nodes.p + h->narrow_range.first; a.n_launch_nodes = h->narrow_range.second - h->narrow_range.first;
+        a.wdesc = reinterpret_cast<const int4 *>(h->d_wdesc.p);
         const int wtiles = (nc + WALK_THREADS - 1) / WALK_THREADS;
         if (K == 20) indel_walk_kernel<20><<<wtiles, WALK_THREADS, 0, st>>>(a);
         else indel_walk_kernel<4><<<wtiles, WALK_THREADS, 0, st>>>(a);
@@ -526,6 +606,19 @@ extern "C" int bnk_indel_create(const bnk_model *base, const bnk_tree *tree, int
     if ((rc = step(upload_vec(h->d_parent, tree->parent, h->stream))) != BNK_OK) return bail(rc);
     if ((rc = step(upload_vec(h->d_dist, tree->dist, h->stream))) != BNK_OK) return bail(rc);
     if ((rc = step(upload_vec(h->d_nodes, nodes, h->stream))) != BNK_OK) return bail(rc);
+    {   // walk descriptors of the narrow nodes: one 32-byte record per step instead of four dependent lookups
+        std::vector<int32_t> wd;
+        for (int32_t i = h->narrow_range.first; i < h->narrow_range.second; i++) {
+            const int v = nodes[i], c0 = tree->first[v], nch = tree->first[v + 1] - c0;
+            const int ch0 = nch > 0 ? tree->kids[c0] : -1, ch1 = nch > 1 ? tree->kids[c0 + 1] : -1;
+            if (nch > 0xffff) return bail(fail(BNK_ERR_TREE, "indel: a narrow node with %d children", nch));
+            const int32_t rec[8] = {v, tree->ent_of_node[v], nch | (tree->parent[v] < 0 ? 1 << 16 : 0), c0, ch0, ch1,
+                                    ch0 >= 0 ? tree->ent_of_node[ch0] : -1, ch1 >= 0 ? tree->ent_of_node[ch1] : -1};
+            wd.insert(wd.end(), rec, rec + 8);
+        }
+        if (wd.empty()) wd.assign(8, 0);
+        if ((rc = step(upload_vec(h->d_wdesc, wd, h->stream))) != BNK_OK) return bail(rc);
+    }
     const size_t nc = (size_t)max_cols + 1, K = h->K;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = h->d_A.ensure((size_t)h->n * K * K);

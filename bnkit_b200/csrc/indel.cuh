@@ -14,7 +14,7 @@ struct GapModelDev {   // device pointers; K1 = residues + gap
 
 // per-branch tables for one (mu, lambda, rate); K = residues
 struct IndelTables {
-    double *A;    // [node][p][x] = P_eps(t_node)[p][x] * (1 - ksi(t_node))     residue block only
+    double *A;    // [node][x][p] = P_eps(t_node)[p][x] * (1 - ksi(t_node))     residue block only; x = child residue, p = parent residue
     double *del;  // [node]       = (1 - ksi(t_node)) * gamma(t_node)
     double *ins;  // [node][q]    = ksi(t_node) * F[q]           read when `node` is the PARENT (IndelPeeler.java:392-400)
 };

@@ -52,7 +52,7 @@ indel_tables_kernel(GapModelDev gm, const double *__restrict__ dist, const int32
     double temp = 0.0;
 #pragma unroll
     for (int k = 0; k < K1; k++) temp += gm.evec[i * K1 + k] * iexp[k * K1 + j];
-    tb.A[((size_t)node * K + i) * K + j] = fabs(temp) * s_noins;
+    tb.A[((size_t)node * K + j) * K + i] = fabs(temp) * s_noins;   // stored child-state-major: A[x][p], p = parent residue
 }
 
 // the full (K+1)^2 matrix at one time, for tests (bnk_indel_probs)
