@@ -212,9 +212,20 @@ class Shard:
         self.d_post = torch.empty((self.n_int if want_post else 1, nc, self.K), dtype=torch.float64, device=self.dev)
         self.d_logl = torch.empty((nc,), dtype=torch.float64, device=self.dev)
         self.d_sum = torch.zeros((1,), dtype=torch.float64, device=self.dev)
+        self.serial = bool(os.environ.get("BNK_BENCH_SERIAL"))
 
     def step(self):
-        """tables (marked stale by the distance upload, as in an optimisation step) + joint + marginal"""
+        """tables (marked stale by the distance upload, as in an optimisation step) + joint + marginal, as ONE call:
+        bnk_joint_marginal_dev runs the two independent passes side by side on two streams"""
+        if self.ncols == 0:
+            return
+        if self.serial:
+            return self.step_serial()
+        self.ws.set_distances(self.dist0)
+        self.ws.joint_marginal_dev(self.ncols, self.d_obs, self.d_present, self.d_state, self.d_post, self.d_logl)
+
+    def step_serial(self):
+        """the same work as two calls, one pass after the other (per-phase CUDA-event times are only meaningful here)"""
         if self.ncols == 0:
             return
         self.ws.set_distances(self.dist0)
@@ -301,6 +312,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the C3b / C4 / C5 sub-results")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="time the step as two calls (bnk_joint_dev, bnk_marginal_dev) instead of bnk_joint_marginal_dev")
     ap.add_argument("--sub", default="c3b,c4,c5,indel", help="which sub-results to run")
     args = ap.parse_args()
 
@@ -391,6 +403,9 @@ def main():
     if args.tile_cols or args.cpt:
         sh.ws.configure(args.tile_cols, args.cpt)
     n, n_int, K = sh.n, sh.n_int, sh.K
+    if args.serial:
+        sh.serial = True
+        os.environ["BNK_BENCH_SERIAL"] = "1"
 
     phase_ms = np.zeros(5)
 
@@ -406,9 +421,16 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    serial_ms = None
+    if not sh.serial:  # first the sweeps one after the other, for the per-phase times the roofline is computed from;
+        # the timed loop follows, so the parity sample below reads what the TIMED calls left in the buffers
+        serial_ms = timed_steps(torch, dist_, world, sh.step_serial, 1, args.steps, after_step=collect_phases)
+        sh.step()
     launches0 = sh.ws.launch_count()
-    total_ms = timed_steps(torch, dist_, world, sh.step, 0, args.steps, after_step=collect_phases)
+    total_ms = timed_steps(torch, dist_, world, sh.step, 0, args.steps, after_step=collect_phases if sh.serial else None)
     launches = sh.ws.launch_count() - launches0
+    if serial_ms is None:
+        serial_ms = total_ms
     clocks = sampler.stop() if rank == 0 else None
     phase_ms /= args.steps
 
@@ -491,7 +513,7 @@ def main():
         del h_post, h_state, h_obs
     # ---- max over ranks
     e_vals = [e2e["joint_ms"], e2e["marginal_ms"], e2e["one_ancestor_ms"], -e2e["d2h_gbs"]] if e2e else [0.0, 0.0, 0.0, 0.0]
-    tmax, ej, em, eo, ed = max_over_ranks(torch, dist_, world, dev, [total_ms] + e_vals)
+    tmax, smax, ej, em, eo, ed = max_over_ranks(torch, dist_, world, dev, [total_ms, serial_ms] + e_vals)
 
     main_cols = n_cols * (world if args.weak else 1)
     updates_step = 3.0 * n_int * main_cols
@@ -528,9 +550,14 @@ def main():
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "gpu_launches": int(launches),
             "cols_per_gpu": sh.ncols,
+            "step_api": "bnk_joint_dev + bnk_marginal_dev" if sh.serial else
+                        "bnk_joint_marginal_dev (joint pass on a second stream beside the marginal pass)",
+            "ms_per_step_serial": smax / args.steps,
             "phase_ms": {"tables": round(float(phase_ms[0]), 4), "joint_up": round(float(phase_ms[1]), 4),
                          "traceback": round(float(phase_ms[2]), 4), "sum_up": round(float(phase_ms[3]), 4),
-                         "sum_down": round(float(phase_ms[4]), 4), "of": "rank 0's block of %d columns" % sh.ncols},
+                         "sum_down": round(float(phase_ms[4]), 4),
+                         "of": "rank 0's block of %d columns; CUDA events of the serial pass (bnk_joint_dev, then "
+                               "bnk_marginal_dev: %d more steps in the same run) -- the sweeps of the timed step overlap" % (sh.ncols, args.steps)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "traffic_note": "DRAM bytes per step of the dominant sweep (all its launches): " + str(traffic_src),
@@ -573,18 +600,26 @@ def main():
             def coll():
                 s2.ws.sync()
                 ph[:] += [s2.ws.phase_ms(i) for i in range(5)]
-            ms = timed_steps(torch, dist_, world, s2.step, sub_warm, sub_steps, after_step=coll)
+            ms_serial = None
+            if not s2.serial:
+                ms_serial = timed_steps(torch, dist_, world, s2.step_serial, 1, sub_steps, after_step=coll)
+            ms = timed_steps(torch, dist_, world, s2.step, sub_warm, sub_steps, after_step=coll if s2.serial else None)
+            if ms_serial is None:
+                ms_serial = ms
             par = None
             if rank == 0 and not args.no_parity and s2.ncols > 0:
                 par = parity_sample(torch, s2, mname, sp, sd, 8 if name == "c3b" else 6)
-            (ms,) = max_over_ranks(torch, dist_, world, dev, [ms])
+            ms, ms_serial = max_over_ranks(torch, dist_, world, dev, [ms, ms_serial])
             ni = s2.n_int
             u = 3.0 * ni * sspec["cols"]
             ph /= sub_steps
             tb = TABLE_BYTES * (s2.n - 1) * sspec["ncat"]
             algo = sum(BYTES_PER_UPDATE.values()) * ni * s2.ncols + 3 * tb
+            algo_all = algo   # rank 0's block in ms (max over ranks): the same quantity per rank
             subs[name] = {"workload": sspec["name"], "cols_per_gpu": s2.ncols, "steps": sub_steps, "warmup": sub_warm,
                           "ms_per_step": ms / sub_steps, "updates_per_s": u / (ms / sub_steps * 1e-3),
+                          "ms_per_step_serial": ms_serial / sub_steps,
+                          "roofline_frac_step": algo_all / 1e9 / (ms / sub_steps * 1e-3) / peak,
                           "phase_ms": {"tables": round(float(ph[0]), 4), "joint_up": round(float(ph[1]), 4),
                                        "traceback": round(float(ph[2]), 4), "sum_up": round(float(ph[3]), 4),
                                        "sum_down": round(float(ph[4]), 4)},

@@ -102,6 +102,9 @@ void bnk::ws_free(bnk_ws *ws)
     DeviceGuard guard(ws->device);
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     for (bnk_ws *sub : ws->subs) ws_free(sub);
+    if (ws->twin) ws_free(ws->twin);
+    if (ws->twin_fork) cudaEventDestroy(ws->twin_fork);
+    if (ws->twin_join) cudaEventDestroy(ws->twin_join);
     if (ws->copy_stream) { cudaStreamSynchronize(ws->copy_stream); cudaStreamDestroy(ws->copy_stream); }
     for (auto &e : ws->chunk_done) if (e) cudaEventDestroy(e);
     for (auto &e : ws->copy_done) if (e) cudaEventDestroy(e);
@@ -143,6 +146,8 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     }
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
+    if (const char *env = std::getenv("BNK_NO_FUSE2")) ws->no_fuse2 = std::atoi(env) != 0;
+    if (const char *env = std::getenv("BNK_DOWN_PIPE")) ws->no_down_pipe = std::atoi(env) == 0;
     if (const char *env = std::getenv("BNK_WALKER"))
         ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "lane") == 0 ? 4 : (std::strcmp(env, "general") == 0 ? 5 : 0))));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
@@ -185,6 +190,27 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
         ws->level_off.push_back((int32_t)wide_all.size());
     }
     step(upload(ws->d_wide, wide_all, ws->stream));
+    if (t->wide_h >= 2) {  // the fused down-sweep of the height-2 level
+        const auto &l1 = t->levels[0], &l2 = t->levels[1];
+        std::vector<int32_t> row_of_node(t->n, -1);
+        for (size_t i = 0; i < l1.size(); i++) row_of_node[l1[i].node] = (int32_t)i;
+        std::vector<uint8_t> taken(l1.size(), 0);
+        std::vector<Wide2Node> f2(l2.size());
+        for (size_t i = 0; i < l2.size(); i++) {
+            f2[i].v = l2[i];
+            for (int e = 0; e < 2; e++) {
+                std::memset(&f2[i].c[e], 0, sizeof(WideNode));
+                f2[i].c[e].node = -1;
+                const int32_t u = e < l2[i].n_child ? l2[i].c_node[e] : -1;
+                if (u >= 0 && row_of_node[u] >= 0) { f2[i].c[e] = l1[row_of_node[u]]; taken[row_of_node[u]] = 1; }
+            }
+        }
+        std::vector<WideNode> rest;
+        for (size_t i = 0; i < l1.size(); i++) if (!taken[i]) rest.push_back(l1[i]);
+        ws->n_fuse2 = (int)f2.size(); ws->n_wide_rest = (int)rest.size();
+        step(upload(ws->d_fuse2, f2, ws->stream));
+        step(upload(ws->d_wide_rest, rest, ws->stream));
+    }
     step(upload(ws->d_parent, t->parent, ws->stream));
     step(upload(ws->d_node_of_ent, t->node_of_ent, ws->stream));
     step(upload(ws->d_leaf_nodes, leaf_nodes, ws->stream));
@@ -249,6 +275,7 @@ extern "C" int64_t bnk_ws_launch_count(const bnk_ws *ws)
     if (!ws) return 0;
     int64_t l = ws->launches;
     for (const bnk_ws *sub : ws->subs) l += sub->launches;
+    if (ws->twin) l += ws->twin->launches;
     return l;
 }
 extern "C" int64_t bnk_ws_device_bytes(const bnk_ws *ws)
@@ -256,12 +283,14 @@ extern "C" int64_t bnk_ws_device_bytes(const bnk_ws *ws)
     if (!ws) return 0;
     int64_t b = ws->reg.bytes;
     for (const bnk_ws *sub : ws->subs) b += sub->reg.bytes;
+    if (ws->twin) b += ws->twin->reg.bytes;
     return b;
 }
 
 extern "C" int bnk_ws_phase_ms(bnk_ws *ws, int phase, float *ms)
 {
     if (!ws || !ms || phase < 0 || phase > 4) return fail(BNK_ERR_ARG, "phase_ms: bad argument");
+    if (ws->twin && ws->twin_phases && (phase == 1 || phase == 2)) ws = ws->twin;  // the joint pass of bnk_joint_marginal_dev
     if (!ws->ev_valid[phase]) { *ms = 0.f; return BNK_OK; }
     CUDA_TRY(cudaEventElapsedTime(ms, ws->ev[phase][0], ws->ev[phase][1]));
     return BNK_OK;
@@ -796,6 +825,7 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
         }
     }
     w.obs = obs_s;
+    w.no_pipe = ws->no_down_pipe ? 1 : 0;
     w.ncols = ws->ncols; w.n_nodes = ws->n;
     w.orig_col = ws->d_orig_col.p;
     w.col_lo = ws->chunk_cols[ci].first; w.col_hi = ws->chunk_cols[ci].second;
@@ -804,11 +834,13 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
 
 // one launch per wide height level (sliced when a level exceeds the grid's y limit)
 template <typename F>
-static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch)
+static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch, int h_lo = 0, int h_hi = -1)
 {
     const int H = ws->tree->wide_h;
+    if (h_hi < 0) h_hi = H;
     for (int k = 0; k < H; k++) {
         const int h = ascending ? k : H - 1 - k;
+        if (h < h_lo || h >= h_hi) continue;
         for (int off = ws->level_off[h]; off < ws->level_off[h + 1]; off += 65535) {
             const int cnt = std::min(65535, ws->level_off[h + 1] - off);
             w.nodes = ws->d_wide.p + off;
@@ -826,6 +858,21 @@ static int for_each_level(bnk_ws *ws, bool ascending, WideArgs &w, F launch)
     return BNK_OK;
 }
 
+// slices of a node list that is not a whole level (the grid's y limit is 65535)
+template <typename F>
+static int for_node_slices(bnk_ws *ws, WideArgs &w, int count, F launch)
+{
+    for (int off = 0; off < count; off += 65535) {
+        const int cnt = std::min(65535, count - off);
+        const int64_t ctas = (int64_t)cnt * w.n_tiles;
+        const int tpc = (int)(ctas / ((int64_t)ws->sm_count * 8));
+        w.tiles_per_cta = std::max(1, std::min(tpc, ws->wide_tpc_max));
+        CUDA_TRY(launch(w, off, cnt));
+        ws->launches++;
+    }
+    return BNK_OK;
+}
+
 // --------------------------------------------------------------------------------------
 // joint
 // --------------------------------------------------------------------------------------
@@ -834,6 +881,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
     if (!ws || !d_obs || !d_out_state) return fail(BNK_ERR_ARG, "joint: null argument");
     ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
+    ws->twin_phases = false;
     const int K = ws->K, nc = ws->ncols;
     bool general;
     const uint8_t *obs_s, *present_s;
@@ -1064,8 +1112,23 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
             ws->launches++;
             if (s.hybrid) {
                 w.tmsg = ws->d_tmsg.p; w.out_post = post_base; w.qrow = s.a.qrow;
+                const bool fuse2 = !gen && K == 20 && t->wide_h >= 2 && ws->n_fuse2 > 0 && !ws->no_fuse2;
                 TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
-                    return gen ? launch_down_wide_gen(K, wa, n_wt, cnt, ws->stream) : launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
+                    return gen ? launch_down_wide_gen(K, wa, n_wt, cnt, ws->stream) : launch_down_wide(K, wa, n_wt, cnt, ws->stream); },
+                    fuse2 ? 2 : 0));
+                if (fuse2) {
+                    // the height-2 level evaluates its height-1 children in the same thread (their from-above vectors
+                    // never reach HBM); height-1 nodes under a taller or walked parent keep the plain level kernel
+                    w.cherry = 0;
+                    TRY(for_node_slices(ws, w, ws->n_fuse2, [&](WideArgs &wa, int off, int cnt) {
+                        wa.fuse2 = ws->d_fuse2.p + off;
+                        return launch_down_wide2(K, wa, n_wt, cnt, ws->stream); }));
+                    w.fuse2 = nullptr;
+                    w.cherry = 1;
+                    TRY(for_node_slices(ws, w, ws->n_wide_rest, [&](WideArgs &wa, int off, int cnt) {
+                        wa.nodes = ws->d_wide_rest.p + off;
+                        return launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
+                }
             }
             for (const LeafQuery &lq : leaf_queries) {
                 LeafPostArgs la;
@@ -1101,6 +1164,51 @@ extern "C" int bnk_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs
 {
     if (!ws || !d_obs) return fail(BNK_ERR_ARG, "marginal: null argument");
     return ws_run_sum(ws, n_cols, d_obs, d_present, query_nodes_host, n_query, d_out_post, d_out_logl, nullptr);
+}
+
+// Joint + marginal of the same alignment as ONE call: the two passes share nothing but their inputs (log-space
+// tables, pointers and states on one side; linear tables, messages and posteriors on the other), so the joint
+// pass runs in a twin workspace on a second stream while this workspace runs the marginal pass.  On deep trees
+// both walks are latency-bound with about one warp per scheduler (profiles/r1_v22_ncu_summary.md), and two
+// co-resident walker CTAs per SM fill each other's stalls; on level-scheduled trees the issue-bound joint
+// kernels and the HBM-bound down-sweep overlap at the tails of their launches.
+extern "C" int bnk_joint_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present,
+                                      uint8_t *d_out_state, const int32_t *query_nodes_host, int32_t n_query,
+                                      double *d_out_post, double *d_out_logl)
+{
+    if (!ws || !d_obs || !d_out_state) return fail(BNK_ERR_ARG, "joint_marginal: null argument");
+    if (ws->is_sub) return fail(BNK_ERR_STATE, "joint_marginal: not on a sub-workspace");
+    ENTER_DEVICE(ws->device);
+    TRY(ensure_rates(ws, n_cols));
+    if (!ws->twin) {
+        bnk_ws *tw = nullptr;
+        TRY(bnk_ws_create(&ws->model, ws->tree, ws->max_cols, ws->device, nullptr, &tw));
+        tw->is_sub = true;
+        ws->twin = tw;
+        ws->twin_dist_version = 0;
+        CUDA_TRY(cudaEventCreateWithFlags(&ws->twin_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ws->twin_join, cudaEventDisableTiming));
+    }
+    bnk_ws *tw = ws->twin;
+    if (tw->cfg_tile_cols != ws->cfg_tile_cols || tw->cfg_cpt != ws->cfg_cpt || tw->force_generic != ws->force_generic ||
+        tw->no_wide != ws->no_wide) {
+        tw->cfg_tile_cols = ws->cfg_tile_cols; tw->cfg_cpt = ws->cfg_cpt; tw->force_generic = ws->force_generic;
+        tw->no_wide = ws->no_wide; tw->retile = true;
+    }
+    tw->evidence_mode = ws->evidence_mode;
+    if (ws->twin_dist_version != ws->dist_version + 1) TRY(bnk_set_distances(tw, ws->dist.data()));
+    ws->twin_dist_version = ws->dist_version + 1;
+    TRY(bnk_set_rates(tw, ws->ncols, ws->rates_null ? nullptr : ws->last_rates.data()));
+    // fork: the twin's stream sees everything queued on this workspace's stream so far (the inputs)
+    CUDA_TRY(cudaEventRecord(ws->twin_fork, ws->stream));
+    CUDA_TRY(cudaStreamWaitEvent(tw->stream, ws->twin_fork, 0));
+    int rc = bnk_joint_dev(tw, n_cols, d_obs, d_present, d_out_state);
+    if (rc == BNK_OK) rc = ws_run_sum(ws, n_cols, d_obs, d_present, query_nodes_host, n_query, d_out_post, d_out_logl, nullptr);
+    // join (also after an error: whatever the twin queued must not outlive the call's ordering)
+    CUDA_TRY(cudaEventRecord(ws->twin_join, tw->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ws->stream, ws->twin_join, 0));
+    ws->twin_phases = rc == BNK_OK;
+    return rc;
 }
 
 extern "C" int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present,

@@ -73,6 +73,13 @@ struct WalkArgs {
     int32_t qstride;
 };
 
+// a height-2 node with the height-1 children the fused down-sweep kernel (wide.cu: down_wide2_kernel) evaluates in
+// the same thread; c[e].node = -1: child e is childless (or absent) and nothing is fused for it
+struct Wide2Node {
+    WideNode v;
+    WideNode c[2];
+};
+
 // arguments of the level kernels (wide.cu); all column indices are in sorted space
 struct WideArgs {
     const WideNode *nodes;   // the level (or a slice of it): gridDim.y entries
@@ -104,7 +111,10 @@ struct WideArgs {
     const double *prior;     // log prior (joint) / prior (sum)
     uint8_t *kind, *kindm;   // [ent][ncols] node kinds (joint / sum)
     double *logl_acc;        // [ncols] += log of component-root totals and scalar factors (atomic)
+    const Wide2Node *fuse2;  // down_wide2_kernel: the height-2 level (or a slice of it) with its fused children
+    int32_t no_pipe;         // BNK_DOWN_PIPE=0: the register-staged down_wide_kernel instead of down_wide_pipe_kernel (A/B, tests)
 };
+cudaError_t launch_down_wide2(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_up_wide_gen(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_down_wide_gen(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_traceback_wide_gen(int K, const WideArgs &a, int n_nodes, cudaStream_t st);

@@ -530,6 +530,7 @@ template <typename KernelT>
 static cudaError_t launch_lane(KernelT kern, const WalkArgs &a, int n_tiles, size_t smem, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     kern<<<n_tiles, LTHREADS, smem, st>>>(a);
     return cudaGetLastError();

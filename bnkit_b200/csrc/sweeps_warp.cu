@@ -913,6 +913,7 @@ static cudaError_t launch_warp(KernelT kern, const WalkArgs &a, int n_tiles, int
     if (W < 1 || W > XMAXW || ns < 2 || ns > XMAXNS || W * XCW * C > 64) return cudaErrorInvalidValue;
     const size_t smem = warp_walk_smem_bytes(W, C, ns, a.smem_slots, down);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     kern<<<n_tiles, (W + 2) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * XCW * C, down));
     return cudaGetLastError();
@@ -952,6 +953,7 @@ static cudaError_t launch_mma(KernelT kern, const WalkArgs &a, int n_tiles, int 
     if (W < 1 || W > XMAXW || ns < 2 || ns > XMAXNS || W * MCW > 64) return cudaErrorInvalidValue;
     const size_t smem = mma_walk_smem_bytes(W, ns, a.smem_slots, down);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     kern<<<n_tiles, (W + 2) * 32, smem, st>>>(a, W, ns, x_child_bytes(W * MCW, down));
     return cudaGetLastError();

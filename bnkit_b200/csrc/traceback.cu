@@ -6,6 +6,9 @@
 // walked root-to-leaves over the static pre-order program.
 #include "device_common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace bnk {
 
 // One warp owns one column: lane p holds "its" pointer byte ptr_v[p] of each step of a batch
@@ -82,9 +85,165 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
     }
 }
 
+// Column-owned traceback for long walks (r2).  The warp-per-column kernel above costs ~300 ns per step on a
+// 10,000-level caterpillar (3.0 ms): per step a warp loads 20 useful bytes, runs two dependent shuffles and lane 0
+// stores one byte into a sector of its own.  Here a warp owns 32 consecutive sorted columns, lane = column.  The
+// walker wrote ptr as [ent][column][K] bytes, so the pointer bytes of a step for the warp's columns are ONE
+// contiguous run of 32 K bytes: they stream into a shared-memory ring with cp.async TC_NB - 1 batches of TC_B
+// steps ahead (16-byte copies -- two instructions per step -- when the run is 16-byte aligned and a multiple of
+// 16 bytes, else 4-byte copies: a run is always 4-byte aligned), and the dependent chain of a step is one
+// shared-memory byte load: the parent's state comes from a register when the parent was the previous step
+// (program order is pre-order, so that is the common case; a uniform branch), else from a per-lane stack in
+// shared memory.  States leave as one 32-byte row segment per step.  (First cut, 4-byte copies only and every
+// field re-derived per step: 110 instructions per step and warp, 2.9 ms -- no faster than the kernel it replaced;
+// ncu: one warp per scheduler, `wait` stalls, i.e. the instruction count IS the time.)
+constexpr int TC_B = 16, TC_NB = 4, TC_WARPS = 2, TC_MAXSLOTS = 192;
+
+template <bool HAS_KIND>
+__global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const TracebackArgs a)
+{
+    extern __shared__ __align__(16) uint8_t tc_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int K = a.K;
+    const int col0 = a.col_lo + (blockIdx.x * TC_WARPS + wid) * 32;
+    const int ncw = min(32, a.col_hi - col0);
+    if (ncw <= 0) return;  // no CTA-wide barrier below
+    const int slots = a.tb_slots > 0 ? a.tb_slots : 1;
+    const int row_bytes = 32 * K;                         // one step of the ring
+    const int warp_bytes = TC_NB * TC_B * row_bytes + slots * 32;
+    uint8_t *ring = tc_smem + (size_t)wid * warp_bytes;
+    uint8_t *stack = ring + TC_NB * TC_B * row_bytes;     // [slot][lane]
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const int lc = lane < ncw ? lane : ncw - 1;           // spare lanes shadow the last column
+    const int col = col0 + lc;
+    const unsigned ncols_u = (unsigned)a.ncols;
+    const int run = ncw * K;                              // bytes of one step's run
+    const size_t ent_stride = (size_t)ncols_u * K;
+    const uint8_t *pbase = a.ptr + (size_t)col0 * K;
+    // 16-byte copies: every run starts on a 16-byte boundary and is a whole number of 16-byte pieces
+    const bool wide = (run & 15) == 0 && (ent_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(pbase) & 15) == 0;
+    const int n_steps = a.n_steps, n_batches = (n_steps + TC_B - 1) / TC_B;
+    const unsigned FULL = 0xffffffffu;
+    const int ocol = HAS_KIND ? a.orig_col[col] : 0;
+    uint8_t *srow = a.state_s + col;
+
+    // copies of batch j: lane u < TC_B knows the step's ent; every lane copies its share of each step's run
+    auto issue = [&](int j) {
+        if (j < n_batches) {
+            const int si = j * TC_B + lane;
+            const int my_ent = (lane < TC_B && si < n_steps) ? a.down[si].ent : -1;
+            const unsigned dst0 = ring_s + (unsigned)((j % TC_NB) * TC_B) * row_bytes;
+            if (wide) {
+                const int n16 = run >> 4;  // <= 2 K <= 40 pieces: at most two per lane
+#pragma unroll
+                for (int u = 0; u < TC_B; u++) {
+                    const int ent = __shfl_sync(FULL, my_ent, u);
+                    if (ent < 0) break;  // uniform
+                    const uint8_t *src = pbase + (size_t)(unsigned)ent * ent_stride + lane * 16;
+                    const unsigned dst = dst0 + u * row_bytes + lane * 16;
+                    if (lane < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                    if (lane + 32 < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 512), "l"(src + 512) : "memory");
+                }
+            } else {
+                const int n_words = run >> 2;
+#pragma unroll 2
+                for (int u = 0; u < TC_B; u++) {
+                    const int ent = __shfl_sync(FULL, my_ent, u);
+                    if (ent < 0) break;  // uniform
+                    const uint8_t *src = pbase + (size_t)(unsigned)ent * ent_stride;
+                    for (int w = lane; w < n_words; w += 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst0 + u * row_bytes + w * 4), "l"(src + w * 4) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    // program fields of batch j (lane u carries step j * TC_B + u) and, HAS_KIND, this lane's kind bytes of the batch
+    int f_node = 0, f_meta = 0;
+    uint8_t f_kind[HAS_KIND ? TC_B : 1];
+    auto fetch = [&](int j) {
+        const int si = j * TC_B + lane;
+        int my_ent = -1;
+        if (lane < TC_B && si < n_steps) {
+            const Step &sp = a.down[si];
+            f_node = sp.node; my_ent = sp.ent;
+            // 0..11 pslot + 1, 12..23 oslot + 1, 24: root step
+            f_meta = (sp.pslot + 1) | ((sp.oslot + 1) << 12) | ((sp.parent < 0 ? 1 : 0) << 24);
+        }
+        if (HAS_KIND) {
+#pragma unroll
+            for (int u = 0; u < TC_B; u++) {
+                const int ent = __shfl_sync(FULL, my_ent, u);
+                f_kind[u] = ent >= 0 ? a.kind[(size_t)(unsigned)ent * ncols_u + col] : (uint8_t)KIND_NONE;
+            }
+        }
+    };
+    for (int j = 0; j < TC_NB - 1; j++) issue(j);
+    fetch(0);
+    int last_oslot = -2, last_s = 0;
+    for (int b = 0; b < n_batches; b++) {
+        const int c_node = f_node, c_meta = f_meta;
+        uint8_t c_kind[HAS_KIND ? TC_B : 1];
+        if (HAS_KIND) {
+#pragma unroll
+            for (int u = 0; u < TC_B; u++) c_kind[u] = f_kind[u];
+        }
+        __syncwarp();             // every lane has finished reading the ring slot batch b + TC_NB - 1 overwrites
+        issue(b + TC_NB - 1);
+        if (b + 1 < n_batches) fetch(b + 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(TC_NB - 1) : "memory");
+        __syncwarp();             // ... and every lane's copies of batch b have landed
+        const uint8_t *rows = ring + (size_t)((b % TC_NB) * TC_B) * row_bytes + lc * K;
+        const int left = n_steps - b * TC_B;
+#pragma unroll
+        for (int u = 0; u < TC_B; u++) {
+            if (u >= left) break;
+            const int node = __shfl_sync(FULL, c_node, u), meta = __shfl_sync(FULL, c_meta, u);
+            const int pslot = (meta & 0xfff) - 1, oslot = ((meta >> 12) & 0xfff) - 1;
+            int ps = 0;
+            if (pslot >= 0) {          // uniform branches: the program is the same for every lane
+                if (pslot == last_oslot) ps = last_s;
+                else ps = stack[pslot * 32 + lane];
+            }
+            int s;
+            if (HAS_KIND) {
+                const int kind = c_kind[u];
+                const int src = (kind == KIND_MSG && ps < K) ? ps : 0;
+                s = rows[u * row_bytes + src];
+                if (kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + ocol];
+                else if (kind != KIND_MSG && kind != KIND_ROOT) s = BNK_NONE;
+            } else {
+                s = rows[u * row_bytes + ((meta >> 24) ? 0 : ps)];  // a root step reads entry 0
+            }
+            if (oslot >= 0) { stack[oslot * 32 + lane] = (uint8_t)s; last_oslot = oslot; last_s = s; }
+            if (lane < ncw) srow[(size_t)(unsigned)node * ncols_u] = (uint8_t)s;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t st)
 {
     if (a.tb_slots >= 4095) return cudaErrorInvalidValue;
+    static const bool old_tb = [] { const char *e = std::getenv("BNK_TRACEBACK"); return e && std::strcmp(e, "warp") == 0; }();
+    if (!old_tb && a.tb_slots <= TC_MAXSLOTS && a.n_steps > 0 && a.col_hi > a.col_lo && (a.K & 3) == 0) {
+        const int n_warps = (a.col_hi - a.col_lo + 31) / 32;
+        const unsigned grid = (n_warps + TC_WARPS - 1) / TC_WARPS;
+        const size_t smem = (size_t)TC_WARPS * (TC_NB * TC_B * 32 * a.K + (a.tb_slots > 0 ? a.tb_slots : 1) * 32);
+        cudaError_t e;
+        if (a.kind) {
+            e = cudaFuncSetAttribute(traceback_cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(traceback_cols_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            traceback_cols_kernel<true><<<grid, TC_WARPS * 32, smem, st>>>(a);
+        } else {
+            e = cudaFuncSetAttribute(traceback_cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(traceback_cols_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            traceback_cols_kernel<false><<<grid, TC_WARPS * 32, smem, st>>>(a);
+        }
+        return cudaGetLastError();
+    }
     const unsigned grid = (a.ncols + TB_WARPS - 1) / TB_WARPS;
     if (a.tb_slots <= 32) {
         traceback_kernel<true><<<grid, TB_WARPS * 32, 0, st>>>(a);

@@ -99,6 +99,12 @@ struct bnk_ws {
     int32_t sub_cols = 0;        // max_cols the sub-workspaces were created with
     uint64_t dist_version = 0, sub_dist_version = 0;  // bnk_set_distances calls seen / forwarded to the subs
     bool is_sub = false;
+    // bnk_joint_marginal_dev: the joint pass runs in a twin workspace on its own stream, beside this workspace's
+    // marginal pass (fork / join through events); phases 1, 2 of bnk_ws_phase_ms then come from the twin
+    bnk_ws *twin = nullptr;
+    cudaEvent_t twin_fork = nullptr, twin_join = nullptr;
+    uint64_t twin_dist_version = 0;
+    bool twin_phases = false;
     int cfg_tile_cols = 0, cfg_cpt = 0;
     bool force_generic = false;
     int wide_tpc_max = 8;  // r1 sweep on C3a: 4-8 tiles per CTA best
@@ -108,6 +114,13 @@ struct bnk_ws {
     DevBuf<Step> d_up{&reg}, d_down{&reg}, d_up_n{&reg}, d_down_n{&reg};             // full / narrow walk programs
     DevBuf<ChildRef> d_up_child{&reg}, d_down_child{&reg}, d_up_child_n{&reg}, d_down_child_n{&reg};
     DevBuf<WideNode> d_wide{&reg};                                  // wide levels, concatenated (height 1 first)
+    // fused down-sweep of the height-2 level (wide.cu: down_wide2_kernel): its nodes with their height-1 children,
+    // and the height-1 nodes whose parent is NOT a wide height-2 node (they keep the plain level kernel)
+    DevBuf<Wide2Node> d_fuse2{&reg};
+    DevBuf<WideNode> d_wide_rest{&reg};
+    int n_fuse2 = 0, n_wide_rest = 0;
+    bool no_fuse2 = false;                                    // BNK_NO_FUSE2=1 (A/B, tests)
+    bool no_down_pipe = false;                                // BNK_DOWN_PIPE=0 (A/B, tests)
     std::vector<int32_t> level_off;                           // [wide_h + 1] into d_wide
     bool no_wide = false;                                     // bnk_ws_configure: walker only (tests, profiling)
     DevBuf<int32_t> d_parent{&reg}, d_node_of_ent{&reg}, d_leaf_nodes{&reg}, d_leaf_parent{&reg};

@@ -34,6 +34,7 @@ SYMBOLS = [
     "bnk_ws_create", "bnk_ws_destroy", "bnk_ws_sync", "bnk_ws_dims", "bnk_ws_configure", "bnk_ws_launch_count",
     "bnk_ws_device_bytes", "bnk_set_rates", "bnk_set_distances", "bnk_probs",
     "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
+    "bnk_joint_marginal_dev",
     "bnk_ws_phase_ms", "bnk_bep_presence",
     "bnk_ws_set_evidence_mode", "bnk_ws_set_pipeline",
     "bnk_bep_infer", "bnk_pogs_n_edges", "bnk_pogs_edges", "bnk_pogs_destroy",
@@ -90,6 +91,7 @@ def lib():
     L.bnk_joint_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
     L.bnk_marginal_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _ip, C.c_int32, _vp, _vp]
     L.bnk_loglik_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
+    L.bnk_joint_marginal_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _ip, C.c_int32, _vp, _vp]
     L.bnk_ws_phase_ms.argtypes = [_vp, C.c_int, C.POINTER(C.c_float)]
     L.bnk_bep_presence.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip]
     L.bnk_bep_infer.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip, C.POINTER(_vp)]
@@ -387,6 +389,16 @@ class Workspace:
             nq = len(q)
         check(lib().bnk_marginal_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _i(q), nq,
                                      _ptr(d_out_post), _ptr(d_out_logl)))
+
+    def joint_marginal_dev(self, n_cols, d_obs, d_present, d_out_state, d_out_post, d_out_logl=None, query=None):
+        """joint_dev + marginal_dev of the same alignment in one call (the two passes overlap on two streams)"""
+        if query is None:
+            nq, q = -1, None
+        else:
+            q = np.ascontiguousarray(query, dtype=np.int32)
+            nq = len(q)
+        check(lib().bnk_joint_marginal_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _ptr(d_out_state), _i(q), nq,
+                                           _ptr(d_out_post), _ptr(d_out_logl)))
 
     def loglik_dev(self, n_cols, d_obs, d_present, d_out_logl, d_out_sum):
         check(lib().bnk_loglik_dev(self.h, int(n_cols), _ptr(d_obs), _ptr(d_present), _ptr(d_out_logl), _ptr(d_out_sum)))

@@ -187,6 +187,14 @@ int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_
 int bnk_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,
                      const int32_t *query_nodes_host, int32_t n_query, double *d_out_post,
                      double *d_out_logl);
+/* Joint AND marginal reconstruction of the same alignment in one call -- what a run with both inference modes
+ * asks for (asr.GRASP `-m Joint` then `-m Marginal`, src/asr/GRASP.java; Prediction.getJoint + getMarginal,
+ * src/asr/Prediction.java:555-649).  Results are those of bnk_joint_dev followed by bnk_marginal_dev; the two
+ * passes are independent and run side by side on two streams inside the library (joined before return of control
+ * to the workspace stream), which is what makes the call cheaper than the two it replaces. */
+int bnk_joint_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,
+                           uint8_t *d_out_state, const int32_t *query_nodes_host, int32_t n_query,
+                           double *d_out_post, double *d_out_logl);
 /* d_out_sum: one double on the device, = sum of the column log-likelihoods (input to the
  * NCCL all-reduce of an optimisation loop) */
 int bnk_loglik_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint8_t *d_present_or_null,

@@ -59,6 +59,15 @@ def run_and_compare(bnk, oracle, model_name, parent, dist, obs, rates, present=N
     ws.joint_dev(n_cols, d_obs, d_present, d_state)
     ws.marginal_dev(n_cols, d_obs, d_present, d_post, d_logl, query=query)
     ws.sync()
+    # the one-call form bench.py times (joint pass on a second stream beside the marginal pass) must leave the very
+    # same bits: same kernels, same inputs, only the scheduling differs
+    d_state2, d_post2, d_logl2 = torch.full_like(d_state, 77), torch.zeros_like(d_post), torch.zeros_like(d_logl)
+    ws.joint_marginal_dev(n_cols, d_obs, d_present, d_state2, d_post2, d_logl2, query=query)
+    ws.sync()
+    assert torch.equal(d_state2, d_state), "bnk_joint_marginal_dev: states differ from bnk_joint_dev"
+    assert torch.equal(d_post2.view(torch.int64), d_post.view(torch.int64)), "bnk_joint_marginal_dev: posteriors differ"
+    assert torch.equal(d_logl2.view(torch.int64), d_logl.view(torch.int64)), "bnk_joint_marginal_dev: logL differs"
+    del d_state2, d_post2, d_logl2
     sel = sample_columns(rates, per_cat)
     tsel = torch.from_numpy(sel).to(dev)
     st = d_state[:, tsel].cpu().numpy()

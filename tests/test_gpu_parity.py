@@ -323,6 +323,43 @@ def test_cherry_pattern_compression(bnk, oracle, monkeypatch):
         assert np.array_equal(res[0][2], res[1][2])
 
 
+def test_fused_height2_down_sweep(bnk, oracle, monkeypatch):
+    """The down-sweep of the height-2 level evaluates its height-1 children in the same thread (wide.cu:
+    down_wide2_kernel; their from-above vectors never reach HBM).  Against the oracle, and bit-identical to the
+    level-by-level kernels (BNK_NO_FUSE2=1): irregular trees (height-1 nodes under taller parents keep the plain
+    kernel), uninstantiated leaves (the staged sum row), unary nodes, ragged categories, a query subset that
+    skips some of the fused children."""
+    from bnkit_b200 import synth
+    rng = np.random.default_rng(57)
+    for name, leaves, n_cols, gap in (("LG", 900, 700, 0.0), ("WAG", 600, 500, 0.04)):
+        m, om = bnk.Model(name), oracle.Model(name)
+        parent, dist = synth.random_tree(leaves, seed=leaves + 3)
+        rates = rng.choice([0.3, 1.0, 2.2], size=n_cols, p=[0.6, 0.3, 0.1])
+        obs = synth.simulate_alignment(parent, dist, m.parts(), n_cols, rates, seed=leaves + 4, gap_fraction=gap)
+        tree = bnk.Tree(parent, dist)
+        internal = tree.internal_nodes()
+        sub = slice(0, n_cols, 7)
+        wpost, wlogl = oracle.fast_marginal(om, parent, dist, np.ascontiguousarray(obs[:, sub]), None, rates[sub], nthreads=8)
+        q = internal[::3]
+        res = []
+        for no_fuse, pipe in (("0", "1"), ("1", "1"), ("1", "0")):
+            monkeypatch.setenv("BNK_NO_FUSE2", no_fuse)
+            monkeypatch.setenv("BNK_DOWN_PIPE", pipe)   # 0: the register-staged level kernel instead of the cp.async-pipelined one
+            ws = bnk.Workspace(m, tree, n_cols)
+            ws.set_rates(n_cols, rates)
+            post, logl = ws.marginal(obs, None)
+            pq, _ = ws.marginal(obs, None, query=q, want_logl=False)
+            ws.close()
+            _post_close(post[:, sub], wpost[internal])
+            assert np.allclose(logl[sub], wlogl, rtol=TOL, atol=1e-9)
+            res.append((post, pq, logl))
+        for other in res[1:]:
+            assert np.array_equal(res[0][0], other[0], equal_nan=True)
+            assert np.array_equal(res[0][1], other[1], equal_nan=True)
+            assert np.array_equal(res[0][2], other[2])
+        assert np.array_equal(res[0][1], res[0][0][::3], equal_nan=True)
+
+
 def test_uninstantiated_childless_nodes_get_a_posterior(bnk, oracle):
     """A present but uninstantiated childless node (orphan flooding keeps such ancestors-turned-leaves,
     IdxTree.java:429-432) has a BN variable like any other: queried explicitly it returns the distribution the
