@@ -147,7 +147,6 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_NO_FUSE2")) ws->no_fuse2 = std::atoi(env) != 0;
-    if (const char *env = std::getenv("BNK_DOWN_PIPE")) ws->no_down_pipe = std::atoi(env) == 0;
     if (const char *env = std::getenv("BNK_WALKER"))
         ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "lane") == 0 ? 4 : (std::strcmp(env, "general") == 0 ? 5 : 0))));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
@@ -651,6 +650,7 @@ struct WalkSetup {
     bool fast = false;    // lean kernels of sweeps_fast.cu apply
     bool hybrid = false;  // wide height levels run as level launches (wide.cu); the walker takes the narrow top
     bool lane = false;    // fast, and the lane walker of sweeps_lane.cu takes the walk
+    bool wmask = false;   // the masked warp-tiled walker takes the walk (s.warp is set too; s.fast stays false)
     int n_ltiles = 0;
     bool warp = false;    // fast, and the warp-tiled kernels of sweeps_warp.cu take the walk
     int xw = 0, xc = 0, xns = 0, n_xtiles = 0;
@@ -711,6 +711,24 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
                                        s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_obs_t.p, ws->stream));
             ws->launches++;
             s.a.obs_t = ws->d_obs_t.p;
+            return BNK_OK;
+        }
+    }
+    if (general && ws->masked_only && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode != 5 &&
+        ws->walker_mode != 4 && ws->walker_mode != 1 && ws->xc == 1) {
+        // masked warp-tiled walker (r2): per-column forests in the fast deep-tree walker.  A pre-pass turns the presence
+        // mask into one case byte per (walker node, column); the wide levels keep the general level kernels
+        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
+        const int slots = use_program(hybrid);
+        int ns = ws->cfg_xns >= 2 && ws->cfg_xns <= 8 ? ws->cfg_xns : 8;
+        if (!(ws->cfg_xns >= 2 && ws->cfg_xns <= 8))
+            while (ns > 3 && warp_walk_smem_bytes(ws->xw, 1, ns, slots, want_down, true) > (size_t)ws->smem_optin / 2 - 1024) ns--;
+        if (warp_walk_smem_bytes(ws->xw, 1, ns, slots, want_down, true) <= (size_t)ws->smem_optin) {
+            s.warp = true; s.wmask = true; s.hybrid = hybrid;
+            s.xw = ws->xw; s.xc = 1; s.xns = ns;
+            s.n_xtiles = ws->chunk_xtiles[ci].second - ws->chunk_xtiles[ci].first;
+            s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
+            s.a.smem_slots = slots;
             return BNK_OK;
         }
     }
@@ -825,7 +843,6 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
         }
     }
     w.obs = obs_s;
-    w.no_pipe = ws->no_down_pipe ? 1 : 0;
     w.ncols = ws->ncols; w.n_nodes = ws->n;
     w.orig_col = ws->d_orig_col.p;
     w.col_lo = ws->chunk_cols[ci].first; w.col_hi = ws->chunk_cols[ci].second;
@@ -912,6 +929,11 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
                 w.msg = ws->d_msg.p; s.a.msg = ws->d_msg.p;
                 TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
                     return gen ? launch_up_wide_gen(K, 0, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
+            }
+            if (s.wmask) {
+                CUDA_TRY(launch_walk_case(s.a.up, s.a.n_steps, present_s, ws->d_orig_col.p, nc, ws->d_kind.p, ws->stream));
+                ws->launches++;
+                s.a.caseb = ws->d_kind.p;
             }
             CUDA_TRY(s.lane ? launch_lane_up(0, s.a, s.n_ltiles, ws->stream)
                      : s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
@@ -1088,6 +1110,12 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
             }
         }
         if (s.mma) s.a.tiles = s.mtiles;
+        if (s.wmask) {
+            CUDA_TRY(ws->d_kindm.ensure((size_t)ws->n_int * nc));
+            CUDA_TRY(launch_walk_case(s.a.up, s.a.n_steps, present_s, ws->d_orig_col.p, nc, ws->d_kindm.p, ws->stream));
+            ws->launches++;
+            s.a.caseb = ws->d_kindm.p;
+        }
         CUDA_TRY(s.lane ? launch_lane_up(1, s.a, s.n_ltiles, ws->stream)
                  : s.mma ? launch_sum_up_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
                  : s.warp ? launch_sum_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)

@@ -68,6 +68,9 @@ struct WalkArgs {
     // tile_base = index of a.tiles[0] among all lane tiles of the workspace
     const uint8_t *obs_t, *present_t;
     int32_t tile_stride, tile_base;
+    // masked warp-tiled walker (sweeps_warp.cu): case byte of every (walker node, sorted column), [n_int][ncols]:
+    // kind | child 0 present << 2 | child 1 present << 3 (launch_walk_case); nullptr selects the unmasked kernels
+    const uint8_t *caseb;
     // general joint up-sweep, nodes with >= 32 children: queue of the pairwise additions, one region per (thread, column)
     double *qscratch;
     int32_t qstride;
@@ -112,7 +115,6 @@ struct WideArgs {
     uint8_t *kind, *kindm;   // [ent][ncols] node kinds (joint / sum)
     double *logl_acc;        // [ncols] += log of component-root totals and scalar factors (atomic)
     const Wide2Node *fuse2;  // down_wide2_kernel: the height-2 level (or a slice of it) with its fused children
-    int32_t no_pipe;         // BNK_DOWN_PIPE=0: the register-staged down_wide_kernel instead of down_wide_pipe_kernel (A/B, tests)
 };
 cudaError_t launch_down_wide2(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_up_wide_gen(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
@@ -155,7 +157,9 @@ cudaError_t launch_sum_down_fast(const WalkLaunch &wl, const WalkArgs &a);
 // warp-tiled walker (sweeps_warp.cu): K = 20, same eligibility as the lean kernels; a.tiles = tiles of one
 // category and at most W * warp_walk_cols_per_warp(C) (<= 64) columns; W consumer warps (+ 1 producer warp),
 // C columns per lane, ns ring stages
-size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down);
+size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down, bool masked = false);
+cudaError_t launch_walk_case(const Step *prog, int n_steps, const uint8_t *present, const int32_t *orig_col, int ncols,
+                             uint8_t *out, cudaStream_t st);
 int warp_walk_cols_per_warp(int C);
 cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
 cudaError_t launch_sum_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);

@@ -39,10 +39,13 @@ constexpr int XSTAGE0 = XPROG + XPB * 32 * (int)sizeof(Step);
 constexpr int XMAXNS = 8, XMAXW = 7;
 
 constexpr int XOBS = 128;          // a stage starts with the observed states: 2 children x 64 tile columns
+constexpr int XOBS_M = 192;        // MASKED: + one case byte per tile column (kind | child 0 present << 2 | child 1 present << 3)
 // area of one child inside a stage: its table (childless) or, going down, the stored up-messages of the tile
 __host__ __device__ inline int x_child_bytes(int tile_cols, bool down) { return (down && tile_cols * XK * 8 > XTAB) ? tile_cols * XK * 8 : XTAB; }
-// stage = [observed states][table of the node][area of child 0][area of child 1]
-__host__ __device__ inline int x_stage_bytes(int chb) { return XOBS + XTAB + 2 * chb; }
+// stage = [observed states (+ case bytes)][table of the node][area of child 0][area of child 1]
+__host__ __device__ inline int x_stage_bytes(int chb, bool masked = false) { return (masked ? XOBS_M : XOBS) + XTAB + 2 * chb; }
+// MASKED: the unit table (zeros in log space, ones in linear space) sits between the program ring and stage 0
+__host__ __device__ inline int x_stage0(bool masked) { return XSTAGE0 + (masked ? XTAB : 0); }
 // a warp's private area: two exchange buffers and the message stack (+ 1 dummy slot), all "planar" vectors:
 // entries 0..9 of column c at c * 80, entries 10..19 at plane + c * 80 (plane = columns * 80 bytes), so that
 // consecutive lanes touch consecutive 16-byte chunks and no quarter-warp sees a bank twice
@@ -122,11 +125,11 @@ struct XGeom {
 };
 
 // barriers + role split shared by the kernels
-__device__ __forceinline__ XGeom x_setup(unsigned sbase, int W, int ns, int chb)
+__device__ __forceinline__ XGeom x_setup(unsigned sbase, int W, int ns, int chb, bool masked = false)
 {
     XGeom g;
     g.chb = chb;
-    g.stage_bytes = x_stage_bytes(chb);
+    g.stage_bytes = x_stage_bytes(chb, masked);
     g.bar_full = sbase;
     g.bar_empty = sbase + 8 * XMAXNS;
     g.bar_prog = sbase + 16 * XMAXNS;
@@ -152,10 +155,12 @@ __device__ __forceinline__ XGeom x_setup(unsigned sbase, int W, int ns, int chb)
 //   warp W + 1  stores the observed states of the childless children, which it requested XPD steps earlier.
 // A stage is full when the 32 lanes of the second and the issuing lane of the first have arrived and the bytes
 // have landed.
-template <bool DOWN>
+template <bool DOWN, bool MASKED = false>
 __device__ __forceinline__ void x_producer_tma(const WalkArgs &a, const TileDesc &tile, const XGeom &g, unsigned char *smem_raw,
                                                unsigned sbase, int ns, int lane)
 {
+    constexpr int XOBS = MASKED ? XOBS_M : bnk::XOBS;
+    constexpr int XSTAGE0 = bnk::XSTAGE0 + (MASKED ? XTAB : 0);
     const Step *prog = DOWN ? a.down : a.up;
     const int n_steps = a.n_steps;
     if (n_steps <= 0) return;  // nothing to stream (and nobody would complete the first program chunk)
@@ -206,13 +211,22 @@ __device__ __forceinline__ void x_producer_tma(const WalkArgs &a, const TileDesc
     }
 }
 
-template <bool DOWN>
+template <bool DOWN, bool MASKED = false>
 __device__ __forceinline__ void x_producer_obs(const WalkArgs &a, const TileDesc &tile, const XGeom &g, unsigned char *smem_raw,
                                                int ns, int lane)
 {
+    constexpr int XSTAGE0 = bnk::XSTAGE0 + (MASKED ? XTAB : 0);
     const int n_steps = a.n_steps;
     if (n_steps <= 0) return;
     const size_t ncols = (size_t)a.ncols;
+    // MASKED: the case bytes of this step's node for tile columns `lane` and `lane + 32` (sorted column space)
+    const uint8_t *case_a = MASKED ? a.caseb + tile.col0 + (lane < tile.ncols ? lane : tile.ncols - 1) : nullptr;
+    const uint8_t *case_b = MASKED ? a.caseb + tile.col0 + (lane + 32 < tile.ncols ? lane + 32 : tile.ncols - 1) : nullptr;
+    auto fetch_case = [&](int i, int half) -> uint8_t {
+        const int po = XPROG + (i & (XPB * 32 - 1)) * (int)sizeof(Step);
+        const int ent = XSTEP(po, ent);
+        return *((half == 0 ? case_a : case_b) + (size_t)(unsigned)ent * ncols);
+    };
     // lane l fetches the observed states of tile columns l and l + 32
     const uint8_t *obs_a = a.obs + a.orig_col[tile.col0 + (lane < tile.ncols ? lane : tile.ncols - 1)];
     const uint8_t *obs_b = a.obs + a.orig_col[tile.col0 + (lane + 32 < tile.ncols ? lane + 32 : tile.ncols - 1)];
@@ -236,12 +250,18 @@ __device__ __forceinline__ void x_producer_obs(const WalkArgs &a, const TileDesc
     };
     need_chunk(0);
     uint8_t o[2][2][XPD];  // [child][column half][ring position]
+    uint8_t cb[MASKED ? 2 : 1][XPD];
 #pragma unroll
-    for (int k = 0; k < XPD; k++)
+    for (int k = 0; k < XPD; k++) {
 #pragma unroll
         for (int e = 0; e < 2; e++)
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) o[e][hf][k] = k < n_steps ? fetch_obs(k, e, hf) : (uint8_t)BNK_NONE;
+        if (MASKED) {
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) cb[hf][k] = k < n_steps ? fetch_case(k, hf) : (uint8_t)0;
+        }
+    }
     int s = 0, ph = 0;
     for (int i0 = 0; i0 < n_steps; i0 += XPD) {
 #pragma unroll
@@ -254,6 +274,10 @@ __device__ __forceinline__ void x_producer_obs(const WalkArgs &a, const TileDesc
                 smem_raw[so + 32 + lane] = o[0][1][k];
                 smem_raw[so + 64 + lane] = o[1][0][k];
                 smem_raw[so + 96 + lane] = o[1][1][k];
+                if (MASKED) {
+                    smem_raw[so + 128 + lane] = cb[0][k];
+                    smem_raw[so + 160 + lane] = cb[1][k];
+                }
                 mbar_arrive(g.bar_full + s * 8);
                 const int ip = i + XPD;
                 if (ip < n_steps) {
@@ -262,6 +286,10 @@ __device__ __forceinline__ void x_producer_obs(const WalkArgs &a, const TileDesc
                     for (int e = 0; e < 2; e++)
 #pragma unroll
                         for (int hf = 0; hf < 2; hf++) o[e][hf][k] = fetch_obs(ip, e, hf);
+                    if (MASKED) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++) cb[hf][k] = fetch_case(ip, hf);
+                    }
                 }
                 if (++s == ns) { s = 0; ph ^= 1; }
             }
@@ -318,17 +346,29 @@ struct XLane {
 // ------------------------------------------------------------------------------------
 // up-sweeps.  MODE 0: max-product in log space (joint), MODE 1: sum-product, linear, rescaled.
 // ------------------------------------------------------------------------------------
-template <int MODE, int C>
+// MASKED (C = 1): per-column forests.  A pre-pass (walk_case_kernel) classified every (step, column) from the
+// presence mask exactly as the general walker does -- KIND_NONE (absent / no BN variable), KIND_ROOT (parent absent:
+// the prior joins, the component closes here), KIND_MSG -- and recorded which children are present; the byte rides
+// in the stage.  The inner loop stays branch-free: an absent child is the unit vector (a select), a component root
+// contracts with the UNIT TABLE kept in shared memory instead of the node's table (a per-lane base address), a
+// node without a variable computes harmlessly and nobody reads what it leaves.
+template <int MODE, int C, bool MASKED>
 __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
 {
+    static_assert(!MASKED || C == 1, "the masked walker keeps one column per lane");
+    constexpr int XOBS = MASKED ? XOBS_M : bnk::XOBS;
+    constexpr int XSTAGE0 = bnk::XSTAGE0 + (MASKED ? XTAB : 0);
+    constexpr int XUNIT = bnk::XSTAGE0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileDesc tile = a.tiles[blockIdx.x];
-    const XGeom g = x_setup(sbase, W, ns, chb);
+    if (MASKED)
+        for (int i = threadIdx.x; i < XK * XK; i += blockDim.x) *reinterpret_cast<double *>(smem_raw + XUNIT + i * 8) = MODE == 0 ? 0.0 : 1.0;
+    const XGeom g = x_setup(sbase, W, ns, chb, MASKED);
     if (warp >= W) {
-        if (warp == W) x_producer_tma<false>(a, tile, g, smem_raw, sbase, ns, lane);
-        else x_producer_obs<false>(a, tile, g, smem_raw, ns, lane);
+        if (warp == W) x_producer_tma<false, MASKED>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<false, MASKED>(a, tile, g, smem_raw, ns, lane);
         return;
     }
     const XLane<C> L(a, tile, warp, lane);
@@ -363,6 +403,17 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
             const int sn = s + 1 == ns ? 0 : s + 1;
             ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
         }
+        // ---- this column's case (MASKED) ----
+        int kindc[C];
+        bool cpres[C][2];
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            kindc[j] = rootstep ? KIND_ROOT : KIND_MSG; cpres[j][0] = cpres[j][1] = true;
+            if (MASKED) {
+                const int cb = smem_raw[so + 128 + L.lc[j]];
+                kindc[j] = cb & 3; cpres[j][0] = (cb & 4) != 0; cpres[j][1] = (cb & 8) != 0;
+            }
+        }
         // ---- the (at most two) children ----
         double cv[C][2][4];
         bool isob[C][2];
@@ -374,7 +425,10 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
 #pragma unroll
             for (int j = 0; j < C; j++) {
                 isob[j][e] = false;
-                if (cs >= 0) {  // message left on this warp's stack
+                if (MASKED && !cpres[j][e]) {  // absent in this column: the unit vector
+#pragma unroll
+                    for (int k = 0; k < 4; k++) cv[j][e][k] = ident;
+                } else if (cs >= 0) {  // message left on this warp's stack
                     XLD4P(cv[j][e], stack0 + cs * slot_bytes + own[j], q, PLANE);
                 } else if (cs == SLOT_WIDE) {  // message a wide level kernel left in HBM, [ent][K][ncols]
                     const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + L.col[j];
@@ -409,19 +463,21 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
         for (int j = 0; j < C; j++) {
             // a root combines [prior, observed children, unobserved children] (the order the factors sit in the
             // reference's bucket); with one child of each kind that fixes the association
-            const bool swap = MODE == 0 && rootstep && !isob[j][0] && isob[j][1];
+            const bool rootc = MASKED ? kindc[j] == KIND_ROOT : rootstep;
+            const bool swap = MODE == 0 && rootc && !isob[j][0] && isob[j][1] && cpres[j][0];
             double G[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const double c0 = swap ? cv[j][1][k] : cv[j][0][k], c1 = swap ? cv[j][0][k] : cv[j][1][k];
-                if (MODE == 0) G[k] = ((rootstep ? prior4[k] : 0.0) + c0) + c1;
-                else G[k] = ((rootstep ? prior4[k] : 1.0) * c0) * c1;
+                if (MODE == 0) G[k] = ((rootc ? prior4[k] : 0.0) + c0) + c1;
+                else G[k] = ((rootc ? prior4[k] : 1.0) * c0) * c1;
             }
             XST4P(gb + own[j], q, G, PLANE);
         }
         __syncwarp();
         // ---- contract with the node's table: out[p] = op_x T[x][p] (.) G[x] for the lane's four p ----
-        const int tv = so + XOBS;
+        // MASKED: a component root contracts with the unit table (every output = max / sum over G)
+        const int tv = (MASKED && kindc[0] == KIND_ROOT) ? XUNIT : so + XOBS;
         const int sdst = slot >= 0 ? stack0 + slot * slot_bytes : dummy;
         if (MODE == 0) {
             double best[C][4];
@@ -430,7 +486,7 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
             for (int j = 0; j < C; j++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) { best[j][k] = -CUDART_INF; bi[j][k] = 0; }
-            if (!rootstep) {
+            if (MASKED || !rootstep) {
 #pragma unroll
                 for (int x2 = 0; x2 < XK / 2; x2++) {
                     double2 gg[C];
@@ -486,7 +542,7 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
 #pragma unroll
                 for (int k = 0; k < 4; k++) { acc[j][k] = 0.0; acb[j][k] = 0.0; }
             }
-            if (!rootstep) {
+            if (MASKED || !rootstep) {
 #pragma unroll
                 for (int x2 = 0; x2 < XK / 2; x2++) {
                     double ta[4], tb4[4];
@@ -523,10 +579,10 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
                 double m[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) m[k] = (acc[j][k] + acb[j][k]) * scale;
-                esum[j] += e;
+                esum[j] += (MASKED && kindc[j] == KIND_NONE) ? 0 : e;
                 XST4P(sdst + own[j], q, m, PLANE);
-                if (rootstep) logacc[j] += log(m[0]);
-                else if (a.msg) {
+                if (MASKED ? kindc[j] == KIND_ROOT : rootstep) logacc[j] += log(m[0]);
+                else if (a.msg && (!MASKED || kindc[j] == KIND_MSG)) {
                     double *dst = a.msg + ((size_t)(unsigned)ent * ncols + L.col[j]) * XK;
                     *reinterpret_cast<double2 *>(dst + L.p0) = make_double2(m[0], m[1]);
                     *reinterpret_cast<double2 *>(dst + L.p1) = make_double2(m[2], m[3]);
@@ -541,7 +597,8 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
 #pragma unroll
         for (int j = 0; j < C; j++) {
             const int ew = a.esum_wide ? a.esum_wide[L.col[j]] : 0;
-            a.out_logl[L.ocol[j]] = logacc[j] + (double)(esum[j] + ew) * 0.693147180559945309417232121458;
+            const double lw = (MASKED && a.logl_wide) ? a.logl_wide[L.col[j]] : 0.0;  // components closed inside the wide levels
+            a.out_logl[L.ocol[j]] = logacc[j] + lw + (double)(esum[j] + ew) * 0.693147180559945309417232121458;
         }
     }
 }
@@ -550,17 +607,20 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_warp_kernel(const Walk
 // down-sweep (see sweeps.cu for the recurrences): from-above vector D = P^T T, posterior
 // D * prod(children) normalised, T_child = D * prod(siblings)
 // ------------------------------------------------------------------------------------
-template <int C>
+template <int C, bool MASKED>
 __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const WalkArgs a, const int W, const int ns, const int chb)
 {
+    static_assert(!MASKED || C == 1, "the masked walker keeps one column per lane");
+    constexpr int XOBS = MASKED ? XOBS_M : bnk::XOBS;
+    constexpr int XSTAGE0 = bnk::XSTAGE0 + (MASKED ? XTAB : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileDesc tile = a.tiles[blockIdx.x];
-    const XGeom g = x_setup(sbase, W, ns, chb);
+    const XGeom g = x_setup(sbase, W, ns, chb, MASKED);
     if (warp >= W) {
-        if (warp == W) x_producer_tma<true>(a, tile, g, smem_raw, sbase, ns, lane);
-        else x_producer_obs<true>(a, tile, g, smem_raw, ns, lane);
+        if (warp == W) x_producer_tma<true, MASKED>(a, tile, g, smem_raw, sbase, ns, lane);
+        else x_producer_obs<true, MASKED>(a, tile, g, smem_raw, ns, lane);
         return;
     }
     const XLane<C> L(a, tile, warp, lane);
@@ -591,9 +651,20 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const Wa
             const int sn = s + 1 == ns ? 0 : s + 1;
             ready = i + 1 < n_steps ? mbar_test(g.bar_full + sn * 8, s + 1 == ns ? ph ^ 1 : ph) : 0u;
         }
+        // ---- this column's case (MASKED): the classification of the up-sweep ----
+        int kindc[C];
+        bool cpres[C][2];
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            kindc[j] = rootstep ? KIND_ROOT : KIND_MSG; cpres[j][0] = cpres[j][1] = true;
+            if (MASKED) {
+                const int cb = smem_raw[so + 128 + L.lc[j]];
+                kindc[j] = cb & 3; cpres[j][0] = (cb & 4) != 0; cpres[j][1] = (cb & 8) != 0;
+            }
+        }
         // ---- from-above vector of this node: D[x] = sum_p P[p][x] T[p], scaled by a power of two ----
         double D[C][4];
-        if (!rootstep) {
+        if (MASKED || !rootstep) {
             const int tv = so + XOBS;
             double acc[C][4], acb[C][4];
             int mhi[C];
@@ -625,6 +696,10 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const Wa
                 const double scale = x_pow2_scale(mhi[j], e);
 #pragma unroll
                 for (int k = 0; k < 4; k++) D[j][k] = (acc[j][k] + acb[j][k]) * scale;
+                if (MASKED && kindc[j] != KIND_MSG) {  // a component root starts from the prior (what the table gave is discarded)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) D[j][k] = prior4[k];
+                }
             }
         } else {
 #pragma unroll
@@ -644,7 +719,9 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const Wa
             const int area = so + XOBS + XTAB + e * g.chb;
 #pragma unroll
             for (int j = 0; j < C; j++) {
-                if (cs == SLOT_WIDE) {
+                if (MASKED && !cpres[j][e]) {  // absent in this column: the unit vector
+                    cv[j][e][0] = cv[j][e][1] = cv[j][e][2] = cv[j][e][3] = 1.0;
+                } else if (cs == SLOT_WIDE) {
                     const double *src = a.msg + (size_t)(unsigned)ce * (ncols * XK) + L.col[j];
                     cv[j][e][0] = src[(size_t)L.p0 * ncols]; cv[j][e][1] = src[(size_t)(L.p0 + 1) * ncols];
                     cv[j][e][2] = src[(size_t)L.p1 * ncols]; cv[j][e][3] = src[(size_t)(L.p1 + 1) * ncols];
@@ -677,6 +754,7 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const Wa
                 U[j][k] = D[j][k] * (cv[j][0][k] * cv[j][1][k]);
                 T0[j][k] = D[j][k] * cv[j][1][k];
                 T1[j][k] = D[j][k] * cv[j][0][k];
+                if (MASKED && kindc[j] == KIND_NONE) U[j][k] = CUDART_NAN;  // no BN variable: no posterior
             }
             XST4P(gb + own[j], q, U[j], PLANE);
         }
@@ -692,7 +770,7 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) down_warp_kernel(const Wa
                 XST4P(d1 + own[j], q, T1[j], PLANE);
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    if (cslot[e] == SLOT_WIDE) {  // handed to the wide level kernels through HBM, [ent][K][ncols]
+                    if (cslot[e] == SLOT_WIDE && (!MASKED || (cpres[j][e] && kindc[j] != KIND_NONE))) {  // handed to the wide level kernels through HBM, [ent][K][ncols]
                         double *dst = a.tmsg + (size_t)(unsigned)cent[e] * (ncols * XK) + L.col[j];
                         const double *Tv = e == 0 ? T0[j] : T1[j];
                         dst[(size_t)L.p0 * ncols] = Tv[0]; dst[(size_t)(L.p0 + 1) * ncols] = Tv[1];
@@ -902,16 +980,17 @@ __global__ void __launch_bounds__((XMAXW + 2) * 32, 1) up_mma_kernel(const WalkA
 
 // ------------------------------------------------------------------------------------
 int warp_walk_cols_per_warp(int C) { return XCW * C; }
-size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down)
+size_t warp_walk_smem_bytes(int W, int C, int ns, int slots, bool down, bool masked)
 {
-    return (size_t)XSTAGE0 + (size_t)ns * x_stage_bytes(x_child_bytes(W * XCW * C, down)) + (size_t)W * x_warp_bytes(C, slots);
+    return (size_t)x_stage0(masked) + (size_t)ns * x_stage_bytes(x_child_bytes(W * XCW * C, down), masked) + (size_t)W * x_warp_bytes(C, slots);
 }
 
 template <typename KernelT>
 static cudaError_t launch_warp(KernelT kern, const WalkArgs &a, int n_tiles, int W, int C, int ns, bool down, cudaStream_t st)
 {
     if (W < 1 || W > XMAXW || ns < 2 || ns > XMAXNS || W * XCW * C > 64) return cudaErrorInvalidValue;
-    const size_t smem = warp_walk_smem_bytes(W, C, ns, a.smem_slots, down);
+    if (a.caseb && C != 1) return cudaErrorInvalidValue;  // the masked walker keeps one column per lane
+    const size_t smem = warp_walk_smem_bytes(W, C, ns, a.smem_slots, down, a.caseb != nullptr);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
@@ -920,26 +999,59 @@ static cudaError_t launch_warp(KernelT kern, const WalkArgs &a, int n_tiles, int
 }
 cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
 {
-    if (C == 1) return launch_warp(up_warp_kernel<0, 1>, a, n_tiles, W, C, ns, false, st);
-    if (C == 2) return launch_warp(up_warp_kernel<0, 2>, a, n_tiles, W, C, ns, false, st);
-    if (C == 3) return launch_warp(up_warp_kernel<0, 3>, a, n_tiles, W, C, ns, false, st);
+    if (a.caseb) return launch_warp(up_warp_kernel<0, 1, true>, a, n_tiles, W, C, ns, false, st);
+    if (C == 1) return launch_warp(up_warp_kernel<0, 1, false>, a, n_tiles, W, C, ns, false, st);
+    if (C == 2) return launch_warp(up_warp_kernel<0, 2, false>, a, n_tiles, W, C, ns, false, st);
+    if (C == 3) return launch_warp(up_warp_kernel<0, 3, false>, a, n_tiles, W, C, ns, false, st);
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_sum_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
 {
-    if (C == 1) return launch_warp(up_warp_kernel<1, 1>, a, n_tiles, W, C, ns, false, st);
-    if (C == 2) return launch_warp(up_warp_kernel<1, 2>, a, n_tiles, W, C, ns, false, st);
-    if (C == 3) return launch_warp(up_warp_kernel<1, 3>, a, n_tiles, W, C, ns, false, st);
+    if (a.caseb) return launch_warp(up_warp_kernel<1, 1, true>, a, n_tiles, W, C, ns, false, st);
+    if (C == 1) return launch_warp(up_warp_kernel<1, 1, false>, a, n_tiles, W, C, ns, false, st);
+    if (C == 2) return launch_warp(up_warp_kernel<1, 2, false>, a, n_tiles, W, C, ns, false, st);
+    if (C == 3) return launch_warp(up_warp_kernel<1, 3, false>, a, n_tiles, W, C, ns, false, st);
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st)
 {
-    if (C == 1) return launch_warp(down_warp_kernel<1>, a, n_tiles, W, C, ns, true, st);
-    if (C == 2) return launch_warp(down_warp_kernel<2>, a, n_tiles, W, C, ns, true, st);
-    if (C == 3) return launch_warp(down_warp_kernel<3>, a, n_tiles, W, C, ns, true, st);
+    if (a.caseb) return launch_warp(down_warp_kernel<1, true>, a, n_tiles, W, C, ns, true, st);
+    if (C == 1) return launch_warp(down_warp_kernel<1, false>, a, n_tiles, W, C, ns, true, st);
+    if (C == 2) return launch_warp(down_warp_kernel<2, false>, a, n_tiles, W, C, ns, true, st);
+    if (C == 3) return launch_warp(down_warp_kernel<3, false>, a, n_tiles, W, C, ns, true, st);
     return cudaErrorInvalidValue;
 }
 
+
+// Pre-pass of the masked walker: the case byte of every (walk step, sorted column) from the presence mask
+// (original column order) -- kind | child 0 present << 2 | child 1 present << 3, where kind follows the general
+// walker (sweeps.cu): KIND_NONE when the node is absent, or root-like without a present child (no BN variable:
+// PhyloBN.create gives variables to connected nodes only); KIND_ROOT when its parent is absent (or it has none);
+// else KIND_MSG.  Row `ent` of out ([n_int][ncols]) is the kind array the traceback reads (it masks with 3).
+__global__ void __launch_bounds__(256) walk_case_kernel(const Step *__restrict__ prog, int n_steps, const uint8_t *__restrict__ present,
+                                                        const int32_t *__restrict__ orig_col, int ncols, uint8_t *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    const int oc = orig_col[c];
+    for (int i = blockIdx.y; i < n_steps; i += gridDim.y) {
+        const Step &sp = prog[i];
+        const bool pv = present[(size_t)sp.node * ncols + oc] != 0;
+        const bool pp = sp.parent >= 0 && present[(size_t)sp.parent * ncols + oc] != 0;
+        const bool c0 = sp.c_node[0] >= 0 && present[(size_t)sp.c_node[0] * ncols + oc] != 0;
+        const bool c1 = sp.c_node[1] >= 0 && present[(size_t)sp.c_node[1] * ncols + oc] != 0;
+        const int kind = !pv ? KIND_NONE : (pp ? KIND_MSG : ((c0 || c1) ? KIND_ROOT : KIND_NONE));
+        out[(size_t)sp.ent * ncols + c] = (uint8_t)(kind | (c0 ? 4 : 0) | (c1 ? 8 : 0));
+    }
+}
+cudaError_t launch_walk_case(const Step *prog, int n_steps, const uint8_t *present, const int32_t *orig_col, int ncols,
+                             uint8_t *out, cudaStream_t st)
+{
+    if (n_steps <= 0 || ncols <= 0) return cudaSuccess;
+    dim3 grid((ncols + 255) / 256, n_steps < 2048 ? n_steps : 2048);
+    walk_case_kernel<<<grid, 256, 0, st>>>(prog, n_steps, present, orig_col, ncols, out);
+    return cudaGetLastError();
+}
 
 // DMMA variants: 8 columns per warp, tiles of at most 8 W columns
 int mma_walk_cols_per_warp() { return MCW; }

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
             const int node = __shfl_sync(FULL, c_node, u), meta = __shfl_sync(FULL, c_meta, u);
             const int pslot = (meta & 0xfff) - 1, oslot = ((meta >> 12) & 0xfff) - 1;
             int kind = (meta >> 24) ? KIND_ROOT : KIND_MSG;
-            if (kcol) kind = kcol[(size_t)(unsigned)__shfl_sync(FULL, c_ent, u) * ncols_u];
+            if (kcol) kind = kcol[(size_t)(unsigned)__shfl_sync(FULL, c_ent, u) * ncols_u] & 3;  // (the masked warp-tiled walker keeps child flags above the kind)
             int src = 0;
             if (REGSTACK) {
                 const int ps = __shfl_sync(FULL, stack_reg, pslot & 31);
@@ -128,21 +128,22 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
     uint8_t *srow = a.state_s + col;
 
     // copies of batch j: lane u < TC_B knows the step's ent; every lane copies its share of each step's run
-    auto issue = [&](int j) {
+    auto load_ent = [&](int j) -> int {
+        const int si = j * TC_B + lane;
+        return (lane < TC_B && si < n_steps) ? a.down[si].ent : -1;
+    };
+    auto issue = [&](int j, int my_ent) {
         if (j < n_batches) {
-            const int si = j * TC_B + lane;
-            const int my_ent = (lane < TC_B && si < n_steps) ? a.down[si].ent : -1;
             const unsigned dst0 = ring_s + (unsigned)((j % TC_NB) * TC_B) * row_bytes;
             if (wide) {
                 const int n16 = run >> 4;  // <= 2 K <= 40 pieces: at most two per lane
 #pragma unroll
                 for (int u = 0; u < TC_B; u++) {
-                    const int ent = __shfl_sync(FULL, my_ent, u);
-                    if (ent < 0) break;  // uniform
+                    const int ent = __shfl_sync(FULL, my_ent, u);  // < 0 past the end of the program: nothing to copy
                     const uint8_t *src = pbase + (size_t)(unsigned)ent * ent_stride + lane * 16;
                     const unsigned dst = dst0 + u * row_bytes + lane * 16;
-                    if (lane < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-                    if (lane + 32 < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 512), "l"(src + 512) : "memory");
+                    if (ent >= 0 && lane < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                    if (ent >= 0 && lane + 32 < n16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 512), "l"(src + 512) : "memory");
                 }
             } else {
                 const int n_words = run >> 2;
@@ -178,8 +179,9 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
             }
         }
     };
-    for (int j = 0; j < TC_NB - 1; j++) issue(j);
+    for (int j = 0; j < TC_NB - 1; j++) issue(j, load_ent(j));
     fetch(0);
+    int next_ent = load_ent(TC_NB - 1);  // requested one batch before the copies that need it are issued
     int last_oslot = -2, last_s = 0;
     for (int b = 0; b < n_batches; b++) {
         const int c_node = f_node, c_meta = f_meta;
@@ -189,7 +191,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
             for (int u = 0; u < TC_B; u++) c_kind[u] = f_kind[u];
         }
         __syncwarp();             // every lane has finished reading the ring slot batch b + TC_NB - 1 overwrites
-        issue(b + TC_NB - 1);
+        issue(b + TC_NB - 1, next_ent);
+        next_ent = load_ent(b + TC_NB);
         if (b + 1 < n_batches) fetch(b + 1);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(TC_NB - 1) : "memory");
         __syncwarp();             // ... and every lane's copies of batch b have landed
@@ -197,17 +200,17 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
         const int left = n_steps - b * TC_B;
 #pragma unroll
         for (int u = 0; u < TC_B; u++) {
-            if (u >= left) break;
+            const bool act = u < left;  // (no break: the shuffles stay convergent; steps past the end store nothing)
             const int node = __shfl_sync(FULL, c_node, u), meta = __shfl_sync(FULL, c_meta, u);
             const int pslot = (meta & 0xfff) - 1, oslot = ((meta >> 12) & 0xfff) - 1;
-            int ps = 0;
-            if (pslot >= 0) {          // uniform branches: the program is the same for every lane
-                if (pslot == last_oslot) ps = last_s;
-                else ps = stack[pslot * 32 + lane];
-            }
+            // the parent's state: the previous step's when the parent was the previous step (program order is
+            // pre-order), else from the stack.  The stack read is unconditional and off the dependent chain -- its
+            // address is known from the program; a stale value is never selected
+            const int stv = stack[(pslot < 0 ? 0 : pslot) * 32 + lane];
+            const int ps = pslot < 0 ? 0 : (pslot == last_oslot ? last_s : stv);
             int s;
             if (HAS_KIND) {
-                const int kind = c_kind[u];
+                const int kind = c_kind[u] & 3;  // (the masked warp-tiled walker keeps child flags above the kind)
                 const int src = (kind == KIND_MSG && ps < K) ? ps : 0;
                 s = rows[u * row_bytes + src];
                 if (kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + ocol];
@@ -215,8 +218,11 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
             } else {
                 s = rows[u * row_bytes + ((meta >> 24) ? 0 : ps)];  // a root step reads entry 0
             }
-            if (oslot >= 0) { stack[oslot * 32 + lane] = (uint8_t)s; last_oslot = oslot; last_s = s; }
-            if (lane < ncw) srow[(size_t)(unsigned)node * ncols_u] = (uint8_t)s;
+            const bool keep = act && oslot >= 0;
+            if (keep) stack[oslot * 32 + lane] = (uint8_t)s;
+            last_s = keep ? s : last_s;
+            last_oslot = keep ? oslot : last_oslot;
+            if (act && lane < ncw) srow[(size_t)(unsigned)node * ncols_u] = (uint8_t)s;
         }
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");

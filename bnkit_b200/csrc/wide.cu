@@ -17,8 +17,6 @@
 // two children per node, one rate category per column tile, wide nodes are never roots.
 #include "wide_common.cuh"
 
-#include <cstdlib>
-
 namespace bnk {
 
 // message of child e of node w for this thread's column, all K states.  MODE 0: log space, 1: linear.
@@ -232,152 +230,13 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
 }
 
 // ------------------------------------------------------------------------------------
-// down-sweep of a level, software-pipelined (r2).  ncu on down_wide_kernel<20, false> (profiles/r2_t1_*): 168
-// registers -> 12 warps per SM, `long_scoreboard` 9.6 stall cycles per issued instruction, 4.9 TB/s on the big
-// levels: every tile pays two exposed memory round trips (T, then the children's messages -- they cannot be
-// requested together, T + c0 + c1 + D do not fit the register file) and nothing is in flight while a warp
-// computes.  Here the vectors travel through shared memory instead of registers: each thread copies ITS OWN
-// column's values with cp.async (LDGSTS; a warp still moves one coalesced 256-byte row segment per state) and
-// reads back only what it copied, so no barrier is needed -- per-thread commit groups are the whole protocol.
-// The children's messages of tile i and the from-above vector of tile i + 1 are requested before tile i's
-// contraction starts; a CTA keeps 60 KB in flight while it computes.  Same arithmetic and order as
-// down_wide_kernel; uninstantiated leaves use the staged sum row (see down_wide2_kernel).
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(double *dst, const double *src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <int K>
-__global__ void __launch_bounds__(WT, 2) down_wide_pipe_kernel(const WideArgs a)
-{
-    constexpr int LS = K + 1;
-    extern __shared__ __align__(16) double dsm[];  // T: [2][K][WT], children: [2][K][WT]
-    __shared__ __align__(16) double PTs[K * K];
-    __shared__ double LT0[LS * LS], LT1[LS * LS];
-    double *Tb = dsm, *Cb = dsm + 2 * K * WT;
-    const int tid = threadIdx.x;
-    const WideNode w = a.nodes[blockIdx.y];
-    const int t_lo = blockIdx.x * a.tiles_per_cta, t_hi = min(t_lo + a.tiles_per_cta, a.n_tiles);
-    if (t_lo >= t_hi) return;
-    const bool two = w.n_child > 1;
-    const bool leaf0 = w.c_ent[0] < 0, leaf1 = two && w.c_ent[1] < 0;
-    const bool push0 = !leaf0, push1 = two && !leaf1;
-    const int q = a.qrow ? a.qrow[w.ent] : w.ent;
-    const size_t ncols = (size_t)a.ncols;
-    const double *tsrc = a.tmsg + (size_t)w.ent * K * ncols;
-    const double *m0 = leaf0 ? nullptr : a.msg + (size_t)w.c_ent[0] * K * ncols;
-    const double *m1 = push1 ? a.msg + (size_t)w.c_ent[1] * K * ncols : nullptr;
-    double *t0 = push0 ? a.tmsg + (size_t)w.c_ent[0] * K * ncols : nullptr;
-    double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * ncols : nullptr;
-    auto col_of = [&](const TileDesc &tile) { return tile.col0 + (tid < tile.ncols ? tid : tile.ncols - 1); };
-    auto issue_T = [&](int ti, int buf) {
-        const int col = col_of(a.tiles[ti]);
-#pragma unroll
-        for (int x = 0; x < K; x++) cp_async8(Tb + (buf * K + x) * WT + tid, tsrc + (size_t)x * ncols + col);
-    };
-    issue_T(t_lo, 0);
-    cp_async_commit();
-    int cur_cat = -1;
-    for (int ti = t_lo; ti < t_hi; ti++) {
-        const int buf = (ti - t_lo) & 1;
-        const TileDesc tile = a.tiles[ti];
-        const size_t tb = (size_t)tile.cat0 * a.n_nodes;
-        const bool valid = tid < tile.ncols;
-        const int col = col_of(tile);
-        // the children's messages of this tile, the from-above vector of the next one
-        if (push0) {
-#pragma unroll
-            for (int x = 0; x < K; x++) cp_async8(Cb + x * WT + tid, m0 + (size_t)x * ncols + col);
-        }
-        if (push1) {
-#pragma unroll
-            for (int x = 0; x < K; x++) cp_async8(Cb + (K + x) * WT + tid, m1 + (size_t)x * ncols + col);
-        }
-        cp_async_commit();
-        if (ti + 1 < t_hi) issue_T(ti + 1, buf ^ 1);
-        cp_async_commit();
-        const int ocol = a.orig_col[col];  // inputs stay in the caller's column order
-        int o0 = 0, o1 = 0;
-        if (leaf0) { o0 = a.obs[(size_t)w.c_node[0] * ncols + ocol]; o0 = o0 == BNK_NONE ? K : o0; }
-        if (leaf1) { o1 = a.obs[(size_t)w.c_node[1] * ncols + ocol]; o1 = o1 == BNK_NONE ? K : o1; }
-        if (tile.cat0 != cur_cat) {
-            __syncthreads();
-            load_table<K>(PTs, a.T_col + (tb + w.node) * (K * K), 0);  // PT[x][xp] = P[xp][x]
-            if (leaf0) load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
-            if (leaf1) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
-            tables_wait();  // (drains this thread's vector copies too: once per category)
-            __syncthreads();
-            {   // row K of a leaf table = sum of its rows (an uninstantiated leaf marginalises its own state)
-                const int wid = tid >> 5, x = tid & 31;
-                double *tab = wid == 0 ? (leaf0 ? LT0 : nullptr) : (wid == 1 ? (leaf1 ? LT1 : nullptr) : nullptr);
-                if (tab && x < K) {
-                    double r = tab[x];
-                    for (int o = 1; o < K; o++) r += tab[o * LS + x];
-                    tab[K * LS + x] = r;
-                }
-            }
-            __syncthreads();
-            cur_cat = tile.cat0;
-        }
-        cp_async_wait<2>();  // this thread's copy of T for this tile has landed
-        double T[K];
-        {
-            int mhi = 0;
-#pragma unroll
-            for (int x = 0; x < K; x++) { T[x] = Tb[(buf * K + x) * WT + tid]; }
-#pragma unroll
-            for (int x = 0; x < K; x++) mhi = max(mhi, __double2hiint(T[x]));
-            int e;
-            const double scale = w_pow2_scale(mhi, e);
-#pragma unroll
-            for (int x = 0; x < K; x++) T[x] *= scale;
-        }
-        double D[K];
-#pragma unroll
-        for (int x = 0; x < K; x++) {
-            const double2 *row2 = reinterpret_cast<const double2 *>(PTs + x * K);
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-            for (int y2 = 0; y2 < K / 2; y2++) {
-                const double2 l = row2[y2];
-                acc0 = fma(l.x, T[2 * y2], acc0);
-                acc1 = fma(l.y, T[2 * y2 + 1], acc1);
-            }
-            D[x] = acc0 + acc1;
-        }
-        cp_async_wait<1>();  // ... and the children's messages
-        double U[K], S = 0.0;
-#pragma unroll
-        for (int x = 0; x < K; x++) {
-            const double c0 = leaf0 ? LT0[o0 * LS + x] : Cb[x * WT + tid];
-            const double c1 = !two ? 1.0 : (leaf1 ? LT1[o1 * LS + x] : Cb[(K + x) * WT + tid]);
-            if (valid && push0) t0[(size_t)x * ncols + col] = D[x] * c1;
-            if (valid && push1) t1[(size_t)x * ncols + col] = D[x] * c0;
-            U[x] = D[x] * (c0 * c1);
-            S += U[x];
-        }
-        if (valid && q >= 0 && a.out_post) {
-            const double r = w_rcp(S);
-            double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)q * ncols + ocol) * K);
-#pragma unroll
-            for (int x2 = 0; x2 < K / 2; x2++) __stcs(o + x2, make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r));
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------
 // down-sweep of the height-2 level FUSED with its height-1 children (r2).  A height-1 node ("cherry") has only
 // childless children, so once its parent v knows its own from-above product D_v, the cherry's posterior is one
 // more 20 x 20 contraction away: T_c = D_v * g_sibling, D_c = P_c^T T_c, post_c ~ D_c * (leaf rows).  Done in the
 // parent's thread, T_c never travels through HBM (160 B written + 160 B read per cherry and column, 20 % of the
 // down-sweep's DRAM traffic on a balanced tree) and the height-1 level needs no launch of its own.  Same arithmetic
-// and order as down_wide_kernel on both levels (incl. the power-of-two rescale of T_c), hence the same bits.
+// and order as down_wide_kernel on both levels (incl. the power-of-two rescale of T_c); results agree to a few ulp
+// (the compiler contracts the multiply-adds of the two kernels differently).
 // Uninstantiated leaves need no slow path here: row K of a staged leaf table holds the sum of its rows (what
 // self_vector<K, 1> computes, same order), and BNK_NONE selects that row.
 // ------------------------------------------------------------------------------------
@@ -598,13 +457,6 @@ cudaError_t launch_down_wide(int K, const WideArgs &a, int n_tiles, int n_nodes,
     if (n_nodes == 0 || n_tiles == 0) return cudaSuccess;
     dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, n_nodes);
     if (K == 20 && a.cherry) down_wide_kernel<20, true><<<grid, WT, 0, st>>>(a);
-    else if (K == 20 && !a.no_pipe) {
-        const size_t smem = sizeof(double) * 4 * 20 * WT;
-        cudaError_t e = cudaFuncSetAttribute(down_wide_pipe_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(down_wide_pipe_kernel<20>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        down_wide_pipe_kernel<20><<<grid, WT, smem, st>>>(a);
-    }
     else if (K == 20) down_wide_kernel<20, false><<<grid, WT, 0, st>>>(a);
     else down_wide_kernel<4, false><<<grid, WT, 0, st>>>(a);
     return cudaGetLastError();

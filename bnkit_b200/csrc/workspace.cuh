@@ -120,7 +120,6 @@ struct bnk_ws {
     DevBuf<WideNode> d_wide_rest{&reg};
     int n_fuse2 = 0, n_wide_rest = 0;
     bool no_fuse2 = false;                                    // BNK_NO_FUSE2=1 (A/B, tests)
-    bool no_down_pipe = false;                                // BNK_DOWN_PIPE=0 (A/B, tests)
     std::vector<int32_t> level_off;                           // [wide_h + 1] into d_wide
     bool no_wide = false;                                     // bnk_ws_configure: walker only (tests, profiling)
     DevBuf<int32_t> d_parent{&reg}, d_node_of_ent{&reg}, d_leaf_nodes{&reg}, d_leaf_parent{&reg};
