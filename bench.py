@@ -239,6 +239,33 @@ class Shard:
         self.torch.cuda.empty_cache()
 
 
+def fused_height1_nodes(parent):
+    """height-1 nodes whose parent is a level-scheduled node (height <= wide_h, not a root): the ones down_wide2_kernel
+    evaluates in the parent's thread (same rule as tree_plan.cpp / api.cu on binary trees: levels with >= 16 nodes)"""
+    parent = np.asarray(parent)
+    n = len(parent)
+    height = np.zeros(n, dtype=np.int64)
+    nch = np.zeros(n, dtype=np.int64)
+    for v in range(n - 1, 0, -1):   # children have larger indices than their parents (IdxTree order)
+        p = parent[v]
+        if p >= 0:
+            height[p] = max(height[p], height[v] + 1)
+            nch[p] += 1
+    if nch.max() > 2:
+        return 0
+    internal = nch > 0
+    width = np.bincount(height[internal & (parent >= 0)], minlength=3)
+    wide_h = 0
+    while wide_h + 1 < len(width) and width[wide_h + 1] >= 16:
+        wide_h += 1
+    if wide_h < 2:
+        return 0
+    par = parent.copy()
+    par[par < 0] = 0
+    ok = (height == 1) & (parent >= 0) & (height[par] >= 2) & (height[par] <= wide_h) & (parent[par] >= 0)
+    return int(ok.sum())
+
+
 def timed_steps(torch, dist_, world, fn, warmup, steps, after_step=None):
     """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events on the launching
     stream; returns this rank's milliseconds (the caller takes the max over ranks)"""
@@ -528,11 +555,19 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     upd = float(n_int) * sh.ncols   # rank 0's block: the kernels whose phase times are reported
     tbl = TABLE_BYTES * (n - 1) * spec["ncat"]
-    kern = {"joint_up+traceback": (phase_ms[1] + phase_ms[2], BYTES_PER_UPDATE["joint_up+traceback"] * upd + tbl),
-            "sum_up": (phase_ms[3], BYTES_PER_UPDATE["sum_up"] * upd + tbl),
-            "sum_down": (phase_ms[4], BYTES_PER_UPDATE["sum_down"] * upd + tbl)}
+    # The fused down-sweep of the height-2 level (r2) never writes or reads the from-above vectors of the height-1
+    # nodes it evaluates in the parent's thread: 2 x 160 B less per such (node, column) than SURVEY 8(d) counts.
+    # The algorithmic bytes of the down-sweep are restated accordingly; the survey's own
+    # figure stays in the line as `survey_GB`.
+    fused = fused_height1_nodes(parent) if present is None else 0
+    down_bytes = BYTES_PER_UPDATE["sum_down"] * upd - 320.0 * fused * sh.ncols + tbl
+    survey = {"joint_up+traceback": BYTES_PER_UPDATE["joint_up+traceback"] * upd + tbl,
+              "sum_up": BYTES_PER_UPDATE["sum_up"] * upd + tbl, "sum_down": BYTES_PER_UPDATE["sum_down"] * upd + tbl}
+    kern = {"joint_up+traceback": (phase_ms[1] + phase_ms[2], survey["joint_up+traceback"]),
+            "sum_up": (phase_ms[3], survey["sum_up"]),
+            "sum_down": (phase_ms[4], down_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
-    per_kernel = {k: {"ms": round(v[0], 4), "algorithmic_GB": round(v[1] / 1e9, 3),
+    per_kernel = {k: {"ms": round(v[0], 4), "algorithmic_GB": round(v[1] / 1e9, 3), "survey_GB": round(survey[k] / 1e9, 3),
                       "achieved_GBps": round(v[1] / 1e9 / (v[0] * 1e-3), 1) if v[0] > 0 else None,
                       "frac": round(v[1] / 1e9 / (v[0] * 1e-3) / peak, 4) if v[0] > 0 else None} for k, v in kern.items()}
     achieved = kern[dom][1] / 1e9 / (kern[dom][0] * 1e-3)
@@ -542,6 +577,11 @@ def main():
         if tr.get("workload") == args.workload and sh.ncols == spec["cols"] and present is None:
             traffic = tr["bytes_per_step"].get(dom)
             traffic_src = tr.get("source")
+            for k in per_kernel:   # what each sweep really moves through DRAM, over this run's event time
+                b = tr["bytes_per_step"].get(k)
+                if b and kern[k][0] > 0:
+                    per_kernel[k]["dram_GB"] = round(b / 1e9, 3)
+                    per_kernel[k]["dram_frac"] = round(b / 1e9 / (kern[k][0] * 1e-3) / peak, 4)
     except Exception:
         pass
 
@@ -561,7 +601,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "traffic_note": "DRAM bytes per step of the dominant sweep (all its launches): " + str(traffic_src),
-                         "algorithmic_bytes": "SURVEY.md 8(d) per-update figures x %d updates + table bytes" % int(upd),
+                         "algorithmic_bytes": "SURVEY.md 8(d) per-update figures x %d updates + table bytes; sum_down restated: minus "
+                                              "320 B x %d fused height-1 nodes x columns (their from-above vectors never reach HBM)" % (int(upd), fused),
                          "per_kernel": per_kernel},
             "clocks": clocks}
     if parity is not None:
@@ -614,7 +655,7 @@ def main():
             u = 3.0 * ni * sspec["cols"]
             ph /= sub_steps
             tb = TABLE_BYTES * (s2.n - 1) * sspec["ncat"]
-            algo = sum(BYTES_PER_UPDATE.values()) * ni * s2.ncols + 3 * tb
+            algo = sum(BYTES_PER_UPDATE.values()) * ni * s2.ncols + 3 * tb - 320.0 * fused_height1_nodes(sp) * s2.ncols
             algo_all = algo   # rank 0's block in ms (max over ranks): the same quantity per rank
             subs[name] = {"workload": sspec["name"], "cols_per_gpu": s2.ncols, "steps": sub_steps, "warmup": sub_warm,
                           "ms_per_step": ms / sub_steps, "updates_per_s": u / (ms / sub_steps * 1e-3),

@@ -14,7 +14,6 @@ UNITS = [
     ("sweeps.cu", []),
     ("sweeps_fast.cu", []),
     ("sweeps_warp.cu", []),
-    ("sweeps_lane.cu", []),
     ("wide.cu", []),
     ("wide_general.cu", []),
     ("cherry.cu", []),

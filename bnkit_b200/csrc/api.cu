@@ -148,7 +148,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_NO_FUSE2")) ws->no_fuse2 = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_WALKER"))
-        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "lane") == 0 ? 4 : (std::strcmp(env, "general") == 0 ? 5 : 0))));
+        ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "general") == 0 ? 5 : 0)));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
     if (const char *env = std::getenv("BNK_WARP_W")) ws->cfg_xw = std::atoi(env);
     if (const char *env = std::getenv("BNK_WARP_NS")) ws->cfg_xns = std::atoi(env);
@@ -189,22 +189,29 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
         ws->level_off.push_back((int32_t)wide_all.size());
     }
     step(upload(ws->d_wide, wide_all, ws->stream));
-    if (t->wide_h >= 2) {  // the fused down-sweep of the height-2 level
-        const auto &l1 = t->levels[0], &l2 = t->levels[1];
+    if (t->wide_h >= 2) {  // the fused down-sweep: every wide node above height 1 evaluates its height-1 children itself
+        const auto &l1 = t->levels[0];
         std::vector<int32_t> row_of_node(t->n, -1);
         for (size_t i = 0; i < l1.size(); i++) row_of_node[l1[i].node] = (int32_t)i;
         std::vector<uint8_t> taken(l1.size(), 0);
-        std::vector<Wide2Node> f2(l2.size());
-        for (size_t i = 0; i < l2.size(); i++) {
-            f2[i].v = l2[i];
-            for (int e = 0; e < 2; e++) {
-                std::memset(&f2[i].c[e], 0, sizeof(WideNode));
-                f2[i].c[e].node = -1;
-                const int32_t u = e < l2[i].n_child ? l2[i].c_node[e] : -1;
-                if (u >= 0 && row_of_node[u] >= 0) { f2[i].c[e] = l1[row_of_node[u]]; taken[row_of_node[u]] = 1; }
+        std::vector<Wide2Node> f2;
+        ws->fuse_off.assign(t->wide_h + 1, 0);
+        for (int h = 1; h < t->wide_h; h++) {
+            ws->fuse_off[h] = (int32_t)f2.size();
+            for (const WideNode &v : t->levels[h]) {
+                Wide2Node f;
+                f.v = v;
+                for (int e = 0; e < 2; e++) {
+                    std::memset(&f.c[e], 0, sizeof(WideNode));
+                    f.c[e].node = -1;
+                    const int32_t u = e < v.n_child ? v.c_node[e] : -1;
+                    if (u >= 0 && row_of_node[u] >= 0) { f.c[e] = l1[row_of_node[u]]; taken[row_of_node[u]] = 1; }
+                }
+                f2.push_back(f);
             }
         }
-        std::vector<WideNode> rest;
+        ws->fuse_off[t->wide_h] = (int32_t)f2.size();
+        std::vector<WideNode> rest;  // height-1 nodes under a walked (narrow) parent keep the plain level kernel
         for (size_t i = 0; i < l1.size(); i++) if (!taken[i]) rest.push_back(l1[i]);
         ws->n_fuse2 = (int)f2.size(); ws->n_wide_rest = (int)rest.size();
         step(upload(ws->d_fuse2, f2, ws->stream));
@@ -366,7 +373,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     ws->chunks.clear(); ws->wtiles.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
     ws->cgroups.clear(); ws->chunk_cgroups.clear(); ws->chunk_crecs.clear(); ws->ctiles.clear(); ws->chunk_ctiles.clear();
     ws->xtiles.clear(); ws->chunk_xtiles.clear();
-    ws->ltiles.clear(); ws->chunk_ltiles.clear();
     {   // warp-tiled walker geometry: W consumer warps of 6 x C columns per CTA.  Every CTA of the grid should be
         // resident at once (a walk is one long dependent chain per column), so prefer the tile width that fills
         // the SMs most evenly -- cost = rounds of CTAs per SM x columns per CTA -- and, for a given width, one
@@ -375,6 +381,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         double best_cost = -1.0;
         for (int c = 1; c <= 2; c++) {
             if (ws->cfg_xc >= 1 && ws->cfg_xc <= 3 && c != ws->cfg_xc) continue;
+            if (!(ws->cfg_xc >= 1 && ws->cfg_xc <= 3) && c != 1) continue;  // one column per lane unless BNK_WARP_C asks (r2 A/B on C3b: C = 2 loses, 31.4 vs 30.2 ms; the masked walker needs C = 1)
             const int cw = warp_walk_cols_per_warp(c);
             for (int w = 2; w <= 7 && w * cw <= 64; w++) {
                 if (c == 2 && w > 4) continue;
@@ -411,11 +418,18 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
         Chunk ck{lo, hi, (int)ws->tiles.size(), 0, 1};
         const int w0 = (int)ws->wtiles.size();
         for (int k = lo; k < hi; k++) {
-            const int nc = cat_begin[k + 1] - cat_begin[k];
-            const int nt = (nc + wt - 1) / wt;
-            for (int q = 0; q < nt; q++) {
-                const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
+            // Tiles of the level kernels: one category each, <= wt columns, and every tile but the first of its
+            // category starts on a multiple of 32 columns of the sorted space -- so each warp's row segment (32
+            // columns x 8 bytes) is one aligned 256-byte run: 8 sectors in 2 lines.  An even split (r1) left all
+            // tiles of a category as misaligned as its first column: 9 sectors in 3 lines per warp and row.
+            const int c_lo = cat_begin[k], c_hi = cat_begin[k + 1];
+            int a0 = c_lo;
+            while (a0 < c_hi) {
+                int a1 = ((a0 + wt) / 32) * 32;          // the last multiple of 32 within reach
+                if (a1 <= a0 || a0 % 32 == 0) a1 = a0 + wt;
+                if (a1 > c_hi) a1 = c_hi;
                 ws->wtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
+                a0 = a1;
             }
         }
         const int x0 = (int)ws->xtiles.size();
@@ -427,18 +441,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 for (int q = 0; q < nt; q++) {
                     const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
                     ws->xtiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
-                }
-            }
-        }
-        const int l0 = (int)ws->ltiles.size();
-        {
-            const int lt = lane_walk_cols();
-            for (int k = lo; k < hi; k++) {
-                const int nc = cat_begin[k + 1] - cat_begin[k];
-                const int nt = (nc + lt - 1) / lt;
-                for (int q = 0; q < nt; q++) {
-                    const int a0 = cat_begin[k] + (int)((int64_t)nc * q / nt), a1 = cat_begin[k] + (int)((int64_t)nc * (q + 1) / nt);
-                    ws->ltiles.push_back(TileDesc{a0, a1 - a0, k - lo, 1});
                 }
             }
         }
@@ -495,7 +497,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
             ws->chunk_crecs.push_back(crecs);
             ws->chunk_ctiles.push_back({ct0, (int)ws->ctiles.size()});
             ws->chunk_xtiles.push_back({x0, (int)ws->xtiles.size()});
-            ws->chunk_ltiles.push_back({l0, (int)ws->ltiles.size()});
             ws->chunk_mtiles.push_back({m0, (int)ws->mtiles.size()});
             ws->chunk_cols.push_back({cat_begin[lo], cat_begin[hi]});
         }
@@ -516,7 +517,6 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_cgroups, ws->cgroups, ws->stream));
     TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
     TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
-    TRY(upload(ws->d_ltiles, ws->ltiles, ws->stream));
     TRY(upload(ws->d_mtiles, ws->mtiles, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));  // host vectors above are about to go out of scope / be reused
     ws->ncols = n_cols;
@@ -592,7 +592,7 @@ static int prepare_inputs(bnk_ws *ws, const uint8_t *d_obs, const uint8_t *d_pre
     const int nc = ws->ncols;
     general = d_present != nullptr || ws->evidence_mode == BNK_EVIDENCE_ANYWHERE;
     // a presence mask with evidence on childless nodes only (what GRASP produces: per-column forests over extants'
-    // residues) keeps a fast walker for deep trees: the masked lane walker of sweeps_lane.cu
+    // residues) keeps a fast walker for deep trees: the masked warp-tiled walker of sweeps_warp.cu
     ws->masked_only = d_present != nullptr && ws->evidence_mode != BNK_EVIDENCE_ANYWHERE;
     if (ws->evidence_mode == BNK_EVIDENCE_AUTO) {
         int32_t flag = 0;
@@ -649,9 +649,7 @@ struct WalkSetup {
     WalkLaunch wl;
     bool fast = false;    // lean kernels of sweeps_fast.cu apply
     bool hybrid = false;  // wide height levels run as level launches (wide.cu); the walker takes the narrow top
-    bool lane = false;    // fast, and the lane walker of sweeps_lane.cu takes the walk
     bool wmask = false;   // the masked warp-tiled walker takes the walk (s.warp is set too; s.fast stays false)
-    int n_ltiles = 0;
     bool warp = false;    // fast, and the warp-tiled kernels of sweeps_warp.cu take the walk
     int xw = 0, xc = 0, xns = 0, n_xtiles = 0;
     bool mma = false;     // warp, and the sum-product sweeps run the DMMA variants
@@ -692,30 +690,8 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
     s.fast = false; s.hybrid = false;
     s.warp = false;
     s.mma = false;
-    s.lane = false;
-    if (!general && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode == 4) {
-        // lane walker (BNK_WALKER=lane; measured slower than the warp-tiled walker: 56.9 vs 33.1 ms per step on C3b):
-        // a thread owns a column, the outputs of a step are split over four warps
-        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
-        const int slots = use_program(hybrid);
-        if (lane_walk_smem_bytes(slots, want_down) <= (size_t)ws->smem_optin) {
-            s.fast = true; s.lane = true; s.hybrid = hybrid;
-            s.n_ltiles = ws->chunk_ltiles[ci].second - ws->chunk_ltiles[ci].first;
-            s.a.tiles = ws->d_ltiles.p + ws->chunk_ltiles[ci].first;
-            s.a.tile_base = ws->chunk_ltiles[ci].first;
-            s.a.tile_stride = (int32_t)ws->ltiles.size() * lane_walk_cols();
-            s.a.smem_slots = slots;
-            // the tiled copy of the observation matrix (childless children are looked up through it)
-            CUDA_TRY(ws->d_obs_t.ensure((size_t)ws->n * s.a.tile_stride));
-            CUDA_TRY(launch_tile_bytes(obs_s, ws->d_orig_col.p, ws->d_ltiles.p + ws->chunk_ltiles[ci].first, s.n_ltiles,
-                                       s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_obs_t.p, ws->stream));
-            ws->launches++;
-            s.a.obs_t = ws->d_obs_t.p;
-            return BNK_OK;
-        }
-    }
     if (general && ws->masked_only && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode != 5 &&
-        ws->walker_mode != 4 && ws->walker_mode != 1 && ws->xc == 1) {
+        ws->walker_mode != 1 && ws->xc == 1) {
         // masked warp-tiled walker (r2): per-column forests in the fast deep-tree walker.  A pre-pass turns the presence
         // mask into one case byte per (walker node, column); the wide levels keep the general level kernels
         const bool hybrid = t->wide_h > 0 && !ws->no_wide;
@@ -729,31 +705,6 @@ static int setup_walk(bnk_ws *ws, const Chunk &ck, bool general, bool want_down,
             s.n_xtiles = ws->chunk_xtiles[ci].second - ws->chunk_xtiles[ci].first;
             s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
             s.a.smem_slots = slots;
-            return BNK_OK;
-        }
-    }
-    if (general && ws->masked_only && !ws->force_generic && t->max_children <= 2 && K == 20 && ws->walker_mode != 5) {
-        // masked lane walker: per-column forests (presence mask, evidence on childless nodes only).  The wide levels
-        // keep the general level kernels (s.fast stays false); the walk -- all of a deep tree -- leaves the general
-        // walker of sweeps.cu (masked C3b: 115 ms there)
-        const bool hybrid = t->wide_h > 0 && !ws->no_wide;
-        const int slots = use_program(hybrid);
-        if (lane_walk_smem_bytes(slots, want_down) <= (size_t)ws->smem_optin) {
-            s.lane = true; s.hybrid = hybrid;
-            s.n_ltiles = ws->chunk_ltiles[ci].second - ws->chunk_ltiles[ci].first;
-            s.a.tiles = ws->d_ltiles.p + ws->chunk_ltiles[ci].first;
-            s.a.tile_base = ws->chunk_ltiles[ci].first;
-            s.a.tile_stride = (int32_t)ws->ltiles.size() * lane_walk_cols();
-            s.a.smem_slots = slots;
-            CUDA_TRY(ws->d_obs_t.ensure((size_t)ws->n * s.a.tile_stride));
-            CUDA_TRY(ws->d_present_t.ensure((size_t)ws->n * s.a.tile_stride));
-            CUDA_TRY(launch_tile_bytes(obs_s, ws->d_orig_col.p, ws->d_ltiles.p + ws->chunk_ltiles[ci].first, s.n_ltiles,
-                                       s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_obs_t.p, ws->stream));
-            CUDA_TRY(launch_tile_bytes(present_s, ws->d_orig_col.p, ws->d_ltiles.p + ws->chunk_ltiles[ci].first, s.n_ltiles,
-                                       s.a.tile_base, ws->n, ws->ncols, s.a.tile_stride, ws->d_present_t.p, ws->stream));
-            ws->launches += 2;
-            s.a.obs_t = ws->d_obs_t.p;
-            s.a.present_t = ws->d_present_t.p;
             return BNK_OK;
         }
     }
@@ -935,8 +886,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
                 ws->launches++;
                 s.a.caseb = ws->d_kind.p;
             }
-            CUDA_TRY(s.lane ? launch_lane_up(0, s.a, s.n_ltiles, ws->stream)
-                     : s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+            CUDA_TRY(s.warp ? launch_joint_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                             : s.fast ? launch_joint_up_fast(s.wl, s.a) : launch_joint_up(s.wl, s.a));
             ws->launches++;
             CUDA_TRY(cudaEventRecord(ws->ev[1][1], ws->stream));
@@ -946,6 +896,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             std::memset(&ta, 0, sizeof(ta));
             ta.down = s.a.down; ta.n_steps = s.a.n_steps; ta.ncols = nc; ta.n_nodes = ws->n; ta.K = K;
             ta.ptr = ws->d_ptr.p; ta.kind = s.fast ? nullptr : ws->d_kind.p;
+            ta.kind_obs = ws->masked_only ? 0 : 1;  // evidence on childless nodes only: no walker node is KIND_OBS
             ta.obs = d_obs; ta.orig_col = ws->d_orig_col.p; ta.state_s = state_s; ta.tb_slots = s.tb_slots;
             ta.col_lo = w.col_lo; ta.col_hi = w.col_hi;
             CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
@@ -1116,8 +1067,7 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
             ws->launches++;
             s.a.caseb = ws->d_kindm.p;
         }
-        CUDA_TRY(s.lane ? launch_lane_up(1, s.a, s.n_ltiles, ws->stream)
-                 : s.mma ? launch_sum_up_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
+        CUDA_TRY(s.mma ? launch_sum_up_mma(s.a, s.n_mtiles, s.mw, s.mns, ws->stream)
                  : s.warp ? launch_sum_up_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                           : s.fast ? launch_sum_up_fast(s.wl, s.a) : launch_sum_up(s.wl, s.a));
         ws->launches++;
@@ -1134,23 +1084,25 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
             }
             CUDA_TRY(cudaEventRecord(ws->ev[4][0], ws->stream));
             if (s.mma) s.a.tiles = ws->d_xtiles.p + ws->chunk_xtiles[ci].first;
-            CUDA_TRY(s.lane ? launch_lane_down(s.a, s.n_ltiles, ws->stream)
-                     : s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
+            CUDA_TRY(s.warp ? launch_sum_down_warp(s.a, s.n_xtiles, s.xw, s.xc, s.xns, ws->stream)
                               : s.fast ? launch_sum_down_fast(s.wl, s.a) : launch_sum_down(s.wl, s.a));
             ws->launches++;
             if (s.hybrid) {
                 w.tmsg = ws->d_tmsg.p; w.out_post = post_base; w.qrow = s.a.qrow;
                 const bool fuse2 = !gen && K == 20 && t->wide_h >= 2 && ws->n_fuse2 > 0 && !ws->no_fuse2;
-                TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
-                    return gen ? launch_down_wide_gen(K, wa, n_wt, cnt, ws->stream) : launch_down_wide(K, wa, n_wt, cnt, ws->stream); },
-                    fuse2 ? 2 : 0));
+                if (!fuse2)
+                    TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
+                        return gen ? launch_down_wide_gen(K, wa, n_wt, cnt, ws->stream) : launch_down_wide(K, wa, n_wt, cnt, ws->stream); }));
                 if (fuse2) {
-                    // the height-2 level evaluates its height-1 children in the same thread (their from-above vectors
-                    // never reach HBM); height-1 nodes under a taller or walked parent keep the plain level kernel
+                    // every wide node above height 1 evaluates its height-1 children in the same thread (their
+                    // from-above vectors never reach HBM); height-1 nodes under a walked parent keep the plain kernel
                     w.cherry = 0;
-                    TRY(for_node_slices(ws, w, ws->n_fuse2, [&](WideArgs &wa, int off, int cnt) {
-                        wa.fuse2 = ws->d_fuse2.p + off;
-                        return launch_down_wide2(K, wa, n_wt, cnt, ws->stream); }));
+                    for (int h = t->wide_h - 1; h >= 1; h--) {
+                        const int base = ws->fuse_off[h];
+                        TRY(for_node_slices(ws, w, ws->fuse_off[h + 1] - base, [&](WideArgs &wa, int off, int cnt) {
+                            wa.fuse2 = ws->d_fuse2.p + base + off;
+                            return launch_down_wide2(K, wa, n_wt, cnt, ws->stream); }));
+                    }
                     w.fuse2 = nullptr;
                     w.cherry = 1;
                     TRY(for_node_slices(ws, w, ws->n_wide_rest, [&](WideArgs &wa, int off, int cnt) {
@@ -1208,6 +1160,16 @@ extern "C" int bnk_joint_marginal_dev(bnk_ws *ws, int32_t n_cols, const uint8_t 
     if (ws->is_sub) return fail(BNK_ERR_STATE, "joint_marginal: not on a sub-workspace");
     ENTER_DEVICE(ws->device);
     TRY(ensure_rates(ws, n_cols));
+    {   // Two streams pay where the walks dominate (deep trees: latency-bound kernels fill each other's stalls).  On a
+        // level-scheduled tree the kernels of one pass fill the machine on their own, the second stream only adds a
+        // second table build and tail effects (C3a: 16.8 ms against 16.4 ms one pass after the other): run in order.
+        const bnk_tree *t = ws->tree;
+        const bool walker_tree = t->wide_h == 0 || ws->no_wide || 2 * (int64_t)t->narrow.up.size() > t->n_int;
+        if (!walker_tree) {
+            TRY(bnk_joint_dev(ws, n_cols, d_obs, d_present, d_out_state));
+            return ws_run_sum(ws, n_cols, d_obs, d_present, query_nodes_host, n_query, d_out_post, d_out_logl, nullptr);
+        }
+    }
     if (!ws->twin) {
         bnk_ws *tw = nullptr;
         TRY(bnk_ws_create(&ws->model, ws->tree, ws->max_cols, ws->device, nullptr, &tw));

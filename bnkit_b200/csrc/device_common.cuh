@@ -64,10 +64,6 @@ struct WalkArgs {
     double *tmsg;               // from-above vectors handed to wide children, [ent][K][ncols]
     const int32_t *esum_wide;   // [ncols] rescale exponents accumulated by the wide sum up-sweep (or nullptr)
     const double *logl_wide;    // [ncols] log-likelihood terms the general wide kernels accumulated (or nullptr)
-    // lane walker (sweeps_lane.cu): tiled copies of the inputs, [node][tile_stride] bytes, 32 per (node, tile);
-    // tile_base = index of a.tiles[0] among all lane tiles of the workspace
-    const uint8_t *obs_t, *present_t;
-    int32_t tile_stride, tile_base;
     // masked warp-tiled walker (sweeps_warp.cu): case byte of every (walker node, sorted column), [n_int][ncols]:
     // kind | child 0 present << 2 | child 1 present << 3 (launch_walk_case); nullptr selects the unmasked kernels
     const uint8_t *caseb;
@@ -165,19 +161,6 @@ cudaError_t launch_joint_up_warp(const WalkArgs &a, int n_tiles, int W, int C, i
 cudaError_t launch_sum_up_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
 cudaError_t launch_sum_down_warp(const WalkArgs &a, int n_tiles, int W, int C, int ns, cudaStream_t st);
 
-// lane walker (sweeps_lane.cu): K = 20, a thread owns a column (32 per CTA), the 20 outputs of a step are split over
-// four warps; a.tiles = tiles of one category and at most lane_walk_cols() columns; a.obs_t must be set when the
-// program has childless children
-size_t lane_walk_smem_bytes(int slots, bool down);
-int lane_walk_cols();
-cudaError_t launch_lane_up(int mode, const WalkArgs &a, int n_tiles, cudaStream_t st);
-cudaError_t launch_lane_down(const WalkArgs &a, int n_tiles, cudaStream_t st);
-cudaError_t launch_tile_bytes(const uint8_t *in, const int32_t *orig_col, const TileDesc *tiles, int n_tiles, int tile_base,
-                              int n_nodes, int ncols, int tile_stride, uint8_t *out, cudaStream_t st);
-
-// joint up-sweep of the warp-tiled walker with ten lanes per column (3 columns per warp, W <= 14 consumer warps);
-// a.tiles = tiles of one category and at most 3 W columns
-
 // sum-product sweeps of the warp-tiled walker on the FP64 tensor-core path (DMMA.8x8x4): 8 columns per warp,
 // a.tiles = tiles of one category and at most 8 W columns
 size_t mma_walk_smem_bytes(int W, int ns, int slots, bool down);
@@ -189,6 +172,7 @@ struct TracebackArgs {
     int32_t n_steps, ncols, n_nodes, K;
     // walk traceback: everything in SORTED column space
     const uint8_t *ptr, *kind;      // kind == nullptr: root steps are KIND_ROOT, all others KIND_MSG
+    int32_t kind_obs;               // 0: no kind byte is KIND_OBS (evidence on childless nodes only)
     const int32_t *orig_col;        // sorted -> original column (KIND_OBS pass-through reads obs)
     uint8_t *state_s;               // [node][ncols] sorted space
     int32_t col_lo, col_hi;         // sorted columns of the chunk being processed

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 5) traceback_kernel(const Trace
 // ncu: one warp per scheduler, `wait` stalls, i.e. the instruction count IS the time.)
 constexpr int TC_B = 16, TC_NB = 4, TC_WARPS = 2, TC_MAXSLOTS = 192;
 
-template <bool HAS_KIND>
+template <bool HAS_KIND, bool HAS_OBS>
 __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const TracebackArgs a)
 {
     extern __shared__ __align__(16) uint8_t tc_smem[];
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
     const bool wide = (run & 15) == 0 && (ent_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(pbase) & 15) == 0;
     const int n_steps = a.n_steps, n_batches = (n_steps + TC_B - 1) / TC_B;
     const unsigned FULL = 0xffffffffu;
-    const int ocol = HAS_KIND ? a.orig_col[col] : 0;
+    const int ocol = (HAS_KIND && HAS_OBS) ? a.orig_col[col] : 0;
     uint8_t *srow = a.state_s + col;
 
     // copies of batch j: lane u < TC_B knows the step's ent; every lane copies its share of each step's run
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
                 const int kind = c_kind[u] & 3;  // (the masked warp-tiled walker keeps child flags above the kind)
                 const int src = (kind == KIND_MSG && ps < K) ? ps : 0;
                 s = rows[u * row_bytes + src];
-                if (kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + ocol];
-                else if (kind != KIND_MSG && kind != KIND_ROOT) s = BNK_NONE;
+                if (HAS_OBS && kind == KIND_OBS) s = a.obs[(size_t)(unsigned)node * ncols_u + ocol];
+                else s = (kind == KIND_MSG || kind == KIND_ROOT) ? s : BNK_NONE;
             } else {
                 s = rows[u * row_bytes + ((meta >> 24) ? 0 : ps)];  // a root step reads entry 0
             }
@@ -231,24 +231,22 @@ __global__ void __launch_bounds__(TC_WARPS * 32) traceback_cols_kernel(const Tra
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t st)
 {
     if (a.tb_slots >= 4095) return cudaErrorInvalidValue;
-    static const bool old_tb = [] { const char *e = std::getenv("BNK_TRACEBACK"); return e && std::strcmp(e, "warp") == 0; }();
+    const char *tb_env = std::getenv("BNK_TRACEBACK");  // "warp": the warp-per-column kernel (its only other use: > TC_MAXSLOTS stack slots)
+    const bool old_tb = tb_env && std::strcmp(tb_env, "warp") == 0;
     if (!old_tb && a.tb_slots <= TC_MAXSLOTS && a.n_steps > 0 && a.col_hi > a.col_lo && (a.K & 3) == 0) {
         const int n_warps = (a.col_hi - a.col_lo + 31) / 32;
         const unsigned grid = (n_warps + TC_WARPS - 1) / TC_WARPS;
         const size_t smem = (size_t)TC_WARPS * (TC_NB * TC_B * 32 * a.K + (a.tb_slots > 0 ? a.tb_slots : 1) * 32);
-        cudaError_t e;
-        if (a.kind) {
-            e = cudaFuncSetAttribute(traceback_cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(traceback_cols_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        auto go = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
-            traceback_cols_kernel<true><<<grid, TC_WARPS * 32, smem, st>>>(a);
-        } else {
-            e = cudaFuncSetAttribute(traceback_cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(traceback_cols_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-            traceback_cols_kernel<false><<<grid, TC_WARPS * 32, smem, st>>>(a);
-        }
-        return cudaGetLastError();
+            kern<<<grid, TC_WARPS * 32, smem, st>>>(a);
+            return cudaGetLastError();
+        };
+        if (a.kind && a.kind_obs) return go(traceback_cols_kernel<true, true>);
+        if (a.kind) return go(traceback_cols_kernel<true, false>);
+        return go(traceback_cols_kernel<false, false>);
     }
     const unsigned grid = (a.ncols + TB_WARPS - 1) / TB_WARPS;
     if (a.tb_slots <= 32) {

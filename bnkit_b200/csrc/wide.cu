@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
     const bool leaf0 = CHERRY || w.c_ent[0] < 0, leaf1 = two && (CHERRY || w.c_ent[1] < 0);
     const bool push0 = !leaf0, push1 = two && !leaf1;
     const int q = a.qrow ? a.qrow[w.ent] : w.ent;
+    const bool post32 = (reinterpret_cast<uintptr_t>(a.out_post) & 31) == 0;
     int cur_cat = -1;
     for (int ti = t_lo; ti < t_hi; ti++) {
         const TileDesc tile = a.tiles[ti];
@@ -144,6 +145,17 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
         const bool valid = (int)threadIdx.x < tile.ncols;
         const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
 
+        // children: an observed leaf is a row of its P^T table (shared memory), an internal child
+        // its up-message in HBM; uninstantiated leaves (rare) go through child_vector
+        int o0 = BNK_NONE, o1 = BNK_NONE;
+        const int ocol = a.orig_col[col];  // inputs stay in the caller's column order
+        if (leaf0) o0 = a.obs[(size_t)w.c_node[0] * a.ncols + ocol];
+        if (leaf1) o1 = a.obs[(size_t)w.c_node[1] * a.ncols + ocol];
+        const bool slow = (leaf0 && o0 == BNK_NONE) || (leaf1 && o1 == BNK_NONE);
+        const double *m0 = leaf0 ? nullptr : a.msg + (size_t)w.c_ent[0] * K * a.ncols + col;
+        const double *m1 = (two && !leaf1) ? a.msg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
+        double *t0 = push0 ? a.tmsg + (size_t)w.c_ent[0] * K * a.ncols + col : nullptr;
+        double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
         double T[K];
         {
             const double *t = a.tmsg + (size_t)w.ent * K * a.ncols + col;
@@ -157,17 +169,6 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
 #pragma unroll
             for (int x = 0; x < K; x++) T[x] *= scale;
         }
-        // children: an observed leaf is a row of its P^T table (shared memory), an internal child
-        // its up-message in HBM; uninstantiated leaves (rare) go through child_vector
-        int o0 = BNK_NONE, o1 = BNK_NONE;
-        const int ocol = a.orig_col[col];  // inputs stay in the caller's column order
-        if (leaf0) o0 = a.obs[(size_t)w.c_node[0] * a.ncols + ocol];
-        if (leaf1) o1 = a.obs[(size_t)w.c_node[1] * a.ncols + ocol];
-        const bool slow = (leaf0 && o0 == BNK_NONE) || (leaf1 && o1 == BNK_NONE);
-        const double *m0 = leaf0 ? nullptr : a.msg + (size_t)w.c_ent[0] * K * a.ncols + col;
-        const double *m1 = (two && !leaf1) ? a.msg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
-        double *t0 = push0 ? a.tmsg + (size_t)w.c_ent[0] * K * a.ncols + col : nullptr;
-        double *t1 = push1 ? a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col : nullptr;
         double U[K], S = 0.0;
         if (!slow) {
             // phase 1: D = P^T T for all states (registers only)
@@ -221,20 +222,18 @@ __global__ void __launch_bounds__(WT, CHERRY ? 4 : 3) down_wide_kernel(const Wid
         if (valid && q >= 0 && a.out_post) {
             // each thread writes its column's 160 contiguous bytes (staging the tile through shared
             // memory for wider stores was measured: no gain, two extra barriers)
-            const double r = w_rcp(S);
-            double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)q * a.ncols + ocol) * K);
-#pragma unroll
-            for (int x2 = 0; x2 < K / 2; x2++) __stcs(o + x2, make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r));
+            store_post_row<K>(a.out_post + ((size_t)q * a.ncols + ocol) * K, U, w_rcp(S), post32);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------
-// down-sweep of the height-2 level FUSED with its height-1 children (r2).  A height-1 node ("cherry") has only
+// down-sweep of a level FUSED with its height-1 children (r2).  A height-1 node ("cherry") has only
 // childless children, so once its parent v knows its own from-above product D_v, the cherry's posterior is one
 // more 20 x 20 contraction away: T_c = D_v * g_sibling, D_c = P_c^T T_c, post_c ~ D_c * (leaf rows).  Done in the
 // parent's thread, T_c never travels through HBM (160 B written + 160 B read per cherry and column, 20 % of the
-// down-sweep's DRAM traffic on a balanced tree) and the height-1 level needs no launch of its own.  Same arithmetic
+// down-sweep's DRAM traffic on a balanced tree) and the height-1 level needs no launch of its own.  Taller
+// children get their from-above vector through HBM as in down_wide_kernel.  Same arithmetic
 // and order as down_wide_kernel on both levels (incl. the power-of-two rescale of T_c); results agree to a few ulp
 // (the compiler contracts the multiply-adds of the two kernels differently).
 // Uninstantiated leaves need no slow path here: row K of a staged leaf table holds the sum of its rows (what
@@ -253,9 +252,11 @@ __global__ void __launch_bounds__(WT, 3) down_wide2_kernel(const WideArgs a)
     const bool two = w.n_child > 1;
     const bool ch0 = w2.c[0].node >= 0, ch1 = two && w2.c[1].node >= 0;   // children fused into this thread
     const bool leaf0 = w.c_ent[0] < 0, leaf1 = two && w.c_ent[1] < 0;
+    const bool push0 = !leaf0 && !ch0, push1 = two && !leaf1 && !ch1;     // taller children: from-above vector through HBM
     const int q = a.qrow ? a.qrow[w.ent] : w.ent;
     const int qc0 = ch0 ? (a.qrow ? a.qrow[w2.c[0].ent] : w2.c[0].ent) : -1;
     const int qc1 = ch1 ? (a.qrow ? a.qrow[w2.c[1].ent] : w2.c[1].ent) : -1;
+    const bool post32 = (reinterpret_cast<uintptr_t>(a.out_post) & 31) == 0;
     int cur_cat = -1;
     for (int ti = t_lo; ti < t_hi; ti++) {
         const TileDesc tile = a.tiles[ti];
@@ -350,11 +351,21 @@ __global__ void __launch_bounds__(WT, 3) down_wide2_kernel(const WideArgs a)
             for (int x = 0; x < K; x++) S += D[x] * (c0[x] * c1[x]);
             if (valid && q >= 0 && a.out_post) {
                 const double r = w_rcp(S);
-                double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)q * a.ncols + ocol) * K);
+                double *row = a.out_post + ((size_t)q * a.ncols + ocol) * K;
+                if (post32) {
 #pragma unroll
-                for (int x2 = 0; x2 < K / 2; x2++)
-                    __stcs(o + x2, make_double2((D[2 * x2] * (c0[2 * x2] * c1[2 * x2])) * r,
-                                                (D[2 * x2 + 1] * (c0[2 * x2 + 1] * c1[2 * x2 + 1])) * r));
+                    for (int x4 = 0; x4 < K / 4; x4++)
+                        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(row + 4 * x4),
+                                     "d"((D[4 * x4] * (c0[4 * x4] * c1[4 * x4])) * r), "d"((D[4 * x4 + 1] * (c0[4 * x4 + 1] * c1[4 * x4 + 1])) * r),
+                                     "d"((D[4 * x4 + 2] * (c0[4 * x4 + 2] * c1[4 * x4 + 2])) * r), "d"((D[4 * x4 + 3] * (c0[4 * x4 + 3] * c1[4 * x4 + 3])) * r)
+                                     : "memory");
+                } else {
+                    double2 *o = reinterpret_cast<double2 *>(row);
+#pragma unroll
+                    for (int x2 = 0; x2 < K / 2; x2++)
+                        __stcs(o + x2, make_double2((D[2 * x2] * (c0[2 * x2] * c1[2 * x2])) * r,
+                                                    (D[2 * x2 + 1] * (c0[2 * x2 + 1] * c1[2 * x2 + 1])) * r));
+                }
             }
         }
         // from-above vectors of the two children, in place: c1 <- T_child0 = D * c1, c0 <- T_child1 = D * c0
@@ -363,6 +374,16 @@ __global__ void __launch_bounds__(WT, 3) down_wide2_kernel(const WideArgs a)
             const double d = D[x], a0 = c0[x], a1 = c1[x];
             c1[x] = d * a1;
             c0[x] = d * a0;
+        }
+        if (valid && push0) {
+            double *t0 = a.tmsg + (size_t)w.c_ent[0] * K * a.ncols + col;
+#pragma unroll
+            for (int x = 0; x < K; x++) t0[(size_t)x * a.ncols] = c1[x];
+        }
+        if (valid && push1) {
+            double *t1 = a.tmsg + (size_t)w.c_ent[1] * K * a.ncols + col;
+#pragma unroll
+            for (int x = 0; x < K; x++) t1[(size_t)x * a.ncols] = c0[x];
         }
         // the fused cherries
 #pragma unroll
@@ -396,12 +417,7 @@ __global__ void __launch_bounds__(WT, 3) down_wide2_kernel(const WideArgs a)
                 U[x] = (acc0 + acc1) * (ra[x] * (ctwo ? rb[x] : 1.0));
                 S += U[x];
             }
-            if (valid) {
-                const double r = w_rcp(S);
-                double2 *o = reinterpret_cast<double2 *>(a.out_post + ((size_t)qc * a.ncols + ocol) * K);
-#pragma unroll
-                for (int x2 = 0; x2 < K / 2; x2++) __stcs(o + x2, make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r));
-            }
+            if (valid) store_post_row<K>(a.out_post + ((size_t)qc * a.ncols + ocol) * K, U, w_rcp(S), post32);
         }
     }
 }

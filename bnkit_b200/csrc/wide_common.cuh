@@ -41,6 +41,27 @@ __device__ __forceinline__ double w_rcp(double s)
     return r;
 }
 
+// One posterior row (K doubles of one (query, column), contiguous) leaves as K / 4 256-bit streaming stores
+// (STG.256, sm_100): a thread then writes whole 32-byte sectors.  With 128-bit stores every sector was written
+// by two instructions, i.e. twice the L2 write requests for the same bytes -- and the level kernels sit closer
+// to the L2's request rate than to anything else (tools/microbench/layout_bw.cu: a kernel that only moves these
+// rows reaches the measured 6.5 TB/s).  Rows that are not 32-byte aligned (a caller's odd pointer) fall back.
+template <int K>
+__device__ __forceinline__ void store_post_row(double *row, const double (&U)[K], double r, bool aligned32)
+{
+    if (K % 4 == 0 && aligned32) {
+#pragma unroll
+        for (int x4 = 0; x4 < K / 4; x4++)
+            asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(row + 4 * x4), "d"(U[4 * x4] * r), "d"(U[4 * x4 + 1] * r),
+                         "d"(U[4 * x4 + 2] * r), "d"(U[4 * x4 + 3] * r)
+                         : "memory");
+    } else {
+        double2 *o = reinterpret_cast<double2 *>(row);
+#pragma unroll
+        for (int x2 = 0; x2 < K / 2; x2++) __stcs(o + x2, make_double2(U[2 * x2] * r, U[2 * x2 + 1] * r));
+    }
+}
+
 // Max-out of one table row (Factorize.getMaxMargin, src/bn/factor/Factorize.java:1472-1481): the first strict
 // maximum of v[x] = Lrow[x] + G[x] scanning x ascending from (-inf, index 0).  Run as a tournament in which a
 // tie keeps the lower index: the winner is the lowest index holding the maximal value -- the same answer as the

@@ -269,12 +269,7 @@ __global__ void __launch_bounds__(WT, 3) down_wide_gen_kernel(const WideArgs a)
             D[x] = D[x] * (c0[x] * c1[x]);
             S += D[x];
         }
-        if (post) {
-            const double r = w_rcp(S);
-#pragma unroll
-            for (int x2 = 0; x2 < K / 2; x2++)
-                __stcs(reinterpret_cast<double2 *>(post) + x2, make_double2(D[2 * x2] * r, D[2 * x2 + 1] * r));
-        }
+        if (post) store_post_row<K>(post, D, w_rcp(S), (reinterpret_cast<uintptr_t>(a.out_post) & 31) == 0);
     }
 }
 

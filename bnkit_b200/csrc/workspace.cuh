@@ -114,11 +114,12 @@ struct bnk_ws {
     DevBuf<Step> d_up{&reg}, d_down{&reg}, d_up_n{&reg}, d_down_n{&reg};             // full / narrow walk programs
     DevBuf<ChildRef> d_up_child{&reg}, d_down_child{&reg}, d_up_child_n{&reg}, d_down_child_n{&reg};
     DevBuf<WideNode> d_wide{&reg};                                  // wide levels, concatenated (height 1 first)
-    // fused down-sweep of the height-2 level (wide.cu: down_wide2_kernel): its nodes with their height-1 children,
-    // and the height-1 nodes whose parent is NOT a wide height-2 node (they keep the plain level kernel)
+    // fused down-sweep (wide.cu: down_wide2_kernel): the wide nodes above height 1 with their height-1 children,
+    // and the height-1 nodes whose parent is NOT a wide node (they keep the plain level kernel)
     DevBuf<Wide2Node> d_fuse2{&reg};
     DevBuf<WideNode> d_wide_rest{&reg};
     int n_fuse2 = 0, n_wide_rest = 0;
+    std::vector<int32_t> fuse_off;                            // [wide_h + 1] into d_fuse2, per height level (index 1 = height 2)
     bool no_fuse2 = false;                                    // BNK_NO_FUSE2=1 (A/B, tests)
     std::vector<int32_t> level_off;                           // [wide_h + 1] into d_wide
     bool no_wide = false;                                     // bnk_ws_configure: walker only (tests, profiling)
@@ -151,14 +152,9 @@ struct bnk_ws {
     std::vector<TileDesc> xtiles, mtiles;  // mtiles: DMMA sum-product up-sweep (<= 8 * mw columns)
     std::vector<std::pair<int, int>> chunk_xtiles, chunk_mtiles;
     DevBuf<TileDesc> d_xtiles{&reg}, d_mtiles{&reg};
-    // lane walker (sweeps_lane.cu): tiles of one category, <= 32 columns; tiled copies of the inputs
-    std::vector<TileDesc> ltiles;
-    std::vector<std::pair<int, int>> chunk_ltiles;
-    DevBuf<TileDesc> d_ltiles{&reg};
-    DevBuf<uint8_t> d_obs_t{&reg}, d_present_t{&reg};
     int mw = 0;                            // consumer warps per CTA of the DMMA variants
     int xw = 0, xc = 2;                    // consumer warps per CTA, columns per lane
-    int walker_mode = 0;                   // BNK_WALKER: 0 auto (= warp-tiled + DMMA), 4 lane walker (sweeps_lane.cu), 1 lean CTA walker,
+    int walker_mode = 0;                   // BNK_WALKER: 0 auto (= warp-tiled + DMMA), 1 lean CTA walker,
                                            // 2 warp-tiled with the scalar sum-product kernels (no DMMA), 3 warp-tiled (r1 default)
     int cfg_xw = 0, cfg_xns = 0, cfg_xc = 0;  // BNK_WARP_W / BNK_WARP_NS / BNK_WARP_C (tuning knobs, tests)
     bool no_cherry = false;                // BNK_NO_CHERRY=1: height-1 level through the plain level kernel (A/B, tests)

@@ -134,7 +134,7 @@ def test_tile_geometries(bnk, oracle, tile_cols, cpt, monkeypatch):
                                  {"BNK_WARP_W": "1", "BNK_WARP_NS": "4", "BNK_WARP_C": "2"},
                                  {"BNK_WARP_W": "7", "BNK_WARP_NS": "6", "BNK_WARP_C": "1"}, {"BNK_WALKER": "lean"},
                                  {"BNK_WALKER": "scalar"}, {"BNK_MMA_W": "1", "BNK_WARP_NS": "2"}, {"BNK_MMA_W": "3"},
-                                 {"BNK_MMA_W": "7", "BNK_WARP_NS": "5"}, {"BNK_WALKER": "lane"}])
+                                 {"BNK_MMA_W": "7", "BNK_WARP_NS": "5"}, {"BNK_TRACEBACK": "warp"}])
 def test_warp_tiled_walker(bnk, oracle, env, monkeypatch):
     """sweeps_warp.cu (warp-owned columns, TMA-fed stage ring; sum-product sweeps on DMMA by default, scalar with
     BNK_WALKER=scalar) against the oracle for every CTA shape and ring depth, and against the lean CTA walker: deep chains (> 4 program chunks), category tiles narrower than a
@@ -488,10 +488,10 @@ def test_device_tables_against_an_independent_matrix_exponential(bnk, name):
     ws.close()
 
 
-@pytest.mark.parametrize("walker", ["", "lane", "general"])
+@pytest.mark.parametrize("walker", ["", "general"])
 def test_masked_walker_per_column_forests(bnk, oracle, walker, monkeypatch):
-    """Per-column forests (presence masks, evidence on extants only) through the masked warp-tiled walker (default),
-    the masked lane walker (BNK_WALKER=lane) and the general walker (BNK_WALKER=general): a 700-level caterpillar (walker only, > 20 program chunks), a balanced
+    """Per-column forests (presence masks, evidence on extants only) through the masked warp-tiled walker (default)
+    and the general walker (BNK_WALKER=general): a 700-level caterpillar (walker only, > 20 program chunks), a balanced
     tree (general level kernels + walker for the top), irregular binary trees with per-column rates, uninstantiated
     present extants, fully absent columns and a column where only one extant is present -- against the oracle."""
     from bnkit_b200 import synth

@@ -21,12 +21,12 @@ ix = {h: i for i, h in enumerate(hdr)}
 def sweep_of(name):
     n = name.replace(" ", "")
     if any(k in n for k in ("cherry_pairs_kernel<20,0>", "cherry_expand_kernel<20,0>", "up_wide_kernel<20,0>", "up_warp_kernel<0", "up_wide_gen_kernel<20,0>",
-                            "traceback", "up_joint10", "lane_up_kernel<0>", "leaf_states_kernel", "scatter_rows_kernel")):
+                            "traceback", "leaf_states_kernel", "scatter_rows_kernel")):
         return "joint_up+traceback"
     if any(k in n for k in ("cherry_pairs_kernel<20,1>", "cherry_expand_kernel<20,1>", "up_wide_kernel<20,1>", "up_mma_kernel", "up_warp_kernel<1",
-                            "up_wide_gen_kernel<20,1>", "sum_escale_kernel", "lane_up_kernel<1>")):
+                            "up_wide_gen_kernel<20,1>", "sum_escale_kernel")):
         return "sum_up"
-    if any(k in n for k in ("down_wide", "down_warp_kernel", "down_mma_kernel", "lane_down_kernel")):
+    if any(k in n for k in ("down_wide", "down_warp_kernel")):
         return "sum_down"
     return None
 

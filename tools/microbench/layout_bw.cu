@@ -3,17 +3,19 @@
 // writes as many).  This microbenchmark moves the same bytes with no arithmetic in two layouts:
 //   rows : msg[node][state][ncols]            (what the library uses)
 //   tiles: msg[node][tile][state][128]        (a CTA's 20 KB are contiguous)
-// each thread reads R vectors of 20 doubles and writes W, like up- / down-sweep kernels do.
+// each thread reads R vectors of 20 doubles and writes W, like up- / down-sweep kernels do.  shift = 2, 5: the rows
+// layout with segments that start 16 / 40 bytes off a 128-byte line (what a rate category of odd size does to
+// every tile behind it).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 layout_bw.cu -o layout_bw
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
 constexpr int K = 20, WT = 128;
 template <int R, int W, bool TILED>
-__global__ void __launch_bounds__(WT) mv(const double *__restrict__ in, double *__restrict__ out, int ncols, int n_tiles, int n_nodes)
+__global__ void __launch_bounds__(WT) mv(const double *__restrict__ in, double *__restrict__ out, int ncols, int n_tiles, int n_nodes, int shift)
 {
     const int node = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    const int col = tile * WT + tid;
+    const int col = tile * WT + tid + shift;  // shift != 0: row segments that start off a sector / line boundary
     if (col >= ncols) return;
     const size_t node_stride = TILED ? (size_t)n_tiles * K * WT : (size_t)K * ncols;
     const size_t xs = TILED ? WT : ncols;
@@ -47,8 +49,8 @@ int main() {
     dim3 grid(n_tiles, nodes);
     const double gb = (double)nodes * ncols * K * 8 / 1e9;
     float ms;
-#define RUN(R, W, T) ms = timeit([&] { mv<R, W, T><<<grid, WT>>>(in, out, ncols, n_tiles, nodes); }); \
-    printf("read %d write %d %-5s  %.3f ms  %.0f GB/s\n", R, W, T ? "tiles" : "rows", ms, gb * (R + W) / ms * 1e3);
+#define RUN(R, W, T) for (int shift : {0, 2, 5}) { if (T && shift) continue; ms = timeit([&] { mv<R, W, T><<<grid, WT>>>(in, out, ncols, n_tiles, nodes, shift); }); \
+    printf("read %d write %d %-5s shift %d  %.3f ms  %.0f GB/s\n", R, W, T ? "tiles" : "rows", shift, ms, gb * (R + W) / ms * 1e3); }
     RUN(3, 3, false) RUN(3, 3, true) RUN(2, 1, false) RUN(2, 1, true) RUN(1, 1, false) RUN(1, 1, true) RUN(3, 0, false) RUN(3, 0, true) RUN(0, 3, false) RUN(0, 3, true)
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
