@@ -147,6 +147,7 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
     for (auto &e : ws->ev) for (auto &x : e) cudaEventCreate(&x);
     if (const char *env = std::getenv("BNK_NO_CHERRY")) ws->no_cherry = std::atoi(env) != 0;
     if (const char *env = std::getenv("BNK_NO_FUSE2")) ws->no_fuse2 = std::atoi(env) != 0;
+    if (const char *env = std::getenv("BNK_CHERRY_DIRECT")) ws->no_cherry_direct = std::atoi(env) == 0;
     if (const char *env = std::getenv("BNK_WALKER"))
         ws->walker_mode = std::strcmp(env, "lean") == 0 ? 1 : (std::strcmp(env, "scalar") == 0 ? 2 : (std::strcmp(env, "warp") == 0 ? 3 : (std::strcmp(env, "general") == 0 ? 5 : 0)));
     if (const char *env = std::getenv("BNK_MMA_W")) ws->mw = -std::atoi(env);  // negative: forced
@@ -205,17 +206,24 @@ extern "C" int bnk_ws_create(const bnk_model *m, const bnk_tree *t, int32_t max_
                     std::memset(&f.c[e], 0, sizeof(WideNode));
                     f.c[e].node = -1;
                     const int32_t u = e < v.n_child ? v.c_node[e] : -1;
-                    if (u >= 0 && row_of_node[u] >= 0) { f.c[e] = l1[row_of_node[u]]; taken[row_of_node[u]] = 1; }
+                    f.crow[e] = -1;
+                    if (u >= 0 && row_of_node[u] >= 0) { f.c[e] = l1[row_of_node[u]]; f.crow[e] = row_of_node[u]; taken[row_of_node[u]] = 1; }
                 }
                 f2.push_back(f);
             }
         }
         ws->fuse_off[t->wide_h] = (int32_t)f2.size();
         std::vector<WideNode> rest;  // height-1 nodes under a walked (narrow) parent keep the plain level kernel
-        for (size_t i = 0; i < l1.size(); i++) if (!taken[i]) rest.push_back(l1[i]);
+        std::vector<int32_t> rest_rows, cherry_row(std::max(t->n_int, 1), -1);
+        for (size_t i = 0; i < l1.size(); i++) {
+            if (!taken[i]) { rest.push_back(l1[i]); rest_rows.push_back((int32_t)i); }
+            else cherry_row[l1[i].ent] = (int32_t)i;  // cherry-direct: its message stays in the record tables
+        }
         ws->n_fuse2 = (int)f2.size(); ws->n_wide_rest = (int)rest.size();
         step(upload(ws->d_fuse2, f2, ws->stream));
         step(upload(ws->d_wide_rest, rest, ws->stream));
+        step(upload(ws->d_rest_rows, rest_rows, ws->stream));
+        step(upload(ws->d_cherry_row, cherry_row, ws->stream));
     }
     step(upload(ws->d_parent, t->parent, ws->stream));
     step(upload(ws->d_node_of_ent, t->node_of_ent, ws->stream));
@@ -370,7 +378,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     const size_t per_cat = (size_t)ws->n * K * K * sizeof(double) * 2;
     int cats_per_chunk = (int)std::max<size_t>(1, ws->table_budget / std::max<size_t>(per_cat, 1));
     if (cats_per_chunk > 60000) cats_per_chunk = 60000;
-    ws->chunks.clear(); ws->wtiles.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
+    ws->chunks.clear(); ws->wtiles.clear(); ws->wtile_group.clear(); ws->chunk_wtiles.clear(); ws->chunk_cols.clear();
     ws->cgroups.clear(); ws->chunk_cgroups.clear(); ws->chunk_crecs.clear(); ws->ctiles.clear(); ws->chunk_ctiles.clear();
     ws->xtiles.clear(); ws->chunk_xtiles.clear();
     {   // warp-tiled walker geometry: W consumer warps of 6 x C columns per CTA.  Every CTA of the grid should be
@@ -469,6 +477,12 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
                 crecs += cherry_group_capacity(K, a1 - a0);  // distinct (state, state) pairs of two children
             }
         }
+        // first cherry group (chunk-local index) overlapping every level tile of this chunk
+        ws->wtile_group.resize(ws->wtiles.size(), 0);
+        for (int ti = w0, gi = g0; ti < (int)ws->wtiles.size(); ti++) {
+            while (gi + 1 < (int)ws->cgroups.size() && ws->wtiles[ti].col0 >= ws->cgroups[gi].col0 + ws->cgroups[gi].ncols) gi++;
+            ws->wtile_group[ti] = gi - g0;
+        }
         TileDesc cur{0, 0, 0, 0};
         auto close = [&]() { if (cur.ncols > 0) { ws->tiles.push_back(cur); ck.ncat_max = std::max(ck.ncat_max, cur.ncat); } cur = TileDesc{0, 0, 0, 0}; };
         for (int k = lo; k < hi; k++) {
@@ -514,6 +528,7 @@ extern "C" int bnk_set_rates(bnk_ws *ws, int32_t n_cols, const double *rates)
     TRY(upload(ws->d_cat_of_col, ws->cat_of_col, ws->stream));
     TRY(upload(ws->d_tiles, ws->tiles, ws->stream));
     TRY(upload(ws->d_wtiles, ws->wtiles, ws->stream));
+    TRY(upload(ws->d_wtile_group, ws->wtile_group, ws->stream));
     TRY(upload(ws->d_cgroups, ws->cgroups, ws->stream));
     TRY(upload(ws->d_ctiles, ws->ctiles, ws->stream));
     TRY(upload(ws->d_xtiles, ws->xtiles, ws->stream));
@@ -782,7 +797,7 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
     {   // site-pattern compression of the height-1 level pays when a group holds enough columns to repeat
         const int g0 = ws->chunk_cgroups[ci].first, ng = ws->chunk_cgroups[ci].second - g0;
         const int cols = ws->chunk_cols[ci].second - ws->chunk_cols[ci].first;
-        const int n_h1 = ws->tree->wide_h > 0 ? std::min(65535, ws->level_off[1] - ws->level_off[0]) : 0;
+        const int n_h1 = ws->tree->wide_h > 0 ? ws->level_off[1] - ws->level_off[0] : 0;  // every row of the level: the records outlive the launch (cherry-direct)
         if (!ws->no_cherry && ng > 0 && cols / ng >= 64 && n_h1 > 0 &&
             ws->d_cscratch.ensure((size_t)n_h1 * ws->chunk_crecs[ci] * cherry_record_bytes(ws->K)) == cudaSuccess &&
             ws->d_cslots.ensure((size_t)n_h1 * ws->ncols) == cudaSuccess) {
@@ -791,6 +806,7 @@ static WideArgs wide_args(bnk_ws *ws, size_t ci, const uint8_t *obs_s)
             w.cslots = ws->d_cslots.p;
             w.ctiles = ws->d_ctiles.p + ws->chunk_ctiles[ci].first;
             w.n_ctiles = ws->chunk_ctiles[ci].second - ws->chunk_ctiles[ci].first;
+            w.tile_group = ws->d_wtile_group.p + ws->chunk_wtiles[ci].first;
         }
     }
     w.obs = obs_s;
@@ -841,6 +857,33 @@ static int for_node_slices(bnk_ws *ws, WideArgs &w, int count, F launch)
     return BNK_OK;
 }
 
+// Up-sweep over the wide levels, lowest first.  Cherry-direct (lean kernels, site-pattern compression active, the
+// fused down-sweep available): the height-1 level only builds its record tables; the nodes under a walked parent
+// are expanded into message rows for the walker, everybody else's records are gathered by the parent level
+// (wide_common.cuh) and never reach HBM as rows.
+static bool cherry_direct(const bnk_ws *ws, const WideArgs &w, bool gen, int K)
+{
+    return !gen && K == 20 && w.cgroups != nullptr && ws->tree->wide_h >= 2 && ws->n_fuse2 > 0 && !ws->no_fuse2 &&
+           !ws->no_cherry_direct;
+}
+static int wide_up_levels(bnk_ws *ws, WideArgs &w, int K, int mode, bool gen, int n_wt)
+{
+    auto plain = [&](const WideArgs &wa, int cnt) {
+        return gen ? launch_up_wide_gen(K, mode, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, mode, wa, n_wt, cnt, ws->stream); };
+    w.cherry_row = nullptr; w.rest_rows = nullptr;
+    if (!cherry_direct(ws, w, gen, K)) return for_each_level(ws, true, w, plain);
+    TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) { return launch_cherry_pairs(K, mode, wa, cnt, ws->stream); }, 0, 1));
+    {
+        WideArgs r = w;
+        TRY(for_node_slices(ws, r, ws->n_wide_rest, [&](WideArgs &wa, int off, int cnt) {
+            wa.nodes = ws->d_wide_rest.p + off;
+            wa.rest_rows = ws->d_rest_rows.p + off;
+            return launch_cherry_expand(K, mode, wa, cnt, ws->stream); }));
+    }
+    w.cherry_row = ws->d_cherry_row.p;
+    return for_each_level(ws, true, w, plain, 1);
+}
+
 // --------------------------------------------------------------------------------------
 // joint
 // --------------------------------------------------------------------------------------
@@ -878,8 +921,7 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             if (s.hybrid) {
                 CUDA_TRY(ws->d_msg.ensure((size_t)ws->n_int * nc * K));
                 w.msg = ws->d_msg.p; s.a.msg = ws->d_msg.p;
-                TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
-                    return gen ? launch_up_wide_gen(K, 0, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 0, wa, n_wt, cnt, ws->stream); }));
+                TRY(wide_up_levels(ws, w, K, 0, gen, n_wt));
             }
             if (s.wmask) {
                 CUDA_TRY(launch_walk_case(s.a.up, s.a.n_steps, present_s, ws->d_orig_col.p, nc, ws->d_kind.p, ws->stream));
@@ -902,9 +944,14 @@ extern "C" int bnk_joint_dev(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, c
             CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
             CUDA_TRY(launch_traceback(ta, ws->stream));
             ws->launches++;
-            if (s.hybrid)
+            if (s.hybrid) {
+                const bool direct = w.cherry_row != nullptr;  // the height-1 level reads its pointers from the record tables
                 TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) {
-                    return gen ? launch_traceback_wide_gen(K, wa, cnt, ws->stream) : launch_traceback_wide(K, wa, cnt, ws->stream); }));
+                    return gen ? launch_traceback_wide_gen(K, wa, cnt, ws->stream) : launch_traceback_wide(K, wa, cnt, ws->stream); },
+                    direct ? 1 : 0));
+                if (direct)
+                    TRY(for_each_level(ws, false, w, [&](const WideArgs &wa, int cnt) { return launch_traceback_cherry(K, wa, cnt, ws->stream); }, 0, 1));
+            }
         } else {
             CUDA_TRY(cudaEventRecord(ws->ev[2][0], ws->stream));
         }
@@ -1052,8 +1099,7 @@ int bnk::ws_run_sum(bnk_ws *ws, int32_t n_cols, const uint8_t *d_obs, const uint
                     s.a.logl_wide = ws->d_logl_wide.p;
                 }
             }
-            TRY(for_each_level(ws, true, w, [&](const WideArgs &wa, int cnt) {
-                return gen ? launch_up_wide_gen(K, 1, wa, n_wt, cnt, ws->stream) : launch_up_wide(K, 1, wa, n_wt, cnt, ws->stream); }));
+            TRY(wide_up_levels(ws, w, K, 1, gen, n_wt));
             if (logl) {
                 CUDA_TRY(launch_sum_escale(ws->d_escale.p, t->n_wide, nc, ws->d_esum_wide.p, ws->stream));
                 ws->launches++;

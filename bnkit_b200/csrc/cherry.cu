@@ -14,37 +14,6 @@
 
 namespace bnk {
 
-// pairs a group of ncols columns can hold: distinct (state, state) codes of two children, a multiple of 4
-__host__ __device__ inline int cherry_cap(int K, int ncols)
-{
-    const int c = (K + 1) * (K + 1) < ncols ? (K + 1) * (K + 1) : ncols;
-    return (c + 3) & ~3;
-}
-
-constexpr int CG = 2048;  // columns per cherry group (api.cu builds groups of one category, <= CG columns)
-
-// Result table of one (node y, group x) in a global scratch area (L2-resident between the two kernels), state-major
-// so that the expansion's gathers of one state row fall into few cache lines: K x cap message values, K x cap
-// traceback pointers, cap rescale exponents, where cap = the group's capacity in pairs (a multiple of 4).  The
-// table starts at byte ((y * recs_per_node + group.ncat) * REC_BYTES) -- api.cu stores the group's record offset
-// in TileDesc::ncat and sizes it with cherry_group_capacity().
-template <int K>
-struct CherryTable {
-    static constexpr int REC_BYTES = ((K * 9 + 4 + 15) / 16) * 16;
-    double *v;
-    uint8_t *ptr;
-    int32_t *e;
-    int cap;
-    __device__ __forceinline__ CherryTable(uint8_t *scratch, size_t node_row, int recs_per_node, const TileDesc &g)
-    {
-        cap = cherry_cap(K, g.ncols);
-        uint8_t *base = scratch + ((size_t)node_row * recs_per_node + g.ncat) * REC_BYTES;
-        v = reinterpret_cast<double *>(base);
-        ptr = base + (size_t)K * cap * 8;
-        e = reinterpret_cast<int32_t *>(base + (size_t)K * cap * 9);
-    }
-};
-
 template <int K, int MODE>
 __global__ void __launch_bounds__(WT, 5) cherry_pairs_kernel(const WideArgs a)
 {
@@ -53,7 +22,7 @@ __global__ void __launch_bounds__(WT, 5) cherry_pairs_kernel(const WideArgs a)
     constexpr int CPT = (NCODE + WT - 1) / WT;  // codes per thread during compaction
     __shared__ __align__(16) double Ls[K * K];
     __shared__ double LT0[K * (K + 1)], LT1[K * (K + 1)];
-    __shared__ int16_t slot[NCODE], list[NCODE], ccode[CG];
+    __shared__ int16_t slot[NCODE], list[NCODE], ccode[CG], pexp[NCODE];
     __shared__ int wsum[WT / 32];
 
     const int tid = threadIdx.x;
@@ -61,7 +30,8 @@ __global__ void __launch_bounds__(WT, 5) cherry_pairs_kernel(const WideArgs a)
     const TileDesc g = a.cgroups[blockIdx.x];
     const size_t tb = (size_t)g.cat0 * a.n_nodes;
     const bool two = w.n_child > 1;
-    const CherryTable<K> tab(a.cscratch, blockIdx.y, a.crecs_per_node, g);
+    const size_t row = (size_t)a.wide_row0 + blockIdx.y;  // the node's row in the height-1 level (the level starts the wide list)
+    const CherryTable<K> tab(a.cscratch, row, a.crecs_per_node, g);
     load_table<K>(Ls, a.T_row + (tb + w.node) * (K * K), 0);
     load_table<K>(LT0, a.T_col + (tb + w.c_node[0]) * (K * K), 1);
     if (two) load_table<K>(LT1, a.T_col + (tb + w.c_node[1]) * (K * K), 1);
@@ -183,11 +153,18 @@ __global__ void __launch_bounds__(WT, 5) cherry_pairs_kernel(const WideArgs a)
                 tab.v[p * tab.cap + j] = acc0 + acc1;
             }
             tab.e[j] = e;
+            pexp[j] = (int16_t)e;
         }
     }
-    // the record index of every column, for the expansion kernel
-    int16_t *rank_g = a.cslots + (size_t)blockIdx.y * a.ncols + g.col0;
+    // the record index of every column (for whoever reads the records: the expansion kernel, or the parent level
+    // directly) and, summing into the log-likelihood later, the column's rescale exponent
+    int16_t *rank_g = a.cslots + row * a.ncols + g.col0;
     for (int i = tid; i < g.ncols; i += WT) rank_g[i] = slot[ccode[i]];
+    if (MODE == 1 && a.escale) {
+        __syncthreads();
+        int16_t *es = a.escale + row * a.ncols + g.col0;
+        for (int i = tid; i < g.ncols; i += WT) es[i] = pexp[slot[ccode[i]]];
+    }
 }
 
 // Expansion: one (node, column) per thread, the same warp-row store pattern as the level kernels.  Each thread
@@ -203,18 +180,17 @@ __global__ void __launch_bounds__(WT, 8) cherry_expand_kernel(const WideArgs a)
     const int c = t.col0 + threadIdx.x;
     if (c < g.col0 || c >= g.col0 + g.ncols) return;
     const WideNode w = a.nodes[blockIdx.y];
-    const CherryTable<K> tab(a.cscratch, blockIdx.y, a.crecs_per_node, g);
-    const int r = a.cslots[(size_t)blockIdx.y * a.ncols + c];
+    // a.rest_rows: the expansion runs on a subset of the level (nodes under a walked parent), rows given explicitly
+    const size_t row = a.rest_rows ? (size_t)a.rest_rows[blockIdx.y] : (size_t)a.wide_row0 + blockIdx.y;
+    const CherryTable<K> tab(a.cscratch, row, a.crecs_per_node, g);
+    const int r = a.cslots[row * a.ncols + c];
     double v[K];
 #pragma unroll
     for (int p = 0; p < K; p++) v[p] = __ldg(tab.v + p * tab.cap + r);
     uint8_t pk[MODE == 0 ? K : 1];
-    int e = 0;
     if (MODE == 0) {
 #pragma unroll
         for (int p = 0; p < K; p++) pk[p] = __ldg(tab.ptr + p * tab.cap + r);
-    } else {
-        e = __ldg(tab.e + r);
     }
     double *m = a.msg + (size_t)w.ent * K * a.ncols + c;
 #pragma unroll
@@ -224,20 +200,64 @@ __global__ void __launch_bounds__(WT, 8) cherry_expand_kernel(const WideArgs a)
 #pragma unroll
         for (int p = 0; p < K; p++) pp[(size_t)p * a.ncols] = pk[p];
     }
-    if (MODE == 1 && a.escale) a.escale[(size_t)(a.wide_row0 + blockIdx.y) * a.ncols + c] = (int16_t)e;
 }
 
 size_t cherry_record_bytes(int K) { return K == 20 ? CherryTable<20>::REC_BYTES : CherryTable<4>::REC_BYTES; }
 int cherry_group_capacity(int K, int ncols) { return cherry_cap(K, ncols); }
 
-cudaError_t launch_up_cherry(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st)
+// the two halves separately: cherry-direct runs the pairs kernel on the whole level and expands only the nodes
+// under a walked parent (a.nodes = that list, a.rest_rows = their rows in the level)
+cudaError_t launch_cherry_pairs(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st)
 {
     if (n_nodes == 0 || a.n_cgroups == 0) return cudaSuccess;
-    dim3 grid(a.n_cgroups, n_nodes), grid2(a.n_ctiles, n_nodes);
-    if (K == 20 && mode == 0) { cherry_pairs_kernel<20, 0><<<grid, WT, 0, st>>>(a); cherry_expand_kernel<20, 0><<<grid2, WT, 0, st>>>(a); }
-    else if (K == 20) { cherry_pairs_kernel<20, 1><<<grid, WT, 0, st>>>(a); cherry_expand_kernel<20, 1><<<grid2, WT, 0, st>>>(a); }
-    else if (mode == 0) { cherry_pairs_kernel<4, 0><<<grid, WT, 0, st>>>(a); cherry_expand_kernel<4, 0><<<grid2, WT, 0, st>>>(a); }
-    else { cherry_pairs_kernel<4, 1><<<grid, WT, 0, st>>>(a); cherry_expand_kernel<4, 1><<<grid2, WT, 0, st>>>(a); }
+    dim3 grid(a.n_cgroups, n_nodes);
+    if (K == 20 && mode == 0) cherry_pairs_kernel<20, 0><<<grid, WT, 0, st>>>(a);
+    else if (K == 20) cherry_pairs_kernel<20, 1><<<grid, WT, 0, st>>>(a);
+    else if (mode == 0) cherry_pairs_kernel<4, 0><<<grid, WT, 0, st>>>(a);
+    else cherry_pairs_kernel<4, 1><<<grid, WT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_cherry_expand(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st)
+{
+    if (n_nodes == 0 || a.n_cgroups == 0) return cudaSuccess;
+    dim3 grid2(a.n_ctiles, n_nodes);
+    if (K == 20 && mode == 0) cherry_expand_kernel<20, 0><<<grid2, WT, 0, st>>>(a);
+    else if (K == 20) cherry_expand_kernel<20, 1><<<grid2, WT, 0, st>>>(a);
+    else if (mode == 0) cherry_expand_kernel<4, 0><<<grid2, WT, 0, st>>>(a);
+    else cherry_expand_kernel<4, 1><<<grid2, WT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_up_cherry(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st)
+{
+    cudaError_t e = launch_cherry_pairs(K, mode, a, n_nodes, st);
+    if (e != cudaSuccess) return e;
+    return launch_cherry_expand(K, mode, a, n_nodes, st);
+}
+
+// Traceback of the height-1 level straight from the record tables (cherry-direct): state = ptr record of the
+// column's pair, entry state(parent).  One (node, column) per thread; the group of a column by a scan of the
+// (few) groups.
+template <int K>
+__global__ void __launch_bounds__(256) traceback_cherry_kernel(const WideArgs a)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < a.col_lo || col >= a.col_hi) return;
+    const WideNode w = a.nodes[blockIdx.y];
+    const size_t row = (size_t)a.wide_row0 + blockIdx.y;
+    int gi = 0;
+    while (gi + 1 < a.n_cgroups && col >= a.cgroups[gi].col0 + a.cgroups[gi].ncols) gi++;
+    const TileDesc g = a.cgroups[gi];
+    const CherryTable<K> tab(a.cscratch, row, a.crecs_per_node, g);
+    const int r = a.cslots[row * a.ncols + col];
+    const int sp = a.state_s[(size_t)w.parent * a.ncols + col];
+    a.state_s[(size_t)w.node * a.ncols + col] = tab.ptr[(size_t)sp * tab.cap + r];
+}
+cudaError_t launch_traceback_cherry(int K, const WideArgs &a, int n_nodes, cudaStream_t st)
+{
+    if (n_nodes == 0) return cudaSuccess;
+    dim3 grid((a.ncols + 255) / 256, n_nodes);
+    if (K == 20) traceback_cherry_kernel<20><<<grid, 256, 0, st>>>(a);
+    else traceback_cherry_kernel<4><<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -77,6 +77,7 @@ struct WalkArgs {
 struct Wide2Node {
     WideNode v;
     WideNode c[2];
+    int32_t crow[2];  // row of c[e] in the height-1 level (cherry-direct: its message lives in the record tables)
 };
 
 // arguments of the level kernels (wide.cu); all column indices are in sorted space
@@ -111,6 +112,10 @@ struct WideArgs {
     uint8_t *kind, *kindm;   // [ent][ncols] node kinds (joint / sum)
     double *logl_acc;        // [ncols] += log of component-root totals and scalar factors (atomic)
     const Wide2Node *fuse2;  // down_wide2_kernel: the height-2 level (or a slice of it) with its fused children
+    // cherry-direct (wide_common.cuh): nullptr = every height-1 message was expanded into a.msg
+    const int32_t *cherry_row;  // [n_int] ent -> row in the height-1 level of a node whose message stays in the record tables, else -1
+    const int32_t *tile_group;  // [n_tiles] first cherry group overlapping a.tiles[i]
+    const int32_t *rest_rows;   // cherry_expand_kernel on a subset: row in the height-1 level of a.nodes[i]
 };
 cudaError_t launch_down_wide2(int K, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
 cudaError_t launch_up_wide_gen(int K, int mode, const WideArgs &a, int n_tiles, int n_nodes, cudaStream_t st);
@@ -124,6 +129,9 @@ cudaError_t launch_scatter_rows(const uint8_t *in, uint8_t *out, const int32_t *
                                 const int32_t *orig_col, int ncols, cudaStream_t st);
 int wide_tile_cols();
 cudaError_t launch_up_cherry(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st);
+cudaError_t launch_cherry_pairs(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st);
+cudaError_t launch_cherry_expand(int K, int mode, const WideArgs &a, int n_nodes, cudaStream_t st);
+cudaError_t launch_traceback_cherry(int K, const WideArgs &a, int n_nodes, cudaStream_t st);
 int cherry_group_cols();
 size_t cherry_record_bytes(int K);
 int cherry_group_capacity(int K, int ncols);

@@ -22,10 +22,13 @@ namespace bnk {
 // message of child e of node w for this thread's column, all K states.  MODE 0: log space, 1: linear.
 template <int K, int MODE>
 __device__ __forceinline__ void child_vector(const WideArgs &a, const WideNode &w, int e, size_t tb, int col, bool valid,
-                                             const double *lt_smem, double (&g)[K])
+                                             const double *lt_smem, double (&g)[K], int tile_index = 0)
 {
     const int cn = w.c_node[e];
-    if (w.c_ent[e] >= 0) {  // internal child: its message row-block in HBM
+    const int crow = (w.c_ent[e] >= 0 && a.cherry_row) ? a.cherry_row[w.c_ent[e]] : -1;
+    if (crow >= 0) {  // a height-1 child whose message was never expanded: gather its record (cherry-direct)
+        cherry_gather<K>(a, crow, tile_index, col, g);
+    } else if (w.c_ent[e] >= 0) {  // internal child: its message row-block in HBM
         const double *m = a.msg + (size_t)w.c_ent[e] * K * a.ncols + col;
 #pragma unroll
         for (int x = 0; x < K; x++) g[x] = m[(size_t)x * a.ncols];
@@ -68,9 +71,9 @@ __global__ void __launch_bounds__(WT, 5) up_wide_kernel(const WideArgs a)
         const int col = tile.col0 + (valid ? (int)threadIdx.x : tile.ncols - 1);
 
         double G[K], g[K];
-        child_vector<K, MODE>(a, w, 0, tb, col, valid, LT0, G);
+        child_vector<K, MODE>(a, w, 0, tb, col, valid, LT0, G, ti);
         if (w.n_child > 1) {
-            child_vector<K, MODE>(a, w, 1, tb, col, valid, LT1, g);
+            child_vector<K, MODE>(a, w, 1, tb, col, valid, LT1, g, ti);
 #pragma unroll
             for (int x = 0; x < K; x++) G[x] = (MODE == 0) ? G[x] + g[x] : G[x] * g[x];
         }
@@ -339,10 +342,15 @@ __global__ void __launch_bounds__(WT, 3) down_wide2_kernel(const WideArgs a)
             D[x] = acc0 + acc1;
         }
         double c0[K], c1[K];
+        if (ch0 && a.cherry_row) cherry_gather<K>(a, w2.crow[0], ti, col, c0);  // cherry-direct: the record, not an HBM row
+        else {
 #pragma unroll
-        for (int x = 0; x < K; x++) {
-            c0[x] = leaf0 ? LTv[0][o0 * LS + x] : __ldg(m0 + (size_t)x * a.ncols);
-            c1[x] = !two ? 1.0 : (leaf1 ? LTv[1][o1 * LS + x] : __ldg(m1 + (size_t)x * a.ncols));
+            for (int x = 0; x < K; x++) c0[x] = leaf0 ? LTv[0][o0 * LS + x] : __ldg(m0 + (size_t)x * a.ncols);
+        }
+        if (ch1 && a.cherry_row) cherry_gather<K>(a, w2.crow[1], ti, col, c1);
+        else {
+#pragma unroll
+            for (int x = 0; x < K; x++) c1[x] = !two ? 1.0 : (leaf1 ? LTv[1][o1 * LS + x] : __ldg(m1 + (size_t)x * a.ncols));
         }
         // posterior of v
         {

@@ -41,6 +41,63 @@ __device__ __forceinline__ double w_rcp(double s)
     return r;
 }
 
+// pairs a group of ncols columns can hold: distinct (state, state) codes of two children, a multiple of 4
+__host__ __device__ inline int cherry_cap(int K, int ncols)
+{
+    const int c = (K + 1) * (K + 1) < ncols ? (K + 1) * (K + 1) : ncols;
+    return (c + 3) & ~3;
+}
+
+constexpr int CG = 2048;  // columns per cherry group (api.cu builds groups of one category, <= CG columns)
+
+// Result table of one (node y, group x) in a global scratch area (L2-resident between the two kernels), state-major
+// so that the expansion's gathers of one state row fall into few cache lines: K x cap message values, K x cap
+// traceback pointers, cap rescale exponents, where cap = the group's capacity in pairs (a multiple of 4).  The
+// table starts at byte ((y * recs_per_node + group.ncat) * REC_BYTES) -- api.cu stores the group's record offset
+// in TileDesc::ncat and sizes it with cherry_group_capacity().
+template <int K>
+struct CherryTable {
+    static constexpr int REC_BYTES = ((K * 9 + 4 + 15) / 16) * 16;
+    double *v;
+    uint8_t *ptr;
+    int32_t *e;
+    int cap;
+    __device__ __forceinline__ CherryTable(uint8_t *scratch, size_t node_row, int recs_per_node, const TileDesc &g)
+    {
+        cap = cherry_cap(K, g.ncols);
+        uint8_t *base = scratch + ((size_t)node_row * recs_per_node + g.ncat) * REC_BYTES;
+        v = reinterpret_cast<double *>(base);
+        ptr = base + (size_t)K * cap * 8;
+        e = reinterpret_cast<int32_t *>(base + (size_t)K * cap * 9);
+    }
+};
+
+// "Cherry-direct" (r2): a height-1 node under a level-scheduled parent never has its message rows written out at all.
+// Its consumers -- the parent's up-sweep thread, the parent's fused down-sweep thread, the traceback -- read the
+// column's record index (a.cslots) and gather the record from the (node, group) table the pairs kernel left in the
+// scratch area: 20 loads of 8 bytes out of a few KB that stay in L1 / L2 while a CTA walks the tiles of one group,
+// instead of 160 bytes per (node, column) written to HBM by an expansion kernel and read back twice.
+// The group of a column: a.tile_group[tile] names the first group overlapping the tile; a tile straddles at most
+// one group boundary (groups of a split category hold >= 1,024 columns).
+__device__ __forceinline__ TileDesc cherry_group_of(const WideArgs &a, int tile_index, int col)
+{
+    int gi = a.tile_group[tile_index];
+    TileDesc g = a.cgroups[gi];
+    if (col >= g.col0 + g.ncols) g = a.cgroups[gi + 1];
+    return g;
+}
+// message of the height-1 node in row y of its level for column col, all K states (MODE as in the level kernels)
+template <int K>
+__device__ __forceinline__ void cherry_gather(const WideArgs &a, int y, int tile_index, int col, double (&g)[K])
+{
+    const TileDesc grp = cherry_group_of(a, tile_index, col);
+    const CherryTable<K> tab(a.cscratch, (size_t)y, a.crecs_per_node, grp);
+    const int r = a.cslots[(size_t)y * a.ncols + col];
+    const double *v = tab.v + r;
+#pragma unroll
+    for (int x = 0; x < K; x++) g[x] = __ldg(v + (size_t)x * tab.cap);
+}
+
 // One posterior row (K doubles of one (query, column), contiguous) leaves as K / 4 256-bit streaming stores
 // (STG.256, sm_100): a thread then writes whole 32-byte sectors.  With 128-bit stores every sector was written
 // by two instructions, i.e. twice the L2 write requests for the same bytes -- and the level kernels sit closer

@@ -119,6 +119,9 @@ struct bnk_ws {
     DevBuf<Wide2Node> d_fuse2{&reg};
     DevBuf<WideNode> d_wide_rest{&reg};
     int n_fuse2 = 0, n_wide_rest = 0;
+    DevBuf<int32_t> d_rest_rows{&reg}, d_cherry_row{&reg}, d_wtile_group{&reg};  // cherry-direct (wide_common.cuh)
+    std::vector<int32_t> wtile_group;
+    bool no_cherry_direct = false;                            // BNK_CHERRY_DIRECT=0 (A/B, tests)
     std::vector<int32_t> fuse_off;                            // [wide_h + 1] into d_fuse2, per height level (index 1 = height 2)
     bool no_fuse2 = false;                                    // BNK_NO_FUSE2=1 (A/B, tests)
     std::vector<int32_t> level_off;                           // [wide_h + 1] into d_wide

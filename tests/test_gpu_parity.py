@@ -307,8 +307,11 @@ def test_cherry_pattern_compression(bnk, oracle, monkeypatch):
         want = oracle.fast_joint(om, parent, dist, np.ascontiguousarray(obs[:, sub]), None, rates[sub], nthreads=8)
         wpost, wlogl = oracle.fast_marginal(om, parent, dist, np.ascontiguousarray(obs[:, sub]), None, rates[sub], nthreads=8)
         res = []
-        for no_cherry in ("0", "1"):
+        # compression with the records read in place by the parent level ("cherry-direct", the default), compression
+        # with every message row expanded, no compression
+        for no_cherry, direct in (("0", "1"), ("0", "0"), ("1", "1")):
             monkeypatch.setenv("BNK_NO_CHERRY", no_cherry)
+            monkeypatch.setenv("BNK_CHERRY_DIRECT", direct)
             ws = bnk.Workspace(m, tree, n_cols)
             ws.set_rates(n_cols, rates)
             st = ws.joint(obs, None)
@@ -318,9 +321,10 @@ def test_cherry_pattern_compression(bnk, oracle, monkeypatch):
             _post_close(post[:, sub], wpost[tree.internal_nodes()])
             assert np.allclose(logl[sub], wlogl, rtol=TOL, atol=1e-9)
             res.append((st, post, logl))
-        assert np.array_equal(res[0][0], res[1][0])
-        assert np.array_equal(res[0][1], res[1][1], equal_nan=True)
-        assert np.array_equal(res[0][2], res[1][2])
+        for other in res[1:]:
+            assert np.array_equal(res[0][0], other[0])
+            assert np.array_equal(res[0][1], other[1], equal_nan=True)
+            assert np.array_equal(res[0][2], other[2])
 
 
 def test_fused_height2_down_sweep(bnk, oracle, monkeypatch):
