@@ -33,6 +33,12 @@ sys.path.insert(0, ROOT)
 
 # algorithmic bytes per update, SURVEY.md section 8(d) (store-all-partials schedule, FP64, K = 20)
 BYTES_PER_UPDATE = {"joint_up+traceback": 361.0, "sum_up": 337.0, "sum_down": 832.0}
+# Bytes the r2 kernels no longer move for a height-1 node under a level-scheduled parent ("cherry-direct" + the fused
+# down-sweep), per (node, column): its message row is neither written by an expansion kernel nor
+# read by the parent (2 x 160 B; joint: + 2 x 20 B of pointer rows; the 2-byte record index is written once and read
+# by the parent / the traceback instead), its from-above vector is neither written nor read (2 x 160 B) and the
+# parent's down-sweep does not read its message (160 B).  The algorithmic bytes of the sweeps are restated by these.
+BYTES_SAVED_PER_DIRECT = {"joint_up+traceback": 336.0, "sum_up": 316.0, "sum_down": 480.0}
 TABLE_BYTES = 3200.0  # per (branch, category) per sweep
 
 WORKLOADS = {
@@ -560,12 +566,11 @@ def main():
     # The algorithmic bytes of the down-sweep are restated accordingly; the survey's own
     # figure stays in the line as `survey_GB`.
     fused = fused_height1_nodes(parent) if present is None else 0
-    down_bytes = BYTES_PER_UPDATE["sum_down"] * upd - 320.0 * fused * sh.ncols + tbl
-    survey = {"joint_up+traceback": BYTES_PER_UPDATE["joint_up+traceback"] * upd + tbl,
-              "sum_up": BYTES_PER_UPDATE["sum_up"] * upd + tbl, "sum_down": BYTES_PER_UPDATE["sum_down"] * upd + tbl}
-    kern = {"joint_up+traceback": (phase_ms[1] + phase_ms[2], survey["joint_up+traceback"]),
-            "sum_up": (phase_ms[3], survey["sum_up"]),
-            "sum_down": (phase_ms[4], down_bytes)}
+    survey = {k: BYTES_PER_UPDATE[k] * upd + tbl for k in BYTES_PER_UPDATE}
+    restated = {k: survey[k] - BYTES_SAVED_PER_DIRECT[k] * fused * sh.ncols for k in survey}
+    kern = {"joint_up+traceback": (phase_ms[1] + phase_ms[2], restated["joint_up+traceback"]),
+            "sum_up": (phase_ms[3], restated["sum_up"]),
+            "sum_down": (phase_ms[4], restated["sum_down"])}
     dom = max(kern, key=lambda k: kern[k][0])
     per_kernel = {k: {"ms": round(v[0], 4), "algorithmic_GB": round(v[1] / 1e9, 3), "survey_GB": round(survey[k] / 1e9, 3),
                       "achieved_GBps": round(v[1] / 1e9 / (v[0] * 1e-3), 1) if v[0] > 0 else None,
@@ -601,8 +606,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "traffic_note": "DRAM bytes per step of the dominant sweep (all its launches): " + str(traffic_src),
-                         "algorithmic_bytes": "SURVEY.md 8(d) per-update figures x %d updates + table bytes; sum_down restated: minus "
-                                              "320 B x %d fused height-1 nodes x columns (their from-above vectors never reach HBM)" % (int(upd), fused),
+                         "algorithmic_bytes": "SURVEY.md 8(d) per-update figures x %d updates + table bytes (`survey_GB`), restated for what "
+                                              "the r2 kernels no longer move: minus %s B per (node, column) of the %d height-1 nodes under "
+                                              "level-scheduled parents (message rows never expanded, from-above vectors never stored)"
+                                              % (int(upd), json.dumps(BYTES_SAVED_PER_DIRECT), fused),
                          "per_kernel": per_kernel},
             "clocks": clocks}
     if parity is not None:
@@ -655,7 +662,7 @@ def main():
             u = 3.0 * ni * sspec["cols"]
             ph /= sub_steps
             tb = TABLE_BYTES * (s2.n - 1) * sspec["ncat"]
-            algo = sum(BYTES_PER_UPDATE.values()) * ni * s2.ncols + 3 * tb - 320.0 * fused_height1_nodes(sp) * s2.ncols
+            algo = sum(BYTES_PER_UPDATE.values()) * ni * s2.ncols + 3 * tb - sum(BYTES_SAVED_PER_DIRECT.values()) * fused_height1_nodes(sp) * s2.ncols
             algo_all = algo   # rank 0's block in ms (max over ranks): the same quantity per rank
             subs[name] = {"workload": sspec["name"], "cols_per_gpu": s2.ncols, "steps": sub_steps, "warmup": sub_warm,
                           "ms_per_step": ms / sub_steps, "updates_per_s": u / (ms / sub_steps * 1e-3),
