@@ -1290,6 +1290,22 @@ extern "C" int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, cons
     return BNK_OK;
 }
 
+// Joint + marginal with host buffers, one call: column chunks through the two sub-workspaces as in bnk_marginal, each
+// chunk running its joint pass too -- the whole joint reconstruction hides under the marginal's result copies (PCIe).
+extern "C" int bnk_joint_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present, uint8_t *out_state,
+                                  const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl)
+{
+    if (!ws || !obs || !out_state) return fail(BNK_ERR_ARG, "joint_marginal: null argument");
+    ENTER_DEVICE(ws->device);
+    TRY(ensure_rates(ws, n_cols));
+    if (ws_wants_pipeline(ws, n_cols)) {
+        HostCall hc{3, n_cols, 0, n_cols, obs, present, ws->rates_null ? nullptr : ws->last_rates.data(), out_state, query_nodes, n_query, out_post, out_logl, nullptr};
+        return ws_run_host_range(ws, hc);
+    }
+    TRY(bnk_joint(ws, n_cols, obs, present, out_state));
+    return bnk_marginal(ws, n_cols, obs, present, query_nodes, n_query, out_post, out_logl);
+}
+
 extern "C" int bnk_loglik(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present, double *out_logl, double *out_sum)
 {
     if (!ws || !obs) return fail(BNK_ERR_ARG, "loglik: null argument");

@@ -109,14 +109,20 @@ int ws_run_host_range(bnk_ws *ws, const HostCall &hc)
                 CUDA_TRY(cudaStreamWaitEvent(ws->copy_stream, ws->chunk_done[j & 1], 0));
                 CUDA_TRY(cudaMemcpy2DAsync(hc.out_state + c0, stride, w->d_state.p, nc, nc, n, cudaMemcpyDeviceToHost, ws->copy_stream));
                 CUDA_TRY(cudaEventRecord(ws->copy_done[j & 1], ws->copy_stream));
-            } else if (hc.op == 1) {
+            } else if (hc.op == 1 || hc.op == 3) {
                 const bool want_post = hc.out_post && nq > 0;
                 if (want_post) CUDA_TRY(w->d_post.ensure((size_t)nq * nc * K));
                 if (hc.out_logl) CUDA_TRY(w->d_logl.ensure(nc));
+                if (hc.op == 3) {  // joint + marginal of the chunk: the joint pass hides under the previous chunk's result copy
+                    CUDA_TRY(w->d_state.ensure(bytes));
+                    TRY(bnk_joint_dev(w, nc, w->d_obs_in.p, d_present, w->d_state.p));
+                }
                 TRY(ws_run_sum(w, nc, w->d_obs_in.p, d_present, hc.query_nodes, hc.n_query, want_post ? w->d_post.p : nullptr,
                                hc.out_logl ? w->d_logl.p : nullptr, nullptr));
                 CUDA_TRY(cudaEventRecord(ws->chunk_done[j & 1], w->stream));
                 CUDA_TRY(cudaStreamWaitEvent(ws->copy_stream, ws->chunk_done[j & 1], 0));
+                if (hc.op == 3)
+                    CUDA_TRY(cudaMemcpy2DAsync(hc.out_state + c0, stride, w->d_state.p, nc, nc, n, cudaMemcpyDeviceToHost, ws->copy_stream));
                 if (want_post)
                     CUDA_TRY(cudaMemcpy2DAsync(hc.out_post + (size_t)c0 * K, stride * K * sizeof(double), w->d_post.p,
                                                (size_t)nc * K * sizeof(double), (size_t)nc * K * sizeof(double), nq,

@@ -34,7 +34,7 @@ SYMBOLS = [
     "bnk_ws_create", "bnk_ws_destroy", "bnk_ws_sync", "bnk_ws_dims", "bnk_ws_configure", "bnk_ws_launch_count",
     "bnk_ws_device_bytes", "bnk_set_rates", "bnk_set_distances", "bnk_probs",
     "bnk_joint", "bnk_marginal", "bnk_loglik", "bnk_joint_dev", "bnk_marginal_dev", "bnk_loglik_dev",
-    "bnk_joint_marginal_dev",
+    "bnk_joint_marginal_dev", "bnk_joint_marginal",
     "bnk_ws_phase_ms", "bnk_bep_presence",
     "bnk_ws_set_evidence_mode", "bnk_ws_set_pipeline",
     "bnk_bep_infer", "bnk_pogs_n_edges", "bnk_pogs_edges", "bnk_pogs_destroy",
@@ -92,6 +92,7 @@ def lib():
     L.bnk_marginal_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _ip, C.c_int32, _vp, _vp]
     L.bnk_loglik_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
     L.bnk_joint_marginal_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _ip, C.c_int32, _vp, _vp]
+    L.bnk_joint_marginal.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _ip, C.c_int32, _vp, _vp]
     L.bnk_ws_phase_ms.argtypes = [_vp, C.c_int, C.POINTER(C.c_float)]
     L.bnk_bep_presence.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip]
     L.bnk_bep_infer.argtypes = [_vp, C.c_int32, _bp, C.c_int, _bp, _ip, C.POINTER(_vp)]
@@ -366,6 +367,24 @@ class Workspace:
         logl = np.empty(n_cols) if want_logl else None
         check(lib().bnk_marginal(self.h, n_cols, _ptr(obs), _ptr(present), _i(q), nq, _ptr(out), _ptr(logl)))
         return out, logl
+
+    def joint_marginal(self, obs, present=None, query=None, want_logl=True):
+        """joint() and marginal() of the same alignment in one call: (states, posteriors, logl)"""
+        obs = _as_u8(obs)
+        n_cols = obs.shape[1]
+        present = None if present is None else _as_u8(present)
+        if query is None:
+            nq, q = -1, None
+            rows = self.tree.n_internal
+        else:
+            q = np.ascontiguousarray(query, dtype=np.int32)
+            nq = rows = len(q)
+        self._check_shapes(obs, present)
+        states = np.empty((self.n, n_cols), dtype=np.uint8)
+        post = np.empty((rows, n_cols, self.K))
+        logl = np.empty(n_cols) if want_logl else None
+        check(lib().bnk_joint_marginal(self.h, n_cols, _ptr(obs), _ptr(present), _ptr(states), _i(q), nq, _ptr(post), _ptr(logl)))
+        return states, post, logl
 
     def loglik(self, obs, present=None):
         obs = _as_u8(obs)

@@ -175,6 +175,11 @@ int bnk_joint(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *pre
  * unconnected); out_logl [n_cols] = VarElim.logLikelihood() of the column; either may be NULL. */
 int bnk_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
                  const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl);
+/* bnk_joint and bnk_marginal of the same alignment in one call (Prediction.getJoint + getMarginal,
+ * src/asr/Prediction.java:555-649): same results; the joint pass of every column chunk runs while the previous
+ * chunk's posteriors cross PCIe, so the call costs what bnk_marginal alone costs. */
+int bnk_joint_marginal(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null, uint8_t *out_state,
+                       const int32_t *query_nodes, int32_t n_query, double *out_post, double *out_logl);
 /* out_logl [n_cols] (may be NULL), *out_sum = sum over columns (may be NULL) */
 int bnk_loglik(bnk_ws *ws, int32_t n_cols, const uint8_t *obs, const uint8_t *present_or_null,
                double *out_logl, double *out_sum);

@@ -40,6 +40,9 @@ public final class NativeInference {
     /** queryNodes == null: every ancestor in index order. outPost: direct buffer of n_query * n_cols * K doubles. */
     static native void marginal(long ws, int nCols, ByteBuffer obs, ByteBuffer presentOrNull, int[] queryNodesOrNull,
                                 DoubleBuffer outPostOrNull, double[] outLoglOrNull);
+    /** joint + marginal of the same alignment in one call: the joint pass hides under the posteriors' way back over PCIe. */
+    static native void jointMarginal(long ws, int nCols, ByteBuffer obs, ByteBuffer presentOrNull, ByteBuffer outState,
+                                     int[] queryNodesOrNull, DoubleBuffer outPostOrNull, double[] outLoglOrNull);
     /** returns the sum over columns; outLogl may be null. */
     static native double logLik(long ws, int nCols, ByteBuffer obs, ByteBuffer presentOrNull, double[] outLoglOrNull);
     /** occupancy != 255 where an extant has a residue; present receives the BEP mask (extants pass through). */

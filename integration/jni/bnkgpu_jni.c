@@ -176,6 +176,35 @@ JNIEXPORT void JNICALL Java_asr_NativeInference_marginal(JNIEnv *env, jclass c, 
     if (rc != BNK_OK) raise(env, rc);
 }
 
+/* joint + marginal of the same alignment in one call (bnk_joint_marginal): the joint pass hides under the result copies */
+JNIEXPORT void JNICALL Java_asr_NativeInference_jointMarginal(JNIEnv *env, jclass c, jlong ws, jint nCols, jobject obs, jobject present,
+                                                              jobject outState, jintArray query, jobject outPost, jdoubleArray outLogl)
+{
+    (void)c;
+    int32_t n, ni, K;
+    int bad = 0, rc;
+    if (dims(env, ws, &n, &ni, &K) != BNK_OK) return;
+    const jint nq = query ? (*env)->GetArrayLength(env, query) : -1;
+    const uint8_t *o = (const uint8_t *)buf(env, obs, (jlong)n * nCols, &bad);
+    const uint8_t *p = (const uint8_t *)buf(env, present, (jlong)n * nCols, &bad);
+    uint8_t *st = (uint8_t *)buf(env, outState, (jlong)n * nCols, &bad);
+    double *post = (double *)buf(env, outPost, (jlong)(nq < 0 ? ni : nq) * nCols * K, &bad);
+    if (bad) return;
+    if (!st) { throw_arg(env, "bnkgpu: outState is null"); return; }
+    if (outLogl && (*env)->GetArrayLength(env, outLogl) < nCols) { throw_arg(env, "bnkgpu: outLogl shorter than nCols"); return; }
+    jint *q = query ? (*env)->GetIntArrayElements(env, query, NULL) : NULL;
+    jdouble *ll = outLogl ? (*env)->GetDoubleArrayElements(env, outLogl, NULL) : NULL;
+    if ((query && !q) || (outLogl && !ll)) {   /* OutOfMemoryError is pending */
+        if (q) (*env)->ReleaseIntArrayElements(env, query, q, JNI_ABORT);
+        if (ll) (*env)->ReleaseDoubleArrayElements(env, outLogl, ll, JNI_ABORT);
+        return;
+    }
+    rc = bnk_joint_marginal((bnk_ws *)(intptr_t)ws, nCols, o, p, st, (const int32_t *)q, nq, post, ll);
+    if (ll) (*env)->ReleaseDoubleArrayElements(env, outLogl, ll, rc == BNK_OK ? 0 : JNI_ABORT);
+    if (q) (*env)->ReleaseIntArrayElements(env, query, q, JNI_ABORT);
+    if (rc != BNK_OK) raise(env, rc);
+}
+
 JNIEXPORT jdouble JNICALL Java_asr_NativeInference_logLik(JNIEnv *env, jclass c, jlong ws, jint nCols, jobject obs, jobject present,
                                                           jdoubleArray outLogl)
 {

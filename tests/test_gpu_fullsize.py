@@ -180,6 +180,12 @@ def test_host_pipeline_equals_single_shot(bnk, oracle):
         assert np.array_equal(np.nan_to_num(p1), np.nan_to_num(p2)) and np.array_equal(l1, l2)
     wpost, wlogl = oracle.fast_marginal(om, parent, dist, obs, present, rates, nthreads=8)
     assert max_rel_err(p2, wpost[q]) <= TOL and max_rel_err(l2, wlogl) <= TOL
+    # both passes in one host-buffer call (bnk_joint_marginal): pipelined and single-shot, against the separate calls
+    for w_ in (one, piped):
+        sb, pb, lb = w_.joint_marginal(obs, present, query=q)
+        assert np.array_equal(sb, s1)
+        assert np.array_equal(np.isnan(pb), np.isnan(p1)) and np.array_equal(np.nan_to_num(pb), np.nan_to_num(p1))
+        assert np.array_equal(lb, l1)
     ll1, t1 = one.loglik(obs, present)
     ll2, t2 = piped.loglik(obs, present)
     assert np.array_equal(ll1, ll2) and np.isclose(t1, t2, rtol=1e-13)
