@@ -5,7 +5,7 @@
 // (SubstNode.java:87 -> SubstModel.getProbs, src/bn/ctmc/SubstModel.java:303-327: 20 exp +
 // 8,000 multiply-adds) and then takes 400 logs per internal node per column
 // (SubstNode.java:498-518).  Only (#branches x #distinct rates) matrices exist, so they are
-// built here once: one CTA per (node, category), one thread per matrix entry.
+// built here once: one thread per matrix entry, a CTA per group of tables.
 //
 // Bit-level contract (what makes joint reconstruction reproducible against the oracle):
 //   iexp[k][j] = ievec[k][j] * exp(t * eval[k])
@@ -19,36 +19,75 @@
 
 namespace bnk {
 
-// grid = (n_nodes, n_cat); block = K*K threads (rounded up to a warp multiple).
-// times[node] * rates[cat] is the branch time (PhyloBN.java:158).  Nodes with skip[node] < 0
-// (tree roots: no branch above them) are left untouched.
-template <int K>
+// One CTA builds TPB consecutive tables (table index = cat * n_nodes + node, the layout's own order); one thread per
+// matrix entry.  r1 had one CTA per table: 20 of its 416 threads computed the exponentials while the rest waited, every
+// k step re-read evec through the load pipe, and the transposed copies left as 8-byte stores 160 bytes apart.  Here the
+// TPB x K exponentials are computed side by side, a thread keeps its row of evec in registers across the tables, and the
+// transposed copies are staged in shared memory (rows padded to K + 1: conflict-free both ways) and leave coalesced.
+// The arithmetic per entry -- and with it every bit of P and L -- is what it was.
+template <int K, int TPB>
 __global__ void __launch_bounds__(((K * K + 31) / 32) * 32)
 build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t *__restrict__ skip,
-                    const double *__restrict__ rates, int n_nodes, TableSet ts)
+                    const double *__restrict__ rates, int n_nodes, int n_tables, TableSet ts)
 {
-    __shared__ double iexp[K * K];
-    __shared__ double ek[K];
-    const int node = blockIdx.x, cat = blockIdx.y, tid = threadIdx.x;
-    if (skip != nullptr && skip[node] < 0) return;
-    const double t = times[node] * rates[cat];
-    if (tid < K) ek[tid] = fd_exp(t * md.eval[tid]);
+    constexpr int KK = K * K, PAD = K + 1;
+    static_assert(TPB * K <= ((KK + 31) / 32) * 32, "one thread per exponential");
+    __shared__ double ek[TPB][K];
+    __shared__ double iexp[TPB][KK];
+    __shared__ double sp[TPB][K * PAD], sl[TPB][K * PAD];
+    __shared__ long long s_base[TPB];  // first entry of the table, -1: nothing to build
+    const int tid = threadIdx.x, t0 = blockIdx.x * TPB;
+    if (tid < TPB * K) {
+        const int m = tid / K, k = tid % K, T = t0 + m;
+        bool live = T < n_tables;
+        if (live) {
+            const int node = T % n_nodes, cat = T / n_nodes;
+            live = skip == nullptr || skip[node] >= 0;
+            if (live) ek[m][k] = fd_exp(times[node] * rates[cat] * md.eval[k]);
+        }
+        if (k == 0) s_base[m] = live ? (long long)T * KK : -1;
+    }
     __syncthreads();
-    if (tid < K * K) iexp[tid] = md.ievec[tid] * ek[tid / K];
-    __syncthreads();
-    if (tid >= K * K) return;
-    const int i = tid / K, j = tid % K;
-    double temp = 0.0;
+    const bool entry = tid < KK;
+    const int i = entry ? tid / K : 0, j = entry ? tid % K : 0;
+    if (entry) {
+        const double iv = md.ievec[tid];
 #pragma unroll
-    for (int k = 0; k < K; k++) temp += md.evec[i * K + k] * iexp[k * K + j];
-    const double p = fabs(temp);
-    const size_t base = ((size_t)cat * n_nodes + node) * (K * K);
-    if (ts.P) ts.P[base + i * K + j] = p;
-    if (ts.PT) ts.PT[base + j * K + i] = p;
-    if (ts.L || ts.LT) {
-        const double l = fd_log(p);
-        if (ts.L) ts.L[base + i * K + j] = l;
-        if (ts.LT) ts.LT[base + j * K + i] = l;
+        for (int m = 0; m < TPB; m++) iexp[m][tid] = iv * ek[m][i];  // iexp[k][j] = ievec[k][j] * exp(t eval[k]): here k = i
+    }
+    __syncthreads();
+    const bool want_log = ts.L || ts.LT;
+    if (entry) {
+        double ev[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) ev[k] = md.evec[i * K + k];
+#pragma unroll
+        for (int m = 0; m < TPB; m++) {
+            const long long base = s_base[m];
+            if (base < 0) continue;
+            double temp = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; k++) temp += ev[k] * iexp[m][k * K + j];
+            const double p = fabs(temp);
+            if (ts.P) ts.P[base + tid] = p;
+            sp[m][j * PAD + i] = p;
+            if (want_log) {
+                const double l = fd_log(p);
+                if (ts.L) ts.L[base + tid] = l;
+                sl[m][j * PAD + i] = l;
+            }
+        }
+    }
+    if (!ts.PT && !ts.LT) return;
+    __syncthreads();
+    if (entry) {  // entry tid of a transposed table is [i][j] of the table itself with i = tid / K: sp[.][i * PAD + j]
+#pragma unroll
+        for (int m = 0; m < TPB; m++) {
+            const long long base = s_base[m];
+            if (base < 0) continue;
+            if (ts.PT) ts.PT[base + tid] = sp[m][i * PAD + j];
+            if (ts.LT) ts.LT[base + tid] = sl[m][i * PAD + j];
+        }
     }
 }
 
@@ -61,9 +100,12 @@ __global__ void log_prior_kernel(const double *__restrict__ prior, double *__res
 void launch_build_tables(int K, const ModelDev &md, const double *times, const int32_t *skip,
                          const double *rates, int n_nodes, int n_cat, const TableSet &ts, cudaStream_t st)
 {
-    dim3 grid(n_nodes, n_cat);
-    if (K == 20) build_tables_kernel<20><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, ts);
-    else build_tables_kernel<4><<<grid, 32, 0, st>>>(md, times, skip, rates, n_nodes, ts);
+    constexpr int TPB = 4;
+    const long long n_tables = (long long)n_nodes * n_cat;
+    if (n_tables < 1) return;
+    const unsigned grid = (unsigned)((n_tables + TPB - 1) / TPB);
+    if (K == 20) build_tables_kernel<20, TPB><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
+    else build_tables_kernel<4, TPB><<<grid, 32, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
 }
 
 void launch_log_prior(const double *prior, double *logprior, int K, cudaStream_t st)

@@ -36,7 +36,7 @@ lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append("| `%s` | %d | %.3f | %.3f | %.3f |" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
 
-rr = None
+recs = []   # one dict per profiled launch: metric name -> (value, unit); every report carries its own unit row
 for rep in reps:
     if rep.suffix == ".csv":   # the raw page exported on the GPU box (tools/gpu_round.sh keeps these: the reports exceed gpurun's 64 MiB)
         raw = rep.read_text()
@@ -45,15 +45,8 @@ for rep in reps:
     part = list(csv.reader(raw.splitlines()))
     if len(part) < 3:
         continue
-    if rr is None:
-        rr = part
-    else:
-        pix = {x: i for i, x in enumerate(part[0])}
-        for r in part[2:]:
-            rr.append([r[pix[x]] if x in pix else "" for x in rr[0]])
-if rr is None:
-    rr = [[], []]
-h = rr[0]; ix = {x: i for i, x in enumerate(h)}
+    for r in part[2:]:
+        recs.append({x: (r[i], part[1][i]) for i, x in enumerate(part[0]) if i < len(r)})
 want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
@@ -62,20 +55,20 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("launch__registers_per_thread", "registers / thread"), ("launch__block_size", "block"), ("launch__grid_size", "grid"),
         ("smsp__inst_executed.sum", "warp instructions"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"), ("lts__t_bytes.sum", "L2 bytes")]
-stalls = [x for x in h if "issue_stalled" in x and x.endswith("_per_issue_active.ratio")]
 lines += ["", "## `ncu --set full --clock-control none --import-source on` (one launch each)", ""]
-for r in rr[2:]:
-    lines.append("### `%s`  grid %s" % (r[ix["Kernel Name"]], r[ix["launch__grid_size"]] if "launch__grid_size" in ix else "?"))
+for rec in recs:
+    lines.append("### `%s`  grid %s" % (rec["Kernel Name"][0], rec.get("launch__grid_size", ("?", ""))[0]))
     lines.append("")
     for key, name in want:
-        if key in ix:
-            lines.append("- %s: %s %s" % (name, r[ix[key]], rr[1][ix[key]]))
-    top = sorted([(float(r[ix[s]]), s.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""))
-                  for s in stalls if r[ix[s]]], reverse=True)[:6]
+        if key in rec:
+            lines.append("- %s: %s %s" % (name, rec[key][0], rec[key][1]))
+    stalls = [x for x in rec if "issue_stalled" in x and x.endswith("_per_issue_active.ratio")]
+    top = sorted([(float(rec[s][0]), s.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""))
+                  for s in stalls if rec[s][0]], reverse=True)[:6]
     lines.append("- warp stalls per issued instruction: " + ", ".join("%s %.2f" % (n, v) for v, n in top))
-    if "dram__bytes_read.sum" in ix:
+    if "dram__bytes_read.sum" in rec:
         def gb(key):
-            v = float(r[ix[key]]); u = rr[1][ix[key]]
+            v, u = float(rec[key][0]), rec[key][1]
             return v * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}.get(u, 1.0)
         lines.append("- DRAM traffic per launch: %.3f GB" % (gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")))
     lines.append("")
