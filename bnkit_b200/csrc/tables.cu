@@ -16,6 +16,7 @@
 // so with contraction off this kernel is bit-identical to any other faithful evaluation.
 #include "device_common.cuh"
 #include "fdlibm.cuh"
+#include <cstdlib>
 
 namespace bnk {
 
@@ -25,15 +26,20 @@ namespace bnk {
 // TPB x K exponentials are computed side by side, a thread keeps its row of evec in registers across the tables, and the
 // transposed copies are staged in shared memory (rows padded to K + 1: conflict-free both ways) and leave coalesced.
 // The arithmetic per entry -- and with it every bit of P and L -- is what it was.
-template <int K, int TPB>
+template <int K, int TPB, bool EXT>
 __global__ void __launch_bounds__(((K * K + 31) / 32) * 32)
 build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t *__restrict__ skip,
                     const double *__restrict__ rates, int n_nodes, int n_tables, TableSet ts)
 {
     constexpr int KK = K * K, PAD = K + 1;
+    // EXT: a row of iexp is stored cyclically extended to 32 doubles (entry x holds column x mod K), so that the 16
+    // lanes of a half-warp -- consecutive j, wrapping at K -- read 16 CONSECUTIVE doubles starting at their first
+    // lane's column: one wavefront per half-warp instead of two or three when the wrap folds banks onto each other
+    constexpr int ROW = EXT ? 32 : K;
+    static_assert(!EXT || (K % 4 == 0 && K + 12 <= ROW), "first column of a half-warp is a multiple of 4");
     static_assert(TPB * K <= ((KK + 31) / 32) * 32, "one thread per exponential");
     __shared__ double ek[TPB][K];
-    __shared__ double iexp[TPB][KK];
+    __shared__ double iexp[TPB][K * ROW];
     __shared__ double sp[TPB][K * PAD], sl[TPB][K * PAD];
     __shared__ long long s_base[TPB];  // first entry of the table, -1: nothing to build
     const int tid = threadIdx.x, t0 = blockIdx.x * TPB;
@@ -50,12 +56,20 @@ build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t
     __syncthreads();
     const bool entry = tid < KK;
     const int i = entry ? tid / K : 0, j = entry ? tid % K : 0;
-    if (entry) {
+    if (EXT) {
+        for (int idx = tid; idx < K * ROW; idx += blockDim.x) {
+            const int k = idx / ROW, x = idx % ROW;
+            const double iv = md.ievec[k * K + x % K];
+#pragma unroll
+            for (int m = 0; m < TPB; m++) iexp[m][idx] = iv * ek[m][k];
+        }
+    } else if (entry) {
         const double iv = md.ievec[tid];
 #pragma unroll
         for (int m = 0; m < TPB; m++) iexp[m][tid] = iv * ek[m][i];  // iexp[k][j] = ievec[k][j] * exp(t eval[k]): here k = i
     }
     __syncthreads();
+    const int jx = EXT ? ((tid & ~15) % K) + (tid & 15) : j;  // where this lane finds column j in a row
     const bool want_log = ts.L || ts.LT;
     if (entry) {
         double ev[K];
@@ -67,7 +81,7 @@ build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t
             if (base < 0) continue;
             double temp = 0.0;
 #pragma unroll
-            for (int k = 0; k < K; k++) temp += ev[k] * iexp[m][k * K + j];
+            for (int k = 0; k < K; k++) temp += ev[k] * iexp[m][k * ROW + jx];
             const double p = fabs(temp);
             if (ts.P) ts.P[base + tid] = p;
             sp[m][j * PAD + i] = p;
@@ -104,8 +118,10 @@ void launch_build_tables(int K, const ModelDev &md, const double *times, const i
     const long long n_tables = (long long)n_nodes * n_cat;
     if (n_tables < 1) return;
     const unsigned grid = (unsigned)((n_tables + TPB - 1) / TPB);
-    if (K == 20) build_tables_kernel<20, TPB><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
-    else build_tables_kernel<4, TPB><<<grid, 32, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
+    static const bool ext = [] { const char *e = std::getenv("BNK_TABLES_EXT"); return e && std::atoi(e) != 0; }();
+    if (K == 20 && ext) build_tables_kernel<20, TPB, true><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
+    else if (K == 20) build_tables_kernel<20, TPB, false><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
+    else build_tables_kernel<4, TPB, false><<<grid, 32, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
 }
 
 void launch_log_prior(const double *prior, double *logprior, int K, cudaStream_t st)

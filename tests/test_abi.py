@@ -26,6 +26,20 @@ def test_every_declared_symbol_is_exported(bnk):
     assert b"sm_100a" in L.bnk_version()
 
 
+def test_every_declared_symbol_is_documented_for_the_reference_side():
+    """INTEGRATION.md names the reference-side counterpart (or owner) of every entry point of the header, and the JNI
+    shim / Java class under integration/ bind nothing the header does not declare."""
+    hdr = open(os.path.join(ROOT, "include", "bnkgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bnk_[a-z_0-9]+)\s*\(", hdr))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert not sorted(s for s in declared if s not in doc)
+    shim = open(os.path.join(ROOT, "integration", "jni", "bnkgpu_jni.c")).read()
+    shim = re.sub(r"/\*.*?\*/", "", shim, flags=re.S)
+    called = set(re.findall(r"\b(bnk_[a-z_0-9]+)\s*\(", shim))
+    assert called and called <= declared, sorted(called - declared)
+
+
 def test_library_has_sm100a_code_only(bnk):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "bnkit_b200", "libbnkgpu.so")],
