@@ -16,7 +16,6 @@
 // so with contraction off this kernel is bit-identical to any other faithful evaluation.
 #include "device_common.cuh"
 #include "fdlibm.cuh"
-#include <cstdlib>
 
 namespace bnk {
 
@@ -75,20 +74,31 @@ build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t
         double ev[K];
 #pragma unroll
         for (int k = 0; k < K; k++) ev[k] = md.evec[i * K + k];
+        // the TPB tables side by side: TPB independent add chains and TPB independent logs per thread (a table that is
+        // not built -- past the end, a root -- is computed from whatever its slot holds and never stored)
+        double temp[TPB], lg[TPB];
+#pragma unroll
+        for (int m = 0; m < TPB; m++) temp[m] = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+            for (int m = 0; m < TPB; m++) temp[m] += ev[k] * iexp[m][k * ROW + jx];
+        }
+#pragma unroll
+        for (int m = 0; m < TPB; m++) temp[m] = fabs(temp[m]);
+        if (want_log) {
+#pragma unroll
+            for (int m = 0; m < TPB; m++) lg[m] = fd_log(temp[m]);
+        }
 #pragma unroll
         for (int m = 0; m < TPB; m++) {
             const long long base = s_base[m];
             if (base < 0) continue;
-            double temp = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; k++) temp += ev[k] * iexp[m][k * ROW + jx];
-            const double p = fabs(temp);
-            if (ts.P) ts.P[base + tid] = p;
-            sp[m][j * PAD + i] = p;
+            if (ts.P) ts.P[base + tid] = temp[m];
+            sp[m][j * PAD + i] = temp[m];
             if (want_log) {
-                const double l = fd_log(p);
-                if (ts.L) ts.L[base + tid] = l;
-                sl[m][j * PAD + i] = l;
+                if (ts.L) ts.L[base + tid] = lg[m];
+                sl[m][j * PAD + i] = lg[m];
             }
         }
     }
@@ -118,9 +128,7 @@ void launch_build_tables(int K, const ModelDev &md, const double *times, const i
     const long long n_tables = (long long)n_nodes * n_cat;
     if (n_tables < 1) return;
     const unsigned grid = (unsigned)((n_tables + TPB - 1) / TPB);
-    static const bool ext = [] { const char *e = std::getenv("BNK_TABLES_EXT"); return e && std::atoi(e) != 0; }();
-    if (K == 20 && ext) build_tables_kernel<20, TPB, true><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
-    else if (K == 20) build_tables_kernel<20, TPB, false><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
+    if (K == 20) build_tables_kernel<20, TPB, true><<<grid, 416, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
     else build_tables_kernel<4, TPB, false><<<grid, 32, 0, st>>>(md, times, skip, rates, n_nodes, (int)n_tables, ts);
 }
 
