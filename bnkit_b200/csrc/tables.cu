@@ -20,11 +20,12 @@
 namespace bnk {
 
 // One CTA builds TPB consecutive tables (table index = cat * n_nodes + node, the layout's own order); one thread per
-// matrix entry.  r1 had one CTA per table: 20 of its 416 threads computed the exponentials while the rest waited, every
-// k step re-read evec through the load pipe, and the transposed copies left as 8-byte stores 160 bytes apart.  Here the
-// TPB x K exponentials are computed side by side, a thread keeps its row of evec in registers across the tables, and the
-// transposed copies are staged in shared memory (rows padded to K + 1: conflict-free both ways) and leave coalesced.
-// The arithmetic per entry -- and with it every bit of P and L -- is what it was.
+// matrix entry.  r1 had one CTA per table: 20 of its 416 threads computed the exponentials while the rest waited, each
+// thread ran one 20-deep add chain and one log at a time, and the transposed copies left as 8-byte stores 160 bytes
+// apart.  Here the TPB x K exponentials are computed side by side, a thread carries the TPB tables' entries together
+// (TPB independent add chains, evec read once per k for all of them), and the transposed copies are staged in shared
+// memory (rows padded to K + 1: conflict-free both ways) and leave coalesced.  The arithmetic per entry -- and with it
+// every bit of P and L -- is what it was.  (profiles/r2_w2_*, r2_w3_*: 0.537 -> 0.484 -> 0.382 ms on C3a.)
 template <int K, int TPB, bool EXT>
 __global__ void __launch_bounds__(((K * K + 31) / 32) * 32)
 build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t *__restrict__ skip,
@@ -86,7 +87,7 @@ build_tables_kernel(ModelDev md, const double *__restrict__ times, const int32_t
         }
 #pragma unroll
         for (int m = 0; m < TPB; m++) temp[m] = fabs(temp[m]);
-        if (want_log) {
+        if (want_log) {   // (a lockstep form of the TPB logs, stage by stage, cost registers and lost: 0.404 against 0.382 ms)
 #pragma unroll
             for (int m = 0; m < TPB; m++) lg[m] = fd_log(temp[m]);
         }
