@@ -267,6 +267,7 @@ __global__ void leaf_states_kernel(const TracebackArgs a)
     if (col >= a.ncols) return;
     const int gcat = a.cat_of_col[col];
     if (gcat < a.cat_lo || gcat >= a.cat_hi) return;
+#pragma unroll 4
     for (int li = blockIdx.y; li < a.n_leaves; li += gridDim.y) {
         const int u = a.leaf_nodes[li], par = a.leaf_parent[li];
         const size_t uc = (size_t)u * a.ncols + col;
@@ -295,7 +296,9 @@ __global__ void leaf_states_kernel(const TracebackArgs a)
 cudaError_t launch_leaf_states(const TracebackArgs &a, cudaStream_t st)
 {
     if (a.n_leaves == 0 || a.ncols == 0) return cudaSuccess;
-    dim3 grid((a.ncols + 255) / 256, a.n_leaves < 8192 ? a.n_leaves : 8192);
+    // a thread keeps its column and walks a slice of the leaves (8,192 slices were 160,000 CTAs of one or two bytes per
+    // thread at C3: 0.18 ms for 50 MB)
+    dim3 grid((a.ncols + 255) / 256, a.n_leaves < 256 ? a.n_leaves : 256);
     leaf_states_kernel<<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
