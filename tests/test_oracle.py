@@ -92,6 +92,32 @@ def test_joint_equals_bruteforce_jc(oracle):
                 assert np.isclose(bb["total_p"], b["best_p"], rtol=1e-12)
 
 
+def test_reference_known_answers_infer1_infer1b(oracle):
+    """The states the reference's own tests assert, MaxLhoodJointTest.infer1 / infer1b
+    (test/asr/MaxLhoodJointTest.java:42-46, 148-191).  Nodes in IdxTree (depth-first) order; A = 0, C = 1."""
+    A, Cc = 0, 1
+    # infer1: ((Leaf1:0.02,Leaf2:0.12)Anc_left:0.19,(Leaf3:0.18,Leaf4:0.15)Anc_right:0.191)Root under JC, Leaf1 = A, Leaf3 = C
+    parent = np.array([-1, 0, 1, 1, 0, 4, 4], dtype=np.int32)
+    dist = np.array([0.0, 0.19, 0.02, 0.12, 0.191, 0.18, 0.15])
+    obs = np.array([NONE, NONE, A, NONE, NONE, Cc, NONE], dtype=np.uint8)
+    st = oracle.fast_joint(oracle.Model("JC"), parent, dist, obs[:, None])[:, 0]
+    assert (st[2], st[1], st[4], st[0]) == (A, A, Cc, A)   # Leaf1, ancestor 1 (Anc_left), ancestor 2 (Anc_right), root
+    # infer1b: JC over the two-letter alphabet {A, C} (JC.java:44-60: q = gamma / n off the diagonal, uniform F);
+    # mini1 = ((Leaf1:0.09,Leaf2:0.11)N1:0.07,Leaf3:0.12)N0, mini2 = ((Leaf1:0.03,Leaf2:0.05)N1:0.13,Leaf3:0.12)N0,
+    # Leaf1 = A, Leaf3 = C: the root follows Leaf1 in mini1 and Leaf3 in mini2, N1 is A in both
+    Q = np.array([[0.0, 0.5], [0.5, 0.0]])
+    jc2 = oracle.Model(custom=(2, [0.5, 0.5], Q, False, False))
+    par = np.array([-1, 0, 1, 1, 0], dtype=np.int32)
+    ob = np.array([NONE, NONE, A, NONE, Cc], dtype=np.uint8)
+    s1 = oracle.fast_joint(jc2, par, np.array([0.0, 0.07, 0.09, 0.11, 0.12]), ob[:, None])[:, 0]
+    s2 = oracle.fast_joint(jc2, par, np.array([0.0, 0.13, 0.03, 0.05, 0.12]), ob[:, None])[:, 0]
+    assert (s1[0], s1[1]) == (A, A) and (s2[0], s2[1]) == (Cc, A)
+    # the brute-force enumerator agrees on all of it
+    for d_ in ([0.0, 0.07, 0.09, 0.11, 0.12], [0.0, 0.13, 0.03, 0.05, 0.12]):
+        b = oracle.brute(jc2, par, np.array(d_), ob, want_post=False)
+        assert np.array_equal(b["state"], oracle.fast_joint(jc2, par, np.array(d_), ob[:, None])[:, 0])
+
+
 def test_joint_with_internal_evidence_wag(oracle):
     """MaxLhoodJointTest.infer0 (:55-147): 7-node tree, 3 randomly instantiated nodes incl. internal ones."""
     m = oracle.Model("WAG")
