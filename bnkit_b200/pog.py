@@ -151,6 +151,30 @@ class POGraph:
     def getEdge(self, a, b):
         return self.edges.get((a, b))
 
+    def isPath(self, a, b):
+        """POGraph.isPath (src/dat/pog/POGraph.java:314-328): a path from a (-1 = start terminal) to b (n = end
+        terminal); a node has a path to itself.  The reference recurses forward; this walks the same edges with a stack."""
+        if a == b:
+            return True
+        if a != -1 and a not in self.nodes:
+            return False
+        if b != self.n and b not in self.nodes:
+            return False
+        seen, stack = set(), [a]
+        while stack:
+            v = stack.pop()
+            if v == b or (b == self.n and v in self.ends):
+                return True
+            if v in seen:
+                continue
+            seen.add(v)
+            stack.extend(self.getForward(v))
+        return False
+
+    def isContiguous(self):
+        """POGraph.isContiguous (:334-336)"""
+        return self.isPath(-1, self.n)
+
     def getIndices(self):
         return sorted(self.nodes)
 

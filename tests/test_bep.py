@@ -92,6 +92,42 @@ def _bitset_parsimony(children, inst, recode_null):
     return out
 
 
+def test_parsimony_known_answers_of_the_reference_tests():
+    """asr.Parsimony's all-optimal sets on the hand-checked cases of ParsimonyTests.testParsimony2 / testParsimony3
+    (test/dat/phylo/ParsimonyTests.java:29-30, 93-186; `infer(ti, false)`: no NULL recoding) -- through the restatement
+    and through the bit-set form the device sweeps use."""
+    from bnkit_b200 import phylo
+    from oracle import bep
+    t = phylo.IdxTree.fromNewick("((((x01,x02)X01_02,x03)X01_03,(x04,((x05,x06)X05_06,(x07,x08)X07_08)X05_08)X04_08)X01_08,"
+                                 "(x09,(x10,x11)X10_11)X09_11)X01_11;")
+    n = t.getSize()
+    children = [list(t.getChildren(i)) for i in range(n)]
+    is_leaf = [not c for c in children]
+    names = ["x%02d" % i for i in range(1, 12)]
+    a, b, c, d, e, f, g = "ABCDEFG"
+
+    def optimal(values, leaves=names):
+        inst = [None] * n
+        for name, v in zip(leaves, values):
+            inst[t.labels.index(name)] = v
+        ref = bep.parsimony(children, inst, is_leaf, False)
+        bits = _bitset_parsimony(children, inst, False)
+        for v in range(n):
+            if children[v]:
+                assert sorted(ref[v] or []) == bits[v]
+        return {lab: set(ref[t.labels.index(lab)]) for lab in ("X01_03", "X04_08")}
+    o = optimal([a, a, c, d, b, b, b, b, e, f, g])                 # init1: every symbol optimal at both nodes
+    assert o["X01_03"] == set("ABCDEFG") and o["X04_08"] == set("ABCDEFG")
+    o = optimal([a, a, c, d, b, b, b, b, e, b, a])                 # init2
+    assert {a, b, c} <= o["X01_03"] and d not in o["X01_03"]
+    assert {a, b, d} <= o["X04_08"] and c not in o["X04_08"]
+    o = optimal([a, a, c, d, b, b, b, b, e, b, f])                 # init3
+    assert {a, b, c} <= o["X01_03"]
+    assert b in o["X04_08"] and not ({a, c, d} & o["X04_08"])
+    o = optimal([a, b, c], names[:3])                              # testParsimony3: the other eight leaves uninstantiated
+    assert {a, b, c} <= o["X01_03"]
+
+
 def test_bitset_formulation_equals_sankoff_tables():
     """Unit costs collapse asr.Parsimony's score tables and traceback lists to two bit sets per node."""
     from oracle import bep

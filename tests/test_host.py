@@ -125,3 +125,27 @@ def test_ancestor_numbers_follow_the_reference_rules():
         IdxTree.fromNewick("((a:1,b:1)N1:1,(c:1,d:1)N1:1);")
     with pytest.raises(RuntimeError):
         IdxTree.fromNewick("((a:1,b:1)Nx:1,c:1);")
+
+
+@pytest.mark.parametrize("fixture, model_name", [("c1_66.json", "LG"), ("c2_3_2_1_1_filt.json", "JTT")])
+def test_node_instances_follow_the_alignment_occupancy(bnk, fixture, model_name):
+    """POGTreeTest.getNodeInstance (test/dat/pog/POGTreeTest.java:44-53): per column, the nodes that carry an instance
+    are exactly the extants with a residue there -- what the `obs` matrix of the C ABI holds (row a4 of SURVEY 8), and
+    the residues are the alignment's own in the model's alphabet order (SubstNodeTest's P(sym | sym) indexing)."""
+    from bnkit_b200.phylo import IdxTree, Prediction, SubstModel
+    with open(os.path.join(os.path.dirname(__file__), "golden", fixture)) as fh:
+        d = json.load(fh)
+    tree = IdxTree.fromJSON(d["tree"])
+    n_cols = len(d["seqs"][0])
+    states = [[None] * n_cols for _ in range(tree.getSize())]
+    for name, seq in zip(d["names"], d["seqs"]):
+        states[tree.getIndex(name)] = [None if ch == "-" else ch for ch in seq]
+    model = SubstModel.createModel(model_name)
+    obs = Prediction(tree, states)._obs(model)
+    occupancy = np.array([sum(seq[c] != "-" for seq in d["seqs"]) for c in range(n_cols)])
+    assert np.array_equal((obs != 255).sum(axis=0), occupancy)
+    assert not (obs[[v for v in range(tree.getSize()) if not tree.isLeaf(v)]] != 255).any()   # GRASP instantiates extants only
+    dom = list(model.domain)
+    for name, seq in zip(d["names"], d["seqs"]):
+        row = obs[tree.getIndex(name)]
+        assert all((row[c] == 255) if ch == "-" else (dom[row[c]] == ch) for c, ch in enumerate(seq))

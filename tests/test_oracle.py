@@ -92,6 +92,26 @@ def test_joint_equals_bruteforce_jc(oracle):
                 assert np.isclose(bb["total_p"], b["best_p"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["JTT", "LG", "WAG", "Dayhoff", "JC", "Yang"])
+def test_conditional_tables_behave_as_substnodetest_demands(oracle, name):
+    """What SubstNodeTest.getBarebone asserts of every SubstNode along a 200-node chain under JTT
+    (test/bn/ctmc/SubstNodeTest.java:47-125): P(sym | sym) falls as the branch grows, every entry is a probability,
+    every row sums to 1 within 1 % -- here for all six models (no row renormalisation: SubstModel.java:303-327)."""
+    m = oracle.Model(name)
+    rng = np.random.default_rng(200)
+    ts = np.sort(np.concatenate([rng.uniform(1e-5, 0.05, 40), rng.uniform(0.05, 5.0, 40)]))
+    prev = np.ones(m.K)
+    for t in ts:
+        P = m.probs(float(t))
+        assert (P >= 0.0).all() and (P <= 1.0).all()
+        assert (np.abs(P.sum(axis=1) - 1.0) < 0.01).all()
+        d = np.diag(P)
+        assert (d <= prev).all()
+        prev = d
+    prior = m.parts()["prior"]
+    assert np.isclose(prior.sum(), 1.0, atol=1e-12) and (prior > 0).all()      # the root's table: F / sum F
+
+
 def test_reference_known_answers_infer1_infer1b(oracle):
     """The states the reference's own tests assert, MaxLhoodJointTest.infer1 / infer1b
     (test/asr/MaxLhoodJointTest.java:42-46, 148-191).  Nodes in IdxTree (depth-first) order; A = 0, C = 1."""

@@ -101,6 +101,62 @@ def _all_paths(g):
     return out
 
 
+def _pograph_test_graph():
+    """POGraphTest.setupPOG (test/dat/pog/POGraphTest.java:26-79): 30 nodes, chains of step 2, 7 and 9 from the start."""
+    from bnkit_b200 import pog
+    N = 30
+    g = pog.POGraph(N)
+    for i in range(N):
+        g.addNode(i)
+    touched = set()
+    for step in (2, 7, 9):
+        last, frm = -1, -1
+        while frm < N - 10:
+            to = min(frm + step, N)
+            g.addEdge(frm, to)
+            touched.add(to)
+            last = to
+            frm += step
+        if last < N:
+            g.addEdge(last, N)
+    return g, touched, N
+
+
+def test_pograph_primitives_against_the_reference_test_values():
+    """The numbers POGraphTest asserts (:165-243, :288-297): three hops on the shortest way in either direction (an edge
+    to the end terminal marks an end node, it is not a forward edge), every chained node visited, isPath."""
+    from oracle import bep
+    g, touched, N = _pograph_test_graph()
+
+    def hops(idx, nrounds, nxt):
+        n = nxt(idx)
+        return nrounds if not n else min(hops(v, nrounds + 1, nxt) for v in n)
+
+    def visit(idx, nxt, acc):
+        for v in nxt(idx):
+            if v not in acc:
+                acc.add(v)
+                visit(v, nxt, acc)
+        return acc
+    assert hops(-1, 0, g.getForward) == 3 and hops(N, 0, g.getBackward) == 3
+    assert visit(-1, g.getForward, set()) >= touched - {N} and visit(N, g.getBackward, set()) >= touched - {N}
+    assert g.isPath(6, 19) and g.isPath(7, 26) and g.isPath(7, 7) and g.isPath(-1, N)
+    assert not g.isPath(8, 20) and not g.isPath(19, 26) and not g.isPath(26, 7) and not g.isPath(0, N)
+    assert g.isContiguous()
+    # the BEP restatement's graph answers the same questions the same way
+    o = bep.POG(N)
+    for i in range(N):
+        o.add_node(i)
+    for a in [-1] + list(range(N)):
+        for b in g.getForward(a):
+            o.add_edge(a, b)
+    for a in g.getEnds():
+        o.add_edge(a, N)
+    assert o.is_contiguous()
+    o.remove_node(20); o.remove_node(21); o.remove_node(26)   # all three ends gone: no way through
+    assert not o.is_contiguous()
+
+
 def test_most_supported_path_is_a_cheapest_path():
     """POGraph.getMostSupported = DijkstraSearch(-1 -> N) (src/dat/pog/GraphSearch.java:105-206): on random terminated
     DAGs the returned path is a start-to-end path whose cost equals the minimum over all paths (enumerated)."""
