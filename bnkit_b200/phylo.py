@@ -51,6 +51,34 @@ class EnumDistrib:
     def getMax(self):
         return self.domain[self.getMaxIndex()]
 
+    _PREDEF = {"DNA": "ACGT", "RNA": "ACGU", "DNA with N": "ACGTN", "RNA with N": "ACGUN", "Protein": "ACDEFGHIKLMNPQRSTVWY",
+               "Protein with X": "ACDEFGHIKLMNPQRSTVWYX", "Protein with gap": "ACDEFGHIKLMNPQRSTVWY-"}
+
+    def toJSON(self):
+        """EnumDistrib.toJSON (src/bn/prob/EnumDistrib.java:165-170) with Enumerable.toJSON (src/dat/Enumerable.java:271-283):
+        a predefined domain goes by name, any other one by its values"""
+        dom = "".join(self.domain) if all(isinstance(c, str) and len(c) == 1 for c in self.domain) else None
+        name = next((k for k, v in self._PREDEF.items() if v == dom), None)
+        domain = {"Predef": name} if name else {"Size": len(self.domain), "Values": list(self.domain),
+                                                "Datatype": "Character" if dom is not None else "Object"}
+        return {"Domain": domain, "Pr": [float(p) for p in self.distrib]}
+
+    @staticmethod
+    def fromJSON(obj, domain=None):
+        """EnumDistrib.fromJSON (:180-193)"""
+        if domain is None:
+            d = obj["Domain"]
+            if d.get("Predef") is not None:
+                if d["Predef"] not in EnumDistrib._PREDEF:
+                    raise ASRRuntimeException("Invalid predefined domain name: \"%s\"" % d["Predef"])
+                domain = list(EnumDistrib._PREDEF[d["Predef"]])
+            else:
+                domain = list(d["Values"])
+        pr = [float(x) for x in obj["Pr"]]
+        if len(pr) != len(domain):
+            raise ASRRuntimeException("EnumDistrib: %d probabilities for a domain of %d" % (len(pr), len(domain)))
+        return EnumDistrib(domain, pr)
+
     def __repr__(self):
         return "<" + " ".join("%s:%.3f" % (s, p) for s, p in zip(self.domain, self.distrib)) + ">"
 
@@ -344,6 +372,36 @@ class TreeInstance:
 
     def getSize(self):
         return len(self.instance)
+
+    def getTree(self):
+        return self.tree
+
+    def _possible(self):
+        out = []
+        for v in self.instance:          # the reference collects them in a HashSet (TreeInstance.java:46-58): any order
+            if v is not None and v not in out:
+                out.append(v)
+        return out
+
+    def encode(self, recodeNullAtLeaves=True):
+        """TreeInstance.encode (src/dat/phylo/TreeInstance.java:141-165): values become 0 .. k - 1, a null at a leaf
+        becomes k when recodeNullAtLeaves; returns the key decode() takes.  In place, as in the reference."""
+        possible = self._possible()
+        key = list(possible) + ([None] if recodeNullAtLeaves else [])
+        for i, v in enumerate(self.instance):
+            if v is not None:
+                self.instance[i] = possible.index(v)
+            elif recodeNullAtLeaves and self.tree.isLeaf(i):
+                self.instance[i] = len(possible)
+        return key
+
+    def decode(self, key):
+        """TreeInstance.decode (:191-206): back to the symbols of the key (the null symbol back to None)"""
+        if len(key) < 1:
+            return
+        for i, v in enumerate(self.instance):
+            if v is not None:
+                self.instance[i] = key[int(v)]
 
 
 def _encode(values, domain):

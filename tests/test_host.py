@@ -149,3 +149,46 @@ def test_node_instances_follow_the_alignment_occupancy(bnk, fixture, model_name)
     for name, seq in zip(d["names"], d["seqs"]):
         row = obs[tree.getIndex(name)]
         assert all((row[c] == 255) if ch == "-" else (dom[row[c]] == ch) for c, ch in enumerate(seq))
+
+
+def test_tree_instance_encode_decode_as_the_reference_test():
+    """TreeInstanceTest.encode1 / encode2 / decode1 / decode2 (test/dat/phylo/TreeInstanceTest.java:40-150): seven
+    leaves carry 11, 11, 22, 11, 33, 33, 33; encoding renumbers them, gives null leaves the extra symbol only when asked
+    to, never touches ancestors; decoding with the key restores every assigned value."""
+    from bnkit_b200.phylo import IdxTree, TreeInstance
+    with open(os.path.join(os.path.dirname(__file__), "golden", "c1_66.json")) as fh:
+        tree = IdxTree.fromJSON(json.load(fh)["tree"])
+    leaves = [i for i in range(tree.getSize()) if tree.isLeaf(i)]
+    assign = dict(zip(leaves[:7], [11, 11, 22, 11, 33, 33, 33]))
+    unique = len(set(assign.values()))
+    for recode in (True, False):
+        ti = TreeInstance(tree, dict(assign))
+        assert all(ti.getInstance(i) == v for i, v in assign.items())
+        key = ti.encode(recode)
+        assert len(key) == unique + (1 if recode else 0) and (key[-1] is None) == recode
+        for i in range(tree.getSize()):
+            if i in assign:
+                assert ti.getInstance(i) != assign[i] and key[ti.getInstance(i)] == assign[i]
+            elif ti.getInstance(i) is not None:           # newly assigned: a leaf, the symbol after the last value
+                assert recode and tree.isLeaf(i) and ti.getInstance(i) == unique
+        n_null_leaves = sum(tree.isLeaf(i) and ti.getInstance(i) is None for i in range(tree.getSize()))
+        assert n_null_leaves == (0 if recode else len(leaves) - 7)
+        ti.decode(key)
+        assert all(ti.getInstance(i) == v for i, v in assign.items())
+        assert sum(tree.isLeaf(i) and ti.getInstance(i) is None for i in range(tree.getSize())) == len(leaves) - 7
+
+
+def test_enum_distrib_json_roundtrip():
+    """EnumDistribTest.toJSON (test/bn/prob/EnumDistribTest.java:10-15): toJSON -> fromJSON -> toJSON is the identity;
+    predefined domains travel by name (Enumerable.java:248-283)."""
+    from bnkit_b200.phylo import ASRRuntimeException, EnumDistrib
+    rng = np.random.default_rng(1)
+    for dom in ("ACGT", "ACDEFGHIKLMNPQRSTVWY", "ARNDCQEGHILKMFPSTWYV", "AC"):
+        p = rng.random(len(dom))
+        d = EnumDistrib(list(dom), p / p.sum())
+        j = d.toJSON()
+        assert ("Predef" in j["Domain"]) == (dom in ("ACGT", "ACDEFGHIKLMNPQRSTVWY"))
+        r = EnumDistrib.fromJSON(json.loads(json.dumps(j)))
+        assert json.dumps(r.toJSON()) == json.dumps(j) and r.domain == list(dom) and np.array_equal(r.distrib, d.distrib)
+    with pytest.raises(ASRRuntimeException):
+        EnumDistrib.fromJSON({"Domain": {"Predef": "Klingon"}, "Pr": [1.0]})
